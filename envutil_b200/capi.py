@@ -1,0 +1,125 @@
+"""ctypes view of the C ABI declared in include/envutil_b200.h.
+
+This is plumbing for the Python tests, the bench and the smoke test: it loads the in-tree
+shared library built by __graft_entry__.build() and mirrors the POD structs field for field.
+There is no fallback: if the library is missing, loading raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libenvutil_b200.so")
+
+# eu_projection_t (reference envutil_basic.h:99-109)
+SPHERICAL, CYLINDRICAL, RECTILINEAR, STEREOGRAPHIC, FISHEYE, CUBEMAP, BIATAN6, PRJ_NONE = range(8)
+PROJECTION_NAMES = ["spherical", "cylindrical", "rectilinear", "stereographic", "fisheye", "cubemap", "biatan6"]
+SYN_PANORAMA, SYN_HDR_MERGE = 0, 1
+EU_OK = 0
+
+
+class Facet(C.Structure):
+    _fields_ = [
+        ("projection", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("nchannels", C.c_int32),
+        ("hfov", C.c_double), ("yaw", C.c_double), ("pitch", C.c_double), ("roll", C.c_double),
+        ("tr_x", C.c_double), ("tr_y", C.c_double), ("tr_z", C.c_double),
+        ("tp_y", C.c_double), ("tp_p", C.c_double), ("tp_r", C.c_double),
+        ("shear_g", C.c_double), ("shear_t", C.c_double),
+        ("a", C.c_double), ("b", C.c_double), ("c", C.c_double),
+        ("h", C.c_double), ("v", C.c_double), ("brighten", C.c_double),
+        ("x0", C.c_double), ("x1", C.c_double), ("y0", C.c_double), ("y1", C.c_double),
+        ("step", C.c_double),
+        ("s", C.c_double), ("d", C.c_double), ("r_max", C.c_double), ("cap_radius", C.c_double),
+        ("has_shift", C.c_int32), ("has_lcp", C.c_int32), ("has_shear", C.c_int32),
+        ("has_2d_tf", C.c_int32), ("has_translation", C.c_int32),
+        ("window_width", C.c_int32), ("window_height", C.c_int32),
+        ("window_x_offset", C.c_int32), ("window_y_offset", C.c_int32),
+    ]
+
+
+class Target(C.Structure):
+    _fields_ = [
+        ("projection", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("nchannels", C.c_int32),
+        ("hfov", C.c_double), ("yaw", C.c_double), ("pitch", C.c_double), ("roll", C.c_double),
+        ("x0", C.c_double), ("x1", C.c_double), ("y0", C.c_double), ("y1", C.c_double),
+        ("step", C.c_double),
+    ]
+
+
+class Opts(C.Structure):
+    _fields_ = [
+        ("spline_degree", C.c_int32), ("prefilter_degree", C.c_int32), ("synopsis", C.c_int32),
+        ("solo", C.c_int32), ("support_min", C.c_int32), ("tile_size", C.c_int32),
+        ("reserved", C.c_int32 * 2),
+    ]
+
+
+class Tap(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("w", C.c_float)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("render_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("launches", C.c_int32), ("reserved", C.c_int32)]
+
+
+SourceH = C.c_void_p
+_FP = C.POINTER(C.c_float)
+
+# every symbol include/envutil_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "eu_get_vfov": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_double]),
+    "eu_get_step": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_double]),
+    "eu_get_extent": (None, [C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double)]),
+    "eu_facet_prepare": (C.c_int, [C.POINTER(Facet)]),
+    "eu_target_prepare": (C.c_int, [C.POINTER(Target)]),
+    "eu_rotation_matrix": (None, [C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double)]),
+    "eu_facet_basis": (None, [C.POINTER(Target), C.POINTER(Facet), C.POINTER(C.c_double)]),
+    "eu_make_spread": (C.c_int, [C.POINTER(Target), C.c_int, C.POINTER(Facet), C.c_int, C.c_double, C.c_double,
+                                 C.c_double, C.c_double, C.c_int, C.POINTER(Tap), C.c_int, C.POINTER(C.c_int)]),
+    "eu_cubemap_metrics": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_double)]),
+    "eu_init": (C.c_int, [C.c_int]),
+    "eu_shutdown": (None, []),
+    "eu_last_error": (C.c_char_p, []),
+    "eu_device_count": (C.c_int, []),
+    "eu_source_upload": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p,
+                                   C.POINTER(SourceH), C.POINTER(Timing)]),
+    "eu_source_upload_device": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p, C.c_void_p,
+                                          C.POINTER(SourceH), C.POINTER(Timing)]),
+    "eu_source_find": (SourceH, [C.c_char_p]),
+    "eu_source_release": (C.c_int, [SourceH]),
+    "eu_cycle": (C.c_int, []),
+    "eu_source_container_floats": (C.c_size_t, [SourceH, C.POINTER(C.c_int32)]),
+    "eu_source_download": (C.c_int, [SourceH, C.c_void_p]),
+    "eu_render": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet), C.POINTER(SourceH),
+                            C.POINTER(Tap), C.c_int, C.c_void_p, C.POINTER(Timing)]),
+    "eu_render_rows": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
+                                 C.POINTER(SourceH), C.POINTER(Tap), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.POINTER(Timing)]),
+    "eu_debug_planes": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
+                                  C.POINTER(SourceH), C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libenvutil_b200.so (built in-tree). Raises if it is missing or a symbol is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, lib=None):
+    if rc != EU_OK:
+        lib = lib or load()
+        raise RuntimeError(f"envutil_b200: status {rc}: {lib.eu_last_error().decode()}")

@@ -1,0 +1,134 @@
+"""Job description shared by the Python host API, the tests and the bench.
+
+A Job is what envutil's command line describes (reference envutil_main.cc:190-372): a set of
+facets (source images with projection, field of view and orientation), a target projection and
+size, and the interpolation / twining / synopsis options. `cli_args()` spells the job for the
+reference binary, `structs()` marshals it into the POD structs of include/envutil_b200.h using
+the library's own host-side set-up functions.
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import capi
+
+
+@dataclass
+class FacetSpec:
+    image: Optional[np.ndarray]  # H x W x C float32 (may be None when only geometry is needed)
+    projection: str
+    hfov: float  # degrees
+    yaw: float = 0.0
+    pitch: float = 0.0
+    roll: float = 0.0
+    brighten: float = 1.0
+    a: float = 0.0
+    b: float = 0.0
+    c: float = 0.0
+    d: float = 0.0  # PTO 'd' (horizontal shift, pixels)
+    e: float = 0.0  # PTO 'e' (vertical shift, pixels)
+    g: float = 0.0  # shear
+    t: float = 0.0
+    tr_x: float = 0.0
+    tr_y: float = 0.0
+    tr_z: float = 0.0
+    tp_y: float = 0.0
+    tp_p: float = 0.0
+    width: int = 0   # used when image is None
+    height: int = 0
+    nchannels: int = 3
+
+    def shape(self):
+        if self.image is not None:
+            h, w = self.image.shape[:2]
+            c = 1 if self.image.ndim == 2 else self.image.shape[2]
+            return w, h, c
+        return self.width, self.height, self.nchannels
+
+
+@dataclass
+class Job:
+    facets: List[FacetSpec]
+    projection: str
+    hfov: float  # degrees
+    width: int
+    height: int = 0
+    yaw: float = 0.0
+    pitch: float = 0.0
+    roll: float = 0.0
+    degree: int = 1
+    prefilter: int = -1
+    twine: int = 0
+    twine_width: float = 1.0
+    twine_density: float = 1.0
+    twine_sigma: float = 0.0
+    twine_threshold: float = 0.0
+    twine_max: int = 8
+    synopsis: str = "panorama"
+    solo: int = -1
+    support_min: int = 8
+    tile_size: int = 64
+    name: str = ""
+
+    # ---- reference command line (real spellings, envutil_main.cc:190-372) ----
+    def cli_args(self, facet_paths, output):
+        args = []
+        for f, p in zip(self.facets, facet_paths):
+            args += ["--facet", p, f.projection, repr(float(f.hfov)), repr(float(f.yaw)), repr(float(f.pitch)),
+                     repr(float(f.roll))]
+        args += ["--projection", self.projection, "--hfov", repr(float(self.hfov)), "--width", str(self.width)]
+        if self.height:
+            args += ["--height", str(self.height)]
+        args += ["--yaw", repr(float(self.yaw)), "--pitch", repr(float(self.pitch)), "--roll", repr(float(self.roll))]
+        args += ["--degree", str(self.degree), "--prefilter", str(self.prefilter), "--twine", str(self.twine)]
+        if self.twine != 0:
+            args += ["--twine_width", repr(float(self.twine_width)), "--twine_sigma", repr(float(self.twine_sigma)),
+                     "--twine_threshold", repr(float(self.twine_threshold))]
+        if self.synopsis != "panorama":
+            args += ["--synopsis", self.synopsis]
+        if self.solo >= 0:
+            args += ["--solo", str(self.solo)]
+        args += ["--output", output]
+        return args
+
+    # ---- POD structs of the C ABI ----
+    def structs(self, lib=None):
+        lib = lib or capi.load()
+        nch = self.facets[0].shape()[2]
+        t = capi.Target()
+        t.projection = capi.PROJECTION_NAMES.index(self.projection)
+        t.width, t.height, t.nchannels = self.width, self.height, nch
+        t.hfov = math.radians(self.hfov)
+        t.yaw, t.pitch, t.roll = (math.radians(v) for v in (self.yaw, self.pitch, self.roll))
+        capi.check(lib.eu_target_prepare(C.byref(t)), lib)
+        n = len(self.facets)
+        fa = (capi.Facet * n)()
+        for i, f in enumerate(self.facets):
+            w, h, c = f.shape()
+            s = fa[i]
+            s.projection = capi.PROJECTION_NAMES.index(f.projection)
+            s.width, s.height, s.nchannels = w, h, c
+            s.hfov = math.radians(f.hfov)
+            s.yaw, s.pitch, s.roll = (math.radians(v) for v in (f.yaw, f.pitch, f.roll))
+            s.tr_x, s.tr_y, s.tr_z = f.tr_x, f.tr_y, -f.tr_z  # TrZ is negated (envutil_main.cc:787-789)
+            s.tp_y, s.tp_p = math.radians(f.tp_y), math.radians(f.tp_p)
+            s.shear_g, s.shear_t = f.g, f.t
+            s.a, s.b, s.c, s.h, s.v = f.a, f.b, f.c, f.d, f.e
+            s.brighten = f.brighten
+            capi.check(lib.eu_facet_prepare(C.byref(s)), lib)
+        o = capi.Opts()
+        o.spline_degree = self.degree
+        o.prefilter_degree = self.prefilter
+        o.synopsis = capi.SYN_HDR_MERGE if self.synopsis == "hdr_merge" else capi.SYN_PANORAMA
+        o.solo = 0 if n == 1 else self.solo  # forced for a single facet (envutil_main.cc:996-997)
+        o.support_min, o.tile_size = self.support_min, self.tile_size
+        taps = (capi.Tap * 1024)()
+        tw = C.c_int(0)
+        ntaps = lib.eu_make_spread(C.byref(t), n, fa, self.twine, self.twine_width, self.twine_density,
+                                   self.twine_sigma, self.twine_threshold, self.twine_max, taps, 1024, C.byref(tw))
+        if ntaps < 0:
+            capi.check(ntaps, lib)
+        return t, fa, o, taps, ntaps

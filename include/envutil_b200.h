@@ -1,0 +1,197 @@
+/* envutil_b200.h - C ABI of the B200 back-end for envutil's per-pixel reprojection path.
+ *
+ * Drop-in boundary: the reference enters its hot path through
+ *     virtual int dispatch_base::payload(int nchannels, int ninputs, projection_t) const
+ * (reference envutil_dispatch.h:63-65, called from core(), envutil_main.cc:1720,1727), with
+ * the job description in the global `arguments args` (envutil_basic.h:633-705). This header
+ * is what a `cuda_dispatch : dispatch_base` adapter marshals `args` into (INTEGRATION.md
+ * shows the adapter). Plain C: pointers, sizes and POD structs only.
+ *
+ * All angles are radians (the reference converts degrees right after parsing,
+ * envutil_main.cc:948-951,1199-1202). Rasters are interleaved float32, row-major, top row
+ * first - the layout of the reference's zimt::array_t targets (envutil_payload.cc:539) and of
+ * the buffers it hands to OIIO (envutil_basic.h:760-775).
+ */
+#ifndef ENVUTIL_B200_H
+#define ENVUTIL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* projection_t, reference envutil_basic.h:99-109 (same numeric values) */
+typedef enum {
+  EU_SPHERICAL = 0,
+  EU_CYLINDRICAL = 1,
+  EU_RECTILINEAR = 2,
+  EU_STEREOGRAPHIC = 3,
+  EU_FISHEYE = 4,
+  EU_CUBEMAP = 5,
+  EU_BIATAN6 = 6,
+  EU_PRJ_NONE = 7
+} eu_projection_t;
+
+/* --synopsis, reference envutil_payload.cc:2302-2315 */
+typedef enum { EU_SYN_PANORAMA = 0, EU_SYN_HDR_MERGE = 1 } eu_synopsis_t;
+
+/* status codes (the reference asserts/exit(-1)s instead; the library never exits) */
+typedef enum {
+  EU_OK = 0,
+  EU_ERR_ARGUMENT = -1,
+  EU_ERR_UNSUPPORTED = -2,
+  EU_ERR_CUDA = -3,
+  EU_ERR_NO_DEVICE = -4,
+  EU_ERR_STATE = -5
+} eu_status_t;
+
+/* Mirror of facet_base + the facet_spec members the hot path reads (reference
+ * envutil_basic.h:432-543). The first block is input; the second block is DERIVED and is
+ * filled by eu_facet_prepare()/eu_target_prepare() with the reference's own arithmetic
+ * (get_extent/get_step envutil_basic.cc:112-226, process_geometry envutil_basic.h:499-543). */
+typedef struct eu_facet {
+  /* input */
+  int32_t projection;     /* eu_projection_t */
+  int32_t width, height;  /* total size in pixels */
+  int32_t nchannels;      /* channels of the raster (1..4); RGB = 3 */
+  double hfov;            /* horizontal field of view */
+  double yaw, pitch, roll;
+  double tr_x, tr_y, tr_z; /* PanoTools translation (TrZ already negated, envutil_main.cc:787) */
+  double tp_y, tp_p, tp_r; /* translation plane orientation */
+  double shear_g, shear_t;
+  double a, b, c;          /* lens polynomial */
+  double h, v;             /* PTO d/e shift, in pixels on input; model units after prepare */
+  double brighten;         /* linear gain applied after interpolation (environment.h:1821) */
+  /* derived */
+  double x0, x1, y0, y1;   /* extent in model space */
+  double step;
+  double s, d, r_max, cap_radius;
+  int32_t has_shift, has_lcp, has_shear, has_2d_tf, has_translation;
+  int32_t window_width, window_height, window_x_offset, window_y_offset;
+} eu_facet_t;
+
+/* Mirror of the members of `arguments` that define the target and the job (reference
+ * envutil_basic.h:633-701). */
+typedef struct eu_target {
+  /* input */
+  int32_t projection;
+  int32_t width, height;
+  int32_t nchannels;
+  double hfov;
+  double yaw, pitch, roll;
+  /* derived */
+  double x0, x1, y0, y1;
+  double step;
+} eu_target_t;
+
+typedef struct eu_opts {
+  int32_t spline_degree;    /* --degree (default 1) */
+  int32_t prefilter_degree; /* --prefilter (<0: same as spline_degree) */
+  int32_t synopsis;         /* eu_synopsis_t */
+  int32_t solo;             /* -1, or the single facet to show; forced to 0 for one facet */
+  int32_t support_min;      /* cubemap IR support, default 8  (envutil_main.cc:458) */
+  int32_t tile_size;        /* cubemap IR tile size, default 64 (envutil_main.cc:457) */
+  int32_t reserved[2];
+} eu_opts_t;
+
+/* One twining tap: sub-pixel offset in units of the target's pixel step and weight
+ * (args.twine_spread, reference envutil_main.cc:1253-1355; consumed at twining.h:106-121). */
+typedef struct eu_tap {
+  float x, y, w;
+} eu_tap_t;
+
+typedef struct eu_timing {
+  float render_ms;  /* CUDA-event time of the render kernel(s) only */
+  float h2d_ms;     /* host->device copies inside the call (0 for device entry points) */
+  float d2h_ms;
+  int32_t launches; /* kernels launched by the call */
+  int32_t reserved;
+} eu_timing_t;
+
+typedef struct eu_source* eu_source_h; /* opaque: a staged, braced, prefiltered source */
+
+/* ---------------------------------------------------------------------------------------
+ * Host-side set-up arithmetic (no GPU needed). Restates, in the reference's precision:
+ *   get_vfov/get_step/get_extent      envutil_basic.cc:50-226
+ *   facet set-up                      envutil_main.cc:935-976, envutil_basic.h:499-543
+ *   target set-up                     envutil_main.cc:483-510,1199-1232
+ *   rotate_3d / make_r3_t / rotate    envutil_payload.cc:136-218, geometry.h:79-97
+ *   make_spread / twine_setup         envutil_main.cc:1253-1355,1405-1616
+ *   metrics_t                         cubemap.h:233-400
+ */
+double eu_get_vfov(int projection, int width, int height, double hfov);
+double eu_get_step(int projection, int width, int height, double hfov);
+void eu_get_extent(int projection, int width, int height, double hfov, double ext[4]);
+/* fills every derived member of *f; returns EU_ERR_ARGUMENT for nonsensical input */
+int eu_facet_prepare(eu_facet_t* f);
+/* applies the height rules (cubemap: 6*width; spherical with height 0: width/2 after rounding
+ * width up to even; else height 0 -> width) and fills the derived members */
+int eu_target_prepare(eu_target_t* t);
+/* rows = images of e_x,e_y,e_z under the rotation (float quaternion, double rows) */
+void eu_rotation_matrix(double roll, double pitch, double yaw, int inverse, double m[9]);
+/* basis handed to the stepper for one facet: R_camera * R_facet^-1 (envutil_payload.cc:1923-1948) */
+void eu_facet_basis(const eu_target_t* t, const eu_facet_t* f, double m[9]);
+/* twining filter. twine > 0: twine*twine taps (box, or truncated gaussian if sigma > 0,
+ * taps below threshold dropped, weights renormalised). twine < 0: automatic twining as
+ * arguments::twine_setup does. Writes at most max_taps taps; returns the tap count
+ * (0 = twining off) or a negative status. *twine_out receives the effective twine factor. */
+int eu_make_spread(const eu_target_t* t, int n_facets, const eu_facet_t* facets, int twine,
+                   double twine_width, double twine_density, double twine_sigma,
+                   double twine_threshold, int twine_max, eu_tap_t* taps, int max_taps,
+                   int* twine_out);
+/* cubemap internal representation metrics (cubemap.h:233-400):
+ * out[0]=section_px out[1]=frame_px (left margin) ; refc_md/model_to_px as the view uses them */
+int eu_cubemap_metrics(int face_px, double hfov, int support_min, int tile_size, int32_t out_i[4],
+                       double out_d[4]);
+
+/* ---------------------------------------------------------------------------------------
+ * Device side. One process drives one GPU (multi-GPU = one process per GPU, each rendering
+ * a row band; see eu_render_rows). Single caller, blocking, like payload(). */
+int eu_init(int device_id);
+void eu_shutdown(void);
+const char* eu_last_error(void);
+int eu_device_count(void);
+
+/* Stage one source raster: upload, place into the braced container (lat/lon & mounted
+ * images, reference environment.h:594-950) or the cubemap internal representation
+ * (cubemap.h:548-946,1147-1233), run the b-spline prefilter, brace. pixels: host pointer,
+ * f->width * f->height * f->nchannels floats (cubemaps: width x 6*width).
+ * asset_key may be NULL; a non-NULL key makes the source findable by eu_source_find and
+ * subject to the two-generation ageing of eu_cycle (environment.h:84-227). */
+int eu_source_upload(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o,
+                     const float* pixels, eu_source_h* out, eu_timing_t* t);
+/* same, pixels already in device memory (contiguous interleaved float32) */
+int eu_source_upload_device(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o,
+                            const float* d_pixels, void* cuda_stream, eu_source_h* out,
+                            eu_timing_t* t);
+eu_source_h eu_source_find(const char* asset_key);
+int eu_source_release(eu_source_h s);
+int eu_cycle(void); /* conclude_cycle(): drop sources not used since the previous cycle */
+/* copy the staged coefficient container back (tests): out must hold eu_source_container_floats */
+size_t eu_source_container_floats(eu_source_h s, int32_t shape[4] /* w,h,left_x,left_y */);
+int eu_source_download(eu_source_h s, float* out);
+
+/* Render. facets[i] pairs with sources[i]. taps/n_taps: twining filter (n_taps 0 = off, the
+ * reference's ninputs==3 path; otherwise the ninputs==9 path). out: host buffer of
+ * width*height*nchannels floats. */
+int eu_render(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+              const eu_source_h* sources, const eu_tap_t* taps, int n_taps, float* out,
+              eu_timing_t* timing);
+/* Rows [row0,row1) only, into device memory: d_out points at the first float of row `row0`
+ * (a band buffer of (row1-row0)*width*nchannels floats). Asynchronous on cuda_stream when
+ * timing is NULL. This is the multi-GPU work unit (one band per rank). */
+int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets,
+                   const eu_facet_t* facets, const eu_source_h* sources, const eu_tap_t* taps,
+                   int n_taps, int row0, int row1, float* d_out, void* cuda_stream,
+                   eu_timing_t* timing);
+/* Index plane for bit-exact parity checks: per target pixel the cube face hit (single cubemap
+ * facet) or the winning facet of the panorama synopsis (-1: no facet hit). Host buffer w*h. */
+int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets,
+                    const eu_facet_t* facets, const eu_source_h* sources, int32_t* index_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENVUTIL_B200_H */

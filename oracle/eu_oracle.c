@@ -1,0 +1,1241 @@
+/* eu_oracle.c - TEST INFRASTRUCTURE (see eu_oracle.h). Plain-C, scalar restatement of the
+ * reference's per-pixel reprojection path. Each function cites the reference code it follows.
+ *
+ * Arithmetic rules followed throughout (they decide the last bit of every result):
+ *  - the reference's SIMD types follow C promotion: float-vector (op) double-scalar is computed
+ *    in double and narrowed on assignment (zimt/common.h:278, zimt/simd/gen_simd_type.h:274-321);
+ *    compound assignments and comparisons against a scalar narrow the scalar to float first
+ *    (zimt/simd/vector_common.h:302-316, zimt/simd/vector_mask.h:50-74);
+ *  - the strict reference build uses no fused multiply-add (-ffp-contract=off, no -march);
+ *    this file must be compiled with -ffp-contract=off as well;
+ *  - sin/cos/tan/atan/atan2 on floats are the functions of include/eu_math.h, the same ones
+ *    oracle/_ref/envutil_ref_pm is linked against.
+ */
+#include "eu_oracle.h"
+
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "eu_math.h"
+
+#define ORC_MAX_DEGREE 7
+#define ORC_SEGMENT 512 /* WIELDING_SEGMENT_SIZE, zimt/bill.h:69 */
+#define ORC_LANES 16    /* zimt/simd.h:106-123 for the goading back-end */
+
+enum { BC_PERIODIC = 0, BC_REFLECT = 1, BC_NATURAL = 2, BC_MIRROR = 3 };
+enum { KIND_MOUNT = 0, KIND_CUBEMAP = 1, KIND_BIATAN6 = 2 };
+/* face_index_t, envutil_basic.h:56-64 */
+enum { CM_LEFT = 0, CM_RIGHT = 1, CM_TOP = 2, CM_BOTTOM = 3, CM_FRONT = 4, CM_BACK = 5 };
+
+/* ------------------------------------------------------------------------------------------
+ * set-up arithmetic
+ * ---------------------------------------------------------------------------------------- */
+
+/* get_vfov, envutil_basic.cc:50-110 (the CUBEMAP case falls through to default) */
+static double orc_get_vfov(int prj, int w, int h, double hfov) {
+  switch (prj) {
+    case EU_RECTILINEAR: return 2.0 * atan(h * tan(hfov / 2.0) / w);
+    case EU_CYLINDRICAL: {
+      double ppr = w / hfov;
+      double hr = h / ppr;
+      return 2.0 * atan(hr / 2.0);
+    }
+    case EU_STEREOGRAPHIC: {
+      double wr = 2.0 * tan(hfov / 4.0);
+      double ppr = w / wr;
+      double hr = h / ppr;
+      return 4.0 * atan(hr / 2.0);
+    }
+    case EU_SPHERICAL:
+    case EU_FISHEYE: return hfov * h / w;
+    default: return hfov;
+  }
+}
+
+/* get_step, envutil_basic.cc:112-156 */
+double orc_get_step(int prj, int w, int h, double hfov) {
+  (void)h;
+  switch (prj) {
+    case EU_RECTILINEAR:
+    case EU_CUBEMAP: return atan(2.0 * tan(hfov / 2.0) / w);
+    case EU_BIATAN6:
+    case EU_SPHERICAL:
+    case EU_CYLINDRICAL:
+    case EU_FISHEYE: return hfov / w;
+    case EU_STEREOGRAPHIC: return atan(4.0 * tan(hfov / 4.0) / w);
+    default: return 0.0;
+  }
+}
+
+/* get_extent, envutil_basic.cc:158-226 */
+void orc_get_extent(int prj, int w, int h, double hfov, double e[4]) {
+  double ax = -hfov / 2.0, bx = hfov / 2.0;
+  double by = orc_get_vfov(prj, w, h, hfov) / 2.0, ay = -by;
+  switch (prj) {
+    case EU_SPHERICAL:
+    case EU_FISHEYE: e[0] = ax; e[1] = bx; e[2] = ay; e[3] = by; break;
+    case EU_CYLINDRICAL: e[0] = ax; e[1] = bx; e[2] = tan(ay); e[3] = tan(by); break;
+    case EU_RECTILINEAR: e[0] = tan(ax); e[1] = tan(bx); e[2] = tan(ay); e[3] = tan(by); break;
+    case EU_STEREOGRAPHIC:
+      e[0] = 2.0 * tan(ax / 2.0); e[1] = 2.0 * tan(bx / 2.0);
+      e[2] = 2.0 * tan(ay / 2.0); e[3] = 2.0 * tan(by / 2.0);
+      break;
+    case EU_CUBEMAP:
+    case EU_BIATAN6: e[0] = tan(ax); e[1] = tan(bx); e[2] = 6 * e[0]; e[3] = 6 * e[1]; break;
+    default: e[0] = e[1] = e[2] = e[3] = 0.0;
+  }
+}
+
+/* rotate_3d / make_r3_t, envutil_payload.cc:136-218. Imath::Eulerf(roll,pitch,yaw,ZXY)
+ * .toQuat() in FLOAT (static frame, even parity, axes i,j,k = Z,X,Y), optional
+ * Quat::invert(), then rows = e_k * Quat<double>(q). */
+void orc_rotation(double roll_d, double pitch_d, double yaw_d, int inverse, double m[9]) {
+  float ti = (float)roll_d * 0.5f, tj = (float)pitch_d * 0.5f, th = (float)yaw_d * 0.5f;
+  float ci, cj, ch, si, sj, sh;
+  eu_sincosf(ti, &si, &ci);
+  eu_sincosf(tj, &sj, &cj);
+  eu_sincosf(th, &sh, &ch);
+  float cc = ci * ch, cs = ci * sh, sc = si * ch, ss = si * sh;
+  float q[3], qr;
+  q[2] = cj * sc - sj * cs;
+  q[0] = cj * ss + sj * cc;
+  q[1] = cj * cs - sj * sc;
+  qr = cj * cc + sj * ss;
+  if (inverse) {
+    float d = qr * qr + (q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    qr /= d;
+    q[0] = -q[0] / d;
+    q[1] = -q[1] / d;
+    q[2] = -q[2] / d;
+  }
+  double r = qr, v0 = q[0], v1 = q[1], v2 = q[2];
+  for (int k = 0; k < 3; k++) {
+    double e[3] = {0, 0, 0};
+    e[k] = 1.0;
+    double a[3] = {v1 * e[2] - v2 * e[1], v2 * e[0] - v0 * e[2], v0 * e[1] - v1 * e[0]};
+    double b[3] = {v1 * a[2] - v2 * a[1], v2 * a[0] - v0 * a[2], v0 * a[1] - v1 * a[0]};
+    for (int c = 0; c < 3; c++) m[3 * k + c] = e[c] + 2.0 * (r * a[c] + b[c]);
+  }
+}
+
+/* rotate(r3, r3), geometry.h:79-97: row_i = lhs[i][0]*rhs[0] + lhs[i][1]*rhs[1] + lhs[i][2]*rhs[2] */
+static void mat_mul(const double a[9], const double b[9], double m[9]) {
+  for (int i = 0; i < 3; i++)
+    for (int c = 0; c < 3; c++)
+      m[3 * i + c] = (a[3 * i] * b[c] + a[3 * i + 1] * b[3 + c]) + a[3 * i + 2] * b[6 + c];
+}
+
+/* B-spline basis of degree n at x2/2 (what zimt/basis.h calls bspline_basis_2), by the
+ * Cox-de Boor recursion on the cardinal spline, in long double. */
+static long double basis2(int x2, int n) {
+  /* N_n(t) on knots 0..n+1, centred: b(x) = N_n(x + (n+1)/2) */
+  long double t = (long double)x2 / 2.0L + (long double)(n + 1) / 2.0L;
+  long double v[ORC_MAX_DEGREE + 3];
+  for (int i = 0; i <= n; i++) v[i] = (t >= i && t < i + 1) ? 1.0L : 0.0L;
+  for (int k = 1; k <= n; k++)
+    for (int i = 0; i <= n - k; i++)
+      v[i] = ((t - i) / k) * v[i] + ((i + k + 1 - t) / k) * v[i + 1];
+  return v[0];
+}
+
+/* poles of the b-spline prefilter: roots z, |z|<1, of sum_k b_n(k) z^(k+m) (what
+ * zimt/poles.h tabulates), largest magnitude first (poles.h:1311-1334). Newton iteration in
+ * long double on the deflated polynomial, polished on the full one. */
+int orc_poles(int degree, long double* poles) {
+  int m = degree / 2;
+  if (degree < 2 || degree > ORC_MAX_DEGREE) return 0;
+  long double c[2 * ORC_MAX_DEGREE + 1];
+  int n = 2 * m;
+  for (int k = -m; k <= m; k++) c[k + m] = basis2(2 * k, degree);
+  /* all roots are real and negative, in reciprocal pairs: scan for sign changes in (-1,0) */
+  int found = 0;
+  long double prev_x = -1.0L, prev_v = 0;
+  {
+    long double v = 0;
+    for (int i = n; i >= 0; i--) v = v * prev_x + c[i];
+    prev_v = v;
+  }
+  const int steps = 200000;
+  for (int s = 1; s <= steps && found < m; s++) {
+    long double x = -1.0L + (long double)s / steps;
+    long double v = 0;
+    for (int i = n; i >= 0; i--) v = v * x + c[i];
+    if ((v < 0) != (prev_v < 0)) {
+      long double lo = prev_x, hi = x;
+      for (int it = 0; it < 200; it++) {
+        long double mid = 0.5L * (lo + hi), vm = 0;
+        for (int i = n; i >= 0; i--) vm = vm * mid + c[i];
+        if ((vm < 0) == (prev_v < 0)) lo = mid; else hi = mid;
+      }
+      long double r = 0.5L * (lo + hi);
+      for (int it = 0; it < 4; it++) { /* Newton polish */
+        long double f = 0, d = 0;
+        for (int i = n; i >= 0; i--) { d = d * r + f; f = f * r + c[i]; }
+        if (d != 0) r -= f / d;
+      }
+      poles[found++] = r;
+    }
+    prev_x = x;
+    prev_v = v;
+  }
+  /* scan went from -1 upward, so poles[] is already sorted by descending magnitude */
+  return found;
+}
+
+/* basis_functor::calculate_weight_matrix, zimt/basis.h:419-543 (derivative 0), narrowed to
+ * float as the evaluator's basis_functor<float> holds it. m[row*(degree+1)+k]. */
+void orc_weight_matrix(int degree, float* mtx) {
+  int order = degree + 1;
+  long double der_line[ORC_MAX_DEGREE + 1];
+  long double faculty = 1;
+  for (int row = 0; row < order; row++) {
+    if (row > 1) faculty *= row;
+    int first = 0;
+    int mm = degree - row;
+    if (mm == 0) {
+      der_line[0] = 1;
+      first = 1;
+    } else if (degree & 1) {
+      for (int x2 = -mm + 1; x2 <= mm - 1; x2 += 2) der_line[first++] = basis2(x2, mm);
+    } else {
+      for (int x2 = -mm; x2 <= mm; x2 += 2) der_line[first++] = basis2(x2, mm);
+    }
+    for (int p = first; p < order; p++) der_line[p] = 0;
+    for (int d = mm; d < degree; d++) {
+      int put = first, pick = first - 1;
+      while (pick >= 0) {
+        der_line[put] = der_line[pick] - der_line[put];
+        --put;
+        --pick;
+      }
+      der_line[put] = -der_line[put];
+      first++;
+    }
+    for (int k = 0; k < order; k++) mtx[row * order + k] = (float)(der_line[k] / faculty);
+  }
+}
+
+/* metrics_t, cubemap.h:233-400 */
+typedef struct {
+  int face_px, section_px, left_frame_px, right_frame_px;
+  double model_to_px, px_to_model, section_md, refc_md;
+} cm_metrics_t;
+
+static void cm_metrics(int face_px, double face_fov, int support_min, int tile_px, cm_metrics_t* m) {
+  double overscan_md = 0.0, diameter_md = 2.0;
+  if (face_fov > M_PI_2) {
+    double radius_md = tan(face_fov / 2.0);
+    diameter_md = 2.0 * radius_md;
+    overscan_md = radius_md - 1.0;
+  }
+  m->face_px = face_px;
+  m->model_to_px = (double)face_px / diameter_md;
+  m->px_to_model = diameter_md / (double)face_px;
+  long inherent = (long)trunc(m->model_to_px * overscan_md);
+  long additional = inherent < support_min ? support_min - inherent : 0;
+  long px_min = face_px + 2 * additional;
+  long n_tiles = px_min / tile_px;
+  if (n_tiles * tile_px < px_min) n_tiles++;
+  m->section_px = (int)(n_tiles * tile_px);
+  long frame_total = m->section_px - face_px;
+  m->left_frame_px = (int)(frame_total / 2);
+  m->right_frame_px = (int)(frame_total - m->left_frame_px);
+  m->section_md = m->px_to_model * m->section_px;
+  m->refc_md = m->px_to_model * ((double)m->left_frame_px + (double)face_px / 2.0);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * recursive prefilter (zimt/recursive.h) on one line of floats with stride
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int bc, npoles;
+  float pole[ORC_MAX_DEGREE / 2 + 1];
+  long double pole_x[ORC_MAX_DEGREE / 2 + 1];
+  int horizon[ORC_MAX_DEGREE / 2 + 1];
+  float gain;
+} iir_t;
+
+/* iir_filter ctor, recursive.h:774-862; overall_gain :93-103 */
+static void iir_setup(iir_t* f, int bc, int degree, long double tolerance) {
+  f->bc = bc;
+  f->npoles = degree / 2;
+  orc_poles(degree, f->pole_x);
+  long double lambda = 1;
+  for (int k = 0; k < f->npoles; k++) {
+    f->pole[k] = (float)f->pole_x[k];
+    if (tolerance > 0)
+      f->horizon[k] = (int)ceill(logl(tolerance) / logl(fabsl(f->pole_x[k])));
+    else
+      f->horizon[k] = INT_MAX;
+    lambda *= (1 - f->pole_x[k]) * (1 - 1 / f->pole_x[k]);
+  }
+  f->gain = (float)lambda;
+}
+
+#define C(n) c[(size_t)(n) * st]
+
+/* initial causal coefficient, recursive.h:321-583 */
+static float iir_icc(const iir_t* f, const float* c, size_t st, int M, int k) {
+  float z = f->pole[k], zn, z2n, iz, Sum;
+  int n, hz = f->horizon[k];
+  switch (f->bc) {
+    case BC_MIRROR:
+      if (hz < M) {
+        zn = z; Sum = C(0);
+        for (n = 1; n < hz; n++) { Sum += zn * C(n); zn *= z; }
+      } else {
+        zn = z; iz = 1.0f / z;
+        z2n = (float)powl(f->pole_x[k], (long double)(M - 1));
+        Sum = C(0) + z2n * C(M - 1);
+        z2n *= z2n * iz;
+        for (n = 1; n <= M - 2; n++) { Sum += (zn + z2n) * C(n); zn *= z; z2n *= iz; }
+        Sum /= (1.0f - zn * zn);
+      }
+      return Sum;
+    case BC_NATURAL:
+      if (hz < M) {
+        float c02 = C(0) + C(0);
+        zn = z; Sum = C(0);
+        for (n = 1; n < hz; n++) { Sum += zn * (c02 - C(n)); zn *= z; }
+        return Sum;
+      } else {
+        zn = z; iz = 1.0f / z;
+        z2n = (float)powl(f->pole_x[k], (long double)(M - 1));
+        Sum = ((1.0f + z) / (1.0f - z)) * (C(0) - z2n * C(M - 1));
+        z2n *= z2n * iz;
+        for (n = 1; n <= M - 2; n++) { Sum -= (zn - z2n) * C(n); zn *= z; z2n *= iz; }
+        return Sum / (1.0f - zn * zn);
+      }
+    case BC_REFLECT:
+      if (hz < M) {
+        zn = z; Sum = C(0);
+        for (n = 0; n < hz; n++) { Sum += zn * C(n); zn *= z; }
+        return Sum;
+      } else {
+        zn = z; iz = 1.0f / z;
+        z2n = (float)powl(f->pole_x[k], (long double)(2 * M));
+        Sum = 0;
+        for (n = 0; n < M - 1; n++) { Sum += (zn + z2n) * C(n); zn *= z; z2n *= iz; }
+        Sum += (zn + z2n) * C(n);
+        return C(0) + Sum / (1.0f - zn * zn);
+      }
+    case BC_PERIODIC:
+    default:
+      if (hz < M) {
+        zn = z; Sum = C(0);
+        for (n = M - 1; n > (M - hz); n--) { Sum += zn * C(n); zn *= z; }
+      } else {
+        zn = z; Sum = C(0);
+        for (n = M - 1; n > 0; n--) { Sum += zn * C(n); zn *= z; }
+        Sum /= (1.0f - zn);
+      }
+      return Sum;
+  }
+}
+
+/* initial anticausal coefficient, recursive.h:360-583 */
+static float iir_iacc(const iir_t* f, const float* c, size_t st, int M, int k) {
+  float z = f->pole[k], zn, Sum;
+  switch (f->bc) {
+    case BC_MIRROR: return (z / (z * z - 1.0f)) * (C(M - 1) + z * C(M - 2));
+    case BC_NATURAL: return -(z / ((1.0f - z) * (1.0f - z))) * (C(M - 1) - z * C(M - 2));
+    case BC_REFLECT: return C(M - 1) / (1.0f - 1.0f / z);
+    case BC_PERIODIC:
+    default:
+      if (f->horizon[k] < M) {
+        zn = z; Sum = C(M - 1) * z;
+        for (int n = 0; n < f->horizon[k]; n++) { zn *= z; Sum += zn * C(n); }
+        Sum = -Sum;
+      } else {
+        zn = z; Sum = C(M - 1);
+        for (int n = 0; n < M - 1; n++) { Sum += zn * C(n); zn *= z; }
+        Sum = z * Sum / (zn - 1.0f);
+      }
+      return Sum;
+  }
+}
+
+/* solve_gain_inlined, recursive.h:631-729 (in place) */
+static void iir_line(const iir_t* f, float* c, size_t st, int M) {
+  if (M == 1 || f->npoles < 1) return;
+  float p = f->pole[0], g = f->gain;
+  float X = g * iir_icc(f, c, st, M, 0);
+  C(0) = X;
+  for (int n = 1; n < M; n++) { X = g * C(n) + p * X; C(n) = X; }
+  X = iir_iacc(f, c, st, M, 0);
+  C(M - 1) = X;
+  for (int n = M - 2; n >= 0; n--) { X = p * (X - C(n)); C(n) = X; }
+  for (int k = 1; k < f->npoles; k++) {
+    p = f->pole[k];
+    X = iir_icc(f, c, st, M, k);
+    C(0) = X;
+    for (int n = 1; n < M; n++) { X = C(n) + p * X; C(n) = X; }
+    X = iir_iacc(f, c, st, M, k);
+    C(M - 1) = X;
+    for (int n = M - 2; n >= 0; n--) { X = p * (X - C(n)); C(n) = X; }
+  }
+}
+#undef C
+
+/* ------------------------------------------------------------------------------------------
+ * staged source
+ * ---------------------------------------------------------------------------------------- */
+struct orc_source {
+  int kind, projection, nch, degree;
+  int w, h;           /* core shape */
+  int cw, chh;        /* container shape */
+  int lx, ly;         /* left frames */
+  float* container;
+  float* core;        /* texel (0,0) of the core */
+  size_t stride;      /* floats per container row */
+  int bc0, bc1;
+  cm_metrics_t cm;
+  float wmat[(ORC_MAX_DEGREE + 1) * (ORC_MAX_DEGREE + 1)];
+};
+
+/* get_left_brace_size / get_right_brace_size, zimt/bspline.h:305-372 */
+static int left_brace(int degree, int bc) {
+  int b = degree / 2;
+  if (bc == BC_REFLECT) b++;
+  else if (degree & 1) b++;
+  if (bc == BC_PERIODIC && !(degree & 1)) b++;
+  return b;
+}
+static int right_brace(int degree, int bc) {
+  int b = degree / 2;
+  if (bc == BC_REFLECT && !(degree & 1)) b++;
+  if (degree & 1) b++;
+  if (bc == BC_PERIODIC) b++;
+  return b;
+}
+
+static float* texel(const orc_source_t* s, int x, int y) { /* core coordinates */
+  return s->core + (ptrdiff_t)y * (ptrdiff_t)s->stride + (ptrdiff_t)x * s->nch;
+}
+
+/* bracer::apply for one axis, zimt/brace.h:151-338, copying boundary conditions */
+static void brace_axis(orc_source_t* s, int axis, int bc, int lsz, int rsz) {
+  int nch = s->nch;
+  if (axis == 0) {
+    int m = s->w;
+    for (int Y = -s->ly; Y < s->chh - s->ly; Y++) {
+      for (int k = 0; k < lsz; k++) {
+        int src = (bc == BC_PERIODIC) ? m - 1 - k : k;
+        memcpy(texel(s, -1 - k, Y), texel(s, src, Y), sizeof(float) * nch);
+      }
+      for (int k = 0; k < rsz; k++) {
+        int src = (bc == BC_PERIODIC) ? k : m - 1 - k;
+        memcpy(texel(s, m + k, Y), texel(s, src, Y), sizeof(float) * nch);
+      }
+    }
+  } else {
+    int m = s->h;
+    size_t rowb = sizeof(float) * s->stride;
+    for (int k = 0; k < lsz; k++) {
+      int src = (bc == BC_PERIODIC) ? m - 1 - k : k;
+      memcpy(texel(s, -s->lx, -1 - k), texel(s, -s->lx, src), rowb);
+    }
+    for (int k = 0; k < rsz; k++) {
+      int src = (bc == BC_PERIODIC) ? k : m - 1 - k;
+      memcpy(texel(s, -s->lx, m + k), texel(s, -s->lx, src), rowb);
+    }
+  }
+}
+
+/* zimt::prefilter, prefilter.h:125-198: axis 0 then axis 1, channels independent */
+static void prefilter_2d(float* base, size_t stride, int nch, int w, int h, int bc0, int bc1, int degree,
+                         long double tolerance) {
+  if (degree <= 1) return;
+  iir_t f0, f1;
+  iir_setup(&f0, bc0, degree, tolerance);
+  iir_setup(&f1, bc1, degree, tolerance);
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < h; y++)
+    for (int c = 0; c < nch; c++) iir_line(&f0, base + (size_t)y * stride + c, (size_t)nch, w);
+#pragma omp parallel for schedule(static)
+  for (int x = 0; x < w; x++)
+    for (int c = 0; c < nch; c++) iir_line(&f1, base + (size_t)x * nch + c, stride, h);
+}
+
+/* spherical_prefilter, environment.h:356-522 */
+static void spherical_prefilter(orc_source_t* s, int degree, int ry) {
+  int w = s->w, h = s->h, nch = s->nch;
+  iir_t f;
+  if (degree > 1) {
+    iir_setup(&f, BC_PERIODIC, degree, (long double)0.0001);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+      for (int c = 0; c < nch; c++) iir_line(&f, texel(s, 0, y) + c, (size_t)nch, w);
+    /* vertical pass over [left half column top->bottom ; right half column bottom->top] */
+    int half = w / 2;
+#pragma omp parallel
+    {
+      float* line = (float*)malloc(sizeof(float) * 2 * (size_t)h);
+#pragma omp for schedule(static)
+      for (int x = 0; x < half; x++)
+        for (int c = 0; c < nch; c++) {
+          for (int y = 0; y < h; y++) {
+            line[y] = texel(s, x, y)[c];
+            line[h + y] = texel(s, x + half, h - 1 - y)[c];
+          }
+          iir_line(&f, line, 1, 2 * h);
+          for (int y = 0; y < h; y++) {
+            texel(s, x, y)[c] = line[y];
+            texel(s, x + half, h - 1 - y)[c] = line[h + y];
+          }
+        }
+      free(line);
+    }
+  }
+  /* brace rows across the poles: row -1-k of one half = row k of the other half */
+  int half = w / 2;
+  for (int k = 0; k < s->ly; k++) {
+    if (k >= h) break;
+    memcpy(texel(s, 0, -1 - k), texel(s, half, k), sizeof(float) * nch * half);
+    memcpy(texel(s, half, -1 - k), texel(s, 0, k), sizeof(float) * nch * half);
+  }
+  for (int k = 0; k < ry; k++) {
+    if (k >= h) break;
+    memcpy(texel(s, 0, h + k), texel(s, half, h - 1 - k), sizeof(float) * nch * half);
+    memcpy(texel(s, half, h + k), texel(s, 0, h - 1 - k), sizeof(float) * nch * half);
+  }
+  brace_axis(s, 0, BC_PERIODIC, s->lx, s->cw - s->lx - s->w);
+}
+
+/* ---- coordinate gates, zimt/map.h (vector variants) ---- */
+static float v_fmod(float lhs, float rhs) {
+  float help = lhs;
+  help /= rhs;
+  help = truncf(help);
+  help *= rhs;
+  lhs -= help;
+  if (fabsf(lhs) >= fabsf(rhs)) lhs = 0;
+  return lhs;
+}
+static float gate_mirror(float c, float lower, float upper) {
+  float cc = c - lower;
+  float w = upper - lower;
+  cc = fabsf(cc);
+  if (cc >= w) {
+    float cm = v_fmod(cc, 2 * w);
+    cm -= w;
+    cm = fabsf(cm);
+    cm = w - cm;
+    cc = cm;
+  }
+  return cc + lower;
+}
+static float gate_periodic(float c, float lower, float upper) {
+  float cc = c - lower;
+  float w = upper - lower;
+  int below = cc < 0, above = cc >= w;
+  if (below || above) {
+    float cm = v_fmod(cc, w);
+    if (below) cm = cm + w;
+    if (cm >= w) cm = 0;
+    cc = cm;
+  }
+  return cc + lower;
+}
+
+/* safe evaluator = mapper + evaluator (zimt/eval.h:2039-2164, :1237-1300, :903-1059).
+ * degree: the evaluator's degree (spline_degree + shift). crd in spline coordinates. */
+static void spline_eval(const orc_source_t* s, int degree, const float* wmat, float cx, float cy, float* out) {
+  int nch = s->nch;
+  /* gates: PERIODIC / REFLECT limits are -0.5 .. N-0.5 (zimt/bspline.h:233-286) */
+  float ux = (float)((long double)(s->w - 1) + 0.5L), uy = (float)((long double)(s->h - 1) + 0.5L);
+  cx = (s->bc0 == BC_PERIODIC) ? gate_periodic(cx, -0.5f, ux) : gate_mirror(cx, -0.5f, ux);
+  cy = (s->bc1 == BC_PERIODIC) ? gate_periodic(cy, -0.5f, uy) : gate_mirror(cy, -0.5f, uy);
+  /* split, zimt/basis.h:102-146 */
+  float fx, fy;
+  int ix, iy;
+  if (degree & 1) {
+    float f = floorf(cx); fx = cx - f; ix = (int)f;
+    f = floorf(cy); fy = cy - f; iy = (int)f;
+  } else {
+    float f = roundf(cx); fx = cx - f; ix = (int)f;
+    f = roundf(cy); fy = cy - f; iy = (int)f;
+  }
+  if (degree == 0) {
+    const float* p = texel(s, ix, iy);
+    for (int c = 0; c < nch; c++) out[c] = p[c];
+    return;
+  }
+  if (degree == 1) { /* _eval_linear, eval.h:1004-1059 */
+    float wl0 = 1.0f - fx, wr0 = fx, wl1 = 1.0f - fy, wr1 = fy;
+    const float* p00 = texel(s, ix, iy);
+    const float* p10 = texel(s, ix + 1, iy);
+    const float* p01 = texel(s, ix, iy + 1);
+    const float* p11 = texel(s, ix + 1, iy + 1);
+    for (int c = 0; c < nch; c++) {
+      float sum = p00[c];
+      sum *= wl0;
+      sum += p10[c] * wr0;
+      sum *= wl1;
+      float sub = p01[c];
+      sub *= wl0;
+      sub += p11[c] * wr0;
+      sum += sub * wr1;
+      out[c] = sum;
+    }
+    return;
+  }
+  /* weights, basis.h:650-689 */
+  int order = degree + 1;
+  float wx[ORC_MAX_DEGREE + 1], wy[ORC_MAX_DEGREE + 1];
+  for (int axis = 0; axis < 2; axis++) {
+    float* w = axis ? wy : wx;
+    float delta = axis ? fy : fx;
+    float power = delta;
+    for (int k = 0; k < order; k++) w[k] = wmat[k];
+    for (int row = 1; row < order; row++) {
+      for (int k = 0; k < order; k++) w[k] += power * wmat[row * order + k];
+      if (row < order - 1) power *= delta;
+    }
+  }
+  /* _eval, eval.h:903-996: window offsets k - degree/2 per axis (:732) */
+  int h2 = degree / 2;
+  for (int c = 0; c < nch; c++) {
+    float sum = 0;
+    for (int j = 0; j < order; j++) {
+      const float* row = texel(s, ix - h2, iy - h2 + j) + c;
+      float sub = row[0];
+      sub *= wx[0];
+      for (int i = 1; i < order; i++) sub += wx[i] * row[(size_t)i * nch];
+      if (j == 0) {
+        sum = sub;
+        sum *= wy[0];
+      } else {
+        sum += sub * wy[j];
+      }
+    }
+    out[c] = sum;
+  }
+}
+
+/* ray_to_cubeface, geometry.h:1178-1357 */
+static void ray_to_cubeface(const float c[3], int* face, float in_face[2]) {
+  int m1 = fabsf(c[0]) >= fabsf(c[1]);
+  int m2 = fabsf(c[0]) >= fabsf(c[2]);
+  int m3 = fabsf(c[1]) >= fabsf(c[2]);
+  if (m1 && m2) {
+    *face = c[0] < 0 ? CM_LEFT : CM_RIGHT;
+    in_face[0] = -c[2] / c[0];
+    in_face[1] = c[1] / fabsf(c[0]);
+  } else if (!m2 && !m3) {
+    *face = c[2] < 0 ? CM_BACK : CM_FRONT;
+    in_face[0] = c[0] / c[2];
+    in_face[1] = c[1] / fabsf(c[2]);
+  } else {
+    *face = c[1] < 0 ? CM_TOP : CM_BOTTOM;
+    in_face[0] = -c[0] / fabsf(c[1]);
+    in_face[1] = c[2] / c[1];
+  }
+}
+
+/* cubemap_t::fill_support, cubemap.h:607-911: 1-px mirrored ring, then the four frame
+ * stripes of every section by bilinear reprojection from the IR itself, in the reference's
+ * order (later stripes see pixels written by earlier ones). */
+static void cubemap_fill_support(orc_source_t* s) {
+  const cm_metrics_t* m = &s->cm;
+  int S = m->section_px, F = m->face_px, L = m->left_frame_px, R = m->right_frame_px, nch = s->nch;
+  if (L == 0 && R == 0) return;
+  size_t tb = sizeof(float) * nch;
+  for (int face = 0; face < 6; face++) { /* mirror_around, :607-660 */
+    int oy = face * S + L, ox = L;
+    int cmin = L > 0 ? -1 : 0, cmax = R > 0 ? F : F - 1;
+    for (int x = cmin; x <= cmax; x++) {
+      if (L) memcpy(texel(s, ox + x, oy - 1), texel(s, ox + x, oy), tb);
+      if (R) memcpy(texel(s, ox + x, oy + F), texel(s, ox + x, oy + F - 1), tb);
+    }
+    for (int y = cmin; y <= cmax; y++) {
+      if (L) memcpy(texel(s, ox - 1, oy + y), texel(s, ox, oy + y), tb);
+      if (R) memcpy(texel(s, ox + F, oy + y), texel(s, ox + F - 1, oy + y), tb);
+    }
+  }
+  int ithird = (int)(m->model_to_px * 2);
+  int ishift = S - 1;
+  float* rowbuf = (float*)malloc(tb * S);
+  for (int face = 0; face < 6; face++) {
+    int win[4][4] = {{0, 0, S, L}, {0, S - R, S, S}, {0, L, L, S - R}, {L + F, L, S, S - R}};
+    int on[4] = {L > 0, R > 0, L > 0, R > 0};
+    for (int st = 0; st < 4; st++) {
+      if (!on[st]) continue;
+      int x0 = win[st][0], y0 = win[st][1], x1 = win[st][2], y1 = win[st][3];
+      /* a stripe never reads its own section, rows can be written as they are computed */
+      for (int y = y0; y < y1; y++) {
+        for (int x = x0; x < x1; x++) {
+          int c0 = 2 * x - ishift, c1 = 2 * y - ishift;
+          float ray[3];
+          switch (face) { /* fill_frame_t::eval, :733-780 */
+            case CM_FRONT: ray[0] = (float)c0; ray[1] = (float)c1; ray[2] = (float)ithird; break;
+            case CM_BACK: ray[0] = (float)(-c0); ray[1] = (float)c1; ray[2] = (float)(-ithird); break;
+            case CM_RIGHT: ray[0] = (float)ithird; ray[1] = (float)c1; ray[2] = (float)(-c0); break;
+            case CM_LEFT: ray[0] = (float)(-ithird); ray[1] = (float)c1; ray[2] = (float)c0; break;
+            case CM_BOTTOM: ray[0] = (float)(-c0); ray[1] = (float)ithird; ray[2] = (float)c1; break;
+            default: ray[0] = (float)(-c0); ray[1] = (float)(-ithird); ray[2] = (float)(-c1); break;
+          }
+          int fv;
+          float in_face[2], pk[2];
+          ray_to_cubeface(ray, &fv, in_face);
+          /* metrics_t::get_pickup_coordinate_px, cubemap.h:401-411: refc_md is a double here */
+          pk[0] = (float)((double)in_face[0] + m->refc_md);
+          pk[1] = (float)((double)in_face[1] + m->refc_md);
+          pk[0] *= (float)m->model_to_px;
+          pk[1] *= (float)m->model_to_px;
+          pk[1] += (float)(fv * S);
+          pk[0] -= .5f;
+          pk[1] -= .5f;
+          spline_eval(s, 1, NULL, pk[0], pk[1], rowbuf + (size_t)(x - x0) * nch);
+        }
+        memcpy(texel(s, x0, face * S + y), rowbuf, tb * (x1 - x0));
+      }
+    }
+  }
+  free(rowbuf);
+}
+
+orc_source_t* orc_source_create(const eu_facet_t* f, const eu_opts_t* o, const float* pixels) {
+  orc_source_t* s = (orc_source_t*)calloc(1, sizeof(*s));
+  int degree = o->spline_degree;
+  int pdeg = o->prefilter_degree < 0 ? degree : o->prefilter_degree;
+  s->projection = f->projection;
+  s->nch = f->nchannels;
+  s->degree = degree;
+  int nch = s->nch;
+  if (degree > 1) orc_weight_matrix(degree, s->wmat);
+  if (f->projection == EU_CUBEMAP || f->projection == EU_BIATAN6) {
+    /* cubemap_t ctor + load, cubemap.h:548-580,1147-1233 */
+    s->kind = f->projection == EU_CUBEMAP ? KIND_CUBEMAP : KIND_BIATAN6;
+    cm_metrics(f->width, f->hfov, o->support_min, o->tile_size, &s->cm);
+    int S = s->cm.section_px, F = f->width, L = s->cm.left_frame_px;
+    s->w = s->cw = S;
+    s->h = s->chh = 6 * S;
+    s->lx = s->ly = 0;
+    s->bc0 = s->bc1 = BC_REFLECT;
+    s->stride = (size_t)S * nch;
+    s->container = (float*)calloc((size_t)S * 6 * S * nch, sizeof(float));
+    s->core = s->container;
+    for (int face = 0; face < 6; face++)
+      for (int y = 0; y < F; y++)
+        memcpy(texel(s, L, face * S + L + y), pixels + ((size_t)(face * F + y) * F) * nch, sizeof(float) * nch * F);
+    cubemap_fill_support(s);
+    if (pdeg > 1)
+      for (int face = 0; face < 6; face++) /* cubemap_t::prefilter, :921-946 */
+        prefilter_2d(texel(s, 0, face * S), s->stride, nch, S, S, BC_NATURAL, BC_NATURAL, pdeg,
+                     (long double)FLT_EPSILON);
+    return s;
+  }
+  /* source_t ctor, environment.h:594-950 */
+  s->kind = KIND_MOUNT;
+  s->w = f->width;
+  s->h = f->height;
+  s->bc0 = BC_REFLECT;
+  s->bc1 = BC_REFLECT;
+  if ((f->projection == EU_SPHERICAL || f->projection == EU_CYLINDRICAL) && fabs(f->hfov - 2.0 * M_PI) < .000001)
+    s->bc0 = BC_PERIODIC;
+  s->lx = left_brace(degree, s->bc0);
+  s->ly = left_brace(degree, s->bc1);
+  int rx = right_brace(degree, s->bc0), ry = right_brace(degree, s->bc1);
+  s->cw = s->w + s->lx + rx;
+  s->chh = s->h + s->ly + ry;
+  s->stride = (size_t)s->cw * nch;
+  s->container = (float*)calloc((size_t)s->cw * s->chh * nch, sizeof(float));
+  s->core = s->container + (size_t)s->ly * s->stride + (size_t)s->lx * nch;
+  for (int y = 0; y < s->h; y++)
+    memcpy(texel(s, 0, y), pixels + (size_t)y * s->w * nch, sizeof(float) * nch * s->w);
+  if (f->projection == EU_SPHERICAL && fabs(f->hfov - 2.0 * M_PI) < .000001 && f->width == 2 * f->height) {
+    spherical_prefilter(s, pdeg, ry);
+  } else {
+    prefilter_2d(s->core, s->stride, nch, s->w, s->h, s->bc0, s->bc1, pdeg, (long double)FLT_EPSILON);
+    brace_axis(s, 0, s->bc0, s->lx, rx);
+    brace_axis(s, 1, s->bc1, s->ly, ry);
+  }
+  return s;
+}
+
+void orc_source_free(orc_source_t* s) {
+  if (!s) return;
+  free(s->container);
+  free(s);
+}
+
+const float* orc_source_container(const orc_source_t* s, int32_t shape[4]) {
+  shape[0] = s->cw; shape[1] = s->chh; shape[2] = s->lx; shape[3] = s->ly;
+  return s->container;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * per-job derived state
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const orc_source_t* src;
+  int projection, kind;
+  float xx[3], yy[3], zz[3]; /* stepper basis rows, narrowed (stepper ctor args) */
+  /* source_t, environment.h:594-645,970-1006 */
+  double ext_x0, ext_y0;
+  float ext_w, ext_h;
+  float win_x0, win_x1, win_y0, win_y1;
+  int total_w, total_h;
+  int has_lcp, has_shift, has_shear;
+  float lcp[4], lcp_s, sh_h, sh_v;
+  double shear_g, shear_t;
+  float refc_md, model_to_px;
+  int section_px;
+  float recip_step, brighten, optimum;
+  int hdr_kind; /* 0 LOW 1 MIDDLE 2 HIGH */
+  int mask_always;
+} facet_ctx;
+
+typedef struct {
+  int projection, width, height, normalize;
+  float fx0, fx1, fy0, fy1, delta;
+  float bias_x, bias_y; /* of the biased steppers r10 / r01 */
+  float section_md, refc_md;
+} target_ctx;
+
+/* stepper_base ctor, stepper.h:294-306 */
+static void target_setup(const eu_target_t* t, target_ctx* T) {
+  double e[4];
+  int w = t->width, h = t->height;
+  orc_get_extent(t->projection, w, h, t->hfov, e);
+  float a0 = (float)e[0], a1 = (float)e[1], b0 = (float)e[2], b1 = (float)e[3];
+  T->projection = t->projection;
+  T->width = w;
+  T->height = h;
+  T->fx1 = (float)(a1 / (2.0 * w));
+  T->fx0 = (float)(a0 / (2.0 * w));
+  T->fy1 = (float)(b1 / (2.0 * h));
+  T->fy0 = (float)(b0 / (2.0 * h));
+  T->bias_x = .25f * (a1 - a0) / (float)w;
+  T->bias_y = .25f * (b1 - b0) / (float)h;
+  T->delta = (float)ORC_LANES * (a1 - a0) / (float)w;
+  T->section_md = a1 - a0;                    /* stepper.h:1265 */
+  T->refc_md = (float)((a1 - a0) / 2.0);      /* stepper.h:1266 */
+}
+
+/* stepper_base::init + increase, stepper.h:324-350, as zimt::process drives them
+ * (zimt/wielding.h:317-455): init at the start of each 512-px segment, then += delta per
+ * 16-px vector. */
+static float planar_x(const target_ctx* T, int x, float bias) {
+  int seg0 = (x / ORC_SEGMENT) * ORC_SEGMENT;
+  int r = x - seg0, lane = r % ORC_LANES, v = r / ORC_LANES;
+  float ll0 = (float)(2 * lane) + (float)(seg0 * 2 + 1);
+  float p = bias + ll0 * T->fx1 + ((float)(2 * T->width) - ll0) * T->fx0;
+  for (int i = 0; i < v; i++) p += T->delta;
+  return p;
+}
+static float planar_y(const target_ctx* T, int y, float bias) {
+  int ll1 = y * 2 + 1;
+  return bias + ll1 * T->fy1 + (float)(2 * T->height - ll1) * T->fy0;
+}
+
+static float norm3(const float v[3]) {
+  float sqn = v[0] * v[0];
+  sqn += v[1] * v[1];
+  sqn += v[2] * v[2];
+  return sqrtf(sqn);
+}
+
+/* the seven steppers, stepper.h:517-1578. (px,py) planar coordinate, (x,y) discrete target
+ * coordinate (needed by the cube steppers and by the cylindrical stepper's per-segment
+ * rcp_length). */
+static void stepper_ray(const target_ctx* T, const facet_ctx* F, float px, float py, int x, int y, float bias_x,
+                        float ray[3]) {
+  const float *xx = F->xx, *yy = F->yy, *zz = F->zz;
+  switch (T->projection) {
+    case EU_SPHERICAL: {
+      float sy, r, sx, z;
+      eu_sincosf(py, &sy, &r);
+      eu_sincosf(px, &sx, &z);
+      for (int i = 0; i < 3; i++) {
+        float xxx = xx[i] * r, yyy = yy[i] * sy, zzz = zz[i] * r;
+        ray[i] = xxx * sx + zzz * z + yyy;
+      }
+      break;
+    }
+    case EU_CYLINDRICAL: {
+      float sx, z;
+      eu_sincosf(px, &sx, &z);
+      for (int i = 0; i < 3; i++) ray[i] = xx[i] * sx + zz[i] * z + yy[i] * py;
+      if (T->normalize) {
+        /* rcp_length is taken from the first vector of the segment, same lane (:766-769) */
+        int seg0 = (x / ORC_SEGMENT) * ORC_SEGMENT, lane = (x - seg0) % ORC_LANES;
+        float p0 = planar_x(T, seg0 + lane, bias_x), s0, z0, first[3];
+        eu_sincosf(p0, &s0, &z0);
+        for (int i = 0; i < 3; i++) first[i] = xx[i] * s0 + zz[i] * z0 + yy[i] * py;
+        float rcp = 1.0f / norm3(first);
+        for (int i = 0; i < 3; i++) ray[i] *= rcp;
+      }
+      break;
+    }
+    case EU_RECTILINEAR: {
+      for (int i = 0; i < 3; i++) {
+        float ddd = yy[i] * py + zz[i];
+        ray[i] = xx[i] * px + ddd;
+      }
+      if (T->normalize) {
+        float n = norm3(ray);
+        for (int i = 0; i < 3; i++) ray[i] /= n;
+      }
+      break;
+    }
+    case EU_FISHEYE:
+    case EU_STEREOGRAPHIC: {
+      float sqn = px * px;
+      sqn += py * py;
+      float nrm = sqrtf(sqn);
+      float a;
+      if (T->projection == EU_FISHEYE)
+        a = (float)(M_PI_2 - (double)nrm); /* :1019-1021, double promotion */
+      else
+        a = (float)(M_PI_2 - 2.0 * eu_atan((double)nrm / 2.0)); /* :1146-1148 */
+      float b = eu_atan2f(px, py);
+      float z, r, sx, cy;
+      eu_sincosf(a, &z, &r);
+      eu_sincosf(b, &sx, &cy);
+      for (int i = 0; i < 3; i++) ray[i] = xx[i] * r * sx + zz[i] * z + yy[i] * r * cy;
+      break;
+    }
+    case EU_CUBEMAP:
+    case EU_BIATAN6: {
+      int face = y / T->width;
+      float p1 = py + (3 - face) * T->section_md - T->refc_md;
+      float p0 = px;
+      if (T->projection == EU_BIATAN6) {
+        p1 = eu_tanf(p1 * (float)(M_PI / 4.0));
+        p0 = eu_tanf(p0 * (float)(M_PI / 4.0));
+      }
+      float ccc[3], vvv[3];
+      for (int i = 0; i < 3; i++) {
+        switch (face) { /* :1304-1331; the +-1.0 factors promote the sum to double */
+          case CM_LEFT: ccc[i] = (float)(-1.0 * xx[i] + (double)(p1 * yy[i])); vvv[i] = zz[i]; break;
+          case CM_RIGHT: ccc[i] = (float)(1.0 * xx[i] + (double)(p1 * yy[i])); vvv[i] = -zz[i]; break;
+          case CM_TOP: ccc[i] = (float)(-1.0 * yy[i] - (double)(p1 * zz[i])); vvv[i] = -xx[i]; break;
+          case CM_BOTTOM: ccc[i] = (float)(1.0 * yy[i] + (double)(p1 * zz[i])); vvv[i] = -xx[i]; break;
+          case CM_FRONT: ccc[i] = (float)((double)(p1 * yy[i]) + 1.0 * zz[i]); vvv[i] = xx[i]; break;
+          default: ccc[i] = (float)((double)(p1 * yy[i]) - 1.0 * zz[i]); vvv[i] = -xx[i]; break;
+        }
+      }
+      for (int i = 0; i < 3; i++) ray[i] = ccc[i] + p0 * vvv[i];
+      if (T->normalize) {
+        float n = norm3(ray);
+        for (int i = 0; i < 3; i++) ray[i] /= n;
+      }
+      break;
+    }
+    default: ray[0] = ray[1] = 0; ray[2] = 1;
+  }
+}
+
+/* mount_t::get_coordinate_nomask, environment.h:1077-1110 + geometry.h:277-534 + pto_planar */
+static void mount_coordinate(const facet_ctx* F, const float r[3], float c[2]) {
+  switch (F->projection) {
+    case EU_RECTILINEAR: c[0] = r[0] / r[2]; c[1] = r[1] / r[2]; break;
+    case EU_SPHERICAL: {
+      float s = sqrtf(r[0] * r[0] + r[2] * r[2]);
+      c[1] = eu_atan2f(r[1], s);
+      c[0] = eu_atan2f(r[0], r[2]);
+      break;
+    }
+    case EU_CYLINDRICAL: {
+      float s = sqrtf(r[0] * r[0] + r[2] * r[2]);
+      c[1] = r[1] / s;
+      c[0] = eu_atan2f(r[0], r[2]);
+      break;
+    }
+    case EU_STEREOGRAPHIC: {
+      float rn = 1.0f / sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+      float right = r[0] * rn, down = r[1] * rn, fwd = r[2] * rn;
+      float factor = 2.0f / (fwd + 1.0f);
+      c[0] = right * factor;
+      c[1] = down * factor;
+      break;
+    }
+    default: { /* FISHEYE */
+      float s = sqrtf(r[0] * r[0] + r[1] * r[1]);
+      float rr = (float)M_PI_2 - eu_atan2f(r[2], s);
+      float phi = eu_atan2f(r[1], r[0]);
+      c[0] = rr * eu_cosf(phi);
+      c[1] = rr * eu_sinf(phi);
+    }
+  }
+  if (F->has_lcp) { /* pto_planar::eval forward, environment.h:254-283; lcp lens_correction.h:94-105 */
+    float sqn = c[0] * c[0];
+    sqn += c[1] * c[1];
+    float x = sqrtf(sqn) / F->lcp_s;
+    float sum = 0.0f, power = 1.0f;
+    for (int i = 0; i <= 3; i++) {
+      sum += F->lcp[3 - i] * power;
+      power *= x;
+    }
+    c[0] *= sum;
+    c[1] *= sum;
+    if (F->has_shift) {
+      c[0] += F->sh_h;
+      c[1] += F->sh_v;
+    }
+    if (F->has_shear) {
+      float h0 = (float)((double)c[0] + (double)c[1] * F->shear_g);
+      float h1 = (float)((double)c[1] + (double)c[0] * F->shear_t);
+      c[0] = h0;
+      c[1] = h1;
+    }
+  }
+}
+
+static int mount_mask(const facet_ctx* F, const float r[3], const float c[2]) {
+  int m = (c[0] >= F->win_x0) && (c[0] <= F->win_x1) && (c[1] >= F->win_y0) && (c[1] <= F->win_y1);
+  if (F->projection == EU_RECTILINEAR) m = m && (r[2] > 0.0f);
+  return m;
+}
+
+/* environment::get_mask, environment.h:1567,1700-1760 */
+static int facet_mask(const facet_ctx* F, const float r[3]) {
+  if (F->mask_always) return 1;
+  float c[2];
+  mount_coordinate(F, r, c);
+  return mount_mask(F, r, c);
+}
+
+/* environment::eval, environment.h:1821-1842 over mount_t::eval :1172-1196 or
+ * cubemap_view_t::eval :1473-1486. Returns the cube face (or -1). */
+static int facet_eval(const facet_ctx* F, const float r[3], float* px) {
+  const orc_source_t* s = F->src;
+  int nch = s->nch, face = -1;
+  if (F->kind == KIND_MOUNT) {
+    float c[2];
+    mount_coordinate(F, r, c);
+    if (!mount_mask(F, r, c)) {
+      for (int i = 0; i < nch; i++) px[i] = 0.0f;
+      return -1;
+    }
+    /* source_t::md_to_spline, :988-1006 */
+    float ix = (float)((double)c[0] - F->ext_x0);
+    ix /= F->ext_w;
+    ix *= (float)F->total_w;
+    ix -= .5f;
+    float iy = (float)((double)c[1] - F->ext_y0);
+    iy /= F->ext_h;
+    iy *= (float)F->total_h;
+    iy -= .5f;
+    spline_eval(s, s->degree, s->wmat, ix, iy, px);
+  } else {
+    float in_face[2], pk[2];
+    ray_to_cubeface(r, &face, in_face);
+    if (F->kind == KIND_BIATAN6) {
+      in_face[0] = (float)(4.0 / M_PI) * eu_atanf(in_face[0]);
+      in_face[1] = (float)(4.0 / M_PI) * eu_atanf(in_face[1]);
+    }
+    /* cubemap_view_t::get_pickup_coordinate_px, :1452-1461 (float members) */
+    pk[0] = in_face[0] + F->refc_md;
+    pk[1] = in_face[1] + F->refc_md;
+    pk[0] *= F->model_to_px;
+    pk[1] *= F->model_to_px;
+    pk[1] += (float)(face * F->section_px);
+    pk[0] -= .5f;
+    pk[1] -= .5f;
+    spline_eval(s, s->degree, s->wmat, pk[0], pk[1], px);
+  }
+  if (F->brighten != 1.0f) {
+    int ncol = (nch == 2 || nch == 4) ? nch - 1 : nch;
+    for (int i = 0; i < ncol; i++) px[i] *= F->brighten;
+  }
+  return face;
+}
+
+/* _hdr_merge_syn::get_quality, envutil_payload.cc:1390-1442 */
+static float hdr_quality(float grey, float optimum, int kind) {
+  int large = grey > optimum;
+  float distance = fabsf(optimum - grey);
+  if (kind == 0 && !large) distance = 0.0f;
+  if (kind == 2 && large) distance = 0.0f;
+  float proximity = optimum - distance;
+  return proximity / (optimum * optimum);
+}
+
+/* one synopsis evaluation for a set of per-facet rays: single facet, _voronoi_syn
+ * (envutil_payload.cc:818-956) or _hdr_merge_syn (:1500-1622) */
+static int synopsis(int mode, int nf, const facet_ctx* F, float (*rays)[3], int nch, float* px) {
+  if (mode == 0) return facet_eval(&F[0], rays[0], px);
+  if (mode == 1) {
+    int champion = -1;
+    float max_z = -FLT_MAX;
+    if (facet_mask(&F[0], rays[0])) {
+      champion = 0;
+      max_z = rays[0][2] * F[0].recip_step;
+    }
+    for (int i = 1; i < nf; i++) {
+      if (!facet_mask(&F[i], rays[i])) continue;
+      float cz = rays[i][2] * F[i].recip_step;
+      if (cz > max_z) {
+        max_z = cz;
+        champion = i;
+      }
+    }
+    if (champion < 0) {
+      for (int c = 0; c < nch; c++) px[c] = 0.0f;
+    } else {
+      facet_eval(&F[champion], rays[champion], px);
+    }
+    return champion;
+  }
+  /* hdr_merge, 1 or 3 channels */
+  float acc[4] = {0, 0, 0, 0}, qsum = 0.0f, p[4];
+  for (int i = 0; i < nf; i++) {
+    facet_eval(&F[i], rays[i], p);
+    float grey = nch == 1 ? p[0] : fmaxf(p[0], fmaxf(p[1], p[2]));
+    /* std::max(r, std::max(g,b)) returns its first argument on ties - same value */
+    float q = hdr_quality(grey, F[i].optimum, F[i].hdr_kind);
+    qsum += q;
+    for (int c = 0; c < nch; c++) acc[c] += p[c] * q;
+  }
+  for (int c = 0; c < nch; c++) {
+    acc[c] /= qsum;
+    if (!(qsum > 0.0f)) acc[c] = 0.0f;
+    px[c] = acc[c];
+  }
+  return -1;
+}
+
+static int facet_setup(const eu_target_t* t, const eu_opts_t* o, const eu_facet_t* f, const orc_source_t* src,
+                       facet_ctx* F) {
+  memset(F, 0, sizeof(*F));
+  F->src = src;
+  F->projection = f->projection;
+  F->kind = src->kind;
+  /* basis = R_camera * R_facet^-1, envutil_payload.cc:1923-1948 */
+  double cam[9], fct[9], m[9];
+  orc_rotation(t->roll, t->pitch, t->yaw, 0, cam);
+  orc_rotation(f->roll, f->pitch, f->yaw, 1, fct);
+  mat_mul(cam, fct, m);
+  for (int i = 0; i < 3; i++) {
+    F->xx[i] = (float)m[i];
+    F->yy[i] = (float)m[3 + i];
+    F->zz[i] = (float)m[6 + i];
+  }
+  double e[4];
+  orc_get_extent(f->projection, f->width, f->height, f->hfov, e);
+  F->ext_x0 = e[0];
+  F->ext_y0 = e[2];
+  F->ext_w = (float)(e[1] - e[0]);
+  F->ext_h = (float)(e[3] - e[2]);
+  F->total_w = f->width;
+  F->total_h = f->height;
+  { /* window extent for an uncropped image, environment.h:616-630 (y uses width, sic) */
+    double wx = e[1] - e[0], wy = e[3] - e[2];
+    double px1 = (double)f->width / f->width, py1 = (double)f->width / f->width;
+    F->win_x0 = (float)(e[0] + 0.0 * wx);
+    F->win_y0 = (float)(e[2] + 0.0 * wy);
+    F->win_x1 = (float)(e[0] + px1 * wx);
+    F->win_y1 = (float)(e[2] + py1 * wy);
+  }
+  F->mask_always = (src->kind != KIND_MOUNT) || (f->projection == EU_FISHEYE && f->hfov >= M_PI * 2.0);
+  /* process_geometry, envutil_basic.h:499-543 */
+  F->has_lcp = (f->a != 0.0 || f->b != 0.0 || f->c != 0.0);
+  F->has_shift = (f->h != 0.0 || f->v != 0.0);
+  F->has_shear = (f->shear_g != 0.0 || f->shear_t != 0.0);
+  {
+    double dv = fabs(e[3] - e[2]) / 2.0, dh = fabs(e[1] - e[0]) / 2.0;
+    double sref = dh < dv ? dh : dv;
+    double factor = fabs(e[1] - e[0]) / f->width;
+    float a = (float)f->a, b = (float)f->b, c = (float)f->c;
+    F->lcp[0] = a; F->lcp[1] = b; F->lcp[2] = c;
+    F->lcp[3] = 1.0f - (a + b + c);
+    F->lcp_s = (float)sref;
+    F->sh_h = (float)(f->h * factor);
+    F->sh_v = (float)(f->v * factor);
+    F->shear_g = f->shear_g;
+    F->shear_t = f->shear_t;
+  }
+  if (src->kind != KIND_MOUNT) {
+    F->refc_md = (float)src->cm.refc_md;
+    F->model_to_px = (float)src->cm.model_to_px;
+    F->section_px = src->cm.section_px;
+  }
+  double step = orc_get_step(f->projection, f->width, f->height, f->hfov);
+  F->recip_step = (float)(1.0 / step);
+  F->brighten = (float)(f->brighten == 0.0 ? 1.0 : f->brighten);
+  (void)o;
+  return 0;
+}
+
+int orc_render(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_t* facets,
+               orc_source_t* const* sources, const eu_tap_t* taps, int n_taps, int row0, int row1, float* out,
+               int32_t* index_out, int n_threads) {
+  if (nf < 1 || nf > 64) return EU_ERR_ARGUMENT;
+  target_ctx T;
+  target_setup(t, &T);
+  facet_ctx* F = (facet_ctx*)calloc((size_t)nf, sizeof(facet_ctx));
+  for (int i = 0; i < nf; i++) facet_setup(t, o, &facets[i], sources[i], &F[i]);
+  int nch = t->nchannels;
+  int mode = 0;
+  int first = 0;
+  if (nf > 1 && o->solo < 0) mode = (o->synopsis == EU_SYN_HDR_MERGE) ? 2 : 1;
+  if (nf > 1 && o->solo >= 0) first = o->solo;
+  /* normalize: envutil_payload.cc:2105,2118 (false: one facet, no twining), else true */
+  T.normalize = !(mode == 0 && n_taps == 0);
+  if (mode == 2) { /* _hdr_merge_syn ctor, :1354-1375 */
+    float lowest = 100000.0f, highest = -1.0f;
+    int lo = -1, hi = -1;
+    for (int i = 0; i < nf; i++) {
+      double br = (float)(facets[i].brighten == 0.0 ? 1.0 : facets[i].brighten);
+      F[i].optimum = (float)(0.5f * br);
+      if (br < lowest) { lowest = (float)br; lo = i; }
+      if (br > highest) { highest = (float)br; hi = i; }
+    }
+    for (int i = 0; i < nf; i++) F[i].hdr_kind = (i == lo) ? 0 : (i == hi) ? 2 : 1;
+  }
+  int nfe = mode == 0 ? 1 : nf;
+  const facet_ctx* FE = mode == 0 ? &F[first] : F;
+#ifdef _OPENMP
+  if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+  n_threads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads)
+  for (int y = row0; y < row1; y++) {
+    float rays[64][3], r10[64][3], r01[64][3], sub[64][3];
+    for (int x = 0; x < T.width; x++) {
+      float* px = out + ((size_t)(y - row0) * T.width + x) * nch;
+      float p0x = planar_x(&T, x, 0.0f), p0y = planar_y(&T, y, 0.0f);
+      int idx;
+      if (n_taps == 0) {
+        for (int i = 0; i < nfe; i++) stepper_ray(&T, &FE[i], p0x, p0y, x, y, 0.0f, rays[i]);
+        idx = synopsis(mode, nfe, FE, rays, nch, px);
+      } else {
+        /* deriv_stepper stepper.h:1606-1694; twine_t twining.h:106-263; synopsis_t
+         * envutil_payload.cc:647-690 */
+        float p1x = planar_x(&T, x, T.bias_x), p1y = planar_y(&T, y, T.bias_y);
+        for (int i = 0; i < nfe; i++) {
+          stepper_ray(&T, &FE[i], p0x, p0y, x, y, 0.0f, rays[i]);
+          stepper_ray(&T, &FE[i], p1x, p0y, x, y, T.bias_x, r10[i]);
+          stepper_ray(&T, &FE[i], p0x, p1y, x, y, 0.0f, r01[i]);
+        }
+        float acc[4] = {0, 0, 0, 0}, help[4];
+        idx = -1;
+        for (int k = 0; k < n_taps; k++) {
+          float cx = taps[k].x * 4.0f, cy = taps[k].y * 4.0f, cw = taps[k].w;
+          for (int i = 0; i < nfe; i++)
+            for (int c = 0; c < 3; c++) {
+              float du = r10[i][c] - rays[i][c], dv = r01[i][c] - rays[i][c];
+              sub[i][c] = rays[i][c] + cx * du + cy * dv;
+            }
+          int id = synopsis(mode, nfe, FE, sub, nch, help);
+          if (k == 0) idx = id;
+          for (int c = 0; c < nch; c++) acc[c] += cw * help[c];
+        }
+        for (int c = 0; c < nch; c++) px[c] = acc[c];
+      }
+      if (index_out) index_out[(size_t)(y - row0) * T.width + x] = idx;
+    }
+  }
+  free(F);
+  return 0;
+}
