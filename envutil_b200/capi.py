@@ -29,6 +29,7 @@ class Facet(C.Structure):
         ("x0", C.c_double), ("x1", C.c_double), ("y0", C.c_double), ("y1", C.c_double),
         ("step", C.c_double),
         ("s", C.c_double), ("d", C.c_double), ("r_max", C.c_double), ("cap_radius", C.c_double),
+        ("shift_h", C.c_double), ("shift_v", C.c_double),
         ("has_shift", C.c_int32), ("has_lcp", C.c_int32), ("has_shear", C.c_int32),
         ("has_2d_tf", C.c_int32), ("has_translation", C.c_int32),
         ("window_width", C.c_int32), ("window_height", C.c_int32),

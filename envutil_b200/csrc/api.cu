@@ -1,0 +1,741 @@
+// api.cu - device side of the C ABI (include/envutil_b200.h): source staging, the asset cache,
+// plan building and kernel launches. This is what a `cuda_dispatch : dispatch_base` adapter
+// calls in place of the reference's payload() body (envutil_payload.cc:2408-2436):
+//   eu_source_upload  ~ environment<...>(fct) construction     (envutil_payload.cc:1934,
+//                       environment.h:594-950 / cubemap.h:548-946,1147-1233)
+//   eu_render         ~ fuse<>() + work()                       (envutil_payload.cc:1885-2284,425-579)
+//   eu_cycle          ~ conclude_cycle()                        (environment.h:224, envutil_payload.cc:2433)
+// There is no CPU fallback: every entry point fails with EU_ERR_NO_DEVICE / EU_ERR_CUDA when
+// the GPU is not usable.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "bspline_consts.h"
+#include "envutil_b200.h"
+#include "host_setup.h"
+#include "kernels.h"
+#include "plan.h"
+
+struct eu_source {
+  std::string key;
+  int kind, projection, nch, degree;
+  int w, h;              // core
+  int cw, chh;           // container
+  int lx, ly, rx, ry;    // brace
+  int bc0, bc1;
+  float* container;      // device, cw*chh texels of `tstride` floats
+  int tstride;           // nch, or 4 for the padded RGB layout
+  eu_cubemap_metrics_t cm;
+  long last_used_cycle;
+  int refs;
+};
+
+namespace {
+
+struct Context {
+  bool up = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<eu_source*> sources;
+  std::map<std::string, eu_source*> by_key;
+  long cycle = 0;
+  // per-job scratch, grown on demand
+  float* d_wmat = nullptr;  // 8 matrices, degree d at offset 64*d, packed (d+1)x(d+1)
+  float* d_planar = nullptr;
+  size_t planar_cap = 0;
+  TargetDev planar_for;
+  bool planar_valid = false;
+  FacetDev* d_facets = nullptr;
+  int facets_cap = 0;
+  float* d_taps = nullptr;
+  int taps_cap = 0;
+  float* d_out = nullptr;
+  size_t out_cap = 0;
+  int32_t* d_index = nullptr;
+  size_t index_cap = 0;
+};
+Context g;
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return fail(EU_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int need_up() {
+  if (!g.up) return fail(EU_ERR_STATE, "eu_init has not been called");
+  return EU_OK;
+}
+
+template <typename T>
+int grow(T*& p, size_t& cap, size_t need) {
+  if (need <= cap) return EU_OK;
+  if (p) CK(cudaFree(p));
+  p = nullptr;
+  cap = 0;
+  CK(cudaMalloc(&p, need * sizeof(T)));
+  cap = need;
+  return EU_OK;
+}
+
+// get_left_brace_size / get_right_brace_size, zimt/bspline.h:305-372
+int left_brace(int degree, int bc) {
+  int b = degree / 2;
+  if (bc == EU_BC_REFLECT) b++;
+  else if (degree & 1) b++;
+  if (bc == EU_BC_PERIODIC && !(degree & 1)) b++;
+  return b;
+}
+int right_brace(int degree, int bc) {
+  int b = degree / 2;
+  if (bc == EU_BC_REFLECT && !(degree & 1)) b++;
+  if (degree & 1) b++;
+  if (bc == EU_BC_PERIODIC) b++;
+  return b;
+}
+
+// iir_filter ctor (zimt/recursive.h:774-862), overall gain (:93-103); everything is held in
+// long double and narrowed at use (:650-662). M: line length (decides which init formula runs).
+void iir_setup(IirDev& f, int bc, int degree, long double tolerance, int M) {
+  memset(&f, 0, sizeof(f));
+  f.bc = bc;
+  f.npoles = degree / 2;
+  long double lambda = 1.0L;
+  for (int k = 0; k < f.npoles; k++) {
+    long double p = eu_bspline_poles[degree][k];
+    f.pole[k] = (float)p;
+    f.horizon[k] = tolerance > 0 ? (int)ceill(logl(tolerance) / logl(fabsl(p))) : INT_MAX;
+    lambda *= (1.0L - p) * (1.0L - 1.0L / p);
+    long double e = (bc == EU_BC_REFLECT) ? (long double)(2 * M) : (long double)(M - 1);
+    f.pole_pow[k] = (float)powl(p, e);
+  }
+  f.gain = (float)lambda;
+}
+
+bool is_full_sphere(const eu_facet_t* f) {  // environment.h:905-907
+  return f->projection == EU_SPHERICAL && fabs(f->hfov - 2.0 * M_PI) < .000001 && f->width == 2 * f->height;
+}
+
+void source_dev(const eu_source* s, SourceDev& d) {
+  d.tstride = s->tstride;
+  d.stride = s->cw * s->tstride;
+  d.core = s->container + (size_t)s->ly * d.stride + (size_t)s->lx * s->tstride;
+  d.nch = s->nch;
+  d.w = s->w;
+  d.h = s->h;
+  d.bc0 = s->bc0;
+  d.bc1 = s->bc1;
+  // limits of the safe evaluator's gates: -0.5 .. N-0.5 (zimt/bspline.h:233-286)
+  d.upper_x = (float)((long double)(s->w - 1) + 0.5L);
+  d.upper_y = (float)((long double)(s->h - 1) + 0.5L);
+}
+
+void free_source(eu_source* s) {
+  if (!s) return;
+  if (s->container) cudaFree(s->container);
+  if (!s->key.empty()) {
+    auto it = g.by_key.find(s->key);
+    if (it != g.by_key.end() && it->second == s) g.by_key.erase(it);
+  }
+  for (size_t i = 0; i < g.sources.size(); i++)
+    if (g.sources[i] == s) {
+      g.sources.erase(g.sources.begin() + i);
+      break;
+    }
+  delete s;
+}
+
+bool known_source(eu_source_h s) {
+  for (auto p : g.sources)
+    if (p == s) return true;
+  return false;
+}
+
+// facet -> FacetDev: what source_t / mount_t / cubemap_view_t / environment hold
+// (environment.h:594-645,970-1006,1428-1461,1786-1860), narrowed as the functors narrow it
+int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, FacetDev& F) {
+  memset(&F, 0, sizeof(F));
+  if (s->projection != f->projection || s->nch != f->nchannels ||
+      (s->kind == EU_SRC_MOUNT && (s->w != f->width || s->h != f->height)))
+    return fail(EU_ERR_ARGUMENT, "facet description does not match its staged source");
+  source_dev(s, F.src);
+  F.kind = s->kind;
+  F.projection = f->projection;
+  double m[9];
+  eu_facet_basis(t, f, m);
+  for (int i = 0; i < 3; i++) {
+    F.xx[i] = (float)m[i];
+    F.yy[i] = (float)m[3 + i];
+    F.zz[i] = (float)m[6 + i];
+  }
+  F.ext_x0 = f->x0;
+  F.ext_y0 = f->y0;
+  F.ext_w = (float)(f->x1 - f->x0);
+  F.ext_h = (float)(f->y1 - f->y0);
+  F.total_w = (float)f->width;
+  F.total_h = (float)f->height;
+  {  // window extent of an uncropped image, environment.h:616-630 (cropped facets are refused
+     // at upload): x0 + (window_width / total_width) * (x1 - x0), in double, narrowed for the
+     // float compares of test_crd (:970-978)
+    double wx = f->x1 - f->x0, wy = f->y1 - f->y0;
+    double p1 = (double)f->width / f->width;
+    F.win_x0 = (float)(f->x0 + 0.0 * wx);
+    F.win_y0 = (float)(f->y0 + 0.0 * wy);
+    F.win_x1 = (float)(f->x0 + p1 * wx);
+    F.win_y1 = (float)(f->y0 + p1 * wy);
+  }
+  F.mask_always = (s->kind != EU_SRC_MOUNT) || (f->projection == EU_FISHEYE && f->hfov >= M_PI * 2.0);
+  F.has_lcp = f->has_lcp;
+  F.has_shift = f->has_shift;
+  F.has_shear = f->has_shear;
+  float a = (float)f->a, b = (float)f->b, c = (float)f->c;
+  F.lcp[0] = a;
+  F.lcp[1] = b;
+  F.lcp[2] = c;
+  F.lcp[3] = 1.0f - (a + b + c);
+  F.lcp_s = (float)f->s;
+  F.shift_h = (float)f->shift_h;
+  F.shift_v = (float)f->shift_v;
+  F.shear_g = f->shear_g;
+  F.shear_t = f->shear_t;
+  if (s->kind != EU_SRC_MOUNT) {
+    F.refc_md = (float)s->cm.refc_md;
+    F.model_to_px = (float)s->cm.model_to_px;
+    F.section_px = s->cm.section_px;
+  }
+  F.recip_step = (float)(1.0 / f->step);
+  F.brighten = (float)(f->brighten == 0.0 ? 1.0 : f->brighten);
+  F.hdr_optimum = 0.0f;
+  F.hdr_kind = EU_HDR_MIDDLE;
+  return EU_OK;
+}
+
+// stepper_base ctor, stepper.h:294-306 (extents narrowed to float first, factors in double)
+void target_dev(const eu_target_t* t, bool normalize, TargetDev& T) {
+  memset(&T, 0, sizeof(T));
+  int w = t->width, h = t->height;
+  float a0 = (float)t->x0, a1 = (float)t->x1, b0 = (float)t->y0, b1 = (float)t->y1;
+  T.projection = t->projection;
+  T.width = w;
+  T.height = h;
+  T.normalize = normalize;
+  T.fx1 = (float)(a1 / (2.0 * w));
+  T.fx0 = (float)(a0 / (2.0 * w));
+  T.fy1 = (float)(b1 / (2.0 * h));
+  T.fy0 = (float)(b0 / (2.0 * h));
+  T.bias_x = .25f * (a1 - a0) / (float)w;
+  T.bias_y = .25f * (b1 - b0) / (float)h;
+  T.delta = (float)EU_LANES * (a1 - a0) / (float)w;
+  T.section_md = a1 - a0;
+  T.refc_md = (float)((a1 - a0) / 2.0);
+}
+
+struct Plan {
+  RenderParams P;
+  int launches;
+};
+
+// builds the plan and uploads the per-job tables; everything is enqueued on g.stream
+int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_t* facets,
+               const eu_source_h* sources, const eu_tap_t* taps, int n_taps, Plan& plan) {
+  if (!t || !o || !facets || !sources) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (nf < 1 || nf > EU_MAX_FACETS) return fail(EU_ERR_ARGUMENT, "facet count %d out of range 1..%d", nf, EU_MAX_FACETS);
+  if (n_taps < 0 || n_taps > EU_MAX_TAPS) return fail(EU_ERR_ARGUMENT, "tap count %d out of range", n_taps);
+  if (n_taps > 0 && !taps) return fail(EU_ERR_ARGUMENT, "taps missing");
+  if (t->width <= 0 || t->height <= 0) return fail(EU_ERR_ARGUMENT, "target not prepared");
+  if (o->spline_degree < 0 || o->spline_degree > EU_MAX_DEGREE)
+    return fail(EU_ERR_ARGUMENT, "spline degree %d out of range 0..%d", o->spline_degree, EU_MAX_DEGREE);
+  int nch = t->nchannels;
+  if (nch != 1 && nch != 3 && nch != 4)
+    return fail(EU_ERR_UNSUPPORTED, "%d-channel targets are not supported (1, 3, 4 are)", nch);
+  for (int i = 0; i < nf; i++) {
+    if (!known_source(sources[i])) return fail(EU_ERR_ARGUMENT, "source %d is not a live handle", i);
+    if (sources[i]->nch != nch)
+      return fail(EU_ERR_UNSUPPORTED, "facet %d has %d channels, target %d: channel adaptation (repix_t) is not built", i,
+                  sources[i]->nch, nch);
+    if (sources[i]->degree != o->spline_degree)
+      return fail(EU_ERR_ARGUMENT, "source %d was staged for degree %d, job asks for %d", i, sources[i]->degree,
+                  o->spline_degree);
+    if (facets[i].has_translation)
+      return fail(EU_ERR_UNSUPPORTED, "facet %d: PanoTools translation (TrX/Y/Z) is not built", i);
+    sources[i]->last_used_cycle = g.cycle;
+  }
+  RenderParams& P = plan.P;
+  memset(&P, 0, sizeof(P));
+  plan.launches = 0;
+  int mode = EU_MODE_SINGLE, first = 0;
+  if (nf > 1 && o->solo < 0) mode = (o->synopsis == EU_SYN_HDR_MERGE) ? EU_MODE_HDR : EU_MODE_VORONOI;
+  if (nf > 1 && o->solo >= 0) {
+    if (o->solo >= nf) return fail(EU_ERR_ARGUMENT, "solo %d >= facet count %d", o->solo, nf);
+    first = o->solo;
+  }
+  if (mode == EU_MODE_HDR && nch == 4) return fail(EU_ERR_UNSUPPORTED, "hdr_merge of RGBA facets is not built");
+  // normalize: envutil_payload.cc:2105,2118 (false for one facet without twining), else true
+  target_dev(t, !(mode == EU_MODE_SINGLE && n_taps == 0), P.trg);
+  P.mode = mode;
+  P.degree = o->spline_degree;
+  P.n_taps = n_taps;
+  P.nch = nch;
+  std::vector<FacetDev> F(nf);
+  for (int i = 0; i < nf; i++) {
+    int rc = facet_dev(t, &facets[i], sources[i], F[i]);
+    if (rc) return rc;
+  }
+  if (mode == EU_MODE_HDR) {  // _hdr_merge_syn ctor, envutil_payload.cc:1354-1375
+    float lowest = 100000.0f, highest = -1.0f;
+    int lo = -1, hi = -1;
+    for (int i = 0; i < nf; i++) {
+      double br = (float)(facets[i].brighten == 0.0 ? 1.0 : facets[i].brighten);
+      F[i].hdr_optimum = (float)(0.5f * br);
+      if (br < lowest) { lowest = (float)br; lo = i; }
+      if (br > highest) { highest = (float)br; hi = i; }
+    }
+    for (int i = 0; i < nf; i++) F[i].hdr_kind = (i == lo) ? EU_HDR_LOW : (i == hi) ? EU_HDR_HIGH : EU_HDR_MIDDLE;
+  }
+  P.f0 = F[first];
+  P.n_facets = mode == EU_MODE_SINGLE ? 1 : nf;
+  if (mode != EU_MODE_SINGLE) {
+    if (nf > g.facets_cap) {
+      if (g.d_facets) CK(cudaFree(g.d_facets));
+      g.d_facets = nullptr;
+      g.facets_cap = 0;
+      CK(cudaMalloc(&g.d_facets, sizeof(FacetDev) * EU_MAX_FACETS));
+      g.facets_cap = EU_MAX_FACETS;
+    }
+    CK(cudaMemcpyAsync(g.d_facets, F.data(), sizeof(FacetDev) * nf, cudaMemcpyHostToDevice, g.stream));
+    P.facets = g.d_facets;
+  }
+  if (n_taps > 0) {
+    if (n_taps > g.taps_cap) {
+      if (g.d_taps) CK(cudaFree(g.d_taps));
+      g.d_taps = nullptr;
+      g.taps_cap = 0;
+      CK(cudaMalloc(&g.d_taps, sizeof(float) * 3 * EU_MAX_TAPS));
+      g.taps_cap = EU_MAX_TAPS;
+    }
+    std::vector<float> tp(3 * (size_t)n_taps);
+    for (int k = 0; k < n_taps; k++) {  // bias 4 = 1/0.25, twining.h:106-121
+      tp[3 * k] = taps[k].x * 4.0f;
+      tp[3 * k + 1] = taps[k].y * 4.0f;
+      tp[3 * k + 2] = taps[k].w;
+    }
+    CK(cudaMemcpyAsync(g.d_taps, tp.data(), sizeof(float) * tp.size(), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaStreamSynchronize(g.stream));  // tp goes out of scope
+    P.taps = g.d_taps;
+  }
+  // planar tables: recomputed only when the target changes
+  size_t need = 2 * (size_t)(t->width + t->height);
+  if (!g.planar_valid || memcmp(&g.planar_for, &P.trg, sizeof(TargetDev)) != 0 || need > g.planar_cap) {
+    TargetDev key = P.trg;
+    CK(cudaDeviceSynchronize());  // nothing in flight may still read the old tables
+    int rc = grow(g.d_planar, g.planar_cap, need);
+    if (rc) return rc;
+    CK(eu_launch_planar_tables(P.trg, g.d_planar, g.d_planar + 2 * (size_t)t->width, g.stream));
+    plan.launches++;
+    g.planar_for = key;
+    g.planar_valid = true;
+  }
+  // normalize is part of TargetDev but does not change the tables; keep the key exact anyway
+  P.planar_x = g.d_planar;
+  P.planar_y = g.d_planar + 2 * (size_t)t->width;
+  P.wmat = g.d_wmat + 64 * o->spline_degree;
+  return EU_OK;
+}
+
+int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixels, cudaStream_t st, eu_source* s,
+                    int* launches) {
+  int degree = o->spline_degree;
+  int pdeg = o->prefilter_degree < 0 ? degree : o->prefilter_degree;
+  if (pdeg > EU_MAX_DEGREE) return fail(EU_ERR_ARGUMENT, "prefilter degree %d out of range", pdeg);
+  int nch = f->nchannels;
+  s->projection = f->projection;
+  s->nch = nch;
+  s->degree = degree;
+  s->tstride = nch;
+  *launches = 0;
+  size_t tb = sizeof(float) * nch;
+  if (f->projection == EU_CUBEMAP || f->projection == EU_BIATAN6) {
+    // cubemap_t ctor + load, cubemap.h:548-580,1147-1233
+    if (f->height != 6 * f->width) return fail(EU_ERR_ARGUMENT, "cubemap input must be 1:6 (got %dx%d)", f->width, f->height);
+    s->kind = f->projection == EU_CUBEMAP ? EU_SRC_CUBEMAP : EU_SRC_BIATAN6;
+    int rc = eu_compute_cubemap_metrics(f->width, f->hfov, o->support_min, o->tile_size, &s->cm);
+    if (rc) return fail(rc, "bad cubemap metrics (face %d px, hfov %g, support %d, tile %d)", f->width, f->hfov,
+                        o->support_min, o->tile_size);
+    int S = s->cm.section_px, Fpx = f->width, L = s->cm.left_frame_px, R = s->cm.right_frame_px;
+    s->w = s->cw = S;
+    s->h = s->chh = 6 * S;
+    s->lx = s->ly = s->rx = s->ry = 0;
+    s->bc0 = s->bc1 = EU_BC_REFLECT;
+    size_t n = (size_t)S * 6 * S * nch;
+    CK(cudaMalloc(&s->container, n * sizeof(float)));
+    CK(cudaMemsetAsync(s->container, 0, n * sizeof(float), st));
+    for (int face = 0; face < 6; face++)
+      CK(cudaMemcpy2DAsync(s->container + ((size_t)(face * S + L) * S + L) * nch, (size_t)S * tb,
+                           d_pixels + (size_t)face * Fpx * Fpx * nch, (size_t)Fpx * tb, (size_t)Fpx * tb, Fpx,
+                           cudaMemcpyDeviceToDevice, st));
+    int nl = 0;
+    CK(eu_launch_cubemap_support(s->container, nch, Fpx, S, L, R, s->cm.refc_md, s->cm.model_to_px, &nl, st));
+    *launches += nl;
+    if (pdeg > 1) {  // cubemap_t::prefilter, cubemap.h:921-946: per section, NATURAL, both axes
+      IirDev fx;
+      iir_setup(fx, EU_BC_NATURAL, pdeg, (long double)FLT_EPSILON, S);
+      CK(eu_launch_iir_x(s->container, S * nch, nch, S, 6 * S, fx, st));
+      CK(eu_launch_iir_y(s->container, S * nch, nch, S, S, 6, fx, st));
+      *launches += 2;
+    }
+    return EU_OK;
+  }
+  // source_t ctor, environment.h:594-950
+  s->kind = EU_SRC_MOUNT;
+  s->w = f->width;
+  s->h = f->height;
+  s->bc0 = s->bc1 = EU_BC_REFLECT;
+  if ((f->projection == EU_SPHERICAL || f->projection == EU_CYLINDRICAL) && fabs(f->hfov - 2.0 * M_PI) < .000001)
+    s->bc0 = EU_BC_PERIODIC;
+  s->lx = left_brace(degree, s->bc0);
+  s->ly = left_brace(degree, s->bc1);
+  s->rx = right_brace(degree, s->bc0);
+  s->ry = right_brace(degree, s->bc1);
+  s->cw = s->w + s->lx + s->rx;
+  s->chh = s->h + s->ly + s->ry;
+  size_t n = (size_t)s->cw * s->chh * nch;
+  CK(cudaMalloc(&s->container, n * sizeof(float)));
+  int stride = s->cw * nch;
+  float* core = s->container + (size_t)s->ly * stride + (size_t)s->lx * nch;
+  CK(cudaMemcpy2DAsync(core, (size_t)stride * sizeof(float), d_pixels, (size_t)s->w * tb, (size_t)s->w * tb, s->h,
+                       cudaMemcpyDeviceToDevice, st));
+  bool sphere = is_full_sphere(f);
+  if (sphere && (s->ly > s->h || s->ry > s->h)) return fail(EU_ERR_ARGUMENT, "image too small for its brace");
+  if (pdeg > 1) {
+    IirDev fx, fy;
+    if (sphere) {  // spherical_prefilter, environment.h:356-522 (tolerance 1e-4)
+      iir_setup(fx, EU_BC_PERIODIC, pdeg, (long double)0.0001, s->w);
+      iir_setup(fy, EU_BC_PERIODIC, pdeg, (long double)0.0001, 2 * s->h);
+      CK(eu_launch_iir_x(core, stride, nch, s->w, s->h, fx, st));
+      CK(eu_launch_iir_y_spherical(core, stride, nch, s->w, s->h, fy, st));
+    } else {  // zimt::prefilter, prefilter.h:125-198
+      iir_setup(fx, s->bc0, pdeg, (long double)FLT_EPSILON, s->w);
+      iir_setup(fy, s->bc1, pdeg, (long double)FLT_EPSILON, s->h);
+      CK(eu_launch_iir_x(core, stride, nch, s->w, s->h, fx, st));
+      CK(eu_launch_iir_y(core, stride, nch, s->w, s->h, 1, fy, st));
+    }
+    *launches += 2;
+  }
+  CK(eu_launch_brace(core, stride, nch, s->w, s->h, s->lx, s->rx, s->ly, s->ry, s->bc0, s->bc1, sphere ? 1 : 0, st));
+  *launches += 1;
+  return EU_OK;
+}
+
+// optional 16-byte texel layout for RGB sources (o->reserved[0] == 1): one LDG.128 per tap
+int maybe_pad(const eu_opts_t* o, eu_source* s, cudaStream_t st, int* launches) {
+  if (o->reserved[0] != 1 || s->nch != 3) return EU_OK;
+  size_t ntex = (size_t)s->cw * s->chh;
+  float* padded = nullptr;
+  CK(cudaMalloc(&padded, ntex * 4 * sizeof(float)));
+  cudaError_t e = eu_launch_pad_texels(s->container, padded, ntex, s->nch, st);
+  if (e != cudaSuccess) {
+    cudaFree(padded);
+    return fail(EU_ERR_CUDA, "pad kernel: %s", cudaGetErrorString(e));
+  }
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(s->container));
+  s->container = padded;
+  s->tstride = 4;
+  ++*launches;
+  return EU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* eu_last_error(void) { return g_err; }
+
+int eu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int eu_init(int device_id) {
+  if (g.up) {
+    if (device_id == g.device) return EU_OK;
+    return fail(EU_ERR_STATE, "already initialised on device %d", g.device);
+  }
+  int n = eu_device_count();
+  if (n <= 0) return fail(EU_ERR_NO_DEVICE, "no CUDA device is visible");
+  if (device_id < 0 || device_id >= n) return fail(EU_ERR_ARGUMENT, "device %d out of range 0..%d", device_id, n - 1);
+  CK(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major < 10)
+    return fail(EU_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device_id, prop.major,
+                prop.minor);
+  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  for (auto& e : g.ev) CK(cudaEventCreate(&e));
+  std::vector<float> wm(8 * 64, 0.0f);
+  for (int d = 0; d <= EU_MAX_DEGREE; d++)
+    for (int row = 0; row <= d; row++)
+      for (int k = 0; k <= d; k++) wm[64 * d + row * (d + 1) + k] = (float)eu_bspline_weights[d][row][k];
+  CK(cudaMalloc(&g.d_wmat, wm.size() * sizeof(float)));
+  CK(cudaMemcpy(g.d_wmat, wm.data(), wm.size() * sizeof(float), cudaMemcpyHostToDevice));
+  g.device = device_id;
+  g.up = true;
+  g.planar_valid = false;
+  return EU_OK;
+}
+
+void eu_shutdown(void) {
+  if (!g.up) return;
+  cudaStreamSynchronize(g.stream);
+  while (!g.sources.empty()) free_source(g.sources.back());
+  cudaFree(g.d_wmat);
+  cudaFree(g.d_planar);
+  cudaFree(g.d_facets);
+  cudaFree(g.d_taps);
+  cudaFree(g.d_out);
+  cudaFree(g.d_index);
+  for (auto& e : g.ev) cudaEventDestroy(e);
+  cudaStreamDestroy(g.stream);
+  g = Context();
+}
+
+int eu_source_upload_device(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* d_pixels,
+                            void* cuda_stream, eu_source_h* out, eu_timing_t* t) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!f || !o || !d_pixels || !out) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (f->width <= 0 || f->height <= 0 || f->nchannels < 1 || f->nchannels > 4 || f->nchannels == 2)
+    return fail(EU_ERR_ARGUMENT, "bad raster description %dx%dx%d", f->width, f->height, f->nchannels);
+  if (o->spline_degree < 0 || o->spline_degree > EU_MAX_DEGREE)
+    return fail(EU_ERR_ARGUMENT, "spline degree %d out of range", o->spline_degree);
+  if (f->window_width != f->width || f->window_height != f->height)
+    return fail(EU_ERR_UNSUPPORTED, "cropped facets (W/h window) are not built");
+  cudaStream_t caller = (cudaStream_t)cuda_stream;
+  cudaStream_t st = g.stream;
+  // order our stream after the caller's work on d_pixels
+  CK(cudaEventRecord(g.ev[2], caller));
+  CK(cudaStreamWaitEvent(st, g.ev[2], 0));
+  eu_source* s = new eu_source();
+  s->container = nullptr;
+  s->last_used_cycle = g.cycle;
+  s->refs = 1;
+  int launches = 0;
+  CK(cudaEventRecord(g.ev[0], st));
+  rc = stage_on_device(f, o, d_pixels, st, s, &launches);
+  if (rc == EU_OK) rc = maybe_pad(o, s, st, &launches);
+  if (rc != EU_OK) {
+    if (s->container) cudaFree(s->container);
+    delete s;
+    return rc;
+  }
+  CK(cudaEventRecord(g.ev[1], st));
+  CK(cudaStreamSynchronize(st));
+  if (t) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+    t->render_ms = ms;
+    t->h2d_ms = t->d2h_ms = 0;
+    t->launches = launches;
+    t->reserved = 0;
+  }
+  g.sources.push_back(s);
+  if (asset_key && *asset_key) {
+    s->key = asset_key;
+    auto it = g.by_key.find(s->key);
+    if (it != g.by_key.end()) {  // replaced: the old object stays alive until released / aged out
+      it->second->key.clear();
+      it->second = s;
+    } else {
+      g.by_key[s->key] = s;
+    }
+  }
+  *out = s;
+  return EU_OK;
+}
+
+int eu_source_upload(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
+                     eu_source_h* out, eu_timing_t* t) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!f || !pixels) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (f->width <= 0 || f->height <= 0 || f->nchannels < 1 || f->nchannels > 4)
+    return fail(EU_ERR_ARGUMENT, "bad raster description");
+  size_t n = (size_t)f->width * f->height * f->nchannels;
+  float* d_raw = nullptr;
+  CK(cudaMalloc(&d_raw, n * sizeof(float)));
+  cudaEventRecord(g.ev[2], g.stream);
+  cudaError_t e = cudaMemcpyAsync(d_raw, pixels, n * sizeof(float), cudaMemcpyHostToDevice, g.stream);
+  cudaEventRecord(g.ev[3], g.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  if (e != cudaSuccess) {
+    cudaFree(d_raw);
+    return fail(EU_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+  }
+  float h2d = 0;
+  cudaEventElapsedTime(&h2d, g.ev[2], g.ev[3]);
+  rc = eu_source_upload_device(asset_key, f, o, d_raw, g.stream, out, t);
+  cudaFree(d_raw);
+  if (rc == EU_OK && t) t->h2d_ms = h2d;
+  return rc;
+}
+
+eu_source_h eu_source_find(const char* asset_key) {
+  if (!g.up || !asset_key) return nullptr;
+  auto it = g.by_key.find(asset_key);
+  if (it == g.by_key.end()) return nullptr;
+  it->second->last_used_cycle = g.cycle;
+  return it->second;
+}
+
+int eu_source_release(eu_source_h s) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!known_source(s)) return fail(EU_ERR_ARGUMENT, "not a live source handle");
+  CK(cudaStreamSynchronize(g.stream));
+  free_source(s);
+  return EU_OK;
+}
+
+// asset_handler_t::conclude_cycle, environment.h:200-227: keyed assets that were not used in
+// the cycle that ends now are dropped; unkeyed sources belong to the caller.
+int eu_cycle(void) {
+  int rc = need_up();
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(g.stream));
+  std::vector<eu_source*> drop;
+  for (auto s : g.sources)
+    if (!s->key.empty() && s->last_used_cycle < g.cycle) drop.push_back(s);
+  for (auto s : drop) free_source(s);
+  g.cycle++;
+  return EU_OK;
+}
+
+size_t eu_source_container_floats(eu_source_h s, int32_t shape[4]) {
+  if (!g.up || !known_source(s)) return 0;
+  if (shape) {
+    shape[0] = s->cw;
+    shape[1] = s->chh;
+    shape[2] = s->lx;
+    shape[3] = s->ly;
+  }
+  return (size_t)s->cw * s->chh * s->nch;
+}
+
+int eu_source_download(eu_source_h s, float* out) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!known_source(s) || !out) return fail(EU_ERR_ARGUMENT, "bad argument");
+  CK(cudaStreamSynchronize(g.stream));
+  size_t ntex = (size_t)s->cw * s->chh;
+  if (s->tstride == s->nch) {
+    CK(cudaMemcpy(out, s->container, ntex * s->nch * sizeof(float), cudaMemcpyDeviceToHost));
+  } else {  // padded layout: strip the padding
+    CK(cudaMemcpy2D(out, s->nch * sizeof(float), s->container, s->tstride * sizeof(float), s->nch * sizeof(float), ntex,
+                    cudaMemcpyDeviceToHost));
+  }
+  return EU_OK;
+}
+
+int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+                   const eu_source_h* sources, const eu_tap_t* taps, int n_taps, int row0, int row1, float* d_out,
+                   void* cuda_stream, eu_timing_t* timing) {
+  int rc = need_up();
+  if (rc) return rc;
+  Plan plan;
+  rc = build_plan(t, o, n_facets, facets, sources, taps, n_taps, plan);
+  if (rc) return rc;
+  if (row0 < 0 || row1 > t->height || row0 >= row1) return fail(EU_ERR_ARGUMENT, "bad row band [%d,%d)", row0, row1);
+  if (!d_out) return fail(EU_ERR_ARGUMENT, "null output");
+  cudaStream_t caller = (cudaStream_t)cuda_stream;
+  // tables were enqueued on the library stream; the render runs on the caller's stream
+  CK(cudaEventRecord(g.ev[2], g.stream));
+  CK(cudaStreamWaitEvent(caller, g.ev[2], 0));
+  plan.P.row0 = row0;
+  plan.P.row1 = row1;
+  plan.P.out = d_out;
+  plan.P.index_out = nullptr;
+  if (timing) CK(cudaEventRecord(g.ev[0], caller));
+  CK(eu_launch_render(plan.P, caller));
+  plan.launches++;
+  if (timing) {
+    CK(cudaEventRecord(g.ev[1], caller));
+    CK(cudaEventSynchronize(g.ev[1]));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+    timing->render_ms = ms;
+    timing->h2d_ms = timing->d2h_ms = 0;
+    timing->launches = plan.launches;
+    timing->reserved = 0;
+  }
+  return EU_OK;
+}
+
+int eu_render(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+              const eu_source_h* sources, const eu_tap_t* taps, int n_taps, float* out, eu_timing_t* timing) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!t || !out) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (t->width <= 0 || t->height <= 0 || t->nchannels < 1) return fail(EU_ERR_ARGUMENT, "target not prepared");
+  size_t n = (size_t)t->width * t->height * t->nchannels;
+  rc = grow(g.d_out, g.out_cap, n);
+  if (rc) return rc;
+  eu_timing_t tm;
+  rc = eu_render_rows(t, o, n_facets, facets, sources, taps, n_taps, 0, t->height, g.d_out, g.stream, &tm);
+  if (rc) return rc;
+  CK(cudaEventRecord(g.ev[2], g.stream));
+  CK(cudaMemcpyAsync(out, g.d_out, n * sizeof(float), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaEventRecord(g.ev[3], g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  if (timing) {
+    *timing = tm;
+    CK(cudaEventElapsedTime(&timing->d2h_ms, g.ev[2], g.ev[3]));
+  }
+  return EU_OK;
+}
+
+int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+                    const eu_source_h* sources, int32_t* index_out) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!t || !index_out) return fail(EU_ERR_ARGUMENT, "null argument");
+  Plan plan;
+  rc = build_plan(t, o, n_facets, facets, sources, nullptr, 0, plan);
+  if (rc) return rc;
+  size_t n = (size_t)t->width * t->height;
+  rc = grow(g.d_index, g.index_cap, n);
+  if (rc) return rc;
+  plan.P.row0 = 0;
+  plan.P.row1 = t->height;
+  plan.P.out = nullptr;
+  plan.P.index_out = g.d_index;
+  CK(eu_launch_render(plan.P, g.stream));
+  CK(cudaMemcpyAsync(index_out, g.d_index, n * sizeof(int32_t), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return EU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,433 @@
+// eu_device.cuh - per-pixel device functions of the reprojection pipeline (sm_100a).
+//
+// Every function restates one functor of the reference in scalar form, one thread per target
+// pixel, with the reference's operation order and C-style promotions (float-vector op
+// double-scalar is evaluated in double and narrowed, zimt/common.h:278). The translation unit
+// is compiled with -fmad=false so that no multiply-add is contracted; the only fused
+// operations are the explicit fmaf/fma calls inside include/eu_math.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "envutil_b200.h"
+#include "eu_math.h"
+#include "plan.h"
+
+#define EU_PI_2 1.57079632679489661923
+#define EU_PI 3.14159265358979323846
+
+enum { CM_LEFT = 0, CM_RIGHT = 1, CM_TOP = 2, CM_BOTTOM = 3, CM_FRONT = 4, CM_BACK = 5 };
+
+__device__ __forceinline__ float dev_norm3(const float v[3]) {  // zimt/xel.h:752-765
+  float sqn = v[0] * v[0];
+  sqn += v[1] * v[1];
+  sqn += v[2] * v[2];
+  return sqrtf(sqn);
+}
+
+// ------------------------------------------------------------------------------------------
+// target side: the seven steppers (stepper.h:517-1578). px,py: planar coordinate of this
+// pixel; px_first: planar x of the same lane in the first vector of the pixel's 512-px
+// segment (the cylindrical stepper keeps rcp_length from there, stepper.h:766-769).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dev_stepper(const TargetDev& T, const float* xx, const float* yy,
+                                            const float* zz, float px, float py, float px_first, int y,
+                                            float ray[3]) {
+  switch (T.projection) {
+    case EU_SPHERICAL: {
+      float sy, r, sx, z;
+      eu_sincosf(py, &sy, &r);
+      eu_sincosf(px, &sx, &z);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float xxx = xx[i] * r, yyy = yy[i] * sy, zzz = zz[i] * r;
+        ray[i] = xxx * sx + zzz * z + yyy;
+      }
+      break;
+    }
+    case EU_CYLINDRICAL: {
+      float sx, z;
+      eu_sincosf(px, &sx, &z);
+#pragma unroll
+      for (int i = 0; i < 3; i++) ray[i] = xx[i] * sx + zz[i] * z + yy[i] * py;
+      if (T.normalize) {
+        float s0, z0, first[3];
+        eu_sincosf(px_first, &s0, &z0);
+#pragma unroll
+        for (int i = 0; i < 3; i++) first[i] = xx[i] * s0 + zz[i] * z0 + yy[i] * py;
+        float rcp = 1.0f / dev_norm3(first);
+#pragma unroll
+        for (int i = 0; i < 3; i++) ray[i] *= rcp;
+      }
+      break;
+    }
+    case EU_RECTILINEAR: {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float ddd = yy[i] * py + zz[i];
+        ray[i] = xx[i] * px + ddd;
+      }
+      if (T.normalize) {
+        float n = dev_norm3(ray);
+#pragma unroll
+        for (int i = 0; i < 3; i++) ray[i] /= n;
+      }
+      break;
+    }
+    case EU_FISHEYE:
+    case EU_STEREOGRAPHIC: {
+      float sqn = px * px;
+      sqn += py * py;
+      float nrm = sqrtf(sqn);
+      float a;
+      if (T.projection == EU_FISHEYE)
+        a = (float)(EU_PI_2 - (double)nrm);  // stepper.h:1019-1021
+      else
+        a = (float)(EU_PI_2 - 2.0 * eu_atan((double)nrm / 2.0));  // stepper.h:1146-1148
+      float b = eu_atan2f(px, py);
+      float z, r, sx, cy;
+      eu_sincosf(a, &z, &r);
+      eu_sincosf(b, &sx, &cy);
+#pragma unroll
+      for (int i = 0; i < 3; i++) ray[i] = xx[i] * r * sx + zz[i] * z + yy[i] * r * cy;
+      break;
+    }
+    default: {  // EU_CUBEMAP, EU_BIATAN6 (stepper.h:1289-1345,1478-1560)
+      int face = y / T.width;
+      float p1 = py + (3 - face) * T.section_md - T.refc_md;
+      float p0 = px;
+      if (T.projection == EU_BIATAN6) {
+        p1 = eu_tanf(p1 * (float)(EU_PI / 4.0));
+        p0 = eu_tanf(p0 * (float)(EU_PI / 4.0));
+      }
+      float ccc[3], vvv[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        // the +-1.0 literals promote the sums to double in the reference
+        switch (face) {
+          case CM_LEFT: ccc[i] = (float)(-1.0 * xx[i] + (double)(p1 * yy[i])); vvv[i] = zz[i]; break;
+          case CM_RIGHT: ccc[i] = (float)(1.0 * xx[i] + (double)(p1 * yy[i])); vvv[i] = -zz[i]; break;
+          case CM_TOP: ccc[i] = (float)(-1.0 * yy[i] - (double)(p1 * zz[i])); vvv[i] = -xx[i]; break;
+          case CM_BOTTOM: ccc[i] = (float)(1.0 * yy[i] + (double)(p1 * zz[i])); vvv[i] = -xx[i]; break;
+          case CM_FRONT: ccc[i] = (float)((double)(p1 * yy[i]) + 1.0 * zz[i]); vvv[i] = xx[i]; break;
+          default: ccc[i] = (float)((double)(p1 * yy[i]) - 1.0 * zz[i]); vvv[i] = -xx[i]; break;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) ray[i] = ccc[i] + p0 * vvv[i];
+      if (T.normalize) {
+        float n = dev_norm3(ray);
+#pragma unroll
+        for (int i = 0; i < 3; i++) ray[i] /= n;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// source side
+// ------------------------------------------------------------------------------------------
+
+// mount_t::get_coordinate_nomask (environment.h:1077-1110) over the ray_to_X functors
+// (geometry.h:277-534) and pto_planar's forward path (environment.h:254-283)
+__device__ __forceinline__ void dev_mount_coordinate(const FacetDev& F, const float r[3], float c[2]) {
+  switch (F.projection) {
+    case EU_RECTILINEAR:
+      c[0] = r[0] / r[2];
+      c[1] = r[1] / r[2];
+      break;
+    case EU_SPHERICAL: {
+      float s = sqrtf(r[0] * r[0] + r[2] * r[2]);
+      c[1] = eu_atan2f(r[1], s);
+      c[0] = eu_atan2f(r[0], r[2]);
+      break;
+    }
+    case EU_CYLINDRICAL: {
+      float s = sqrtf(r[0] * r[0] + r[2] * r[2]);
+      c[1] = r[1] / s;
+      c[0] = eu_atan2f(r[0], r[2]);
+      break;
+    }
+    case EU_STEREOGRAPHIC: {
+      float rn = 1.0f / sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+      float right = r[0] * rn, down = r[1] * rn, fwd = r[2] * rn;
+      float factor = 2.0f / (fwd + 1.0f);
+      c[0] = right * factor;
+      c[1] = down * factor;
+      break;
+    }
+    default: {  // EU_FISHEYE
+      float s = sqrtf(r[0] * r[0] + r[1] * r[1]);
+      float rr = (float)EU_PI_2 - eu_atan2f(r[2], s);
+      float phi = eu_atan2f(r[1], r[0]);
+      float sp, cp;
+      eu_sincosf(phi, &sp, &cp);
+      c[0] = rr * cp;
+      c[1] = rr * sp;
+    }
+  }
+  if (F.has_lcp) {
+    float sqn = c[0] * c[0];
+    sqn += c[1] * c[1];
+    float x = sqrtf(sqn) / F.lcp_s;
+    float sum = 0.0f, power = 1.0f;  // eu_polynomial::function, lens_correction.h:94-105
+#pragma unroll
+    for (int i = 0; i <= 3; i++) {
+      sum += F.lcp[3 - i] * power;
+      power *= x;
+    }
+    c[0] *= sum;
+    c[1] *= sum;
+    if (F.has_shift) {
+      c[0] += F.shift_h;
+      c[1] += F.shift_v;
+    }
+    if (F.has_shear) {
+      float h0 = (float)((double)c[0] + (double)c[1] * F.shear_g);
+      float h1 = (float)((double)c[1] + (double)c[0] * F.shear_t);
+      c[0] = h0;
+      c[1] = h1;
+    }
+  }
+}
+
+// source_t::test_crd (environment.h:970-978) + the z > 0 test of rectilinear mounts (:1123-1127)
+__device__ __forceinline__ bool dev_mount_mask(const FacetDev& F, const float r[3], const float c[2]) {
+  bool m = (c[0] >= F.win_x0) && (c[0] <= F.win_x1) && (c[1] >= F.win_y0) && (c[1] <= F.win_y1);
+  if (F.projection == EU_RECTILINEAR) m = m && (r[2] > 0.0f);
+  return m;
+}
+
+__device__ __forceinline__ bool dev_facet_mask(const FacetDev& F, const float r[3]) {
+  if (F.mask_always) return true;
+  float c[2];
+  dev_mount_coordinate(F, r, c);
+  return dev_mount_mask(F, r, c);
+}
+
+// coordinate gates, zimt/map.h (vector variants)
+__device__ __forceinline__ float dev_vfmod(float lhs, float rhs) {
+  float help = lhs;
+  help /= rhs;
+  help = truncf(help);
+  help *= rhs;
+  lhs -= help;
+  if (fabsf(lhs) >= fabsf(rhs)) lhs = 0.0f;
+  return lhs;
+}
+__device__ __forceinline__ float dev_gate(float c, int bc, float upper) {
+  const float lower = -0.5f;
+  float cc = c - lower;
+  float w = upper - lower;
+  if (bc == EU_BC_PERIODIC) {
+    bool below = cc < 0.0f, above = cc >= w;
+    if (below || above) {
+      float cm = dev_vfmod(cc, w);
+      if (below) cm = cm + w;
+      if (cm >= w) cm = 0.0f;
+      cc = cm;
+    }
+  } else {
+    cc = fabsf(cc);
+    if (cc >= w) {
+      float cm = dev_vfmod(cc, 2 * w);
+      cm -= w;
+      cm = fabsf(cm);
+      cm = w - cm;
+      cc = cm;
+    }
+  }
+  return cc + lower;
+}
+
+template <int NCH>
+__device__ __forceinline__ void dev_load_texel(const SourceDev& S, int x, int y, float v[NCH]) {
+  const float* p = S.core + (ptrdiff_t)y * S.stride + (ptrdiff_t)x * S.tstride;
+  if (NCH == 4 || (NCH == 3 && S.tstride == 4)) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x;
+    if (NCH > 1) v[1] = t.y;
+    if (NCH > 2) v[2] = t.z;
+    if (NCH > 3) v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCH; c++) v[c] = __ldg(p + c);
+  }
+}
+
+// b-spline weights for one axis: basis_functor::operator()(result, delta), zimt/basis.h:650-689
+template <int ORDER>
+__device__ __forceinline__ void dev_weights(const float* __restrict__ wmat, float delta, float w[ORDER]) {
+  float power = delta;
+#pragma unroll
+  for (int k = 0; k < ORDER; k++) w[k] = wmat[k];
+#pragma unroll
+  for (int row = 1; row < ORDER; row++) {
+#pragma unroll
+    for (int k = 0; k < ORDER; k++) w[k] += power * wmat[row * ORDER + k];
+    if (row < ORDER - 1) power *= delta;
+  }
+}
+
+// evaluator::eval for a fixed degree > 1: window sum in the reference's order
+// (zimt/eval.h:903-996), window offsets k - degree/2 (:732)
+template <int NCH, int DEG>
+__device__ __forceinline__ void dev_window_sum(const SourceDev& S, const float* __restrict__ wmat, int ix, int iy,
+                                               float fx, float fy, float out[NCH]) {
+  constexpr int ORDER = DEG + 1;
+  float wx[ORDER], wy[ORDER];
+  dev_weights<ORDER>(wmat, fx, wx);
+  dev_weights<ORDER>(wmat, fy, wy);
+  constexpr int H2 = DEG / 2;
+#pragma unroll
+  for (int j = 0; j < ORDER; j++) {
+    float sub[NCH], t[NCH];
+    dev_load_texel<NCH>(S, ix - H2, iy - H2 + j, sub);
+#pragma unroll
+    for (int c = 0; c < NCH; c++) sub[c] *= wx[0];
+#pragma unroll
+    for (int i = 1; i < ORDER; i++) {
+      dev_load_texel<NCH>(S, ix - H2 + i, iy - H2 + j, t);
+#pragma unroll
+      for (int c = 0; c < NCH; c++) sub[c] += wx[i] * t[c];
+    }
+    if (j == 0) {
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        out[c] = sub[c];
+        out[c] *= wy[0];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NCH; c++) out[c] += sub[c] * wy[j];
+    }
+  }
+}
+
+// safe evaluator = mapper + evaluator (zimt/eval.h:2039-2164, :1237-1300)
+template <int NCH>
+__device__ __forceinline__ void dev_spline_eval(const SourceDev& S, int degree, const float* __restrict__ wmat,
+                                                float cx, float cy, float out[NCH]) {
+  cx = dev_gate(cx, S.bc0, S.upper_x);
+  cy = dev_gate(cy, S.bc1, S.upper_y);
+  float fx, fy;
+  int ix, iy;
+  if (degree & 1) {  // odd_split / even_split, zimt/basis.h:102-146
+    float f = floorf(cx); fx = cx - f; ix = (int)f;
+    f = floorf(cy); fy = cy - f; iy = (int)f;
+  } else {
+    float f = roundf(cx); fx = cx - f; ix = (int)f;
+    f = roundf(cy); fy = cy - f; iy = (int)f;
+  }
+  switch (degree) {
+    case 0: dev_load_texel<NCH>(S, ix, iy, out); break;
+    case 1: {  // _eval_linear, zimt/eval.h:1004-1059
+      float wl0 = 1.0f - fx, wr0 = fx, wl1 = 1.0f - fy, wr1 = fy;
+      float p00[NCH], p10[NCH], p01[NCH], p11[NCH];
+      dev_load_texel<NCH>(S, ix, iy, p00);
+      dev_load_texel<NCH>(S, ix + 1, iy, p10);
+      dev_load_texel<NCH>(S, ix, iy + 1, p01);
+      dev_load_texel<NCH>(S, ix + 1, iy + 1, p11);
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        float sum = p00[c];
+        sum *= wl0;
+        sum += p10[c] * wr0;
+        sum *= wl1;
+        float sub = p01[c];
+        sub *= wl0;
+        sub += p11[c] * wr0;
+        sum += sub * wr1;
+        out[c] = sum;
+      }
+      break;
+    }
+    case 2: dev_window_sum<NCH, 2>(S, wmat, ix, iy, fx, fy, out); break;
+    case 3: dev_window_sum<NCH, 3>(S, wmat, ix, iy, fx, fy, out); break;
+    case 4: dev_window_sum<NCH, 4>(S, wmat, ix, iy, fx, fy, out); break;
+    case 5: dev_window_sum<NCH, 5>(S, wmat, ix, iy, fx, fy, out); break;
+    case 6: dev_window_sum<NCH, 6>(S, wmat, ix, iy, fx, fy, out); break;
+    default: dev_window_sum<NCH, 7>(S, wmat, ix, iy, fx, fy, out); break;
+  }
+}
+
+// ray_to_cubeface, geometry.h:1178-1357 (>= ties favour x over y over z)
+__device__ __forceinline__ void dev_cubeface(const float c[3], int& face, float in_face[2]) {
+  bool m1 = fabsf(c[0]) >= fabsf(c[1]);
+  bool m2 = fabsf(c[0]) >= fabsf(c[2]);
+  bool m3 = fabsf(c[1]) >= fabsf(c[2]);
+  if (m1 && m2) {
+    face = c[0] < 0.0f ? CM_LEFT : CM_RIGHT;
+    in_face[0] = -c[2] / c[0];
+    in_face[1] = c[1] / fabsf(c[0]);
+  } else if (!m2 && !m3) {
+    face = c[2] < 0.0f ? CM_BACK : CM_FRONT;
+    in_face[0] = c[0] / c[2];
+    in_face[1] = c[1] / fabsf(c[2]);
+  } else {
+    face = c[1] < 0.0f ? CM_TOP : CM_BOTTOM;
+    in_face[0] = -c[0] / fabsf(c[1]);
+    in_face[1] = c[2] / c[1];
+  }
+}
+
+// environment::eval (environment.h:1821-1842) over mount_t::eval (:1172-1196) or
+// cubemap_view_t::eval (:1473-1486). Returns the cube face hit, or -1.
+template <int NCH>
+__device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, const float* __restrict__ wmat,
+                                              const float r[3], float px[NCH]) {
+  int face = -1;
+  if (F.kind == EU_SRC_MOUNT) {
+    float c[2];
+    dev_mount_coordinate(F, r, c);
+    if (!dev_mount_mask(F, r, c)) {
+#pragma unroll
+      for (int i = 0; i < NCH; i++) px[i] = 0.0f;
+      return -1;
+    }
+    // source_t::md_to_spline, environment.h:988-1006
+    float ix = (float)((double)c[0] - F.ext_x0);
+    ix /= F.ext_w;
+    ix *= F.total_w;
+    ix -= .5f;
+    float iy = (float)((double)c[1] - F.ext_y0);
+    iy /= F.ext_h;
+    iy *= F.total_h;
+    iy -= .5f;
+    dev_spline_eval<NCH>(F.src, degree, wmat, ix, iy, px);
+  } else {
+    float in_face[2], pk[2];
+    dev_cubeface(r, face, in_face);
+    if (F.kind == EU_SRC_BIATAN6) {
+      in_face[0] = (float)(4.0 / EU_PI) * eu_atanf(in_face[0]);
+      in_face[1] = (float)(4.0 / EU_PI) * eu_atanf(in_face[1]);
+    }
+    // cubemap_view_t::get_pickup_coordinate_px, environment.h:1452-1461
+    pk[0] = in_face[0] + F.refc_md;
+    pk[1] = in_face[1] + F.refc_md;
+    pk[0] *= F.model_to_px;
+    pk[1] *= F.model_to_px;
+    pk[1] += (float)(face * F.section_px);
+    pk[0] -= .5f;
+    pk[1] -= .5f;
+    dev_spline_eval<NCH>(F.src, degree, wmat, pk[0], pk[1], px);
+  }
+  if (F.brighten != 1.0f) {
+    constexpr int NCOL = (NCH == 2 || NCH == 4) ? NCH - 1 : NCH;
+#pragma unroll
+    for (int i = 0; i < NCOL; i++) px[i] *= F.brighten;
+  }
+  return face;
+}
+
+// _hdr_merge_syn::get_quality, envutil_payload.cc:1390-1442
+__device__ __forceinline__ float dev_hdr_quality(float grey, float optimum, int kind) {
+  bool large = grey > optimum;
+  float distance = fabsf(optimum - grey);
+  if (kind == EU_HDR_LOW && !large) distance = 0.0f;
+  if (kind == EU_HDR_HIGH && large) distance = 0.0f;
+  float proximity = optimum - distance;
+  return proximity / (optimum * optimum);
+}

@@ -133,8 +133,8 @@ int eu_facet_prepare(eu_facet_t* f) {
   f->r_max = sqrt(1 + aspect * aspect);
   f->d = 1.0 - (f->a + f->b + f->c);
   double factor = fabs(f->x1 - f->x0) / f->width;
-  f->h *= factor;
-  f->v *= factor;
+  f->shift_h = f->h * factor;
+  f->shift_v = f->v * factor;
   // the reference really adds y0 twice instead of squaring it (envutil_basic.h:531-534)
   double d1 = f->x0 * f->x0 + f->y0 + f->y0;
   double d2 = f->x1 * f->x1 + f->y0 + f->y0;
@@ -184,15 +184,17 @@ void eu_rotation_matrix(double roll_d, double pitch_d, double yaw_d, int inverse
   qv[0] = (cj * ss + sj * cc) * 1.0f; // a[j], j = X
   qv[1] = cj * cs - sj * sc;          // a[k], k = Y
   qr = cj * cc + sj * ss;
-  if (inverse) {  // Quat::invert()
-    float qdot = qr * qr + (qv[0] * qv[0] + qv[1] * qv[1] + qv[2] * qv[2]);
-    qr /= qdot;
-    qv[0] = -qv[0] / qdot;
-    qv[1] = -qv[1] / qdot;
-    qv[2] = -qv[2] / qdot;
+  // the reference holds the quaternion as Imath::Quat<double> (rotate_3d<double,1>): the float
+  // result of toQuat() is widened, and Quat::invert() then runs in double
+  double r = qr, v0 = qv[0], v1 = qv[1], v2 = qv[2];
+  if (inverse) {
+    double qdot = r * r + ((v0 * v0 + v1 * v1) + v2 * v2);
+    r /= qdot;
+    v0 = -v0 / qdot;
+    v1 = -v1 / qdot;
+    v2 = -v2 / qdot;
   }
   // rows = e_k * Quat<double>(q):  v + 2 (q.r (q.v x v) + q.v x (q.v x v))
-  double r = qr, v0 = qv[0], v1 = qv[1], v2 = qv[2];
   for (int k = 0; k < 3; k++) {
     double e[3] = {0.0, 0.0, 0.0};
     e[k] = 1.0;

@@ -1,0 +1,30 @@
+// kernels.h - launchers of the sm_100a kernels (render.cu, stage.cu), called by api.cu only.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "plan.h"
+
+// prefilter of one axis (zimt/recursive.h iir_filter): poles, horizons and gain narrowed to
+// float exactly as solve_gain_inlined uses them (recursive.h:650-662)
+struct IirDev {
+  int32_t bc, npoles;
+  float pole[EU_MAX_DEGREE / 2 + 1];
+  float pole_pow[EU_MAX_DEGREE / 2 + 1];  // float(powl(pole, e)) for the full-loop variants
+  int32_t horizon[EU_MAX_DEGREE / 2 + 1];
+  float gain;
+};
+
+cudaError_t eu_launch_planar_tables(const TargetDev& T, float* d_x, float* d_y, cudaStream_t st);
+cudaError_t eu_launch_render(const RenderParams& P, cudaStream_t st);
+
+// staging (stage.cu). `core` is texel (0,0) of the core inside the container.
+cudaError_t eu_launch_iir_x(float* core, int stride, int nch, int w, int h, const IirDev& f, cudaStream_t st);
+cudaError_t eu_launch_iir_y(float* core, int stride, int nch, int w, int h, int n_sections, const IirDev& f,
+                            cudaStream_t st);
+cudaError_t eu_launch_iir_y_spherical(float* core, int stride, int nch, int w, int h, const IirDev& f,
+                                      cudaStream_t st);
+cudaError_t eu_launch_brace(float* core, int stride, int nch, int w, int h, int lx, int rx, int ly, int ry, int bc0,
+                            int bc1, int spherical, cudaStream_t st);
+cudaError_t eu_launch_cubemap_support(float* ir, int nch, int face_px, int section_px, int left, int right,
+                                      double refc_md, double model_to_px, int* n_launches, cudaStream_t st);
+cudaError_t eu_launch_pad_texels(const float* src, float* dst, size_t n_texels, int nch, cudaStream_t st);

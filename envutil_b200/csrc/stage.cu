@@ -1,0 +1,327 @@
+// stage.cu - source staging kernels: b-spline prefilter (line-parallel recursive filter),
+// brace, cubemap internal-representation support. They turn an uploaded raster into the
+// coefficient container the render kernel gathers from, with the reference's arithmetic:
+//   zimt::prefilter / iir_filter         zimt/prefilter.h:125-198, zimt/recursive.h:321-729
+//   spherical_prefilter                   environment.h:356-522
+//   bracer                                zimt/brace.h:151-338
+//   cubemap_t::fill_support / prefilter   cubemap.h:607-946
+#include "eu_device.cuh"
+#include "kernels.h"
+
+// ---- the recursive filter on one line, addressed through an accessor ----------------------
+// Acc::operator()(n) -> float& of element n of the line.
+template <typename Acc>
+__device__ __forceinline__ float iir_icc(const IirDev& f, Acc& c, int M, int k) {  // recursive.h:321-583
+  float z = f.pole[k], zn, z2n, iz, Sum;
+  int n, hz = f.horizon[k];
+  switch (f.bc) {
+    case EU_BC_MIRROR:
+      if (hz < M) {
+        zn = z; Sum = c(0);
+        for (n = 1; n < hz; n++) { Sum += zn * c(n); zn *= z; }
+      } else {
+        zn = z; iz = 1.0f / z;
+        z2n = f.pole_pow[k];
+        Sum = c(0) + z2n * c(M - 1);
+        z2n *= z2n * iz;
+        for (n = 1; n <= M - 2; n++) { Sum += (zn + z2n) * c(n); zn *= z; z2n *= iz; }
+        Sum /= (1.0f - zn * zn);
+      }
+      return Sum;
+    case EU_BC_NATURAL:
+      if (hz < M) {
+        float c02 = c(0) + c(0);
+        zn = z; Sum = c(0);
+        for (n = 1; n < hz; n++) { Sum += zn * (c02 - c(n)); zn *= z; }
+        return Sum;
+      } else {
+        zn = z; iz = 1.0f / z;
+        z2n = f.pole_pow[k];
+        Sum = ((1.0f + z) / (1.0f - z)) * (c(0) - z2n * c(M - 1));
+        z2n *= z2n * iz;
+        for (n = 1; n <= M - 2; n++) { Sum -= (zn - z2n) * c(n); zn *= z; z2n *= iz; }
+        return Sum / (1.0f - zn * zn);
+      }
+    case EU_BC_REFLECT:
+      if (hz < M) {
+        zn = z; Sum = c(0);
+        for (n = 0; n < hz; n++) { Sum += zn * c(n); zn *= z; }
+        return Sum;
+      } else {
+        zn = z; iz = 1.0f / z;
+        z2n = f.pole_pow[k];
+        Sum = 0.0f;
+        for (n = 0; n < M - 1; n++) { Sum += (zn + z2n) * c(n); zn *= z; z2n *= iz; }
+        Sum += (zn + z2n) * c(n);
+        return c(0) + Sum / (1.0f - zn * zn);
+      }
+    default:  // EU_BC_PERIODIC
+      if (hz < M) {
+        zn = z; Sum = c(0);
+        for (n = M - 1; n > (M - hz); n--) { Sum += zn * c(n); zn *= z; }
+      } else {
+        zn = z; Sum = c(0);
+        for (n = M - 1; n > 0; n--) { Sum += zn * c(n); zn *= z; }
+        Sum /= (1.0f - zn);
+      }
+      return Sum;
+  }
+}
+
+template <typename Acc>
+__device__ __forceinline__ float iir_iacc(const IirDev& f, Acc& c, int M, int k) {
+  float z = f.pole[k], zn, Sum;
+  switch (f.bc) {
+    case EU_BC_MIRROR: return (z / (z * z - 1.0f)) * (c(M - 1) + z * c(M - 2));
+    case EU_BC_NATURAL: return -(z / ((1.0f - z) * (1.0f - z))) * (c(M - 1) - z * c(M - 2));
+    case EU_BC_REFLECT: return c(M - 1) / (1.0f - 1.0f / z);
+    default:
+      if (f.horizon[k] < M) {
+        zn = z; Sum = c(M - 1) * z;
+        for (int n = 0; n < f.horizon[k]; n++) { zn *= z; Sum += zn * c(n); }
+        Sum = -Sum;
+      } else {
+        zn = z; Sum = c(M - 1);
+        for (int n = 0; n < M - 1; n++) { Sum += zn * c(n); zn *= z; }
+        Sum = z * Sum / (zn - 1.0f);
+      }
+      return Sum;
+  }
+}
+
+template <typename Acc>
+__device__ __forceinline__ void iir_line(const IirDev& f, Acc& c, int M) {  // recursive.h:631-729
+  if (M == 1 || f.npoles < 1) return;
+  float p = f.pole[0], g = f.gain;
+  float X = g * iir_icc(f, c, M, 0);
+  c(0) = X;
+  for (int n = 1; n < M; n++) { X = g * c(n) + p * X; c(n) = X; }
+  X = iir_iacc(f, c, M, 0);
+  c(M - 1) = X;
+  for (int n = M - 2; n >= 0; n--) { X = p * (X - c(n)); c(n) = X; }
+  for (int k = 1; k < f.npoles; k++) {
+    p = f.pole[k];
+    X = iir_icc(f, c, M, k);
+    c(0) = X;
+    for (int n = 1; n < M; n++) { X = c(n) + p * X; c(n) = X; }
+    X = iir_iacc(f, c, M, k);
+    c(M - 1) = X;
+    for (int n = M - 2; n >= 0; n--) { X = p * (X - c(n)); c(n) = X; }
+  }
+}
+
+struct StrideAcc {
+  float* base;
+  ptrdiff_t st;
+  __device__ __forceinline__ float& operator()(int n) { return base[(ptrdiff_t)n * st]; }
+};
+// [left-half column top->bottom ; right-half column bottom->top], environment.h:425-447
+struct PoleAcc {
+  float* up;    // (x, 0)
+  float* down;  // (x + w/2, h-1)
+  ptrdiff_t st;
+  int h;
+  __device__ __forceinline__ float& operator()(int n) {
+    return n < h ? up[(ptrdiff_t)n * st] : down[-(ptrdiff_t)(n - h) * st];
+  }
+};
+
+// lines along x: one thread per (row, channel). A warp covers 32 consecutive rows of one
+// channel; each thread walks its row, so a 32-B sector fetched for texel n is reused for the
+// next texels of the same row out of L1.
+__global__ void k_iir_x(float* core, int stride, int nch, int w, int h, IirDev f) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * nch) return;
+  int c = i / h, y = i % h;
+  StrideAcc a{core + (ptrdiff_t)y * stride + c, nch};
+  iir_line(f, a, w);
+}
+
+// lines along y: one thread per float of a row (column x channel): consecutive threads touch
+// consecutive addresses at every step of the recursion -> fully coalesced. n_sections > 1:
+// the container is a stack of sections of height h that are filtered separately (cubemap IR).
+__global__ void k_iir_y(float* core, int stride, int rowfloats, int h, int n_sections, IirDev f) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rowfloats * n_sections) return;
+  int s = i / rowfloats, x = i % rowfloats;
+  StrideAcc a{core + (ptrdiff_t)s * h * stride + x, stride};
+  iir_line(f, a, h);
+}
+
+__global__ void k_iir_y_spherical(float* core, int stride, int nch, int w, int h, IirDev f) {
+  int half = w / 2;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= half * nch) return;
+  PoleAcc a{core + i, core + (ptrdiff_t)(h - 1) * stride + (ptrdiff_t)half * nch + i, stride, h};
+  iir_line(f, a, 2 * h);
+}
+
+// brace: every container texel outside the core is a copy of a core texel (PERIODIC / REFLECT
+// index maps of zimt/brace.h:189-215; spherical: rows beyond the poles continue on the
+// opposite meridian, environment.h:473-516, then the periodic x brace over all rows)
+__device__ __forceinline__ int brace_map(int i, int n, int bc) {
+  if (i < 0) return bc == EU_BC_PERIODIC ? n + i : -1 - i;
+  if (i >= n) return bc == EU_BC_PERIODIC ? i - n : 2 * n - 1 - i;
+  return i;
+}
+__global__ void k_brace(float* core, int stride, int nch, int w, int h, int lx, int rx, int ly, int ry, int bc0,
+                        int bc1, int spherical) {
+  int cw = w + lx + rx, chh = h + ly + ry;
+  int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
+  if (X >= cw || Y >= chh) return;
+  int x = X - lx, y = Y - ly;
+  if (x >= 0 && x < w && y >= 0 && y < h) return;
+  int sx = brace_map(x, w, bc0), sy;
+  if (spherical && (y < 0 || y >= h)) {
+    sy = y < 0 ? -1 - y : 2 * h - 1 - y;
+    int half = w / 2;
+    sx = sx < half ? sx + half : sx - half;
+  } else {
+    sy = brace_map(y, h, bc1);
+  }
+  const float* s = core + (ptrdiff_t)sy * stride + (ptrdiff_t)sx * nch;
+  float* d = core + (ptrdiff_t)y * stride + (ptrdiff_t)x * nch;
+  for (int c = 0; c < nch; c++) d[c] = s[c];
+}
+
+// ---- cubemap IR support (cubemap.h:607-911) ------------------------------------------------
+// 1-px mirrored ring around every cube face (mirror_around, :607-660). Corners are written by
+// the column pass from the row pass' result in the reference; the value is the face corner.
+__global__ void k_cm_ring(float* ir, int nch, int F, int S, int L, int R) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // position along the ring side, -1..F
+  int face = blockIdx.y, side = blockIdx.z;
+  int t = i - 1;
+  if (t > F) return;
+  int cmin = L > 0 ? -1 : 0, cmax = R > 0 ? F : F - 1;
+  if (t < cmin || t > cmax) return;
+  int stride = S * nch;
+  float* f0 = ir + ((ptrdiff_t)(face * S + L) * S + L) * nch;  // face texel (0,0)
+  auto px = [&](int x, int y) { return f0 + (ptrdiff_t)y * stride + (ptrdiff_t)x * nch; };
+  int tc = t < 0 ? 0 : (t > F - 1 ? F - 1 : t);  // the row pass has filled (t,-1)/(t,F) from (t,0)/(t,F-1)
+  const float* s;
+  float* d;
+  switch (side) {
+    case 0: if (!L) return; d = px(t, -1); s = px(tc, 0); break;
+    case 1: if (!R) return; d = px(t, F); s = px(tc, F - 1); break;
+    case 2: if (!L) return; d = px(-1, t); s = px(0, tc); break;
+    default: if (!R) return; d = px(F, t); s = px(F - 1, tc); break;
+  }
+  for (int c = 0; c < nch; c++) d[c] = s[c];
+}
+
+// one frame stripe of one section, by bilinear reprojection from the other sections
+// (fill_frame_t::eval, cubemap.h:733-810). Coordinates are doubled integers relative to the
+// section centre (:867-868).
+template <int NCH>
+__global__ void k_cm_fill(float* ir, SourceDev S, int face, int x0, int y0, int x1, int y1, int section_px,
+                          int ithird, double refc_md, float model_to_px) {
+  int x = x0 + blockIdx.x * blockDim.x + threadIdx.x;
+  int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= x1 || y >= y1) return;
+  int ishift = section_px - 1;
+  int c0 = 2 * x - ishift, c1 = 2 * y - ishift;
+  float ray[3];
+  switch (face) {
+    case CM_FRONT: ray[0] = (float)c0; ray[1] = (float)c1; ray[2] = (float)ithird; break;
+    case CM_BACK: ray[0] = (float)(-c0); ray[1] = (float)c1; ray[2] = (float)(-ithird); break;
+    case CM_RIGHT: ray[0] = (float)ithird; ray[1] = (float)c1; ray[2] = (float)(-c0); break;
+    case CM_LEFT: ray[0] = (float)(-ithird); ray[1] = (float)c1; ray[2] = (float)c0; break;
+    case CM_BOTTOM: ray[0] = (float)(-c0); ray[1] = (float)ithird; ray[2] = (float)c1; break;
+    default: ray[0] = (float)(-c0); ray[1] = (float)(-ithird); ray[2] = (float)(-c1); break;
+  }
+  int fv;
+  float in_face[2], pk[2], px[NCH];
+  dev_cubeface(ray, fv, in_face);
+  // metrics_t::get_pickup_coordinate_px, cubemap.h:401-411 (refc_md is a double member there)
+  pk[0] = (float)((double)in_face[0] + refc_md);
+  pk[1] = (float)((double)in_face[1] + refc_md);
+  pk[0] *= model_to_px;
+  pk[1] *= model_to_px;
+  pk[1] += (float)(fv * section_px);
+  pk[0] -= .5f;
+  pk[1] -= .5f;
+  dev_spline_eval<NCH>(S, 1, nullptr, pk[0], pk[1], px);
+  float* d = ir + ((ptrdiff_t)(face * section_px + y) * section_px + x) * NCH;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) d[c] = px[c];
+}
+
+// interleaved nch-float texels -> 16-byte texels (padded layout for one-instruction gathers)
+__global__ void k_pad_texels(const float* __restrict__ src, float4* __restrict__ dst, size_t n, int nch) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* s = src + i * nch;
+  float4 v = make_float4(s[0], nch > 1 ? s[1] : 0.f, nch > 2 ? s[2] : 0.f, 0.f);
+  dst[i] = v;
+}
+
+// ---- launchers -----------------------------------------------------------------------------
+cudaError_t eu_launch_iir_x(float* core, int stride, int nch, int w, int h, const IirDev& f, cudaStream_t st) {
+  int n = h * nch;
+  k_iir_x<<<(n + 63) / 64, 64, 0, st>>>(core, stride, nch, w, h, f);
+  return cudaGetLastError();
+}
+cudaError_t eu_launch_iir_y(float* core, int stride, int nch, int w, int h, int n_sections, const IirDev& f,
+                            cudaStream_t st) {
+  int n = w * nch * n_sections;
+  k_iir_y<<<(n + 63) / 64, 64, 0, st>>>(core, stride, w * nch, h, n_sections, f);
+  return cudaGetLastError();
+}
+cudaError_t eu_launch_iir_y_spherical(float* core, int stride, int nch, int w, int h, const IirDev& f,
+                                      cudaStream_t st) {
+  int n = (w / 2) * nch;
+  k_iir_y_spherical<<<(n + 63) / 64, 64, 0, st>>>(core, stride, nch, w, h, f);
+  return cudaGetLastError();
+}
+cudaError_t eu_launch_brace(float* core, int stride, int nch, int w, int h, int lx, int rx, int ly, int ry, int bc0,
+                            int bc1, int spherical, cudaStream_t st) {
+  int cw = w + lx + rx, chh = h + ly + ry;
+  dim3 grid((cw + 127) / 128, chh);
+  k_brace<<<grid, 128, 0, st>>>(core, stride, nch, w, h, lx, rx, ly, ry, bc0, bc1, spherical);
+  return cudaGetLastError();
+}
+
+cudaError_t eu_launch_cubemap_support(float* ir, int nch, int F, int S, int L, int R, double refc_md,
+                                      double model_to_px, int* n_launches, cudaStream_t st) {
+  *n_launches = 0;
+  if (L == 0 && R == 0) return cudaSuccess;
+  dim3 rgrid((F + 2 + 127) / 128, 6, 4);
+  k_cm_ring<<<rgrid, 128, 0, st>>>(ir, nch, F, S, L, R);
+  ++*n_launches;
+  SourceDev src;
+  src.core = ir;
+  src.stride = S * nch;
+  src.tstride = nch;
+  src.nch = nch;
+  src.w = S;
+  src.h = 6 * S;
+  src.bc0 = src.bc1 = EU_BC_REFLECT;
+  src.upper_x = (float)((long double)(S - 1) + 0.5L);
+  src.upper_y = (float)((long double)(6 * S - 1) + 0.5L);
+  int ithird = (int)(model_to_px * 2);
+  // the reference fills face after face, stripe after stripe, and later stripes read ring
+  // pixels that earlier ones have overwritten (cubemap.h:819-911): keep that order.
+  for (int face = 0; face < 6; face++) {
+    int win[4][4] = {{0, 0, S, L}, {0, S - R, S, S}, {0, L, L, S - R}, {L + F, L, S, S - R}};
+    int on[4] = {L > 0, R > 0, L > 0, R > 0};
+    for (int s = 0; s < 4; s++) {
+      if (!on[s]) continue;
+      int x0 = win[s][0], y0 = win[s][1], x1 = win[s][2], y1 = win[s][3];
+      if (x1 <= x0 || y1 <= y0) continue;
+      dim3 block(32, 8), grid((x1 - x0 + 31) / 32, (y1 - y0 + 7) / 8);
+      switch (nch) {
+        case 1: k_cm_fill<1><<<grid, block, 0, st>>>(ir, src, face, x0, y0, x1, y1, S, ithird, refc_md, (float)model_to_px); break;
+        case 3: k_cm_fill<3><<<grid, block, 0, st>>>(ir, src, face, x0, y0, x1, y1, S, ithird, refc_md, (float)model_to_px); break;
+        case 4: k_cm_fill<4><<<grid, block, 0, st>>>(ir, src, face, x0, y0, x1, y1, S, ithird, refc_md, (float)model_to_px); break;
+        default: return cudaErrorInvalidValue;
+      }
+      ++*n_launches;
+    }
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t eu_launch_pad_texels(const float* src, float* dst, size_t n_texels, int nch, cudaStream_t st) {
+  k_pad_texels<<<(unsigned)((n_texels + 255) / 256), 256, 0, st>>>(src, reinterpret_cast<float4*>(dst), n_texels, nch);
+  return cudaGetLastError();
+}

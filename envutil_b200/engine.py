@@ -1,0 +1,116 @@
+"""Thin Python driver over the C ABI (include/envutil_b200.h) for the tests, the bench and the
+smoke test: stage the facets of a Job, render, read index planes. All compute happens in
+libenvutil_b200.so on the GPU; there is no CPU path here and nothing imports the oracle.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = capi.load()
+        capi.check(self.lib.eu_init(device), self.lib)
+        self.last_timing = capi.Timing()
+        self.last_stage_timing = []
+        self.launches = 0  # kernels launched through this engine (claimed by bench.py)
+
+    def close(self):
+        self.lib.eu_shutdown()
+
+    # ---- staging --------------------------------------------------------------------------
+    def stage(self, job, structs=None, keys=None, padded=False):
+        """Upload + brace + prefilter every facet of the job. Returns the handle array."""
+        t, fa, o, taps, ntaps = structs or job.structs(self.lib)
+        o.reserved[0] = 1 if padded else 0
+        hs = (capi.SourceH * len(job.facets))()
+        self.last_stage_timing = []
+        for i, f in enumerate(job.facets):
+            img = np.ascontiguousarray(f.image, dtype=np.float32)
+            tm = capi.Timing()
+            key = keys[i].encode() if keys else None
+            h = capi.SourceH()
+            capi.check(self.lib.eu_source_upload(key, C.byref(fa[i]), C.byref(o), img.ctypes.data, C.byref(h),
+                                                 C.byref(tm)), self.lib)
+            hs[i] = h
+            self.last_stage_timing.append(tm)
+            self.launches += tm.launches
+        return hs
+
+    def stage_device(self, job, dev_ptrs, structs=None, stream=0, padded=False):
+        """Same, rasters already in device memory (dev_ptrs: one device address per facet)."""
+        t, fa, o, taps, ntaps = structs or job.structs(self.lib)
+        o.reserved[0] = 1 if padded else 0
+        hs = (capi.SourceH * len(job.facets))()
+        self.last_stage_timing = []
+        for i in range(len(job.facets)):
+            tm = capi.Timing()
+            h = capi.SourceH()
+            capi.check(self.lib.eu_source_upload_device(None, C.byref(fa[i]), C.byref(o), C.c_void_p(dev_ptrs[i]),
+                                                        C.c_void_p(stream), C.byref(h), C.byref(tm)), self.lib)
+            hs[i] = h
+            self.last_stage_timing.append(tm)
+            self.launches += tm.launches
+        return hs
+
+    def release(self, handles):
+        for h in handles:
+            if h:
+                capi.check(self.lib.eu_source_release(h), self.lib)
+
+    def container(self, handle):
+        shp = (C.c_int32 * 4)()
+        n = self.lib.eu_source_container_floats(handle, shp)
+        out = np.empty(n, dtype=np.float32)
+        capi.check(self.lib.eu_source_download(handle, out.ctypes.data), self.lib)
+        return out, tuple(shp)
+
+    # ---- rendering ------------------------------------------------------------------------
+    def render(self, job, sources=None, structs=None, out=None):
+        """Render the job into a host array H x W x C (allocated unless `out` is given)."""
+        st = structs or job.structs(self.lib)
+        t, fa, o, taps, ntaps = st
+        hs = sources if sources is not None else self.stage(job, st)
+        if out is None:
+            out = np.empty((t.height, t.width, t.nchannels), dtype=np.float32)
+        tm = capi.Timing()
+        try:
+            capi.check(self.lib.eu_render(C.byref(t), C.byref(o), len(job.facets), fa, hs, taps, ntaps,
+                                          out.ctypes.data if isinstance(out, np.ndarray) else out, C.byref(tm)),
+                       self.lib)
+        finally:
+            if sources is None:
+                self.release(hs)
+        self.last_timing = tm
+        self.launches += tm.launches
+        return out
+
+    def render_rows(self, job, sources, structs, row0, row1, d_out, stream=0, timed=True):
+        """Rows [row0,row1) into device memory at address d_out, on CUDA stream `stream`."""
+        t, fa, o, taps, ntaps = structs
+        tm = capi.Timing()
+        capi.check(self.lib.eu_render_rows(C.byref(t), C.byref(o), len(job.facets), fa, sources, taps, ntaps,
+                                           row0, row1, C.c_void_p(d_out), C.c_void_p(stream),
+                                           C.byref(tm) if timed else None), self.lib)
+        if timed:
+            self.last_timing = tm
+            self.launches += tm.launches
+        else:
+            self.launches += 1
+        return tm
+
+    def index_plane(self, job, sources=None, structs=None):
+        st = structs or job.structs(self.lib)
+        t, fa, o, taps, ntaps = st
+        hs = sources if sources is not None else self.stage(job, st)
+        idx = np.empty((t.height, t.width), dtype=np.int32)
+        try:
+            capi.check(self.lib.eu_debug_planes(C.byref(t), C.byref(o), len(job.facets), fa, hs, idx.ctypes.data),
+                       self.lib)
+        finally:
+            if sources is None:
+                self.release(hs)
+        self.launches += 1
+        return idx

@@ -24,7 +24,8 @@ class FacetSpec:
     yaw: float = 0.0
     pitch: float = 0.0
     roll: float = 0.0
-    brighten: float = 1.0
+    brighten: float = 1.0  # linear gain; overridden by eev when the job goes through PTO
+    eev: float = 0.0       # PTO Eev (0 = not given); brighten = 2^(Eev - mean Eev), envutil_main.cc:1006-1061
     a: float = 0.0
     b: float = 0.0
     c: float = 0.0
@@ -74,11 +75,37 @@ class Job:
     name: str = ""
 
     # ---- reference command line (real spellings, envutil_main.cc:190-372) ----
+    def uses_pto(self):
+        return any(f.eev or f.a or f.b or f.c or f.d or f.e or f.g or f.t or f.tr_x or f.tr_y or f.tr_z
+                   for f in self.facets)
+
+    _PTO_CODE = {"rectilinear": 0, "cylindrical": 1, "fisheye": 3, "spherical": 4, "stereographic": 10}
+
+    def pto_lines(self, facet_paths):
+        """i-lines for the facets (PTO subset, reference envutil_main.cc:655-822)."""
+        lines = []
+        for f, p in zip(self.facets, facet_paths):
+            w, h, _ = f.shape()
+            ln = (f'i w{w} h{h} f{self._PTO_CODE[f.projection]} v{float(f.hfov)!r} y{float(f.yaw)!r} '
+                  f'p{float(f.pitch)!r} r{float(f.roll)!r}')
+            for key, val in (("Eev", f.eev), ("a", f.a), ("b", f.b), ("c", f.c), ("d", f.d), ("e", f.e), ("g", f.g),
+                             ("t", f.t), ("TrX", f.tr_x), ("TrY", f.tr_y), ("TrZ", f.tr_z), ("Tpy", f.tp_y),
+                             ("Tpp", f.tp_p)):
+                if val:
+                    ln += f" {key}{float(val)!r}"
+            ln += f' n"{p}"'
+            lines.append(ln)
+        return lines
+
     def cli_args(self, facet_paths, output):
         args = []
-        for f, p in zip(self.facets, facet_paths):
-            args += ["--facet", p, f.projection, repr(float(f.hfov)), repr(float(f.yaw)), repr(float(f.pitch)),
-                     repr(float(f.roll))]
+        if self.uses_pto():
+            for ln in self.pto_lines(facet_paths):
+                args += ["--pto_line", ln]
+        else:
+            for f, p in zip(self.facets, facet_paths):
+                args += ["--facet", p, f.projection, repr(float(f.hfov)), repr(float(f.yaw)), repr(float(f.pitch)),
+                         repr(float(f.roll))]
         args += ["--projection", self.projection, "--hfov", repr(float(self.hfov)), "--width", str(self.width)]
         if self.height:
             args += ["--height", str(self.height)]
@@ -91,8 +118,22 @@ class Job:
             args += ["--synopsis", self.synopsis]
         if self.solo >= 0:
             args += ["--solo", str(self.solo)]
+        if self.support_min != 8:
+            args += ["--support_min", str(self.support_min)]
+        if self.tile_size != 64:
+            args += ["--tile_size", str(self.tile_size)]
         args += ["--output", output]
         return args
+
+    def facet_gains(self):
+        """brighten per facet as arguments::init derives it (envutil_main.cc:1006-1061): from the
+        PTO Eev values when any is given (facet_spec::brighten is a float), else 1."""
+        eevs = [np.float32(f.eev) for f in self.facets]
+        given = [e for e in eevs if e != 0]
+        if not given or not self.uses_pto():
+            return [float(np.float32(f.brighten)) for f in self.facets]
+        mean = sum(float(e) for e in given) / len(given)
+        return [1.0 if e == 0 else float(np.float32(2.0 ** (float(e) - mean))) for e in eevs]
 
     # ---- POD structs of the C ABI ----
     def structs(self, lib=None):
@@ -106,6 +147,7 @@ class Job:
         capi.check(lib.eu_target_prepare(C.byref(t)), lib)
         n = len(self.facets)
         fa = (capi.Facet * n)()
+        gains = self.facet_gains()
         for i, f in enumerate(self.facets):
             w, h, c = f.shape()
             s = fa[i]
@@ -115,9 +157,9 @@ class Job:
             s.yaw, s.pitch, s.roll = (math.radians(v) for v in (f.yaw, f.pitch, f.roll))
             s.tr_x, s.tr_y, s.tr_z = f.tr_x, f.tr_y, -f.tr_z  # TrZ is negated (envutil_main.cc:787-789)
             s.tp_y, s.tp_p = math.radians(f.tp_y), math.radians(f.tp_p)
-            s.shear_g, s.shear_t = f.g, f.t
+            s.shear_g, s.shear_t = f.g / h, f.t / w  # envutil_main.cc:795-796
             s.a, s.b, s.c, s.h, s.v = f.a, f.b, f.c, f.d, f.e
-            s.brighten = f.brighten
+            s.brighten = gains[i]
             capi.check(lib.eu_facet_prepare(C.byref(s)), lib)
         o = capi.Opts()
         o.spline_degree = self.degree

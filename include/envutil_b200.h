@@ -62,12 +62,13 @@ typedef struct eu_facet {
   double tp_y, tp_p, tp_r; /* translation plane orientation */
   double shear_g, shear_t;
   double a, b, c;          /* lens polynomial */
-  double h, v;             /* PTO d/e shift, in pixels on input; model units after prepare */
+  double h, v;             /* PTO d/e shift, in pixels (never modified by the library) */
   double brighten;         /* linear gain applied after interpolation (environment.h:1821) */
   /* derived */
   double x0, x1, y0, y1;   /* extent in model space */
   double step;
   double s, d, r_max, cap_radius;
+  double shift_h, shift_v; /* h, v in model units (what facet_base::h/v hold after process_geometry) */
   int32_t has_shift, has_lcp, has_shear, has_2d_tf, has_translation;
   int32_t window_width, window_height, window_x_offset, window_y_offset;
 } eu_facet_t;

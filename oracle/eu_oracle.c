@@ -107,14 +107,16 @@ void orc_rotation(double roll_d, double pitch_d, double yaw_d, int inverse, doub
   q[0] = cj * ss + sj * cc;
   q[1] = cj * cs - sj * sc;
   qr = cj * cc + sj * ss;
-  if (inverse) {
-    float d = qr * qr + (q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
-    qr /= d;
-    q[0] = -q[0] / d;
-    q[1] = -q[1] / d;
-    q[2] = -q[2] / d;
-  }
+  /* Imath::Quat<T> q with T = double (make_r3_t is called with the double members of args /
+   * facet_spec): the float quaternion is widened first, invert() then runs in double */
   double r = qr, v0 = q[0], v1 = q[1], v2 = q[2];
+  if (inverse) {
+    double d = r * r + ((v0 * v0 + v1 * v1) + v2 * v2);
+    r /= d;
+    v0 = -v0 / d;
+    v1 = -v1 / d;
+    v2 = -v2 / d;
+  }
   for (int k = 0; k < 3; k++) {
     double e[3] = {0, 0, 0};
     e[k] = 1.0;

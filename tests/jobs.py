@@ -1,0 +1,157 @@
+"""The small parity jobs: every stepper x source kind x interpolator x synopsis combination of
+the hot path at sizes the CPU oracle and the reference binary finish in
+well under a second. Shared by the oracle-vs-reference tests, the golden-fixture generator
+(tools/make_golden.py) and the GPU parity tests. Sources are deterministic (envutil_b200.synth),
+so a job is fully described by its name.
+"""
+import functools
+
+import numpy as np
+
+from envutil_b200 import synth
+from envutil_b200.job import FacetSpec, Job
+
+
+@functools.lru_cache(maxsize=None)
+def _ll(w, h=None):
+    return synth.latlon(w, h)
+
+
+@functools.lru_cache(maxsize=None)
+def _cm(face, biatan6=False, hfov=90.0):
+    return synth.cubemap(face, biatan6=biatan6, hfov_deg=hfov)
+
+
+@functools.lru_cache(maxsize=None)
+def _rect(w, h, hfov, yaw=0.0, pitch=0.0, roll=0.0, gain=1.0):
+    return synth.rectilinear_facet(w, h, hfov, yaw, pitch, roll, gain=gain)
+
+
+def _grey(img):
+    return np.ascontiguousarray(img[:, :, 1:2])
+
+
+def _rgba(img):
+    a = np.ones(img.shape[:2] + (1,), dtype=np.float32)
+    return np.ascontiguousarray(np.concatenate([img, a], axis=2))
+
+
+def _ll_facet(w, **kw):
+    return FacetSpec(_ll(w), "spherical", 360.0, **kw)
+
+
+ROT = dict(yaw=33.0, pitch=-21.0, roll=7.0)
+
+
+def _voronoi_facets(w=96, h=64, hfov=80.0, n=4, step=70.0, pitch=(0, 12, -9, 5, -14, 8), roll=(0, 3, -5, 2, 0, -4)):
+    fs = []
+    for k in range(n):
+        y, p, r = step * k - 100.0, float(pitch[k % 6]), float(roll[k % 6])
+        fs.append(FacetSpec(_rect(w, h, hfov, y, p, r), "rectilinear", hfov, yaw=y, pitch=p, roll=r))
+    return fs
+
+
+def _bracket_facets(w=96, h=64, hfov=70.0, yaw=20.0):
+    # Eev 12 / 10 / 14 (mean 12): brighten 1, 1/4, 4; bracket images = clamp(f * 2^(12-Eev), 0, 1),
+    # so the Eev-10 frame clips and exercises the over-exposure logic
+    fs = []
+    for ev in (12.0, 10.0, 14.0):
+        gain = 2.0 ** (12.0 - ev)
+        fs.append(FacetSpec(_rect(w, h, hfov, yaw, 0.0, 0.0, gain), "rectilinear", hfov, yaw=yaw, eev=ev))
+    return fs
+
+
+def _lens_facets():
+    # PanoTools lens polynomial + shift + shear on the source side (environment.h:240-284)
+    return [FacetSpec(_rect(96, 64, 75.0, -30.0, 5.0, 0.0), "rectilinear", 75.0, yaw=-30.0, pitch=5.0,
+                      a=0.02, b=-0.05, c=0.01, d=3.5, e=-2.25, g=1.5, t=-0.75),
+            FacetSpec(_rect(96, 64, 75.0, 25.0, -8.0, 3.0), "rectilinear", 75.0, yaw=25.0, pitch=-8.0, roll=3.0,
+                      a=-0.01, b=0.03, c=0.0),
+            FacetSpec(_ll(96, 96), "fisheye", 140.0, yaw=90.0, b=-0.02, d=-1.0)]
+
+
+def _build():
+    J = {}
+
+    def add(name, job):
+        job.name = name
+        J[name] = job
+
+    # --- lat/lon source, all seven target projections -----------------------------------
+    add("ll_rect_d1", Job([_ll_facet(256)], "rectilinear", 90.0, 96, 54))                       # C1 shape
+    add("ll_rect_d1_rot", Job([_ll_facet(256)], "rectilinear", 90.0, 96, 54, **ROT))
+    add("ll_rect_d3_rot", Job([_ll_facet(256)], "rectilinear", 70.0, 96, 54, degree=3, **ROT))
+    add("ll_rect_d2", Job([_ll_facet(128)], "rectilinear", 100.0, 80, 60, degree=2, yaw=170.0))
+    add("ll_rect_d5", Job([_ll_facet(128)], "rectilinear", 60.0, 64, 64, degree=5, pitch=80.0))
+    add("ll_rect_d7", Job([_ll_facet(128)], "rectilinear", 60.0, 40, 40, degree=7, pitch=-88.0, roll=45.0))
+    add("ll_rect_d0", Job([_ll_facet(128)], "rectilinear", 60.0, 40, 40, degree=0, yaw=-120.0))
+    add("ll_sph_d1", Job([_ll_facet(256)], "spherical", 360.0, 128, 64))
+    add("ll_sph_d3_rot_wide", Job([_ll_facet(128)], "spherical", 360.0, 1100, 8, degree=3, **ROT))  # > 2 segments
+    add("ll_cyl_d1", Job([_ll_facet(256)], "cylindrical", 200.0, 128, 64, pitch=10.0))
+    add("ll_cyl_d1_tw2", Job([_ll_facet(256)], "cylindrical", 360.0, 600, 40, twine=2, **ROT))     # normalised cyl.
+    add("ll_ster_d1", Job([_ll_facet(256)], "stereographic", 200.0, 96, 96, yaw=-45.0))
+    add("ll_fish_d1_tw4", Job([_ll_facet(256)], "fisheye", 180.0, 96, 96, twine=4))              # C4 shape
+    add("ll_fish_d3_rot", Job([_ll_facet(128)], "fisheye", 220.0, 80, 80, degree=3, **ROT))
+    add("ll_cube_d1", Job([_ll_facet(256)], "cubemap", 90.0, 48))
+    add("ll_cube_d3_rot", Job([_ll_facet(128)], "cubemap", 100.0, 32, degree=3, **ROT))
+    add("ll_ba6_d1", Job([_ll_facet(256)], "biatan6", 90.0, 48))                                  # C3a shape
+    add("ll_ba6_d1_tw2", Job([_ll_facet(256)], "biatan6", 90.0, 40, twine=2, yaw=12.0))
+    # twining variants: gaussian weights with threshold, wide kernel
+    add("ll_rect_d1_tw3_sigma", Job([_ll_facet(256)], "rectilinear", 90.0, 64, 36, twine=3, twine_width=1.5,
+                                    twine_sigma=1.2, twine_threshold=0.05))
+    add("ll_rect_d3_tw2", Job([_ll_facet(128)], "rectilinear", 50.0, 64, 36, degree=3, twine=2, **ROT))
+    # non-2:1 and partial lat/lon sources (plain prefilter, REFLECT / PERIODIC without the pole brace)
+    add("llpart_rect_d3", Job([FacetSpec(_ll(128, 64)[8:56, 16:112].copy(), "spherical", 270.0)], "rectilinear", 80.0,
+                              64, 48, degree=3, yaw=10.0))
+    add("ll360x90_rect_d3", Job([FacetSpec(_ll(128, 64)[16:48].copy(), "spherical", 360.0)], "rectilinear", 70.0,
+                                64, 40, degree=3, yaw=175.0))
+    add("cyl360_src_sph_d2", Job([FacetSpec(_ll(128, 64)[8:56].copy(), "cylindrical", 360.0)], "spherical", 360.0,
+                                 96, 48, degree=2))
+    # --- cubemap / biatan6 sources ------------------------------------------------------
+    add("cm_sph_d1", Job([FacetSpec(_cm(64), "cubemap", 90.0)], "spherical", 360.0, 192, 96))
+    add("cm_sph_d3", Job([FacetSpec(_cm(64), "cubemap", 90.0)], "spherical", 360.0, 192, 96, degree=3))  # C2 shape
+    add("cm_sph_d3_rot", Job([FacetSpec(_cm(48), "cubemap", 90.0)], "spherical", 360.0, 160, 80, degree=3, **ROT))
+    add("cm_rect_d1_tw3_rot", Job([FacetSpec(_cm(64), "cubemap", 90.0)], "rectilinear", 110.0, 80, 60, twine=3, **ROT))
+    add("cm100_sph_d2", Job([FacetSpec(_cm(64, hfov=100.0), "cubemap", 100.0)], "spherical", 360.0, 128, 64, degree=2))
+    add("cm_sph_d5", Job([FacetSpec(_cm(40), "cubemap", 90.0)], "spherical", 360.0, 96, 48, degree=5))
+    add("ba6_sph_d1", Job([FacetSpec(_cm(64, True), "biatan6", 90.0)], "spherical", 360.0, 192, 96))      # C3b shape
+    add("ba6_sph_d3_rot", Job([FacetSpec(_cm(48, True), "biatan6", 90.0)], "spherical", 360.0, 160, 80, degree=3, **ROT))
+    add("ba6_cube_d1", Job([FacetSpec(_cm(48, True), "biatan6", 90.0)], "cubemap", 90.0, 40, yaw=20.0))
+    add("cm_sph_d1_support4_tile16", Job([FacetSpec(_cm(50), "cubemap", 90.0)], "spherical", 360.0, 128, 64,
+                                         support_min=4, tile_size=16))
+    # --- mounted single images of every projection ---------------------------------------
+    add("rect_src_sph_d1", Job([FacetSpec(_rect(96, 64, 80.0, 30.0, 10.0, 5.0), "rectilinear", 80.0, yaw=30.0, pitch=10.0,
+                                          roll=5.0)], "spherical", 360.0, 192, 96))
+    add("rect_src_rect_d3", Job([FacetSpec(_rect(96, 64, 80.0), "rectilinear", 80.0)], "rectilinear", 60.0, 80, 60,
+                                degree=3, yaw=8.0, roll=-12.0))
+    add("fish_src_rect_d1", Job([FacetSpec(_ll(128, 128), "fisheye", 180.0, yaw=-20.0)], "rectilinear", 100.0, 80, 60))
+    add("fish360_src_sph_d1", Job([FacetSpec(_ll(96, 96), "fisheye", 360.0)], "spherical", 360.0, 128, 64))
+    add("ster_src_sph_d2", Job([FacetSpec(_ll(96, 64), "stereographic", 150.0, pitch=15.0)], "spherical", 360.0, 128, 64,
+                               degree=2))
+    add("cyl_src_fish_d1", Job([FacetSpec(_ll(128, 48), "cylindrical", 180.0)], "fisheye", 200.0, 72, 72, yaw=15.0))
+    # --- channel counts -------------------------------------------------------------------
+    add("grey_ll_rect_d3", Job([FacetSpec(_grey(_ll(128)), "spherical", 360.0)], "rectilinear", 90.0, 64, 36, degree=3,
+                               **ROT))
+    add("grey_cm_sph_d1_tw2", Job([FacetSpec(_grey(_cm(32)), "cubemap", 90.0)], "spherical", 360.0, 96, 48, twine=2))
+    # --- multi-facet synopses -------------------------------------------------------------
+    add("voronoi4_sph_d1", Job(_voronoi_facets(), "spherical", 360.0, 256, 128))                    # C5-B shape
+    add("voronoi4_sph_d3_rot", Job(_voronoi_facets(), "spherical", 360.0, 192, 96, degree=3, **ROT))
+    add("voronoi3_rect_d1_tw2", Job(_voronoi_facets(n=3), "rectilinear", 120.0, 96, 64, twine=2, yaw=-60.0))
+    add("voronoi_mixed_sph_d1", Job([_ll_facet(128), FacetSpec(_rect(96, 64, 60.0, 40.0), "rectilinear", 60.0, yaw=40.0),
+                                     FacetSpec(_cm(32), "cubemap", 90.0)], "spherical", 360.0, 160, 80))
+    add("voronoi4_solo2", Job(_voronoi_facets(), "spherical", 360.0, 128, 64, solo=2))
+    add("hdr3_rect_d1", Job(_bracket_facets(), "rectilinear", 70.0, 96, 64, yaw=20.0, synopsis="hdr_merge"))  # C5-A shape
+    add("hdr3_sph_d3_tw2", Job(_bracket_facets(), "spherical", 120.0, 96, 48, yaw=20.0, degree=3, twine=2,
+                               synopsis="hdr_merge"))
+    add("lens3_voronoi_sph_d1", Job(_lens_facets(), "spherical", 360.0, 256, 128))
+    add("lens1_rect_d3_tw2", Job(_lens_facets()[:1], "rectilinear", 60.0, 80, 60, yaw=-30.0, degree=3, twine=2))
+    add("eev_voronoi_sph_d1", Job([FacetSpec(_rect(96, 64, 80.0, 0.0, 0.0, 0.0, 0.5), "rectilinear", 80.0, eev=13.0),
+                                   FacetSpec(_rect(96, 64, 80.0, 60.0), "rectilinear", 80.0, yaw=60.0, eev=12.0),
+                                   FacetSpec(_rect(96, 64, 80.0, -60.0), "rectilinear", 80.0, yaw=-60.0)],
+                                  "spherical", 360.0, 192, 96))
+    return J
+
+
+JOBS = _build()
+# the subset whose reference outputs are committed under tests/golden/
+GOLDEN_JOBS = sorted(JOBS)

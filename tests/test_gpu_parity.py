@@ -1,0 +1,138 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the
+same inputs. Bar (BASELINE.json north_star): pixel values within 1e-5 relative, face / facet
+indices bit-exact. Because the kernels use the same binary32 elementary functions and the
+same operation order as the oracle (include/eu_math.h, -fmad=false), the tests demand more:
+every float of every small job is BIT-IDENTICAL (0 differing values)."""
+import copy
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import harness
+import jobs
+from envutil_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # north_star: relative, on linear float RGB, denominator floored at 1e-3
+
+
+@pytest.mark.parametrize("name", sorted(jobs.JOBS))
+def test_small_job_bit_exact(engine, name):
+    job = jobs.JOBS[name]
+    out = engine.render(job)
+    ref, ridx = harness.oracle_render(job, want_index=True)
+    c = harness.compare(out, ref)
+    assert c["max_rel"] <= TOL, c
+    assert c["n_diff"] == 0, c
+    if job.twine == 0:
+        idx = engine.index_plane(job)
+        assert np.array_equal(idx, ridx)
+
+
+@pytest.mark.parametrize("name", ["ll_rect_d3_rot", "ll_rect_d5", "ll_rect_d2", "llpart_rect_d3", "ll360x90_rect_d3",
+                                  "cyl360_src_sph_d2", "cm_sph_d3", "cm100_sph_d2", "cm_sph_d5", "ba6_sph_d1",
+                                  "cm_sph_d1_support4_tile16", "rect_src_rect_d3", "ll_rect_d7"])
+def test_staged_container_bit_exact(engine, name):
+    """Staging: brace, b-spline prefilter (all boundary conditions), spherical over-the-pole
+    prefilter, cubemap IR with support fill - the coefficient container equals the oracle's."""
+    job = jobs.JOBS[name]
+    st = job.structs()
+    hs = engine.stage(job, st)
+    ohs = harness.oracle_sources(job, st)
+    try:
+        for h, oh in zip(hs, ohs):
+            got, shp = engine.container(h)
+            p, oshp = harness.oracle_container(oh)
+            assert shp == oshp
+            want = np.ctypeslib.as_array(p, shape=(got.size,))
+            assert np.array_equal(got, want), (name, int((got != want).sum()), got.size)
+    finally:
+        engine.release(hs)
+        for oh in ohs:
+            harness.oracle().orc_source_free(oh)
+
+
+@pytest.mark.parametrize("name", ["ll_rect_d1_rot", "cm_sph_d3", "voronoi4_sph_d1", "ll_fish_d1_tw4"])
+def test_padded_texel_layout_is_bit_exact(engine, name):
+    """The 16-byte texel layout (one 128-bit load per tap) changes addresses, not values."""
+    job = jobs.JOBS[name]
+    st = job.structs()
+    hs = engine.stage(job, st, padded=True)
+    try:
+        out = engine.render(job, sources=hs, structs=st)
+    finally:
+        engine.release(hs)
+    assert harness.compare(out, harness.oracle_render(job))["n_diff"] == 0
+
+
+def test_twine_single_centre_tap_equals_plain(engine):
+    """twining with one tap (0,0,1) == no twining (normalised rays differ from
+    unnormalised ones only by scale, which lat/lon lookup ignores up to rounding)."""
+    job = copy.deepcopy(jobs.JOBS["ll_rect_d1_rot"])
+    st = list(job.structs())
+    plain = engine.render(job, structs=tuple(st))
+    taps = (capi.Tap * 1024)()
+    taps[0].x, taps[0].y, taps[0].w = 0.0, 0.0, 1.0
+    st[3], st[4] = taps, 1
+    tw = engine.render(job, structs=tuple(st))
+    c = harness.compare(tw, plain)
+    assert c["max_rel"] < 1e-4, c
+
+
+def test_row_bands_tile_the_full_render(engine):
+    """eu_render_rows (the multi-GPU work unit): bands rendered separately equal the full frame."""
+    torch = pytest.importorskip("torch")
+    job = jobs.JOBS["voronoi4_sph_d3_rot"]
+    st = job.structs()
+    t = st[0]
+    hs = engine.stage(job, st)
+    try:
+        full = engine.render(job, sources=hs, structs=st)
+        buf = torch.empty((t.height, t.width, t.nchannels), dtype=torch.float32, device="cuda:0")
+        edges = [0, 7, 40, 41, t.height]
+        stream = torch.cuda.current_stream().cuda_stream
+        for r0, r1 in zip(edges[:-1], edges[1:]):
+            engine.render_rows(job, hs, st, r0, r1, buf[r0].data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(buf.cpu().numpy(), full)
+    finally:
+        engine.release(hs)
+
+
+def test_asset_cache_cycles(engine):
+    """Two-generation cache keyed by asset_key (environment.h:84-227): an asset survives the
+    cycle it was used in, and is dropped after a cycle in which it was not used."""
+    lib = engine.lib
+    job = jobs.JOBS["ll_rect_d1"]
+    st = job.structs()
+    hs = engine.stage(job, st, keys=["test-asset-A"])
+    assert lib.eu_source_find(b"test-asset-A") == hs[0]
+    assert lib.eu_cycle() == 0
+    assert lib.eu_source_find(b"test-asset-A") == hs[0]  # touched in the new cycle
+    assert lib.eu_cycle() == 0
+    assert lib.eu_cycle() == 0  # not used during the cycle that just ended -> dropped
+    assert lib.eu_source_find(b"test-asset-A") is None
+    assert lib.eu_source_release(hs[0]) != 0  # the handle is dead
+
+
+def test_errors_are_reported_not_fatal(engine):
+    lib = engine.lib
+    job = copy.deepcopy(jobs.JOBS["ll_rect_d1"])
+    st = job.structs()
+    hs = engine.stage(job, st)
+    try:
+        t, fa, o, taps, ntaps = st
+        out = np.empty((t.height, t.width, 3), dtype=np.float32)
+        o2 = capi.Opts.from_buffer_copy(o)
+        o2.spline_degree = 3  # staged for degree 1
+        rc = lib.eu_render(C.byref(t), C.byref(o2), 1, fa, hs, taps, 0, out.ctypes.data, None)
+        assert rc == -1 and b"degree" in lib.eu_last_error()
+        bogus = (capi.SourceH * 1)(C.c_void_p(0x1234))
+        assert lib.eu_render(C.byref(t), C.byref(o), 1, fa, bogus, taps, 0, out.ctypes.data, None) == -1
+        fa[0].tr_x = 0.5
+        fa[0].has_translation = 1
+        assert lib.eu_render(C.byref(t), C.byref(o), 1, fa, hs, taps, 0, out.ctypes.data, None) == -2
+    finally:
+        engine.release(hs)

@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/: reference outputs for the small parity jobs of tests/jobs.py.
+
+Runs every job through the UNMODIFIED reference built by oracle/Makefile:
+  oracle/_ref/envutil_ref_pm   reference sources + the elementary functions of include/eu_math.h
+                               (the numerical contract of the B200 back-end)  -> golden outputs
+  oracle/_ref/envutil_ref      reference sources + glibc libm                 -> drift statistics
+and writes
+  tests/golden/manifest.json   per job: shape, sha256 of the float32 output bytes of the
+                               pinned-math build, and max/RMS relative difference between the
+                               two builds (how far two legitimate builds of the reference are
+                               apart - the context for the 1e-5 tolerance)
+  tests/golden/<job>.npz       full pinned-math output for the jobs listed in FULL (small)
+Only this container can run it (it needs oracle/_ref, which is built from /root/reference);
+tests read the committed files.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import harness  # noqa: E402
+import jobs  # noqa: E402
+
+FULL = ["ll_rect_d1", "ll_rect_d3_rot", "cm_sph_d3", "ba6_sph_d1", "ll_ba6_d1", "ll_fish_d1_tw4",
+        "voronoi4_sph_d1", "hdr3_rect_d1", "lens3_voronoi_sph_d1", "ll_cyl_d1_tw2"]
+
+
+def main():
+    os.makedirs(harness.GOLDEN, exist_ok=True)
+    manifest = {}
+    for name in sorted(jobs.JOBS):
+        job = jobs.JOBS[name]
+        pm = harness.reference_render(job, "pm")
+        lm = harness.reference_render(job, "libm")
+        c = harness.compare(lm, pm)
+        manifest[name] = {
+            "shape": list(pm.shape),
+            "sha256": hashlib.sha256(np.ascontiguousarray(pm, dtype="<f4").tobytes()).hexdigest(),
+            "libm_vs_pinned": {k: c[k] for k in ("max_rel", "rms_rel", "max_abs", "n_diff")},
+        }
+        if name in FULL:
+            np.savez_compressed(os.path.join(harness.GOLDEN, name + ".npz"), out=pm)
+        print(name, manifest[name]["sha256"][:12], c["max_rel"])
+    with open(os.path.join(harness.GOLDEN, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
