@@ -68,6 +68,7 @@ class ImageBuf {
     }
     eushim::write_ms() += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     std::cout << "eushim: write time " << eushim::write_ms() << " ms (cumulated)" << std::endl;
+    std::cout << "eushim: read time " << eushim::read_ms() << " ms (cumulated)" << std::endl;
     return ok;
   }
 };

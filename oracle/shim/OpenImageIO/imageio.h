@@ -111,7 +111,17 @@ inline bool read_header(const std::string& fn, int& w, int& h, int& c) {
   w = hdr[0]; h = hdr[1]; c = hdr[2];
   return true;
 }
+// accumulated wall time spent reading input files / writing output files, so that a harness can
+// subtract file I/O from the reference's own timers (its "frame rendering time" includes
+// save_array, envutil_payload.cc:476-555)
+inline double& read_ms() { static double ms = 0; return ms; }
+inline double& write_ms() { static double ms = 0; return ms; }
+struct ReadTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  ~ReadTimer() { read_ms() += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
 inline bool read_raster(const std::string& fn, Raster& r) {
+  ReadTimer timer;
   FILE* f = std::fopen(fn.c_str(), "rb");
   if (!f) return false;
   char magic[4];
@@ -125,9 +135,6 @@ inline bool read_raster(const std::string& fn, Raster& r) {
   std::fclose(f);
   return ok;
 }
-// accumulated wall time spent writing output files, so that a harness can subtract it from
-// the reference's "frame rendering time" (which includes save_array, envutil_payload.cc:476-555)
-inline double& write_ms() { static double ms = 0; return ms; }
 }  // namespace eushim
 
 class ImageInput {

@@ -71,4 +71,5 @@ def test_constant_image_is_reproduced(engine):
     img = np.full((256, 512, 3), 0.625, dtype=np.float32)
     job = Job([FacetSpec(img, "spherical", 360.0)], "fisheye", 200.0, 300, 300, degree=3, twine=3, yaw=40.0, pitch=25.0)
     out = engine.render(job)
-    assert np.abs(out - 0.625).max() < 2e-6
+    # the full-sphere prefilter truncates its initial sums at tolerance 1e-4 (environment.h:385)
+    assert np.abs(out - 0.625).max() < 1e-4
