@@ -50,8 +50,7 @@ struct Context {
   std::map<std::string, eu_source*> by_key;
   long cycle = 0;
   // per-job scratch, grown on demand
-  float* d_wmat = nullptr;  // 8 matrices, degree d at offset 64*d, packed (d+1)x(d+1)
-  float* d_planar = nullptr;
+  float2* d_planar = nullptr;  // column terms [2][W] then row terms [2][H]
   size_t planar_cap = 0;
   TargetDev planar_for;
   bool planar_valid = false;
@@ -296,6 +295,10 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   P.degree = o->spline_degree;
   P.n_taps = n_taps;
   P.nch = nch;
+  P.tstride = sources[0]->tstride;
+  for (int i = 1; i < nf; i++)
+    if (sources[i]->tstride != P.tstride)
+      return fail(EU_ERR_ARGUMENT, "all facets of a job must use the same texel layout");
   std::vector<FacetDev> F(nf);
   for (int i = 0; i < nf; i++) {
     int rc = facet_dev(t, &facets[i], sources[i], F[i]);
@@ -356,9 +359,13 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     g.planar_valid = true;
   }
   // normalize is part of TargetDev but does not change the tables; keep the key exact anyway
-  P.planar_x = g.d_planar;
-  P.planar_y = g.d_planar + 2 * (size_t)t->width;
-  P.wmat = g.d_wmat + 64 * o->spline_degree;
+  P.col_tab = g.d_planar;
+  P.row_tab = g.d_planar + 2 * (size_t)t->width;
+  {
+    int d = o->spline_degree;
+    for (int row = 0; row <= d; row++)
+      for (int k = 0; k <= d; k++) P.wmat[row * (d + 1) + k] = (float)eu_bspline_weights[d][row][k];
+  }
   return EU_OK;
 }
 
@@ -496,12 +503,6 @@ int eu_init(int device_id) {
                 prop.minor);
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   for (auto& e : g.ev) CK(cudaEventCreate(&e));
-  std::vector<float> wm(8 * 64, 0.0f);
-  for (int d = 0; d <= EU_MAX_DEGREE; d++)
-    for (int row = 0; row <= d; row++)
-      for (int k = 0; k <= d; k++) wm[64 * d + row * (d + 1) + k] = (float)eu_bspline_weights[d][row][k];
-  CK(cudaMalloc(&g.d_wmat, wm.size() * sizeof(float)));
-  CK(cudaMemcpy(g.d_wmat, wm.data(), wm.size() * sizeof(float), cudaMemcpyHostToDevice));
   g.device = device_id;
   g.up = true;
   g.planar_valid = false;
@@ -512,7 +513,6 @@ void eu_shutdown(void) {
   if (!g.up) return;
   cudaStreamSynchronize(g.stream);
   while (!g.sources.empty()) free_source(g.sources.back());
-  cudaFree(g.d_wmat);
   cudaFree(g.d_planar);
   cudaFree(g.d_facets);
   cudaFree(g.d_taps);

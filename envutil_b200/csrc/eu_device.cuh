@@ -28,18 +28,50 @@ __device__ __forceinline__ float dev_norm3(const float v[3]) {  // zimt/xel.h:75
 }
 
 // ------------------------------------------------------------------------------------------
-// target side: the seven steppers (stepper.h:517-1578). px,py: planar coordinate of this
-// pixel; px_first: planar x of the same lane in the first vector of the pixel's 512-px
-// segment (the cylindrical stepper keeps rcp_length from there, stepper.h:766-769).
+// target side: the seven steppers (stepper.h:517-1578).
+//
+// Everything a stepper derives from the planar x coordinate alone is the same for a whole
+// column, everything derived from planar y alone for a whole row. k_planar_tables evaluates
+// those terms once per column / row with the very same functions (so the bits are the ones the
+// per-pixel evaluation would produce) and the render kernel only combines them:
+//   projection      col.a        col.b        row.a        row.b
+//   spherical       sin(px)      cos(px)      sin(py)      cos(py)
+//   cylindrical     sin(px)      cos(px)      py           -
+//   rectilinear     px           -            py           -
+//   fisheye/stereo  px           -            py           -          (not separable)
+//   cubemap         px           -            p1           -          p1 = py + (3-face) section_md - refc_md
+//   biatan6         tan(px pi/4) -            tan(p1 pi/4) -
+// `first` is the column term of the same lane in the first vector of the pixel's 512-px segment
+// (the cylindrical stepper keeps rcp_length from there, stepper.h:766-769).
 // ------------------------------------------------------------------------------------------
+struct ColTerm { float a, b; };
+struct RowTerm { float a, b; };
+
+__device__ __forceinline__ void dev_col_term(const TargetDev& T, float px, ColTerm& c) {
+  c.a = px;
+  c.b = 0.0f;
+  if (T.projection == EU_SPHERICAL || T.projection == EU_CYLINDRICAL) eu_sincosf(px, &c.a, &c.b);
+  else if (T.projection == EU_BIATAN6) c.a = eu_tanf(px * (float)(EU_PI / 4.0));
+}
+__device__ __forceinline__ void dev_row_term(const TargetDev& T, float py, int y, RowTerm& r) {
+  r.a = py;
+  r.b = 0.0f;
+  if (T.projection == EU_SPHERICAL) {
+    eu_sincosf(py, &r.a, &r.b);
+  } else if (T.projection == EU_CUBEMAP || T.projection == EU_BIATAN6) {
+    int face = y / T.width;  // stepper.h:1289-1294
+    float p1 = py + (3 - face) * T.section_md - T.refc_md;
+    if (T.projection == EU_BIATAN6) p1 = eu_tanf(p1 * (float)(EU_PI / 4.0));
+    r.a = p1;
+  }
+}
+
 __device__ __forceinline__ void dev_stepper(const TargetDev& T, const float* xx, const float* yy,
-                                            const float* zz, float px, float py, float px_first, int y,
+                                            const float* zz, ColTerm col, RowTerm row, ColTerm first, int y,
                                             float ray[3]) {
   switch (T.projection) {
     case EU_SPHERICAL: {
-      float sy, r, sx, z;
-      eu_sincosf(py, &sy, &r);
-      eu_sincosf(px, &sx, &z);
+      float sy = row.a, r = row.b, sx = col.a, z = col.b;
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         float xxx = xx[i] * r, yyy = yy[i] * sy, zzz = zz[i] * r;
@@ -48,22 +80,21 @@ __device__ __forceinline__ void dev_stepper(const TargetDev& T, const float* xx,
       break;
     }
     case EU_CYLINDRICAL: {
-      float sx, z;
-      eu_sincosf(px, &sx, &z);
+      float sx = col.a, z = col.b, py = row.a;
 #pragma unroll
       for (int i = 0; i < 3; i++) ray[i] = xx[i] * sx + zz[i] * z + yy[i] * py;
       if (T.normalize) {
-        float s0, z0, first[3];
-        eu_sincosf(px_first, &s0, &z0);
+        float s0 = first.a, z0 = first.b, f3[3];
 #pragma unroll
-        for (int i = 0; i < 3; i++) first[i] = xx[i] * s0 + zz[i] * z0 + yy[i] * py;
-        float rcp = 1.0f / dev_norm3(first);
+        for (int i = 0; i < 3; i++) f3[i] = xx[i] * s0 + zz[i] * z0 + yy[i] * py;
+        float rcp = 1.0f / dev_norm3(f3);
 #pragma unroll
         for (int i = 0; i < 3; i++) ray[i] *= rcp;
       }
       break;
     }
     case EU_RECTILINEAR: {
+      float px = col.a, py = row.a;
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         float ddd = yy[i] * py + zz[i];
@@ -78,6 +109,7 @@ __device__ __forceinline__ void dev_stepper(const TargetDev& T, const float* xx,
     }
     case EU_FISHEYE:
     case EU_STEREOGRAPHIC: {
+      float px = col.a, py = row.a;
       float sqn = px * px;
       sqn += py * py;
       float nrm = sqrtf(sqn);
@@ -96,12 +128,7 @@ __device__ __forceinline__ void dev_stepper(const TargetDev& T, const float* xx,
     }
     default: {  // EU_CUBEMAP, EU_BIATAN6 (stepper.h:1289-1345,1478-1560)
       int face = y / T.width;
-      float p1 = py + (3 - face) * T.section_md - T.refc_md;
-      float p0 = px;
-      if (T.projection == EU_BIATAN6) {
-        p1 = eu_tanf(p1 * (float)(EU_PI / 4.0));
-        p0 = eu_tanf(p0 * (float)(EU_PI / 4.0));
-      }
+      float p1 = row.a, p0 = col.a;
       float ccc[3], vvv[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
@@ -242,22 +269,23 @@ __device__ __forceinline__ float dev_gate(float c, int bc, float upper) {
   return cc + lower;
 }
 
-template <int NCH>
-__device__ __forceinline__ void dev_load_texel(const SourceDev& S, int x, int y, float v[NCH]) {
-  const float* p = S.core + (ptrdiff_t)y * S.stride + (ptrdiff_t)x * S.tstride;
-  if (NCH == 4 || (NCH == 3 && S.tstride == 4)) {
+// one texel at p. TS: floats from one texel to the next (NCH, or 4 = 16-byte texels: one LDG.128)
+template <int NCH, int TS>
+__device__ __forceinline__ void dev_load_texel(const float* __restrict__ p, float v[NCH]) {
+  if constexpr (TS == 4) {
     float4 t = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = t.x;
-    if (NCH > 1) v[1] = t.y;
-    if (NCH > 2) v[2] = t.z;
-    if (NCH > 3) v[3] = t.w;
+    if constexpr (NCH > 1) v[1] = t.y;
+    if constexpr (NCH > 2) v[2] = t.z;
+    if constexpr (NCH > 3) v[3] = t.w;
   } else {
 #pragma unroll
     for (int c = 0; c < NCH; c++) v[c] = __ldg(p + c);
   }
 }
 
-// b-spline weights for one axis: basis_functor::operator()(result, delta), zimt/basis.h:650-689
+// b-spline weights for one axis: basis_functor::operator()(result, delta), zimt/basis.h:650-689.
+// wmat lives in the kernel parameter block: with ORDER fixed the operands are constant-bank reads.
 template <int ORDER>
 __device__ __forceinline__ void dev_weights(const float* __restrict__ wmat, float delta, float w[ORDER]) {
   float power = delta;
@@ -272,26 +300,33 @@ __device__ __forceinline__ void dev_weights(const float* __restrict__ wmat, floa
 }
 
 // evaluator::eval for a fixed degree > 1: window sum in the reference's order
-// (zimt/eval.h:903-996), window offsets k - degree/2 (:732)
-template <int NCH, int DEG>
+// (zimt/eval.h:903-996), window offsets k - degree/2 (:732). All ORDER*ORDER texel loads are
+// issued before the arithmetic so that they are in flight together.
+template <int NCH, int TS, int DEG>
 __device__ __forceinline__ void dev_window_sum(const SourceDev& S, const float* __restrict__ wmat, int ix, int iy,
                                                float fx, float fy, float out[NCH]) {
   constexpr int ORDER = DEG + 1;
+  constexpr int H2 = DEG / 2;
+  const float* __restrict__ p0 = S.core + (ptrdiff_t)(iy - H2) * S.stride + (ptrdiff_t)(ix - H2) * TS;
+  float t[ORDER][ORDER][NCH];
+#pragma unroll
+  for (int j = 0; j < ORDER; j++) {
+    const float* __restrict__ row = p0 + (ptrdiff_t)j * S.stride;
+#pragma unroll
+    for (int i = 0; i < ORDER; i++) dev_load_texel<NCH, TS>(row + i * TS, t[j][i]);
+  }
   float wx[ORDER], wy[ORDER];
   dev_weights<ORDER>(wmat, fx, wx);
   dev_weights<ORDER>(wmat, fy, wy);
-  constexpr int H2 = DEG / 2;
 #pragma unroll
   for (int j = 0; j < ORDER; j++) {
-    float sub[NCH], t[NCH];
-    dev_load_texel<NCH>(S, ix - H2, iy - H2 + j, sub);
+    float sub[NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; c++) sub[c] *= wx[0];
+    for (int c = 0; c < NCH; c++) sub[c] = t[j][0][c] * wx[0];
 #pragma unroll
     for (int i = 1; i < ORDER; i++) {
-      dev_load_texel<NCH>(S, ix - H2 + i, iy - H2 + j, t);
 #pragma unroll
-      for (int c = 0; c < NCH; c++) sub[c] += wx[i] * t[c];
+      for (int c = 0; c < NCH; c++) sub[c] += wx[i] * t[j][i][c];
     }
     if (j == 0) {
 #pragma unroll
@@ -306,10 +341,36 @@ __device__ __forceinline__ void dev_window_sum(const SourceDev& S, const float* 
   }
 }
 
-// safe evaluator = mapper + evaluator (zimt/eval.h:2039-2164, :1237-1300)
-template <int NCH>
+template <int NCH, int TS>
+__device__ __forceinline__ void dev_eval_linear(const SourceDev& S, int ix, int iy, float fx, float fy,
+                                                float out[NCH]) {  // _eval_linear, zimt/eval.h:1004-1059
+  const float* __restrict__ p = S.core + (ptrdiff_t)iy * S.stride + (ptrdiff_t)ix * TS;
+  float p00[NCH], p10[NCH], p01[NCH], p11[NCH];
+  dev_load_texel<NCH, TS>(p, p00);
+  dev_load_texel<NCH, TS>(p + TS, p10);
+  dev_load_texel<NCH, TS>(p + S.stride, p01);
+  dev_load_texel<NCH, TS>(p + S.stride + TS, p11);
+  float wl0 = 1.0f - fx, wr0 = fx, wl1 = 1.0f - fy, wr1 = fy;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) {
+    float sum = p00[c];
+    sum *= wl0;
+    sum += p10[c] * wr0;
+    sum *= wl1;
+    float sub = p01[c];
+    sub *= wl0;
+    sub += p11[c] * wr0;
+    sum += sub * wr1;
+    out[c] = sum;
+  }
+}
+
+// safe evaluator = mapper + evaluator (zimt/eval.h:2039-2164, :1237-1300). DEG >= 0: the degree
+// is fixed at compile time; DEG < 0: `degree` is read at run time (all degrees 0..7).
+template <int NCH, int TS, int DEG>
 __device__ __forceinline__ void dev_spline_eval(const SourceDev& S, int degree, const float* __restrict__ wmat,
                                                 float cx, float cy, float out[NCH]) {
+  if constexpr (DEG >= 0) degree = DEG;
   cx = dev_gate(cx, S.bc0, S.upper_x);
   cy = dev_gate(cy, S.bc1, S.upper_y);
   float fx, fy;
@@ -321,35 +382,21 @@ __device__ __forceinline__ void dev_spline_eval(const SourceDev& S, int degree, 
     float f = roundf(cx); fx = cx - f; ix = (int)f;
     f = roundf(cy); fy = cy - f; iy = (int)f;
   }
-  switch (degree) {
-    case 0: dev_load_texel<NCH>(S, ix, iy, out); break;
-    case 1: {  // _eval_linear, zimt/eval.h:1004-1059
-      float wl0 = 1.0f - fx, wr0 = fx, wl1 = 1.0f - fy, wr1 = fy;
-      float p00[NCH], p10[NCH], p01[NCH], p11[NCH];
-      dev_load_texel<NCH>(S, ix, iy, p00);
-      dev_load_texel<NCH>(S, ix + 1, iy, p10);
-      dev_load_texel<NCH>(S, ix, iy + 1, p01);
-      dev_load_texel<NCH>(S, ix + 1, iy + 1, p11);
-#pragma unroll
-      for (int c = 0; c < NCH; c++) {
-        float sum = p00[c];
-        sum *= wl0;
-        sum += p10[c] * wr0;
-        sum *= wl1;
-        float sub = p01[c];
-        sub *= wl0;
-        sub += p11[c] * wr0;
-        sum += sub * wr1;
-        out[c] = sum;
-      }
-      break;
+  if constexpr (DEG == 1) {
+    dev_eval_linear<NCH, TS>(S, ix, iy, fx, fy, out);
+  } else if constexpr (DEG == 3) {
+    dev_window_sum<NCH, TS, 3>(S, wmat, ix, iy, fx, fy, out);
+  } else {
+    switch (degree) {
+      case 0: dev_load_texel<NCH, TS>(S.core + (ptrdiff_t)iy * S.stride + (ptrdiff_t)ix * TS, out); break;
+      case 1: dev_eval_linear<NCH, TS>(S, ix, iy, fx, fy, out); break;
+      case 2: dev_window_sum<NCH, TS, 2>(S, wmat, ix, iy, fx, fy, out); break;
+      case 3: dev_window_sum<NCH, TS, 3>(S, wmat, ix, iy, fx, fy, out); break;
+      case 4: dev_window_sum<NCH, TS, 4>(S, wmat, ix, iy, fx, fy, out); break;
+      case 5: dev_window_sum<NCH, TS, 5>(S, wmat, ix, iy, fx, fy, out); break;
+      case 6: dev_window_sum<NCH, TS, 6>(S, wmat, ix, iy, fx, fy, out); break;
+      default: dev_window_sum<NCH, TS, 7>(S, wmat, ix, iy, fx, fy, out); break;
     }
-    case 2: dev_window_sum<NCH, 2>(S, wmat, ix, iy, fx, fy, out); break;
-    case 3: dev_window_sum<NCH, 3>(S, wmat, ix, iy, fx, fy, out); break;
-    case 4: dev_window_sum<NCH, 4>(S, wmat, ix, iy, fx, fy, out); break;
-    case 5: dev_window_sum<NCH, 5>(S, wmat, ix, iy, fx, fy, out); break;
-    case 6: dev_window_sum<NCH, 6>(S, wmat, ix, iy, fx, fy, out); break;
-    default: dev_window_sum<NCH, 7>(S, wmat, ix, iy, fx, fy, out); break;
   }
 }
 
@@ -375,7 +422,7 @@ __device__ __forceinline__ void dev_cubeface(const float c[3], int& face, float 
 
 // environment::eval (environment.h:1821-1842) over mount_t::eval (:1172-1196) or
 // cubemap_view_t::eval (:1473-1486). Returns the cube face hit, or -1.
-template <int NCH>
+template <int NCH, int TS, int DEG>
 __device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, const float* __restrict__ wmat,
                                               const float r[3], float px[NCH]) {
   int face = -1;
@@ -396,7 +443,7 @@ __device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, con
     iy /= F.ext_h;
     iy *= F.total_h;
     iy -= .5f;
-    dev_spline_eval<NCH>(F.src, degree, wmat, ix, iy, px);
+    dev_spline_eval<NCH, TS, DEG>(F.src, degree, wmat, ix, iy, px);
   } else {
     float in_face[2], pk[2];
     dev_cubeface(r, face, in_face);
@@ -412,7 +459,7 @@ __device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, con
     pk[1] += (float)(face * F.section_px);
     pk[0] -= .5f;
     pk[1] -= .5f;
-    dev_spline_eval<NCH>(F.src, degree, wmat, pk[0], pk[1], px);
+    dev_spline_eval<NCH, TS, DEG>(F.src, degree, wmat, pk[0], pk[1], px);
   }
   if (F.brighten != 1.0f) {
     constexpr int NCOL = (NCH == 2 || NCH == 4) ? NCH - 1 : NCH;

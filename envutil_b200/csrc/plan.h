@@ -64,16 +64,17 @@ struct TargetDev {
 struct RenderParams {
   TargetDev trg;
   FacetDev f0;              // the facet of single-facet jobs (constant bank)
+  float wmat[64];           // (degree+1)^2 weight matrix (zimt/basis.h:419-543), float, packed
   const FacetDev* facets;   // all facets (global memory), used by the synopsis modes
   const float* taps;        // n_taps x (x*4, y*4, w)  (twining.h:106-121)
-  const float* planar_x;    // [2][width]: r00 and r10 steppers' planar[0] for every column
-  const float* planar_y;    // [2][height]: r00 and r01 steppers' planar[1] for every row
-  const float* wmat;        // (degree+1)^2 weight matrix (zimt/basis.h:419-543), float
+  const float2* col_tab;    // [2][width]: per-column stepper terms, plain and x-biased (eu_device.cuh)
+  const float2* row_tab;    // [2][height]: per-row stepper terms, plain and y-biased
   int32_t n_facets;
   int32_t mode;       // EU_MODE_*
   int32_t degree;     // spline degree of the evaluator
   int32_t n_taps;     // 0: plain rays (ninputs 3), else twining (ninputs 9)
   int32_t nch;
+  int32_t tstride;    // floats per texel in HBM: nch, or 4 (padded RGB); same for all facets
   int32_t row0, row1;  // rows rendered by this launch
   float* out;          // first float of row `row0`
   int32_t* index_out;  // optional index plane (face / winning facet)

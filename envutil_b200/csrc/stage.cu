@@ -240,7 +240,7 @@ __global__ void k_cm_fill(float* ir, SourceDev S, int face, int x0, int y0, int 
   pk[1] += (float)(fv * section_px);
   pk[0] -= .5f;
   pk[1] -= .5f;
-  dev_spline_eval<NCH>(S, 1, nullptr, pk[0], pk[1], px);
+  dev_spline_eval<NCH, NCH, 1>(S, 1, nullptr, pk[0], pk[1], px);
   float* d = ir + ((ptrdiff_t)(face * section_px + y) * section_px + x) * NCH;
 #pragma unroll
   for (int c = 0; c < NCH; c++) d[c] = px[c];
