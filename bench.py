@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=int, default=1, help="shrink the workload (tests only; invalid as a bench)")
     ap.add_argument("--padded", type=int, default=0, help="1: 16-byte RGB texels in HBM")
+    ap.add_argument("--no-tiles", type=int, default=0, help="1: direct-gather kernel (no shared-memory staging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: min(steps, 5))")
     return ap.parse_args()
@@ -273,6 +274,7 @@ def ours(args):
     h_src.copy_(d_src)
     torch.cuda.synchronize()
     job.yaw = 360.0 * rank / world  # every rank renders its own view of the same environment
+    job.padded, job.no_tiles = bool(args.padded), bool(args.no_tiles)
     eng = Engine(local)
     st = job.structs(eng.lib)
     t, fa, o, taps, ntaps = st
@@ -367,10 +369,11 @@ def ours(args):
             "config": {"workload": name, "frames_per_step": world, "out_mpix_per_frame": mpix,
                        "l2": "inputs_larger_than_l2 (321 MB source IR + 403 MB output per frame vs 126 MB L2)",
                        "texel_layout": "float4-padded" if args.padded else "interleaved-rgb",
+                       "gather": "direct (L1)" if args.no_tiles else "footprint staged in shared memory by cp.async.bulk",
                        "parity": "bit-exact vs pinned-math reference build (tests/)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                         "kernel": "k_render<3,SINGLE,false>", "frac_of_8TBs_spec": achieved / 8000.0},
+                         "kernel": "k_render<3,...>" if args.no_tiles else "k_render_tiled<3,...>", "frac_of_8TBs_spec": achieved / 8000.0},
             "e2e": {"value": world * mpix / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h_src.numel() * 4), "d2h_bytes_per_step": int(h_out.numel() * 4),
                     "ms_per_step": e2e_ms, "steps": e2e_steps,

@@ -32,8 +32,9 @@ struct eu_source {
   int cw, chh;           // container
   int lx, ly, rx, ry;    // brace
   int bc0, bc1;
-  float* container;      // device, cw*chh texels of `tstride` floats
+  float* container;      // device: chh rows of `pitch` floats, cw texels of `tstride` floats each
   int tstride;           // nch, or 4 for the padded RGB layout
+  int pitch;             // floats per container row, a multiple of 4 (16-byte row granules for bulk copies)
   eu_cubemap_metrics_t cm;
   long last_used_cycle;
   int refs;
@@ -84,6 +85,16 @@ int fail(int code, const char* fmt, ...) {
 int need_up() {
   if (!g.up) return fail(EU_ERR_STATE, "eu_init has not been called");
   return EU_OK;
+}
+
+// Large device buffers (containers, upload staging) come from CUDA's stream-ordered pool with
+// the release threshold lifted: a freed container is handed to the next upload instead of going
+// back to the driver (cudaMalloc/cudaFree of a few hundred MB cost milliseconds and synchronise).
+cudaError_t pool_alloc(float** p, size_t n_floats) {
+  return cudaMallocAsync((void**)p, n_floats * sizeof(float), g.stream);
+}
+void pool_free(void* p) {
+  if (p) cudaFreeAsync(p, g.stream);
 }
 
 template <typename T>
@@ -137,7 +148,7 @@ bool is_full_sphere(const eu_facet_t* f) {  // environment.h:905-907
 
 void source_dev(const eu_source* s, SourceDev& d) {
   d.tstride = s->tstride;
-  d.stride = s->cw * s->tstride;
+  d.stride = s->pitch;
   d.core = s->container + (size_t)s->ly * d.stride + (size_t)s->lx * s->tstride;
   d.nch = s->nch;
   d.w = s->w;
@@ -151,7 +162,7 @@ void source_dev(const eu_source* s, SourceDev& d) {
 
 void free_source(eu_source* s) {
   if (!s) return;
-  if (s->container) cudaFree(s->container);
+  pool_free(s->container);
   if (!s->key.empty()) {
     auto it = g.by_key.find(s->key);
     if (it != g.by_key.end() && it->second == s) g.by_key.erase(it);
@@ -316,6 +327,12 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     for (int i = 0; i < nf; i++) F[i].hdr_kind = (i == lo) ? EU_HDR_LOW : (i == hi) ? EU_HDR_HIGH : EU_HDR_MIDDLE;
   }
   P.f0 = F[first];
+  P.use_tiles = o->reserved[1] == 1 ? 0 : 1;
+  P.src_cw = sources[first]->cw;
+  P.src_ch = sources[first]->chh;
+  P.src_lx = sources[first]->lx;
+  P.src_ly = sources[first]->ly;
+  P.src_base = sources[first]->container;
   P.n_facets = mode == EU_MODE_SINGLE ? 1 : nf;
   if (mode != EU_MODE_SINGLE) {
     if (nf > g.facets_cap) {
@@ -369,8 +386,10 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   return EU_OK;
 }
 
-int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixels, cudaStream_t st, eu_source* s,
-                    int* launches) {
+// `pixels` is a device pointer (kind = DeviceToDevice) or a host pointer (HostToDevice): the
+// raster is copied straight into its place inside the container, there is no staging copy.
+int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixels, cudaMemcpyKind kind,
+                    cudaStream_t st, eu_source* s, int* launches, float* copy_ms) {
   int degree = o->spline_degree;
   int pdeg = o->prefilter_degree < 0 ? degree : o->prefilter_degree;
   if (pdeg > EU_MAX_DEGREE) return fail(EU_ERR_ARGUMENT, "prefilter degree %d out of range", pdeg);
@@ -393,21 +412,24 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
     s->h = s->chh = 6 * S;
     s->lx = s->ly = s->rx = s->ry = 0;
     s->bc0 = s->bc1 = EU_BC_REFLECT;
-    size_t n = (size_t)S * 6 * S * nch;
-    CK(cudaMalloc(&s->container, n * sizeof(float)));
+    s->pitch = (S * nch + 3) & ~3;
+    const int pitch = s->pitch;
+    size_t n = (size_t)pitch * 6 * S;
+    CK(pool_alloc(&s->container, n));
     CK(cudaMemsetAsync(s->container, 0, n * sizeof(float), st));
+    CK(cudaEventRecord(g.ev[2], st));
     for (int face = 0; face < 6; face++)
-      CK(cudaMemcpy2DAsync(s->container + ((size_t)(face * S + L) * S + L) * nch, (size_t)S * tb,
-                           d_pixels + (size_t)face * Fpx * Fpx * nch, (size_t)Fpx * tb, (size_t)Fpx * tb, Fpx,
-                           cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpy2DAsync(s->container + (size_t)(face * S + L) * pitch + (size_t)L * nch, (size_t)pitch * sizeof(float),
+                           d_pixels + (size_t)face * Fpx * Fpx * nch, (size_t)Fpx * tb, (size_t)Fpx * tb, Fpx, kind, st));
+    CK(cudaEventRecord(g.ev[3], st));
     int nl = 0;
-    CK(eu_launch_cubemap_support(s->container, nch, Fpx, S, L, R, s->cm.refc_md, s->cm.model_to_px, &nl, st));
+    CK(eu_launch_cubemap_support(s->container, pitch, nch, Fpx, S, L, R, s->cm.refc_md, s->cm.model_to_px, &nl, st));
     *launches += nl;
     if (pdeg > 1) {  // cubemap_t::prefilter, cubemap.h:921-946: per section, NATURAL, both axes
       IirDev fx;
       iir_setup(fx, EU_BC_NATURAL, pdeg, (long double)FLT_EPSILON, S);
-      CK(eu_launch_iir_x(s->container, S * nch, nch, S, 6 * S, fx, st));
-      CK(eu_launch_iir_y(s->container, S * nch, nch, S, S, 6, fx, st));
+      CK(eu_launch_iir_x(s->container, pitch, nch, S, 6 * S, fx, st));
+      CK(eu_launch_iir_y(s->container, pitch, nch, S, S, 6, fx, st));
       *launches += 2;
     }
     return EU_OK;
@@ -425,12 +447,15 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
   s->ry = right_brace(degree, s->bc1);
   s->cw = s->w + s->lx + s->rx;
   s->chh = s->h + s->ly + s->ry;
-  size_t n = (size_t)s->cw * s->chh * nch;
-  CK(cudaMalloc(&s->container, n * sizeof(float)));
-  int stride = s->cw * nch;
+  s->pitch = (s->cw * nch + 3) & ~3;
+  size_t n = (size_t)s->pitch * s->chh;
+  CK(pool_alloc(&s->container, n));
+  int stride = s->pitch;
   float* core = s->container + (size_t)s->ly * stride + (size_t)s->lx * nch;
-  CK(cudaMemcpy2DAsync(core, (size_t)stride * sizeof(float), d_pixels, (size_t)s->w * tb, (size_t)s->w * tb, s->h,
-                       cudaMemcpyDeviceToDevice, st));
+  CK(cudaEventRecord(g.ev[2], st));
+  CK(cudaMemcpy2DAsync(core, (size_t)stride * sizeof(float), d_pixels, (size_t)s->w * tb, (size_t)s->w * tb, s->h, kind,
+                       st));
+  CK(cudaEventRecord(g.ev[3], st));
   bool sphere = is_full_sphere(f);
   if (sphere && (s->ly > s->h || s->ry > s->h)) return fail(EU_ERR_ARGUMENT, "image too small for its brace");
   if (pdeg > 1) {
@@ -458,16 +483,16 @@ int maybe_pad(const eu_opts_t* o, eu_source* s, cudaStream_t st, int* launches) 
   if (o->reserved[0] != 1 || s->nch != 3) return EU_OK;
   size_t ntex = (size_t)s->cw * s->chh;
   float* padded = nullptr;
-  CK(cudaMalloc(&padded, ntex * 4 * sizeof(float)));
-  cudaError_t e = eu_launch_pad_texels(s->container, padded, ntex, s->nch, st);
+  CK(pool_alloc(&padded, ntex * 4));
+  cudaError_t e = eu_launch_pad_texels(s->container, s->pitch, padded, s->cw, s->chh, s->nch, st);
   if (e != cudaSuccess) {
-    cudaFree(padded);
+    pool_free(padded);
     return fail(EU_ERR_CUDA, "pad kernel: %s", cudaGetErrorString(e));
   }
-  CK(cudaStreamSynchronize(st));
-  CK(cudaFree(s->container));
+  pool_free(s->container);
   s->container = padded;
   s->tstride = 4;
+  s->pitch = s->cw * 4;
   ++*launches;
   return EU_OK;
 }
@@ -502,6 +527,12 @@ int eu_init(int device_id) {
     return fail(EU_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device_id, prop.major,
                 prop.minor);
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t mp;
+    CK(cudaDeviceGetDefaultMemPool(&mp, device_id));
+    uint64_t keep = UINT64_MAX;
+    CK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   for (auto& e : g.ev) CK(cudaEventCreate(&e));
   g.device = device_id;
   g.up = true;
@@ -519,36 +550,42 @@ void eu_shutdown(void) {
   cudaFree(g.d_out);
   cudaFree(g.d_index);
   for (auto& e : g.ev) cudaEventDestroy(e);
+  cudaStreamSynchronize(g.stream);
+  {
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, g.device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
+  }
   cudaStreamDestroy(g.stream);
   g = Context();
 }
 
-int eu_source_upload_device(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* d_pixels,
-                            void* cuda_stream, eu_source_h* out, eu_timing_t* t) {
+static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
+                         cudaMemcpyKind kind, cudaStream_t caller, eu_source_h* out, eu_timing_t* t) {
   int rc = need_up();
   if (rc) return rc;
-  if (!f || !o || !d_pixels || !out) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (!f || !o || !pixels || !out) return fail(EU_ERR_ARGUMENT, "null argument");
   if (f->width <= 0 || f->height <= 0 || f->nchannels < 1 || f->nchannels > 4 || f->nchannels == 2)
     return fail(EU_ERR_ARGUMENT, "bad raster description %dx%dx%d", f->width, f->height, f->nchannels);
   if (o->spline_degree < 0 || o->spline_degree > EU_MAX_DEGREE)
     return fail(EU_ERR_ARGUMENT, "spline degree %d out of range", o->spline_degree);
   if (f->window_width != f->width || f->window_height != f->height)
     return fail(EU_ERR_UNSUPPORTED, "cropped facets (W/h window) are not built");
-  cudaStream_t caller = (cudaStream_t)cuda_stream;
   cudaStream_t st = g.stream;
-  // order our stream after the caller's work on d_pixels
-  CK(cudaEventRecord(g.ev[2], caller));
-  CK(cudaStreamWaitEvent(st, g.ev[2], 0));
+  if (kind == cudaMemcpyDeviceToDevice) {  // order our stream after the caller's work on the raster
+    CK(cudaEventRecord(g.ev[2], caller));
+    CK(cudaStreamWaitEvent(st, g.ev[2], 0));
+  }
   eu_source* s = new eu_source();
   s->container = nullptr;
   s->last_used_cycle = g.cycle;
   s->refs = 1;
   int launches = 0;
+  float copy_ms = 0;
   CK(cudaEventRecord(g.ev[0], st));
-  rc = stage_on_device(f, o, d_pixels, st, s, &launches);
+  rc = stage_on_device(f, o, pixels, kind, st, s, &launches, &copy_ms);
   if (rc == EU_OK) rc = maybe_pad(o, s, st, &launches);
   if (rc != EU_OK) {
-    if (s->container) cudaFree(s->container);
+    pool_free(s->container);
     delete s;
     return rc;
   }
@@ -557,8 +594,11 @@ int eu_source_upload_device(const char* asset_key, const eu_facet_t* f, const eu
   if (t) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
-    t->render_ms = ms;
-    t->h2d_ms = t->d2h_ms = 0;
+    CK(cudaEventElapsedTime(&copy_ms, g.ev[2], g.ev[3]));
+    bool host = kind == cudaMemcpyHostToDevice;
+    t->render_ms = host ? ms - copy_ms : ms;  // staging kernels (device-side placement copy included)
+    t->h2d_ms = host ? copy_ms : 0.0f;
+    t->d2h_ms = 0;
     t->launches = launches;
     t->reserved = 0;
   }
@@ -577,30 +617,14 @@ int eu_source_upload_device(const char* asset_key, const eu_facet_t* f, const eu
   return EU_OK;
 }
 
+int eu_source_upload_device(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* d_pixels,
+                            void* cuda_stream, eu_source_h* out, eu_timing_t* t) {
+  return upload_common(asset_key, f, o, d_pixels, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream, out, t);
+}
+
 int eu_source_upload(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
                      eu_source_h* out, eu_timing_t* t) {
-  int rc = need_up();
-  if (rc) return rc;
-  if (!f || !pixels) return fail(EU_ERR_ARGUMENT, "null argument");
-  if (f->width <= 0 || f->height <= 0 || f->nchannels < 1 || f->nchannels > 4)
-    return fail(EU_ERR_ARGUMENT, "bad raster description");
-  size_t n = (size_t)f->width * f->height * f->nchannels;
-  float* d_raw = nullptr;
-  CK(cudaMalloc(&d_raw, n * sizeof(float)));
-  cudaEventRecord(g.ev[2], g.stream);
-  cudaError_t e = cudaMemcpyAsync(d_raw, pixels, n * sizeof(float), cudaMemcpyHostToDevice, g.stream);
-  cudaEventRecord(g.ev[3], g.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
-  if (e != cudaSuccess) {
-    cudaFree(d_raw);
-    return fail(EU_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
-  }
-  float h2d = 0;
-  cudaEventElapsedTime(&h2d, g.ev[2], g.ev[3]);
-  rc = eu_source_upload_device(asset_key, f, o, d_raw, g.stream, out, t);
-  cudaFree(d_raw);
-  if (rc == EU_OK && t) t->h2d_ms = h2d;
-  return rc;
+  return upload_common(asset_key, f, o, pixels, cudaMemcpyHostToDevice, nullptr, out, t);
 }
 
 eu_source_h eu_source_find(const char* asset_key) {
@@ -615,7 +639,7 @@ int eu_source_release(eu_source_h s) {
   int rc = need_up();
   if (rc) return rc;
   if (!known_source(s)) return fail(EU_ERR_ARGUMENT, "not a live source handle");
-  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaDeviceSynchronize());  // renders on caller streams may still be reading the container
   free_source(s);
   return EU_OK;
 }
@@ -625,7 +649,7 @@ int eu_source_release(eu_source_h s) {
 int eu_cycle(void) {
   int rc = need_up();
   if (rc) return rc;
-  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaDeviceSynchronize());
   std::vector<eu_source*> drop;
   for (auto s : g.sources)
     if (!s->key.empty() && s->last_used_cycle < g.cycle) drop.push_back(s);
@@ -650,10 +674,13 @@ int eu_source_download(eu_source_h s, float* out) {
   if (rc) return rc;
   if (!known_source(s) || !out) return fail(EU_ERR_ARGUMENT, "bad argument");
   CK(cudaStreamSynchronize(g.stream));
-  size_t ntex = (size_t)s->cw * s->chh;
+  // strip the row padding (and the texel padding of the 16-byte layout): the caller gets the
+  // reference's container layout, cw*chh texels of nch floats
   if (s->tstride == s->nch) {
-    CK(cudaMemcpy(out, s->container, ntex * s->nch * sizeof(float), cudaMemcpyDeviceToHost));
-  } else {  // padded layout: strip the padding
+    CK(cudaMemcpy2D(out, (size_t)s->cw * s->nch * sizeof(float), s->container, (size_t)s->pitch * sizeof(float),
+                    (size_t)s->cw * s->nch * sizeof(float), s->chh, cudaMemcpyDeviceToHost));
+  } else {
+    size_t ntex = (size_t)s->cw * s->chh;
     CK(cudaMemcpy2D(out, s->nch * sizeof(float), s->container, s->tstride * sizeof(float), s->nch * sizeof(float), ntex,
                     cudaMemcpyDeviceToHost));
   }

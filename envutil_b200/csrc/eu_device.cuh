@@ -269,18 +269,19 @@ __device__ __forceinline__ float dev_gate(float c, int bc, float upper) {
   return cc + lower;
 }
 
-// one texel at p. TS: floats from one texel to the next (NCH, or 4 = 16-byte texels: one LDG.128)
-template <int NCH, int TS>
+// one texel at p. TS: floats from one texel to the next (NCH, or 4 = 16-byte texels: one 128-bit
+// load). SMEM: p points into the block's shared-memory tile, else into HBM (read-only path).
+template <int NCH, int TS, bool SMEM>
 __device__ __forceinline__ void dev_load_texel(const float* __restrict__ p, float v[NCH]) {
   if constexpr (TS == 4) {
-    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    float4 t = SMEM ? *reinterpret_cast<const float4*>(p) : __ldg(reinterpret_cast<const float4*>(p));
     v[0] = t.x;
     if constexpr (NCH > 1) v[1] = t.y;
     if constexpr (NCH > 2) v[2] = t.z;
     if constexpr (NCH > 3) v[3] = t.w;
   } else {
 #pragma unroll
-    for (int c = 0; c < NCH; c++) v[c] = __ldg(p + c);
+    for (int c = 0; c < NCH; c++) v[c] = SMEM ? p[c] : __ldg(p + c);
   }
 }
 
@@ -299,21 +300,37 @@ __device__ __forceinline__ void dev_weights(const float* __restrict__ wmat, floa
   }
 }
 
+// Where a spline coordinate lands: gates (zimt/eval.h:2039-2164) + split (zimt/basis.h:102-146).
+struct Located {
+  int ix, iy;    // integral part: the window covers [ix - deg/2, ix - deg/2 + deg] (zimt/eval.h:732)
+  float fx, fy;  // remainder fed to the weight functor
+};
+__device__ __forceinline__ Located dev_locate(const SourceDev& S, int degree, float cx, float cy) {
+  cx = dev_gate(cx, S.bc0, S.upper_x);
+  cy = dev_gate(cy, S.bc1, S.upper_y);
+  Located L;
+  if (degree & 1) {
+    float f = floorf(cx); L.fx = cx - f; L.ix = (int)f;
+    f = floorf(cy); L.fy = cy - f; L.iy = (int)f;
+  } else {
+    float f = roundf(cx); L.fx = cx - f; L.ix = (int)f;
+    f = roundf(cy); L.fy = cy - f; L.iy = (int)f;
+  }
+  return L;
+}
+
 // evaluator::eval for a fixed degree > 1: window sum in the reference's order
-// (zimt/eval.h:903-996), window offsets k - degree/2 (:732). All ORDER*ORDER texel loads are
-// issued before the arithmetic so that they are in flight together.
-template <int NCH, int TS, int DEG>
-__device__ __forceinline__ void dev_window_sum(const SourceDev& S, const float* __restrict__ wmat, int ix, int iy,
+// (zimt/eval.h:903-996). p0 -> texel (ix - deg/2, iy - deg/2); pitch: floats per row.
+template <int NCH, int TS, int DEG, bool SMEM>
+__device__ __forceinline__ void dev_window_sum(const float* __restrict__ p0, int pitch, const float* __restrict__ wmat,
                                                float fx, float fy, float out[NCH]) {
   constexpr int ORDER = DEG + 1;
-  constexpr int H2 = DEG / 2;
-  const float* __restrict__ p0 = S.core + (ptrdiff_t)(iy - H2) * S.stride + (ptrdiff_t)(ix - H2) * TS;
   float t[ORDER][ORDER][NCH];
 #pragma unroll
   for (int j = 0; j < ORDER; j++) {
-    const float* __restrict__ row = p0 + (ptrdiff_t)j * S.stride;
+    const float* __restrict__ row = p0 + (ptrdiff_t)j * pitch;
 #pragma unroll
-    for (int i = 0; i < ORDER; i++) dev_load_texel<NCH, TS>(row + i * TS, t[j][i]);
+    for (int i = 0; i < ORDER; i++) dev_load_texel<NCH, TS, SMEM>(row + i * TS, t[j][i]);
   }
   float wx[ORDER], wy[ORDER];
   dev_weights<ORDER>(wmat, fx, wx);
@@ -341,15 +358,14 @@ __device__ __forceinline__ void dev_window_sum(const SourceDev& S, const float* 
   }
 }
 
-template <int NCH, int TS>
-__device__ __forceinline__ void dev_eval_linear(const SourceDev& S, int ix, int iy, float fx, float fy,
+template <int NCH, int TS, bool SMEM>
+__device__ __forceinline__ void dev_eval_linear(const float* __restrict__ p, int pitch, float fx, float fy,
                                                 float out[NCH]) {  // _eval_linear, zimt/eval.h:1004-1059
-  const float* __restrict__ p = S.core + (ptrdiff_t)iy * S.stride + (ptrdiff_t)ix * TS;
   float p00[NCH], p10[NCH], p01[NCH], p11[NCH];
-  dev_load_texel<NCH, TS>(p, p00);
-  dev_load_texel<NCH, TS>(p + TS, p10);
-  dev_load_texel<NCH, TS>(p + S.stride, p01);
-  dev_load_texel<NCH, TS>(p + S.stride + TS, p11);
+  dev_load_texel<NCH, TS, SMEM>(p, p00);
+  dev_load_texel<NCH, TS, SMEM>(p + TS, p10);
+  dev_load_texel<NCH, TS, SMEM>(p + pitch, p01);
+  dev_load_texel<NCH, TS, SMEM>(p + pitch + TS, p11);
   float wl0 = 1.0f - fx, wr0 = fx, wl1 = 1.0f - fy, wr1 = fy;
 #pragma unroll
   for (int c = 0; c < NCH; c++) {
@@ -365,39 +381,38 @@ __device__ __forceinline__ void dev_eval_linear(const SourceDev& S, int ix, int 
   }
 }
 
-// safe evaluator = mapper + evaluator (zimt/eval.h:2039-2164, :1237-1300). DEG >= 0: the degree
-// is fixed at compile time; DEG < 0: `degree` is read at run time (all degrees 0..7).
+// the window evaluation for a located coordinate; p0 -> texel (ix - degree/2, iy - degree/2).
+// DEG >= 0: degree fixed at compile time; DEG < 0: read at run time (all degrees 0..7).
+template <int NCH, int TS, int DEG, bool SMEM>
+__device__ __forceinline__ void dev_window_eval(const float* __restrict__ p0, int pitch, int degree,
+                                                const float* __restrict__ wmat, float fx, float fy, float out[NCH]) {
+  if constexpr (DEG == 1) {
+    dev_eval_linear<NCH, TS, SMEM>(p0, pitch, fx, fy, out);
+  } else if constexpr (DEG == 3) {
+    dev_window_sum<NCH, TS, 3, SMEM>(p0, pitch, wmat, fx, fy, out);
+  } else {
+    switch (degree) {
+      case 0: dev_load_texel<NCH, TS, SMEM>(p0, out); break;
+      case 1: dev_eval_linear<NCH, TS, SMEM>(p0, pitch, fx, fy, out); break;
+      case 2: dev_window_sum<NCH, TS, 2, SMEM>(p0, pitch, wmat, fx, fy, out); break;
+      case 3: dev_window_sum<NCH, TS, 3, SMEM>(p0, pitch, wmat, fx, fy, out); break;
+      case 4: dev_window_sum<NCH, TS, 4, SMEM>(p0, pitch, wmat, fx, fy, out); break;
+      case 5: dev_window_sum<NCH, TS, 5, SMEM>(p0, pitch, wmat, fx, fy, out); break;
+      case 6: dev_window_sum<NCH, TS, 6, SMEM>(p0, pitch, wmat, fx, fy, out); break;
+      default: dev_window_sum<NCH, TS, 7, SMEM>(p0, pitch, wmat, fx, fy, out); break;
+    }
+  }
+}
+
+// safe evaluator = mapper + evaluator (zimt/eval.h:2039-2164, :1237-1300), gathering from HBM
 template <int NCH, int TS, int DEG>
 __device__ __forceinline__ void dev_spline_eval(const SourceDev& S, int degree, const float* __restrict__ wmat,
                                                 float cx, float cy, float out[NCH]) {
   if constexpr (DEG >= 0) degree = DEG;
-  cx = dev_gate(cx, S.bc0, S.upper_x);
-  cy = dev_gate(cy, S.bc1, S.upper_y);
-  float fx, fy;
-  int ix, iy;
-  if (degree & 1) {  // odd_split / even_split, zimt/basis.h:102-146
-    float f = floorf(cx); fx = cx - f; ix = (int)f;
-    f = floorf(cy); fy = cy - f; iy = (int)f;
-  } else {
-    float f = roundf(cx); fx = cx - f; ix = (int)f;
-    f = roundf(cy); fy = cy - f; iy = (int)f;
-  }
-  if constexpr (DEG == 1) {
-    dev_eval_linear<NCH, TS>(S, ix, iy, fx, fy, out);
-  } else if constexpr (DEG == 3) {
-    dev_window_sum<NCH, TS, 3>(S, wmat, ix, iy, fx, fy, out);
-  } else {
-    switch (degree) {
-      case 0: dev_load_texel<NCH, TS>(S.core + (ptrdiff_t)iy * S.stride + (ptrdiff_t)ix * TS, out); break;
-      case 1: dev_eval_linear<NCH, TS>(S, ix, iy, fx, fy, out); break;
-      case 2: dev_window_sum<NCH, TS, 2>(S, wmat, ix, iy, fx, fy, out); break;
-      case 3: dev_window_sum<NCH, TS, 3>(S, wmat, ix, iy, fx, fy, out); break;
-      case 4: dev_window_sum<NCH, TS, 4>(S, wmat, ix, iy, fx, fy, out); break;
-      case 5: dev_window_sum<NCH, TS, 5>(S, wmat, ix, iy, fx, fy, out); break;
-      case 6: dev_window_sum<NCH, TS, 6>(S, wmat, ix, iy, fx, fy, out); break;
-      default: dev_window_sum<NCH, TS, 7>(S, wmat, ix, iy, fx, fy, out); break;
-    }
-  }
+  Located L = dev_locate(S, degree, cx, cy);
+  const int h2 = degree / 2;
+  const float* p0 = S.core + (ptrdiff_t)(L.iy - h2) * S.stride + (ptrdiff_t)(L.ix - h2) * TS;
+  dev_window_eval<NCH, TS, DEG, false>(p0, S.stride, degree, wmat, L.fx, L.fy, out);
 }
 
 // ray_to_cubeface, geometry.h:1178-1357 (>= ties favour x over y over z)
@@ -420,21 +435,16 @@ __device__ __forceinline__ void dev_cubeface(const float c[3], int& face, float 
   }
 }
 
-// environment::eval (environment.h:1821-1842) over mount_t::eval (:1172-1196) or
-// cubemap_view_t::eval (:1473-1486). Returns the cube face hit, or -1.
-template <int NCH, int TS, int DEG>
-__device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, const float* __restrict__ wmat,
-                                              const float r[3], float px[NCH]) {
-  int face = -1;
+// First half of environment::eval (environment.h:1821-1842): ray -> spline coordinate of the
+// facet's source, via mount_t (:1172-1196, md_to_spline :988-1006) or cubemap_view_t
+// (:1452-1486). Returns false when the ray misses a mounted image; `face` = cube face or -1.
+__device__ __forceinline__ bool dev_facet_coordinate(const FacetDev& F, const float r[3], int& face, float& cx,
+                                                     float& cy) {
+  face = -1;
   if (F.kind == EU_SRC_MOUNT) {
     float c[2];
     dev_mount_coordinate(F, r, c);
-    if (!dev_mount_mask(F, r, c)) {
-#pragma unroll
-      for (int i = 0; i < NCH; i++) px[i] = 0.0f;
-      return -1;
-    }
-    // source_t::md_to_spline, environment.h:988-1006
+    if (!dev_mount_mask(F, r, c)) return false;
     float ix = (float)((double)c[0] - F.ext_x0);
     ix /= F.ext_w;
     ix *= F.total_w;
@@ -443,7 +453,8 @@ __device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, con
     iy /= F.ext_h;
     iy *= F.total_h;
     iy -= .5f;
-    dev_spline_eval<NCH, TS, DEG>(F.src, degree, wmat, ix, iy, px);
+    cx = ix;
+    cy = iy;
   } else {
     float in_face[2], pk[2];
     dev_cubeface(r, face, in_face);
@@ -451,7 +462,6 @@ __device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, con
       in_face[0] = (float)(4.0 / EU_PI) * eu_atanf(in_face[0]);
       in_face[1] = (float)(4.0 / EU_PI) * eu_atanf(in_face[1]);
     }
-    // cubemap_view_t::get_pickup_coordinate_px, environment.h:1452-1461
     pk[0] = in_face[0] + F.refc_md;
     pk[1] = in_face[1] + F.refc_md;
     pk[0] *= F.model_to_px;
@@ -459,13 +469,34 @@ __device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, con
     pk[1] += (float)(face * F.section_px);
     pk[0] -= .5f;
     pk[1] -= .5f;
-    dev_spline_eval<NCH, TS, DEG>(F.src, degree, wmat, pk[0], pk[1], px);
+    cx = pk[0];
+    cy = pk[1];
   }
+  return true;
+}
+
+template <int NCH>
+__device__ __forceinline__ void dev_brighten(const FacetDev& F, float px[NCH]) {
   if (F.brighten != 1.0f) {
     constexpr int NCOL = (NCH == 2 || NCH == 4) ? NCH - 1 : NCH;
 #pragma unroll
     for (int i = 0; i < NCOL; i++) px[i] *= F.brighten;
   }
+}
+
+// environment::eval, gathering from HBM. Returns the cube face hit, or -1.
+template <int NCH, int TS, int DEG>
+__device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, const float* __restrict__ wmat,
+                                              const float r[3], float px[NCH]) {
+  int face;
+  float cx, cy;
+  if (!dev_facet_coordinate(F, r, face, cx, cy)) {
+#pragma unroll
+    for (int i = 0; i < NCH; i++) px[i] = 0.0f;
+    return -1;
+  }
+  dev_spline_eval<NCH, TS, DEG>(F.src, degree, wmat, cx, cy, px);
+  dev_brighten<NCH>(F, px);
   return face;
 }
 

@@ -30,6 +30,6 @@ cudaError_t eu_launch_iir_y_spherical(float* core, int stride, int nch, int w, i
                                       cudaStream_t st);
 cudaError_t eu_launch_brace(float* core, int stride, int nch, int w, int h, int lx, int rx, int ly, int ry, int bc0,
                             int bc1, int spherical, cudaStream_t st);
-cudaError_t eu_launch_cubemap_support(float* ir, int nch, int face_px, int section_px, int left, int right,
+cudaError_t eu_launch_cubemap_support(float* ir, int pitch, int nch, int face_px, int section_px, int left, int right,
                                       double refc_md, double model_to_px, int* n_launches, cudaStream_t st);
-cudaError_t eu_launch_pad_texels(const float* src, float* dst, size_t n_texels, int nch, cudaStream_t st);
+cudaError_t eu_launch_pad_texels(const float* src, int src_pitch, float* dst, int cw, int chh, int nch, cudaStream_t st);

@@ -75,6 +75,10 @@ struct RenderParams {
   int32_t n_taps;     // 0: plain rays (ninputs 3), else twining (ninputs 9)
   int32_t nch;
   int32_t tstride;    // floats per texel in HBM: nch, or 4 (padded RGB); same for all facets
+  int32_t use_tiles;  // 1: stage the gather footprint in shared memory where the kernel supports it
+  int32_t src_cw, src_ch;  // container shape of f0's source in texels (tile path)
+  int32_t src_lx, src_ly;  // its left / top brace: core texel (0,0) is container texel (lx, ly)
+  const float* src_base;   // first float of f0's container (256-byte aligned, rows 16-byte aligned)
   int32_t row0, row1;  // rows rendered by this launch
   float* out;          // first float of row `row0`
   int32_t* index_out;  // optional index plane (face / winning facet)

@@ -11,6 +11,8 @@
 // MODE (single facet / voronoi / hdr_merge), TWINE, DEG (1, 3, or -1 = degree read at run time).
 // Included by render_c*.cu, one translation unit per (NCH, TS) so that they compile in parallel.
 #pragma once
+#include <limits.h>
+
 #include "eu_device.cuh"
 #include "kernels.h"
 
@@ -179,8 +181,215 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
   if (P.index_out) P.index_out[o] = idx;
 }
 
+// ------------------------------------------------------------------------------------------
+// Single-facet render with the block's gather footprint staged in shared memory.
+//
+// The direct kernel above is bound by the L1 data pipe: a quarter-warp 128-bit gather whose
+// texels straddle a 128-byte line costs two wavefronts, and every tap of every pixel goes
+// through it. Here a block first locates all its pixels, reduces the bounding box of their
+// windows, and pulls exactly those container rows into shared memory with one bulk asynchronous
+// copy per row (cp.async.bulk -> mbarrier complete_tx, the TMA engine: no registers, no LSU
+// instructions, 16-byte granules). The windows are then read from shared memory, where an
+// unaligned run of consecutive texels is conflict-free. Blocks whose footprint does not fit
+// (cube-face seams, the +-pi seam, poles) take the direct path; with twining every tap checks
+// its own window against the staged box and falls back to HBM individually. Values and their
+// order of combination are untouched: the result is bit-identical to the direct kernel.
+// ------------------------------------------------------------------------------------------
+#define EU_TILE_FLOATS 6144  // 24 KB staged footprint per block
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one row of the footprint: global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_row_g2s(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NCH, int TS, bool TWINE, int DEG>
+__global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_constant__ RenderParams P) {
+  static_assert(DEG == 1 || DEG == 3, "tile path is built for the bilinear and cubic evaluators");
+  constexpr int ORDER = DEG + 1, H2 = DEG / 2;
+  constexpr int NWARP = TILE_X * TILE_Y / 32;
+  __shared__ __align__(128) float tile[EU_TILE_FLOATS];
+  __shared__ int red[NWARP][4];
+  __shared__ int box[4];  // A0 (float offset in the container row), first container row, floats per row, rows
+  __shared__ __align__(8) uint64_t mbar;
+
+  const TargetDev& T = P.trg;
+  const FacetDev& F = P.f0;
+  const SourceDev& S = F.src;
+  const int tid = threadIdx.y * TILE_X + threadIdx.x;
+  const int x = blockIdx.x * TILE_X + threadIdx.x;
+  const int y = P.row0 + blockIdx.y * TILE_Y + threadIdx.y;
+  const bool inside = x < T.width && y < P.row1;
+  if (tid == 0) mbar_init(&mbar, 1);
+
+  // ---- phase 1: rays and window origins ------------------------------------------------
+  const int xc = inside ? x : 0, yc = inside ? y : P.row0;
+  const int xf = first_lane_column(xc);
+  float2 c0 = __ldg(P.col_tab + xc), r0 = __ldg(P.row_tab + yc);
+  ColTerm col{c0.x, c0.y};
+  RowTerm row{r0.x, r0.y};
+  ColTerm first = col;
+  if (T.projection == EU_CYLINDRICAL && T.normalize) {
+    float2 f0 = __ldg(P.col_tab + xf);
+    first = ColTerm{f0.x, f0.y};
+  }
+  float r00[3];
+  dev_stepper(T, F.xx, F.yy, F.zz, col, row, first, yc, r00);
+  int face;
+  float cx, cy;
+  bool hit = dev_facet_coordinate(F, r00, face, cx, cy) && inside;
+  Located L = dev_locate(S, DEG, hit ? cx : 0.0f, hit ? cy : 0.0f);
+  // window origin in CONTAINER texel coordinates (container rows start 16-byte aligned)
+  const int lox = L.ix - H2 + P.src_lx, loy = L.iy - H2 + P.src_ly;
+  {
+    int mnx = hit ? lox : INT_MAX, mxx = hit ? lox : INT_MIN, mny = hit ? loy : INT_MAX, mxy = hit ? loy : INT_MIN;
+    mnx = __reduce_min_sync(0xffffffffu, mnx);
+    mxx = __reduce_max_sync(0xffffffffu, mxx);
+    mny = __reduce_min_sync(0xffffffffu, mny);
+    mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if ((tid & 31) == 0) {
+      red[tid >> 5][0] = mnx; red[tid >> 5][1] = mxx; red[tid >> 5][2] = mny; red[tid >> 5][3] = mxy;
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    int l = tid < NWARP ? tid : 0;
+    int mnx = __reduce_min_sync(0xffffffffu, red[l][0]);
+    int mxx = __reduce_max_sync(0xffffffffu, red[l][1]);
+    int mny = __reduce_min_sync(0xffffffffu, red[l][2]);
+    int mxy = __reduce_max_sync(0xffffffffu, red[l][3]);
+    if (tid == 0) {
+      int rows = 0, a0 = 0, wf = 0;
+      if (mnx <= mxx) {  // at least one pixel of the block hits the source
+        if constexpr (TWINE) {  // sub-rays stray up to half a pixel from the centre ray
+          int bw = mxx - mnx + 1, bh = mxy - mny + 1;
+          int mx = (bw * 5) / 64 + 2, my = (bh * 5) / 64 + 2;
+          mnx -= mx; mxx += mx; mny -= my; mxy += my;
+          // keep the box inside the container
+          mnx = max(mnx, 0); mny = max(mny, 0);
+          mxx = min(mxx, P.src_cw - ORDER); mxy = min(mxy, P.src_ch - ORDER);
+        }
+        a0 = (mnx * TS) & ~3;  // 16-byte granule within the container row
+        wf = (((mxx + ORDER) * TS - a0) + 3) & ~3;
+        rows = mxy - mny + ORDER;
+        if (rows > TILE_X * TILE_Y || rows * wf > EU_TILE_FLOATS || wf <= 0 || rows <= 0) rows = 0;
+      }
+      box[0] = a0; box[1] = mny; box[2] = wf; box[3] = rows;
+      if (rows > 0) mbar_expect_tx(&mbar, (uint32_t)(rows * wf) * 4u);
+    }
+  }
+  __syncthreads();
+  const int a0 = box[0], by0 = box[1], wf = box[2], rows = box[3];
+  const bool staged = rows > 0;
+  if (staged) {
+    // rows are dealt round-robin to the warps (the copy is issued from the uniform datapath, so
+    // the lanes of one warp take turns)
+    const int rid = (tid & 31) * NWARP + (tid >> 5);
+    if (rid < rows)
+      bulk_row_g2s(tile + rid * wf, P.src_base + (ptrdiff_t)(by0 + rid) * S.stride + a0, (uint32_t)wf * 4u, &mbar);
+    mbar_wait(&mbar, 0);
+  }
+
+  // ---- phase 2: windows ------------------------------------------------------------------
+  if (!inside) return;
+  float px[NCH];
+  if constexpr (!TWINE) {
+    if (!hit) {
+#pragma unroll
+      for (int c = 0; c < NCH; c++) px[c] = 0.0f;
+    } else {
+      if (staged)
+        dev_window_eval<NCH, TS, DEG, true>(tile + (loy - by0) * wf + (lox * TS - a0), wf, DEG, P.wmat, L.fx, L.fy, px);
+      else
+        dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)loy * S.stride + (ptrdiff_t)lox * TS, S.stride, DEG,
+                                             P.wmat, L.fx, L.fy, px);
+      dev_brighten<NCH>(F, px);
+    }
+  } else {
+    // deriv_stepper (stepper.h:1606-1694) + twine_t (twining.h:106-263)
+    float2 c1 = __ldg(P.col_tab + T.width + x), r1 = __ldg(P.row_tab + T.height + y);
+    ColTerm colb{c1.x, c1.y};
+    RowTerm rowb{r1.x, r1.y};
+    ColTerm firstb = colb;
+    if (T.projection == EU_CYLINDRICAL && T.normalize) {
+      float2 f1 = __ldg(P.col_tab + T.width + xf);
+      firstb = ColTerm{f1.x, f1.y};
+    }
+    float du[3], dv[3], help[NCH];
+    dev_stepper(T, F.xx, F.yy, F.zz, colb, row, firstb, y, du);
+    dev_stepper(T, F.xx, F.yy, F.zz, col, rowb, first, y, dv);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      du[c] = du[c] - r00[c];
+      dv[c] = dv[c] - r00[c];
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; c++) px[c] = 0.0f;
+    const int bx1 = a0 + wf, by1 = by0 + rows;
+    for (int k = 0; k < P.n_taps; k++) {
+      float tx = __ldg(P.taps + 3 * k), ty = __ldg(P.taps + 3 * k + 1), tw = __ldg(P.taps + 3 * k + 2);
+      float r[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) r[c] = r00[c] + tx * du[c] + ty * dv[c];
+      int fc;
+      float sx, sy;
+      if (!dev_facet_coordinate(F, r, fc, sx, sy)) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) help[c] = 0.0f;
+      } else {
+        Located K = dev_locate(S, DEG, sx, sy);
+        const int kx = K.ix - H2 + P.src_lx, ky = K.iy - H2 + P.src_ly;
+        const bool in_box = staged && kx * TS >= a0 && (kx + ORDER) * TS <= bx1 && ky >= by0 && ky + ORDER <= by1;
+        if (in_box)
+          dev_window_eval<NCH, TS, DEG, true>(tile + (ky - by0) * wf + (kx * TS - a0), wf, DEG, P.wmat, K.fx, K.fy, help);
+        else
+          dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)ky * S.stride + (ptrdiff_t)kx * TS, S.stride, DEG,
+                                               P.wmat, K.fx, K.fy, help);
+        dev_brighten<NCH>(F, help);
+      }
+#pragma unroll
+      for (int c = 0; c < NCH; c++) px[c] += tw * help[c];
+    }
+  }
+  float* dst = P.out + ((size_t)(y - P.row0) * T.width + x) * NCH;
+  if constexpr (NCH == 4) {
+    *reinterpret_cast<float4*>(dst) = make_float4(px[0], px[1], px[2], px[3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCH; c++) dst[c] = px[c];
+  }
+}
+
 template <int NCH, int TS, int MODE, bool TWINE>
 static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st) {
+  if constexpr (MODE == EU_MODE_SINGLE) {
+    // footprint-staged kernel: needs 16-byte row granules and a pixel output (no index plane)
+    if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0) {
+      if (P.degree == 1) { k_render_tiled<NCH, TS, TWINE, 1><<<grid, block, 0, st>>>(P); return; }
+      if (P.degree == 3) { k_render_tiled<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P); return; }
+    }
+  }
   switch (P.degree) {
     case 1: k_render<NCH, TS, MODE, TWINE, 1><<<grid, block, 0, st>>>(P); break;
     case 3: k_render<NCH, TS, MODE, TWINE, 3><<<grid, block, 0, st>>>(P); break;

@@ -89,24 +89,51 @@ __device__ __forceinline__ float iir_iacc(const IirDev& f, Acc& c, int M, int k)
   }
 }
 
-template <typename Acc>
-__device__ __forceinline__ void iir_line(const IirDev& f, Acc& c, int M) {  // recursive.h:631-729
+// solve_gain_inlined (recursive.h:631-729) on one line, in place. The recursion itself is serial,
+// but the loads are not: elements are fetched U at a time before the dependent chain runs over
+// them, so that every thread keeps U loads in flight (the in-place stores would otherwise
+// serialise the loads behind them).
+template <int U, typename Acc>
+__device__ __forceinline__ void iir_line(const IirDev& f, Acc& c, int M) {
   if (M == 1 || f.npoles < 1) return;
-  float p = f.pole[0], g = f.gain;
-  float X = g * iir_icc(f, c, M, 0);
-  c(0) = X;
-  for (int n = 1; n < M; n++) { X = g * c(n) + p * X; c(n) = X; }
-  X = iir_iacc(f, c, M, 0);
-  c(M - 1) = X;
-  for (int n = M - 2; n >= 0; n--) { X = p * (X - c(n)); c(n) = X; }
-  for (int k = 1; k < f.npoles; k++) {
-    p = f.pole[k];
-    X = iir_icc(f, c, M, k);
+  float v[U];
+  for (int k = 0; k < f.npoles; k++) {
+    const float p = f.pole[k], g = f.gain;
+    float X = iir_icc(f, c, M, k);
+    if (k == 0) X = g * X;
     c(0) = X;
-    for (int n = 1; n < M; n++) { X = c(n) + p * X; c(n) = X; }
+    for (int n0 = 1; n0 < M; n0 += U) {
+      const int cnt = min(U, M - n0);
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (u < cnt) v[u] = c(n0 + u);
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (u < cnt) {
+          X = (k == 0) ? g * v[u] + p * X : v[u] + p * X;
+          v[u] = X;
+        }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (u < cnt) c(n0 + u) = v[u];
+    }
     X = iir_iacc(f, c, M, k);
     c(M - 1) = X;
-    for (int n = M - 2; n >= 0; n--) { X = p * (X - c(n)); c(n) = X; }
+    for (int n0 = M - 2; n0 >= 0; n0 -= U) {
+      const int cnt = min(U, n0 + 1);
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (u < cnt) v[u] = c(n0 - u);
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (u < cnt) {
+          X = p * (X - v[u]);
+          v[u] = X;
+        }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (u < cnt) c(n0 - u) = v[u];
+    }
   }
 }
 
@@ -134,7 +161,86 @@ __global__ void k_iir_x(float* core, int stride, int nch, int w, int h, IirDev f
   if (i >= h * nch) return;
   int c = i / h, y = i % h;
   StrideAcc a{core + (ptrdiff_t)y * stride + c, nch};
-  iir_line(f, a, w);
+  iir_line<8>(f, a, w);
+}
+
+// lines along x, tiled: a block owns IIR_R rows (all channels: IIR_R*NCH lines, one thread
+// each). The row segments of a tile are moved between HBM and shared memory by all threads
+// together (coalesced 4-byte accesses along the rows); the recursion runs on the tile in shared
+// memory, carrying X from tile to tile: a forward sweep over the tiles for the causal filter, a
+// backward sweep for the anticausal one. The initial coefficients read the line in HBM directly
+// (they touch `horizon` elements). Tile pitch = IIR_TW*NCH + NCH floats, so that thread
+// (row r, channel ch) = lane r*NCH+ch reads bank (lane + n*NCH) mod 32: conflict-free.
+#define IIR_R 32
+#define IIR_TW 64
+template <int NCH>
+__global__ void __launch_bounds__(IIR_R* NCH) k_iir_x_tiled(float* core, int stride, int w, int h, IirDev f) {
+  constexpr int ROWF = IIR_TW * NCH;  // floats per tile row
+  constexpr int PITCH = ROWF + NCH;
+  constexpr int NT = IIR_R * NCH;
+  __shared__ float tile[IIR_R * PITCH];
+  const int tid = threadIdx.x;
+  const int y0 = blockIdx.x * IIR_R;
+  const int r = tid / NCH, ch = tid % NCH;
+  const bool active = (y0 + r) < h;
+  const int rows = min(IIR_R, h - y0);
+  const int ntiles = (w + IIR_TW - 1) / IIR_TW;
+  StrideAcc line{core + (ptrdiff_t)(y0 + (active ? r : 0)) * stride + ch, NCH};
+  float* const trow = tile + r * PITCH + ch;
+  float* const base = core + (ptrdiff_t)y0 * stride;
+  auto load_tile = [&](int t) {
+    const int x0f = t * ROWF, nf = min(ROWF, w * NCH - x0f);
+    for (int i = tid; i < rows * ROWF; i += NT) {
+      int rr = i / ROWF, kk = i - rr * ROWF;
+      if (kk < nf) tile[rr * PITCH + kk] = base[(ptrdiff_t)rr * stride + x0f + kk];
+    }
+  };
+  auto store_tile = [&](int t) {
+    const int x0f = t * ROWF, nf = min(ROWF, w * NCH - x0f);
+    for (int i = tid; i < rows * ROWF; i += NT) {
+      int rr = i / ROWF, kk = i - rr * ROWF;
+      if (kk < nf) base[(ptrdiff_t)rr * stride + x0f + kk] = tile[rr * PITCH + kk];
+    }
+  };
+  if (w == 1 || f.npoles < 1) return;
+  for (int k = 0; k < f.npoles; k++) {
+    const float p = f.pole[k], g = f.gain;
+    float X = 0.0f;
+    if (active) {
+      X = iir_icc(f, line, w, k);
+      if (k == 0) X = g * X;
+    }
+    __syncthreads();  // every line has read its initial sum before the sweep rewrites the rows
+    for (int t = 0; t < ntiles; t++) {
+      load_tile(t);
+      __syncthreads();
+      if (active) {
+        const int n0 = t * IIR_TW, cnt = min(IIR_TW, w - n0);
+        for (int n = 0; n < cnt; n++) {
+          if (n0 + n > 0) X = (k == 0) ? g * trow[n * NCH] + p * X : trow[n * NCH] + p * X;
+          trow[n * NCH] = X;
+        }
+      }
+      __syncthreads();
+      store_tile(t);
+      __syncthreads();
+    }
+    if (active) X = iir_iacc(f, line, w, k);  // reads what this block has just stored
+    for (int t = ntiles - 1; t >= 0; t--) {
+      load_tile(t);
+      __syncthreads();
+      if (active) {
+        const int n0 = t * IIR_TW, cnt = min(IIR_TW, w - n0);
+        for (int n = cnt - 1; n >= 0; n--) {
+          if (n0 + n < w - 1) X = p * (X - trow[n * NCH]);
+          trow[n * NCH] = X;
+        }
+      }
+      __syncthreads();
+      store_tile(t);
+      __syncthreads();
+    }
+  }
 }
 
 // lines along y: one thread per float of a row (column x channel): consecutive threads touch
@@ -145,7 +251,7 @@ __global__ void k_iir_y(float* core, int stride, int rowfloats, int h, int n_sec
   if (i >= rowfloats * n_sections) return;
   int s = i / rowfloats, x = i % rowfloats;
   StrideAcc a{core + (ptrdiff_t)s * h * stride + x, stride};
-  iir_line(f, a, h);
+  iir_line<16>(f, a, h);
 }
 
 __global__ void k_iir_y_spherical(float* core, int stride, int nch, int w, int h, IirDev f) {
@@ -153,7 +259,7 @@ __global__ void k_iir_y_spherical(float* core, int stride, int nch, int w, int h
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= half * nch) return;
   PoleAcc a{core + i, core + (ptrdiff_t)(h - 1) * stride + (ptrdiff_t)half * nch + i, stride, h};
-  iir_line(f, a, 2 * h);
+  iir_line<16>(f, a, 2 * h);
 }
 
 // brace: every container texel outside the core is a copy of a core texel (PERIODIC / REFLECT
@@ -187,15 +293,14 @@ __global__ void k_brace(float* core, int stride, int nch, int w, int h, int lx, 
 // ---- cubemap IR support (cubemap.h:607-911) ------------------------------------------------
 // 1-px mirrored ring around every cube face (mirror_around, :607-660). Corners are written by
 // the column pass from the row pass' result in the reference; the value is the face corner.
-__global__ void k_cm_ring(float* ir, int nch, int F, int S, int L, int R) {
+__global__ void k_cm_ring(float* ir, int stride, int nch, int F, int S, int L, int R) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // position along the ring side, -1..F
   int face = blockIdx.y, side = blockIdx.z;
   int t = i - 1;
   if (t > F) return;
   int cmin = L > 0 ? -1 : 0, cmax = R > 0 ? F : F - 1;
   if (t < cmin || t > cmax) return;
-  int stride = S * nch;
-  float* f0 = ir + ((ptrdiff_t)(face * S + L) * S + L) * nch;  // face texel (0,0)
+  float* f0 = ir + (ptrdiff_t)(face * S + L) * stride + (ptrdiff_t)L * nch;  // face texel (0,0)
   auto px = [&](int x, int y) { return f0 + (ptrdiff_t)y * stride + (ptrdiff_t)x * nch; };
   int tc = t < 0 ? 0 : (t > F - 1 ? F - 1 : t);  // the row pass has filled (t,-1)/(t,F) from (t,0)/(t,F-1)
   const float* s;
@@ -241,24 +346,32 @@ __global__ void k_cm_fill(float* ir, SourceDev S, int face, int x0, int y0, int 
   pk[0] -= .5f;
   pk[1] -= .5f;
   dev_spline_eval<NCH, NCH, 1>(S, 1, nullptr, pk[0], pk[1], px);
-  float* d = ir + ((ptrdiff_t)(face * section_px + y) * section_px + x) * NCH;
+  float* d = ir + (ptrdiff_t)(face * section_px + y) * S.stride + (ptrdiff_t)x * NCH;
 #pragma unroll
   for (int c = 0; c < NCH; c++) d[c] = px[c];
 }
 
-// interleaved nch-float texels -> 16-byte texels (padded layout for one-instruction gathers)
-__global__ void k_pad_texels(const float* __restrict__ src, float4* __restrict__ dst, size_t n, int nch) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* s = src + i * nch;
-  float4 v = make_float4(s[0], nch > 1 ? s[1] : 0.f, nch > 2 ? s[2] : 0.f, 0.f);
-  dst[i] = v;
+// interleaved nch-float texels (rows of src_pitch floats) -> dense 16-byte texels
+__global__ void k_pad_texels(const float* __restrict__ src, int src_pitch, float4* __restrict__ dst, int cw, int chh,
+                             int nch) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= cw || y >= chh) return;
+  const float* s = src + (size_t)y * src_pitch + (size_t)x * nch;
+  dst[(size_t)y * cw + x] = make_float4(s[0], nch > 1 ? s[1] : 0.f, nch > 2 ? s[2] : 0.f, 0.f);
 }
 
 // ---- launchers -----------------------------------------------------------------------------
 cudaError_t eu_launch_iir_x(float* core, int stride, int nch, int w, int h, const IirDev& f, cudaStream_t st) {
-  int n = h * nch;
-  k_iir_x<<<(n + 63) / 64, 64, 0, st>>>(core, stride, nch, w, h, f);
+  int nb = (h + IIR_R - 1) / IIR_R;
+  switch (nch) {
+    case 1: k_iir_x_tiled<1><<<nb, IIR_R * 1, 0, st>>>(core, stride, w, h, f); break;
+    case 3: k_iir_x_tiled<3><<<nb, IIR_R * 3, 0, st>>>(core, stride, w, h, f); break;
+    case 4: k_iir_x_tiled<4><<<nb, IIR_R * 4, 0, st>>>(core, stride, w, h, f); break;
+    default: {
+      int n = h * nch;
+      k_iir_x<<<(n + 63) / 64, 64, 0, st>>>(core, stride, nch, w, h, f);
+    }
+  }
   return cudaGetLastError();
 }
 cudaError_t eu_launch_iir_y(float* core, int stride, int nch, int w, int h, int n_sections, const IirDev& f,
@@ -281,16 +394,16 @@ cudaError_t eu_launch_brace(float* core, int stride, int nch, int w, int h, int 
   return cudaGetLastError();
 }
 
-cudaError_t eu_launch_cubemap_support(float* ir, int nch, int F, int S, int L, int R, double refc_md,
+cudaError_t eu_launch_cubemap_support(float* ir, int pitch, int nch, int F, int S, int L, int R, double refc_md,
                                       double model_to_px, int* n_launches, cudaStream_t st) {
   *n_launches = 0;
   if (L == 0 && R == 0) return cudaSuccess;
   dim3 rgrid((F + 2 + 127) / 128, 6, 4);
-  k_cm_ring<<<rgrid, 128, 0, st>>>(ir, nch, F, S, L, R);
+  k_cm_ring<<<rgrid, 128, 0, st>>>(ir, pitch, nch, F, S, L, R);
   ++*n_launches;
   SourceDev src;
   src.core = ir;
-  src.stride = S * nch;
+  src.stride = pitch;
   src.tstride = nch;
   src.nch = nch;
   src.w = S;
@@ -321,7 +434,8 @@ cudaError_t eu_launch_cubemap_support(float* ir, int nch, int F, int S, int L, i
   return cudaGetLastError();
 }
 
-cudaError_t eu_launch_pad_texels(const float* src, float* dst, size_t n_texels, int nch, cudaStream_t st) {
-  k_pad_texels<<<(unsigned)((n_texels + 255) / 256), 256, 0, st>>>(src, reinterpret_cast<float4*>(dst), n_texels, nch);
+cudaError_t eu_launch_pad_texels(const float* src, int src_pitch, float* dst, int cw, int chh, int nch, cudaStream_t st) {
+  dim3 grid((cw + 255) / 256, chh);
+  k_pad_texels<<<grid, 256, 0, st>>>(src, src_pitch, reinterpret_cast<float4*>(dst), cw, chh, nch);
   return cudaGetLastError();
 }

@@ -24,7 +24,8 @@ class Engine:
     def stage(self, job, structs=None, keys=None, padded=False):
         """Upload + brace + prefilter every facet of the job. Returns the handle array."""
         t, fa, o, taps, ntaps = structs or job.structs(self.lib)
-        o.reserved[0] = 1 if padded else 0
+        if padded:
+            o.reserved[0] = 1
         hs = (capi.SourceH * len(job.facets))()
         self.last_stage_timing = []
         for i, f in enumerate(job.facets):
@@ -42,7 +43,8 @@ class Engine:
     def stage_device(self, job, dev_ptrs, structs=None, stream=0, padded=False):
         """Same, rasters already in device memory (dev_ptrs: one device address per facet)."""
         t, fa, o, taps, ntaps = structs or job.structs(self.lib)
-        o.reserved[0] = 1 if padded else 0
+        if padded:
+            o.reserved[0] = 1
         hs = (capi.SourceH * len(job.facets))()
         self.last_stage_timing = []
         for i in range(len(job.facets)):

@@ -67,6 +67,21 @@ def test_padded_texel_layout_is_bit_exact(engine, name):
     assert harness.compare(out, harness.oracle_render(job))["n_diff"] == 0
 
 
+@pytest.mark.parametrize("name", ["ll_rect_d1_rot", "ll_rect_d3_rot", "cm_sph_d3", "ba6_sph_d1", "ll_fish_d1_tw4",
+                                  "ll_cube_d1", "cm_rect_d1_tw3_rot", "lens1_rect_d3_tw2", "grey_ll_rect_d3"])
+@pytest.mark.parametrize("padded", [False, True])
+def test_direct_and_staged_kernels_agree(engine, name, padded):
+    """Single-facet jobs run the footprint-staged kernel (cp.async.bulk into shared memory) by
+    default; no_tiles forces the direct-gather kernel. Both must equal the oracle bit for bit."""
+    ref = harness.oracle_render(jobs.JOBS[name])
+    for no_tiles in (False, True):
+        job = copy.copy(jobs.JOBS[name])
+        job.padded, job.no_tiles = padded, no_tiles
+        out = engine.render(job)
+        c = harness.compare(out, ref)
+        assert c["n_diff"] == 0, (no_tiles, c)
+
+
 def test_twine_single_centre_tap_equals_plain(engine):
     """twining with one tap (0,0,1) == no twining (normalised rays differ from
     unnormalised ones only by scale, which lat/lon lookup ignores up to rounding)."""

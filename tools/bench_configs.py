@@ -34,9 +34,11 @@ def run(eng, job, alg, steps, padded, keep_output=False, flush=None):
         for p in padded[:-1]:
             print(json.dumps(run(eng, job, alg, steps, p, False, flush)[0]), flush=True)
         padded = padded[-1]
+    job.padded = bool(padded & 1)
+    job.no_tiles = bool(padded & 2)
     st = job.structs(eng.lib)
     t = st[0]
-    hs = eng.stage(job, st, padded=padded)
+    hs = eng.stage(job, st)
     stage_ms = sum(tm.render_ms for tm in eng.last_stage_timing)
     h2d_ms = sum(tm.h2d_ms for tm in eng.last_stage_timing)
     out = torch.empty((t.height, t.width, t.nchannels), dtype=torch.float32, device="cuda")
@@ -75,7 +77,7 @@ def run(eng, job, alg, steps, padded, keep_output=False, flush=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="C1,C2,C3a,C3b,C4")
-    ap.add_argument("--padded", default="0", help="0, 1 or 0,1 (both layouts on the same inputs)")
+    ap.add_argument("--padded", default="0", help="comma list of variants: bit 0 = 16-byte texels, bit 1 = direct-gather kernel (no staging)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--scale", type=int, default=1)
     a = ap.parse_args()
