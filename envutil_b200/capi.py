@@ -75,7 +75,7 @@ SYMBOLS = {
     "eu_target_prepare": (C.c_int, [C.POINTER(Target)]),
     "eu_rotation_matrix": (None, [C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     "eu_facet_basis": (None, [C.POINTER(Target), C.POINTER(Facet), C.POINTER(C.c_double)]),
-    "eu_make_spread": (C.c_int, [C.POINTER(Target), C.c_int, C.POINTER(Facet), C.c_int, C.c_double, C.c_double,
+    "eu_make_spread": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet), C.c_int, C.c_double, C.c_double,
                                  C.c_double, C.c_double, C.c_int, C.POINTER(Tap), C.c_int, C.POINTER(C.c_int)]),
     "eu_cubemap_metrics": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int32),
                                      C.POINTER(C.c_double)]),

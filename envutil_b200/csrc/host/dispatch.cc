@@ -1,0 +1,128 @@
+// dispatch.cc - cuda_dispatch: the dispatch_base whose payload() runs on the B200.
+// Replaces dispatch::payload -> roll_out -> fuse -> work (reference envutil_payload.cc:2408,
+// 2336,1885,425): per facet find-or-stage the source (the asset cache lives in the library),
+// render, write the raster, conclude the cycle.
+#include <chrono>
+#include <cstdio>
+
+#include "envutil_host.h"
+
+namespace eu_host {
+
+namespace {
+
+struct cuda_dispatch : public dispatch_base {
+  int payload(int nchannels, int ninputs, int projection) const override {
+    arguments& a = args;
+    int rc = eu_init(a.device);
+    if (rc) {
+      fprintf(stderr, "envutil_b200: %s\n", eu_last_error());
+      return rc;
+    }
+    eu_target_t t = a.t;
+    t.projection = projection;
+    t.nchannels = nchannels;
+    eu_opts_t o{};
+    o.spline_degree = a.spline_degree;
+    o.prefilter_degree = a.prefilter_degree;
+    o.synopsis = a.synopsis == "hdr_merge" ? EU_SYN_HDR_MERGE : EU_SYN_PANORAMA;
+    o.solo = a.solo;
+    o.support_min = a.support_min;
+    o.tile_size = a.tile_size;
+    o.reserved[0] = a.padded ? 1 : 0;
+    o.reserved[1] = a.no_tiles ? 1 : 0;
+    std::vector<eu_facet_t> fv;
+    std::vector<eu_source_h> sv;
+    float stage_ms = 0, h2d_ms = 0;
+    for (const auto& fs : a.facet_spec_v) {
+      fv.push_back(fs.f);
+      // one staged source per (file, degree, prefilter, layout): the reference's asset_key is the
+      // file name because a process run has one degree; a library that outlives jobs needs more
+      std::string key = fs.asset_key + "|" + std::to_string(o.spline_degree) + "|" + std::to_string(o.prefilter_degree) +
+                        "|" + std::to_string(o.reserved[0]) + "|" + std::to_string(o.support_min) + "|" +
+                        std::to_string(o.tile_size);
+      eu_source_h h = eu_source_find(key.c_str());
+      if (!h) {
+        int w, hh, c;
+        std::vector<float> px;
+        if (!read_raster(fs.filename, w, hh, c, px) || w != fs.f.width || hh != fs.f.height || c != fs.f.nchannels) {
+          fprintf(stderr, "envutil_b200: cannot read facet image '%s'\n", fs.filename.c_str());
+          return EU_ERR_ARGUMENT;
+        }
+        eu_timing_t tm{};
+        rc = eu_source_upload(key.c_str(), &fv.back(), &o, px.data(), &h, &tm);
+        if (rc) {
+          fprintf(stderr, "envutil_b200: %s\n", eu_last_error());
+          return rc;
+        }
+        stage_ms += tm.render_ms;
+        h2d_ms += tm.h2d_ms;
+      }
+      sv.push_back(h);
+    }
+    const std::vector<eu_tap_t>& taps = a.twine_spread;
+    int n_taps = ninputs == 9 ? (int)taps.size() : 0;  // ninputs == 9 <=> twining (envutil_main.cc:1673)
+    std::vector<float> out((size_t)t.width * t.height * nchannels);
+    eu_timing_t tm{};
+    rc = eu_render(&t, &o, (int)fv.size(), fv.data(), sv.data(), taps.data(), n_taps, out.data(), &tm);
+    if (rc) {
+      fprintf(stderr, "envutil_b200: %s\n", eu_last_error());
+      return rc;
+    }
+    if (a.verbose) {
+      // the reference prints wall-clock "frame rendering time" (envutil_payload.cc:555)
+      printf("frame rendering time: %.3f ms (device), staging %.3f ms, h2d %.3f ms, d2h %.3f ms, %d launches\n",
+             tm.render_ms, stage_ms, h2d_ms, tm.d2h_ms, tm.launches);
+    }
+    if (!write_raster(a.output, t.width, t.height, nchannels, out.data())) {
+      fprintf(stderr, "envutil_b200: cannot write '%s'\n", a.output.c_str());
+      return EU_ERR_ARGUMENT;
+    }
+    eu_cycle();  // conclude_cycle(), envutil_payload.cc:2433
+    return 0;
+  }
+};
+
+}  // namespace
+
+const dispatch_base* get_dispatch() {
+  static cuda_dispatch d;
+  return &d;
+}
+
+// core(), envutil_main.cc:1634-1733
+int core(int argc, const char** argv) {
+  int rc = args.init(argc, argv);
+  if (rc) {
+    fprintf(stderr, "envutil_b200: %s\n", args.error.c_str());
+    return rc;
+  }
+  const dispatch_base* dp = get_dispatch();
+  if (args.verbose) printf("using %s ISA\n", dp->hwy_target_name);
+  rc = args.twine_setup();
+  if (rc) {
+    fprintf(stderr, "envutil_b200: %s\n", args.error.c_str());
+    return rc;
+  }
+  int nch = args.nchannels;
+  int ninp = (args.twine == 0) ? 3 : 9;
+  if (args.dry_run) {  // print what the kernels would be given; no GPU needed
+    const eu_target_t& t = args.t;
+    printf("target %s %dx%d nch %d hfov %.17g yaw %.17g pitch %.17g roll %.17g\n", projection_name[t.projection], t.width,
+           t.height, nch, t.hfov, t.yaw, t.pitch, t.roll);
+    printf("extent %.17g %.17g %.17g %.17g step %.17g\n", t.x0, t.x1, t.y0, t.y1, t.step);
+    printf("degree %d prefilter %d twine %d ninputs %d synopsis %s solo %d\n", args.spline_degree, args.prefilter_degree,
+           args.twine, ninp, args.synopsis.c_str(), args.solo);
+    for (const auto& f : args.facet_spec_v)
+      printf("facet %d %s %s %dx%dx%d hfov %.17g ypr %.17g %.17g %.17g step %.17g brighten %.9g lcp %d shift %.17g %.17g "
+             "shear %.17g %.17g\n",
+             f.facet_no, f.filename.c_str(), projection_name[f.f.projection], f.f.width, f.f.height, f.f.nchannels,
+             f.f.hfov, f.f.yaw, f.f.pitch, f.f.roll, f.f.step, f.brighten, f.f.has_lcp, f.f.shift_h, f.f.shift_v,
+             f.f.shear_g, f.f.shear_t);
+    for (const auto& c : args.twine_spread) printf("tap %.9g %.9g %.9g\n", c.x, c.y, c.w);
+    return 0;
+  }
+  return dp->payload(nch, ninp, args.t.projection);
+}
+
+}  // namespace eu_host

@@ -261,13 +261,12 @@ static void make_spread(std::vector<eu_tap_t>& trg, int w, int h, float d, float
   }
 }
 
-int eu_make_spread(const eu_target_t* t, int n_facets, const eu_facet_t* facets, int twine,
-                   double twine_width, double twine_density, double twine_sigma,
-                   double twine_threshold, int twine_max, eu_tap_t* taps, int max_taps,
-                   int* twine_out) {
-  return eu_make_spread_ex(t, n_facets, facets, /*spline_degree*/ 1, /*solo*/ n_facets == 1 ? 0 : -1, twine,
-                           twine_width, twine_density, twine_sigma, twine_threshold, twine_max, taps,
-                           max_taps, twine_out);
+int eu_make_spread(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets, int twine,
+                   double twine_width, double twine_density, double twine_sigma, double twine_threshold,
+                   int twine_max, eu_tap_t* taps, int max_taps, int* twine_out) {
+  if (!o) return EU_ERR_ARGUMENT;
+  return eu_make_spread_ex(t, n_facets, facets, o->spline_degree, o->solo, twine, twine_width, twine_density,
+                           twine_sigma, twine_threshold, twine_max, taps, max_taps, twine_out);
 }
 
 int eu_cubemap_metrics(int face_px, double hfov, int support_min, int tile_size, int32_t out_i[4],
@@ -295,7 +294,7 @@ int eu_make_spread_ex(const eu_target_t* t, int n_facets, const eu_facet_t* face
   } else {
     double smallest_step = std::numeric_limits<double>::max();
     if (n_facets == 1 || solo > 0) {
-      smallest_step = facets[solo].step;
+      smallest_step = facets[n_facets == 1 ? 0 : solo].step;
     } else {
       for (int i = 0; i < n_facets; i++) smallest_step = std::min(facets[i].step, smallest_step);
     }

@@ -134,8 +134,11 @@ class Job:
         given = [e for e in eevs if e != 0]
         if not given or not self.uses_pto():
             return [float(np.float32(f.brighten)) for f in self.facets]
-        mean = sum(float(e) for e in given) / len(given)
-        return [1.0 if e == 0 else float(np.float32(2.0 ** (float(e) - mean))) for e in eevs]
+        acc = np.float32(0.0)  # `float eev_sum`, envutil_main.cc:519
+        for e in given:
+            acc = np.float32(acc + e)
+        mean = np.float32(acc / np.float32(len(given)))
+        return [1.0 if e == 0 else float(np.float32(2.0 ** float(np.float32(e - mean)))) for e in eevs]
 
     # ---- POD structs of the C ABI ----
     def structs(self, lib=None):
@@ -144,8 +147,11 @@ class Job:
         t = capi.Target()
         t.projection = capi.PROJECTION_NAMES.index(self.projection)
         t.width, t.height, t.nchannels = self.width, self.height, nch
-        t.hfov = math.radians(self.hfov)
-        t.yaw, t.pitch, t.roll = (math.radians(v) for v in (self.yaw, self.pitch, self.roll))
+        # the reference parses the target's --hfov/--yaw/--pitch/--roll as FLOAT (ap[...].get<float>,
+        # envutil_main.cc:468-477) and converts to radians in double (:1199-1202)
+        f32 = lambda v: float(np.float32(v)) * (math.pi / 180.0)
+        t.hfov = f32(self.hfov)
+        t.yaw, t.pitch, t.roll = f32(self.yaw), f32(self.pitch), f32(self.roll)
         capi.check(lib.eu_target_prepare(C.byref(t)), lib)
         n = len(self.facets)
         fa = (capi.Facet * n)()
@@ -155,10 +161,11 @@ class Job:
             s = fa[i]
             s.projection = capi.PROJECTION_NAMES.index(f.projection)
             s.width, s.height, s.nchannels = w, h, c
-            s.hfov = math.radians(f.hfov)
-            s.yaw, s.pitch, s.roll = (math.radians(v) for v in (f.yaw, f.pitch, f.roll))
+            # facet angles are parsed as doubles (%F / std::stod) and scaled by M_PI / 180.0
+            s.hfov = f.hfov * (math.pi / 180.0)
+            s.yaw, s.pitch, s.roll = (v * (math.pi / 180.0) for v in (f.yaw, f.pitch, f.roll))
             s.tr_x, s.tr_y, s.tr_z = f.tr_x, f.tr_y, -f.tr_z  # TrZ is negated (envutil_main.cc:787-789)
-            s.tp_y, s.tp_p = math.radians(f.tp_y), math.radians(f.tp_p)
+            s.tp_y, s.tp_p = (math.pi / 180.0) * f.tp_y, (math.pi / 180.0) * f.tp_p
             s.shear_g, s.shear_t = f.g / h, f.t / w  # envutil_main.cc:795-796
             s.a, s.b, s.c, s.h, s.v = f.a, f.b, f.c, f.d, f.e
             s.brighten = gains[i]
@@ -173,7 +180,7 @@ class Job:
         o.reserved[1] = 1 if self.no_tiles else 0
         taps = (capi.Tap * 1024)()
         tw = C.c_int(0)
-        ntaps = lib.eu_make_spread(C.byref(t), n, fa, self.twine, self.twine_width, self.twine_density,
+        ntaps = lib.eu_make_spread(C.byref(t), C.byref(o), n, fa, self.twine, self.twine_width, self.twine_density,
                                    self.twine_sigma, self.twine_threshold, self.twine_max, taps, 1024, C.byref(tw))
         if ntaps < 0:
             capi.check(ntaps, lib)

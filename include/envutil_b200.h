@@ -136,9 +136,9 @@ void eu_rotation_matrix(double roll, double pitch, double yaw, int inverse, doub
 void eu_facet_basis(const eu_target_t* t, const eu_facet_t* f, double m[9]);
 /* twining filter. twine > 0: twine*twine taps (box, or truncated gaussian if sigma > 0,
  * taps below threshold dropped, weights renormalised). twine < 0: automatic twining as
- * arguments::twine_setup does. Writes at most max_taps taps; returns the tap count
+ * arguments::twine_setup does (it looks at o->spline_degree and o->solo). Writes at most max_taps taps; returns the tap count
  * (0 = twining off) or a negative status. *twine_out receives the effective twine factor. */
-int eu_make_spread(const eu_target_t* t, int n_facets, const eu_facet_t* facets, int twine,
+int eu_make_spread(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets, int twine,
                    double twine_width, double twine_density, double twine_sigma,
                    double twine_threshold, int twine_max, eu_tap_t* taps, int max_taps,
                    int* twine_out);

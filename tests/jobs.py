@@ -81,6 +81,9 @@ def _build():
     add("ll_rect_d1", Job([_ll_facet(256)], "rectilinear", 90.0, 96, 54))                       # C1 shape
     add("ll_rect_d1_rot", Job([_ll_facet(256)], "rectilinear", 90.0, 96, 54, **ROT))
     add("ll_rect_d3_rot", Job([_ll_facet(256)], "rectilinear", 70.0, 96, 54, degree=3, **ROT))
+    # angles that are not float-representable: the target's go through float, the facet's through double
+    add("ll_rect_d1_oddangles", Job([_ll_facet(256, yaw=12.34, pitch=-3.21, roll=0.77)], "rectilinear", 47.3, 96, 54,
+                                    yaw=33.3, pitch=-21.7, roll=7.1))
     add("ll_rect_d2", Job([_ll_facet(128)], "rectilinear", 100.0, 80, 60, degree=2, yaw=170.0))
     add("ll_rect_d5", Job([_ll_facet(128)], "rectilinear", 60.0, 64, 64, degree=5, pitch=80.0))
     add("ll_rect_d7", Job([_ll_facet(128)], "rectilinear", 60.0, 40, 40, degree=7, pitch=-88.0, roll=45.0))

@@ -1,0 +1,163 @@
+"""The C++ host (envutil_b200_cli): envutil's command line and PTO subset restated above the C
+ABI. CPU part: --dry_run prints what the kernels would be given; it must equal the marshalling
+the parity tests use (which is pinned to the reference binary through the golden outputs)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import harness
+import jobs
+from envutil_b200 import euf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "envutil_b200", "envutil_b200_cli")
+
+
+@pytest.fixture(scope="module")
+def cli(lib):
+    if not os.path.exists(CLI):
+        import __graft_entry__ as g
+        g.build_cli()
+    return CLI
+
+
+def _write_facets(job, d):
+    paths = []
+    for i, f in enumerate(job.facets):
+        p = os.path.join(d, "facet%d.euf" % i)
+        euf.write_euf(p, f.image)
+        paths.append(p)
+    return paths
+
+
+def _floats(line, key):
+    m = re.search(key + r" ((?:[-+0-9.eEinfa]+ ?)+)", line)
+    return [float(v) for v in m.group(1).split()]
+
+
+@pytest.mark.parametrize("name", ["ll_rect_d1_oddangles", "ll_fish_d1_tw4", "ll_rect_d1_tw3_sigma", "hdr3_sph_d3_tw2",
+                                  "lens3_voronoi_sph_d1", "eev_voronoi_sph_d1", "ll_cube_d3_rot", "voronoi4_solo2",
+                                  "cm_sph_d1_support4_tile16"])
+def test_dry_run_equals_marshalling(cli, tmp_path, name):
+    job = jobs.JOBS[name]
+    paths = _write_facets(job, str(tmp_path))
+    r = subprocess.run([cli] + job.cli_args(paths, str(tmp_path / "out.euf")) + ["--dry_run"], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    t, fa, o, taps, ntaps = job.structs()
+    tl = [l for l in lines if l.startswith("target ")][0]
+    assert "%dx%d" % (t.width, t.height) in tl
+    assert _floats(tl, "hfov")[0] == t.hfov and _floats(tl, "yaw")[0] == t.yaw
+    assert _floats(tl, "pitch")[0] == t.pitch and _floats(tl, "roll")[0] == t.roll
+    el = [l for l in lines if l.startswith("extent ")][0]
+    assert _floats(el, "extent") == [t.x0, t.x1, t.y0, t.y1] and _floats(el, "step")[0] == t.step
+    fl = [l for l in lines if l.startswith("facet ")]
+    assert len(fl) == len(job.facets)
+    for i, l in enumerate(fl):
+        assert _floats(l, "hfov")[0] == fa[i].hfov
+        assert _floats(l, "ypr") == [fa[i].yaw, fa[i].pitch, fa[i].roll]
+        assert _floats(l, " step")[0] == fa[i].step
+        assert np.float32(_floats(l, "brighten")[0]) == np.float32(fa[i].brighten)
+        assert _floats(l, "shift") == [fa[i].shift_h, fa[i].shift_v]
+        assert _floats(l, "shear") == [fa[i].shear_g, fa[i].shear_t]
+    tp = [l for l in lines if l.startswith("tap ")]
+    assert len(tp) == ntaps
+    for k, l in enumerate(tp):
+        x, y, w = (np.float32(v) for v in l.split()[1:])
+        assert (x, y, w) == (np.float32(taps[k].x), np.float32(taps[k].y), np.float32(taps[k].w))
+
+
+def test_input_alias_and_spline_degree(cli, tmp_path):
+    """--input X == one facet with the projection inferred from the aspect
+    (2:1 -> spherical 360, 1:6 -> cubemap 90); --spline_degree == --degree."""
+    job = jobs.JOBS["cm_sph_d3"]
+    p = _write_facets(job, str(tmp_path))[0]
+    base = ["--projection", "spherical", "--hfov", "360", "--width", "192", "--height", "96", "--twine", "0",
+            "--output", str(tmp_path / "o.euf"), "--dry_run"]
+    a = subprocess.run([cli, "--input", p, "--spline_degree", "3"] + base, capture_output=True, text=True)
+    b = subprocess.run([cli, "--facet", p, "cubemap", "90", "0", "0", "0", "--degree", "3"] + base,
+                       capture_output=True, text=True)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    assert a.stdout == b.stdout and "degree 3" in a.stdout
+
+
+def test_pipe_mode_and_errors(cli, tmp_path):
+    job = jobs.JOBS["ll_rect_d1"]
+    p = _write_facets(job, str(tmp_path))[0]
+    common = [cli, "--facet", p, "spherical", "360", "0", "0", "0", "--dry_run", "-"]
+    feed = ("--projection rectilinear --hfov 90 --width 96 --height 54 --output '%s'\n"
+            "--projection fisheye --hfov 180 --width 64 --height 64 --yaw 10 --output \"%s\"\n"
+            % (tmp_path / "a b.euf", tmp_path / "b.euf"))
+    r = subprocess.run(common, input=feed, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("target ") == 2 and "target fisheye 64x64" in r.stdout and "pipe has reached EOF" in r.stdout
+    bad = subprocess.run([cli, "--facet", p, "spherical", "360", "0", "0", "0", "--frobnicate", "1", "--output", "x.euf"],
+                         capture_output=True, text=True)
+    assert bad.returncode != 0 and "unknown argument" in bad.stderr
+    bad = subprocess.run([cli, "--facet", p, "spherical", "360", "0", "0", "0", "--projection", "cubemap", "--hfov", "60",
+                          "--output", "x.euf", "--dry_run"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "hfov >= 90" in bad.stderr
+    bad = subprocess.run([cli, "--facet", str(tmp_path / "missing.euf"), "spherical", "360", "0", "0", "0", "--output",
+                          "x.euf"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "failed to open facet image" in bad.stderr
+
+
+def test_pto_back_references(cli, tmp_path):
+    """`=N` takes the field from i-line N (reference pto.h:137-147)."""
+    job = jobs.JOBS["voronoi3_rect_d1_tw2"]
+    paths = _write_facets(job, str(tmp_path))
+    pto = tmp_path / "p.pto"
+    pto.write_text("# comment\np f2 w200 h100 v360\n"
+                   'i w96 h64 f0 v80 y-100 p0 r0 Eev12 n"%s"\n'
+                   'i w96 h64 f0 v=0 y-30 p12 r3 Eev=0 n"%s"\n'
+                   'i w96 h64 f0 v=0 y40 p-9 r-5 Eev14 n"%s"\n' % tuple(paths))
+    r = subprocess.run([cli, "--pto", str(pto), "--output", str(tmp_path / "o.euf"), "--dry_run"], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stderr
+    assert "target spherical 200x100" in r.stdout
+    fl = [l for l in r.stdout.splitlines() if l.startswith("facet ")]
+    hf = [_floats(l, "hfov")[0] for l in fl]
+    assert hf[0] == hf[1] == hf[2] == 80 * (np.pi / 180.0)
+    br = [_floats(l, "brighten")[0] for l in fl]
+    mean = np.float32(np.float32(12 + 12 + 14) / np.float32(3))
+    want = [np.float32(2.0 ** float(np.float32(np.float32(e) - mean))) for e in (12, 12, 14)]
+    assert [np.float32(b) for b in br] == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ll_rect_d1_oddangles", "cm_sph_d3_rot", "ll_fish_d1_tw4", "hdr3_sph_d3_tw2",
+                                  "lens3_voronoi_sph_d1", "eev_voronoi_sph_d1", "ll_ba6_d1_tw2", "voronoi4_solo2",
+                                  "grey_cm_sph_d1_tw2", "ll_cyl_d1_tw2"])
+def test_cli_output_equals_reference_output(cli, tmp_path, name):
+    """The drop-in claim end to end: the SAME command line given to the reference binary and to
+    envutil_b200_cli produces the same file, bit for bit (golden sha256 of the reference run)."""
+    import hashlib
+    import json
+    job = jobs.JOBS[name]
+    paths = _write_facets(job, str(tmp_path))
+    outp = str(tmp_path / "out.euf")
+    r = subprocess.run([cli] + job.cli_args(paths, outp), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    img = euf.read_euf(outp)
+    man = json.load(open(os.path.join(harness.GOLDEN, "manifest.json")))[name]
+    assert list(img.shape) == man["shape"]
+    assert hashlib.sha256(np.ascontiguousarray(img, dtype="<f4").tobytes()).hexdigest() == man["sha256"]
+
+
+@pytest.mark.gpu
+def test_cli_pipe_mode_keeps_sources_staged(cli, tmp_path):
+    job = jobs.JOBS["cm_sph_d3"]
+    p = _write_facets(job, str(tmp_path))[0]
+    feed = "".join("--yaw %d --output %s\n" % (y, tmp_path / ("o%d.euf" % y)) for y in (0, 40, 80))
+    r = subprocess.run([cli, "-v", "--facet", p, "cubemap", "90", "0", "0", "0", "--projection", "spherical", "--hfov",
+                        "360", "--width", "192", "--height", "96", "--degree", "3", "--twine", "0", "-"], input=feed,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    st = [float(m) for m in re.findall(r"staging ([0-9.]+) ms", r.stdout)]
+    assert len(st) == 3 and st[0] > 0.0 and st[1] == 0.0 and st[2] == 0.0  # staged once, found twice
+    a = euf.read_euf(str(tmp_path / "o0.euf"))
+    assert np.array_equal(a, harness.oracle_render(job))

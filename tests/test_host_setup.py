@@ -109,7 +109,9 @@ def test_box_spread(lib, twine):
     lib.eu_facet_prepare(C.byref(f))
     taps = (capi.Tap * 1024)()
     tw = C.c_int()
-    n = lib.eu_make_spread(C.byref(t), 1, C.byref(f), twine, 1.0, 1.0, 0.0, 0.0, 8, taps, 1024, C.byref(tw))
+    o = capi.Opts()
+    o.spline_degree, o.solo = 1, 0
+    n = lib.eu_make_spread(C.byref(t), C.byref(o), 1, C.byref(f), twine, 1.0, 1.0, 0.0, 0.0, 8, taps, 1024, C.byref(tw))
     assert n == twine * twine and tw.value == twine
     xs = sorted({round(taps[i].x, 6) for i in range(n)})
     want = [-(twine - 1) / (2 * twine) + i / twine for i in range(twine)]
@@ -129,7 +131,9 @@ def test_auto_twine(lib):
     lib.eu_facet_prepare(C.byref(f))
     taps = (capi.Tap * 1024)()
     tw = C.c_int()
-    n = lib.eu_make_spread(C.byref(t), 1, C.byref(f), -1, 1.0, 1.0, 0.0, 0.0, 8, taps, 1024, C.byref(tw))
+    o = capi.Opts()
+    o.spline_degree, o.solo = 1, 0
+    n = lib.eu_make_spread(C.byref(t), C.byref(o), 1, C.byref(f), -1, 1.0, 1.0, 0.0, 0.0, 8, taps, 1024, C.byref(tw))
     assert tw.value == 2 and n == 4
 
 
