@@ -237,6 +237,35 @@ int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, Fac
   F.brighten = (float)(f->brighten == 0.0 ? 1.0 : f->brighten);
   F.hdr_optimum = 0.0f;
   F.hdr_kind = EU_HDR_MIDDLE;
+  F.generic = f->has_translation ? 1 : 0;
+  if (F.generic) {
+    // generic_r3(ft, fs) for an untranslated target (envutil_payload.cc:1640-1716): the matrices
+    // are r3_t<float>, built from make_r3_t's double rows narrowed element by element
+    auto rot = [](double r, double p, double y, int inv, float out[9]) {
+      double d[9];
+      eu_rotation_matrix(r, p, y, inv, d);
+      for (int i = 0; i < 9; i++) out[i] = (float)d[i];
+    };
+    auto mul = [](const float a[9], const float b[9], float o[9]) {  // rotate(r3_t, r3_t), geometry.h:84-91
+      for (int i = 0; i < 3; i++)
+        for (int c = 0; c < 3; c++) o[3 * i + c] = (a[3 * i] * b[c] + a[3 * i + 1] * b[3 + c]) + a[3 * i + 2] * b[6 + c];
+    };
+    float r_camera[9], rs_tp[9], rs_tpi[9], r_facet[9];
+    rot(t->roll, t->pitch, t->yaw, 0, r_camera);
+    rot(f->tp_r, f->tp_p, f->tp_y, 1, rs_tp);
+    rot(f->tp_r, f->tp_p, f->tp_y, 0, rs_tpi);
+    rot(f->roll, f->pitch, f->yaw, 1, r_facet);
+    float sh[3] = {(float)f->tr_x, (float)f->tr_y, (float)f->tr_z};
+    if (f->tp_y != 0 || f->tp_p != 0 || f->tp_r != 0) {  // rotate(xel_t<double,3>(shift_s), rs_tp): in double
+      double sd[3] = {sh[0], sh[1], sh[2]}, od[3];
+      for (int c = 0; c < 3; c++) od[c] = (sd[0] * rs_tp[c] + sd[1] * rs_tp[3 + c]) + sd[2] * rs_tp[6 + c];
+      for (int c = 0; c < 3; c++) sh[c] = (float)od[c];
+    }
+    mul(r_camera, rs_tp, F.g_t2m);
+    mul(rs_tpi, r_facet, F.g_m2s);
+    for (int c = 0; c < 3; c++) F.g_shift[c] = sh[c];
+    F.g_dcp = 1.0f;
+  }
   return EU_OK;
 }
 
@@ -286,8 +315,8 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     if (sources[i]->degree != o->spline_degree)
       return fail(EU_ERR_ARGUMENT, "source %d was staged for degree %d, job asks for %d", i, sources[i]->degree,
                   o->spline_degree);
-    if (facets[i].has_translation)
-      return fail(EU_ERR_UNSUPPORTED, "facet %d: PanoTools translation (TrX/Y/Z) is not built", i);
+    if (facets[i].has_translation && (t->projection == EU_CUBEMAP || t->projection == EU_BIATAN6))
+      return fail(EU_ERR_UNSUPPORTED, "facet %d: PanoTools translation with a cubemap target is not built", i);
     sources[i]->last_used_cycle = g.cycle;
   }
   RenderParams& P = plan.P;
@@ -364,13 +393,14 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     P.taps = g.d_taps;
   }
   // planar tables: recomputed only when the target changes
-  size_t need = 2 * (size_t)(t->width + t->height);
+  size_t need = 3 * (size_t)(t->width + t->height);  // float2 terms + the bare planar coordinate per entry, in float2 units
   if (!g.planar_valid || memcmp(&g.planar_for, &P.trg, sizeof(TargetDev)) != 0 || need > g.planar_cap) {
     TargetDev key = P.trg;
     CK(cudaDeviceSynchronize());  // nothing in flight may still read the old tables
     int rc = grow(g.d_planar, g.planar_cap, need);
     if (rc) return rc;
-    CK(eu_launch_planar_tables(P.trg, g.d_planar, g.d_planar + 2 * (size_t)t->width, g.stream));
+    CK(eu_launch_planar_tables(P.trg, g.d_planar, g.d_planar + 2 * (size_t)t->width,
+                               reinterpret_cast<float*>(g.d_planar + 2 * (size_t)(t->width + t->height)), g.stream));
     plan.launches++;
     g.planar_for = key;
     g.planar_valid = true;
@@ -378,6 +408,9 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   // normalize is part of TargetDev but does not change the tables; keep the key exact anyway
   P.col_tab = g.d_planar;
   P.row_tab = g.d_planar + 2 * (size_t)t->width;
+  P.planar_raw = reinterpret_cast<const float*>(g.d_planar + 2 * (size_t)(t->width + t->height));
+  P.any_generic = 0;
+  for (int i = 0; i < nf; i++) P.any_generic |= F[i].generic;
   {
     int d = o->spline_degree;
     for (int row = 0; row <= d; row++)

@@ -153,6 +153,68 @@ __device__ __forceinline__ void dev_stepper(const TargetDev& T, const float* xx,
   }
 }
 
+// rotate(xel_t<float,3>, r3_t<float>), geometry.h:74-82
+__device__ __forceinline__ void dev_rot3(const float v[3], const float* __restrict__ m, float out[3]) {
+  float o[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) o[c] = (v[0] * m[c] + v[1] * m[3 + c]) + v[2] * m[6 + c];
+  out[0] = o[0]; out[1] = o[1]; out[2] = o[2];
+}
+
+// generic_stepper (stepper.h:353-470) over tf_ex_facet::eval (envutil_payload.cc:1841-1883): the
+// bare planar coordinate -> X_to_ray of the target projection (geometry.h:151-567) -> tf3d_t::eval
+// (geometry.h:1886-1925). Used for facets with PanoTools translation (TrX/TrY/TrZ).
+__device__ __forceinline__ void dev_generic_ray(const TargetDev& T, const FacetDev& F, float h, float v, float ray[3]) {
+  float in[3];  // RIGHT, DOWN, FORWARD
+  switch (T.projection) {
+    case EU_SPHERICAL: {
+      float sinlat, coslat, sinlon, coslon;
+      eu_sincosf(v, &sinlat, &coslat);
+      eu_sincosf(h, &sinlon, &coslon);
+      in[0] = sinlon * coslat; in[2] = coslon * coslat; in[1] = sinlat;
+      break;
+    }
+    case EU_CYLINDRICAL: in[2] = eu_cosf(h); in[0] = eu_sinf(h); in[1] = v; break;
+    case EU_RECTILINEAR: in[0] = h; in[1] = v; in[2] = 1.0f; break;
+    case EU_STEREOGRAPHIC: {
+      float r = sqrtf(h * h + v * v);
+      float theta = eu_atanf(r / 2.0f) * 2.0f;
+      float phi = eu_atan2f(h, -v);
+      in[2] = eu_cosf(theta);
+      in[1] = -eu_sinf(theta) * eu_cosf(phi);
+      in[0] = eu_sinf(theta) * eu_sinf(phi);
+      break;
+    }
+    default: {  // EU_FISHEYE
+      float r = sqrtf(h * h + v * v);
+      float phi = eu_atan2f(h, -v);
+      in[2] = eu_cosf(r);
+      in[1] = -eu_sinf(r) * eu_cosf(phi);
+      in[0] = eu_sinf(r) * eu_sinf(phi);
+    }
+  }
+  float out[3];
+  dev_rot3(in, F.g_t2m, out);
+  if (out[2] <= 0.0f) {
+    out[0] = 0.0f; out[1] = 0.0f; out[2] = -INFINITY;
+  } else {
+    out[0] /= out[2];
+    out[1] /= out[2];
+    out[2] = 1.0f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) out[c] *= F.g_dcp;
+#pragma unroll
+    for (int c = 0; c < 3; c++) out[c] -= F.g_shift[c];
+    dev_rot3(out, F.g_m2s, out);
+  }
+  if (T.normalize) {
+    float n = dev_norm3(out);
+#pragma unroll
+    for (int c = 0; c < 3; c++) out[c] /= n;
+  }
+  ray[0] = out[0]; ray[1] = out[1]; ray[2] = out[2];
+}
+
 // ------------------------------------------------------------------------------------------
 // source side
 // ------------------------------------------------------------------------------------------

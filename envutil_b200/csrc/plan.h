@@ -51,6 +51,10 @@ struct FacetDev {
   // _hdr_merge_syn (envutil_payload.cc:1354-1375)
   float hdr_optimum;
   int32_t hdr_kind;
+  // generic_stepper + tf_ex_facet + generic_r3 + tf3d_t: facets with PanoTools translation
+  // (envutil_payload.cc:1628-1883, geometry.h:1850-1942). Float matrices, rows as r3_t holds them.
+  int32_t generic;
+  float g_t2m[9], g_m2s[9], g_shift[3], g_dcp;
 };
 
 struct TargetDev {
@@ -69,12 +73,14 @@ struct RenderParams {
   const float* taps;        // n_taps x (x*4, y*4, w)  (twining.h:106-121)
   const float2* col_tab;    // [2][width]: per-column stepper terms, plain and x-biased (eu_device.cuh)
   const float2* row_tab;    // [2][height]: per-row stepper terms, plain and y-biased
+  const float* planar_raw;  // [2][width] then [2][height]: the bare planar coordinates (generic steppers)
   int32_t n_facets;
   int32_t mode;       // EU_MODE_*
   int32_t degree;     // spline degree of the evaluator
   int32_t n_taps;     // 0: plain rays (ninputs 3), else twining (ninputs 9)
   int32_t nch;
   int32_t tstride;    // floats per texel in HBM: nch, or 4 (padded RGB); same for all facets
+  int32_t any_generic;  // some facet uses the generic stepper (needs planar_raw)
   int32_t use_tiles;  // 1: stage the gather footprint in shared memory where the kernel supports it
   int32_t src_cw, src_ch;  // container shape of f0's source in texels (tile path)
   int32_t src_lx, src_ly;  // its left / top brace: core texel (0,0) is container texel (lx, ly)

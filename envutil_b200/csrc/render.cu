@@ -7,7 +7,8 @@
 // segment, += delta per 16-px vector (stepper.h:324-350, zimt/wielding.h:317-455).
 // col[0..W) plain, [W..2W) x-biased stepper (deriv_stepper's r10); row[0..H) plain, [H..2H)
 // y-biased (r01).
-__global__ void k_planar_tables(TargetDev T, float2* __restrict__ col, float2* __restrict__ row) {
+__global__ void k_planar_tables(TargetDev T, float2* __restrict__ col, float2* __restrict__ row,
+                                float* __restrict__ raw) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 2 * T.width) {
     int x = i % T.width;
@@ -20,6 +21,7 @@ __global__ void k_planar_tables(TargetDev T, float2* __restrict__ col, float2* _
     ColTerm c;
     dev_col_term(T, p, c);
     col[i] = make_float2(c.a, c.b);
+    raw[i] = p;
   }
   int j = i - 2 * T.width;
   if (j >= 0 && j < 2 * T.height) {
@@ -30,12 +32,13 @@ __global__ void k_planar_tables(TargetDev T, float2* __restrict__ col, float2* _
     RowTerm rt;
     dev_row_term(T, p, y, rt);
     row[j] = make_float2(rt.a, rt.b);
+    raw[2 * T.width + j] = p;
   }
 }
 
-cudaError_t eu_launch_planar_tables(const TargetDev& T, float2* d_col, float2* d_row, cudaStream_t st) {
+cudaError_t eu_launch_planar_tables(const TargetDev& T, float2* d_col, float2* d_row, float* d_raw, cudaStream_t st) {
   int n = 2 * T.width + 2 * T.height;
-  k_planar_tables<<<(n + 255) / 256, 256, 0, st>>>(T, d_col, d_row);
+  k_planar_tables<<<(n + 255) / 256, 256, 0, st>>>(T, d_col, d_row, d_raw);
   return cudaGetLastError();
 }
 

@@ -24,6 +24,23 @@ __device__ __forceinline__ int first_lane_column(int x) {
   return seg0 + (x - seg0) % EU_LANES;
 }
 
+// the ray of one facet for a pixel: the projection's own stepper, or the generic stepper for
+// facets with translation. which: 0 = r00, 1 = r10 (x-biased), 2 = r01 (y-biased)
+struct PixelTerms {
+  ColTerm col, colb, first, firstb;
+  RowTerm row, rowb;
+  float px, pxb, py, pyb;  // bare planar coordinates (generic steppers only)
+};
+__device__ __forceinline__ void dev_facet_ray(const TargetDev& T, const FacetDev& F, const PixelTerms& t, int which,
+                                              int y, float r[3]) {
+  if (F.generic) {
+    dev_generic_ray(T, F, which == 1 ? t.pxb : t.px, which == 2 ? t.pyb : t.py, r);
+  } else {
+    dev_stepper(T, F.xx, F.yy, F.zz, which == 1 ? t.colb : t.col, which == 2 ? t.rowb : t.row,
+                which == 1 ? t.firstb : t.first, y, r);
+  }
+}
+
 // one synopsis evaluation (envutil_payload.cc:818-956 voronoi, :1500-1622 hdr_merge) for rays
 // produced by `ray_of(i, ray)`; returns the index-plane value
 template <int NCH, int TS, int MODE, int DEG, typename RayFn>
@@ -86,42 +103,57 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
   int y = P.row0 + blockIdx.y * TILE_Y + threadIdx.y;
   if (x >= T.width || y >= P.row1) return;
   int xf = first_lane_column(x);
-  float2 c0 = __ldg(P.col_tab + x), r0 = __ldg(P.row_tab + y);
-  ColTerm col{c0.x, c0.y};
-  RowTerm row{r0.x, r0.y};
-  ColTerm first = col;
-  if (T.projection == EU_CYLINDRICAL && T.normalize) {
-    float2 f0 = __ldg(P.col_tab + xf);
-    first = ColTerm{f0.x, f0.y};
+  PixelTerms t;
+  {
+    float2 c0 = __ldg(P.col_tab + x), r0 = __ldg(P.row_tab + y);
+    t.col = ColTerm{c0.x, c0.y};
+    t.row = RowTerm{r0.x, r0.y};
+    t.first = t.col;
+    if (T.projection == EU_CYLINDRICAL && T.normalize) {
+      float2 f0 = __ldg(P.col_tab + xf);
+      t.first = ColTerm{f0.x, f0.y};
+    }
+    t.px = t.py = t.pxb = t.pyb = 0.0f;
+    if (P.any_generic) {
+      t.px = __ldg(P.planar_raw + x);
+      t.py = __ldg(P.planar_raw + 2 * T.width + y);
+    }
+    t.colb = t.col; t.firstb = t.first; t.rowb = t.row;
+    if constexpr (TWINE) {
+      float2 c1 = __ldg(P.col_tab + T.width + x), r1 = __ldg(P.row_tab + T.height + y);
+      t.colb = ColTerm{c1.x, c1.y};
+      t.rowb = RowTerm{r1.x, r1.y};
+      t.firstb = t.colb;
+      if (T.projection == EU_CYLINDRICAL && T.normalize) {
+        float2 f1 = __ldg(P.col_tab + T.width + xf);
+        t.firstb = ColTerm{f1.x, f1.y};
+      }
+      if (P.any_generic) {
+        t.pxb = __ldg(P.planar_raw + T.width + x);
+        t.pyb = __ldg(P.planar_raw + 2 * T.width + T.height + y);
+      }
+    }
   }
   float px[NCH];
   int idx;
   if constexpr (!TWINE) {
     auto ray_of = [&](int i, float r[3]) {
       const FacetDev& F = MODE == EU_MODE_SINGLE ? P.f0 : P.facets[i];
-      dev_stepper(T, F.xx, F.yy, F.zz, col, row, first, y, r);
+      dev_facet_ray(T, F, t, 0, y, r);
     };
     idx = dev_synopsis<NCH, TS, MODE, DEG>(P, ray_of, px);
   } else {
     // deriv_stepper (stepper.h:1606-1694) + twine_t (twining.h:106-263) /
     // synopsis_t (envutil_payload.cc:647-690)
-    float2 c1 = __ldg(P.col_tab + T.width + x), r1 = __ldg(P.row_tab + T.height + y);
-    ColTerm colb{c1.x, c1.y};
-    RowTerm rowb{r1.x, r1.y};
-    ColTerm firstb = colb;
-    if (T.projection == EU_CYLINDRICAL && T.normalize) {
-      float2 f1 = __ldg(P.col_tab + T.width + xf);
-      firstb = ColTerm{f1.x, f1.y};
-    }
     float acc[NCH], help[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; c++) acc[c] = 0.0f;
     idx = -1;
     if constexpr (MODE == EU_MODE_SINGLE) {
       float r00[3], du[3], dv[3];
-      dev_stepper(T, P.f0.xx, P.f0.yy, P.f0.zz, col, row, first, y, r00);
-      dev_stepper(T, P.f0.xx, P.f0.yy, P.f0.zz, colb, row, firstb, y, du);
-      dev_stepper(T, P.f0.xx, P.f0.yy, P.f0.zz, col, rowb, first, y, dv);
+      dev_facet_ray(T, P.f0, t, 0, y, r00);
+      dev_facet_ray(T, P.f0, t, 1, y, du);
+      dev_facet_ray(T, P.f0, t, 2, y, dv);
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         du[c] = du[c] - r00[c];
@@ -143,9 +175,9 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
       for (int i = 0; i < P.n_facets; i++) {
         const FacetDev& F = P.facets[i];
         float r00[3], r10[3], r01[3];
-        dev_stepper(T, F.xx, F.yy, F.zz, col, row, first, y, r00);
-        dev_stepper(T, F.xx, F.yy, F.zz, colb, row, firstb, y, r10);
-        dev_stepper(T, F.xx, F.yy, F.zz, col, rowb, first, y, r01);
+        dev_facet_ray(T, F, t, 0, y, r00);
+        dev_facet_ray(T, F, t, 1, y, r10);
+        dev_facet_ray(T, F, t, 2, y, r01);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           np[i][c] = r00[c];
@@ -385,7 +417,7 @@ template <int NCH, int TS, int MODE, bool TWINE>
 static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st) {
   if constexpr (MODE == EU_MODE_SINGLE) {
     // footprint-staged kernel: needs 16-byte row granules and a pixel output (no index plane)
-    if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0) {
+    if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.f0.generic) {
       if (P.degree == 1) { k_render_tiled<NCH, TS, TWINE, 1><<<grid, block, 0, st>>>(P); return; }
       if (P.degree == 3) { k_render_tiled<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P); return; }
     }

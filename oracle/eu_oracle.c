@@ -793,6 +793,10 @@ typedef struct {
   float recip_step, brighten, optimum;
   int hdr_kind; /* 0 LOW 1 MIDDLE 2 HIGH */
   int mask_always;
+  /* generic_stepper + tf_ex_facet + generic_r3 + tf3d_t for facets with PanoTools translation
+   * (envutil_payload.cc:1628-1883, geometry.h:1850-1942); float matrices, rows as r3_t holds them */
+  int generic;
+  float g_t2m[9], g_m2s[9], g_shift[3], g_dcp;
 } facet_ctx;
 
 typedef struct {
@@ -845,12 +849,78 @@ static float norm3(const float v[3]) {
   return sqrtf(sqn);
 }
 
+/* rotate(xel_t<float,3>, r3_t<float>), geometry.h:74-82: (v0*m0 + v1*m1) + v2*m2, per component */
+static void rot3f(const float v[3], const float m[9], float out[3]) {
+  float o[3];
+  for (int c = 0; c < 3; c++) o[c] = (v[0] * m[c] + v[1] * m[3 + c]) + v[2] * m[6 + c];
+  out[0] = o[0]; out[1] = o[1]; out[2] = o[2];
+}
+/* rotate(r3_t<float>, r3_t<float>), geometry.h:84-91 */
+static void matmulf(const float a[9], const float b[9], float m[9]) {
+  for (int i = 0; i < 3; i++) rot3f(a + 3 * i, b, m + 3 * i);
+}
+
+/* generic_stepper::init/increase (stepper.h:353-470) over tf_ex_facet::eval
+ * (envutil_payload.cc:1841-1883): planar -> X_to_ray of the target projection (geometry.h:151-567)
+ * -> tf3d_t::eval (geometry.h:1886-1925). */
+static void generic_ray(const target_ctx* T, const facet_ctx* F, float h, float v, float ray[3]) {
+  float in[3]; /* RIGHT, DOWN, FORWARD */
+  switch (T->projection) {
+    case EU_SPHERICAL: {
+      float sinlat, coslat, sinlon, coslon;
+      eu_sincosf(v, &sinlat, &coslat);
+      eu_sincosf(h, &sinlon, &coslon);
+      in[0] = sinlon * coslat; in[2] = coslon * coslat; in[1] = sinlat;
+      break;
+    }
+    case EU_CYLINDRICAL: in[2] = eu_cosf(h); in[0] = eu_sinf(h); in[1] = v; break;
+    case EU_RECTILINEAR: in[0] = h; in[1] = v; in[2] = 1.0f; break;
+    case EU_STEREOGRAPHIC: {
+      float r = sqrtf(h * h + v * v);
+      float theta = eu_atanf(r / 2.0f) * 2.0f;
+      float phi = eu_atan2f(h, -v);
+      in[2] = eu_cosf(theta);
+      in[1] = -eu_sinf(theta) * eu_cosf(phi);
+      in[0] = eu_sinf(theta) * eu_sinf(phi);
+      break;
+    }
+    default: { /* EU_FISHEYE */
+      float r = sqrtf(h * h + v * v);
+      float phi = eu_atan2f(h, -v);
+      in[2] = eu_cosf(r);
+      in[1] = -eu_sinf(r) * eu_cosf(phi);
+      in[0] = eu_sinf(r) * eu_sinf(phi);
+    }
+  }
+  float out[3];
+  rot3f(in, F->g_t2m, out);
+  if (out[2] <= 0.0f) {
+    out[0] = 0.0f; out[1] = 0.0f; out[2] = -INFINITY;
+  } else {
+    out[0] /= out[2];
+    out[1] /= out[2];
+    out[2] = 1.0f;
+    for (int c = 0; c < 3; c++) out[c] *= F->g_dcp;
+    for (int c = 0; c < 3; c++) out[c] -= F->g_shift[c];
+    rot3f(out, F->g_m2s, out);
+  }
+  if (T->normalize) {
+    float n = norm3(out);
+    for (int c = 0; c < 3; c++) out[c] /= n;
+  }
+  ray[0] = out[0]; ray[1] = out[1]; ray[2] = out[2];
+}
+
 /* the seven steppers, stepper.h:517-1578. (px,py) planar coordinate, (x,y) discrete target
  * coordinate (needed by the cube steppers and by the cylindrical stepper's per-segment
  * rcp_length). */
 static void stepper_ray(const target_ctx* T, const facet_ctx* F, float px, float py, int x, int y, float bias_x,
                         float ray[3]) {
   const float *xx = F->xx, *yy = F->yy, *zz = F->zz;
+  if (F->generic) {
+    generic_ray(T, F, px, py, ray);
+    return;
+  }
   switch (T->projection) {
     case EU_SPHERICAL: {
       float sy, r, sx, z;
@@ -1160,6 +1230,29 @@ static int facet_setup(const eu_target_t* t, const eu_opts_t* o, const eu_facet_
     F->refc_md = (float)src->cm.refc_md;
     F->model_to_px = (float)src->cm.model_to_px;
     F->section_px = src->cm.section_px;
+  }
+  F->generic = (f->tr_x != 0 || f->tr_y != 0 || f->tr_z != 0); /* has_translation, envutil_basic.h:505 */
+  if (F->generic) { /* generic_r3(ft, fs) with an untranslated target, envutil_payload.cc:1640-1716 */
+    double d[9];
+    float r_camera[9], rs_tp[9], rs_tpi[9], r_facet[9];
+    orc_rotation(t->roll, t->pitch, t->yaw, 0, d);
+    for (int i = 0; i < 9; i++) r_camera[i] = (float)d[i];
+    orc_rotation(f->tp_r, f->tp_p, f->tp_y, 1, d);
+    for (int i = 0; i < 9; i++) rs_tp[i] = (float)d[i];
+    orc_rotation(f->tp_r, f->tp_p, f->tp_y, 0, d);
+    for (int i = 0; i < 9; i++) rs_tpi[i] = (float)d[i];
+    orc_rotation(f->roll, f->pitch, f->yaw, 1, d);
+    for (int i = 0; i < 9; i++) r_facet[i] = (float)d[i];
+    float sh[3] = {(float)f->tr_x, (float)f->tr_y, (float)f->tr_z};
+    if (f->tp_y != 0 || f->tp_p != 0 || f->tp_r != 0) { /* rotate(xel_t<double,3>(shift), rs_tp): in double */
+      double sd[3] = {sh[0], sh[1], sh[2]}, o[3];
+      for (int c = 0; c < 3; c++) o[c] = (sd[0] * rs_tp[c] + sd[1] * rs_tp[3 + c]) + sd[2] * rs_tp[6 + c];
+      for (int c = 0; c < 3; c++) sh[c] = (float)o[c];
+    }
+    matmulf(r_camera, rs_tp, F->g_t2m);
+    matmulf(rs_tpi, r_facet, F->g_m2s);
+    for (int c = 0; c < 3; c++) F->g_shift[c] = sh[c];
+    F->g_dcp = 1.0f;
   }
   double step = orc_get_step(f->projection, f->width, f->height, f->hfov);
   F->recip_step = (float)(1.0 / step);

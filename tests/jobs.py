@@ -70,6 +70,15 @@ def _lens_facets():
             FacetSpec(_ll(96, 96), "fisheye", 140.0, yaw=90.0, b=-0.02, d=-1.0)]
 
 
+def _translated_facets():
+    # PanoTools translation (TrX/TrY/TrZ, optionally on a tilted plane Tpy/Tpp): generic stepper path
+    return [FacetSpec(_rect(96, 64, 80.0, -30.0, 5.0, 0.0), "rectilinear", 80.0, yaw=-30.0, pitch=5.0,
+                      tr_x=0.05, tr_y=-0.03, tr_z=0.02),
+            FacetSpec(_rect(96, 64, 80.0, 30.0, -4.0, 2.0), "rectilinear", 80.0, yaw=30.0, pitch=-4.0, roll=2.0,
+                      tr_x=-0.04, tr_y=0.02, tr_z=0.1, tp_y=10.0, tp_p=-5.0),
+            FacetSpec(_rect(96, 64, 80.0, 100.0, 0.0, 0.0), "rectilinear", 80.0, yaw=100.0)]
+
+
 def _build():
     J = {}
 
@@ -152,6 +161,13 @@ def _build():
                                    FacetSpec(_rect(96, 64, 80.0, 60.0), "rectilinear", 80.0, yaw=60.0, eev=12.0),
                                    FacetSpec(_rect(96, 64, 80.0, -60.0), "rectilinear", 80.0, yaw=-60.0)],
                                   "spherical", 360.0, 192, 96))
+    tr = _translated_facets()
+    add("tr1_sph_d1", Job(tr[:1], "spherical", 360.0, 192, 96))
+    add("tr1_rect_d1_tw2", Job(tr[1:2], "rectilinear", 100.0, 96, 64, yaw=30.0, twine=2))
+    add("tr3_voronoi_sph_d1", Job(tr, "spherical", 360.0, 256, 128, yaw=11.0, pitch=3.0))
+    add("tr3_voronoi_fish_d3_tw2", Job(tr, "fisheye", 200.0, 96, 96, degree=3, twine=2))
+    add("tr2_cyl_d1", Job(tr[:2], "cylindrical", 300.0, 200, 60))
+    add("tr2_ster_d1", Job(tr[1::-1], "stereographic", 220.0, 100, 100, yaw=-10.0))
     return J
 
 

@@ -146,8 +146,12 @@ def test_errors_are_reported_not_fatal(engine):
         assert rc == -1 and b"degree" in lib.eu_last_error()
         bogus = (capi.SourceH * 1)(C.c_void_p(0x1234))
         assert lib.eu_render(C.byref(t), C.byref(o), 1, fa, bogus, taps, 0, out.ctypes.data, None) == -1
-        fa[0].tr_x = 0.5
-        fa[0].has_translation = 1
-        assert lib.eu_render(C.byref(t), C.byref(o), 1, fa, hs, taps, 0, out.ctypes.data, None) == -2
+        # sub-features that are not built are refused, never approximated
+        crop = capi.Facet.from_buffer_copy(fa[0])
+        crop.window_width = crop.width // 2
+        h = capi.SourceH()
+        img = np.ascontiguousarray(job.facets[0].image)
+        assert lib.eu_source_upload(None, C.byref(crop), C.byref(o), img.ctypes.data, C.byref(h), None) == -2
+        assert b"cropped" in lib.eu_last_error()
     finally:
         engine.release(hs)
