@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #define EU_MAX_FACETS 64
+#define EU_SMEM_FACETS 24  // synopsis jobs with up to this many facets keep them in shared memory
 #define EU_MAX_TAPS 1024
 #define EU_MAX_DEGREE 7
 #define EU_SEGMENT 512  // WIELDING_SEGMENT_SIZE (zimt/bill.h:69)

@@ -12,6 +12,7 @@
 // Included by render_c*.cu, one translation unit per (NCH, TS) so that they compile in parallel.
 #pragma once
 #include <limits.h>
+#include <stdlib.h>
 
 #include "eu_device.cuh"
 #include "kernels.h"
@@ -31,20 +32,28 @@ struct PixelTerms {
   RowTerm row, rowb;
   float px, pxb, py, pyb;  // bare planar coordinates (generic steppers only)
 };
-__device__ __forceinline__ void dev_facet_ray(const TargetDev& T, const FacetDev& F, const PixelTerms& t, int which,
-                                              int y, float r[3]) {
-  if (F.generic) {
-    dev_generic_ray(T, F, which == 1 ? t.pxb : t.px, which == 2 ? t.pyb : t.py, r);
-  } else {
-    dev_stepper(T, F.xx, F.yy, F.zz, which == 1 ? t.colb : t.col, which == 2 ? t.rowb : t.row,
-                which == 1 ? t.firstb : t.first, y, r);
+template <bool GEN, int WHICH>
+__device__ __forceinline__ void dev_facet_ray(const TargetDev& T, const FacetDev& F, const PixelTerms& t, int y,
+                                              float r[3]) {
+  if constexpr (GEN) {
+    if (F.generic) {
+      dev_generic_ray(T, F, WHICH == 1 ? t.pxb : t.px, WHICH == 2 ? t.pyb : t.py, r);
+      return;
+    }
   }
+  dev_stepper(T, F.xx, F.yy, F.zz, WHICH == 1 ? t.colb : t.col, WHICH == 2 ? t.rowb : t.row,
+              WHICH == 1 ? t.firstb : t.first, y, r);
 }
 
 // one synopsis evaluation (envutil_payload.cc:818-956 voronoi, :1500-1622 hdr_merge) for rays
 // produced by `ray_of(i, ray)`; returns the index-plane value
+// The facet array of synopsis jobs: `fa` points at the block's shared-memory copy (PF, up to
+// EU_SMEM_FACETS facets: every lane reads the same field, one broadcast wavefront instead of a
+// global load) or at the array in global memory.
+
 template <int NCH, int TS, int MODE, int DEG, typename RayFn>
-__device__ __forceinline__ int dev_synopsis(const RenderParams& P, RayFn ray_of, float px[NCH]) {
+__device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDev* __restrict__ fa, RayFn ray_of,
+                                            float px[NCH]) {
   if constexpr (MODE == EU_MODE_SINGLE) {
     float r[3];
     ray_of(0, r);
@@ -53,7 +62,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, RayFn ray_of,
     int champion = -1;
     float max_z = -FLT_MAX, best[3] = {0.f, 0.f, 0.f};
     for (int i = 0; i < P.n_facets; i++) {
-      const FacetDev& F = P.facets[i];
+      const FacetDev& F = fa[i];
       float r[3];
       ray_of(i, r);
       if (!dev_facet_mask(F, r)) continue;
@@ -68,7 +77,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, RayFn ray_of,
 #pragma unroll
       for (int c = 0; c < NCH; c++) px[c] = 0.0f;
     } else {
-      dev_facet_eval<NCH, TS, DEG>(P.facets[champion], P.degree, P.wmat, best, px);
+      dev_facet_eval<NCH, TS, DEG>(fa[champion], P.degree, P.wmat, best, px);
     }
     return champion;
   } else {
@@ -76,7 +85,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, RayFn ray_of,
 #pragma unroll
     for (int c = 0; c < NCH; c++) px[c] = 0.0f;
     for (int i = 0; i < P.n_facets; i++) {
-      const FacetDev& F = P.facets[i];
+      const FacetDev& F = fa[i];
       float r[3];
       ray_of(i, r);
       dev_facet_eval<NCH, TS, DEG>(F, P.degree, P.wmat, r, p);
@@ -96,9 +105,22 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, RayFn ray_of,
   }
 }
 
-template <int NCH, int TS, int MODE, bool TWINE, int DEG>
+// GEN: some facet of the job uses the generic stepper (PanoTools translation); kept out of the
+// common instantiations because the extra per-facet branch costs ~20 % on multi-facet jobs
+template <int NCH, int TS, int MODE, bool TWINE, int DEG, bool PF, bool GEN>
 __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant__ RenderParams P) {
   const TargetDev& T = P.trg;
+  const FacetDev* __restrict__ fa = P.facets;
+  if constexpr (PF && MODE != EU_MODE_SINGLE) {
+    __shared__ __align__(16) unsigned char sfa[EU_SMEM_FACETS * sizeof(FacetDev)];
+    static_assert(sizeof(FacetDev) % 4 == 0, "FacetDev is copied word by word");
+    const int words = P.n_facets * (int)(sizeof(FacetDev) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.facets);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sfa);
+    for (int i = threadIdx.y * TILE_X + threadIdx.x; i < words; i += TILE_X * TILE_Y) dst[i] = __ldg(src + i);
+    __syncthreads();
+    fa = reinterpret_cast<const FacetDev*>(sfa);
+  }
   int x = blockIdx.x * TILE_X + threadIdx.x;
   int y = P.row0 + blockIdx.y * TILE_Y + threadIdx.y;
   if (x >= T.width || y >= P.row1) return;
@@ -114,7 +136,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
       t.first = ColTerm{f0.x, f0.y};
     }
     t.px = t.py = t.pxb = t.pyb = 0.0f;
-    if (P.any_generic) {
+    if constexpr (GEN) {
       t.px = __ldg(P.planar_raw + x);
       t.py = __ldg(P.planar_raw + 2 * T.width + y);
     }
@@ -128,7 +150,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
         float2 f1 = __ldg(P.col_tab + T.width + xf);
         t.firstb = ColTerm{f1.x, f1.y};
       }
-      if (P.any_generic) {
+      if constexpr (GEN) {
         t.pxb = __ldg(P.planar_raw + T.width + x);
         t.pyb = __ldg(P.planar_raw + 2 * T.width + T.height + y);
       }
@@ -138,10 +160,10 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
   int idx;
   if constexpr (!TWINE) {
     auto ray_of = [&](int i, float r[3]) {
-      const FacetDev& F = MODE == EU_MODE_SINGLE ? P.f0 : P.facets[i];
-      dev_facet_ray(T, F, t, 0, y, r);
+      const FacetDev& F = MODE == EU_MODE_SINGLE ? P.f0 : fa[i];
+      dev_facet_ray<GEN, 0>(T, F, t, y, r);
     };
-    idx = dev_synopsis<NCH, TS, MODE, DEG>(P, ray_of, px);
+    idx = dev_synopsis<NCH, TS, MODE, DEG>(P, fa, ray_of, px);
   } else {
     // deriv_stepper (stepper.h:1606-1694) + twine_t (twining.h:106-263) /
     // synopsis_t (envutil_payload.cc:647-690)
@@ -151,9 +173,9 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
     idx = -1;
     if constexpr (MODE == EU_MODE_SINGLE) {
       float r00[3], du[3], dv[3];
-      dev_facet_ray(T, P.f0, t, 0, y, r00);
-      dev_facet_ray(T, P.f0, t, 1, y, du);
-      dev_facet_ray(T, P.f0, t, 2, y, dv);
+      dev_facet_ray<GEN, 0>(T, P.f0, t, y, r00);
+      dev_facet_ray<GEN, 1>(T, P.f0, t, y, du);
+      dev_facet_ray<GEN, 2>(T, P.f0, t, y, dv);
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         du[c] = du[c] - r00[c];
@@ -173,11 +195,11 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
       // per-facet ninepacks live in local memory; the taps loop re-reads them
       float np[EU_MAX_FACETS][9];
       for (int i = 0; i < P.n_facets; i++) {
-        const FacetDev& F = P.facets[i];
+        const FacetDev& F = fa[i];
         float r00[3], r10[3], r01[3];
-        dev_facet_ray(T, F, t, 0, y, r00);
-        dev_facet_ray(T, F, t, 1, y, r10);
-        dev_facet_ray(T, F, t, 2, y, r01);
+        dev_facet_ray<GEN, 0>(T, F, t, y, r00);
+        dev_facet_ray<GEN, 1>(T, F, t, y, r10);
+        dev_facet_ray<GEN, 2>(T, F, t, y, r01);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           np[i][c] = r00[c];
@@ -191,7 +213,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
 #pragma unroll
           for (int c = 0; c < 3; c++) r[c] = np[i][c] + cx * np[i][3 + c] + cy * np[i][6 + c];
         };
-        int id = dev_synopsis<NCH, TS, MODE, DEG>(P, ray_of, help);
+        int id = dev_synopsis<NCH, TS, MODE, DEG>(P, fa, ray_of, help);
         if (k == 0) idx = id;
 #pragma unroll
         for (int c = 0; c < NCH; c++) acc[c] += cw * help[c];
@@ -422,10 +444,25 @@ static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_
       if (P.degree == 3) { k_render_tiled<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P); return; }
     }
   }
+  if (P.any_generic) {  // translation: the generic-stepper build (run-time degree, facets in global memory)
+    k_render<NCH, TS, MODE, TWINE, -1, false, true><<<grid, block, 0, st>>>(P);
+    return;
+  }
+  if constexpr (MODE != EU_MODE_SINGLE) {
+    static const bool no_smem_facets = getenv("EU_NO_SMEM_FACETS") != nullptr;  // A/B switch for measurements
+    if (P.n_facets <= EU_SMEM_FACETS && !no_smem_facets) {
+      switch (P.degree) {
+        case 1: k_render<NCH, TS, MODE, TWINE, 1, true, false><<<grid, block, 0, st>>>(P); break;
+        case 3: k_render<NCH, TS, MODE, TWINE, 3, true, false><<<grid, block, 0, st>>>(P); break;
+        default: k_render<NCH, TS, MODE, TWINE, -1, true, false><<<grid, block, 0, st>>>(P); break;
+      }
+      return;
+    }
+  }
   switch (P.degree) {
-    case 1: k_render<NCH, TS, MODE, TWINE, 1><<<grid, block, 0, st>>>(P); break;
-    case 3: k_render<NCH, TS, MODE, TWINE, 3><<<grid, block, 0, st>>>(P); break;
-    default: k_render<NCH, TS, MODE, TWINE, -1><<<grid, block, 0, st>>>(P); break;
+    case 1: k_render<NCH, TS, MODE, TWINE, 1, false, false><<<grid, block, 0, st>>>(P); break;
+    case 3: k_render<NCH, TS, MODE, TWINE, 3, false, false><<<grid, block, 0, st>>>(P); break;
+    default: k_render<NCH, TS, MODE, TWINE, -1, false, false><<<grid, block, 0, st>>>(P); break;
   }
 }
 
