@@ -289,6 +289,9 @@ void target_dev(const eu_target_t* t, bool normalize, TargetDev& T) {
   T.refc_md = (float)((a1 - a0) / 2.0);
 }
 
+// the facet a single-facet job renders (solo), else facet 0
+int first_of(int nf, const eu_opts_t* o) { return (nf > 1 && o->solo >= 0 && o->solo < nf) ? o->solo : 0; }
+
 struct Plan {
   RenderParams P;
   int launches;
@@ -305,13 +308,9 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   if (o->spline_degree < 0 || o->spline_degree > EU_MAX_DEGREE)
     return fail(EU_ERR_ARGUMENT, "spline degree %d out of range 0..%d", o->spline_degree, EU_MAX_DEGREE);
   int nch = t->nchannels;
-  if (nch != 1 && nch != 3 && nch != 4)
-    return fail(EU_ERR_UNSUPPORTED, "%d-channel targets are not supported (1, 3, 4 are)", nch);
+  if (nch < 1 || nch > 4) return fail(EU_ERR_ARGUMENT, "%d-channel target", nch);
   for (int i = 0; i < nf; i++) {
     if (!known_source(sources[i])) return fail(EU_ERR_ARGUMENT, "source %d is not a live handle", i);
-    if (sources[i]->nch != nch)
-      return fail(EU_ERR_UNSUPPORTED, "facet %d has %d channels, target %d: channel adaptation (repix_t) is not built", i,
-                  sources[i]->nch, nch);
     if (sources[i]->degree != o->spline_degree)
       return fail(EU_ERR_ARGUMENT, "source %d was staged for degree %d, job asks for %d", i, sources[i]->degree,
                   o->spline_degree);
@@ -328,17 +327,15 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     if (o->solo >= nf) return fail(EU_ERR_ARGUMENT, "solo %d >= facet count %d", o->solo, nf);
     first = o->solo;
   }
-  if (mode == EU_MODE_HDR && nch == 4) return fail(EU_ERR_UNSUPPORTED, "hdr_merge of RGBA facets is not built");
+  // roll_out: 2/4-channel panoramas composite with alpha (voronoi_syn_plus, envutil_payload.cc:2306-2311)
+  if (mode == EU_MODE_VORONOI && (nch == 2 || nch == 4)) mode = EU_MODE_VORONOI_PLUS;
   // normalize: envutil_payload.cc:2105,2118 (false for one facet without twining), else true
   target_dev(t, !(mode == EU_MODE_SINGLE && n_taps == 0), P.trg);
   P.mode = mode;
   P.degree = o->spline_degree;
   P.n_taps = n_taps;
   P.nch = nch;
-  P.tstride = sources[0]->tstride;
-  for (int i = 1; i < nf; i++)
-    if (sources[i]->tstride != P.tstride)
-      return fail(EU_ERR_ARGUMENT, "all facets of a job must use the same texel layout");
+  P.tstride = sources[first_of(nf, o)]->tstride;
   std::vector<FacetDev> F(nf);
   for (int i = 0; i < nf; i++) {
     int rc = facet_dev(t, &facets[i], sources[i], F[i]);
@@ -409,8 +406,13 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   P.col_tab = g.d_planar;
   P.row_tab = g.d_planar + 2 * (size_t)t->width;
   P.planar_raw = reinterpret_cast<const float*>(g.d_planar + 2 * (size_t)(t->width + t->height));
+  // the specialised kernels assume every facet they touch has the job's channel count and one
+  // texel stride; anything else (and translation) runs the general build
   P.any_generic = 0;
-  for (int i = 0; i < nf; i++) P.any_generic |= F[i].generic;
+  for (int i = 0; i < nf; i++) {
+    if (mode == EU_MODE_SINGLE && i != first) continue;
+    if (F[i].generic || sources[i]->nch != nch || sources[i]->tstride != P.tstride) P.any_generic = 1;
+  }
   {
     int d = o->spline_degree;
     for (int row = 0; row <= d; row++)
@@ -597,7 +599,7 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
   int rc = need_up();
   if (rc) return rc;
   if (!f || !o || !pixels || !out) return fail(EU_ERR_ARGUMENT, "null argument");
-  if (f->width <= 0 || f->height <= 0 || f->nchannels < 1 || f->nchannels > 4 || f->nchannels == 2)
+  if (f->width <= 0 || f->height <= 0 || f->nchannels < 1 || f->nchannels > 4)
     return fail(EU_ERR_ARGUMENT, "bad raster description %dx%dx%d", f->width, f->height, f->nchannels);
   if (o->spline_degree < 0 || o->spline_degree > EU_MAX_DEGREE)
     return fail(EU_ERR_ARGUMENT, "spline degree %d out of range", o->spline_degree);

@@ -562,6 +562,127 @@ __device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, con
   return face;
 }
 
+// ---- the general build: any mix of channel counts and texel strides, degree at run time ------
+// safe evaluator with the texel stride and the degree read at run time (same operation order as
+// the specialised code above; loops instead of unrolled windows)
+template <int SNCH>
+__device__ __noinline__ void dev_spline_eval_rt(const SourceDev& S, int degree, const float* __restrict__ wmat,
+                                                float cx, float cy, float out[SNCH]) {
+  Located L = dev_locate(S, degree, cx, cy);
+  const int ts = S.tstride, h2 = degree / 2, order = degree + 1;
+  const float* __restrict__ p0 = S.core + (ptrdiff_t)(L.iy - h2) * S.stride + (ptrdiff_t)(L.ix - h2) * ts;
+  if (degree == 0) {
+#pragma unroll
+    for (int c = 0; c < SNCH; c++) out[c] = __ldg(p0 + c);
+    return;
+  }
+  if (degree == 1) {  // _eval_linear, zimt/eval.h:1004-1059
+    float wl0 = 1.0f - L.fx, wr0 = L.fx, wl1 = 1.0f - L.fy, wr1 = L.fy;
+#pragma unroll
+    for (int c = 0; c < SNCH; c++) {
+      float sum = __ldg(p0 + c);
+      sum *= wl0;
+      sum += __ldg(p0 + ts + c) * wr0;
+      sum *= wl1;
+      float sub = __ldg(p0 + S.stride + c);
+      sub *= wl0;
+      sub += __ldg(p0 + S.stride + ts + c) * wr0;
+      sum += sub * wr1;
+      out[c] = sum;
+    }
+    return;
+  }
+  float wx[EU_MAX_DEGREE + 1], wy[EU_MAX_DEGREE + 1];
+  for (int axis = 0; axis < 2; axis++) {  // basis_functor, zimt/basis.h:650-689
+    float* w = axis ? wy : wx;
+    float delta = axis ? L.fy : L.fx;
+    float power = delta;
+    for (int k = 0; k < order; k++) w[k] = wmat[k];
+    for (int row = 1; row < order; row++) {
+      for (int k = 0; k < order; k++) w[k] += power * wmat[row * order + k];
+      if (row < order - 1) power *= delta;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < SNCH; c++) {  // _eval, zimt/eval.h:903-996
+    float sum = 0.0f;
+    for (int j = 0; j < order; j++) {
+      const float* __restrict__ row = p0 + (ptrdiff_t)j * S.stride + c;
+      float sub = __ldg(row);
+      sub *= wx[0];
+      for (int i = 1; i < order; i++) sub += wx[i] * __ldg(row + i * ts);
+      if (j == 0) {
+        sum = sub;
+        sum *= wy[0];
+      } else {
+        sum += sub * wy[j];
+      }
+    }
+    out[c] = sum;
+  }
+}
+
+// repix_t, environment.h:1205-1309: a facet pixel of in_n channels as a pixel of OUT channels
+template <int OUT>
+__device__ __forceinline__ void dev_repix(int in_n, const float in[4], float out[OUT]) {
+  if (in_n == OUT) {
+#pragma unroll
+    for (int i = 0; i < OUT; i++) out[i] = in[i];
+    return;
+  }
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  switch (in_n) {
+    case 1:
+      if (OUT == 3) { o[0] = o[1] = o[2] = in[0]; }
+      else if (OUT == 2) { o[0] = in[0]; o[1] = 1.0f; }
+      else { o[0] = o[1] = o[2] = in[0]; o[3] = 1.0f; }
+      break;
+    case 2:
+      if (OUT == 1) { o[0] = in[0] / in[1]; if (in[1] == 0.0f) o[0] = 0.0f; }
+      else if (OUT == 3) { float g = in[0] / in[1]; if (in[1] == 0.0f) g = 0.0f; o[0] = o[1] = o[2] = g; }
+      else { o[0] = o[1] = o[2] = in[0]; o[3] = in[1]; }
+      break;
+    case 3: {
+      float sum = in[0];
+      sum += in[1];
+      sum += in[2];
+      if (OUT == 1) o[0] = sum / 3.0f;
+      else if (OUT == 2) { o[0] = sum / 3.0f; o[1] = 1.0f; }
+      else { o[0] = in[0]; o[1] = in[1]; o[2] = in[2]; o[3] = 1.0f; }
+      break;
+    }
+    default:
+      if (OUT == 1) { o[0] = (in[0] + in[1] + in[2]) / 3.0f; o[0] /= in[3]; if (in[3] == 0.0f) o[0] = 0.0f; }
+      else if (OUT == 2) { o[0] = (in[0] + in[1] + in[2]) / 3.0f; o[1] = in[3]; }
+      else {
+        o[0] = in[0] / in[3]; o[1] = in[1] / in[3]; o[2] = in[2] / in[3];
+        if (in[3] == 0.0f) o[0] = o[1] = o[2] = 0.0f;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < OUT; i++) out[i] = o[i];
+}
+
+// environment::eval for any facet: evaluate in the source's channel count, repix, brighten
+template <int NCH>
+__device__ __forceinline__ int dev_facet_eval_general(const FacetDev& F, int degree, const float* __restrict__ wmat,
+                                                      const float r[3], float px[NCH]) {
+  int face;
+  float cx, cy, sp[4] = {0.f, 0.f, 0.f, 0.f};
+  bool hit = dev_facet_coordinate(F, r, face, cx, cy);
+  if (hit) {
+    switch (F.src.nch) {
+      case 1: dev_spline_eval_rt<1>(F.src, degree, wmat, cx, cy, sp); break;
+      case 2: dev_spline_eval_rt<2>(F.src, degree, wmat, cx, cy, sp); break;
+      case 3: dev_spline_eval_rt<3>(F.src, degree, wmat, cx, cy, sp); break;
+      default: dev_spline_eval_rt<4>(F.src, degree, wmat, cx, cy, sp); break;
+    }
+  }
+  dev_repix<NCH>(F.src.nch, sp, px);  // a miss is a zero pixel of the SOURCE type (environment.h:1190-1193)
+  dev_brighten<NCH>(F, px);
+  return hit ? face : -1;
+}
+
 // _hdr_merge_syn::get_quality, envutil_payload.cc:1390-1442
 __device__ __forceinline__ float dev_hdr_quality(float grey, float optimum, int kind) {
   bool large = grey > optimum;

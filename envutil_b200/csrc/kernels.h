@@ -17,6 +17,7 @@ struct IirDev {
 cudaError_t eu_launch_planar_tables(const TargetDev& T, float2* d_col, float2* d_row, float* d_raw, cudaStream_t st);
 // per (channels, texel stride) translation units (render_c*.cu)
 cudaError_t eu_launch_render_c1(const RenderParams& P, cudaStream_t st);
+cudaError_t eu_launch_render_c2(const RenderParams& P, cudaStream_t st);
 cudaError_t eu_launch_render_c3(const RenderParams& P, cudaStream_t st);
 cudaError_t eu_launch_render_c3p(const RenderParams& P, cudaStream_t st);
 cudaError_t eu_launch_render_c4(const RenderParams& P, cudaStream_t st);

@@ -15,7 +15,8 @@
 
 enum { EU_SRC_MOUNT = 0, EU_SRC_CUBEMAP = 1, EU_SRC_BIATAN6 = 2 };
 enum { EU_BC_PERIODIC = 0, EU_BC_REFLECT = 1, EU_BC_NATURAL = 2, EU_BC_MIRROR = 3 };
-enum { EU_MODE_SINGLE = 0, EU_MODE_VORONOI = 1, EU_MODE_HDR = 2 };
+// VORONOI_PLUS: alpha compositing of the z-sorted facets (_voronoi_syn_plus), 2/4-channel jobs
+enum { EU_MODE_SINGLE = 0, EU_MODE_VORONOI = 1, EU_MODE_HDR = 2, EU_MODE_VORONOI_PLUS = 3 };
 enum { EU_HDR_LOW = 0, EU_HDR_MIDDLE = 1, EU_HDR_HIGH = 2 };
 
 // staged source in HBM: interleaved float texels, row-major container = core + brace frame
@@ -81,7 +82,8 @@ struct RenderParams {
   int32_t n_taps;     // 0: plain rays (ninputs 3), else twining (ninputs 9)
   int32_t nch;
   int32_t tstride;    // floats per texel in HBM: nch, or 4 (padded RGB); same for all facets
-  int32_t any_generic;  // some facet uses the generic stepper (needs planar_raw)
+  int32_t any_generic;  // the general build is needed: some facet uses the generic stepper (translation) or
+                        // differs from the job in channel count / texel stride
   int32_t use_tiles;  // 1: stage the gather footprint in shared memory where the kernel supports it
   int32_t src_cw, src_ch;  // container shape of f0's source in texels (tile path)
   int32_t src_lx, src_ly;  // its left / top brace: core texel (0,0) is container texel (lx, ly)

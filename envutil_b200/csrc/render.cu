@@ -43,9 +43,12 @@ cudaError_t eu_launch_planar_tables(const TargetDev& T, float2* d_col, float2* d
 }
 
 cudaError_t eu_launch_render(const RenderParams& P, cudaStream_t st) {
-  if (P.nch == 1 && P.tstride == 1) return eu_launch_render_c1(P, st);
-  if (P.nch == 3 && P.tstride == 3) return eu_launch_render_c3(P, st);
+  // the general build (any_generic) ignores the compile-time texel stride, any TU of the right
+  // channel count serves it
+  if (P.nch == 1) return eu_launch_render_c1(P, st);
+  if (P.nch == 2) return eu_launch_render_c2(P, st);
+  if (P.nch == 3 && (P.tstride == 3 || P.any_generic)) return eu_launch_render_c3(P, st);
   if (P.nch == 3 && P.tstride == 4) return eu_launch_render_c3p(P, st);
-  if (P.nch == 4 && P.tstride == 4) return eu_launch_render_c4(P, st);
+  if (P.nch == 4) return eu_launch_render_c4(P, st);
   return cudaErrorInvalidValue;
 }

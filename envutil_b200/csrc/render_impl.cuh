@@ -45,19 +45,30 @@ __device__ __forceinline__ void dev_facet_ray(const TargetDev& T, const FacetDev
               WHICH == 1 ? t.firstb : t.first, y, r);
 }
 
-// one synopsis evaluation (envutil_payload.cc:818-956 voronoi, :1500-1622 hdr_merge) for rays
-// produced by `ray_of(i, ray)`; returns the index-plane value
-// The facet array of synopsis jobs: `fa` points at the block's shared-memory copy (PF, up to
-// EU_SMEM_FACETS facets: every lane reads the same field, one broadcast wavefront instead of a
-// global load) or at the array in global memory.
+// environment::eval of one facet: the specialised evaluator, or - in the general build - the one
+// that copes with any channel count / texel stride / degree
+template <int NCH, int TS, int DEG, bool GEN>
+__device__ __forceinline__ int dev_eval_facet(const RenderParams& P, const FacetDev& F, const float r[3],
+                                              float px[NCH]) {
+  if constexpr (GEN) return dev_facet_eval_general<NCH>(F, P.degree, P.wmat, r, px);
+  else return dev_facet_eval<NCH, TS, DEG>(F, P.degree, P.wmat, r, px);
+}
 
-template <int NCH, int TS, int MODE, int DEG, typename RayFn>
+// One synopsis evaluation for rays produced by `ray_of(i, ray)`; returns the index-plane value.
+//   single facet / _voronoi_syn (envutil_payload.cc:818-956) / _hdr_merge_syn (:1500-1622) /
+//   _voronoi_syn_plus (:964-1233)
+// `fa`: the facet array - the block's shared-memory copy (PF, up to EU_SMEM_FACETS facets: every
+// lane reads the same field, one broadcast wavefront instead of a global load) or global memory.
+// `active`: this lane renders a pixel. Only VORONOI_PLUS needs it: the reference takes a shortcut
+// per 16-lane zimt vector there, which is voted on by the half-warp, so every lane of the warp
+// must walk through the code (a warp is 32 consecutive pixels of one row = two zimt vectors).
+template <int NCH, int TS, int MODE, int DEG, bool GEN, typename RayFn>
 __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDev* __restrict__ fa, RayFn ray_of,
-                                            float px[NCH]) {
+                                            bool active, float px[NCH]) {
   if constexpr (MODE == EU_MODE_SINGLE) {
     float r[3];
     ray_of(0, r);
-    return dev_facet_eval<NCH, TS, DEG>(P.f0, P.degree, P.wmat, r, px);
+    return dev_eval_facet<NCH, TS, DEG, GEN>(P, P.f0, r, px);
   } else if constexpr (MODE == EU_MODE_VORONOI) {
     int champion = -1;
     float max_z = -FLT_MAX, best[3] = {0.f, 0.f, 0.f};
@@ -77,10 +88,14 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
 #pragma unroll
       for (int c = 0; c < NCH; c++) px[c] = 0.0f;
     } else {
-      dev_facet_eval<NCH, TS, DEG>(fa[champion], P.degree, P.wmat, best, px);
+      dev_eval_facet<NCH, TS, DEG, GEN>(P, fa[champion], best, px);
     }
     return champion;
-  } else {
+  } else if constexpr (MODE == EU_MODE_HDR) {
+    // with alpha the colour is de-associated for the weighted sum, alpha is the maximum seen and
+    // the result is re-associated (:1527-1547,1597-1620)
+    constexpr int NA = (NCH == 2 || NCH == 4) ? NCH - 1 : -1;
+    constexpr int NCOL = NA >= 0 ? NA : NCH;
     float qsum = 0.0f, p[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; c++) px[c] = 0.0f;
@@ -88,20 +103,99 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
       const FacetDev& F = fa[i];
       float r[3];
       ray_of(i, r);
-      dev_facet_eval<NCH, TS, DEG>(F, P.degree, P.wmat, r, p);
+      dev_eval_facet<NCH, TS, DEG, GEN>(P, F, r, p);
       float grey = p[0];
       if constexpr (NCH >= 3) grey = fmaxf(p[0], fmaxf(p[1], p[2]));
       float q = dev_hdr_quality(grey, F.hdr_optimum, F.hdr_kind);
+      if constexpr (NA >= 0) q = p[NA] * q;
       qsum += q;
+      if constexpr (NA < 0) {
 #pragma unroll
-      for (int c = 0; c < NCH; c++) px[c] += p[c] * q;
+        for (int c = 0; c < NCH; c++) px[c] += p[c] * q;
+      } else {
+#pragma unroll
+        for (int c = 0; c < NCOL; c++) {
+          float v = 0.0f;
+          if (p[NA] > 0.000001f) v = p[c] / p[NA];
+          px[c] += v * q;
+        }
+        px[NA] = fmaxf(px[NA], p[NA]);
+      }
     }
 #pragma unroll
-    for (int c = 0; c < NCH; c++) {
+    for (int c = 0; c < NCOL; c++) {
       px[c] /= qsum;
       if (!(qsum > 0.0f)) px[c] = 0.0f;
+      if constexpr (NA >= 0) px[c] *= px[NA];
     }
     return -1;
+  } else {
+    // _voronoi_syn_plus: facets the ray hits, sorted by z * recip_step (stable, strictly greater
+    // moves up), composited front to back as associated alpha
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned gmask = (lane < 16u) ? 0x0000ffffu : 0xffff0000u;
+    float zs[EU_MAX_FACETS];
+    int ids[EU_MAX_FACETS];
+    int cnt = 0, next_best = -1;  // next_best: the last facet any lane of this zimt vector hit
+    for (int i = 0; i < P.n_facets; i++) {
+      const FacetDev& F = fa[i];
+      float r[3];
+      ray_of(i, r);
+      const bool valid = active && dev_facet_mask(F, r);
+      if (__ballot_sync(0xffffffffu, valid) & gmask) next_best = i;
+      if (valid) {
+        float z = r[2] * F.recip_step;
+        int k = cnt++;
+        while (k > 0 && z > zs[k - 1]) {
+          zs[k] = zs[k - 1];
+          ids[k] = ids[k - 1];
+          k--;
+        }
+        zs[k] = z;
+        ids[k] = i;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; c++) px[c] = 0.0f;
+    const int top = cnt ? ids[0] : -1;
+    float help[NCH];
+    bool have_top = false, done = false;
+    // shortcut (:1132-1150): all lanes of the vector have next_best in front and are opaque there
+    const unsigned not_top = __ballot_sync(0xffffffffu, active && top != next_best) & gmask;
+    const bool try_shortcut = next_best >= 0 && not_top == 0u;
+    bool opaque = true;
+    if (try_shortcut && active) {
+      float r[3];
+      ray_of(top, r);
+      dev_eval_facet<NCH, TS, DEG, GEN>(P, fa[top], r, help);
+      have_top = true;
+      opaque = help[NCH - 1] >= 1.0f;
+    }
+    const unsigned not_opaque = __ballot_sync(0xffffffffu, active && !opaque) & gmask;
+    if (try_shortcut && not_opaque == 0u) {
+      done = true;
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) px[c] = help[c];
+      }
+    }
+    if (!done) {
+      for (int k = 0; k < cnt; k++) {
+        if (!(k == 0 && have_top)) {
+          float r[3];
+          ray_of(ids[k], r);
+          dev_eval_facet<NCH, TS, DEG, GEN>(P, fa[ids[k]], r, help);
+        }
+        if (k == 0) {
+#pragma unroll
+          for (int c = 0; c < NCH; c++) px[c] = help[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < NCH; c++) px[c] += (1.0f - px[NCH - 1]) * help[c];
+        }
+      }
+    }
+    return top;
   }
 }
 
@@ -123,7 +217,13 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
   }
   int x = blockIdx.x * TILE_X + threadIdx.x;
   int y = P.row0 + blockIdx.y * TILE_Y + threadIdx.y;
-  if (x >= T.width || y >= P.row1) return;
+  const bool active = x < T.width && y < P.row1;
+  if constexpr (MODE != EU_MODE_VORONOI_PLUS) {
+    if (!active) return;
+  } else {  // all lanes stay for the half-warp votes; idle ones compute on a pixel that exists
+    if (y >= P.row1) return;  // whole warp (a warp is one row of the tile)
+    x = min(x, T.width - 1);
+  }
   int xf = first_lane_column(x);
   PixelTerms t;
   {
@@ -163,7 +263,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
       const FacetDev& F = MODE == EU_MODE_SINGLE ? P.f0 : fa[i];
       dev_facet_ray<GEN, 0>(T, F, t, y, r);
     };
-    idx = dev_synopsis<NCH, TS, MODE, DEG>(P, fa, ray_of, px);
+    idx = dev_synopsis<NCH, TS, MODE, DEG, GEN>(P, fa, ray_of, active, px);
   } else {
     // deriv_stepper (stepper.h:1606-1694) + twine_t (twining.h:106-263) /
     // synopsis_t (envutil_payload.cc:647-690)
@@ -186,7 +286,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
         float r[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) r[c] = r00[c] + cx * du[c] + cy * dv[c];
-        int id = dev_facet_eval<NCH, TS, DEG>(P.f0, P.degree, P.wmat, r, help);
+        int id = dev_eval_facet<NCH, TS, DEG, GEN>(P, P.f0, r, help);
         if (k == 0) idx = id;
 #pragma unroll
         for (int c = 0; c < NCH; c++) acc[c] += cw * help[c];
@@ -213,7 +313,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
 #pragma unroll
           for (int c = 0; c < 3; c++) r[c] = np[i][c] + cx * np[i][3 + c] + cy * np[i][6 + c];
         };
-        int id = dev_synopsis<NCH, TS, MODE, DEG>(P, fa, ray_of, help);
+        int id = dev_synopsis<NCH, TS, MODE, DEG, GEN>(P, fa, ray_of, active, help);
         if (k == 0) idx = id;
 #pragma unroll
         for (int c = 0; c < NCH; c++) acc[c] += cw * help[c];
@@ -222,6 +322,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
 #pragma unroll
     for (int c = 0; c < NCH; c++) px[c] = acc[c];
   }
+  if (!active) return;
   size_t o = (size_t)(y - P.row0) * T.width + x;
   if (P.out) {
     float* dst = P.out + o * NCH;
@@ -439,7 +540,7 @@ template <int NCH, int TS, int MODE, bool TWINE>
 static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st) {
   if constexpr (MODE == EU_MODE_SINGLE) {
     // footprint-staged kernel: needs 16-byte row granules and a pixel output (no index plane)
-    if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.f0.generic) {
+    if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.any_generic) {
       if (P.degree == 1) { k_render_tiled<NCH, TS, TWINE, 1><<<grid, block, 0, st>>>(P); return; }
       if (P.degree == 3) { k_render_tiled<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P); return; }
     }
@@ -471,14 +572,27 @@ static cudaError_t launch_render(const RenderParams& P, cudaStream_t st) {
   dim3 block(TILE_X, TILE_Y);
   dim3 grid((P.trg.width + TILE_X - 1) / TILE_X, (P.row1 - P.row0 + TILE_Y - 1) / TILE_Y);
   bool tw = P.n_taps > 0;
+  constexpr bool ALPHA = (NCH == 2 || NCH == 4);
   switch (P.mode) {
     case EU_MODE_SINGLE:
       if (tw) launch_deg<NCH, TS, EU_MODE_SINGLE, true>(P, grid, block, st);
       else launch_deg<NCH, TS, EU_MODE_SINGLE, false>(P, grid, block, st);
       break;
     case EU_MODE_VORONOI:
-      if (tw) launch_deg<NCH, TS, EU_MODE_VORONOI, true>(P, grid, block, st);
-      else launch_deg<NCH, TS, EU_MODE_VORONOI, false>(P, grid, block, st);
+      if constexpr (!ALPHA) {
+        if (tw) launch_deg<NCH, TS, EU_MODE_VORONOI, true>(P, grid, block, st);
+        else launch_deg<NCH, TS, EU_MODE_VORONOI, false>(P, grid, block, st);
+      } else {
+        return cudaErrorInvalidValue;
+      }
+      break;
+    case EU_MODE_VORONOI_PLUS:
+      if constexpr (ALPHA) {
+        if (tw) launch_deg<NCH, TS, EU_MODE_VORONOI_PLUS, true>(P, grid, block, st);
+        else launch_deg<NCH, TS, EU_MODE_VORONOI_PLUS, false>(P, grid, block, st);
+      } else {
+        return cudaErrorInvalidValue;
+      }
       break;
     default:
       if (tw) launch_deg<NCH, TS, EU_MODE_HDR, true>(P, grid, block, st);

@@ -143,7 +143,12 @@ class Job:
     # ---- POD structs of the C ABI ----
     def structs(self, lib=None):
         lib = lib or capi.load()
-        nch = self.facets[0].shape()[2]
+        # channel-count rule of arguments::init (envutil_main.cc:1063-1122): the maximum over the
+        # facets; RGB together with any alpha-carrying facet renders RGBA
+        counts = [f.shape()[2] for f in self.facets]
+        nch = max(counts)
+        if nch == 3 and any(c in (2, 4) for c in counts):
+            nch = 4
         t = capi.Target()
         t.projection = capi.PROJECTION_NAMES.index(self.projection)
         t.width, t.height, t.nchannels = self.width, self.height, nch

@@ -1076,28 +1076,67 @@ static int facet_mask(const facet_ctx* F, const float r[3]) {
   return mount_mask(F, r, c);
 }
 
+/* repix_t, environment.h:1205-1309: channel-count adaptation between a facet and the target */
+static void repix(int in_n, int out_n, const float* in, float* out) {
+  if (in_n == out_n) {
+    for (int i = 0; i < in_n; i++) out[i] = in[i];
+    return;
+  }
+  switch (in_n) {
+    case 1:
+      if (out_n == 3) { out[0] = out[1] = out[2] = in[0]; }
+      else if (out_n == 2) { out[0] = in[0]; out[1] = 1.0f; }
+      else { out[0] = out[1] = out[2] = in[0]; out[3] = 1.0f; }
+      break;
+    case 2:
+      if (out_n == 1) { out[0] = in[0] / in[1]; if (in[1] == 0.0f) out[0] = 0.0f; }
+      else if (out_n == 3) { float g = in[0] / in[1]; if (in[1] == 0.0f) g = 0.0f; out[0] = out[1] = out[2] = g; }
+      else { out[0] = out[1] = out[2] = in[0]; out[3] = in[1]; }
+      break;
+    case 3: {
+      float sum = in[0];  /* xel_t::sum(): ((in0 + in1) + in2), zimt/xel.h */
+      sum += in[1];
+      sum += in[2];
+      if (out_n == 1) out[0] = sum / 3.0f;
+      else if (out_n == 2) { out[0] = sum / 3.0f; out[1] = 1.0f; }
+      else { out[0] = in[0]; out[1] = in[1]; out[2] = in[2]; out[3] = 1.0f; }
+      break;
+    }
+    default:
+      if (out_n == 1) { out[0] = (in[0] + in[1] + in[2]) / 3.0f; out[0] /= in[3]; if (in[3] == 0.0f) out[0] = 0.0f; }
+      else if (out_n == 2) { out[0] = (in[0] + in[1] + in[2]) / 3.0f; out[1] = in[3]; }
+      else {
+        out[0] = in[0] / in[3]; out[1] = in[1] / in[3]; out[2] = in[2] / in[3];
+        if (in[3] == 0.0f) out[0] = out[1] = out[2] = 0.0f;
+      }
+  }
+}
+
 /* environment::eval, environment.h:1821-1842 over mount_t::eval :1172-1196 or
- * cubemap_view_t::eval :1473-1486. Returns the cube face (or -1). */
-static int facet_eval(const facet_ctx* F, const float r[3], float* px) {
+ * cubemap_view_t::eval :1473-1486, then repix_t to the job's channel count (:1862-1960), then
+ * brighten on the colour channels. Returns the cube face (or -1). */
+static int facet_eval(const facet_ctx* F, int nch, const float r[3], float* px) {
   const orc_source_t* s = F->src;
-  int nch = s->nch, face = -1;
+  int snch = s->nch, face = -1;
+  float sp[4] = {0, 0, 0, 0};
+  int hit = 1;
   if (F->kind == KIND_MOUNT) {
     float c[2];
     mount_coordinate(F, r, c);
     if (!mount_mask(F, r, c)) {
-      for (int i = 0; i < nch; i++) px[i] = 0.0f;
-      return -1;
+      hit = 0; /* mount_t::eval zeroes the source-typed pixel (:1190-1193); repix then sees zeros */
+    } else {
+      /* source_t::md_to_spline, :988-1006 */
+      float ix = (float)((double)c[0] - F->ext_x0);
+      ix /= F->ext_w;
+      ix *= (float)F->total_w;
+      ix -= .5f;
+      float iy = (float)((double)c[1] - F->ext_y0);
+      iy /= F->ext_h;
+      iy *= (float)F->total_h;
+      iy -= .5f;
+      spline_eval(s, s->degree, s->wmat, ix, iy, sp);
     }
-    /* source_t::md_to_spline, :988-1006 */
-    float ix = (float)((double)c[0] - F->ext_x0);
-    ix /= F->ext_w;
-    ix *= (float)F->total_w;
-    ix -= .5f;
-    float iy = (float)((double)c[1] - F->ext_y0);
-    iy /= F->ext_h;
-    iy *= (float)F->total_h;
-    iy -= .5f;
-    spline_eval(s, s->degree, s->wmat, ix, iy, px);
   } else {
     float in_face[2], pk[2];
     ray_to_cubeface(r, &face, in_face);
@@ -1113,13 +1152,15 @@ static int facet_eval(const facet_ctx* F, const float r[3], float* px) {
     pk[1] += (float)(face * F->section_px);
     pk[0] -= .5f;
     pk[1] -= .5f;
-    spline_eval(s, s->degree, s->wmat, pk[0], pk[1], px);
+    spline_eval(s, s->degree, s->wmat, pk[0], pk[1], sp);
   }
+  (void)hit;
+  repix(snch, nch, sp, px);
   if (F->brighten != 1.0f) {
     int ncol = (nch == 2 || nch == 4) ? nch - 1 : nch;
     for (int i = 0; i < ncol; i++) px[i] *= F->brighten;
   }
-  return face;
+  return hit ? face : -1;
 }
 
 /* _hdr_merge_syn::get_quality, envutil_payload.cc:1390-1442 */
@@ -1135,7 +1176,7 @@ static float hdr_quality(float grey, float optimum, int kind) {
 /* one synopsis evaluation for a set of per-facet rays: single facet, _voronoi_syn
  * (envutil_payload.cc:818-956) or _hdr_merge_syn (:1500-1622) */
 static int synopsis(int mode, int nf, const facet_ctx* F, float (*rays)[3], int nch, float* px) {
-  if (mode == 0) return facet_eval(&F[0], rays[0], px);
+  if (mode == 0) return facet_eval(&F[0], nch, rays[0], px);
   if (mode == 1) {
     int champion = -1;
     float max_z = -FLT_MAX;
@@ -1154,26 +1195,104 @@ static int synopsis(int mode, int nf, const facet_ctx* F, float (*rays)[3], int 
     if (champion < 0) {
       for (int c = 0; c < nch; c++) px[c] = 0.0f;
     } else {
-      facet_eval(&F[champion], rays[champion], px);
+      facet_eval(&F[champion], nch, rays[champion], px);
     }
     return champion;
   }
-  /* hdr_merge, 1 or 3 channels */
+  /* hdr_merge (envutil_payload.cc:1500-1622); with alpha the colour is de-associated for the
+   * weighted sum, the alpha is the maximum seen, and the result is re-associated */
   float acc[4] = {0, 0, 0, 0}, qsum = 0.0f, p[4];
+  int na = (nch == 2 || nch == 4) ? nch - 1 : -1; /* alpha channel index, or -1 */
   for (int i = 0; i < nf; i++) {
-    facet_eval(&F[i], rays[i], p);
-    float grey = nch == 1 ? p[0] : fmaxf(p[0], fmaxf(p[1], p[2]));
+    facet_eval(&F[i], nch, rays[i], p);
+    float grey = (nch <= 2) ? p[0] : fmaxf(p[0], fmaxf(p[1], p[2]));
     /* std::max(r, std::max(g,b)) returns its first argument on ties - same value */
     float q = hdr_quality(grey, F[i].optimum, F[i].hdr_kind);
+    if (na >= 0) q = p[na] * q; /* get_quality(grey, alpha, ...), :1400-1408 */
     qsum += q;
-    for (int c = 0; c < nch; c++) acc[c] += p[c] * q;
+    if (na < 0) {
+      for (int c = 0; c < nch; c++) acc[c] += p[c] * q;
+    } else {
+      for (int c = 0; c < na; c++) {
+        float v = 0.0f;
+        if (p[na] > 0.000001f) v = p[c] / p[na];
+        acc[c] += v * q;
+      }
+      acc[na] = fmaxf(acc[na], p[na]);
+    }
   }
-  for (int c = 0; c < nch; c++) {
+  int ncol = na >= 0 ? na : nch;
+  for (int c = 0; c < ncol; c++) {
     acc[c] /= qsum;
     if (!(qsum > 0.0f)) acc[c] = 0.0f;
-    px[c] = acc[c];
+    if (na >= 0) acc[c] *= acc[na];
   }
+  for (int c = 0; c < nch; c++) px[c] = acc[c];
   return -1;
+}
+
+/* _voronoi_syn_plus::operator() (envutil_payload.cc:964-1233) for one zimt vector of `nl` lanes
+ * (a 16-pixel run of a row): facets that the ray hits, sorted by z * recip_step (stable, strict
+ * >), composited front to back as associated alpha. The reference takes a shortcut per VECTOR:
+ * if every lane's front facet is the last facet that was hit at all (`next_best`) and every
+ * lane's alpha is >= 1, the front facet's pixels are the result - which differs from the
+ * composite where a b-spline overshoots alpha beyond 1. Hence the group-wise restatement. */
+static void voronoi_plus_group(int nf, const facet_ctx* F, int nl, float (*rays)[64][3], int nch, float (*out)[4],
+                               int* idx) {
+  static __thread int ids[ORC_LANES][64];
+  static __thread float zs[ORC_LANES][64];
+  int cnt[ORC_LANES];
+  int next_best = -1;
+  for (int l = 0; l < nl; l++) cnt[l] = 0;
+  for (int i = 0; i < nf; i++) {
+    int any = 0;
+    for (int l = 0; l < nl; l++) {
+      if (!facet_mask(&F[i], rays[l][i])) continue;
+      any = 1;
+      float z = rays[l][i][2] * F[i].recip_step;
+      int k = cnt[l]++;
+      zs[l][k] = z;
+      ids[l][k] = i;
+      while (k > 0 && zs[l][k] > zs[l][k - 1]) { /* masked_swap while strictly greater */
+        float tz = zs[l][k]; zs[l][k] = zs[l][k - 1]; zs[l][k - 1] = tz;
+        int ti = ids[l][k]; ids[l][k] = ids[l][k - 1]; ids[l][k - 1] = ti;
+        k--;
+      }
+    }
+    if (any) next_best = i;
+  }
+  for (int l = 0; l < nl; l++) {
+    for (int c = 0; c < nch; c++) out[l][c] = 0.0f;
+    if (idx) idx[l] = cnt[l] ? ids[l][0] : -1;
+  }
+  if (next_best < 0) return;
+  int all_top = 1;
+  for (int l = 0; l < nl; l++)
+    if (!(cnt[l] > 0 && ids[l][0] == next_best)) all_top = 0;
+  if (all_top) {
+    float help[ORC_LANES][4];
+    int opaque = 1;
+    for (int l = 0; l < nl; l++) {
+      facet_eval(&F[next_best], nch, rays[l][next_best], help[l]);
+      if (!(help[l][nch - 1] >= 1.0f)) opaque = 0;
+    }
+    if (opaque) {
+      for (int l = 0; l < nl; l++)
+        for (int c = 0; c < nch; c++) out[l][c] = help[l][c];
+      return;
+    }
+  }
+  for (int l = 0; l < nl; l++) {
+    float help[4];
+    for (int k = 0; k < cnt[l]; k++) {
+      facet_eval(&F[ids[l][k]], nch, rays[l][ids[l][k]], help);
+      if (k == 0) {
+        for (int c = 0; c < nch; c++) out[l][c] = help[c];
+      } else {
+        for (int c = 0; c < nch; c++) out[l][c] += (1.0f - out[l][nch - 1]) * help[c];
+      }
+    }
+  }
 }
 
 static int facet_setup(const eu_target_t* t, const eu_opts_t* o, const eu_facet_t* f, const orc_source_t* src,
@@ -1294,42 +1413,66 @@ int orc_render(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
 #else
   n_threads = 1;
 #endif
+  if (mode == 1 && (nch == 2 || nch == 4)) mode = 3; /* roll_out: voronoi_syn_plus for alpha, :2306-2311 */
 #pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads)
   for (int y = row0; y < row1; y++) {
-    float rays[64][3], r10[64][3], r01[64][3], sub[64][3];
-    for (int x = 0; x < T.width; x++) {
-      float* px = out + ((size_t)(y - row0) * T.width + x) * nch;
-      float p0x = planar_x(&T, x, 0.0f), p0y = planar_y(&T, y, 0.0f);
-      int idx;
+    /* one zimt vector at a time: 16 consecutive pixels of the row (segments are multiples of 16) */
+    float (*rays)[64][3] = (float (*)[64][3])malloc(sizeof(float) * ORC_LANES * 64 * 3);
+    float (*r10)[64][3] = (float (*)[64][3])malloc(sizeof(float) * ORC_LANES * 64 * 3);
+    float (*r01)[64][3] = (float (*)[64][3])malloc(sizeof(float) * ORC_LANES * 64 * 3);
+    float (*sub)[64][3] = (float (*)[64][3])malloc(sizeof(float) * ORC_LANES * 64 * 3);
+    for (int g0 = 0; g0 < T.width; g0 += ORC_LANES) {
+      int nl = T.width - g0 < ORC_LANES ? T.width - g0 : ORC_LANES;
+      float res[ORC_LANES][4], help[ORC_LANES][4];
+      int ids[ORC_LANES], hid[ORC_LANES];
+      float p0y = planar_y(&T, y, 0.0f), p1y = planar_y(&T, y, T.bias_y);
+      for (int l = 0; l < nl; l++) {
+        int x = g0 + l;
+        float p0x = planar_x(&T, x, 0.0f);
+        for (int i = 0; i < nfe; i++) stepper_ray(&T, &FE[i], p0x, p0y, x, y, 0.0f, rays[l][i]);
+        if (n_taps) {
+          float p1x = planar_x(&T, x, T.bias_x);
+          for (int i = 0; i < nfe; i++) {
+            stepper_ray(&T, &FE[i], p1x, p0y, x, y, T.bias_x, r10[l][i]);
+            stepper_ray(&T, &FE[i], p0x, p1y, x, y, 0.0f, r01[l][i]);
+          }
+        }
+      }
       if (n_taps == 0) {
-        for (int i = 0; i < nfe; i++) stepper_ray(&T, &FE[i], p0x, p0y, x, y, 0.0f, rays[i]);
-        idx = synopsis(mode, nfe, FE, rays, nch, px);
+        if (mode == 3) voronoi_plus_group(nfe, FE, nl, rays, nch, res, ids);
+        else
+          for (int l = 0; l < nl; l++) ids[l] = synopsis(mode, nfe, FE, rays[l], nch, res[l]);
       } else {
         /* deriv_stepper stepper.h:1606-1694; twine_t twining.h:106-263; synopsis_t
          * envutil_payload.cc:647-690 */
-        float p1x = planar_x(&T, x, T.bias_x), p1y = planar_y(&T, y, T.bias_y);
-        for (int i = 0; i < nfe; i++) {
-          stepper_ray(&T, &FE[i], p0x, p0y, x, y, 0.0f, rays[i]);
-          stepper_ray(&T, &FE[i], p1x, p0y, x, y, T.bias_x, r10[i]);
-          stepper_ray(&T, &FE[i], p0x, p1y, x, y, 0.0f, r01[i]);
+        for (int l = 0; l < nl; l++) {
+          ids[l] = -1;
+          for (int c = 0; c < 4; c++) res[l][c] = 0.0f;
         }
-        float acc[4] = {0, 0, 0, 0}, help[4];
-        idx = -1;
         for (int k = 0; k < n_taps; k++) {
           float cx = taps[k].x * 4.0f, cy = taps[k].y * 4.0f, cw = taps[k].w;
-          for (int i = 0; i < nfe; i++)
-            for (int c = 0; c < 3; c++) {
-              float du = r10[i][c] - rays[i][c], dv = r01[i][c] - rays[i][c];
-              sub[i][c] = rays[i][c] + cx * du + cy * dv;
-            }
-          int id = synopsis(mode, nfe, FE, sub, nch, help);
-          if (k == 0) idx = id;
-          for (int c = 0; c < nch; c++) acc[c] += cw * help[c];
+          for (int l = 0; l < nl; l++)
+            for (int i = 0; i < nfe; i++)
+              for (int c = 0; c < 3; c++) {
+                float du = r10[l][i][c] - rays[l][i][c], dv = r01[l][i][c] - rays[l][i][c];
+                sub[l][i][c] = rays[l][i][c] + cx * du + cy * dv;
+              }
+          if (mode == 3) voronoi_plus_group(nfe, FE, nl, sub, nch, help, hid);
+          else
+            for (int l = 0; l < nl; l++) hid[l] = synopsis(mode, nfe, FE, sub[l], nch, help[l]);
+          for (int l = 0; l < nl; l++) {
+            if (k == 0) ids[l] = hid[l];
+            for (int c = 0; c < nch; c++) res[l][c] += cw * help[l][c];
+          }
         }
-        for (int c = 0; c < nch; c++) px[c] = acc[c];
       }
-      if (index_out) index_out[(size_t)(y - row0) * T.width + x] = idx;
+      for (int l = 0; l < nl; l++) {
+        float* px = out + ((size_t)(y - row0) * T.width + g0 + l) * nch;
+        for (int c = 0; c < nch; c++) px[c] = res[l][c];
+        if (index_out) index_out[(size_t)(y - row0) * T.width + g0 + l] = ids[l];
+      }
     }
+    free(rays); free(r10); free(r01); free(sub);
   }
   free(F);
   return 0;

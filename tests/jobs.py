@@ -31,9 +31,22 @@ def _grey(img):
     return np.ascontiguousarray(img[:, :, 1:2])
 
 
-def _rgba(img):
-    a = np.ones(img.shape[:2] + (1,), dtype=np.float32)
-    return np.ascontiguousarray(np.concatenate([img, a], axis=2))
+def _alpha(h, w, seed):
+    """A smooth alpha plane in [0,1] with fully opaque and fully transparent regions."""
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    r = np.hypot((x - w * (0.45 + 0.1 * seed)) / w, (y - h * 0.5) / h)
+    return np.clip(1.6 - 3.2 * r, 0.0, 1.0).astype(np.float32)
+
+
+def _rgba(img, seed=0):
+    """Associated-alpha RGBA (colour premultiplied), as OIIO hands it over."""
+    a = _alpha(img.shape[0], img.shape[1], seed)[:, :, None]
+    return np.ascontiguousarray(np.concatenate([img * a, a], axis=2).astype(np.float32))
+
+
+def _ga(img, seed=0):
+    a = _alpha(img.shape[0], img.shape[1], seed)[:, :, None]
+    return np.ascontiguousarray(np.concatenate([img[:, :, 1:2] * a, a], axis=2).astype(np.float32))
 
 
 def _ll_facet(w, **kw):
@@ -161,6 +174,26 @@ def _build():
                                    FacetSpec(_rect(96, 64, 80.0, 60.0), "rectilinear", 80.0, yaw=60.0, eev=12.0),
                                    FacetSpec(_rect(96, 64, 80.0, -60.0), "rectilinear", 80.0, yaw=-60.0)],
                                   "spherical", 360.0, 192, 96))
+    # --- alpha path: RGBA / grey+alpha facets, voronoi_syn_plus compositing, channel adaptation ---
+    vf = _voronoi_facets(hfov=95.0, step=55.0)
+    rgba = [FacetSpec(_rgba(f.image, k), f.projection, f.hfov, yaw=f.yaw, pitch=f.pitch, roll=f.roll)
+            for k, f in enumerate(vf)]
+    add("rgba1_rect_d1", Job(rgba[:1], "rectilinear", 90.0, 96, 64, yaw=-100.0))
+    add("rgba1_sph_d3_tw2", Job(rgba[1:2], "spherical", 200.0, 128, 64, yaw=-45.0, degree=3, twine=2))
+    add("rgba4_voronoi_sph_d1", Job(rgba, "spherical", 360.0, 256, 128))
+    add("rgba4_voronoi_sph_d3", Job(rgba, "spherical", 360.0, 200, 100, degree=3, yaw=20.0, roll=5.0))
+    add("rgba4_voronoi_rect_d1_tw2", Job(rgba, "rectilinear", 120.0, 96, 64, twine=2, yaw=-20.0))
+    add("mixed_rgb_rgba_voronoi_sph_d1", Job([vf[0], rgba[1], vf[2], rgba[3]], "spherical", 360.0, 256, 128))
+    add("mixed_grey_rgba_voronoi_sph_d1", Job([FacetSpec(_grey(vf[0].image), "rectilinear", 95.0, yaw=vf[0].yaw),
+                                               rgba[1], FacetSpec(_ga(vf[2].image, 2), "rectilinear", 95.0,
+                                                                  yaw=vf[2].yaw, pitch=vf[2].pitch, roll=vf[2].roll)],
+                                              "spherical", 360.0, 256, 128))
+    add("ga2_voronoi_sph_d1", Job([FacetSpec(_ga(f.image, k), f.projection, f.hfov, yaw=f.yaw, pitch=f.pitch,
+                                             roll=f.roll) for k, f in enumerate(vf[:2])], "spherical", 360.0, 192, 96))
+    add("rgba_cm_sph_d1", Job([FacetSpec(_rgba(_cm(32), 1), "cubemap", 90.0)], "spherical", 360.0, 128, 64))
+    hb = _bracket_facets()
+    add("hdr3_rgba_rect_d1", Job([FacetSpec(_rgba(f.image, 1), f.projection, f.hfov, yaw=f.yaw, eev=f.eev) for f in hb],
+                                 "rectilinear", 70.0, 96, 64, yaw=20.0, synopsis="hdr_merge"))
     tr = _translated_facets()
     add("tr1_sph_d1", Job(tr[:1], "spherical", 360.0, 192, 96))
     add("tr1_rect_d1_tw2", Job(tr[1:2], "rectilinear", 100.0, 96, 64, yaw=30.0, twine=2))
