@@ -116,6 +116,10 @@ class Job:
         if self.twine != 0:
             args += ["--twine_width", repr(float(self.twine_width)), "--twine_sigma", repr(float(self.twine_sigma)),
                      "--twine_threshold", repr(float(self.twine_threshold))]
+            if self.twine_density != 1.0:
+                args += ["--twine_density", repr(float(self.twine_density))]
+            if self.twine_max != 8:
+                args += ["--twine_max", str(self.twine_max)]
         if self.synopsis != "panorama":
             args += ["--synopsis", self.synopsis]
         if self.solo >= 0:

@@ -194,6 +194,13 @@ def _build():
     hb = _bracket_facets()
     add("hdr3_rgba_rect_d1", Job([FacetSpec(_rgba(f.image, 1), f.projection, f.hfov, yaw=f.yaw, eev=f.eev) for f in hb],
                                  "rectilinear", 70.0, 96, 64, yaw=20.0, synopsis="hdr_merge"))
+    # --- automatic twining (--twine omitted = -1): arguments::twine_setup picks the filter from the
+    # magnification (envutil_main.cc:1450-1547) -------------------------------------------------
+    add("auto_tw_down_ll_rect_d1", Job([_ll_facet(256)], "rectilinear", 100.0, 48, 32, twine=-1))          # mag < 1
+    add("auto_tw_up_ll_rect_d1", Job([_ll_facet(128)], "rectilinear", 30.0, 96, 64, twine=-1, yaw=10.0))   # mag > 1, bilinear
+    add("auto_tw_up_ll_rect_d3", Job([_ll_facet(128)], "rectilinear", 30.0, 96, 64, twine=-1, degree=3))   # mag > 1, cubic
+    add("auto_tw_voronoi_d3", Job(_voronoi_facets(n=3), "spherical", 360.0, 512, 256, twine=-1, degree=3))  # several facets
+    add("auto_tw_density_ll_ba6", Job([_ll_facet(256)], "biatan6", 90.0, 24, twine=-1, twine_density=1.5))
     tr = _translated_facets()
     add("tr1_sph_d1", Job(tr[:1], "spherical", 360.0, 192, 96))
     add("tr1_rect_d1_tw2", Job(tr[1:2], "rectilinear", 100.0, 96, 64, yaw=30.0, twine=2))
@@ -207,3 +214,11 @@ def _build():
 JOBS = _build()
 # the subset whose reference outputs are committed under tests/golden/
 GOLDEN_JOBS = sorted(JOBS)
+
+
+# Jobs that need command-line features outside the Job description: name -> (base job, contents of
+# a .twf twining-filter file (x y weight per line, envutil_main.cc:1360-1403), extra arguments)
+CLI_EXTRAS = {
+    "twf_ll_rect_d1": ("ll_rect_d1_rot", "-0.3 -0.2 1\n0.3 -0.2 2\n0.0 0.35 3\n0.1 0.0 1.5\n", ["--twine_normalize"]),
+    "twf_raw_voronoi_d1": ("voronoi4_sph_d1", "-0.25 0 0.5\n0.25 0 0.5\n", ["--twine_width", "1.5"]),
+}

@@ -131,7 +131,9 @@ def test_pto_back_references(cli, tmp_path):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["ll_rect_d1_oddangles", "cm_sph_d3_rot", "ll_fish_d1_tw4", "hdr3_sph_d3_tw2",
                                   "lens3_voronoi_sph_d1", "eev_voronoi_sph_d1", "ll_ba6_d1_tw2", "voronoi4_solo2",
-                                  "grey_cm_sph_d1_tw2", "ll_cyl_d1_tw2"])
+                                  "grey_cm_sph_d1_tw2", "ll_cyl_d1_tw2", "tr3_voronoi_fish_d3_tw2",
+                                  "mixed_grey_rgba_voronoi_sph_d1", "rgba4_voronoi_sph_d3", "hdr3_rgba_rect_d1",
+                                  "auto_tw_voronoi_d3", "auto_tw_up_ll_rect_d1", "auto_tw_density_ll_ba6"])
 def test_cli_output_equals_reference_output(cli, tmp_path, name):
     """The drop-in claim end to end: the SAME command line given to the reference binary and to
     envutil_b200_cli produces the same file, bit for bit (golden sha256 of the reference run)."""
@@ -145,6 +147,25 @@ def test_cli_output_equals_reference_output(cli, tmp_path, name):
     img = euf.read_euf(outp)
     man = json.load(open(os.path.join(harness.GOLDEN, "manifest.json")))[name]
     assert list(img.shape) == man["shape"]
+    assert hashlib.sha256(np.ascontiguousarray(img, dtype="<f4").tobytes()).hexdigest() == man["sha256"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(jobs.CLI_EXTRAS))
+def test_cli_twf_filter_equals_reference(cli, tmp_path, name):
+    """--twf_file / --twine_normalize / --twine_width scaling: same command line, same bits."""
+    import hashlib
+    import json
+    base, twf, extra = jobs.CLI_EXTRAS[name]
+    job = jobs.JOBS[base]
+    paths = _write_facets(job, str(tmp_path))
+    tp = tmp_path / "filter.twf"
+    tp.write_text(twf)
+    outp = str(tmp_path / "out.euf")
+    r = subprocess.run([cli] + job.cli_args(paths, outp) + ["--twf_file", str(tp)] + extra, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    img = euf.read_euf(outp)
+    man = json.load(open(os.path.join(harness.GOLDEN, "manifest.json")))[name]
     assert hashlib.sha256(np.ascontiguousarray(img, dtype="<f4").tobytes()).hexdigest() == man["sha256"]
 
 
