@@ -50,7 +50,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only wit
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=int, default=1, help="shrink the workload (tests only; invalid as a bench)")
@@ -73,7 +73,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._pump, daemon=True)
             self.th.start()
@@ -85,7 +85,13 @@ class ClockSampler:
             self.rows.append((time.perf_counter(), line.strip()))
 
     def window(self, t0, t1):
-        return [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
+        """Samples taken inside [t0, t1]; if the region was shorter than one sampling period, the
+        samples nearest to it (within 150 ms)."""
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1]
+        if inside:
+            return inside
+        near = sorted(self.rows, key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t1)))[:3]
+        return [r for (t, r) in near if min(abs(t - t0), abs(t - t1)) < 0.15]
 
     def stop(self):
         if self.proc:
@@ -124,6 +130,20 @@ def measured_peak():
         except (KeyError, ValueError):
             pass
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the render kernel, from the
+    newest ncu --set full capture summarised under profiles/ (tools/summarise_profile.py)."""
+    pd = os.path.join(ROOT, "profiles")
+    best = None
+    for f in sorted(os.listdir(pd)) if os.path.isdir(pd) else []:
+        if f.endswith("_traffic.json"):
+            try:
+                best = json.load(open(os.path.join(pd, f)))
+            except ValueError:
+                pass
+    return best
 
 
 def workload(scale):
@@ -282,6 +302,8 @@ def ours(args):
     mpix = W * H / 1e6
     stream = torch.cuda.current_stream().cuda_stream
     hs = eng.stage_device(job, [d_src.data_ptr()], st, stream=stream, padded=bool(args.padded))
+    eng.release(hs)  # the first staging grows the device pool; report the steady state
+    hs = eng.stage_device(job, [d_src.data_ptr()], st, stream=stream, padded=bool(args.padded))
     stage_ms = eng.last_stage_timing[0].render_ms
     stage_launches = eng.last_stage_timing[0].launches
     d_out = torch.empty((H, W, C), dtype=torch.float32, device=dev)
@@ -351,6 +373,7 @@ def ours(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = alg / (ms_per_step * 1e-3) / 1e9
+        tr = measured_traffic() if (args.scale == 1 and not args.padded and not args.no_tiles) else None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             with tempfile.TemporaryDirectory(prefix="eubench_",
@@ -372,7 +395,8 @@ def ours(args):
                        "gather": "direct (L1)" if args.no_tiles else "footprint staged in shared memory by cp.async.bulk",
                        "parity": "bit-exact vs pinned-math reference build (tests/)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "traffic": tr["traffic_bytes"] if tr else None,
+                         "traffic_source": tr["source"] if tr else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "kernel": "k_render<3,...>" if args.no_tiles else "k_render_tiled<3,...>", "frac_of_8TBs_spec": achieved / 8000.0},
             "e2e": {"value": world * mpix / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h_src.numel() * 4), "d2h_bytes_per_step": int(h_out.numel() * 4),

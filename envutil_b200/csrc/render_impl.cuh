@@ -539,10 +539,13 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
 template <int NCH, int TS, int MODE, bool TWINE>
 static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st) {
   if constexpr (MODE == EU_MODE_SINGLE) {
-    // footprint-staged kernel: needs 16-byte row granules and a pixel output (no index plane)
-    if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.any_generic) {
-      if (P.degree == 1) { k_render_tiled<NCH, TS, TWINE, 1><<<grid, block, 0, st>>>(P); return; }
-      if (P.degree == 3) { k_render_tiled<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P); return; }
+    // footprint-staged kernel: needs 16-byte row granules and a pixel output (no index plane).
+    // Measured on B200 (profiles/): it wins for the cubic window (16 taps/px: C2 0.60 vs 0.75 ms)
+    // and loses for the bilinear one (4 taps/px: C3b 1.56 vs 1.32 ms), where the two block-wide
+    // synchronisations cost more than the gathers they replace - so it is used for degree 3 only.
+    if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.any_generic && P.degree == 3) {
+      k_render_tiled<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P);
+      return;
     }
   }
   if (P.any_generic) {  // translation: the generic-stepper build (run-time degree, facets in global memory)

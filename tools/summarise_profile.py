@@ -73,6 +73,17 @@ def main():
                 for i, h in enumerate(hdr):
                     if h in KEYS:
                         f.write("  %-62s %-14s %s\n" % (h, units[i], vals[i]))
+        import json
+        kr = [v for v in rows[2:] if "k_render" in v[hdr.index("Kernel Name")]]
+        if kr:
+            v = kr[-1]
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd = float(v[hdr.index("dram__bytes_read.sum")]) * unit[units[hdr.index("dram__bytes_read.sum")]]
+            wr = float(v[hdr.index("dram__bytes_write.sum")]) * unit[units[hdr.index("dram__bytes_write.sum")]]
+            json.dump({"traffic_bytes": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
+                       "kernel": v[hdr.index("Kernel Name")].split("(")[0],
+                       "source": "profiles/%s_k_render_metrics.txt (ncu --set full, one launch)" % tag},
+                      open(os.path.join(pd, "%s_traffic.json" % tag), "w"))
     print("profiles written for", tag)
 
 
