@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--scale", type=int, default=1, help="shrink the workload (tests only; invalid as a bench)")
     ap.add_argument("--padded", type=int, default=0, help="1: 16-byte RGB texels in HBM")
     ap.add_argument("--no-tiles", type=int, default=0, help="1: direct-gather kernel (no shared-memory staging)")
+    ap.add_argument("--partition", default="frames", choices=["frames", "bands"],
+                    help="N > 1: frames = one full frame per rank per step (weak scaling, default); bands = the ranks "
+                         "split ONE frame into row bands, gathered on rank 0 over NCCL (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: min(steps, 5))")
     return ap.parse_args()
@@ -293,7 +296,9 @@ def ours(args):
     h_src = torch.empty(shape, dtype=torch.float32).pin_memory()
     h_src.copy_(d_src)
     torch.cuda.synchronize()
-    job.yaw = 360.0 * rank / world  # every rank renders its own view of the same environment
+    bands_mode = args.partition == "bands" and world > 1
+    if not bands_mode:
+        job.yaw = 360.0 * rank / world  # every rank renders its own view of the same environment
     job.padded, job.no_tiles = bool(args.padded), bool(args.no_tiles)
     eng = Engine(local)
     st = job.structs(eng.lib)
@@ -306,12 +311,14 @@ def ours(args):
     hs = eng.stage_device(job, [d_src.data_ptr()], st, stream=stream, padded=bool(args.padded))
     stage_ms = eng.last_stage_timing[0].render_ms
     stage_launches = eng.last_stage_timing[0].launches
-    d_out = torch.empty((H, W, C), dtype=torch.float32, device=dev)
+    from envutil_b200 import bands as eu_bands
+    row0, row1 = eu_bands.band(H, world, rank) if bands_mode else (0, H)
+    d_out = torch.empty((row1 - row0, W, C), dtype=torch.float32, device=dev)
     setup_s = time.perf_counter() - t_setup
 
     # ---- device-timed render: W warm-up launches, then exactly K, events on the launch stream
     for _ in range(max(args.warmup, 3)):
-        eng.render_rows(job, hs, st, 0, H, d_out.data_ptr(), stream, timed=False)
+        eng.render_rows(job, hs, st, row0, row1, d_out.data_ptr(), stream, timed=False)
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     time.sleep(0.25 if sampler else 0.0)
@@ -321,7 +328,7 @@ def ours(args):
     tw0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        eng.render_rows(job, hs, st, 0, H, d_out.data_ptr(), stream, timed=False)
+        eng.render_rows(job, hs, st, row0, row1, d_out.data_ptr(), stream, timed=False)
     ev1.record()
     barrier()
     tw1 = time.perf_counter()
@@ -336,9 +343,26 @@ def ours(args):
         time.sleep(0.15)
         clocks = ClockSampler.summarise(sampler.window(tw0, tw1))
     checksum = float(d_out[::64, ::64].double().sum().item())
+    gather_ms = 0.0
+    if bands_mode:  # output bands gathered on rank 0 (NCCL), timed on its own: not part of `value`
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = eu_bands.gather_bands(d_out, H, world, rank, dist)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+        if rank == 0:
+            assert tuple(full.shape) == (H, W, C)
+            checksum = float(full[::64, ::64].double().sum().item())
+        del full
 
     # ---- e2e: host buffers through the C ABI, H2D + staging + render + D2H every step ----
     e2e_steps = args.e2e_steps or max(1, min(args.steps, 5))
+    if bands_mode:  # the e2e leg renders full frames through eu_render; compare against a full device frame
+        d_out = torch.empty((H, W, C), dtype=torch.float32, device=dev)
+        eng.render_rows(job, hs, st, 0, H, d_out.data_ptr(), stream, timed=False)
+        torch.cuda.synchronize()
     h_out = torch.empty((H, W, C), dtype=torch.float32).pin_memory()
     import ctypes as Ct
     from envutil_b200 import capi
@@ -372,8 +396,9 @@ def ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = alg / (ms_per_step * 1e-3) / 1e9
-        tr = measured_traffic() if (args.scale == 1 and not args.padded and not args.no_tiles) else None
+        tr = measured_traffic() if (args.scale == 1 and not args.padded and not args.no_tiles and not bands_mode) else None
+        alg_launch = alg // world if bands_mode else alg  # a band touches its share of output and source
+        achieved = alg_launch / (ms_per_step * 1e-3) / 1e9  # per launch = per GPU
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             with tempfile.TemporaryDirectory(prefix="eubench_",
@@ -386,17 +411,20 @@ def ours(args):
                     cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                            "sample": "failed: %s" % str(e)[:200]}
         line = {
-            "metric": METRIC, "value": world * mpix / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": (1 if bands_mode else world) * mpix / (ms_per_step * 1e-3), "unit": UNIT,
+            "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "frames_per_step": world, "out_mpix_per_frame": mpix,
+            "higher_is_better": True, "scaling": "strong" if bands_mode else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": name, "frames_per_step": 1 if bands_mode else world,
+                       "partition": "row bands of one frame, gathered on rank 0" if bands_mode else "one frame per rank", "out_mpix_per_frame": mpix,
                        "l2": "inputs_larger_than_l2 (321 MB source IR + 403 MB output per frame vs 126 MB L2)",
                        "texel_layout": "float4-padded" if args.padded else "interleaved-rgb",
                        "gather": "direct (L1)" if args.no_tiles else "footprint staged in shared memory by cp.async.bulk",
                        "parity": "bit-exact vs pinned-math reference build (tests/)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": tr["traffic_bytes"] if tr else None,
-                         "traffic_source": tr["source"] if tr else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "traffic_source": tr["source"] if tr else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_launch,
                          "kernel": "k_render<3,...>" if args.no_tiles else "k_render_tiled<3,...>", "frac_of_8TBs_spec": achieved / 8000.0},
             "e2e": {"value": world * mpix / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h_src.numel() * 4), "d2h_bytes_per_step": int(h_out.numel() * 4),
@@ -411,7 +439,7 @@ def ours(args):
             "clocks": clocks,
             "staging": {"ms": stage_ms, "launches": stage_launches,
                         "what": "cubemap IR build + support fill + per-section prefilter (device-timed, outside value)"},
-            "multi_gpu": {"broadcast_ms": bcast_ms, "collectives_in_timed_region": 0},
+            "multi_gpu": {"broadcast_ms": bcast_ms, "gather_ms": gather_ms, "collectives_in_timed_region": 0},
             "cpu_baseline": cpu, "checksum": checksum, "setup_s": setup_s,
         }
         print(json.dumps(line))
