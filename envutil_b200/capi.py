@@ -63,6 +63,12 @@ class Timing(C.Structure):
                 ("launches", C.c_int32), ("reserved", C.c_int32)]
 
 
+class AlphaSpec(C.Structure):
+    _fields_ = [("native_nchannels", C.c_int32), ("has_crop", C.c_int32), ("crop_x0", C.c_int32),
+                ("crop_x1", C.c_int32), ("crop_y0", C.c_int32), ("crop_y1", C.c_int32), ("n_masks", C.c_int32),
+                ("mask_sizes", C.POINTER(C.c_int32)), ("mask_xy", C.POINTER(C.c_float))]
+
+
 SourceH = C.c_void_p
 _FP = C.POINTER(C.c_float)
 
@@ -87,6 +93,8 @@ SYMBOLS = {
                                    C.POINTER(SourceH), C.POINTER(Timing)]),
     "eu_source_upload_device": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p, C.c_void_p,
                                           C.POINTER(SourceH), C.POINTER(Timing)]),
+    "eu_source_upload_alpha": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p,
+                                         C.POINTER(AlphaSpec), C.POINTER(SourceH), C.POINTER(Timing)]),
     "eu_source_find": (SourceH, [C.c_char_p]),
     "eu_source_release": (C.c_int, [SourceH]),
     "eu_cycle": (C.c_int, []),

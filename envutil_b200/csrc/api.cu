@@ -662,6 +662,51 @@ int eu_source_upload(const char* asset_key, const eu_facet_t* f, const eu_opts_t
   return upload_common(asset_key, f, o, pixels, cudaMemcpyHostToDevice, nullptr, out, t);
 }
 
+int eu_source_upload_alpha(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
+                           const eu_alpha_spec_t* a, eu_source_h* out, eu_timing_t* t) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!f || !o || !pixels || !a || !out) return fail(EU_ERR_ARGUMENT, "null argument");
+  const int nat = a->native_nchannels, C = f->nchannels;
+  if (nat < 1 || nat > 4 || !(C == nat || (C == nat + 1 && (nat == 1 || nat == 3))) || (C != 2 && C != 4))
+    return fail(EU_ERR_ARGUMENT, "masked facets carry alpha: %d native channels cannot become %d", nat, C);
+  if (f->projection == EU_CUBEMAP || f->projection == EU_BIATAN6)
+    return fail(EU_ERR_ARGUMENT, "masks and lens crop apply to single images, not to cubemaps");
+  if (a->n_masks < 0 || (a->n_masks > 0 && (!a->mask_sizes || !a->mask_xy))) return fail(EU_ERR_ARGUMENT, "bad mask list");
+  if (f->width <= 0 || f->height <= 0) return fail(EU_ERR_ARGUMENT, "bad raster description");
+  const int w = f->width, h = f->height;
+  const size_t n = (size_t)w * h;
+  std::vector<unsigned char> plane(n);
+  eu_build_alpha_mask(f, a, plane.data());  // host: polygons and crop are a few scan lines each
+  unsigned char* d_mask = nullptr;
+  float *d_raw = nullptr, *d_a = nullptr, *d_b = nullptr, *d_px = nullptr;
+  cudaStream_t st = g.stream;
+  CK(cudaMallocAsync((void**)&d_mask, n, st));
+  CK(pool_alloc(&d_raw, n * nat));
+  CK(pool_alloc(&d_a, n));
+  CK(pool_alloc(&d_b, n));
+  CK(pool_alloc(&d_px, n * C));
+  CK(cudaEventRecord(g.ev[2], st));
+  CK(cudaMemcpyAsync(d_mask, plane.data(), n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_raw, pixels, n * nat * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(g.ev[3], st));
+  CK(eu_launch_alpha_apply(d_mask, d_a, d_b, d_raw, nat, d_px, C, w, h, st));
+  CK(cudaStreamSynchronize(st));  // plane goes out of scope; ev[2]/ev[3] are reused by the staging below
+  float h2d = 0;
+  CK(cudaEventElapsedTime(&h2d, g.ev[2], g.ev[3]));
+  rc = upload_common(asset_key, f, o, d_px, cudaMemcpyDeviceToDevice, st, out, t);
+  cudaFreeAsync(d_mask, st);
+  pool_free(d_raw);
+  pool_free(d_a);
+  pool_free(d_b);
+  pool_free(d_px);
+  if (rc == EU_OK && t) {
+    t->h2d_ms = h2d;
+    t->launches += 3;
+  }
+  return rc;
+}
+
 eu_source_h eu_source_find(const char* asset_key) {
   if (!g.up || !asset_key) return nullptr;
   auto it = g.by_key.find(asset_key);

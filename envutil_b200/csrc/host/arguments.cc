@@ -3,7 +3,9 @@
 // Eev -> brighten (:1006-1061), channel-count rule (:1063-1154), target set-up (:1171-1232).
 // Arithmetic follows the reference's types: command-line angles and hfov are parsed as FLOAT
 // (ap[...].get<float>) and converted to radians in double; PTO values are parsed as double.
+#include <cctype>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -187,15 +189,11 @@ int arguments::init(int argc, const char** argv) {
       }
     }
     for (const auto& ln : lines) {
-      if (ln.head == 'k') {
-        error = "k-lines (exclude masks) need the alpha path, which is not built";
-        return EU_ERR_UNSUPPORTED;
-      }
       if (ln.head != 'i') continue;
       facet_spec fs;
       fs.facet_no = nfacets++;
-      if (!ln.get("Pano").empty() || !ln.get("W").empty() || !ln.get("S").empty()) {
-        error = "i-line Pano / W / S clauses (unstitching, cropped input, lens crop) are outside the built path";
+      if (!ln.get("Pano").empty() || !ln.get("W").empty()) {
+        error = "i-line Pano / W clauses (unstitching, cropped input) are outside the built path";
         return EU_ERR_UNSUPPORTED;
       }
       fs.filename = ln.get("n");
@@ -247,7 +245,60 @@ int arguments::init(int argc, const char** argv) {
         eev_sum += fs.brighten;
         eev_count++;
       }
+      fs.native_nchannels = c;
+      {  // lens crop "S x0,x1,y0,y1" (envutil_main.cc:811-822)
+        const std::string& crop = ln.get("S");
+        if (!crop.empty()) {
+          int v[4];
+          if (sscanf(crop.c_str(), "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) != 4) {
+            error = "bad S clause '" + crop + "'";
+            return EU_ERR_ARGUMENT;
+          }
+          fs.has_lens_crop = true;
+          fs.crop_x0 = v[0]; fs.crop_x1 = v[1]; fs.crop_y0 = v[2]; fs.crop_y1 = v[3];
+        }
+      }
       facet_spec_v.push_back(fs);
+    }
+    // k-lines: exclude masks "k iN t0 p"x y x y ..."" (envutil_main.cc:826-904)
+    int mask_no = 0;
+    for (const auto& ln : lines) {
+      if (ln.head != 'k') continue;
+      int image = iglean(ln.get("i")), variant = iglean(ln.get("t"));
+      if (image < 0 || image >= (int)facet_spec_v.size()) {
+        error = "k-line refers to image " + std::to_string(image);
+        return EU_ERR_ARGUMENT;
+      }
+      facet_spec& fct = facet_spec_v[image];
+      fct.has_pto_mask = true;
+      std::vector<float> xy;
+      {  // pairs "number<one blank>number", scanned left to right without overlap
+        const std::string& vl = ln.get("p");
+        const char* p = vl.c_str();
+        auto is_num = [](char ch) { return (ch >= '0' && ch <= '9') || ch == '.' || ch == '+' || ch == '-'; };
+        while (*p) {
+          while (*p && !is_num(*p)) p++;
+          if (!*p) break;
+          char* e1;
+          double x = strtod(p, &e1);
+          if (e1 == p) { p++; continue; }
+          if (!isspace((unsigned char)*e1) || !is_num(e1[1])) { p = e1; continue; }
+          char* e2;
+          double y = strtod(e1 + 1, &e2);
+          if (e2 == e1 + 1) { p = e1; continue; }
+          xy.push_back((float)x);
+          xy.push_back((float)y);
+          p = e2;
+        }
+      }
+      if (variant != 0) {
+        fprintf(stderr, "warning: mask type not implemented: %d this mask will be ignored\n", variant);
+      } else {
+        fct.mask_xy.push_back(xy);
+      }
+      if (fct.filename == fct.asset_key) fct.asset_key += "." + pto_file + ".";
+      else fct.asset_key += ".";
+      fct.asset_key += std::to_string(mask_no++);
     }
   }
 
@@ -326,6 +377,10 @@ int arguments::init(int argc, const char** argv) {
     }
     if (brighten != 1.0) m.brighten *= brighten;
     m.f.brighten = m.brighten;
+    if (m.native_nchannels == 0) m.native_nchannels = m.f.nchannels;
+    if (m.has_pto_mask || m.has_lens_crop) {  // masks and crops act through alpha (envutil_main.cc:1065-1069)
+      if (m.f.nchannels == 1 || m.f.nchannels == 3) m.f.nchannels++;
+    }
     if (m.f.nchannels == 2 || m.f.nchannels == 4) alpha_seen = true;
     if (m.f.nchannels > nchannels) nchannels = m.f.nchannels;
   }

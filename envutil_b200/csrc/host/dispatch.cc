@@ -45,12 +45,30 @@ struct cuda_dispatch : public dispatch_base {
       if (!h) {
         int w, hh, c;
         std::vector<float> px;
-        if (!read_raster(fs.filename, w, hh, c, px) || w != fs.f.width || hh != fs.f.height || c != fs.f.nchannels) {
+        if (!read_raster(fs.filename, w, hh, c, px) || w != fs.f.width || hh != fs.f.height ||
+            c != fs.native_nchannels) {
           fprintf(stderr, "envutil_b200: cannot read facet image '%s'\n", fs.filename.c_str());
           return EU_ERR_ARGUMENT;
         }
         eu_timing_t tm{};
-        rc = eu_source_upload(key.c_str(), &fv.back(), &o, px.data(), &h, &tm);
+        if (fs.has_pto_mask || fs.has_lens_crop) {
+          std::vector<int32_t> sizes;
+          std::vector<float> xy;
+          for (const auto& m : fs.mask_xy) {
+            sizes.push_back((int32_t)(m.size() / 2));
+            xy.insert(xy.end(), m.begin(), m.end());
+          }
+          eu_alpha_spec_t as{};
+          as.native_nchannels = fs.native_nchannels;
+          as.has_crop = fs.has_lens_crop ? 1 : 0;
+          as.crop_x0 = fs.crop_x0; as.crop_x1 = fs.crop_x1; as.crop_y0 = fs.crop_y0; as.crop_y1 = fs.crop_y1;
+          as.n_masks = (int32_t)sizes.size();
+          as.mask_sizes = sizes.data();
+          as.mask_xy = xy.data();
+          rc = eu_source_upload_alpha(key.c_str(), &fv.back(), &o, px.data(), &as, &h, &tm);
+        } else {
+          rc = eu_source_upload(key.c_str(), &fv.back(), &o, px.data(), &h, &tm);
+        }
         if (rc) {
           fprintf(stderr, "envutil_b200: %s\n", eu_last_error());
           return rc;

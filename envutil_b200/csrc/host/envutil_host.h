@@ -26,6 +26,9 @@ struct facet_spec {
   std::string filename, asset_key, projection_str;
   float brighten = 0.0f;  // Eev while parsing, linear gain after init (envutil_main.cc:1030-1061)
   bool has_lens_crop = false, has_pto_mask = false;
+  int crop_x0 = 0, crop_x1 = 0, crop_y0 = 0, crop_y1 = 0;  // i-line S clause
+  std::vector<std::vector<float>> mask_xy;                  // k-lines t0: x y x y ... per polygon
+  int native_nchannels = 0;                                 // channels of the file (f.nchannels may be +1)
 };
 
 struct arguments {

@@ -355,3 +355,84 @@ int eu_compute_cubemap_metrics(int face_px, double face_fov, int support_min, in
   m->refc_md = m->px_to_model * refc_px;
   return EU_OK;
 }
+
+// fill_polygon, envutil_basic.cc:236-321: scan-line fill with the non-zero winding rule; node x
+// positions are truncated to int exactly as there
+static void fill_polygon_clear(const float* px, const float* py, int N, int w, int h, unsigned char* plane) {
+  std::vector<int> nodeX(N + 1), dir(N + 1);
+  for (int pixelY = 0; pixelY < h; pixelY++) {
+    int nodes = 0, j = N - 1;
+    for (int i = 0; i < N; i++) {
+      int cross = 0;
+      if (py[i] < (float)pixelY && py[j] >= (float)pixelY) cross = 1;
+      else if (py[j] < (float)pixelY && py[i] >= (float)pixelY) cross = -1;
+      if (cross) {
+        nodeX[nodes] = (int)(px[i] + (pixelY - py[i]) / (py[j] - py[i]) * (px[j] - px[i]));
+        dir[nodes++] = cross;
+      }
+      j = i;
+    }
+    int i = 0;
+    while (i < nodes - 1) {
+      if (nodeX[i] > nodeX[i + 1]) {
+        std::swap(nodeX[i], nodeX[i + 1]);
+        std::swap(dir[i], dir[i + 1]);
+        if (i) i--;
+      } else {
+        i++;
+      }
+    }
+    int w_ord = 0;
+    for (i = 0; i < nodes; i++) {
+      w_ord += dir[i];
+      if (!w_ord) continue;
+      if (i + 1 >= nodes) break;
+      if (nodeX[i] >= w) break;
+      if (nodeX[i + 1] > 0) {
+        if (nodeX[i] < 0) nodeX[i] = 0;
+        if (nodeX[i + 1] > w) nodeX[i + 1] = w;
+        for (int x = nodeX[i]; x < nodeX[i + 1]; x++) plane[(size_t)pixelY * w + x] = 0;
+      }
+    }
+  }
+}
+
+void eu_build_alpha_mask(const eu_facet_t* f, const eu_alpha_spec_t* a, unsigned char* plane) {
+  const int w = f->width, h = f->height;
+  memset(plane, 1, (size_t)w * h);
+  const float* xy = a->mask_xy;
+  for (int m = 0; m < a->n_masks; m++) {
+    int n = a->mask_sizes[m];
+    std::vector<float> vx(n), vy(n);
+    for (int k = 0; k < n; k++) {
+      vx[k] = xy[2 * k];
+      vy[k] = xy[2 * k + 1];
+    }
+    if (n >= 3) fill_polygon_clear(vx.data(), vy.data(), n, w, h, plane);
+    xy += 2 * n;
+  }
+  if (a->has_crop) {
+    float ca = (float)(fabs((double)(a->crop_x1 - a->crop_x0)) / 2.0);
+    float cb = (float)(fabs((double)(a->crop_y1 - a->crop_y0)) / 2.0);
+    if (f->projection == EU_FISHEYE) {  // elliptic crop, environment.h:746-772
+      float mx = (float)((a->crop_x0 + a->crop_x1) / 2.0);
+      float my = (float)((a->crop_y0 + a->crop_y1) / 2.0);
+      for (int y = 0; y < h; y++) {
+        float dy = fabsf((float)y - my);
+        if (dy > cb) {
+          memset(plane + (size_t)y * w, 0, w);
+          continue;
+        }
+        float xmargin = (float)sqrt((double)(ca * ca) * (1.0 - (double)((dy * dy) / (cb * cb))));
+        for (int x = 0; x < w; x++) {
+          float dx = fabsf((float)x - mx);
+          if (dx > xmargin) plane[(size_t)y * w + x] = 0;
+        }
+      }
+    } else {  // rectangular crop, environment.h:773-790
+      for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+          if (x < a->crop_x0 || x >= a->crop_x1 || y < a->crop_y0 || y >= a->crop_y1) plane[(size_t)y * w + x] = 0;
+    }
+  }
+}

@@ -360,6 +360,48 @@ __global__ void k_pad_texels(const float* __restrict__ src, int src_pitch, float
   dst[(size_t)y * cw + x] = make_float4(s[0], nch > 1 ? s[1] : 0.f, nch > 2 ? s[2] : 0.f, 0.f);
 }
 
+// ---- alpha of masked / cropped facets (environment.h:703-890) -----------------------------
+// 5-tap binomial (1 4 6 4 1)/16, REFLECT extrapolation (zimt/extrapolate.h:141-153). On 0/1 data
+// the x pass yields multiples of 1/16, the y pass multiples of 1/256: all partial sums are exact,
+// so the summation order of the reference's circular-buffer FIR (zimt/convolve.h) is immaterial.
+__device__ __forceinline__ int dev_reflect(int i, int w) {
+  if (i < 0) i = -1 - i;
+  if (i >= w) {
+    i %= 2 * w;
+    if (i >= w) i = 2 * w - i - 1;
+  }
+  return i;
+}
+__global__ void k_alpha_feather_x(const unsigned char* __restrict__ in, float* __restrict__ out, int w, int h) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const float k5[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
+  float s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 5; j++) s += k5[j] * (float)in[(size_t)y * w + dev_reflect(x - 2 + j, w)];
+  out[(size_t)y * w + x] = s;
+}
+__global__ void k_alpha_feather_y(const float* __restrict__ in, float* __restrict__ out, int w, int h) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w) return;
+  const float k5[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
+  float s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 5; j++) s += k5[j] * in[(size_t)dev_reflect(y - 2 + j, h) * w + x];
+  out[(size_t)y * w + x] = s;
+}
+// raster of native_nch channels -> nch channels (an added alpha channel is 1), times alpha
+__global__ void k_alpha_apply(const float* __restrict__ raw, int native_nch, const float* __restrict__ alpha,
+                              float* __restrict__ out, int nch, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = alpha[i];
+  for (int c = 0; c < nch; c++) {
+    float v = c < native_nch ? raw[i * native_nch + c] : 1.0f;
+    out[i * nch + c] = v * a;
+  }
+}
+
 // ---- launchers -----------------------------------------------------------------------------
 cudaError_t eu_launch_iir_x(float* core, int stride, int nch, int w, int h, const IirDev& f, cudaStream_t st) {
   int nb = (h + IIR_R - 1) / IIR_R;
@@ -437,5 +479,15 @@ cudaError_t eu_launch_cubemap_support(float* ir, int pitch, int nch, int F, int 
 cudaError_t eu_launch_pad_texels(const float* src, int src_pitch, float* dst, int cw, int chh, int nch, cudaStream_t st) {
   dim3 grid((cw + 255) / 256, chh);
   k_pad_texels<<<grid, 256, 0, st>>>(src, src_pitch, reinterpret_cast<float4*>(dst), cw, chh, nch);
+  return cudaGetLastError();
+}
+
+cudaError_t eu_launch_alpha_apply(const unsigned char* mask, float* tmp_a, float* tmp_b, const float* raw, int native_nch,
+                                  float* out, int nch, int w, int h, cudaStream_t st) {
+  dim3 grid((w + 255) / 256, h);
+  k_alpha_feather_x<<<grid, 256, 0, st>>>(mask, tmp_a, w, h);
+  k_alpha_feather_y<<<grid, 256, 0, st>>>(tmp_a, tmp_b, w, h);
+  size_t n = (size_t)w * h;
+  k_alpha_apply<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(raw, native_nch, tmp_b, out, nch, n);
   return cudaGetLastError();
 }

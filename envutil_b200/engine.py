@@ -33,8 +33,13 @@ class Engine:
             tm = capi.Timing()
             key = keys[i].encode() if keys else None
             h = capi.SourceH()
-            capi.check(self.lib.eu_source_upload(key, C.byref(fa[i]), C.byref(o), img.ctypes.data, C.byref(h),
-                                                 C.byref(tm)), self.lib)
+            if f.has_alpha_spec():  # PTO exclude masks / lens crop
+                a = f.alpha_spec()
+                capi.check(self.lib.eu_source_upload_alpha(key, C.byref(fa[i]), C.byref(o), img.ctypes.data,
+                                                           C.byref(a), C.byref(h), C.byref(tm)), self.lib)
+            else:
+                capi.check(self.lib.eu_source_upload(key, C.byref(fa[i]), C.byref(o), img.ctypes.data, C.byref(h),
+                                                     C.byref(tm)), self.lib)
             hs[i] = h
             self.last_stage_timing.append(tm)
             self.launches += tm.launches

@@ -38,16 +38,44 @@ class FacetSpec:
     tr_z: float = 0.0
     tp_y: float = 0.0
     tp_p: float = 0.0
+    crop: Optional[tuple] = None   # PTO i-line S clause: (x0, x1, y0, y1) lens crop -> alpha (needs the PTO route)
+    masks: tuple = ()              # PTO k-lines, variant t0: polygons ((x, y), ...) excluded -> alpha
     width: int = 0   # used when image is None
     height: int = 0
     nchannels: int = 3
 
-    def shape(self):
+    def native_shape(self):
         if self.image is not None:
             h, w = self.image.shape[:2]
             c = 1 if self.image.ndim == 2 else self.image.shape[2]
             return w, h, c
         return self.width, self.height, self.nchannels
+
+    def has_alpha_spec(self):
+        return self.crop is not None or len(self.masks) > 0
+
+    def shape(self):
+        """Shape of the STAGED facet: masks / lens crop add an alpha channel to 1- and 3-channel
+        images (envutil_main.cc:1065-1069)."""
+        w, h, c = self.native_shape()
+        if self.has_alpha_spec() and c in (1, 3):
+            c += 1
+        return w, h, c
+
+    def alpha_spec(self):
+        """ctypes AlphaSpec for the C ABI / the oracle (keeps the arrays alive on the object)."""
+        a = capi.AlphaSpec()
+        a.native_nchannels = self.native_shape()[2]
+        if self.crop is not None:
+            a.has_crop = 1
+            a.crop_x0, a.crop_x1, a.crop_y0, a.crop_y1 = (int(v) for v in self.crop)
+        a.n_masks = len(self.masks)
+        sizes = (C.c_int32 * max(1, len(self.masks)))(*[len(m) for m in self.masks])
+        flat = [float(np.float32(v)) for m in self.masks for xy in m for v in xy]
+        xy = (C.c_float * max(1, len(flat)))(*flat)
+        a.mask_sizes, a.mask_xy = sizes, xy
+        a._keep = (sizes, xy)
+        return a
 
 
 @dataclass
@@ -79,7 +107,7 @@ class Job:
     # ---- reference command line (real spellings, envutil_main.cc:190-372) ----
     def uses_pto(self):
         return any(f.eev or f.a or f.b or f.c or f.d or f.e or f.g or f.t or f.tr_x or f.tr_y or f.tr_z
-                   for f in self.facets)
+                   or f.has_alpha_spec() for f in self.facets)
 
     _PTO_CODE = {"rectilinear": 0, "cylindrical": 1, "fisheye": 3, "spherical": 4, "stereographic": 10}
 
@@ -87,7 +115,7 @@ class Job:
         """i-lines for the facets (PTO subset, reference envutil_main.cc:655-822)."""
         lines = []
         for f, p in zip(self.facets, facet_paths):
-            w, h, _ = f.shape()
+            w, h, _ = f.native_shape()
             ln = (f'i w{w} h{h} f{self._PTO_CODE[f.projection]} v{float(f.hfov)!r} y{float(f.yaw)!r} '
                   f'p{float(f.pitch)!r} r{float(f.roll)!r}')
             for key, val in (("Eev", f.eev), ("a", f.a), ("b", f.b), ("c", f.c), ("d", f.d), ("e", f.e), ("g", f.g),
@@ -95,8 +123,14 @@ class Job:
                              ("Tpp", f.tp_p)):
                 if val:
                     ln += f" {key}{float(val)!r}"
+            if f.crop is not None:
+                ln += " S%d,%d,%d,%d" % tuple(int(v) for v in f.crop)
             ln += f' n"{p}"'
             lines.append(ln)
+        for i, f in enumerate(self.facets):
+            for m in f.masks:  # k-lines: exclude masks (envutil_main.cc:829-904)
+                pts = " ".join("%s %s" % (repr(float(x)), repr(float(y))) for x, y in m)
+                lines.append(f'k i{i} t0 p"{pts}"')
         return lines
 
     def cli_args(self, facet_paths, output):

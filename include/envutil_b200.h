@@ -111,6 +111,21 @@ typedef struct eu_timing {
   int32_t reserved;
 } eu_timing_t;
 
+/* Alpha from PTO: exclude masks (k-lines, variant t0) and the lens crop of an i-line (S clause)
+ * make parts of a facet transparent (reference environment.h:703-890): a 0/1 plane is built
+ * (polygons by scan-line fill envutil_basic.cc:236-321, crop rectangle, or ellipse for fisheye
+ * facets), feathered with the 5-tap binomial (1 4 6 4 1)/16 along both axes, and multiplied into
+ * every channel; facets without alpha get an alpha channel first (nchannels = native + 1). */
+typedef struct eu_alpha_spec {
+  int32_t native_nchannels; /* channels of the raster handed in; the facet's nchannels is this, or
+                               this + 1 when an alpha channel has to be added (1 -> 2, 3 -> 4) */
+  int32_t has_crop;
+  int32_t crop_x0, crop_x1, crop_y0, crop_y1;
+  int32_t n_masks;
+  const int32_t* mask_sizes; /* vertices per polygon */
+  const float* mask_xy;      /* all vertices, x y x y ..., polygon after polygon */
+} eu_alpha_spec_t;
+
 typedef struct eu_source* eu_source_h; /* opaque: a staged, braced, prefiltered source */
 
 /* ---------------------------------------------------------------------------------------
@@ -167,6 +182,10 @@ int eu_source_upload(const char* asset_key, const eu_facet_t* f, const eu_opts_t
 int eu_source_upload_device(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o,
                             const float* d_pixels, void* cuda_stream, eu_source_h* out,
                             eu_timing_t* t);
+/* eu_source_upload for a facet with exclude masks and/or a lens crop: pixels has
+ * a->native_nchannels channels, the staged source f->nchannels */
+int eu_source_upload_alpha(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
+                           const eu_alpha_spec_t* a, eu_source_h* out, eu_timing_t* t);
 eu_source_h eu_source_find(const char* asset_key);
 int eu_source_release(eu_source_h s);
 int eu_cycle(void); /* conclude_cycle(): drop sources not used since the previous cycle */

@@ -762,6 +762,134 @@ orc_source_t* orc_source_create(const eu_facet_t* f, const eu_opts_t* o, const f
   return s;
 }
 
+/* fill_polygon, envutil_basic.cc:236-321 (non-zero winding scan-line fill; clears alpha) */
+static void fill_polygon_clear(const float* px, const float* py, int N, int w, int h, float* alpha) {
+  int* nodeX = (int*)malloc(sizeof(int) * (N + 1));
+  int* dir = (int*)malloc(sizeof(int) * (N + 1));
+  for (int pixelY = 0; pixelY < h; pixelY++) {
+    int nodes = 0, j = N - 1;
+    for (int i = 0; i < N; i++) {
+      int cross = 0;
+      if (py[i] < (float)pixelY && py[j] >= (float)pixelY) cross = 1;
+      else if (py[j] < (float)pixelY && py[i] >= (float)pixelY) cross = -1;
+      if (cross) {
+        nodeX[nodes] = (int)(px[i] + (pixelY - py[i]) / (py[j] - py[i]) * (px[j] - px[i]));
+        dir[nodes++] = cross;
+      }
+      j = i;
+    }
+    int i = 0;
+    while (i < nodes - 1) {
+      if (nodeX[i] > nodeX[i + 1]) {
+        int sw = nodeX[i]; nodeX[i] = nodeX[i + 1]; nodeX[i + 1] = sw;
+        sw = dir[i]; dir[i] = dir[i + 1]; dir[i + 1] = sw;
+        if (i) i--;
+      } else {
+        i++;
+      }
+    }
+    int w_ord = 0;
+    for (i = 0; i < nodes; i++) {
+      w_ord += dir[i];
+      if (!w_ord) continue;
+      if (i + 1 >= nodes) break; /* the reference reads nodeX[i+1] unchecked; a closed polygon never gets here */
+      if (nodeX[i] >= w) break;
+      if (nodeX[i + 1] > 0) {
+        if (nodeX[i] < 0) nodeX[i] = 0;
+        if (nodeX[i + 1] > w) nodeX[i + 1] = w;
+        for (int x = nodeX[i]; x < nodeX[i + 1]; x++) alpha[(size_t)pixelY * w + x] = 0.0f;
+      }
+    }
+  }
+  free(nodeX);
+  free(dir);
+}
+
+static int reflect_index(int i, int w) { /* zimt/extrapolate.h:141-153 */
+  if (i < 0) i = -1 - i;
+  if (i >= w) {
+    i %= 2 * w;
+    if (i >= w) i = 2 * w - i - 1;
+  }
+  return i;
+}
+
+/* the 0/1 plane of a masked / cropped facet, feathered (environment.h:711-843). The binomial
+ * kernel applied to 0/1 data yields multiples of 1/256: every partial sum is exact in float, the
+ * order of summation of the reference's circular-buffer FIR (zimt/convolve.h) does not matter. */
+static float* build_alpha_plane(const eu_facet_t* f, const eu_alpha_spec_t* a) {
+  int w = f->width, h = f->height;
+  float* alpha = (float*)malloc(sizeof(float) * (size_t)w * h);
+  for (size_t i = 0; i < (size_t)w * h; i++) alpha[i] = 1.0f;
+  const float* xy = a->mask_xy;
+  for (int m = 0; m < a->n_masks; m++) {
+    int n = a->mask_sizes[m];
+    float* vx = (float*)malloc(sizeof(float) * n);
+    float* vy = (float*)malloc(sizeof(float) * n);
+    for (int k = 0; k < n; k++) { vx[k] = xy[2 * k]; vy[k] = xy[2 * k + 1]; }
+    fill_polygon_clear(vx, vy, n, w, h, alpha);
+    free(vx); free(vy);
+    xy += 2 * n;
+  }
+  if (a->has_crop) {
+    float ca = (float)(fabs((double)(a->crop_x1 - a->crop_x0)) / 2.0);
+    float cb = (float)(fabs((double)(a->crop_y1 - a->crop_y0)) / 2.0);
+    if (f->projection == EU_FISHEYE) { /* elliptic crop, :746-772 */
+      float mx = (float)((a->crop_x0 + a->crop_x1) / 2.0);
+      float my = (float)((a->crop_y0 + a->crop_y1) / 2.0);
+      for (int y = 0; y < h; y++) {
+        float dy = fabsf((float)y - my);
+        if (dy > cb) {
+          for (int x = 0; x < w; x++) alpha[(size_t)y * w + x] = 0.0f;
+          continue;
+        }
+        float xmargin = (float)sqrt((double)(ca * ca) * (1.0 - (double)((dy * dy) / (cb * cb))));
+        for (int x = 0; x < w; x++) {
+          float dx = fabsf((float)x - mx);
+          if (dx > xmargin) alpha[(size_t)y * w + x] = 0.0f;
+        }
+      }
+    } else { /* rectangular crop, :773-790 */
+      for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+          if (x < a->crop_x0 || x >= a->crop_x1 || y < a->crop_y0 || y >= a->crop_y1) alpha[(size_t)y * w + x] = 0.0f;
+    }
+  }
+  static const float k5[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
+  float* tmp = (float*)malloc(sizeof(float) * (size_t)w * h);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      float s = 0.0f;
+      for (int j = 0; j < 5; j++) s += k5[j] * alpha[(size_t)y * w + reflect_index(x - 2 + j, w)];
+      tmp[(size_t)y * w + x] = s;
+    }
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      float s = 0.0f;
+      for (int j = 0; j < 5; j++) s += k5[j] * tmp[(size_t)reflect_index(y - 2 + j, h) * w + x];
+      alpha[(size_t)y * w + x] = s;
+    }
+  free(tmp);
+  return alpha;
+}
+
+orc_source_t* orc_source_create_alpha(const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
+                                      const eu_alpha_spec_t* a) {
+  int w = f->width, h = f->height, C = f->nchannels, nat = a->native_nchannels;
+  float* alpha = build_alpha_plane(f, a);
+  float* px = (float*)malloc(sizeof(float) * (size_t)w * h * C);
+  for (size_t i = 0; i < (size_t)w * h; i++) {
+    for (int c = 0; c < C; c++) {
+      float v = c < nat ? pixels[i * nat + c] : 1.0f; /* added alpha channel is 1 (:698-709) */
+      px[i * C + c] = v * alpha[i];                   /* v3 = v1 * v2, every channel (:867-872) */
+    }
+  }
+  free(alpha);
+  orc_source_t* s = orc_source_create(f, o, px);
+  free(px);
+  return s;
+}
+
 void orc_source_free(orc_source_t* s) {
   if (!s) return;
   free(s->container);

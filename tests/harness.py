@@ -37,6 +37,9 @@ def oracle():
         lib.orc_source_create.restype = C.c_void_p
         lib.orc_source_create.argtypes = [C.POINTER(capi.Facet), C.POINTER(capi.Opts), C.c_void_p]
         lib.orc_source_free.argtypes = [C.c_void_p]
+        lib.orc_source_create_alpha.restype = C.c_void_p
+        lib.orc_source_create_alpha.argtypes = [C.POINTER(capi.Facet), C.POINTER(capi.Opts), C.c_void_p,
+                                                C.POINTER(capi.AlphaSpec)]
         lib.orc_source_container.restype = C.POINTER(C.c_float)
         lib.orc_source_container.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         lib.orc_render.restype = C.c_int
@@ -61,7 +64,11 @@ def oracle_sources(job, structs=None):
     hs = (C.c_void_p * len(job.facets))()
     for i, f in enumerate(job.facets):
         img = np.ascontiguousarray(f.image, dtype=np.float32)
-        hs[i] = lib.orc_source_create(C.byref(fa[i]), C.byref(o), img.ctypes.data)
+        if f.has_alpha_spec():
+            a = f.alpha_spec()
+            hs[i] = lib.orc_source_create_alpha(C.byref(fa[i]), C.byref(o), img.ctypes.data, C.byref(a))
+        else:
+            hs[i] = lib.orc_source_create(C.byref(fa[i]), C.byref(o), img.ctypes.data)
     return hs
 
 

@@ -201,6 +201,27 @@ def _build():
     add("auto_tw_up_ll_rect_d3", Job([_ll_facet(128)], "rectilinear", 30.0, 96, 64, twine=-1, degree=3))   # mag > 1, cubic
     add("auto_tw_voronoi_d3", Job(_voronoi_facets(n=3), "spherical", 360.0, 512, 256, twine=-1, degree=3))  # several facets
     add("auto_tw_density_ll_ba6", Job([_ll_facet(256)], "biatan6", 90.0, 24, twine=-1, twine_density=1.5))
+    # --- PTO exclude masks (k-lines) and lens crop (i-line S): alpha by polygon fill / crop + feather ---
+    mf = _voronoi_facets(hfov=95.0, step=55.0)
+    tri = ((10.5, 8.0), (60.0, 12.25), (30.0, 50.0))
+    quad = ((70.0, 5.0), (90.0, 5.0), (90.0, 60.0), (70.0, 60.0))
+    star = ((48.0, 2.0), (56.0, 40.0), (94.0, 30.0), (60.0, 50.0), (80.0, 63.0), (48.0, 52.0), (10.0, 62.0), (36.0, 46.0),
+            (2.0, 20.0), (40.0, 36.0))
+    add("mask1_rect_d1", Job([FacetSpec(mf[0].image, "rectilinear", 95.0, yaw=mf[0].yaw, masks=(tri, quad))],
+                             "rectilinear", 90.0, 96, 64, yaw=mf[0].yaw))
+    add("crop1_rect_d3", Job([FacetSpec(mf[1].image, "rectilinear", 95.0, yaw=mf[1].yaw, pitch=mf[1].pitch, roll=mf[1].roll,
+                                        crop=(8, 80, 6, 50))], "rectilinear", 100.0, 96, 64, yaw=mf[1].yaw, degree=3))
+    add("crop_fish_sph_d1", Job([FacetSpec(_ll(96, 96), "fisheye", 180.0, crop=(6, 92, 10, 84))], "spherical", 360.0,
+                                192, 96))
+    add("mask_crop4_voronoi_sph_d1", Job([FacetSpec(mf[0].image, "rectilinear", 95.0, yaw=mf[0].yaw, masks=(star,)),
+                                          FacetSpec(mf[1].image, "rectilinear", 95.0, yaw=mf[1].yaw, pitch=mf[1].pitch,
+                                                    roll=mf[1].roll, crop=(10, 90, 4, 60)),
+                                          mf[2],
+                                          FacetSpec(_rgba(mf[3].image, 3), "rectilinear", 95.0, yaw=mf[3].yaw,
+                                                    pitch=mf[3].pitch, roll=mf[3].roll, masks=(tri,), crop=(0, 80, 0, 64))],
+                                         "spherical", 360.0, 256, 128))
+    add("mask_grey_sph_d1_tw2", Job([FacetSpec(_grey(mf[0].image), "rectilinear", 95.0, yaw=mf[0].yaw, masks=(quad,))],
+                                    "spherical", 200.0, 128, 64, yaw=mf[0].yaw, twine=2))
     tr = _translated_facets()
     add("tr1_sph_d1", Job(tr[:1], "spherical", 360.0, 192, 96))
     add("tr1_rect_d1_tw2", Job(tr[1:2], "rectilinear", 100.0, 96, 64, yaw=30.0, twine=2))
