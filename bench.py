@@ -321,7 +321,10 @@ def ours(args):
         eng.render_rows(job, hs, st, row0, row1, d_out.data_ptr(), stream, timed=False)
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
-    time.sleep(0.25 if sampler else 0.0)
+    if sampler:  # nvidia-smi takes a moment to deliver its first sample
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 5.0:
+            time.sleep(0.02)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches_before = eng.launches
