@@ -186,7 +186,7 @@ bool known_source(eu_source_h s) {
 int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, FacetDev& F) {
   memset(&F, 0, sizeof(F));
   if (s->projection != f->projection || s->nch != f->nchannels ||
-      (s->kind == EU_SRC_MOUNT && (s->w != f->width || s->h != f->height)))
+      (s->kind == EU_SRC_MOUNT && (s->w != f->window_width || s->h != f->window_height)))
     return fail(EU_ERR_ARGUMENT, "facet description does not match its staged source");
   source_dev(s, F.src);
   F.kind = s->kind;
@@ -204,15 +204,18 @@ int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, Fac
   F.ext_h = (float)(f->y1 - f->y0);
   F.total_w = (float)f->width;
   F.total_h = (float)f->height;
-  {  // window extent of an uncropped image, environment.h:616-630 (cropped facets are refused
-     // at upload): x0 + (window_width / total_width) * (x1 - x0), in double, narrowed for the
-     // float compares of test_crd (:970-978)
+  {  // window extent, environment.h:607-618: x0 + (offset / total_width) * (x1 - x0) etc., in double,
+     // narrowed for the float compares of test_crd (:970-978). BOTH axes use widths (sic).
     double wx = f->x1 - f->x0, wy = f->y1 - f->y0;
-    double p1 = (double)f->width / f->width;
-    F.win_x0 = (float)(f->x0 + 0.0 * wx);
-    F.win_y0 = (float)(f->y0 + 0.0 * wy);
-    F.win_x1 = (float)(f->x0 + p1 * wx);
-    F.win_y1 = (float)(f->y0 + p1 * wy);
+    double px0 = (double)f->window_x_offset / f->width, py0 = (double)f->window_y_offset / f->width;
+    double px1 = (double)(f->window_x_offset + f->window_width) / f->width;
+    double py1 = (double)(f->window_y_offset + f->window_width) / f->width;
+    F.win_x0 = (float)(f->x0 + px0 * wx);
+    F.win_y0 = (float)(f->y0 + py0 * wy);
+    F.win_x1 = (float)(f->x0 + px1 * wx);
+    F.win_y1 = (float)(f->y0 + py1 * wy);
+    F.win_xoff = (float)f->window_x_offset;
+    F.win_yoff = (float)f->window_y_offset;
   }
   F.mask_always = (s->kind != EU_SRC_MOUNT) || (f->projection == EU_FISHEYE && f->hfov >= M_PI * 2.0);
   F.has_lcp = f->has_lcp;
@@ -471,8 +474,8 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
   }
   // source_t ctor, environment.h:594-950
   s->kind = EU_SRC_MOUNT;
-  s->w = f->width;
-  s->h = f->height;
+  s->w = f->window_width;   // the raster handed in is the window ('W' clause, envutil_main.cc:754-786);
+  s->h = f->window_height;  // the geometry refers to the total size
   s->bc0 = s->bc1 = EU_BC_REFLECT;
   if ((f->projection == EU_SPHERICAL || f->projection == EU_CYLINDRICAL) && fabs(f->hfov - 2.0 * M_PI) < .000001)
     s->bc0 = EU_BC_PERIODIC;
@@ -603,8 +606,13 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
     return fail(EU_ERR_ARGUMENT, "bad raster description %dx%dx%d", f->width, f->height, f->nchannels);
   if (o->spline_degree < 0 || o->spline_degree > EU_MAX_DEGREE)
     return fail(EU_ERR_ARGUMENT, "spline degree %d out of range", o->spline_degree);
-  if (f->window_width != f->width || f->window_height != f->height)
-    return fail(EU_ERR_UNSUPPORTED, "cropped facets (W/h window) are not built");
+  if (f->window_width <= 0 || f->window_height <= 0 || f->window_x_offset < 0 || f->window_y_offset < 0 ||
+      f->window_x_offset + f->window_width > f->width || f->window_y_offset + f->window_height > f->height)
+    return fail(EU_ERR_ARGUMENT, "facet window %dx%d+%d+%d does not lie inside %dx%d (run eu_facet_prepare)",
+                f->window_width, f->window_height, f->window_x_offset, f->window_y_offset, f->width, f->height);
+  if ((f->projection == EU_CUBEMAP || f->projection == EU_BIATAN6) &&
+      (f->window_width != f->width || f->window_height != f->height))
+    return fail(EU_ERR_ARGUMENT, "cubemaps cannot be windowed");
   cudaStream_t st = g.stream;
   if (kind == cudaMemcpyDeviceToDevice) {  // order our stream after the caller's work on the raster
     CK(cudaEventRecord(g.ev[2], caller));
@@ -673,8 +681,9 @@ int eu_source_upload_alpha(const char* asset_key, const eu_facet_t* f, const eu_
   if (f->projection == EU_CUBEMAP || f->projection == EU_BIATAN6)
     return fail(EU_ERR_ARGUMENT, "masks and lens crop apply to single images, not to cubemaps");
   if (a->n_masks < 0 || (a->n_masks > 0 && (!a->mask_sizes || !a->mask_xy))) return fail(EU_ERR_ARGUMENT, "bad mask list");
-  if (f->width <= 0 || f->height <= 0) return fail(EU_ERR_ARGUMENT, "bad raster description");
-  const int w = f->width, h = f->height;
+  if (f->width <= 0 || f->height <= 0 || f->window_width <= 0 || f->window_height <= 0)
+    return fail(EU_ERR_ARGUMENT, "bad raster description (run eu_facet_prepare)");
+  const int w = f->window_width, h = f->window_height;  // the raster on hand is the window
   const size_t n = (size_t)w * h;
   std::vector<unsigned char> plane(n);
   eu_build_alpha_mask(f, a, plane.data());  // host: polygons and crop are a few scan lines each

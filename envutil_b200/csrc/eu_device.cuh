@@ -511,10 +511,12 @@ __device__ __forceinline__ bool dev_facet_coordinate(const FacetDev& F, const fl
     ix /= F.ext_w;
     ix *= F.total_w;
     ix -= .5f;
+    ix = ix - F.win_xoff;
     float iy = (float)((double)c[1] - F.ext_y0);
     iy /= F.ext_h;
     iy *= F.total_h;
     iy -= .5f;
+    iy = iy - F.win_yoff;
     cx = ix;
     cy = iy;
   } else {

@@ -137,8 +137,10 @@ int arguments::init(int argc, const char** argv) {
     error = "--output is mandatory";
     return EU_ERR_ARGUMENT;
   }
-  if (has("--photo") || !split.empty() || has("--single") || has("--mask_for") || twine_precise) {
-    error = "--photo / --split / --single / --mask_for / --twine_precise are outside the built path";
+  // --twine_precise is accepted and ignored, as in the reference: only environment9 reads it
+  // (environment.h:1997), which dispatch::payload never instantiates
+  if (has("--photo") || !split.empty() || has("--single") || has("--mask_for")) {
+    error = "--photo / --split / --single / --mask_for are outside the built path";
     return EU_ERR_UNSUPPORTED;
   }
 
@@ -192,8 +194,8 @@ int arguments::init(int argc, const char** argv) {
       if (ln.head != 'i') continue;
       facet_spec fs;
       fs.facet_no = nfacets++;
-      if (!ln.get("Pano").empty() || !ln.get("W").empty()) {
-        error = "i-line Pano / W clauses (unstitching, cropped input) are outside the built path";
+      if (!ln.get("Pano").empty()) {
+        error = "i-line Pano clause (unstitching) is outside the built path";
         return EU_ERR_UNSUPPORTED;
       }
       fs.filename = ln.get("n");
@@ -218,6 +220,30 @@ int arguments::init(int argc, const char** argv) {
       fs.f.height = h;
       fs.f.nchannels = c;
       fs.f.hfov = (M_PI / 180.0) * std::stod(ln.get("v"));
+      {  // 'W x0,x1,y0,y1': the file holds a window of an image of w x h pixels (envutil_main.cc:754-786)
+        const std::string& win = ln.get("W");
+        if (!win.empty()) {
+          int v[4];
+          if (sscanf(win.c_str(), "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) != 4) {
+            error = "bad W clause '" + win + "'";
+            return EU_ERR_ARGUMENT;
+          }
+          fs.f.window_x_offset = v[0];
+          fs.f.window_y_offset = v[2];
+          fs.f.window_width = v[1] - v[0];
+          fs.f.window_height = v[3] - v[2];
+          if (fs.f.window_width != w || fs.f.window_height != h) {
+            error = "the W window must have the size of the image file";
+            return EU_ERR_ARGUMENT;
+          }
+          fs.f.width = iglean(ln.get("w"));
+          fs.f.height = iglean(ln.get("h"));
+          if (fs.f.width == 0 || fs.f.height == 0) {
+            error = "a W window needs the total size (w, h)";
+            return EU_ERR_ARGUMENT;
+          }
+        }
+      }
       fs.projection_str = projection_name[fs.f.projection];
       fs.f.yaw = (M_PI / 180.0) * glean(ln.get("y"));
       fs.f.pitch = (M_PI / 180.0) * glean(ln.get("p"));

@@ -45,7 +45,7 @@ struct cuda_dispatch : public dispatch_base {
       if (!h) {
         int w, hh, c;
         std::vector<float> px;
-        if (!read_raster(fs.filename, w, hh, c, px) || w != fs.f.width || hh != fs.f.height ||
+        if (!read_raster(fs.filename, w, hh, c, px) || w != fs.f.window_width || hh != fs.f.window_height ||
             c != fs.native_nchannels) {
           fprintf(stderr, "envutil_b200: cannot read facet image '%s'\n", fs.filename.c_str());
           return EU_ERR_ARGUMENT;

@@ -26,19 +26,19 @@ double eu_get_vfov(int projection, int width, int height, double hfov) {
   double vfov = 0.0;
   switch (projection) {
     case EU_RECTILINEAR:
-      vfov = 2.0 * atan(height * tan(hfov / 2.0) / width);
+      vfov = 2.0 * eu_atan(height * tan(hfov / 2.0) / width);
       break;
     case EU_CYLINDRICAL: {
       double pixels_per_rad = width / hfov;
       double h_rad = height / pixels_per_rad;
-      vfov = 2.0 * atan(h_rad / 2.0);
+      vfov = 2.0 * eu_atan(h_rad / 2.0);
       break;
     }
     case EU_STEREOGRAPHIC: {
       double w_rad = 2.0 * tan(hfov / 4.0);
       double pixels_per_rad = width / w_rad;
       double h_rad = height / pixels_per_rad;
-      vfov = 4.0 * atan(h_rad / 2.0);
+      vfov = 4.0 * eu_atan(h_rad / 2.0);
       break;
     }
     case EU_SPHERICAL:
@@ -60,7 +60,7 @@ double eu_get_step(int projection, int width, int height, double hfov) {
   switch (projection) {
     case EU_RECTILINEAR:
     case EU_CUBEMAP:
-      step = atan(2.0 * tan(hfov / 2.0) / width);
+      step = eu_atan(2.0 * tan(hfov / 2.0) / width);
       break;
     case EU_BIATAN6:
     case EU_SPHERICAL:
@@ -69,7 +69,7 @@ double eu_get_step(int projection, int width, int height, double hfov) {
       step = hfov / width;
       break;
     case EU_STEREOGRAPHIC:
-      step = atan(4.0 * tan(hfov / 4.0) / width);
+      step = eu_atan(4.0 * tan(hfov / 4.0) / width);
       break;
     default:
       break;
@@ -113,9 +113,11 @@ int eu_facet_prepare(eu_facet_t* f) {
   if (!f || f->width <= 0 || f->height <= 0 || f->projection < 0 || f->projection >= EU_PRJ_NONE ||
       !(f->hfov > 0.0) || f->nchannels < 1 || f->nchannels > 4)
     return EU_ERR_ARGUMENT;
-  f->window_width = f->width;
-  f->window_height = f->height;
-  f->window_x_offset = f->window_y_offset = 0;
+  if (f->window_width <= 0 || f->window_height <= 0) {  // no 'W' window given: the whole image
+    f->window_width = f->width;
+    f->window_height = f->height;
+    f->window_x_offset = f->window_y_offset = 0;
+  }
   f->step = eu_get_step(f->projection, f->width, f->height, f->hfov);
   double e[4];
   eu_get_extent(f->projection, f->width, f->height, f->hfov, e);
@@ -398,7 +400,7 @@ static void fill_polygon_clear(const float* px, const float* py, int N, int w, i
 }
 
 void eu_build_alpha_mask(const eu_facet_t* f, const eu_alpha_spec_t* a, unsigned char* plane) {
-  const int w = f->width, h = f->height;
+  const int w = f->window_width, h = f->window_height;
   memset(plane, 1, (size_t)w * h);
   const float* xy = a->mask_xy;
   for (int m = 0; m < a->n_masks; m++) {

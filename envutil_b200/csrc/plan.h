@@ -41,6 +41,7 @@ struct FacetDev {
   float ext_w, ext_h;      // float(x1-x0), float(y1-y0)              (:993,:998)
   float total_w, total_h;  // float(total_width/height)               (:994,:999)
   float win_x0, win_x1, win_y0, win_y1;  // window_extent narrowed for the float compares (:970-978)
+  float win_xoff, win_yoff;  // window offset in pixels, subtracted after md_to_spline (:1003-1005)
   int32_t mask_always;     // get_mask yields all-true (cubemaps, fisheye >= 360: :1567,:1741)
   int32_t has_lcp, has_shift, has_shear;  // pto_planar (environment.h:240-284)
   float lcp[4], lcp_s, shift_h, shift_v;

@@ -38,6 +38,10 @@ class FacetSpec:
     tr_z: float = 0.0
     tp_y: float = 0.0
     tp_p: float = 0.0
+    window: Optional[tuple] = None  # PTO i-line W clause (x0, x1, y0, y1): `image` is this window of a larger
+                                    # image whose total size is (total_width, total_height)
+    total_width: int = 0
+    total_height: int = 0
     crop: Optional[tuple] = None   # PTO i-line S clause: (x0, x1, y0, y1) lens crop -> alpha (needs the PTO route)
     masks: tuple = ()              # PTO k-lines, variant t0: polygons ((x, y), ...) excluded -> alpha
     width: int = 0   # used when image is None
@@ -107,7 +111,7 @@ class Job:
     # ---- reference command line (real spellings, envutil_main.cc:190-372) ----
     def uses_pto(self):
         return any(f.eev or f.a or f.b or f.c or f.d or f.e or f.g or f.t or f.tr_x or f.tr_y or f.tr_z
-                   or f.has_alpha_spec() for f in self.facets)
+                   or f.has_alpha_spec() or f.window is not None for f in self.facets)
 
     _PTO_CODE = {"rectilinear": 0, "cylindrical": 1, "fisheye": 3, "spherical": 4, "stereographic": 10}
 
@@ -116,6 +120,8 @@ class Job:
         lines = []
         for f, p in zip(self.facets, facet_paths):
             w, h, _ = f.native_shape()
+            if f.window is not None:
+                w, h = f.total_width, f.total_height
             ln = (f'i w{w} h{h} f{self._PTO_CODE[f.projection]} v{float(f.hfov)!r} y{float(f.yaw)!r} '
                   f'p{float(f.pitch)!r} r{float(f.roll)!r}')
             for key, val in (("Eev", f.eev), ("a", f.a), ("b", f.b), ("c", f.c), ("d", f.d), ("e", f.e), ("g", f.g),
@@ -125,6 +131,8 @@ class Job:
                     ln += f" {key}{float(val)!r}"
             if f.crop is not None:
                 ln += " S%d,%d,%d,%d" % tuple(int(v) for v in f.crop)
+            if f.window is not None:
+                ln += " W%d,%d,%d,%d" % tuple(int(v) for v in f.window)
             ln += f' n"{p}"'
             lines.append(ln)
         for i, f in enumerate(self.facets):
@@ -204,6 +212,13 @@ class Job:
             s = fa[i]
             s.projection = capi.PROJECTION_NAMES.index(f.projection)
             s.width, s.height, s.nchannels = w, h, c
+            if f.window is not None:  # 'W' clause: geometry from the total size, raster = the window
+                x0, x1, y0, y1 = (int(v) for v in f.window)
+                s.width, s.height = f.total_width, f.total_height
+                s.window_x_offset, s.window_y_offset = x0, y0
+                s.window_width, s.window_height = x1 - x0, y1 - y0
+                assert (s.window_width, s.window_height) == (w, h), "image must have the window's size"
+                w, h = s.width, s.height
             # facet angles are parsed as doubles (%F / std::stod) and scaled by M_PI / 180.0
             s.hfov = f.hfov * (math.pi / 180.0)
             s.yaw, s.pitch, s.roll = (v * (math.pi / 180.0) for v in (f.yaw, f.pitch, f.roll))

@@ -70,6 +70,9 @@ typedef struct eu_facet {
   double s, d, r_max, cap_radius;
   double shift_h, shift_v; /* h, v in model units (what facet_base::h/v hold after process_geometry) */
   int32_t has_shift, has_lcp, has_shear, has_2d_tf, has_translation;
+  /* input, optional: a window of the total image ('W' clause of an i-line: the raster handed to
+   * eu_source_upload is window_width x window_height, width/height/hfov describe the whole image).
+   * Leave zero for uncropped facets; eu_facet_prepare then sets the window to the whole image. */
   int32_t window_width, window_height, window_x_offset, window_y_offset;
 } eu_facet_t;
 

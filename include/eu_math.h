@@ -179,6 +179,8 @@ EU_HD float eu_atan2f(float y, float x) {
 /* ---- double-precision atan. One per-pixel call site of the reference works in double:
  * stereographic_stepper computes  a = M_PI_2 - 2.0 * atan ( norm(planar) / 2.0 )  with a
  * double-promoted operand (reference stepper.h:1146-1151, promotion rules zimt/common.h:278).
+ * The set-up arithmetic (get_vfov / get_step, envutil_basic.cc:50-156) uses the same function for
+ * its double atan, so that host, device and the pinned reference build see one definition.
  * Specified here as a fixed sequence of binary64 operations so host and device agree bit for
  * bit: |x|>1 -> pi/2 - atan(1/|x|); t>tan(pi/8) -> pi/4 + atan((t-1)/(t+1)); then the Taylor
  * series of atan on |u| <= tan(pi/8) with 24 terms (truncation error < 1e-20). */

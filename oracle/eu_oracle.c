@@ -40,17 +40,17 @@ enum { CM_LEFT = 0, CM_RIGHT = 1, CM_TOP = 2, CM_BOTTOM = 3, CM_FRONT = 4, CM_BA
 /* get_vfov, envutil_basic.cc:50-110 (the CUBEMAP case falls through to default) */
 static double orc_get_vfov(int prj, int w, int h, double hfov) {
   switch (prj) {
-    case EU_RECTILINEAR: return 2.0 * atan(h * tan(hfov / 2.0) / w);
+    case EU_RECTILINEAR: return 2.0 * eu_atan(h * tan(hfov / 2.0) / w);
     case EU_CYLINDRICAL: {
       double ppr = w / hfov;
       double hr = h / ppr;
-      return 2.0 * atan(hr / 2.0);
+      return 2.0 * eu_atan(hr / 2.0);
     }
     case EU_STEREOGRAPHIC: {
       double wr = 2.0 * tan(hfov / 4.0);
       double ppr = w / wr;
       double hr = h / ppr;
-      return 4.0 * atan(hr / 2.0);
+      return 4.0 * eu_atan(hr / 2.0);
     }
     case EU_SPHERICAL:
     case EU_FISHEYE: return hfov * h / w;
@@ -63,12 +63,12 @@ double orc_get_step(int prj, int w, int h, double hfov) {
   (void)h;
   switch (prj) {
     case EU_RECTILINEAR:
-    case EU_CUBEMAP: return atan(2.0 * tan(hfov / 2.0) / w);
+    case EU_CUBEMAP: return eu_atan(2.0 * tan(hfov / 2.0) / w);
     case EU_BIATAN6:
     case EU_SPHERICAL:
     case EU_CYLINDRICAL:
     case EU_FISHEYE: return hfov / w;
-    case EU_STEREOGRAPHIC: return atan(4.0 * tan(hfov / 4.0) / w);
+    case EU_STEREOGRAPHIC: return eu_atan(4.0 * tan(hfov / 4.0) / w);
     default: return 0.0;
   }
 }
@@ -736,8 +736,12 @@ orc_source_t* orc_source_create(const eu_facet_t* f, const eu_opts_t* o, const f
   }
   /* source_t ctor, environment.h:594-950 */
   s->kind = KIND_MOUNT;
-  s->w = f->width;
-  s->h = f->height;
+  /* a 'W' window: the raster on disk is the window, the geometry refers to the total size
+   * (envutil_main.cc:754-786, environment.h:596-601) */
+  int ww = f->window_width > 0 ? f->window_width : f->width;
+  int wh = f->window_height > 0 ? f->window_height : f->height;
+  s->w = ww;
+  s->h = wh;
   s->bc0 = BC_REFLECT;
   s->bc1 = BC_REFLECT;
   if ((f->projection == EU_SPHERICAL || f->projection == EU_CYLINDRICAL) && fabs(f->hfov - 2.0 * M_PI) < .000001)
@@ -818,7 +822,7 @@ static int reflect_index(int i, int w) { /* zimt/extrapolate.h:141-153 */
  * kernel applied to 0/1 data yields multiples of 1/256: every partial sum is exact in float, the
  * order of summation of the reference's circular-buffer FIR (zimt/convolve.h) does not matter. */
 static float* build_alpha_plane(const eu_facet_t* f, const eu_alpha_spec_t* a) {
-  int w = f->width, h = f->height;
+  int w = f->window_width > 0 ? f->window_width : f->width, h = f->window_height > 0 ? f->window_height : f->height;
   float* alpha = (float*)malloc(sizeof(float) * (size_t)w * h);
   for (size_t i = 0; i < (size_t)w * h; i++) alpha[i] = 1.0f;
   const float* xy = a->mask_xy;
@@ -875,7 +879,8 @@ static float* build_alpha_plane(const eu_facet_t* f, const eu_alpha_spec_t* a) {
 
 orc_source_t* orc_source_create_alpha(const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
                                       const eu_alpha_spec_t* a) {
-  int w = f->width, h = f->height, C = f->nchannels, nat = a->native_nchannels;
+  int w = f->window_width > 0 ? f->window_width : f->width, h = f->window_height > 0 ? f->window_height : f->height;
+  int C = f->nchannels, nat = a->native_nchannels;
   float* alpha = build_alpha_plane(f, a);
   float* px = (float*)malloc(sizeof(float) * (size_t)w * h * C);
   for (size_t i = 0; i < (size_t)w * h; i++) {
@@ -913,6 +918,7 @@ typedef struct {
   float ext_w, ext_h;
   float win_x0, win_x1, win_y0, win_y1;
   int total_w, total_h;
+  int win_xoff, win_yoff;
   int has_lcp, has_shift, has_shear;
   float lcp[4], lcp_s, sh_h, sh_v;
   double shear_g, shear_t;
@@ -1259,10 +1265,12 @@ static int facet_eval(const facet_ctx* F, int nch, const float r[3], float* px) 
       ix /= F->ext_w;
       ix *= (float)F->total_w;
       ix -= .5f;
+      ix = ix - (float)F->win_xoff; /* crd_spl = image_crd - window offset, environment.h:1003-1005 */
       float iy = (float)((double)c[1] - F->ext_y0);
       iy /= F->ext_h;
       iy *= (float)F->total_h;
       iy -= .5f;
+      iy = iy - (float)F->win_yoff;
       spline_eval(s, s->degree, s->wmat, ix, iy, sp);
     }
   } else {
@@ -1447,13 +1455,18 @@ static int facet_setup(const eu_target_t* t, const eu_opts_t* o, const eu_facet_
   F->ext_h = (float)(e[3] - e[2]);
   F->total_w = f->width;
   F->total_h = f->height;
-  { /* window extent for an uncropped image, environment.h:616-630 (y uses width, sic) */
+  { /* window extent, environment.h:607-618: BOTH axes are scaled by widths (sic) */
     double wx = e[1] - e[0], wy = e[3] - e[2];
-    double px1 = (double)f->width / f->width, py1 = (double)f->width / f->width;
-    F->win_x0 = (float)(e[0] + 0.0 * wx);
-    F->win_y0 = (float)(e[2] + 0.0 * wy);
+    int ww = f->window_width > 0 ? f->window_width : f->width;
+    int xo = f->window_width > 0 ? f->window_x_offset : 0, yo = f->window_width > 0 ? f->window_y_offset : 0;
+    double px0 = (double)xo / f->width, py0 = (double)yo / f->width;
+    double px1 = (double)(xo + ww) / f->width, py1 = (double)(yo + ww) / f->width;
+    F->win_x0 = (float)(e[0] + px0 * wx);
+    F->win_y0 = (float)(e[2] + py0 * wy);
     F->win_x1 = (float)(e[0] + px1 * wx);
     F->win_y1 = (float)(e[2] + py1 * wy);
+    F->win_xoff = xo;
+    F->win_yoff = yo;
   }
   F->mask_always = (src->kind != KIND_MOUNT) || (f->projection == EU_FISHEYE && f->hfov >= M_PI * 2.0);
   /* process_geometry, envutil_basic.h:499-543 */

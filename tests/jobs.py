@@ -222,6 +222,17 @@ def _build():
                                          "spherical", 360.0, 256, 128))
     add("mask_grey_sph_d1_tw2", Job([FacetSpec(_grey(mf[0].image), "rectilinear", 95.0, yaw=mf[0].yaw, masks=(quad,))],
                                     "spherical", 200.0, 128, 64, yaw=mf[0].yaw, twine=2))
+    # --- 'W' windows: the file holds a crop of a larger image whose geometry the i-line describes ---
+    big = _rect(128, 96, 90.0, 15.0, -5.0, 0.0)
+    add("win_rect_sph_d1", Job([FacetSpec(np.ascontiguousarray(big[20:84, 16:112]), "rectilinear", 90.0, yaw=15.0, pitch=-5.0,
+                                          window=(16, 112, 20, 84), total_width=128, total_height=96)],
+                               "spherical", 360.0, 256, 128))
+    add("win_rect_rect_d3_tw2", Job([FacetSpec(np.ascontiguousarray(big[8:72, 0:96]), "rectilinear", 90.0, yaw=15.0, pitch=-5.0,
+                                               window=(0, 96, 8, 72), total_width=128, total_height=96)],
+                                    "rectilinear", 80.0, 96, 64, yaw=15.0, degree=3, twine=2))
+    add("win_voronoi_sph_d1", Job([FacetSpec(np.ascontiguousarray(big[20:84, 16:112]), "rectilinear", 90.0, yaw=15.0, pitch=-5.0,
+                                             window=(16, 112, 20, 84), total_width=128, total_height=96),
+                                   _voronoi_facets()[3]], "spherical", 360.0, 256, 128))
     tr = _translated_facets()
     add("tr1_sph_d1", Job(tr[:1], "spherical", 360.0, 192, 96))
     add("tr1_rect_d1_tw2", Job(tr[1:2], "rectilinear", 100.0, 96, 64, yaw=30.0, twine=2))

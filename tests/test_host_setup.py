@@ -31,6 +31,20 @@ def test_extent_and_step_match_oracle(lib, prj, w, h, hfov):
     assert lib.eu_get_step(prj, w, h, hf) == orc.orc_get_step(prj, w, h, hf)
 
 
+def test_setup_atan_is_the_contract_function(lib):
+    """get_vfov / get_step use the double atan of include/eu_math.h (the pinned reference build
+    interposes it for the whole program): 128x96 at hfov 90 is a case where glibc's atan gives a
+    different last bit of the vertical extent, which showed as 1-ulp pixel differences."""
+    orc = harness.oracle()
+    a = (C.c_double * 4)()
+    b = (C.c_double * 4)()
+    for (w, h, hf) in ((128, 96, 90.0), (100, 75, 90.0), (6000, 4000, 100.0), (1920, 1080, 90.0)):
+        lib.eu_get_extent(capi.RECTILINEAR, w, h, math.radians(hf), a)
+        orc.orc_get_extent(capi.RECTILINEAR, w, h, math.radians(hf), b)
+        assert list(a) == list(b)
+        assert abs(a[3] - h / w * math.tan(math.radians(hf) / 2)) < 1e-15
+
+
 def test_rotation_known_answer(lib):
     """roll 7, pitch -21, yaw 33 degrees, rows = images of e_x, e_y, e_z."""
     m = (C.c_double * 9)()
