@@ -146,12 +146,17 @@ def test_errors_are_reported_not_fatal(engine):
         assert rc == -1 and b"degree" in lib.eu_last_error()
         bogus = (capi.SourceH * 1)(C.c_void_p(0x1234))
         assert lib.eu_render(C.byref(t), C.byref(o), 1, fa, bogus, taps, 0, out.ctypes.data, None) == -1
-        # sub-features that are not built are refused, never approximated
+        # nonsense is refused, never approximated: a window larger than the image
         crop = capi.Facet.from_buffer_copy(fa[0])
-        crop.window_width = crop.width // 2
+        crop.window_width = crop.width * 2
         h = capi.SourceH()
         img = np.ascontiguousarray(job.facets[0].image)
-        assert lib.eu_source_upload(None, C.byref(crop), C.byref(o), img.ctypes.data, C.byref(h), None) == -2
-        assert b"cropped" in lib.eu_last_error()
+        assert lib.eu_source_upload(None, C.byref(crop), C.byref(o), img.ctypes.data, C.byref(h), None) == -1
+        assert b"does not lie inside" in lib.eu_last_error()
+        # translation with a cubemap target is not built
+        cj = copy.deepcopy(jobs.JOBS["tr1_sph_d1"])
+        cj.projection, cj.width, cj.height, cj.hfov = "cubemap", 32, 0, 90.0
+        with pytest.raises(RuntimeError, match="cubemap target"):
+            engine.render(cj)
     finally:
         engine.release(hs)
