@@ -348,6 +348,8 @@ def ours(args):
     checksum = float(d_out[::64, ::64].double().sum().item())
     gather_ms = 0.0
     if bands_mode:  # output bands gathered on rank 0 (NCCL), timed on its own: not part of `value`
+        full = eu_bands.gather_bands(d_out, H, world, rank, dist)  # first use sets up the NCCL channels
+        del full
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
