@@ -41,6 +41,7 @@ class Target(C.Structure):
     _fields_ = [
         ("projection", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("nchannels", C.c_int32),
         ("hfov", C.c_double), ("yaw", C.c_double), ("pitch", C.c_double), ("roll", C.c_double),
+        ("gain", C.c_double),
         ("x0", C.c_double), ("x1", C.c_double), ("y0", C.c_double), ("y1", C.c_double),
         ("step", C.c_double),
     ]

@@ -290,6 +290,7 @@ void target_dev(const eu_target_t* t, bool normalize, TargetDev& T) {
   T.delta = (float)EU_LANES * (a1 - a0) / (float)w;
   T.section_md = a1 - a0;
   T.refc_md = (float)((a1 - a0) / 2.0);
+  T.unbrighten = (t->gain == 0.0) ? 1.0f : (float)t->gain;
 }
 
 // the facet a single-facet job renders (solo), else facet 0

@@ -139,8 +139,8 @@ int arguments::init(int argc, const char** argv) {
   }
   // --twine_precise is accepted and ignored, as in the reference: only environment9 reads it
   // (environment.h:1997), which dispatch::payload never instantiates
-  if (has("--photo") || !split.empty() || has("--single") || has("--mask_for")) {
-    error = "--photo / --split / --single / --mask_for are outside the built path";
+  if (has("--photo") || !split.empty() || has("--mask_for")) {
+    error = "--photo / --split / --mask_for are outside the built path";
     return EU_ERR_UNSUPPORTED;
   }
 
@@ -388,6 +388,11 @@ int arguments::init(int argc, const char** argv) {
     return EU_ERR_ARGUMENT;
   }
   if (nfacets == 1) solo = 0;
+  single = geti("--single", -1);
+  if (single != -1 && (single < 0 || single >= nfacets)) {
+    error = "--single is beyond the facet count";
+    return EU_ERR_ARGUMENT;
+  }
 
   // ---- Eev -> brighten, channel count (envutil_main.cc:1003-1154) -----------------------
   nchannels = 1;
@@ -415,7 +420,27 @@ int arguments::init(int argc, const char** argv) {
   if (nch > 0) nchannels = nch;
 
   // ---- target (envutil_main.cc:1180-1232) -----------------------------------------------
-  if (p_line_present) {
+  if (single >= 0) {
+    // 'single': the target takes over the facet's geometry (envutil_main.cc:1157-1178); the facet's
+    // own lens correction / translation on the TARGET side needs the inverse lens path
+    const facet_spec& fs = facet_spec_v[single];
+    if (fs.f.has_2d_tf || fs.f.has_translation) {
+      error = "--single on a facet with lens correction or translation needs the inverse lens path, which is not built";
+      return EU_ERR_UNSUPPORTED;
+    }
+    t.projection = fs.f.projection;
+    projection_str = projection_name[t.projection];
+    t.width = fs.f.width;
+    t.height = fs.f.height;
+    t.hfov = fs.f.hfov;
+    t.yaw = fs.f.yaw;
+    t.pitch = fs.f.pitch;
+    t.roll = fs.f.roll;
+    if (fs.brighten != 1.0) {  // work(): float unbrighten = 1.0 / fct.brighten
+      float unbrighten = 1.0 / fs.brighten;
+      t.gain = unbrighten;
+    }
+  } else if (p_line_present) {
     t.hfov = p_line_hfov;
     t.projection = p_line_projection;
     projection_str = projection_name[t.projection];

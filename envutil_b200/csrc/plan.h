@@ -66,6 +66,7 @@ struct TargetDev {
   float delta;               // 16 * (a1-a0)/W                (stepper.h:305)
   float bias_x, bias_y;      // bias of deriv_stepper's r10 / r01 (stepper.h:303-304,1606-1625)
   float section_md, refc_md; // cubemap/biatan6 steppers    (stepper.h:1265-1266)
+  float unbrighten;          // --single: colour channels of the result are multiplied by this (work(), :481-511)
 };
 
 struct RenderParams {

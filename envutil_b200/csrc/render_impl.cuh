@@ -323,6 +323,11 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
     for (int c = 0; c < NCH; c++) px[c] = acc[c];
   }
   if (!active) return;
+  if (T.unbrighten != 1.0f) {  // amplify_type after everything else (envutil_payload.cc:500-511)
+    constexpr int NCOL = (NCH == 2 || NCH == 4) ? NCH - 1 : NCH;
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) px[c] *= T.unbrighten;
+  }
   size_t o = (size_t)(y - P.row0) * T.width + x;
   if (P.out) {
     float* dst = P.out + o * NCH;
@@ -526,6 +531,11 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
 #pragma unroll
       for (int c = 0; c < NCH; c++) px[c] += tw * help[c];
     }
+  }
+  if (T.unbrighten != 1.0f) {
+    constexpr int NCOL = (NCH == 2 || NCH == 4) ? NCH - 1 : NCH;
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) px[c] *= T.unbrighten;
   }
   float* dst = P.out + ((size_t)(y - P.row0) * T.width + x) * NCH;
   if constexpr (NCH == 4) {

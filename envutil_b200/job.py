@@ -102,6 +102,7 @@ class Job:
     twine_max: int = 8
     synopsis: str = "panorama"
     solo: int = -1
+    single: int = -1  # --single K: render into facet K's geometry, undo its brighten (envutil_main.cc:1157-1178)
     support_min: int = 8
     tile_size: int = 64
     padded: bool = False    # back-end option: 16-byte RGB texels in HBM (eu_opts.reserved[0])
@@ -166,6 +167,8 @@ class Job:
             args += ["--synopsis", self.synopsis]
         if self.solo >= 0:
             args += ["--solo", str(self.solo)]
+        if self.single >= 0:
+            args += ["--single", str(self.single)]
         if self.support_min != 8:
             args += ["--support_min", str(self.support_min)]
         if self.tile_size != 64:
@@ -203,7 +206,8 @@ class Job:
         f32 = lambda v: float(np.float32(v)) * (math.pi / 180.0)
         t.hfov = f32(self.hfov)
         t.yaw, t.pitch, t.roll = f32(self.yaw), f32(self.pitch), f32(self.roll)
-        capi.check(lib.eu_target_prepare(C.byref(t)), lib)
+        if self.single < 0:
+            capi.check(lib.eu_target_prepare(C.byref(t)), lib)
         n = len(self.facets)
         fa = (capi.Facet * n)()
         gains = self.facet_gains()
@@ -228,6 +232,13 @@ class Job:
             s.a, s.b, s.c, s.h, s.v = f.a, f.b, f.c, f.d, f.e
             s.brighten = gains[i]
             capi.check(lib.eu_facet_prepare(C.byref(s)), lib)
+        if self.single >= 0:  # (facet_base&) args = facet_spec_v[single]: geometry in radians as the facet has it
+            sf = fa[self.single]
+            t.projection, t.width, t.height = sf.projection, sf.width, sf.height
+            t.hfov, t.yaw, t.pitch, t.roll = sf.hfov, sf.yaw, sf.pitch, sf.roll
+            b = np.float32(gains[self.single])
+            t.gain = float(np.float32(1.0 / float(b))) if b != 1.0 else 0.0
+            capi.check(lib.eu_target_prepare(C.byref(t)), lib)
         o = capi.Opts()
         o.spline_degree = self.degree
         o.prefilter_degree = self.prefilter

@@ -79,7 +79,9 @@ def c5_stage_a(facets3, **kw):
     middle bracket (the reference cannot merge and stitch in one pass)."""
     f = facets3[0]
     h, w = f.image.shape[:2]
-    job = Job(list(facets3), "rectilinear", f.hfov, w, h, yaw=f.yaw, synopsis="hdr_merge", name="C5A", **kw)
+    # `--synopsis hdr_merge --single 0`: the target takes the geometry of the first (middle-exposure)
+    # bracket, whose brighten is 1, so the un-brighten step of work() is a no-op (SURVEY.md 8d)
+    job = Job(list(facets3), "rectilinear", f.hfov, w, h, yaw=f.yaw, synopsis="hdr_merge", single=0, name="C5A", **kw)
     alg = w * h * RGB * (1 + len(facets3))
     return job, alg
 

@@ -85,6 +85,8 @@ typedef struct eu_target {
   int32_t nchannels;
   double hfov;
   double yaw, pitch, roll;
+  double gain;             /* --single: 1 / brighten of the facet whose geometry the target takes over
+                              (work(), envutil_payload.cc:481-511); 0 or 1 = none */
   /* derived */
   double x0, x1, y0, y1;
   double step;

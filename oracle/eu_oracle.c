@@ -1555,6 +1555,7 @@ int orc_render(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   n_threads = 1;
 #endif
   if (mode == 1 && (nch == 2 || nch == 4)) mode = 3; /* roll_out: voronoi_syn_plus for alpha, :2306-2311 */
+  const float unbrighten = (t->gain == 0.0) ? 1.0f : (float)t->gain;
 #pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads)
   for (int y = row0; y < row1; y++) {
     /* one zimt vector at a time: 16 consecutive pixels of the row (segments are multiples of 16) */
@@ -1609,6 +1610,10 @@ int orc_render(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
       }
       for (int l = 0; l < nl; l++) {
         float* px = out + ((size_t)(y - row0) * T.width + g0 + l) * nch;
+        if (unbrighten != 1.0f) { /* amplify_type in work(), envutil_payload.cc:481-511 */
+          int ncol = (nch == 2 || nch == 4) ? nch - 1 : nch;
+          for (int c = 0; c < ncol; c++) res[l][c] *= unbrighten;
+        }
         for (int c = 0; c < nch; c++) px[c] = res[l][c];
         if (index_out) index_out[(size_t)(y - row0) * T.width + g0 + l] = ids[l];
       }

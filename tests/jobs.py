@@ -233,6 +233,11 @@ def _build():
     add("win_voronoi_sph_d1", Job([FacetSpec(np.ascontiguousarray(big[20:84, 16:112]), "rectilinear", 90.0, yaw=15.0, pitch=-5.0,
                                              window=(16, 112, 20, 84), total_width=128, total_height=96),
                                    _voronoi_facets()[3]], "spherical", 360.0, 256, 128))
+    # --- --single K: the target takes facet K's geometry, the result is un-brightened (C5 stage A) ---
+    add("single0_hdr3_d1", Job(_bracket_facets(), "rectilinear", 70.0, 96, 64, synopsis="hdr_merge", single=0))
+    add("single1_hdr3_d1", Job(_bracket_facets(), "rectilinear", 70.0, 96, 64, synopsis="hdr_merge", single=1))
+    add("single2_voronoi4_d3_tw2", Job(_voronoi_facets(), "spherical", 360.0, 64, 32, single=2, degree=3, twine=2))
+    add("single0_cm_ll", Job([FacetSpec(_cm(32), "cubemap", 90.0), _ll_facet(128)], "spherical", 360.0, 64, 32, single=0))
     tr = _translated_facets()
     add("tr1_sph_d1", Job(tr[:1], "spherical", 360.0, 192, 96))
     add("tr1_rect_d1_tw2", Job(tr[1:2], "rectilinear", 100.0, 96, 64, yaw=30.0, twine=2))

@@ -135,7 +135,8 @@ def test_pto_back_references(cli, tmp_path):
                                   "mixed_grey_rgba_voronoi_sph_d1", "rgba4_voronoi_sph_d3", "hdr3_rgba_rect_d1",
                                   "auto_tw_voronoi_d3", "auto_tw_up_ll_rect_d1", "auto_tw_density_ll_ba6",
                                   "mask_crop4_voronoi_sph_d1", "crop_fish_sph_d1", "mask_grey_sph_d1_tw2",
-                                  "win_voronoi_sph_d1", "win_rect_rect_d3_tw2"])
+                                  "win_voronoi_sph_d1", "win_rect_rect_d3_tw2", "single1_hdr3_d1",
+                                  "single2_voronoi4_d3_tw2", "single0_cm_ll"])
 def test_cli_output_equals_reference_output(cli, tmp_path, name):
     """The drop-in claim end to end: the SAME command line given to the reference binary and to
     envutil_b200_cli produces the same file, bit for bit (golden sha256 of the reference run)."""
