@@ -73,3 +73,29 @@ def test_constant_image_is_reproduced(engine):
     out = engine.render(job)
     # the full-sphere prefilter truncates its initial sums at tolerance 1e-4 (environment.h:385)
     assert np.abs(out - 0.625).max() < 1e-4
+
+
+def test_c5_two_stage_reduced(engine):
+    """configs[4] at 1/10 size, as the reference can run it: (A) per position,
+    `--synopsis hdr_merge --single 0` of the three exposure brackets; (B) the voronoi panorama of
+    the merged facets. Both stages bit-exact against the oracle; the merge reproduces the
+    unclipped middle exposure where nothing is clipped."""
+    from envutil_b200 import workloads
+    fs = workloads.c5_facets(scale=10)
+    merged, yaws = [], []
+    for k in range(0, len(fs), 3):
+        job, _ = workloads.c5_stage_a(fs[k:k + 3])
+        out = engine.render(job)
+        ref = harness.oracle_render(job)
+        assert harness.compare(out, ref)["n_diff"] == 0, k
+        merged.append(out)
+        yaws.append(fs[k].yaw)
+    mid = fs[0].image
+    ok = mid < 0.2  # far from clipping in every bracket (the Eev-10 frame is 4x brighter)
+    assert np.abs(merged[0] - mid)[ok].max() < 1e-5
+    job, _ = workloads.c5_stage_b(merged, yaws, scale=10)
+    out, idx = engine.render(job), engine.index_plane(job)
+    ref, ridx = harness.oracle_render(job, want_index=True)
+    assert harness.compare(out, ref)["n_diff"] == 0
+    assert np.array_equal(idx, ridx)
+    assert set(np.unique(idx)) == {-1, 0, 1, 2, 3, 4, 5}  # every facet wins somewhere; the poles are uncovered
