@@ -619,7 +619,17 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
     CK(cudaEventRecord(g.ev[2], caller));
     CK(cudaStreamWaitEvent(st, g.ev[2], 0));
   }
-  eu_source* s = new eu_source();
+  // until it is registered the source is owned here: any early return frees the container
+  struct Guard {
+    eu_source* s;
+    ~Guard() {
+      if (s) {
+        pool_free(s->container);
+        delete s;
+      }
+    }
+  } guard{new eu_source()};
+  eu_source* s = guard.s;
   s->container = nullptr;
   s->last_used_cycle = g.cycle;
   s->refs = 1;
@@ -628,11 +638,7 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
   CK(cudaEventRecord(g.ev[0], st));
   rc = stage_on_device(f, o, pixels, kind, st, s, &launches, &copy_ms);
   if (rc == EU_OK) rc = maybe_pad(o, s, st, &launches);
-  if (rc != EU_OK) {
-    pool_free(s->container);
-    delete s;
-    return rc;
-  }
+  if (rc != EU_OK) return rc;
   CK(cudaEventRecord(g.ev[1], st));
   CK(cudaStreamSynchronize(st));
   if (t) {
@@ -646,6 +652,7 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
     t->launches = launches;
     t->reserved = 0;
   }
+  guard.s = nullptr;  // from here on the registry owns it
   g.sources.push_back(s);
   if (asset_key && *asset_key) {
     s->key = asset_key;
@@ -688,28 +695,32 @@ int eu_source_upload_alpha(const char* asset_key, const eu_facet_t* f, const eu_
   const size_t n = (size_t)w * h;
   std::vector<unsigned char> plane(n);
   eu_build_alpha_mask(f, a, plane.data());  // host: polygons and crop are a few scan lines each
-  unsigned char* d_mask = nullptr;
-  float *d_raw = nullptr, *d_a = nullptr, *d_b = nullptr, *d_px = nullptr;
   cudaStream_t st = g.stream;
-  CK(cudaMallocAsync((void**)&d_mask, n, st));
-  CK(pool_alloc(&d_raw, n * nat));
-  CK(pool_alloc(&d_a, n));
-  CK(pool_alloc(&d_b, n));
-  CK(pool_alloc(&d_px, n * C));
+  struct Scratch {  // freed (stream-ordered) on every path out of this function
+    unsigned char* mask = nullptr;
+    float *raw = nullptr, *a = nullptr, *b = nullptr, *px = nullptr;
+    ~Scratch() {
+      if (mask) cudaFreeAsync(mask, g.stream);
+      pool_free(raw);
+      pool_free(a);
+      pool_free(b);
+      pool_free(px);
+    }
+  } d;
+  CK(cudaMallocAsync((void**)&d.mask, n, st));
+  CK(pool_alloc(&d.raw, n * nat));
+  CK(pool_alloc(&d.a, n));
+  CK(pool_alloc(&d.b, n));
+  CK(pool_alloc(&d.px, n * C));
   CK(cudaEventRecord(g.ev[2], st));
-  CK(cudaMemcpyAsync(d_mask, plane.data(), n, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_raw, pixels, n * nat * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d.mask, plane.data(), n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d.raw, pixels, n * nat * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(g.ev[3], st));
-  CK(eu_launch_alpha_apply(d_mask, d_a, d_b, d_raw, nat, d_px, C, w, h, st));
+  CK(eu_launch_alpha_apply(d.mask, d.a, d.b, d.raw, nat, d.px, C, w, h, st));
   CK(cudaStreamSynchronize(st));  // plane goes out of scope; ev[2]/ev[3] are reused by the staging below
   float h2d = 0;
   CK(cudaEventElapsedTime(&h2d, g.ev[2], g.ev[3]));
-  rc = upload_common(asset_key, f, o, d_px, cudaMemcpyDeviceToDevice, st, out, t);
-  cudaFreeAsync(d_mask, st);
-  pool_free(d_raw);
-  pool_free(d_a);
-  pool_free(d_b);
-  pool_free(d_px);
+  rc = upload_common(asset_key, f, o, d.px, cudaMemcpyDeviceToDevice, st, out, t);
   if (rc == EU_OK && t) {
     t->h2d_ms = h2d;
     t->launches += 3;
