@@ -302,8 +302,11 @@ struct Plan {
 };
 
 // builds the plan and uploads the per-job tables; everything is enqueued on g.stream
+// `cs`: the stream the render will be launched on. The per-job facet array and tap list live in
+// one device buffer each; they are rewritten ON THAT STREAM, i.e. after every render enqueued
+// before (another job's kernel may still be reading them) and before this job's.
 int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_t* facets,
-               const eu_source_h* sources, const eu_tap_t* taps, int n_taps, Plan& plan) {
+               const eu_source_h* sources, const eu_tap_t* taps, int n_taps, cudaStream_t cs, Plan& plan) {
   if (!t || !o || !facets || !sources) return fail(EU_ERR_ARGUMENT, "null argument");
   if (nf < 1 || nf > EU_MAX_FACETS) return fail(EU_ERR_ARGUMENT, "facet count %d out of range 1..%d", nf, EU_MAX_FACETS);
   if (n_taps < 0 || n_taps > EU_MAX_TAPS) return fail(EU_ERR_ARGUMENT, "tap count %d out of range", n_taps);
@@ -372,7 +375,7 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
       CK(cudaMalloc(&g.d_facets, sizeof(FacetDev) * EU_MAX_FACETS));
       g.facets_cap = EU_MAX_FACETS;
     }
-    CK(cudaMemcpyAsync(g.d_facets, F.data(), sizeof(FacetDev) * nf, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.d_facets, F.data(), sizeof(FacetDev) * nf, cudaMemcpyHostToDevice, cs));
     P.facets = g.d_facets;
   }
   if (n_taps > 0) {
@@ -389,8 +392,8 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
       tp[3 * k + 1] = taps[k].y * 4.0f;
       tp[3 * k + 2] = taps[k].w;
     }
-    CK(cudaMemcpyAsync(g.d_taps, tp.data(), sizeof(float) * tp.size(), cudaMemcpyHostToDevice, g.stream));
-    CK(cudaStreamSynchronize(g.stream));  // tp goes out of scope
+    // pageable source: the call returns once the data sit in the driver's staging buffer
+    CK(cudaMemcpyAsync(g.d_taps, tp.data(), sizeof(float) * tp.size(), cudaMemcpyHostToDevice, cs));
     P.taps = g.d_taps;
   }
   // planar tables: recomputed only when the target changes
@@ -794,7 +797,7 @@ int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets, const
   int rc = need_up();
   if (rc) return rc;
   Plan plan;
-  rc = build_plan(t, o, n_facets, facets, sources, taps, n_taps, plan);
+  rc = build_plan(t, o, n_facets, facets, sources, taps, n_taps, (cudaStream_t)cuda_stream, plan);
   if (rc) return rc;
   if (row0 < 0 || row1 > t->height || row0 >= row1) return fail(EU_ERR_ARGUMENT, "bad row band [%d,%d)", row0, row1);
   if (!d_out) return fail(EU_ERR_ARGUMENT, "null output");
@@ -851,7 +854,7 @@ int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
   if (rc) return rc;
   if (!t || !index_out) return fail(EU_ERR_ARGUMENT, "null argument");
   Plan plan;
-  rc = build_plan(t, o, n_facets, facets, sources, nullptr, 0, plan);
+  rc = build_plan(t, o, n_facets, facets, sources, nullptr, 0, g.stream, plan);
   if (rc) return rc;
   size_t n = (size_t)t->width * t->height;
   rc = grow(g.d_index, g.index_cap, n);

@@ -60,7 +60,10 @@ def c4(scale=1, **kw):
     return job, alg
 
 
-def c5_facets(scale=1, positions=6, brackets=(12.0, 10.0, 14.0)):
+C5_BRACKETS = (12.0, 10.0, 14.0)  # Eev of the three exposures, middle exposure first
+
+
+def c5_facets(scale=1, positions=6, brackets=C5_BRACKETS):
     """configs[4] inputs: `positions` rectilinear 6000x4000 views, yaw 60k degrees, hfov 100,
     each in three exposure brackets Eev 12/10/14 (images = clamp(scene * 2^(12-Eev), 0, 1))."""
     w, h = 6000 // scale, 4000 // scale
@@ -78,7 +81,7 @@ def c5_stage_a(facets3, **kw):
     """C5 stage A: hdr_merge of the three brackets of one position into the geometry of the
     middle bracket (the reference cannot merge and stitch in one pass)."""
     f = facets3[0]
-    h, w = f.image.shape[:2]
+    w, h, _ = f.shape()
     # `--synopsis hdr_merge --single 0`: the target takes the geometry of the first (middle-exposure)
     # bracket, whose brighten is 1, so the un-brighten step of work() is a no-op (SURVEY.md 8d)
     job = Job(list(facets3), "rectilinear", f.hfov, w, h, yaw=f.yaw, synopsis="hdr_merge", single=0, name="C5A", **kw)
@@ -86,9 +89,18 @@ def c5_stage_a(facets3, **kw):
     return job, alg
 
 
+def c5_stage_a_geometry(facets3, w, h, **kw):
+    """Stage A for facets whose rasters live elsewhere (FacetSpec.image None, width/height set)."""
+    return c5_stage_a(facets3, **kw)
+
+
 def c5_stage_b(merged, yaws, hfov=100.0, scale=1, **kw):
     """C5 stage B: voronoi panorama of the merged facets -> spherical 16384x8192."""
     fs = [FacetSpec(m, "rectilinear", hfov, yaw=y) for m, y in zip(merged, yaws)]
+    return c5_stage_b_geometry(fs, scale, **kw)
+
+
+def c5_stage_b_geometry(fs, scale=1, **kw):
     job = Job(fs, "spherical", 360.0, 16384 // scale, 8192 // scale, name="C5B", **kw)
-    alg = job.width * job.height * RGB + sum(m.shape[0] * m.shape[1] for m in merged) * RGB
+    alg = job.width * job.height * RGB + sum(f.shape()[0] * f.shape()[1] for f in fs) * RGB
     return job, alg

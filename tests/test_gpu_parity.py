@@ -160,3 +160,30 @@ def test_errors_are_reported_not_fatal(engine):
             engine.render(cj)
     finally:
         engine.release(hs)
+
+
+def test_async_jobs_do_not_share_plan_buffers(engine):
+    """eu_render_rows is asynchronous on the caller's stream. Different multi-facet jobs enqueued
+    back to back must not see each other's facet array / tap list (they live in one device buffer
+    each and are rewritten in stream order) - found with the multi-GPU C5 pipeline."""
+    torch = pytest.importorskip("torch")
+    names = ["voronoi4_sph_d1", "hdr3_rect_d1", "voronoi3_rect_d1_tw2", "hdr3_sph_d3_tw2", "voronoi4_sph_d3_rot"]
+    stream = torch.cuda.current_stream().cuda_stream
+    work = []
+    for n in names:
+        job = jobs.JOBS[n]
+        st = job.structs()
+        hs = engine.stage(job, st)
+        t = st[0]
+        buf = torch.empty((t.height, t.width, t.nchannels), dtype=torch.float32, device="cuda:0")
+        work.append((n, job, st, hs, buf))
+    try:
+        for _ in range(3):
+            for n, job, st, hs, buf in work:
+                engine.render_rows(job, hs, st, 0, st[0].height, buf.data_ptr(), stream, timed=False)
+        torch.cuda.synchronize()
+        for n, job, st, hs, buf in work:
+            assert np.array_equal(buf.cpu().numpy(), harness.oracle_render(job)), n
+    finally:
+        for n, job, st, hs, buf in work:
+            engine.release(hs)
