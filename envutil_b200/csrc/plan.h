@@ -1,6 +1,6 @@
 // plan.h - POD job description handed from the host plan builder to the sm_100a kernels.
 //
-// The host computes every per-job scalar in the reference's precision (plan.cc) and narrows
+// The host computes every per-job scalar in the reference's precision (api.cu) and narrows
 // it to what the reference's functors hold (mostly float); the kernels only do the per-pixel
 // work. Field comments cite the reference member each value replaces.
 #pragma once

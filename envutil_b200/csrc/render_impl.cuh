@@ -12,7 +12,6 @@
 // Included by render_c*.cu, one translation unit per (NCH, TS) so that they compile in parallel.
 #pragma once
 #include <limits.h>
-#include <stdlib.h>
 
 #include "eu_device.cuh"
 #include "kernels.h"
@@ -563,8 +562,7 @@ static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_
     return;
   }
   if constexpr (MODE != EU_MODE_SINGLE) {
-    static const bool no_smem_facets = getenv("EU_NO_SMEM_FACETS") != nullptr;  // A/B switch for measurements
-    if (P.n_facets <= EU_SMEM_FACETS && !no_smem_facets) {
+    if (P.n_facets <= EU_SMEM_FACETS) {
       switch (P.degree) {
         case 1: k_render<NCH, TS, MODE, TWINE, 1, true, false><<<grid, block, 0, st>>>(P); break;
         case 3: k_render<NCH, TS, MODE, TWINE, 3, true, false><<<grid, block, 0, st>>>(P); break;

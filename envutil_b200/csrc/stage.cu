@@ -407,6 +407,7 @@ cudaError_t eu_launch_iir_x(float* core, int stride, int nch, int w, int h, cons
   int nb = (h + IIR_R - 1) / IIR_R;
   switch (nch) {
     case 1: k_iir_x_tiled<1><<<nb, IIR_R * 1, 0, st>>>(core, stride, w, h, f); break;
+    case 2: k_iir_x_tiled<2><<<nb, IIR_R * 2, 0, st>>>(core, stride, w, h, f); break;
     case 3: k_iir_x_tiled<3><<<nb, IIR_R * 3, 0, st>>>(core, stride, w, h, f); break;
     case 4: k_iir_x_tiled<4><<<nb, IIR_R * 4, 0, st>>>(core, stride, w, h, f); break;
     default: {
@@ -466,6 +467,7 @@ cudaError_t eu_launch_cubemap_support(float* ir, int pitch, int nch, int F, int 
       dim3 block(32, 8), grid((x1 - x0 + 31) / 32, (y1 - y0 + 7) / 8);
       switch (nch) {
         case 1: k_cm_fill<1><<<grid, block, 0, st>>>(ir, src, face, x0, y0, x1, y1, S, ithird, refc_md, (float)model_to_px); break;
+        case 2: k_cm_fill<2><<<grid, block, 0, st>>>(ir, src, face, x0, y0, x1, y1, S, ithird, refc_md, (float)model_to_px); break;
         case 3: k_cm_fill<3><<<grid, block, 0, st>>>(ir, src, face, x0, y0, x1, y1, S, ithird, refc_md, (float)model_to_px); break;
         case 4: k_cm_fill<4><<<grid, block, 0, st>>>(ir, src, face, x0, y0, x1, y1, S, ithird, refc_md, (float)model_to_px); break;
         default: return cudaErrorInvalidValue;

@@ -190,6 +190,9 @@ def _build():
                                               "spherical", 360.0, 256, 128))
     add("ga2_voronoi_sph_d1", Job([FacetSpec(_ga(f.image, k), f.projection, f.hfov, yaw=f.yaw, pitch=f.pitch,
                                              roll=f.roll) for k, f in enumerate(vf[:2])], "spherical", 360.0, 192, 96))
+    add("ga_cm_sph_d3", Job([FacetSpec(_ga(_cm(32), 1), "cubemap", 90.0)], "spherical", 360.0, 128, 64, degree=3))
+    add("ga1_rect_d5_tw2", Job([FacetSpec(_ga(vf[0].image, 0), "rectilinear", 95.0, yaw=vf[0].yaw)], "rectilinear", 90.0,
+                               64, 48, yaw=vf[0].yaw, degree=5, twine=2))
     add("rgba_cm_sph_d1", Job([FacetSpec(_rgba(_cm(32), 1), "cubemap", 90.0)], "spherical", 360.0, 128, 64))
     hb = _bracket_facets()
     add("hdr3_rgba_rect_d1", Job([FacetSpec(_rgba(f.image, 1), f.projection, f.hfov, yaw=f.yaw, eev=f.eev) for f in hb],
