@@ -390,11 +390,36 @@ def ours(args):
     for _ in range(e2e_steps):
         parts.append(e2e_step())
     barrier()
+    e2e_blocking_s = time.perf_counter() - t0
+    # pipelined: the same per-step work (H2D of the raster, staging, render, D2H of the frame) through
+    # eu_source_upload_async / eu_render_async / eu_job_wait with up to three jobs in flight, so the
+    # upload of step n+1 overlaps the download of step n
+    DEPTH = 3
+    ring = [h_out] + [torch.empty((H, W, C), dtype=torch.float32).pin_memory() for _ in range(DEPTH - 1)]
+    pipe_steps = max(e2e_steps, 2 * DEPTH)
+
+    def pipelined(n_steps):
+        pending = []
+        for i in range(n_steps):
+            pending.append(eng.submit(job, st, [h_src.data_ptr()], ring[i % DEPTH].data_ptr()))
+            if len(pending) >= DEPTH:
+                eng.finish(pending.pop(0))
+        while pending:
+            eng.finish(pending.pop(0))
+
+    pipelined(DEPTH)
+    barrier()
+    t0 = time.perf_counter()
+    pipelined(pipe_steps)
+    barrier()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    te = torch.tensor([e2e_s / pipe_steps, e2e_blocking_s / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item()) / e2e_steps * 1e3
+    e2e_ms = float(te[0].item()) * 1e3
+    e2e_blocking_ms = float(te[1].item()) * 1e3
+    e2e_steps = pipe_steps
+    h_out = ring[(pipe_steps - 1) % DEPTH]
     e2e_ok = bool(np.array_equal(h_out[::97, ::89].numpy(), d_out[::97, ::89].cpu().numpy()))
     if sampler:
         sampler.stop()
@@ -434,8 +459,12 @@ def ours(args):
             "e2e": {"value": world * mpix / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h_src.numel() * 4), "d2h_bytes_per_step": int(h_out.numel() * 4),
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "scope": "eu_source_upload (H2D + cubemap IR + prefilter) + eu_render (kernel + D2H), pinned host "
-                             "buffers, wall clock", "matches_device_path": e2e_ok,
+                    "scope": "every step: H2D of the 302 MB raster + cubemap IR + prefilter + render + D2H of the 403 MB "
+                             "frame, pinned host buffers, wall clock; eu_source_upload_async / eu_render_async / "
+                             "eu_job_wait with 3 jobs in flight (upload of step n+1 overlaps download of step n)",
+                    "blocking": {"value": world * mpix / (e2e_blocking_ms * 1e-3), "ms_per_step": e2e_blocking_ms,
+                                 "scope": "eu_source_upload + eu_render, one blocking call pair per step"},
+                    "matches_device_path": e2e_ok,
                     "breakdown_ms": {"h2d": float(np.mean([p[0].h2d_ms for p in parts])),
                                      "staging_kernels": float(np.mean([p[0].render_ms for p in parts])),
                                      "render_kernel": float(np.mean([p[1].render_ms for p in parts])),

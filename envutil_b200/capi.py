@@ -106,6 +106,11 @@ SYMBOLS = {
     "eu_render_rows": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
                                  C.POINTER(SourceH), C.POINTER(Tap), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.POINTER(Timing)]),
+    "eu_source_upload_async": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p,
+                                         C.POINTER(SourceH)]),
+    "eu_render_async": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet), C.POINTER(SourceH),
+                                  C.POINTER(Tap), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "eu_job_wait": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
     "eu_debug_planes": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
                                   C.POINTER(SourceH), C.c_void_p]),
 }

@@ -38,6 +38,7 @@ struct eu_source {
   eu_cubemap_metrics_t cm;
   long last_used_cycle;
   int refs;
+  bool foreign_use;  // rendered from on a caller's stream: release has to synchronise the device
 };
 
 namespace {
@@ -45,8 +46,18 @@ namespace {
 struct Context {
   bool up = false;
   int device = -1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // staging + render
+  cudaStream_t up_stream = nullptr;    // H2D of asynchronous uploads
+  cudaStream_t down_stream = nullptr;  // D2H of asynchronous jobs
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  struct JobSlot {
+    float* d_out = nullptr;
+    size_t cap = 0;
+    cudaEvent_t start = nullptr, rendered = nullptr, done = nullptr;
+    bool pending = false;
+    int launches = 0;
+  } jobs[EU_MAX_JOBS_IN_FLIGHT];
+  int next_job = 0;
   std::vector<eu_source*> sources;
   std::map<std::string, eu_source*> by_key;
   long cycle = 0;
@@ -90,8 +101,8 @@ int need_up() {
 // Large device buffers (containers, upload staging) come from CUDA's stream-ordered pool with
 // the release threshold lifted: a freed container is handed to the next upload instead of going
 // back to the driver (cudaMalloc/cudaFree of a few hundred MB cost milliseconds and synchronise).
-cudaError_t pool_alloc(float** p, size_t n_floats) {
-  return cudaMallocAsync((void**)p, n_floats * sizeof(float), g.stream);
+cudaError_t pool_alloc(float** p, size_t n_floats, cudaStream_t st = nullptr) {
+  return cudaMallocAsync((void**)p, n_floats * sizeof(float), st ? st : g.stream);
 }
 void pool_free(void* p) {
   if (p) cudaFreeAsync(p, g.stream);
@@ -430,8 +441,15 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
 
 // `pixels` is a device pointer (kind = DeviceToDevice) or a host pointer (HostToDevice): the
 // raster is copied straight into its place inside the container, there is no staging copy.
+// `cpst`: the stream the placement copies run on (the staging stream itself, or the upload stream
+// of an asynchronous upload; the two are ordered by events around the copies).
 int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixels, cudaMemcpyKind kind,
-                    cudaStream_t st, eu_source* s, int* launches, float* copy_ms) {
+                    cudaStream_t st, cudaStream_t cpst, eu_source* s, int* launches, float* copy_ms) {
+  auto copies_end = [&]() -> cudaError_t {  // the staging kernels start after the copy
+    cudaError_t e = cudaEventRecord(g.ev[3], cpst);
+    if (e == cudaSuccess && cpst != st) e = cudaStreamWaitEvent(st, g.ev[3], 0);
+    return e;
+  };
   int degree = o->spline_degree;
   int pdeg = o->prefilter_degree < 0 ? degree : o->prefilter_degree;
   if (pdeg > EU_MAX_DEGREE) return fail(EU_ERR_ARGUMENT, "prefilter degree %d out of range", pdeg);
@@ -457,13 +475,15 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
     s->pitch = (S * nch + 3) & ~3;
     const int pitch = s->pitch;
     size_t n = (size_t)pitch * 6 * S;
-    CK(pool_alloc(&s->container, n));
-    CK(cudaMemsetAsync(s->container, 0, n * sizeof(float), st));
-    CK(cudaEventRecord(g.ev[2], st));
+    // allocate, clear and fill on the copy stream: an asynchronous upload does not wait for the
+    // staging stream (which may still be busy with the previous job), only the other way round
+    CK(pool_alloc(&s->container, n, cpst));
+    CK(cudaMemsetAsync(s->container, 0, n * sizeof(float), cpst));
+    CK(cudaEventRecord(g.ev[2], cpst));  // start of the placement copies (timing of the blocking upload)
     for (int face = 0; face < 6; face++)
       CK(cudaMemcpy2DAsync(s->container + (size_t)(face * S + L) * pitch + (size_t)L * nch, (size_t)pitch * sizeof(float),
-                           d_pixels + (size_t)face * Fpx * Fpx * nch, (size_t)Fpx * tb, (size_t)Fpx * tb, Fpx, kind, st));
-    CK(cudaEventRecord(g.ev[3], st));
+                           d_pixels + (size_t)face * Fpx * Fpx * nch, (size_t)Fpx * tb, (size_t)Fpx * tb, Fpx, kind, cpst));
+    CK(copies_end());
     int nl = 0;
     CK(eu_launch_cubemap_support(s->container, pitch, nch, Fpx, S, L, R, s->cm.refc_md, s->cm.model_to_px, &nl, st));
     *launches += nl;
@@ -491,13 +511,13 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
   s->chh = s->h + s->ly + s->ry;
   s->pitch = (s->cw * nch + 3) & ~3;
   size_t n = (size_t)s->pitch * s->chh;
-  CK(pool_alloc(&s->container, n));
+  CK(pool_alloc(&s->container, n, cpst));
   int stride = s->pitch;
   float* core = s->container + (size_t)s->ly * stride + (size_t)s->lx * nch;
-  CK(cudaEventRecord(g.ev[2], st));
+  CK(cudaEventRecord(g.ev[2], cpst));
   CK(cudaMemcpy2DAsync(core, (size_t)stride * sizeof(float), d_pixels, (size_t)s->w * tb, (size_t)s->w * tb, s->h, kind,
-                       st));
-  CK(cudaEventRecord(g.ev[3], st));
+                       cpst));
+  CK(copies_end());
   bool sphere = is_full_sphere(f);
   if (sphere && (s->ly > s->h || s->ry > s->h)) return fail(EU_ERR_ARGUMENT, "image too small for its brace");
   if (pdeg > 1) {
@@ -569,6 +589,13 @@ int eu_init(int device_id) {
     return fail(EU_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device_id, prop.major,
                 prop.minor);
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g.up_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g.down_stream, cudaStreamNonBlocking));
+  for (auto& j : g.jobs) {
+    CK(cudaEventCreate(&j.start));
+    CK(cudaEventCreate(&j.rendered));
+    CK(cudaEventCreate(&j.done));
+  }
   {
     cudaMemPool_t mp;
     CK(cudaDeviceGetDefaultMemPool(&mp, device_id));
@@ -591,8 +618,16 @@ void eu_shutdown(void) {
   cudaFree(g.d_taps);
   cudaFree(g.d_out);
   cudaFree(g.d_index);
+  cudaDeviceSynchronize();
   for (auto& e : g.ev) cudaEventDestroy(e);
-  cudaStreamSynchronize(g.stream);
+  for (auto& j : g.jobs) {
+    cudaFree(j.d_out);
+    cudaEventDestroy(j.start);
+    cudaEventDestroy(j.rendered);
+    cudaEventDestroy(j.done);
+  }
+  cudaStreamDestroy(g.up_stream);
+  cudaStreamDestroy(g.down_stream);
   {
     cudaMemPool_t mp;
     if (cudaDeviceGetDefaultMemPool(&mp, g.device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
@@ -602,7 +637,8 @@ void eu_shutdown(void) {
 }
 
 static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
-                         cudaMemcpyKind kind, cudaStream_t caller, eu_source_h* out, eu_timing_t* t) {
+                         cudaMemcpyKind kind, cudaStream_t caller, eu_source_h* out, eu_timing_t* t,
+                         bool async = false) {
   int rc = need_up();
   if (rc) return rc;
   if (!f || !o || !pixels || !out) return fail(EU_ERR_ARGUMENT, "null argument");
@@ -636,15 +672,16 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
   s->container = nullptr;
   s->last_used_cycle = g.cycle;
   s->refs = 1;
+  s->foreign_use = false;
   int launches = 0;
   float copy_ms = 0;
   CK(cudaEventRecord(g.ev[0], st));
-  rc = stage_on_device(f, o, pixels, kind, st, s, &launches, &copy_ms);
+  rc = stage_on_device(f, o, pixels, kind, st, async ? g.up_stream : st, s, &launches, &copy_ms);
   if (rc == EU_OK) rc = maybe_pad(o, s, st, &launches);
   if (rc != EU_OK) return rc;
   CK(cudaEventRecord(g.ev[1], st));
-  CK(cudaStreamSynchronize(st));
-  if (t) {
+  if (!async) CK(cudaStreamSynchronize(st));  // renders are enqueued on the same stream, i.e. behind the staging
+  if (t && !async) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
     CK(cudaEventElapsedTime(&copy_ms, g.ev[2], g.ev[3]));
@@ -743,7 +780,9 @@ int eu_source_release(eu_source_h s) {
   int rc = need_up();
   if (rc) return rc;
   if (!known_source(s)) return fail(EU_ERR_ARGUMENT, "not a live source handle");
-  CK(cudaDeviceSynchronize());  // renders on caller streams may still be reading the container
+  // the container is freed in stream order on the library stream, behind every render enqueued
+  // there; only renders on a caller's stream (eu_render_rows) need a device-wide wait
+  if (s->foreign_use) CK(cudaDeviceSynchronize());
   free_source(s);
   return EU_OK;
 }
@@ -802,6 +841,8 @@ int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets, const
   if (row0 < 0 || row1 > t->height || row0 >= row1) return fail(EU_ERR_ARGUMENT, "bad row band [%d,%d)", row0, row1);
   if (!d_out) return fail(EU_ERR_ARGUMENT, "null output");
   cudaStream_t caller = (cudaStream_t)cuda_stream;
+  if (caller != g.stream)
+    for (int i = 0; i < n_facets; i++) sources[i]->foreign_use = true;
   // tables were enqueued on the library stream; the render runs on the caller's stream
   CK(cudaEventRecord(g.ev[2], g.stream));
   CK(cudaStreamWaitEvent(caller, g.ev[2], 0));
@@ -844,6 +885,75 @@ int eu_render(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_f
   if (timing) {
     *timing = tm;
     CK(cudaEventElapsedTime(&timing->d2h_ms, g.ev[2], g.ev[3]));
+  }
+  return EU_OK;
+}
+
+int eu_source_upload_async(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
+                           eu_source_h* out) {
+  return upload_common(asset_key, f, o, pixels, cudaMemcpyHostToDevice, nullptr, out, nullptr, true);
+}
+
+struct eu_job {
+  int slot;
+};
+static eu_job g_job_handles[EU_MAX_JOBS_IN_FLIGHT];
+
+int eu_render_async(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+                    const eu_source_h* sources, const eu_tap_t* taps, int n_taps, float* out, eu_job_h* job) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!t || !out || !job) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (t->width <= 0 || t->height <= 0 || t->nchannels < 1) return fail(EU_ERR_ARGUMENT, "target not prepared");
+  const int slot = g.next_job;
+  Context::JobSlot& J = g.jobs[slot];
+  if (J.pending) return fail(EU_ERR_STATE, "%d jobs are in flight already: eu_job_wait one first", EU_MAX_JOBS_IN_FLIGHT);
+  const size_t n = (size_t)t->width * t->height * t->nchannels;
+  if (n > J.cap) {
+    CK(cudaDeviceSynchronize());
+    if (J.d_out) CK(cudaFree(J.d_out));
+    J.d_out = nullptr;
+    J.cap = 0;
+    CK(cudaMalloc(&J.d_out, n * sizeof(float)));
+    J.cap = n;
+  }
+  Plan plan;
+  rc = build_plan(t, o, n_facets, facets, sources, taps, n_taps, g.stream, plan);
+  if (rc) return rc;
+  plan.P.row0 = 0;
+  plan.P.row1 = t->height;
+  plan.P.out = J.d_out;
+  plan.P.index_out = nullptr;
+  CK(cudaEventRecord(J.start, g.stream));
+  CK(eu_launch_render(plan.P, g.stream));
+  CK(cudaEventRecord(J.rendered, g.stream));
+  CK(cudaStreamWaitEvent(g.down_stream, J.rendered, 0));
+  CK(cudaMemcpyAsync(out, J.d_out, n * sizeof(float), cudaMemcpyDeviceToHost, g.down_stream));
+  CK(cudaEventRecord(J.done, g.down_stream));
+  // the slot's buffer is rewritten only after its download: the render stream waits when it wraps
+  J.pending = true;
+  J.launches = plan.launches + 1;
+  g.next_job = (slot + 1) % EU_MAX_JOBS_IN_FLIGHT;
+  CK(cudaStreamWaitEvent(g.stream, g.jobs[g.next_job].done, 0));  // no-op for a slot that was never used
+  g_job_handles[slot].slot = slot;
+  *job = &g_job_handles[slot];
+  return EU_OK;
+}
+
+int eu_job_wait(eu_job_h job, eu_timing_t* timing) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!job || job->slot < 0 || job->slot >= EU_MAX_JOBS_IN_FLIGHT) return fail(EU_ERR_ARGUMENT, "not a job handle");
+  Context::JobSlot& J = g.jobs[job->slot];
+  if (!J.pending) return fail(EU_ERR_STATE, "job is not pending");
+  CK(cudaEventSynchronize(J.done));
+  J.pending = false;
+  if (timing) {
+    CK(cudaEventElapsedTime(&timing->render_ms, J.start, J.rendered));
+    CK(cudaEventElapsedTime(&timing->d2h_ms, J.rendered, J.done));  // includes waiting for the download stream
+    timing->h2d_ms = 0;
+    timing->launches = J.launches;
+    timing->reserved = 0;
   }
   return EU_OK;
 }

@@ -108,6 +108,35 @@ class Engine:
             self.launches += 1
         return tm
 
+    # ---- pipelined jobs (eu_source_upload_async / eu_render_async / eu_job_wait) ---------
+    def submit(self, job, structs, pinned_pixels, pinned_out):
+        """Enqueue upload + staging + render + download of a single-raster job; returns a ticket for
+        finish(). pinned_pixels / pinned_out: addresses of page-locked host buffers."""
+        t, fa, o, taps, ntaps = structs
+        n = len(job.facets)
+        hs = (capi.SourceH * n)()
+        for i in range(n):
+            h = capi.SourceH()
+            capi.check(self.lib.eu_source_upload_async(None, C.byref(fa[i]), C.byref(o), C.c_void_p(pinned_pixels[i]),
+                                                       C.byref(h)), self.lib)
+            hs[i] = h
+        jh = C.c_void_p()
+        try:
+            capi.check(self.lib.eu_render_async(C.byref(t), C.byref(o), n, fa, hs, taps, ntaps, C.c_void_p(pinned_out),
+                                                C.byref(jh)), self.lib)
+        except RuntimeError:
+            self.release(hs)
+            raise
+        return jh, hs
+
+    def finish(self, ticket):
+        jh, hs = ticket
+        tm = capi.Timing()
+        capi.check(self.lib.eu_job_wait(jh, C.byref(tm)), self.lib)
+        self.release(hs)
+        self.launches += tm.launches
+        return tm
+
     def index_plane(self, job, sources=None, structs=None):
         st = structs or job.structs(self.lib)
         t, fa, o, taps, ntaps = st

@@ -211,6 +211,21 @@ int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets,
                    const eu_facet_t* facets, const eu_source_h* sources, const eu_tap_t* taps,
                    int n_taps, int row0, int row1, float* d_out, void* cuda_stream,
                    eu_timing_t* timing);
+/* Pipelined jobs. payload() is blocking, but a host that streams jobs (pipe mode, sequences) can
+ * keep the PCIe links busy in both directions: eu_source_upload_async enqueues the H2D copy on an
+ * upload stream and the staging kernels behind it, eu_render_async enqueues the render and - on a
+ * download stream - the D2H copy of the result, and eu_job_wait blocks until that copy is done.
+ * With two or three jobs in flight the upload of job n+1 overlaps the download of job n. `pixels`
+ * and `out` must be page-locked host memory and stay valid until eu_job_wait returns; sources may
+ * be released after the wait. At most EU_MAX_JOBS_IN_FLIGHT jobs may be pending. */
+#define EU_MAX_JOBS_IN_FLIGHT 4
+typedef struct eu_job* eu_job_h;
+int eu_source_upload_async(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
+                           eu_source_h* out);
+int eu_render_async(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+                    const eu_source_h* sources, const eu_tap_t* taps, int n_taps, float* out, eu_job_h* job);
+int eu_job_wait(eu_job_h job, eu_timing_t* timing);
+
 /* Index plane for bit-exact parity checks: per target pixel the cube face hit (single cubemap
  * facet) or the winning facet of the panorama synopsis (-1: no facet hit). Host buffer w*h. */
 int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets,

@@ -187,3 +187,38 @@ def test_async_jobs_do_not_share_plan_buffers(engine):
     finally:
         for n, job, st, hs, buf in work:
             engine.release(hs)
+
+
+def test_pipelined_jobs_match_blocking_calls(engine):
+    """eu_source_upload_async / eu_render_async / eu_job_wait: several jobs in flight on the
+    upload, render and download streams give the frames the blocking calls give."""
+    torch = pytest.importorskip("torch")
+    names = ["cm_sph_d3", "ll_rect_d3_rot", "ll_fish_d1_tw4", "ba6_sph_d1", "cm_sph_d3_rot", "ll_cube_d1"]
+    tickets, outs = [], []
+    for rep in range(2):
+        for n in names:
+            job = jobs.JOBS[n]
+            st = job.structs()
+            src = torch.from_numpy(np.ascontiguousarray(job.facets[0].image)).pin_memory()
+            out = torch.empty((st[0].height, st[0].width, st[0].nchannels), dtype=torch.float32).pin_memory()
+            tickets.append((engine.submit(job, st, [src.data_ptr()], out.data_ptr()), src))
+            outs.append((n, out))
+            if len(tickets) >= 3:
+                tk, _ = tickets.pop(0)
+                tm = engine.finish(tk)
+                assert tm.render_ms > 0
+    while tickets:
+        engine.finish(tickets.pop(0)[0])
+    for n, out in outs:
+        assert np.array_equal(out.numpy(), harness.oracle_render(jobs.JOBS[n])), n
+    # a fifth pending job is refused
+    job = jobs.JOBS["ll_rect_d1"]
+    st = job.structs()
+    src = torch.from_numpy(np.ascontiguousarray(job.facets[0].image)).pin_memory()
+    bufs = [torch.empty((st[0].height, st[0].width, 3), dtype=torch.float32).pin_memory() for _ in range(5)]
+    tks = [engine.submit(job, st, [src.data_ptr()], bufs[i].data_ptr()) for i in range(4)]
+    with pytest.raises(RuntimeError, match="in flight"):
+        engine.submit(job, st, [src.data_ptr()], bufs[4].data_ptr())
+    for tk in tks:
+        engine.finish(tk)
+    engine.lib.eu_cycle()
