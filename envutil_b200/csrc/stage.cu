@@ -5,6 +5,8 @@
 //   spherical_prefilter                   environment.h:356-522
 //   bracer                                zimt/brace.h:151-338
 //   cubemap_t::fill_support / prefilter   cubemap.h:607-946
+#include <algorithm>
+
 #include "eu_device.cuh"
 #include "kernels.h"
 
@@ -90,50 +92,64 @@ __device__ __forceinline__ float iir_iacc(const IirDev& f, Acc& c, int M, int k)
 }
 
 // solve_gain_inlined (recursive.h:631-729) on one line, in place. The recursion itself is serial,
-// but the loads are not: elements are fetched U at a time before the dependent chain runs over
-// them, so that every thread keeps U loads in flight (the in-place stores would otherwise
-// serialise the loads behind them).
+// but the loads are not: a sweep is software-pipelined in chunks of U elements - the loads of the
+// next chunk are issued before the dependent chain runs over the current one, so every thread
+// keeps U..2U loads in flight all the time (left to the compiler, the in-place stores would
+// serialise the loads behind them). Elements start, start+DIR, ... (count of them); step(v) is one
+// step of the recursion. Full chunks run without bounds checks: with few lines per SM (the
+// row-resident x sweep) the instruction count per element is what bounds the kernel.
+template <int U, int DIR, typename Acc, typename Step>
+__device__ __forceinline__ void iir_sweep(Acc& c, int start, int count, Step step) {
+  float a[U], b[U];
+  int j0 = 0;
+  if (count >= 2 * U) {
+#pragma unroll
+    for (int u = 0; u < U; u++) a[u] = c(start + DIR * u);
+    for (; j0 + 3 * U <= count; j0 += 2 * U) {  // chunks j0 (in a), j0+U and j0+2U are complete
+      const int n = start + DIR * j0;
+#pragma unroll
+      for (int u = 0; u < U; u++) b[u] = c(n + DIR * (U + u));
+#pragma unroll
+      for (int u = 0; u < U; u++) a[u] = step(a[u]);
+#pragma unroll
+      for (int u = 0; u < U; u++) c(n + DIR * u) = a[u];
+#pragma unroll
+      for (int u = 0; u < U; u++) a[u] = c(n + DIR * (2 * U + u));
+#pragma unroll
+      for (int u = 0; u < U; u++) b[u] = step(b[u]);
+#pragma unroll
+      for (int u = 0; u < U; u++) c(n + DIR * (U + u)) = b[u];
+    }
+    {  // chunk j0 is loaded and complete
+      const int n = start + DIR * j0;
+#pragma unroll
+      for (int u = 0; u < U; u++) a[u] = step(a[u]);
+#pragma unroll
+      for (int u = 0; u < U; u++) c(n + DIR * u) = a[u];
+      j0 += U;
+    }
+  }
+  for (; j0 < count; j0++) {
+    const int n = start + DIR * j0;
+    c(n) = step(c(n));
+  }
+}
+
 template <int U, typename Acc>
 __device__ __forceinline__ void iir_line(const IirDev& f, Acc& c, int M) {
   if (M == 1 || f.npoles < 1) return;
-  float v[U];
   for (int k = 0; k < f.npoles; k++) {
     const float p = f.pole[k], g = f.gain;
     float X = iir_icc(f, c, M, k);
     if (k == 0) X = g * X;
     c(0) = X;
-    for (int n0 = 1; n0 < M; n0 += U) {
-      const int cnt = min(U, M - n0);
-#pragma unroll
-      for (int u = 0; u < U; u++)
-        if (u < cnt) v[u] = c(n0 + u);
-#pragma unroll
-      for (int u = 0; u < U; u++)
-        if (u < cnt) {
-          X = (k == 0) ? g * v[u] + p * X : v[u] + p * X;
-          v[u] = X;
-        }
-#pragma unroll
-      for (int u = 0; u < U; u++)
-        if (u < cnt) c(n0 + u) = v[u];
-    }
+    if (k == 0)
+      iir_sweep<U, 1>(c, 1, M - 1, [&](float v) { X = g * v + p * X; return X; });
+    else
+      iir_sweep<U, 1>(c, 1, M - 1, [&](float v) { X = v + p * X; return X; });
     X = iir_iacc(f, c, M, k);
     c(M - 1) = X;
-    for (int n0 = M - 2; n0 >= 0; n0 -= U) {
-      const int cnt = min(U, n0 + 1);
-#pragma unroll
-      for (int u = 0; u < U; u++)
-        if (u < cnt) v[u] = c(n0 - u);
-#pragma unroll
-      for (int u = 0; u < U; u++)
-        if (u < cnt) {
-          X = p * (X - v[u]);
-          v[u] = X;
-        }
-#pragma unroll
-      for (int u = 0; u < U; u++)
-        if (u < cnt) c(n0 - u) = v[u];
-    }
+    iir_sweep<U, -1>(c, M - 2, M - 1, [&](float v) { X = p * (X - v); return X; });
   }
 }
 
@@ -243,10 +259,77 @@ __global__ void __launch_bounds__(IIR_R* NCH) k_iir_x_tiled(float* core, int str
   }
 }
 
+// lines along x, row-resident: a block pulls its rows WHOLE into shared memory - one bulk
+// asynchronous copy per row (cp.async.bulk -> mbarrier complete_tx, the TMA engine) - runs every
+// pole's causal and anticausal recursion there, one thread per (row, channel) line, and writes
+// the rows back with one bulk copy each. HBM sees every float once in each direction (the tiled
+// kernel above moves it twice per pole), and no thread ever waits for HBM inside the recursion.
+// What bounds it is the recursion's dependent multiply-add chain (2 x w steps per pole) times
+// the lines that fit an SM's shared memory, so the launcher sizes blocks for two per SM: one
+// computes while the other one's copies are in flight.
+// Rows are copied as the 16-byte-aligned span around the core row (`lead` floats before it, the
+// span rounded up to a granule): those few brace floats belong to the same container row and
+// come back unchanged. Row pitch in shared memory = span + 4 floats, so that the lines of
+// consecutive rows start four banks apart.
+__device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int NCH>
+struct SmemLineAcc {
+  float* base;
+  __device__ __forceinline__ float& operator()(int n) { return base[n * NCH]; }
+};
+template <int NCH>
+__global__ void k_iir_x_rows(float* core, int stride, int w, int h, IirDev f, int rpb, int lead, int span) {
+  extern __shared__ __align__(128) float srows[];
+  __shared__ __align__(8) uint64_t mbar;
+  const int tid = threadIdx.x;
+  const int y0 = blockIdx.x * rpb;
+  const int nrows = min(rpb, h - y0);
+  const int spitch = span + 4;
+  const uint32_t bar = st_smem_u32(&mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(nrows * span) * 4u)
+                 : "memory");
+  }
+  __syncthreads();
+  float* const g0 = core - lead + (ptrdiff_t)y0 * stride;
+  for (int r = tid; r < nrows; r += blockDim.x)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     st_smem_u32(srows + r * spitch)),
+                 "l"(g0 + (ptrdiff_t)r * stride), "r"((uint32_t)span * 4u), "r"(bar)
+                 : "memory");
+  uint32_t landed;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(landed)
+        : "r"(bar)
+        : "memory");
+  } while (!landed);
+  if (tid < nrows * NCH) {
+    SmemLineAcc<NCH> line{srows + (tid / NCH) * spitch + lead + (tid % NCH)};
+    iir_line<8>(f, line, w);
+  }
+  // the rows were written through the generic proxy; the bulk store reads them through the async one
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  for (int r = tid; r < nrows; r += blockDim.x)
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g0 + (ptrdiff_t)r * stride),
+                 "r"(st_smem_u32(srows + r * spitch)), "r"((uint32_t)span * 4u)
+                 : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the reads
+}
+
 // lines along y: one thread per float of a row (column x channel): consecutive threads touch
 // consecutive addresses at every step of the recursion -> fully coalesced. n_sections > 1:
 // the container is a stack of sections of height h that are filtered separately (cubemap IR).
-__global__ void k_iir_y(float* core, int stride, int rowfloats, int h, int n_sections, IirDev f) {
+__global__ void __launch_bounds__(64, 8) k_iir_y(float* core, int stride, int rowfloats, int h, int n_sections, IirDev f) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rowfloats * n_sections) return;
   int s = i / rowfloats, x = i % rowfloats;
@@ -254,7 +337,7 @@ __global__ void k_iir_y(float* core, int stride, int rowfloats, int h, int n_sec
   iir_line<16>(f, a, h);
 }
 
-__global__ void k_iir_y_spherical(float* core, int stride, int nch, int w, int h, IirDev f) {
+__global__ void __launch_bounds__(64, 8) k_iir_y_spherical(float* core, int stride, int nch, int w, int h, IirDev f) {
   int half = w / 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= half * nch) return;
@@ -403,7 +486,39 @@ __global__ void k_alpha_apply(const float* __restrict__ raw, int native_nch, con
 }
 
 // ---- launchers -----------------------------------------------------------------------------
+template <int NCH>
+static bool launch_iir_x_rows(float* core, int stride, int w, int h, const IirDev& f, cudaStream_t st) {
+  if ((stride & 3) || ((uintptr_t)core & 3)) return false;
+  const int lead = (int)(((uintptr_t)core & 15) / 4);
+  const int span = (lead + w * NCH + 3) & ~3;
+  const size_t row_bytes = (size_t)(span + 4) * sizeof(float);
+  const size_t budget = (228 * 1024 - 2 * 1024) / 2 - 64;  // two blocks per SM
+  int rpb = (int)(budget / row_bytes);
+  if (rpb < 2) return false;  // too few lines per SM to hide the chain: the tiled kernel streams instead
+  rpb = std::min(rpb, 256 / NCH);
+  rpb = std::min(rpb, std::max(2, (h + 295) / 296));  // small rasters: spread the rows over the SMs
+  const int threads = ((rpb * NCH + 31) / 32) * 32;
+  const size_t smem = (size_t)rpb * row_bytes;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(k_iir_x_rows<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess)
+      return false;
+    configured = true;
+  }
+  k_iir_x_rows<NCH><<<(h + rpb - 1) / rpb, threads, smem, st>>>(core, stride, w, h, f, rpb, lead, span);
+  return true;
+}
+
 cudaError_t eu_launch_iir_x(float* core, int stride, int nch, int w, int h, const IirDev& f, cudaStream_t st) {
+  if (w == 1 || f.npoles < 1) return cudaSuccess;
+  bool done = false;
+  switch (nch) {
+    case 1: done = launch_iir_x_rows<1>(core, stride, w, h, f, st); break;
+    case 2: done = launch_iir_x_rows<2>(core, stride, w, h, f, st); break;
+    case 3: done = launch_iir_x_rows<3>(core, stride, w, h, f, st); break;
+    case 4: done = launch_iir_x_rows<4>(core, stride, w, h, f, st); break;
+  }
+  if (done) return cudaGetLastError();
   int nb = (h + IIR_R - 1) / IIR_R;
   switch (nch) {
     case 1: k_iir_x_tiled<1><<<nb, IIR_R * 1, 0, st>>>(core, stride, w, h, f); break;
