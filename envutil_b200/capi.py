@@ -61,7 +61,7 @@ class Tap(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("render_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
-                ("launches", C.c_int32), ("reserved", C.c_int32)]
+                ("launches", C.c_int32), ("shape", C.c_int32)]
 
 
 class AlphaSpec(C.Structure):

@@ -371,7 +371,7 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     for (int i = 0; i < nf; i++) F[i].hdr_kind = (i == lo) ? EU_HDR_LOW : (i == hi) ? EU_HDR_HIGH : EU_HDR_MIDDLE;
   }
   P.f0 = F[first];
-  P.use_tiles = o->reserved[1] == 1 ? 0 : 1;
+  P.use_tiles = (o->reserved[1] & 1) ? 0 : 1;
   P.src_cw = sources[first]->cw;
   P.src_ch = sources[first]->chh;
   P.src_lx = sources[first]->lx;
@@ -431,6 +431,22 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     if (mode == EU_MODE_SINGLE && i != first) continue;
     if (F[i].generic || sources[i]->nch != nch || sources[i]->tstride != P.tstride) P.any_generic = 1;
   }
+  // a compiled-in job shape (plan.h: eu_render_specs): the target and every facet that is
+  // evaluated must agree with all values the entry fixes
+  P.spec = 0;
+  for (int sp = 1; sp < EU_N_SPECS && !P.spec; sp++) {
+    const RenderSpec& rs = eu_render_specs[sp];
+    bool fits = (rs.tproj < 0 || rs.tproj == P.trg.projection) && (rs.tnorm < 0 || rs.tnorm == P.trg.normalize);
+    for (int i = 0; i < nf && fits; i++) {
+      if (mode == EU_MODE_SINGLE && i != first) continue;
+      const FacetDev& f = F[i];
+      fits = !f.has_lcp && !f.generic && (rs.skind < 0 || rs.skind == f.kind) &&
+             (rs.sproj < 0 || rs.sproj == f.projection) && (rs.bc0 < 0 || rs.bc0 == f.src.bc0) &&
+             (rs.bc1 < 0 || rs.bc1 == f.src.bc1) && (rs.mask_always < 0 || rs.mask_always == f.mask_always);
+    }
+    if (fits) P.spec = sp;
+  }
+  if (o->reserved[1] & 2) P.spec = 0;  // back-end option: general kernels only
   {
     int d = o->spline_degree;
     for (int row = 0; row <= d; row++)
@@ -690,7 +706,7 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
     t->h2d_ms = host ? copy_ms : 0.0f;
     t->d2h_ms = 0;
     t->launches = launches;
-    t->reserved = 0;
+    t->shape = 0;
   }
   guard.s = nullptr;  // from here on the registry owns it
   g.sources.push_back(s);
@@ -851,7 +867,8 @@ int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets, const
   plan.P.out = d_out;
   plan.P.index_out = nullptr;
   if (timing) CK(cudaEventRecord(g.ev[0], caller));
-  CK(eu_launch_render(plan.P, caller));
+  int shape = 0;
+  CK(eu_launch_render(plan.P, caller, &shape));
   plan.launches++;
   if (timing) {
     CK(cudaEventRecord(g.ev[1], caller));
@@ -861,7 +878,7 @@ int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets, const
     timing->render_ms = ms;
     timing->h2d_ms = timing->d2h_ms = 0;
     timing->launches = plan.launches;
-    timing->reserved = 0;
+    timing->shape = shape;
   }
   return EU_OK;
 }
@@ -953,7 +970,7 @@ int eu_job_wait(eu_job_h job, eu_timing_t* timing) {
     CK(cudaEventElapsedTime(&timing->d2h_ms, J.rendered, J.done));  // includes waiting for the download stream
     timing->h2d_ms = 0;
     timing->launches = J.launches;
-    timing->reserved = 0;
+    timing->shape = 0;
   }
   return EU_OK;
 }

@@ -20,6 +20,35 @@
 
 enum { CM_LEFT = 0, CM_RIGHT = 1, CM_TOP = 2, CM_BOTTOM = 3, CM_FRONT = 4, CM_BACK = 5 };
 
+// a job's target / facet with the fields a compiled-in shape fixes (plan.h: eu_render_specs)
+// replaced by constants, so that the switches on them below fold away
+template <int SP>
+__device__ __forceinline__ void dev_spec_target(TargetDev& T) {
+  constexpr RenderSpec s = eu_render_specs[SP];
+  if constexpr (s.tproj >= 0) T.projection = s.tproj;
+  if constexpr (s.tnorm >= 0) T.normalize = s.tnorm;
+}
+template <int SP>
+__device__ __forceinline__ void dev_spec_facet(FacetDev& F) {
+  constexpr RenderSpec s = eu_render_specs[SP];
+  if constexpr (s.skind >= 0) F.kind = s.skind;
+  if constexpr (s.sproj >= 0) F.projection = s.sproj;
+  if constexpr (s.bc0 >= 0) F.src.bc0 = s.bc0;
+  if constexpr (s.bc1 >= 0) F.src.bc1 = s.bc1;
+  if constexpr (s.mask_always >= 0) F.mask_always = s.mask_always;
+  if constexpr (SP != 0) F.has_lcp = 0;
+}
+template <int SP>
+__device__ __forceinline__ decltype(auto) dev_facet_at(const FacetDev* __restrict__ fa, int i) {
+  if constexpr (SP == 0) {
+    return (fa[i]);
+  } else {
+    FacetDev F = fa[i];
+    dev_spec_facet<SP>(F);
+    return F;
+  }
+}
+
 __device__ __forceinline__ float dev_norm3(const float v[3]) {  // zimt/xel.h:752-765
   float sqn = v[0] * v[0];
   sqn += v[1] * v[1];

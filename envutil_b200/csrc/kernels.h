@@ -21,7 +21,10 @@ cudaError_t eu_launch_render_c2(const RenderParams& P, cudaStream_t st);
 cudaError_t eu_launch_render_c3(const RenderParams& P, cudaStream_t st);
 cudaError_t eu_launch_render_c3p(const RenderParams& P, cudaStream_t st);
 cudaError_t eu_launch_render_c4(const RenderParams& P, cudaStream_t st);
-cudaError_t eu_launch_render(const RenderParams& P, cudaStream_t st);
+// kernels compiled for one job shape (render_spec.cu); false: none fits, use the general ones
+bool eu_launch_render_spec(const RenderParams& P, cudaStream_t st);
+// spec_used (optional): index of the compiled-in job shape whose kernel ran, 0 = a general kernel
+cudaError_t eu_launch_render(const RenderParams& P, cudaStream_t st, int* spec_used = nullptr);
 
 // staging (stage.cu). `core` is texel (0,0) of the core inside the container.
 cudaError_t eu_launch_iir_x(float* core, int stride, int nch, int w, int h, const IirDev& f, cudaStream_t st);

@@ -69,6 +69,29 @@ struct TargetDev {
   float unbrighten;          // --single: colour channels of the result are multiplied by this (work(), :481-511)
 };
 
+// Job shapes with kernels compiled for them: where the table gives a value the kernel folds the
+// reference's run-time switch on it (stepper of the target projection, ray -> source coordinate
+// functor, boundary gates) into straight-line code; -1 = read from the job as usual. A job
+// matches an entry if its target and EVERY facet it evaluates agree with all fixed values and no
+// facet has lens correction (pto_planar). Entry 0 = nothing fixed. Same arithmetic either way.
+struct RenderSpec {
+  int tproj, tnorm;        // TargetDev.projection / .normalize
+  int skind, sproj;        // FacetDev.kind / .projection
+  int bc0, bc1;            // SourceDev.bc0 / .bc1
+  int mask_always;         // FacetDev.mask_always
+};
+#define EU_N_SPECS 8
+constexpr RenderSpec eu_render_specs[EU_N_SPECS] = {
+    {-1, -1, -1, -1, -1, -1, -1},
+    {0 /*spherical*/, -1, EU_SRC_CUBEMAP, -1, EU_BC_REFLECT, EU_BC_REFLECT, 1},      // 1: cubemap -> spherical
+    {0 /*spherical*/, -1, EU_SRC_BIATAN6, -1, EU_BC_REFLECT, EU_BC_REFLECT, 1},      // 2: biatan6 -> spherical
+    {2 /*rectilinear*/, 0, EU_SRC_MOUNT, 0, EU_BC_PERIODIC, EU_BC_REFLECT, -1},     // 3: full lat/lon -> rectilinear view
+    {6 /*biatan6*/, 0, EU_SRC_MOUNT, 0, EU_BC_PERIODIC, EU_BC_REFLECT, -1},         // 4: full lat/lon -> biatan6 cubemap
+    {4 /*fisheye*/, -1, EU_SRC_MOUNT, 0, EU_BC_PERIODIC, EU_BC_REFLECT, -1},        // 5: full lat/lon -> fisheye
+    {2 /*rectilinear*/, 1, EU_SRC_MOUNT, 2, EU_BC_REFLECT, EU_BC_REFLECT, 0},       // 6: rectilinear facets -> rectilinear (hdr_merge of brackets)
+    {0 /*spherical*/, -1, EU_SRC_MOUNT, 2, EU_BC_REFLECT, EU_BC_REFLECT, 0},        // 7: rectilinear facets -> spherical panorama
+};
+
 struct RenderParams {
   TargetDev trg;
   FacetDev f0;              // the facet of single-facet jobs (constant bank)
@@ -86,6 +109,7 @@ struct RenderParams {
   int32_t tstride;    // floats per texel in HBM: nch, or 4 (padded RGB); same for all facets
   int32_t any_generic;  // the general build is needed: some facet uses the generic stepper (translation) or
                         // differs from the job in channel count / texel stride
+  int32_t spec;       // index into eu_render_specs the job matches (0: none)
   int32_t use_tiles;  // 1: stage the gather footprint in shared memory where the kernel supports it
   int32_t src_cw, src_ch;  // container shape of f0's source in texels (tile path)
   int32_t src_lx, src_ly;  // its left / top brace: core texel (0,0) is container texel (lx, ly)

@@ -42,9 +42,14 @@ cudaError_t eu_launch_planar_tables(const TargetDev& T, float2* d_col, float2* d
   return cudaGetLastError();
 }
 
-cudaError_t eu_launch_render(const RenderParams& P, cudaStream_t st) {
+cudaError_t eu_launch_render(const RenderParams& P, cudaStream_t st, int* spec_used) {
+  if (spec_used) *spec_used = 0;
   // the general build (any_generic) ignores the compile-time texel stride, any TU of the right
   // channel count serves it
+  if (eu_launch_render_spec(P, st)) {
+    if (spec_used) *spec_used = P.spec;
+    return cudaGetLastError();
+  }
   if (P.nch == 1) return eu_launch_render_c1(P, st);
   if (P.nch == 2) return eu_launch_render_c2(P, st);
   if (P.nch == 3 && (P.tstride == 3 || P.any_generic)) return eu_launch_render_c3(P, st);

@@ -24,6 +24,27 @@ __device__ __forceinline__ int first_lane_column(int x) {
   return seg0 + (x - seg0) % EU_LANES;
 }
 
+// the job's target and first facet as the kernel sees them: the parameter block itself (SP 0), or
+// copies with the fields of the compiled-in shape replaced by constants
+template <int SP>
+struct SpecView {
+  TargetDev t;
+  FacetDev f;
+  __device__ __forceinline__ explicit SpecView(const RenderParams& P) : t(P.trg), f(P.f0) {
+    dev_spec_target<SP>(t);
+    dev_spec_facet<SP>(f);
+  }
+  __device__ __forceinline__ const TargetDev& trg() const { return t; }
+  __device__ __forceinline__ const FacetDev& f0() const { return f; }
+};
+template <>
+struct SpecView<0> {
+  const RenderParams& p;
+  __device__ __forceinline__ explicit SpecView(const RenderParams& P) : p(P) {}
+  __device__ __forceinline__ const TargetDev& trg() const { return p.trg; }
+  __device__ __forceinline__ const FacetDev& f0() const { return p.f0; }
+};
+
 // the ray of one facet for a pixel: the projection's own stepper, or the generic stepper for
 // facets with translation. which: 0 = r00, 1 = r10 (x-biased), 2 = r01 (y-biased)
 struct PixelTerms {
@@ -61,18 +82,18 @@ __device__ __forceinline__ int dev_eval_facet(const RenderParams& P, const Facet
 // `active`: this lane renders a pixel. Only VORONOI_PLUS needs it: the reference takes a shortcut
 // per 16-lane zimt vector there, which is voted on by the half-warp, so every lane of the warp
 // must walk through the code (a warp is 32 consecutive pixels of one row = two zimt vectors).
-template <int NCH, int TS, int MODE, int DEG, bool GEN, typename RayFn>
-__device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDev* __restrict__ fa, RayFn ray_of,
-                                            bool active, float px[NCH]) {
+template <int NCH, int TS, int MODE, int DEG, bool GEN, int SP, typename RayFn>
+__device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDev& f0, const FacetDev* __restrict__ fa,
+                                            RayFn ray_of, bool active, float px[NCH]) {
   if constexpr (MODE == EU_MODE_SINGLE) {
     float r[3];
     ray_of(0, r);
-    return dev_eval_facet<NCH, TS, DEG, GEN>(P, P.f0, r, px);
+    return dev_eval_facet<NCH, TS, DEG, GEN>(P, f0, r, px);
   } else if constexpr (MODE == EU_MODE_VORONOI) {
     int champion = -1;
     float max_z = -FLT_MAX, best[3] = {0.f, 0.f, 0.f};
     for (int i = 0; i < P.n_facets; i++) {
-      const FacetDev& F = fa[i];
+      const FacetDev& F = dev_facet_at<SP>(fa, i);
       float r[3];
       ray_of(i, r);
       if (!dev_facet_mask(F, r)) continue;
@@ -87,7 +108,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
 #pragma unroll
       for (int c = 0; c < NCH; c++) px[c] = 0.0f;
     } else {
-      dev_eval_facet<NCH, TS, DEG, GEN>(P, fa[champion], best, px);
+      dev_eval_facet<NCH, TS, DEG, GEN>(P, dev_facet_at<SP>(fa, champion), best, px);
     }
     return champion;
   } else if constexpr (MODE == EU_MODE_HDR) {
@@ -99,7 +120,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
 #pragma unroll
     for (int c = 0; c < NCH; c++) px[c] = 0.0f;
     for (int i = 0; i < P.n_facets; i++) {
-      const FacetDev& F = fa[i];
+      const FacetDev& F = dev_facet_at<SP>(fa, i);
       float r[3];
       ray_of(i, r);
       dev_eval_facet<NCH, TS, DEG, GEN>(P, F, r, p);
@@ -137,7 +158,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
     int ids[EU_MAX_FACETS];
     int cnt = 0, next_best = -1;  // next_best: the last facet any lane of this zimt vector hit
     for (int i = 0; i < P.n_facets; i++) {
-      const FacetDev& F = fa[i];
+      const FacetDev& F = dev_facet_at<SP>(fa, i);
       float r[3];
       ray_of(i, r);
       const bool valid = active && dev_facet_mask(F, r);
@@ -166,7 +187,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
     if (try_shortcut && active) {
       float r[3];
       ray_of(top, r);
-      dev_eval_facet<NCH, TS, DEG, GEN>(P, fa[top], r, help);
+      dev_eval_facet<NCH, TS, DEG, GEN>(P, dev_facet_at<SP>(fa, top), r, help);
       have_top = true;
       opaque = help[NCH - 1] >= 1.0f;
     }
@@ -183,7 +204,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
         if (!(k == 0 && have_top)) {
           float r[3];
           ray_of(ids[k], r);
-          dev_eval_facet<NCH, TS, DEG, GEN>(P, fa[ids[k]], r, help);
+          dev_eval_facet<NCH, TS, DEG, GEN>(P, dev_facet_at<SP>(fa, ids[k]), r, help);
         }
         if (k == 0) {
 #pragma unroll
@@ -200,9 +221,12 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
 
 // GEN: some facet of the job uses the generic stepper (PanoTools translation); kept out of the
 // common instantiations because the extra per-facet branch costs ~20 % on multi-facet jobs
-template <int NCH, int TS, int MODE, bool TWINE, int DEG, bool PF, bool GEN>
+// SP: the job shape the kernel is compiled for (plan.h: eu_render_specs; 0 = any)
+template <int NCH, int TS, int MODE, bool TWINE, int DEG, bool PF, bool GEN, int SP = 0>
 __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant__ RenderParams P) {
-  const TargetDev& T = P.trg;
+  SpecView<SP> V(P);
+  const TargetDev& T = V.trg();
+  const FacetDev& f0 = V.f0();
   const FacetDev* __restrict__ fa = P.facets;
   if constexpr (PF && MODE != EU_MODE_SINGLE) {
     __shared__ __align__(16) unsigned char sfa[EU_SMEM_FACETS * sizeof(FacetDev)];
@@ -259,10 +283,10 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
   int idx;
   if constexpr (!TWINE) {
     auto ray_of = [&](int i, float r[3]) {
-      const FacetDev& F = MODE == EU_MODE_SINGLE ? P.f0 : fa[i];
-      dev_facet_ray<GEN, 0>(T, F, t, y, r);
+      if constexpr (MODE == EU_MODE_SINGLE) dev_facet_ray<GEN, 0>(T, f0, t, y, r);
+      else dev_facet_ray<GEN, 0>(T, dev_facet_at<SP>(fa, i), t, y, r);
     };
-    idx = dev_synopsis<NCH, TS, MODE, DEG, GEN>(P, fa, ray_of, active, px);
+    idx = dev_synopsis<NCH, TS, MODE, DEG, GEN, SP>(P, f0, fa, ray_of, active, px);
   } else {
     // deriv_stepper (stepper.h:1606-1694) + twine_t (twining.h:106-263) /
     // synopsis_t (envutil_payload.cc:647-690)
@@ -272,9 +296,9 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
     idx = -1;
     if constexpr (MODE == EU_MODE_SINGLE) {
       float r00[3], du[3], dv[3];
-      dev_facet_ray<GEN, 0>(T, P.f0, t, y, r00);
-      dev_facet_ray<GEN, 1>(T, P.f0, t, y, du);
-      dev_facet_ray<GEN, 2>(T, P.f0, t, y, dv);
+      dev_facet_ray<GEN, 0>(T, f0, t, y, r00);
+      dev_facet_ray<GEN, 1>(T, f0, t, y, du);
+      dev_facet_ray<GEN, 2>(T, f0, t, y, dv);
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         du[c] = du[c] - r00[c];
@@ -285,7 +309,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
         float r[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) r[c] = r00[c] + cx * du[c] + cy * dv[c];
-        int id = dev_eval_facet<NCH, TS, DEG, GEN>(P, P.f0, r, help);
+        int id = dev_eval_facet<NCH, TS, DEG, GEN>(P, f0, r, help);
         if (k == 0) idx = id;
 #pragma unroll
         for (int c = 0; c < NCH; c++) acc[c] += cw * help[c];
@@ -294,7 +318,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
       // per-facet ninepacks live in local memory; the taps loop re-reads them
       float np[EU_MAX_FACETS][9];
       for (int i = 0; i < P.n_facets; i++) {
-        const FacetDev& F = fa[i];
+        const FacetDev& F = dev_facet_at<SP>(fa, i);
         float r00[3], r10[3], r01[3];
         dev_facet_ray<GEN, 0>(T, F, t, y, r00);
         dev_facet_ray<GEN, 1>(T, F, t, y, r10);
@@ -312,7 +336,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
 #pragma unroll
           for (int c = 0; c < 3; c++) r[c] = np[i][c] + cx * np[i][3 + c] + cy * np[i][6 + c];
         };
-        int id = dev_synopsis<NCH, TS, MODE, DEG, GEN>(P, fa, ray_of, active, help);
+        int id = dev_synopsis<NCH, TS, MODE, DEG, GEN, SP>(P, f0, fa, ray_of, active, help);
         if (k == 0) idx = id;
 #pragma unroll
         for (int c = 0; c < NCH; c++) acc[c] += cw * help[c];
@@ -383,7 +407,7 @@ __device__ __forceinline__ void bulk_row_g2s(float* dst, const float* src, uint3
                : "memory");
 }
 
-template <int NCH, int TS, bool TWINE, int DEG>
+template <int NCH, int TS, bool TWINE, int DEG, int SP = 0>
 __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_constant__ RenderParams P) {
   static_assert(DEG == 1 || DEG == 3, "tile path is built for the bilinear and cubic evaluators");
   constexpr int ORDER = DEG + 1, H2 = DEG / 2;
@@ -393,8 +417,9 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
   __shared__ int box[4];  // A0 (float offset in the container row), first container row, floats per row, rows
   __shared__ __align__(8) uint64_t mbar;
 
-  const TargetDev& T = P.trg;
-  const FacetDev& F = P.f0;
+  SpecView<SP> V(P);
+  const TargetDev& T = V.trg();
+  const FacetDev& F = V.f0();
   const SourceDev& S = F.src;
   const int tid = threadIdx.y * TILE_X + threadIdx.x;
   const int x = blockIdx.x * TILE_X + threadIdx.x;

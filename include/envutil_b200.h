@@ -99,7 +99,8 @@ typedef struct eu_opts {
   int32_t solo;             /* -1, or the single facet to show; forced to 0 for one facet */
   int32_t support_min;      /* cubemap IR support, default 8  (envutil_main.cc:458) */
   int32_t tile_size;        /* cubemap IR tile size, default 64 (envutil_main.cc:457) */
-  int32_t reserved[2];
+  int32_t reserved[2];      /* back-end options, 0 = defaults. [0] 1: 16-byte RGB texels in HBM; [1] bit 0: no
+                               shared-memory footprint staging, bit 1: no kernels compiled for one job shape */
 } eu_opts_t;
 
 /* One twining tap: sub-pixel offset in units of the target's pixel step and weight
@@ -113,7 +114,8 @@ typedef struct eu_timing {
   float h2d_ms;     /* host->device copies inside the call (0 for device entry points) */
   float d2h_ms;
   int32_t launches; /* kernels launched by the call */
-  int32_t reserved;
+  int32_t shape;    /* eu_render / eu_render_rows: index of the compiled-in job shape whose kernel rendered
+                       (0: a general kernel); 0 from the other entry points */
 } eu_timing_t;
 
 /* Alpha from PTO: exclude masks (k-lines, variant t0) and the lens crop of an i-line (S clause)

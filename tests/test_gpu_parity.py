@@ -67,6 +67,29 @@ def test_padded_texel_layout_is_bit_exact(engine, name):
     assert harness.compare(out, harness.oracle_render(job))["n_diff"] == 0
 
 
+# job -> the compiled-in job shape (plan.h: eu_render_specs) whose kernel must have rendered it
+SHAPED = {"cm_sph_d1": 1, "cm_sph_d3": 1, "cm_sph_d3_rot": 1, "cm_sph_d1_support4_tile16": 1, "ba6_sph_d1": 2,
+          "ll_rect_d1": 3, "ll_rect_d1_rot": 3, "ll_rect_d3_rot": 3, "ll_rect_d1_oddangles": 3, "ll_ba6_d1": 4,
+          "ll_fish_d1_tw4": 5, "hdr3_rect_d1": 6, "voronoi4_sph_d1": 7, "win_voronoi_sph_d1": 7,
+          # same projections, but outside what the shape kernels were compiled for -> general kernels
+          "ba6_sph_d3_rot": 0, "cm100_sph_d2": 0, "ll_fish_d3_rot": 0, "lens3_voronoi_sph_d1": 0, "llpart_rect_d3": 0,
+          "voronoi4_sph_d3_rot": 0, "grey_cm_sph_d1_tw2": 0, "rgba_cm_sph_d1": 0, "tr1_sph_d1": 0}
+
+
+@pytest.mark.parametrize("name", sorted(SHAPED))
+def test_shape_kernels_and_general_kernels_agree(engine, name):
+    """Jobs of the commonest shapes run kernels with the target projection / source kind / gates
+    compiled in (render_spec.cu); no_spec forces the general kernels. Both equal the oracle bit for
+    bit, and the library reports which one ran."""
+    ref = harness.oracle_render(jobs.JOBS[name])
+    for no_spec in (False, True):
+        job = copy.copy(jobs.JOBS[name])
+        job.no_spec = no_spec
+        out = engine.render(job)
+        assert engine.last_timing.shape == (0 if no_spec else SHAPED[name]), (name, no_spec, engine.last_timing.shape)
+        assert harness.compare(out, ref)["n_diff"] == 0, (name, no_spec)
+
+
 @pytest.mark.parametrize("name", ["ll_rect_d1_rot", "ll_rect_d3_rot", "cm_sph_d3", "ba6_sph_d1", "ll_fish_d1_tw4",
                                   "ll_cube_d1", "cm_rect_d1_tw3_rot", "lens1_rect_d3_tw2", "grey_ll_rect_d3"])
 @pytest.mark.parametrize("padded", [False, True])
