@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--partition", default="frames", choices=["frames", "bands"],
                     help="N > 1: frames = one full frame per rank per step (weak scaling, default); bands = the ranks "
                          "split ONE frame into row bands, gathered on rank 0 over NCCL (strong scaling)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="bands: peer = every rank's render kernel stores its band straight into rank 0's frame over "
+                         "NVLink (eu_frame_*; render and gather are one kernel, default); nccl = band buffers + gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: min(steps, 5))")
     return ap.parse_args()
@@ -313,12 +316,19 @@ def ours(args):
     stage_launches = eng.last_stage_timing[0].launches
     from envutil_b200 import bands as eu_bands
     row0, row1 = eu_bands.band(H, world, rank) if bands_mode else (0, H)
-    d_out = torch.empty((row1 - row0, W, C), dtype=torch.float32, device=dev)
+    peer = None
+    if bands_mode and args.gather == "peer":
+        peer = eu_bands.PeerFrame(eng.lib, dist, H, W, C, rank, world)
+        out_ptr = peer.band_ptr(row0)
+        d_out = None
+    else:
+        d_out = torch.empty((row1 - row0, W, C), dtype=torch.float32, device=dev)
+        out_ptr = d_out.data_ptr()
     setup_s = time.perf_counter() - t_setup
 
     # ---- device-timed render: W warm-up launches, then exactly K, events on the launch stream
     for _ in range(max(args.warmup, 3)):
-        eng.render_rows(job, hs, st, row0, row1, d_out.data_ptr(), stream, timed=False)
+        eng.render_rows(job, hs, st, row0, row1, out_ptr, stream, timed=False)
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     if sampler:  # nvidia-smi takes a moment to deliver its first sample
@@ -331,7 +341,7 @@ def ours(args):
     tw0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        eng.render_rows(job, hs, st, row0, row1, d_out.data_ptr(), stream, timed=False)
+        eng.render_rows(job, hs, st, row0, row1, out_ptr, stream, timed=False)
     ev1.record()
     barrier()
     tw1 = time.perf_counter()
@@ -345,9 +355,12 @@ def ours(args):
     if sampler:
         time.sleep(0.15)
         clocks = ClockSampler.summarise(sampler.window(tw0, tw1))
-    checksum = float(d_out[::64, ::64].double().sum().item())
     gather_ms = 0.0
-    if bands_mode:  # output bands gathered on rank 0 (NCCL), timed on its own: not part of `value`
+    if peer is not None:  # the timed launches already left every band in rank 0's frame (barrier above)
+        checksum = float(peer.as_tensor()[::64, ::64].double().sum().item()) if rank == 0 else 0.0
+    else:
+        checksum = float(d_out[::64, ::64].double().sum().item())
+    if bands_mode and peer is None:  # output bands gathered on rank 0 (NCCL), timed on its own: not part of `value`
         full = eu_bands.gather_bands(d_out, H, world, rank, dist)  # first use sets up the NCCL channels
         del full
         barrier()
@@ -364,10 +377,20 @@ def ours(args):
 
     # ---- e2e: host buffers through the C ABI, H2D + staging + render + D2H every step ----
     e2e_steps = args.e2e_steps or max(1, min(args.steps, 5))
+    peer_ok = None
     if bands_mode:  # the e2e leg renders full frames through eu_render; compare against a full device frame
         d_out = torch.empty((H, W, C), dtype=torch.float32, device=dev)
         eng.render_rows(job, hs, st, 0, H, d_out.data_ptr(), stream, timed=False)
         torch.cuda.synchronize()
+        if peer is not None:
+            if rank == 0:  # the frame assembled by the ranks' peer stores equals one GPU's full render
+                peer_ok = bool(torch.equal(peer.as_tensor(), d_out))
+            barrier()
+            if rank != 0:
+                peer.close()
+            barrier()
+            if rank == 0:
+                peer.close()
     h_out = torch.empty((H, W, C), dtype=torch.float32).pin_memory()
     import ctypes as Ct
     from envutil_b200 import capi
@@ -473,7 +496,11 @@ def ours(args):
             "clocks": clocks,
             "staging": {"ms": stage_ms, "launches": stage_launches,
                         "what": "cubemap IR build + support fill + per-section prefilter (device-timed, outside value)"},
-            "multi_gpu": {"broadcast_ms": bcast_ms, "gather_ms": gather_ms, "collectives_in_timed_region": 0},
+            "multi_gpu": {"broadcast_ms": bcast_ms, "gather_ms": gather_ms, "collectives_in_timed_region": 0,
+                          "gather": (("peer stores over NVLink into rank 0's frame inside the timed render kernels "
+                                      "(eu_frame_*), no band buffers") if peer_ok is not None else
+                                     ("NCCL gather of band buffers, timed separately" if bands_mode else None)),
+                          "peer_frame_equals_single_gpu_render": peer_ok},
             "cpu_baseline": cpu, "checksum": checksum, "setup_s": setup_s,
         }
         print(json.dumps(line))

@@ -29,3 +29,48 @@ def gather_bands(local, height, world, rank, dist, dst=0):
         return None
     parts = [out[r][: b[1] - b[0]] for r, b in enumerate(bands(height, world))]
     return torch.cat(parts, dim=0)
+
+
+class PeerFrame:
+    """One frame in the HBM of rank `dst` that every rank renders its row band into (fused render +
+    gather: the kernel's stores travel over NVLink, include/envutil_b200.h eu_frame_*). The owner
+    allocates and exports, the handle travels through torch.distributed's object broadcast (any
+    backend), the other ranks open it. band_ptr(row0) is the d_out to hand to eu_render_rows."""
+
+    def __init__(self, lib, dist, height, width, nch, rank, world, dst=0):
+        import ctypes as C
+        from . import capi
+        self.lib, self.rank, self.dst, self.row_bytes = lib, rank, dst, width * nch * 4
+        self.height, self.width, self.nch = height, width, nch
+        self.ptr = C.c_void_p()
+        box = [None]
+        if rank == dst:
+            capi.check(lib.eu_frame_alloc(height * width * nch, C.byref(self.ptr)), lib)
+            buf = C.create_string_buffer(64)
+            capi.check(lib.eu_frame_export(self.ptr, buf), lib)
+            box[0] = buf.raw
+        if world > 1:
+            dist.broadcast_object_list(box, src=dst)
+        if rank != dst:
+            capi.check(lib.eu_frame_open(box[0], C.byref(self.ptr)), lib)
+
+    def band_ptr(self, row0):
+        return self.ptr.value + row0 * self.row_bytes
+
+    def as_tensor(self):
+        """The whole frame as a CUDA tensor (owner only; valid until close())."""
+        import torch
+        assert self.rank == self.dst
+        class _Mem:  # __cuda_array_interface__ carrier
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (self.height, self.width, self.nch), "typestr": "<f4",
+                                      "data": (self.ptr.value, False), "version": 3, "strides": None}
+        return torch.as_tensor(m, device="cuda")
+
+    def close(self):
+        from . import capi
+        if self.ptr.value:
+            fn = self.lib.eu_frame_free if self.rank == self.dst else self.lib.eu_frame_close
+            capi.check(fn(self.ptr), self.lib)
+            self.ptr.value = None

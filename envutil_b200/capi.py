@@ -111,6 +111,11 @@ SYMBOLS = {
     "eu_render_async": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet), C.POINTER(SourceH),
                                   C.POINTER(Tap), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "eu_job_wait": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
+    "eu_frame_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "eu_frame_free": (C.c_int, [C.c_void_p]),
+    "eu_frame_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "eu_frame_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "eu_frame_close": (C.c_int, [C.c_void_p]),
     "eu_debug_planes": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
                                   C.POINTER(SourceH), C.c_void_p]),
 }

@@ -996,4 +996,53 @@ int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
   return EU_OK;
 }
 
+// ---- frames shared between the processes of one box (CUDA IPC) -----------------------------
+int eu_frame_alloc(size_t n_floats, float** d_frame) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!d_frame || n_floats == 0) return fail(EU_ERR_ARGUMENT, "null argument");
+  // cudaMalloc, not the stream-ordered pool: pool memory cannot be exported with cudaIpcGetMemHandle
+  CK(cudaMalloc((void**)d_frame, n_floats * sizeof(float)));
+  return EU_OK;
+}
+
+int eu_frame_free(float* d_frame) {
+  int rc = need_up();
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  CK(cudaFree(d_frame));
+  return EU_OK;
+}
+
+int eu_frame_export(const float* d_frame, unsigned char handle[EU_FRAME_HANDLE_BYTES]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == EU_FRAME_HANDLE_BYTES, "handle size");
+  int rc = need_up();
+  if (rc) return rc;
+  if (!d_frame || !handle) return fail(EU_ERR_ARGUMENT, "null argument");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, const_cast<float*>(d_frame)));
+  memcpy(handle, &h, sizeof(h));
+  return EU_OK;
+}
+
+int eu_frame_open(const unsigned char handle[EU_FRAME_HANDLE_BYTES], float** d_frame) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!d_frame || !handle) return fail(EU_ERR_ARGUMENT, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *d_frame = static_cast<float*>(p);
+  return EU_OK;
+}
+
+int eu_frame_close(float* d_frame) {
+  int rc = need_up();
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());  // no store of ours may still be in flight towards the owner
+  CK(cudaIpcCloseMemHandle(d_frame));
+  return EU_OK;
+}
+
 }  // extern "C"

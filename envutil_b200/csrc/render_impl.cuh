@@ -24,6 +24,37 @@ __device__ __forceinline__ int first_lane_column(int x) {
   return seg0 + (x - seg0) % EU_LANES;
 }
 
+// The pixel store (zimt/put.h:122-135: interleaved NCH-tuples). RGB pixels are 12 bytes: written
+// per lane that is three 4-byte stores scattered over the warp's 384 contiguous bytes. Where the
+// warp is complete and its span 16-byte aligned, the pixels go through a 384-byte shared-memory
+// slot of the warp and leave as 24 128-bit stores - a third of the store instructions and full
+// 32-byte sectors per request, which matters most when `out` is a peer GPU's frame (NVLink).
+template <int NCH>
+__device__ __forceinline__ void dev_store_pixel(const RenderParams& P, const TargetDev& T, int x, int y,
+                                                const float px[NCH], float* wslot) {
+  float* dst = P.out + ((size_t)(y - P.row0) * T.width + x) * NCH;
+  if constexpr (NCH == 4) {
+    *reinterpret_cast<float4*>(dst) = make_float4(px[0], px[1], px[2], px[3]);
+  } else if constexpr (NCH == 3) {
+    const int lane = threadIdx.x;  // TILE_X == 32: a warp is one row of the tile
+    const bool vec = ((T.width & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) &&
+                     (blockIdx.x * TILE_X + TILE_X <= T.width);  // warp-uniform
+    if (vec) {
+      wslot[lane * 3] = px[0];
+      wslot[lane * 3 + 1] = px[1];
+      wslot[lane * 3 + 2] = px[2];
+      __syncwarp();
+      if (lane < 24)
+        reinterpret_cast<float4*>(dst - lane * 3)[lane] = reinterpret_cast<const float4*>(wslot)[lane];
+    } else {
+      dst[0] = px[0]; dst[1] = px[1]; dst[2] = px[2];
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < NCH; c++) dst[c] = px[c];
+  }
+}
+
 // the job's target and first facet as the kernel sees them: the parameter block itself (SP 0), or
 // copies with the fields of the compiled-in shape replaced by constants
 template <int SP>
@@ -228,6 +259,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
   const TargetDev& T = V.trg();
   const FacetDev& f0 = V.f0();
   const FacetDev* __restrict__ fa = P.facets;
+  __shared__ __align__(16) float wslot[TILE_Y][NCH == 3 ? TILE_X * 3 : 4];  // dev_store_pixel
   if constexpr (PF && MODE != EU_MODE_SINGLE) {
     __shared__ __align__(16) unsigned char sfa[EU_SMEM_FACETS * sizeof(FacetDev)];
     static_assert(sizeof(FacetDev) % 4 == 0, "FacetDev is copied word by word");
@@ -352,15 +384,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
     for (int c = 0; c < NCOL; c++) px[c] *= T.unbrighten;
   }
   size_t o = (size_t)(y - P.row0) * T.width + x;
-  if (P.out) {
-    float* dst = P.out + o * NCH;
-    if constexpr (NCH == 4) {
-      *reinterpret_cast<float4*>(dst) = make_float4(px[0], px[1], px[2], px[3]);
-    } else {
-#pragma unroll
-      for (int c = 0; c < NCH; c++) dst[c] = px[c];
-    }
-  }
+  if (P.out) dev_store_pixel<NCH>(P, T, x, y, px, wslot[threadIdx.y]);
   if (P.index_out) P.index_out[o] = idx;
 }
 
@@ -414,6 +438,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
   constexpr int NWARP = TILE_X * TILE_Y / 32;
   __shared__ __align__(128) float tile[EU_TILE_FLOATS];
   __shared__ int red[NWARP][4];
+  __shared__ __align__(16) float wslot[TILE_Y][NCH == 3 ? TILE_X * 3 : 4];  // dev_store_pixel
   __shared__ int box[4];  // A0 (float offset in the container row), first container row, floats per row, rows
   __shared__ __align__(8) uint64_t mbar;
 
@@ -561,13 +586,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
 #pragma unroll
     for (int c = 0; c < NCOL; c++) px[c] *= T.unbrighten;
   }
-  float* dst = P.out + ((size_t)(y - P.row0) * T.width + x) * NCH;
-  if constexpr (NCH == 4) {
-    *reinterpret_cast<float4*>(dst) = make_float4(px[0], px[1], px[2], px[3]);
-  } else {
-#pragma unroll
-    for (int c = 0; c < NCH; c++) dst[c] = px[c];
-  }
+  dev_store_pixel<NCH>(P, T, x, y, px, wslot[threadIdx.y]);
 }
 
 template <int NCH, int TS, int MODE, bool TWINE>

@@ -228,6 +228,21 @@ int eu_render_async(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
                     const eu_source_h* sources, const eu_tap_t* taps, int n_taps, float* out, eu_job_h* job);
 int eu_job_wait(eu_job_h job, eu_timing_t* timing);
 
+/* Frames shared between the GPUs of one box ("output bands gathered"). The rank that
+ * wants the whole frame allocates it and exports a handle; the other ranks (one process per
+ * GPU) open the handle and pass `frame + row0*width*nchannels` as d_out of eu_render_rows: the
+ * render kernel then stores its band straight into the owner's HBM over NVLink (peer stores,
+ * 128-bit for RGB) - rendering and gathering are one kernel, there is no band buffer and no
+ * collective. The owner may read the frame once every rank has synchronised its stream (the
+ * host's barrier). CUDA IPC underneath: the handle is EU_FRAME_HANDLE_BYTES opaque bytes that
+ * travel through any host channel (torch.distributed, a pipe, MPI). */
+#define EU_FRAME_HANDLE_BYTES 64
+int eu_frame_alloc(size_t n_floats, float** d_frame);
+int eu_frame_free(float* d_frame);
+int eu_frame_export(const float* d_frame, unsigned char handle[EU_FRAME_HANDLE_BYTES]);
+int eu_frame_open(const unsigned char handle[EU_FRAME_HANDLE_BYTES], float** d_frame);
+int eu_frame_close(float* d_frame);
+
 /* Index plane for bit-exact parity checks: per target pixel the cube face hit (single cubemap
  * facet) or the winning facet of the panorama synopsis (-1: no facet hit). Host buffer w*h. */
 int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets,
