@@ -157,6 +157,9 @@ struct StrideAcc {
   float* base;
   ptrdiff_t st;
   __device__ __forceinline__ float& operator()(int n) { return base[(ptrdiff_t)n * st]; }
+  __device__ __forceinline__ float* ptr(int n) { return base + (ptrdiff_t)n * st; }
+  __device__ __forceinline__ bool linear(int, int) { return true; }  // elements n0..n1 are evenly spaced
+  __device__ __forceinline__ ptrdiff_t delta(int) { return st; }     // floats from element n to n+1
 };
 // [left-half column top->bottom ; right-half column bottom->top], environment.h:425-447
 struct PoleAcc {
@@ -167,7 +170,88 @@ struct PoleAcc {
   __device__ __forceinline__ float& operator()(int n) {
     return n < h ? up[(ptrdiff_t)n * st] : down[-(ptrdiff_t)(n - h) * st];
   }
+  __device__ __forceinline__ float* ptr(int n) { return n < h ? up + (ptrdiff_t)n * st : down - (ptrdiff_t)(n - h) * st; }
+  __device__ __forceinline__ bool linear(int n0, int n1) { return (n0 < h) == (n1 < h); }
+  __device__ __forceinline__ ptrdiff_t delta(int n) { return n < h ? st : -st; }
 };
+
+// ---- lines along y through a shared-memory prefetch ring -----------------------------------
+// One thread per column float, as before, but the loads no longer pass through registers: every
+// thread keeps IIRY_D elements of its line in flight as 4-byte cp.async copies into its own column
+// of a [IIRY_D][blockDim.x] ring (committed in groups of IIRY_G rows), waits for the oldest group,
+// runs the recursion over it, stores the results and refills the slots. A thread only ever reads
+// what it copied itself, so cp.async.wait_group is all the synchronisation there is. Bytes in
+// flight per SM = lines x IIRY_D x 4 - set by shared memory, not by the register file, which is
+// what held the register-prefetching version at a third of the HBM roofline.
+#define IIRY_D 64
+#define IIRY_G 8
+#define IIRY_THREADS 64
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+template <int DIR, typename Acc, typename Step>
+__device__ __forceinline__ void iir_sweep_ring(Acc& c, int start, int count, Step step, float* ring) {
+  // element j of the sweep = c(start + DIR * j); its ring slot = ring[(j % IIRY_D) * IIRY_THREADS]
+#pragma unroll 1
+  for (int g0 = 0; g0 < IIRY_D; g0 += IIRY_G) {
+#pragma unroll
+    for (int u = 0; u < IIRY_G; u++)
+      if (g0 + u < count) cp_async4(ring + (g0 + u) * IIRY_THREADS, c.ptr(start + DIR * (g0 + u)));
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+#pragma unroll 1
+  for (int j0 = 0; j0 < count; j0 += IIRY_G) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(IIRY_D / IIRY_G - 1) : "memory");
+    float* slot = ring + (j0 & (IIRY_D - 1)) * IIRY_THREADS;
+    float v[IIRY_G];
+#pragma unroll
+    for (int u = 0; u < IIRY_G; u++) v[u] = slot[u * IIRY_THREADS];  // stale beyond count: never used
+    const int ns = start + DIR * j0, nl = start + DIR * (j0 + IIRY_D);
+    if (j0 + IIRY_D + IIRY_G <= count && c.linear(ns, ns + DIR * (IIRY_G - 1)) && c.linear(nl, nl + DIR * (IIRY_G - 1))) {
+      // steady state: the group and its refill are complete and evenly spaced - two pointers
+      // and immediate multiples of the line's step, no bounds checks
+      float* ps = c.ptr(ns);
+      const float* pl = c.ptr(nl);
+      const int ds = (int)c.delta(ns) * DIR, dl = (int)c.delta(nl) * DIR;  // 32-bit: one IMAD.WIDE per address
+#pragma unroll
+      for (int u = 0; u < IIRY_G; u++) v[u] = step(v[u]);
+#pragma unroll
+      for (int u = 0; u < IIRY_G; u++) ps[u * ds] = v[u];
+#pragma unroll
+      for (int u = 0; u < IIRY_G; u++) cp_async4(slot + u * IIRY_THREADS, pl + u * dl);
+    } else {
+#pragma unroll
+      for (int u = 0; u < IIRY_G; u++)
+        if (j0 + u < count) v[u] = step(v[u]);
+#pragma unroll
+      for (int u = 0; u < IIRY_G; u++)
+        if (j0 + u < count) *c.ptr(start + DIR * (j0 + u)) = v[u];
+#pragma unroll
+      for (int u = 0; u < IIRY_G; u++)
+        if (j0 + IIRY_D + u < count) cp_async4(slot + u * IIRY_THREADS, c.ptr(start + DIR * (j0 + IIRY_D + u)));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+template <typename Acc>
+__device__ __forceinline__ void iir_line_ring(const IirDev& f, Acc& c, int M, float* ring) {
+  if (M == 1 || f.npoles < 1) return;
+  for (int k = 0; k < f.npoles; k++) {
+    const float p = f.pole[k], g = f.gain;
+    float X = iir_icc(f, c, M, k);
+    if (k == 0) X = g * X;
+    c(0) = X;
+    if (k == 0)
+      iir_sweep_ring<1>(c, 1, M - 1, [&](float v) { X = g * v + p * X; return X; }, ring);
+    else
+      iir_sweep_ring<1>(c, 1, M - 1, [&](float v) { X = v + p * X; return X; }, ring);
+    X = iir_iacc(f, c, M, k);
+    c(M - 1) = X;
+    iir_sweep_ring<-1>(c, M - 2, M - 1, [&](float v) { X = p * (X - v); return X; }, ring);
+  }
+}
 
 // lines along x: one thread per (row, channel). A warp covers 32 consecutive rows of one
 // channel; each thread walks its row, so a 32-B sector fetched for texel n is reused for the
@@ -329,20 +413,22 @@ __global__ void k_iir_x_rows(float* core, int stride, int w, int h, IirDev f, in
 // lines along y: one thread per float of a row (column x channel): consecutive threads touch
 // consecutive addresses at every step of the recursion -> fully coalesced. n_sections > 1:
 // the container is a stack of sections of height h that are filtered separately (cubemap IR).
-__global__ void __launch_bounds__(64, 8) k_iir_y(float* core, int stride, int rowfloats, int h, int n_sections, IirDev f) {
+__global__ void __launch_bounds__(IIRY_THREADS) k_iir_y(float* core, int stride, int rowfloats, int h, int n_sections, IirDev f) {
+  __shared__ float ring[IIRY_D * IIRY_THREADS];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rowfloats * n_sections) return;
   int s = i / rowfloats, x = i % rowfloats;
   StrideAcc a{core + (ptrdiff_t)s * h * stride + x, stride};
-  iir_line<16>(f, a, h);
+  iir_line_ring(f, a, h, ring + threadIdx.x);
 }
 
-__global__ void __launch_bounds__(64, 8) k_iir_y_spherical(float* core, int stride, int nch, int w, int h, IirDev f) {
+__global__ void __launch_bounds__(IIRY_THREADS) k_iir_y_spherical(float* core, int stride, int nch, int w, int h, IirDev f) {
+  __shared__ float ring[IIRY_D * IIRY_THREADS];
   int half = w / 2;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= half * nch) return;
   PoleAcc a{core + i, core + (ptrdiff_t)(h - 1) * stride + (ptrdiff_t)half * nch + i, stride, h};
-  iir_line<16>(f, a, 2 * h);
+  iir_line_ring(f, a, 2 * h, ring + threadIdx.x);
 }
 
 // brace: every container texel outside the core is a copy of a core texel (PERIODIC / REFLECT
@@ -492,17 +578,20 @@ static bool launch_iir_x_rows(float* core, int stride, int w, int h, const IirDe
   const int lead = (int)(((uintptr_t)core & 15) / 4);
   const int span = (lead + w * NCH + 3) & ~3;
   const size_t row_bytes = (size_t)(span + 4) * sizeof(float);
-  const size_t budget = (228 * 1024 - 2 * 1024) / 2 - 64;  // two blocks per SM
+  size_t budget = (228 * 1024 - 2 * 1024) / 2 - 64;  // two blocks per SM
+  if (row_bytes > budget) budget = 226 * 1024;        // very wide rows: one block per SM, one row each
   int rpb = (int)(budget / row_bytes);
-  if (rpb < 2) return false;  // too few lines per SM to hide the chain: the tiled kernel streams instead
+  if (rpb < 1) return false;  // a row does not fit an SM's shared memory: the tiled kernel streams it
   rpb = std::min(rpb, 256 / NCH);
-  rpb = std::min(rpb, std::max(2, (h + 295) / 296));  // small rasters: spread the rows over the SMs
+  rpb = std::min(rpb, std::max(1, (h + 295) / 296));  // small rasters: spread the rows over the SMs
   const int threads = ((rpb * NCH + 31) / 32) * 32;
   const size_t smem = (size_t)rpb * row_bytes;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(k_iir_x_rows<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_iir_x_rows<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
+      cudaGetLastError();  // not sticky: the tiled kernel takes over
       return false;
+    }
     configured = true;
   }
   k_iir_x_rows<NCH><<<(h + rpb - 1) / rpb, threads, smem, st>>>(core, stride, w, h, f, rpb, lead, span);
@@ -535,13 +624,13 @@ cudaError_t eu_launch_iir_x(float* core, int stride, int nch, int w, int h, cons
 cudaError_t eu_launch_iir_y(float* core, int stride, int nch, int w, int h, int n_sections, const IirDev& f,
                             cudaStream_t st) {
   int n = w * nch * n_sections;
-  k_iir_y<<<(n + 63) / 64, 64, 0, st>>>(core, stride, w * nch, h, n_sections, f);
+  k_iir_y<<<(n + IIRY_THREADS - 1) / IIRY_THREADS, IIRY_THREADS, 0, st>>>(core, stride, w * nch, h, n_sections, f);
   return cudaGetLastError();
 }
 cudaError_t eu_launch_iir_y_spherical(float* core, int stride, int nch, int w, int h, const IirDev& f,
                                       cudaStream_t st) {
   int n = (w / 2) * nch;
-  k_iir_y_spherical<<<(n + 63) / 64, 64, 0, st>>>(core, stride, nch, w, h, f);
+  k_iir_y_spherical<<<(n + IIRY_THREADS - 1) / IIRY_THREADS, IIRY_THREADS, 0, st>>>(core, stride, nch, w, h, f);
   return cudaGetLastError();
 }
 cudaError_t eu_launch_brace(float* core, int stride, int nch, int w, int h, int lx, int rx, int ly, int ry, int bc0,
