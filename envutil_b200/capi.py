@@ -106,6 +106,12 @@ SYMBOLS = {
     "eu_render_rows": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
                                  C.POINTER(SourceH), C.POINTER(Tap), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                  C.c_void_p, C.POINTER(Timing)]),
+    "eu_render_rows_pitched": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
+                                         C.POINTER(SourceH), C.POINTER(Tap), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_int, C.c_void_p, C.POINTER(Timing)]),
+    "eu_source_reserve": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.POINTER(SourceH),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "eu_source_commit": (C.c_int, [SourceH, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p, C.POINTER(Timing)]),
     "eu_source_upload_async": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p,
                                          C.POINTER(SourceH)]),
     "eu_render_async": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet), C.POINTER(SourceH),

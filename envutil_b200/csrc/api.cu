@@ -455,6 +455,50 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   return EU_OK;
 }
 
+// source_t ctor, environment.h:594-950: shape, boundary conditions and brace of a mounted image's container
+void mount_layout(const eu_facet_t* f, int degree, eu_source* s) {
+  const int nch = f->nchannels;
+  s->kind = EU_SRC_MOUNT;
+  s->w = f->window_width;   // the raster handed in is the window ('W' clause, envutil_main.cc:754-786);
+  s->h = f->window_height;  // the geometry refers to the total size
+  s->bc0 = s->bc1 = EU_BC_REFLECT;
+  if ((f->projection == EU_SPHERICAL || f->projection == EU_CYLINDRICAL) && fabs(f->hfov - 2.0 * M_PI) < .000001)
+    s->bc0 = EU_BC_PERIODIC;
+  s->lx = left_brace(degree, s->bc0);
+  s->ly = left_brace(degree, s->bc1);
+  s->rx = right_brace(degree, s->bc0);
+  s->ry = right_brace(degree, s->bc1);
+  s->cw = s->w + s->lx + s->rx;
+  s->chh = s->h + s->ly + s->ry;
+  s->pitch = (s->cw * nch + 3) & ~3;
+}
+
+// the core of a mounted image is in place: prefilter (degree > 1) and brace
+int mount_finish(const eu_facet_t* f, int pdeg, eu_source* s, cudaStream_t st, int* launches) {
+  const int nch = f->nchannels, stride = s->pitch;
+  float* core = s->container + (size_t)s->ly * stride + (size_t)s->lx * nch;
+  bool sphere = is_full_sphere(f);
+  if (sphere && (s->ly > s->h || s->ry > s->h)) return fail(EU_ERR_ARGUMENT, "image too small for its brace");
+  if (pdeg > 1) {
+    IirDev fx, fy;
+    if (sphere) {  // spherical_prefilter, environment.h:356-522 (tolerance 1e-4)
+      iir_setup(fx, EU_BC_PERIODIC, pdeg, (long double)0.0001, s->w);
+      iir_setup(fy, EU_BC_PERIODIC, pdeg, (long double)0.0001, 2 * s->h);
+      CK(eu_launch_iir_x(core, stride, nch, s->w, s->h, fx, st));
+      CK(eu_launch_iir_y_spherical(core, stride, nch, s->w, s->h, fy, st));
+    } else {  // zimt::prefilter, prefilter.h:125-198
+      iir_setup(fx, s->bc0, pdeg, (long double)FLT_EPSILON, s->w);
+      iir_setup(fy, s->bc1, pdeg, (long double)FLT_EPSILON, s->h);
+      CK(eu_launch_iir_x(core, stride, nch, s->w, s->h, fx, st));
+      CK(eu_launch_iir_y(core, stride, nch, s->w, s->h, 1, fy, st));
+    }
+    *launches += 2;
+  }
+  CK(eu_launch_brace(core, stride, nch, s->w, s->h, s->lx, s->rx, s->ly, s->ry, s->bc0, s->bc1, sphere ? 1 : 0, st));
+  *launches += 1;
+  return EU_OK;
+}
+
 // `pixels` is a device pointer (kind = DeviceToDevice) or a host pointer (HostToDevice): the
 // raster is copied straight into its place inside the container, there is no staging copy.
 // `cpst`: the stream the placement copies run on (the staging stream itself, or the upload stream
@@ -512,20 +556,7 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
     }
     return EU_OK;
   }
-  // source_t ctor, environment.h:594-950
-  s->kind = EU_SRC_MOUNT;
-  s->w = f->window_width;   // the raster handed in is the window ('W' clause, envutil_main.cc:754-786);
-  s->h = f->window_height;  // the geometry refers to the total size
-  s->bc0 = s->bc1 = EU_BC_REFLECT;
-  if ((f->projection == EU_SPHERICAL || f->projection == EU_CYLINDRICAL) && fabs(f->hfov - 2.0 * M_PI) < .000001)
-    s->bc0 = EU_BC_PERIODIC;
-  s->lx = left_brace(degree, s->bc0);
-  s->ly = left_brace(degree, s->bc1);
-  s->rx = right_brace(degree, s->bc0);
-  s->ry = right_brace(degree, s->bc1);
-  s->cw = s->w + s->lx + s->rx;
-  s->chh = s->h + s->ly + s->ry;
-  s->pitch = (s->cw * nch + 3) & ~3;
+  mount_layout(f, degree, s);
   size_t n = (size_t)s->pitch * s->chh;
   CK(pool_alloc(&s->container, n, cpst));
   int stride = s->pitch;
@@ -534,26 +565,7 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
   CK(cudaMemcpy2DAsync(core, (size_t)stride * sizeof(float), d_pixels, (size_t)s->w * tb, (size_t)s->w * tb, s->h, kind,
                        cpst));
   CK(copies_end());
-  bool sphere = is_full_sphere(f);
-  if (sphere && (s->ly > s->h || s->ry > s->h)) return fail(EU_ERR_ARGUMENT, "image too small for its brace");
-  if (pdeg > 1) {
-    IirDev fx, fy;
-    if (sphere) {  // spherical_prefilter, environment.h:356-522 (tolerance 1e-4)
-      iir_setup(fx, EU_BC_PERIODIC, pdeg, (long double)0.0001, s->w);
-      iir_setup(fy, EU_BC_PERIODIC, pdeg, (long double)0.0001, 2 * s->h);
-      CK(eu_launch_iir_x(core, stride, nch, s->w, s->h, fx, st));
-      CK(eu_launch_iir_y_spherical(core, stride, nch, s->w, s->h, fy, st));
-    } else {  // zimt::prefilter, prefilter.h:125-198
-      iir_setup(fx, s->bc0, pdeg, (long double)FLT_EPSILON, s->w);
-      iir_setup(fy, s->bc1, pdeg, (long double)FLT_EPSILON, s->h);
-      CK(eu_launch_iir_x(core, stride, nch, s->w, s->h, fx, st));
-      CK(eu_launch_iir_y(core, stride, nch, s->w, s->h, 1, fy, st));
-    }
-    *launches += 2;
-  }
-  CK(eu_launch_brace(core, stride, nch, s->w, s->h, s->lx, s->rx, s->ly, s->ry, s->bc0, s->bc1, sphere ? 1 : 0, st));
-  *launches += 1;
-  return EU_OK;
+  return mount_finish(f, pdeg, s, st, launches);
 }
 
 // optional 16-byte texel layout for RGB sources (o->reserved[0] == 1): one LDG.128 per tap
@@ -849,6 +861,14 @@ int eu_source_download(eu_source_h s, float* out) {
 int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
                    const eu_source_h* sources, const eu_tap_t* taps, int n_taps, int row0, int row1, float* d_out,
                    void* cuda_stream, eu_timing_t* timing) {
+  if (!t) return fail(EU_ERR_ARGUMENT, "null argument");
+  return eu_render_rows_pitched(t, o, n_facets, facets, sources, taps, n_taps, row0, row1, d_out,
+                                t->width * t->nchannels, cuda_stream, timing);
+}
+
+int eu_render_rows_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+                           const eu_source_h* sources, const eu_tap_t* taps, int n_taps, int row0, int row1,
+                           float* d_out, int out_pitch_floats, void* cuda_stream, eu_timing_t* timing) {
   int rc = need_up();
   if (rc) return rc;
   Plan plan;
@@ -856,6 +876,7 @@ int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets, const
   if (rc) return rc;
   if (row0 < 0 || row1 > t->height || row0 >= row1) return fail(EU_ERR_ARGUMENT, "bad row band [%d,%d)", row0, row1);
   if (!d_out) return fail(EU_ERR_ARGUMENT, "null output");
+  if (out_pitch_floats < t->width * t->nchannels) return fail(EU_ERR_ARGUMENT, "output pitch %d is shorter than a row", out_pitch_floats);
   cudaStream_t caller = (cudaStream_t)cuda_stream;
   if (caller != g.stream)
     for (int i = 0; i < n_facets; i++) sources[i]->foreign_use = true;
@@ -865,6 +886,7 @@ int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets, const
   plan.P.row0 = row0;
   plan.P.row1 = row1;
   plan.P.out = d_out;
+  plan.P.out_pitch = out_pitch_floats;
   plan.P.index_out = nullptr;
   if (timing) CK(cudaEventRecord(g.ev[0], caller));
   int shape = 0;
@@ -940,6 +962,7 @@ int eu_render_async(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
   plan.P.row0 = 0;
   plan.P.row1 = t->height;
   plan.P.out = J.d_out;
+  plan.P.out_pitch = t->width * t->nchannels;
   plan.P.index_out = nullptr;
   CK(cudaEventRecord(J.start, g.stream));
   CK(eu_launch_render(plan.P, g.stream));
@@ -989,10 +1012,74 @@ int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
   plan.P.row0 = 0;
   plan.P.row1 = t->height;
   plan.P.out = nullptr;
+  plan.P.out_pitch = t->width * t->nchannels;
   plan.P.index_out = g.d_index;
   CK(eu_launch_render(plan.P, g.stream));
   CK(cudaMemcpyAsync(index_out, g.d_index, n * sizeof(int32_t), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
+  return EU_OK;
+}
+
+// ---- a source whose raster is produced on the device, in place -----------------------------
+int eu_source_reserve(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, eu_source_h* out, float** d_core,
+                      int* pitch_floats) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!f || !o || !out || !d_core || !pitch_floats) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (f->projection == EU_CUBEMAP || f->projection == EU_BIATAN6)
+    return fail(EU_ERR_UNSUPPORTED, "eu_source_reserve is for single images (a cubemap's faces are re-arranged on upload)");
+  if (f->width <= 0 || f->height <= 0 || f->nchannels < 1 || f->nchannels > 4 || f->window_width <= 0 || f->window_height <= 0)
+    return fail(EU_ERR_ARGUMENT, "bad raster description (run eu_facet_prepare)");
+  if (o->spline_degree < 0 || o->spline_degree > EU_MAX_DEGREE) return fail(EU_ERR_ARGUMENT, "spline degree out of range");
+  eu_source* s = new eu_source();
+  s->container = nullptr;
+  s->last_used_cycle = g.cycle;
+  s->refs = 1;
+  s->foreign_use = false;
+  s->projection = f->projection;
+  s->nch = f->nchannels;
+  s->degree = o->spline_degree;
+  s->tstride = f->nchannels;
+  mount_layout(f, o->spline_degree, s);
+  cudaError_t e = pool_alloc(&s->container, (size_t)s->pitch * s->chh);
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(EU_ERR_CUDA, "container: %s", cudaGetErrorString(e));
+  }
+  g.sources.push_back(s);
+  if (asset_key && *asset_key) {
+    s->key = asset_key;
+    g.by_key[s->key] = s;
+  }
+  *out = s;
+  *d_core = s->container + (size_t)s->ly * s->pitch + (size_t)s->lx * s->nch;
+  *pitch_floats = s->pitch;
+  return EU_OK;
+}
+
+int eu_source_commit(eu_source_h s, const eu_facet_t* f, const eu_opts_t* o, void* cuda_stream, eu_timing_t* t) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!s || !f || !o) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (!known_source(s)) return fail(EU_ERR_ARGUMENT, "not a live source handle");
+  if (s->kind != EU_SRC_MOUNT) return fail(EU_ERR_ARGUMENT, "not a reserved single-image source");
+  int pdeg = o->prefilter_degree < 0 ? o->spline_degree : o->prefilter_degree;
+  if (pdeg > EU_MAX_DEGREE) return fail(EU_ERR_ARGUMENT, "prefilter degree %d out of range", pdeg);
+  cudaStream_t caller = (cudaStream_t)cuda_stream, st = g.stream;
+  CK(cudaEventRecord(g.ev[2], caller));  // the rows were written on the caller's stream
+  CK(cudaStreamWaitEvent(st, g.ev[2], 0));
+  int launches = 0;
+  CK(cudaEventRecord(g.ev[0], st));
+  rc = mount_finish(f, pdeg, s, st, &launches);
+  if (rc) return rc;
+  CK(cudaEventRecord(g.ev[1], st));
+  CK(cudaStreamSynchronize(st));
+  if (t) {
+    CK(cudaEventElapsedTime(&t->render_ms, g.ev[0], g.ev[1]));
+    t->h2d_ms = t->d2h_ms = 0;
+    t->launches = launches;
+    t->shape = 0;
+  }
   return EU_OK;
 }
 

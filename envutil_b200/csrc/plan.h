@@ -116,5 +116,6 @@ struct RenderParams {
   const float* src_base;   // first float of f0's container (256-byte aligned, rows 16-byte aligned)
   int32_t row0, row1;  // rows rendered by this launch
   float* out;          // first float of row `row0`
+  int32_t out_pitch;   // floats from one output row to the next (width * nch for a dense band)
   int32_t* index_out;  // optional index plane (face / winning facet)
 };

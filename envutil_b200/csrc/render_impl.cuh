@@ -32,12 +32,16 @@ __device__ __forceinline__ int first_lane_column(int x) {
 template <int NCH>
 __device__ __forceinline__ void dev_store_pixel(const RenderParams& P, const TargetDev& T, int x, int y,
                                                 const float px[NCH], float* wslot) {
-  float* dst = P.out + ((size_t)(y - P.row0) * T.width + x) * NCH;
+  float* dst = P.out + (size_t)(y - P.row0) * P.out_pitch + (size_t)x * NCH;
   if constexpr (NCH == 4) {
-    *reinterpret_cast<float4*>(dst) = make_float4(px[0], px[1], px[2], px[3]);
+    if (((P.out_pitch & 3) | (int)(reinterpret_cast<uintptr_t>(P.out) & 15)) == 0) {
+      *reinterpret_cast<float4*>(dst) = make_float4(px[0], px[1], px[2], px[3]);
+    } else {
+      dst[0] = px[0]; dst[1] = px[1]; dst[2] = px[2]; dst[3] = px[3];
+    }
   } else if constexpr (NCH == 3) {
     const int lane = threadIdx.x;  // TILE_X == 32: a warp is one row of the tile
-    const bool vec = ((T.width & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) &&
+    const bool vec = ((P.out_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) &&
                      (blockIdx.x * TILE_X + TILE_X <= T.width);  // warp-uniform
     if (vec) {
       wslot[lane * 3] = px[0];

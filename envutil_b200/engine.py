@@ -62,6 +62,33 @@ class Engine:
             self.launches += tm.launches
         return hs
 
+    # ---- sources produced on the device, in place (eu_source_reserve / eu_source_commit) -----
+    def reserve(self, facet_struct, opts):
+        """Container of a single-image source whose raster a render will write; returns
+        (handle, device address of core texel (0,0), row pitch in floats)."""
+        h, core, pitch = capi.SourceH(), C.c_void_p(), C.c_int()
+        capi.check(self.lib.eu_source_reserve(None, C.byref(facet_struct), C.byref(opts), C.byref(h), C.byref(core),
+                                              C.byref(pitch)), self.lib)
+        return h, core.value, pitch.value
+
+    def render_rows_pitched(self, job, sources, structs, row0, row1, d_out, pitch_floats, stream=0, timed=True):
+        t, fa, o, taps, ntaps = structs
+        tm = capi.Timing()
+        capi.check(self.lib.eu_render_rows_pitched(C.byref(t), C.byref(o), len(job.facets), fa, sources, taps, ntaps,
+                                                   row0, row1, C.c_void_p(d_out), pitch_floats, C.c_void_p(stream),
+                                                   C.byref(tm) if timed else None), self.lib)
+        self.launches += tm.launches if timed else 1
+        if timed:
+            self.last_timing = tm
+        return tm
+
+    def commit(self, handle, facet_struct, opts, stream=0):
+        tm = capi.Timing()
+        capi.check(self.lib.eu_source_commit(handle, C.byref(facet_struct), C.byref(opts), C.c_void_p(stream), C.byref(tm)),
+                   self.lib)
+        self.launches += tm.launches
+        return tm
+
     def release(self, handles):
         for h in handles:
             if h:

@@ -213,6 +213,24 @@ int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets,
                    const eu_facet_t* facets, const eu_source_h* sources, const eu_tap_t* taps,
                    int n_taps, int row0, int row1, float* d_out, void* cuda_stream,
                    eu_timing_t* timing);
+/* same, with the output rows `out_pitch_floats` apart (>= width*nchannels): renders into a larger
+ * raster in place - e.g. into the core of a reserved source, below */
+int eu_render_rows_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facets,
+                           const eu_facet_t* facets, const eu_source_h* sources, const eu_tap_t* taps,
+                           int n_taps, int row0, int row1, float* d_out, int out_pitch_floats,
+                           void* cuda_stream, eu_timing_t* timing);
+/* A source whose raster is produced on the device: two-stage jobs (BASELINE configs[4]: hdr_merge
+ * of a position's brackets, then the panorama over the merged images) hand the first stage's result
+ * to the second without an intermediate raster and without the placement copy of
+ * eu_source_upload_device. eu_source_reserve allocates the braced container of a single image
+ * (not a cubemap) and returns the device address of core texel (0,0) and the row pitch in floats;
+ * the caller fills the rows (eu_render_rows_pitched with that address and pitch), then
+ * eu_source_commit - ordered after cuda_stream's work - prefilters and braces. The handle is
+ * used and released like any other source. */
+int eu_source_reserve(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, eu_source_h* out,
+                      float** d_core, int* pitch_floats);
+int eu_source_commit(eu_source_h s, const eu_facet_t* f, const eu_opts_t* o, void* cuda_stream,
+                     eu_timing_t* t);
 /* Pipelined jobs. payload() is blocking, but a host that streams jobs (pipe mode, sequences) can
  * keep the PCIe links busy in both directions: eu_source_upload_async enqueues the H2D copy on an
  * upload stream and the staging kernels behind it, eu_render_async enqueues the render and - on a

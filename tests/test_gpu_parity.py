@@ -245,3 +245,45 @@ def test_pipelined_jobs_match_blocking_calls(engine):
     for tk in tks:
         engine.finish(tk)
     engine.lib.eu_cycle()
+
+
+@pytest.mark.parametrize("degree", [1, 3])
+def test_stage_one_renders_into_stage_two_source(engine, degree):
+    """Two-stage jobs (BASELINE configs[4]): the hdr_merge of a position's brackets is rendered straight
+    into the container of the source the panorama stage reads (eu_source_reserve +
+    eu_render_rows_pitched + eu_source_commit). The container equals the one obtained by rendering
+    into a dense raster and uploading that, and so does a panorama rendered from it."""
+    import ctypes as C
+    import torch
+    from envutil_b200.job import FacetSpec, Job
+    ja = copy.copy(jobs.JOBS["single0_hdr3_d1"])          # stage one: --synopsis hdr_merge --single 0
+    sta = ja.structs(engine.lib)
+    ta = sta[0]
+    hsa = engine.stage(ja, sta)
+    dense = torch.empty((ta.height, ta.width, ta.nchannels), dtype=torch.float32, device="cuda")
+    engine.render_rows(ja, hsa, sta, 0, ta.height, dense.data_ptr(), 0, timed=True)
+    f0 = ja.facets[0]
+    jb = Job([FacetSpec(None, f0.projection, f0.hfov, yaw=f0.yaw, pitch=f0.pitch, roll=f0.roll, width=ta.width,
+                        height=ta.height, nchannels=ta.nchannels)], "spherical", 360.0, 256, 128, degree=degree)
+    stb = jb.structs(engine.lib)
+    fb, ob = stb[1], stb[2]
+    via_upload = engine.stage_device(jb, [dense.data_ptr()], stb)
+    h, core, pitch = engine.reserve(fb[0], ob)
+    try:
+        # two bands, to exercise the row offset inside the container
+        mid = ta.height // 3
+        engine.render_rows_pitched(ja, hsa, sta, 0, mid, core, pitch, 0, timed=True)
+        engine.render_rows_pitched(ja, hsa, sta, mid, ta.height, core + mid * pitch * 4, pitch, 0, timed=True)
+        engine.commit(h, fb[0], ob)
+        got, shp = engine.container(h)
+        want, wshp = engine.container(via_upload[0])
+        assert shp == wshp
+        assert np.array_equal(got, want)  # the download strips the row padding
+        one = (type(via_upload))(h)
+        out_a = engine.render(jb, sources=one, structs=stb)
+        out_b = engine.render(jb, sources=via_upload, structs=stb)
+        assert np.array_equal(out_a, out_b)
+    finally:
+        engine.release([h])
+        engine.release(via_upload)
+        engine.release(hsa)

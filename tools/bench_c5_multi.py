@@ -171,6 +171,13 @@ def main():
     eng = Engine(local)
     stream = torch.cuda.current_stream().cuda_stream
 
+    # stage B's job description is needed first: in the stripes plan stage A renders straight into the
+    # containers of stage B's sources (eu_source_reserve / eu_render_rows_pitched / eu_source_commit)
+    fsb = [FacetSpec(None, "rectilinear", 100.0, yaw=60.0 * p, width=w, height=h, nchannels=3) for p in range(P)]
+    jobb, algb = workloads.c5_stage_b_geometry(fsb, a.scale)
+    stb = jobb.structs(eng.lib)
+    reserved = {}
+
     # ---- 2. stage A on the owners ------------------------------------------------------
     merged = {}
     a_jobs = []
@@ -186,17 +193,26 @@ def main():
             eng.release(hs)
             hs = eng.stage_device(job, [d_br[(p, b)].data_ptr() for b in range(B)], st, stream=stream)
         stage_a_ms += sum(tm.render_ms for tm in eng.last_stage_timing)
-        # full-size merged raster; the stripes plan fills rows [wr0, wr1) only (the rest is never sampled)
-        out = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
-        a_jobs.append((job, st, hs, out))
-        merged[p] = out
+        if windows_plan:
+            # the merged image IS stage B's source: rows [wr0, wr1) are rendered into its container (the
+            # other rows are never sampled by this rank's band)
+            reserved[p] = eng.reserve(stb[1][p], stb[2])
+            out = None
+        else:
+            out = torch.empty((h, w, 3), dtype=torch.float32, device=dev)
+            merged[p] = out
+        a_jobs.append((p, job, st, hs, out))
 
     def run_a():
-        for job, st, hs, out in a_jobs:
-            eng.render_rows(job, hs, st, wr0, wr1, out[wr0:].data_ptr(), stream, timed=False)
+        for p, job, st, hs, out in a_jobs:
+            if windows_plan:
+                hnd, core, pitch = reserved[p]
+                eng.render_rows_pitched(job, hs, st, wr0, wr1, core + wr0 * pitch * 4, pitch, stream, timed=False)
+            else:
+                eng.render_rows(job, hs, st, 0, h, out.data_ptr(), stream, timed=False)
     run_a()
     a_ms = timed(run_a, a.steps)
-    for job, st, hs, out in a_jobs:
+    for p, job, st, hs, out in a_jobs:
         eng.release(hs)
     d_br.clear()
 
@@ -215,15 +231,19 @@ def main():
     xchg_ms = dev_max(e0.elapsed_time(e1))
 
     # ---- 4. stage B: row bands ------------------------------------------------------------
-    fsb = [FacetSpec(None, "rectilinear", 100.0, yaw=60.0 * p, width=w, height=h, nchannels=3) for p in range(P)]
-    jobb, algb = workloads.c5_stage_b_geometry(fsb, a.scale)
-    stb = jobb.structs(eng.lib)
     H, W = stb[0].height, stb[0].width
-    t_stage = time.perf_counter()
-    hsb = eng.stage_device(jobb, [merged[p].data_ptr() for p in range(P)], stb, stream=stream)
-    eng.release(hsb)  # steady state, as above
-    hsb = eng.stage_device(jobb, [merged[p].data_ptr() for p in range(P)], stb, stream=stream)
-    stage_b_ms = sum(tm.render_ms for tm in eng.last_stage_timing)
+    if windows_plan:  # the sources are in place: brace them
+        from envutil_b200 import capi
+        hsb = (capi.SourceH * P)()
+        stage_b_ms = 0.0
+        for p in range(P):
+            stage_b_ms += eng.commit(reserved[p][0], stb[1][p], stb[2], stream).render_ms
+            hsb[p] = reserved[p][0]
+    else:
+        hsb = eng.stage_device(jobb, [merged[p].data_ptr() for p in range(P)], stb, stream=stream)
+        eng.release(hsb)  # steady state, as above
+        hsb = eng.stage_device(jobb, [merged[p].data_ptr() for p in range(P)], stb, stream=stream)
+        stage_b_ms = sum(tm.render_ms for tm in eng.last_stage_timing)
     assert (H, W) == (H_pano, W_pano)
     peer = None
     if world > 1 and a.gather == "peer":
