@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="bands: peer = every rank's render kernel stores its band straight into rank 0's frame over "
                          "NVLink (eu_frame_*; render and gather are one kernel, default); nccl = band buffers + gather")
+    ap.add_argument("--narrow-stores", type=int, default=0, help="1: 4-byte pixel stores even into a peer frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: min(steps, 5))")
     return ap.parse_args()
@@ -303,6 +304,7 @@ def ours(args):
     if not bands_mode:
         job.yaw = 360.0 * rank / world  # every rank renders its own view of the same environment
     job.padded, job.no_tiles = bool(args.padded), bool(args.no_tiles)
+    job.narrow_stores = bool(args.narrow_stores)
     eng = Engine(local)
     st = job.structs(eng.lib)
     t, fa, o, taps, ntaps = st
@@ -439,7 +441,9 @@ def ours(args):
             eng.finish(pending.pop(0))
             finish_stamps.append(time.perf_counter())
 
-    pipelined(DEPTH)
+    # warm-up until the stream-ordered pool has enough containers cycling between the upload and the
+    # staging stream (the first passes still grow it: 321 MB from the driver per job, tens of ms each)
+    pipelined(4 * DEPTH)
     barrier()
     t0 = time.perf_counter()
     pipelined(pipe_steps)

@@ -888,6 +888,22 @@ int eu_render_rows_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facet
   plan.P.out = d_out;
   plan.P.out_pitch = out_pitch_floats;
   plan.P.index_out = nullptr;
+  {  // a frame opened with eu_frame_open lives on another GPU: wide stores for the link
+    static const float* asked = nullptr;  // a band is rendered to the same address frame after frame:
+    static int answer = 0;                // the driver is asked once per address
+    if (d_out != asked) {
+      cudaPointerAttributes pa;
+      answer = 0;
+      if (cudaPointerGetAttributes(&pa, d_out) == cudaSuccess) {
+        if (pa.type == cudaMemoryTypeDevice && pa.device != g.device) answer = 1;
+      } else {
+        cudaGetLastError();
+      }
+      asked = d_out;
+    }
+    plan.P.wide_stores = answer;
+    if (o->reserved[1] & 4) plan.P.wide_stores = 0;  // back-end option: 4-byte stores everywhere
+  }
   if (timing) CK(cudaEventRecord(g.ev[0], caller));
   int shape = 0;
   CK(eu_launch_render(plan.P, caller, &shape));

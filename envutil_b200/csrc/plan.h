@@ -117,5 +117,6 @@ struct RenderParams {
   int32_t row0, row1;  // rows rendered by this launch
   float* out;          // first float of row `row0`
   int32_t out_pitch;   // floats from one output row to the next (width * nch for a dense band)
+  int32_t wide_stores; // 1: `out` is another GPU's memory - RGB pixels leave as 128-bit stores (dev_store_pixel)
   int32_t* index_out;  // optional index plane (face / winning facet)
 };
