@@ -501,6 +501,7 @@ def ours(args):
                     "blocking": {"value": world * mpix / (e2e_blocking_ms * 1e-3), "ms_per_step": e2e_blocking_ms,
                                  "scope": "eu_source_upload + eu_render, one blocking call pair per step"},
                     "ms_between_results": [round((b - a) * 1e3, 2) for a, b in zip([t0] + finish_stamps, finish_stamps)],
+                    "median_ms_between_results": float(np.median(np.diff(np.array([t0] + finish_stamps)))) * 1e3,
                     "matches_device_path": e2e_ok,
                     "breakdown_ms": {"h2d": float(np.mean([p[0].h2d_ms for p in parts])),
                                      "staging_kernels": float(np.mean([p[0].render_ms for p in parts])),

@@ -858,6 +858,9 @@ int eu_source_download(eu_source_h s, float* out) {
   return EU_OK;
 }
 
+static const float* g_peer_asked = nullptr;  // last d_out looked up with cudaPointerGetAttributes ...
+static int g_peer_answer = 0;                // ... and whether it is another GPU's memory
+
 int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
                    const eu_source_h* sources, const eu_tap_t* taps, int n_taps, int row0, int row1, float* d_out,
                    void* cuda_stream, eu_timing_t* timing) {
@@ -889,19 +892,19 @@ int eu_render_rows_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facet
   plan.P.out_pitch = out_pitch_floats;
   plan.P.index_out = nullptr;
   {  // a frame opened with eu_frame_open lives on another GPU: wide stores for the link
-    static const float* asked = nullptr;  // a band is rendered to the same address frame after frame:
-    static int answer = 0;                // the driver is asked once per address
-    if (d_out != asked) {
+    // a band is rendered to the same address frame after frame: the driver is asked once per address
+    // (the answer is dropped whenever a frame is opened, closed or freed)
+    if (d_out != g_peer_asked) {
       cudaPointerAttributes pa;
-      answer = 0;
+      g_peer_answer = 0;
       if (cudaPointerGetAttributes(&pa, d_out) == cudaSuccess) {
-        if (pa.type == cudaMemoryTypeDevice && pa.device != g.device) answer = 1;
+        if (pa.type == cudaMemoryTypeDevice && pa.device != g.device) g_peer_answer = 1;
       } else {
         cudaGetLastError();
       }
-      asked = d_out;
+      g_peer_asked = d_out;
     }
-    plan.P.wide_stores = answer;
+    plan.P.wide_stores = g_peer_answer;
     if (o->reserved[1] & 4) plan.P.wide_stores = 0;  // back-end option: 4-byte stores everywhere
   }
   if (timing) CK(cudaEventRecord(g.ev[0], caller));
@@ -1112,6 +1115,7 @@ int eu_frame_alloc(size_t n_floats, float** d_frame) {
 int eu_frame_free(float* d_frame) {
   int rc = need_up();
   if (rc) return rc;
+  g_peer_asked = nullptr;
   CK(cudaDeviceSynchronize());
   CK(cudaFree(d_frame));
   return EU_OK;
@@ -1136,6 +1140,7 @@ int eu_frame_open(const unsigned char handle[EU_FRAME_HANDLE_BYTES], float** d_f
   memcpy(&h, handle, sizeof(h));
   void* p = nullptr;
   CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  g_peer_asked = nullptr;
   *d_frame = static_cast<float*>(p);
   return EU_OK;
 }
@@ -1143,6 +1148,7 @@ int eu_frame_open(const unsigned char handle[EU_FRAME_HANDLE_BYTES], float** d_f
 int eu_frame_close(float* d_frame) {
   int rc = need_up();
   if (rc) return rc;
+  g_peer_asked = nullptr;
   CK(cudaDeviceSynchronize());  // no store of ours may still be in flight towards the owner
   CK(cudaIpcCloseMemHandle(d_frame));
   return EU_OK;
