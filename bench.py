@@ -315,6 +315,8 @@ def ours(args):
     eng.release(hs)  # the first staging grows the device pool; report the steady state
     hs = eng.stage_device(job, [d_src.data_ptr()], st, stream=stream, padded=bool(args.padded))
     stage_ms = eng.last_stage_timing[0].render_ms
+    import ctypes as _C
+    ir_bytes = 4 * int(eng.lib.eu_source_container_floats(hs[0], (_C.c_int32 * 4)()))  # the staged cubemap IR
     stage_launches = eng.last_stage_timing[0].launches
     from envutil_b200 import bands as eu_bands
     row0, row1 = eu_bands.band(H, world, rank) if bands_mode else (0, H)
@@ -510,7 +512,12 @@ def ours(args):
             "gpu_launches": int(launches) * world,
             "clocks": clocks,
             "staging": {"ms": stage_ms, "launches": stage_launches,
-                        "what": "cubemap IR build + support fill + per-section prefilter (device-timed, outside value)"},
+                        "what": "cubemap IR build + support fill + per-section prefilter (device-timed, outside value)",
+                        # the IR build reads the raster and writes the IR, the prefilter reads
+                        # and writes the IR once per axis
+                        "algorithmic_bytes": int(h_src.numel() * 4 + ir_bytes + 4 * ir_bytes),
+                        "achieved_gbs": (h_src.numel() * 4 + 5 * ir_bytes) / (stage_ms * 1e-3) / 1e9,
+                        "frac_measured_peak": (h_src.numel() * 4 + 5 * ir_bytes) / (stage_ms * 1e-3) / 1e9 / peak},
             "multi_gpu": {"broadcast_ms": bcast_ms, "gather_ms": gather_ms, "collectives_in_timed_region": 0,
                           "gather": (("peer stores over NVLink into rank 0's frame inside the timed render kernels "
                                       "(eu_frame_*), no band buffers") if peer_ok is not None else

@@ -44,7 +44,14 @@ class Target(C.Structure):
         ("gain", C.c_double),
         ("x0", C.c_double), ("x1", C.c_double), ("y0", C.c_double), ("y1", C.c_double),
         ("step", C.c_double),
+        ("crop_x0", C.c_int32), ("crop_y0", C.c_int32), ("crop_width", C.c_int32), ("crop_height", C.c_int32),
     ]
+
+    def out_shape(self):
+        """(rows, columns) of the raster a job produces: the target, or its crop."""
+        if self.crop_width > 0:
+            return self.crop_height, self.crop_width
+        return self.height, self.width
 
 
 class Opts(C.Structure):

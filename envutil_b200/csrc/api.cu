@@ -284,13 +284,21 @@ int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, Fac
 }
 
 // stepper_base ctor, stepper.h:294-306 (extents narrowed to float first, factors in double)
+// the raster a job produces: the target, or its crop (eu_target_t::crop_*)
+int out_width(const eu_target_t* t) { return t->crop_width > 0 ? t->crop_width : t->width; }
+int out_height(const eu_target_t* t) { return t->crop_width > 0 ? t->crop_height : t->height; }
+
 void target_dev(const eu_target_t* t, bool normalize, TargetDev& T) {
   memset(&T, 0, sizeof(T));
   int w = t->width, h = t->height;
   float a0 = (float)t->x0, a1 = (float)t->x1, b0 = (float)t->y0, b1 = (float)t->y1;
   T.projection = t->projection;
-  T.width = w;
-  T.height = h;
+  T.width = out_width(t);
+  T.height = out_height(t);
+  T.full_w = w;
+  T.full_h = h;
+  T.off_x = t->crop_width > 0 ? t->crop_x0 : 0;
+  T.off_y = t->crop_width > 0 ? t->crop_y0 : 0;
   T.normalize = normalize;
   T.fx1 = (float)(a1 / (2.0 * w));
   T.fx0 = (float)(a0 / (2.0 * w));
@@ -323,6 +331,14 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   if (n_taps < 0 || n_taps > EU_MAX_TAPS) return fail(EU_ERR_ARGUMENT, "tap count %d out of range", n_taps);
   if (n_taps > 0 && !taps) return fail(EU_ERR_ARGUMENT, "taps missing");
   if (t->width <= 0 || t->height <= 0) return fail(EU_ERR_ARGUMENT, "target not prepared");
+  if (t->crop_width > 0) {
+    if (t->projection == EU_CUBEMAP || t->projection == EU_BIATAN6)
+      return fail(EU_ERR_UNSUPPORTED, "cropped output of a cubemap target");
+    if (t->crop_height <= 0 || t->crop_x0 < 0 || t->crop_y0 < 0 || t->crop_x0 + t->crop_width > t->width ||
+        t->crop_y0 + t->crop_height > t->height)
+      return fail(EU_ERR_ARGUMENT, "crop %dx%d+%d+%d does not lie inside the %dx%d target", t->crop_width, t->crop_height,
+                  t->crop_x0, t->crop_y0, t->width, t->height);
+  }
   if (o->spline_degree < 0 || o->spline_degree > EU_MAX_DEGREE)
     return fail(EU_ERR_ARGUMENT, "spline degree %d out of range 0..%d", o->spline_degree, EU_MAX_DEGREE);
   int nch = t->nchannels;
@@ -408,22 +424,23 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     P.taps = g.d_taps;
   }
   // planar tables: recomputed only when the target changes
-  size_t need = 3 * (size_t)(t->width + t->height);  // float2 terms + the bare planar coordinate per entry, in float2 units
+  const int ow = out_width(t), oh = out_height(t);
+  size_t need = 3 * (size_t)(ow + oh);  // float2 terms + the bare planar coordinate per entry, in float2 units
   if (!g.planar_valid || memcmp(&g.planar_for, &P.trg, sizeof(TargetDev)) != 0 || need > g.planar_cap) {
     TargetDev key = P.trg;
     CK(cudaDeviceSynchronize());  // nothing in flight may still read the old tables
     int rc = grow(g.d_planar, g.planar_cap, need);
     if (rc) return rc;
-    CK(eu_launch_planar_tables(P.trg, g.d_planar, g.d_planar + 2 * (size_t)t->width,
-                               reinterpret_cast<float*>(g.d_planar + 2 * (size_t)(t->width + t->height)), g.stream));
+    CK(eu_launch_planar_tables(P.trg, g.d_planar, g.d_planar + 2 * (size_t)ow,
+                               reinterpret_cast<float*>(g.d_planar + 2 * (size_t)(ow + oh)), g.stream));
     plan.launches++;
     g.planar_for = key;
     g.planar_valid = true;
   }
   // normalize is part of TargetDev but does not change the tables; keep the key exact anyway
   P.col_tab = g.d_planar;
-  P.row_tab = g.d_planar + 2 * (size_t)t->width;
-  P.planar_raw = reinterpret_cast<const float*>(g.d_planar + 2 * (size_t)(t->width + t->height));
+  P.row_tab = g.d_planar + 2 * (size_t)ow;
+  P.planar_raw = reinterpret_cast<const float*>(g.d_planar + 2 * (size_t)(ow + oh));
   // the specialised kernels assume every facet they touch has the job's channel count and one
   // texel stride; anything else (and translation) runs the general build
   P.any_generic = 0;
@@ -866,7 +883,7 @@ int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets, const
                    void* cuda_stream, eu_timing_t* timing) {
   if (!t) return fail(EU_ERR_ARGUMENT, "null argument");
   return eu_render_rows_pitched(t, o, n_facets, facets, sources, taps, n_taps, row0, row1, d_out,
-                                t->width * t->nchannels, cuda_stream, timing);
+                                out_width(t) * t->nchannels, cuda_stream, timing);
 }
 
 int eu_render_rows_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
@@ -877,9 +894,9 @@ int eu_render_rows_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facet
   Plan plan;
   rc = build_plan(t, o, n_facets, facets, sources, taps, n_taps, (cudaStream_t)cuda_stream, plan);
   if (rc) return rc;
-  if (row0 < 0 || row1 > t->height || row0 >= row1) return fail(EU_ERR_ARGUMENT, "bad row band [%d,%d)", row0, row1);
+  if (row0 < 0 || row1 > out_height(t) || row0 >= row1) return fail(EU_ERR_ARGUMENT, "bad row band [%d,%d)", row0, row1);
   if (!d_out) return fail(EU_ERR_ARGUMENT, "null output");
-  if (out_pitch_floats < t->width * t->nchannels) return fail(EU_ERR_ARGUMENT, "output pitch %d is shorter than a row", out_pitch_floats);
+  if (out_pitch_floats < out_width(t) * t->nchannels) return fail(EU_ERR_ARGUMENT, "output pitch %d is shorter than a row", out_pitch_floats);
   cudaStream_t caller = (cudaStream_t)cuda_stream;
   if (caller != g.stream)
     for (int i = 0; i < n_facets; i++) sources[i]->foreign_use = true;
@@ -930,11 +947,11 @@ int eu_render(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_f
   if (rc) return rc;
   if (!t || !out) return fail(EU_ERR_ARGUMENT, "null argument");
   if (t->width <= 0 || t->height <= 0 || t->nchannels < 1) return fail(EU_ERR_ARGUMENT, "target not prepared");
-  size_t n = (size_t)t->width * t->height * t->nchannels;
+  size_t n = (size_t)out_width(t) * out_height(t) * t->nchannels;
   rc = grow(g.d_out, g.out_cap, n);
   if (rc) return rc;
   eu_timing_t tm;
-  rc = eu_render_rows(t, o, n_facets, facets, sources, taps, n_taps, 0, t->height, g.d_out, g.stream, &tm);
+  rc = eu_render_rows(t, o, n_facets, facets, sources, taps, n_taps, 0, out_height(t), g.d_out, g.stream, &tm);
   if (rc) return rc;
   CK(cudaEventRecord(g.ev[2], g.stream));
   CK(cudaMemcpyAsync(out, g.d_out, n * sizeof(float), cudaMemcpyDeviceToHost, g.stream));
@@ -966,7 +983,7 @@ int eu_render_async(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
   const int slot = g.next_job;
   Context::JobSlot& J = g.jobs[slot];
   if (J.pending) return fail(EU_ERR_STATE, "%d jobs are in flight already: eu_job_wait one first", EU_MAX_JOBS_IN_FLIGHT);
-  const size_t n = (size_t)t->width * t->height * t->nchannels;
+  const size_t n = (size_t)out_width(t) * out_height(t) * t->nchannels;
   if (n > J.cap) {
     CK(cudaDeviceSynchronize());
     if (J.d_out) CK(cudaFree(J.d_out));
@@ -979,9 +996,9 @@ int eu_render_async(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
   rc = build_plan(t, o, n_facets, facets, sources, taps, n_taps, g.stream, plan);
   if (rc) return rc;
   plan.P.row0 = 0;
-  plan.P.row1 = t->height;
+  plan.P.row1 = out_height(t);
   plan.P.out = J.d_out;
-  plan.P.out_pitch = t->width * t->nchannels;
+  plan.P.out_pitch = out_width(t) * t->nchannels;
   plan.P.index_out = nullptr;
   CK(cudaEventRecord(J.start, g.stream));
   CK(eu_launch_render(plan.P, g.stream));
@@ -1025,13 +1042,13 @@ int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
   Plan plan;
   rc = build_plan(t, o, n_facets, facets, sources, nullptr, 0, g.stream, plan);
   if (rc) return rc;
-  size_t n = (size_t)t->width * t->height;
+  size_t n = (size_t)out_width(t) * out_height(t);
   rc = grow(g.d_index, g.index_cap, n);
   if (rc) return rc;
   plan.P.row0 = 0;
-  plan.P.row1 = t->height;
+  plan.P.row1 = out_height(t);
   plan.P.out = nullptr;
-  plan.P.out_pitch = t->width * t->nchannels;
+  plan.P.out_pitch = out_width(t) * t->nchannels;
   plan.P.index_out = g.d_index;
   CK(eu_launch_render(plan.P, g.stream));
   CK(cudaMemcpyAsync(index_out, g.d_index, n * sizeof(int32_t), cudaMemcpyDeviceToHost, g.stream));

@@ -183,9 +183,14 @@ int arguments::init(int argc, const char** argv) {
         p_line_height = iglean(ln.get("h"));
         p_line_hfov = (M_PI / 180.0) * glean(ln.get("v"));
         p_line_eev = glean(ln.get("Eev"));
-        if (!ln.get("S").empty()) {
-          error = "p-line crop (S) is outside the built path";
-          return EU_ERR_UNSUPPORTED;
+        if (!ln.get("S").empty()) {  // store_cropped, envutil_main.cc:615-627
+          int v[4];
+          if (sscanf(ln.get("S").c_str(), "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) != 4) {
+            error = "bad S clause '" + ln.get("S") + "' in the p-line";
+            return EU_ERR_ARGUMENT;
+          }
+          store_cropped = true;
+          p_crop_x0 = v[0]; p_crop_x1 = v[1]; p_crop_y0 = v[2]; p_crop_y1 = v[3];
         }
         break;  // additional p-lines are ignored
       }
@@ -467,6 +472,18 @@ int arguments::init(int argc, const char** argv) {
     return EU_ERR_ARGUMENT;
   }
   t.step = (t.x1 - t.x0) / t.width;
+  // a 'single' job stores the whole facet geometry (core(): args.store_cropped = false, envutil_main.cc:1714,1726)
+  if (store_cropped && single < 0) {
+    t.crop_x0 = p_crop_x0;
+    t.crop_y0 = p_crop_y0;
+    t.crop_width = p_crop_x1 - p_crop_x0;
+    t.crop_height = p_crop_y1 - p_crop_y0;
+    if (t.crop_width <= 0 || t.crop_height <= 0 || t.crop_x0 < 0 || t.crop_y0 < 0 || p_crop_x1 > t.width ||
+        p_crop_y1 > t.height) {
+      error = "p-line crop does not lie inside the target";
+      return EU_ERR_ARGUMENT;
+    }
+  }
   return EU_OK;
 }
 

@@ -80,7 +80,9 @@ struct cuda_dispatch : public dispatch_base {
     }
     const std::vector<eu_tap_t>& taps = a.twine_spread;
     int n_taps = ninputs == 9 ? (int)taps.size() : 0;  // ninputs == 9 <=> twining (envutil_main.cc:1673)
-    std::vector<float> out((size_t)t.width * t.height * nchannels);
+    // a cropped output (p-line S) has the crop's size (envutil_payload.cc:440-443)
+    const int ow = t.crop_width > 0 ? t.crop_width : t.width, oh = t.crop_width > 0 ? t.crop_height : t.height;
+    std::vector<float> out((size_t)ow * oh * nchannels);
     eu_timing_t tm{};
     rc = eu_render(&t, &o, (int)fv.size(), fv.data(), sv.data(), taps.data(), n_taps, out.data(), &tm);
     if (rc) {
@@ -92,7 +94,7 @@ struct cuda_dispatch : public dispatch_base {
       printf("frame rendering time: %.3f ms (device), staging %.3f ms, h2d %.3f ms, d2h %.3f ms, %d launches\n",
              tm.render_ms, stage_ms, h2d_ms, tm.d2h_ms, tm.launches);
     }
-    if (!write_raster(a.output, t.width, t.height, nchannels, out.data())) {
+    if (!write_raster(a.output, ow, oh, nchannels, out.data())) {
       fprintf(stderr, "envutil_b200: cannot write '%s'\n", a.output.c_str());
       return EU_ERR_ARGUMENT;
     }
@@ -129,6 +131,7 @@ int core(int argc, const char** argv) {
     printf("target %s %dx%d nch %d hfov %.17g yaw %.17g pitch %.17g roll %.17g\n", projection_name[t.projection], t.width,
            t.height, nch, t.hfov, t.yaw, t.pitch, t.roll);
     printf("extent %.17g %.17g %.17g %.17g step %.17g\n", t.x0, t.x1, t.y0, t.y1, t.step);
+    if (t.crop_width > 0) printf("crop %dx%d+%d+%d\n", t.crop_width, t.crop_height, t.crop_x0, t.crop_y0);
     printf("degree %d prefilter %d twine %d ninputs %d synopsis %s solo %d\n", args.spline_degree, args.prefilter_degree,
            args.twine, ninp, args.synopsis.c_str(), args.solo);
     for (const auto& f : args.facet_spec_v)

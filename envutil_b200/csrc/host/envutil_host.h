@@ -44,6 +44,8 @@ struct arguments {
   std::vector<eu_tap_t> twine_spread;
   int support_min = 8, tile_size = 64;
   int nchannels = 0, nfacets = 0, solo = -1, single = -1, mask_for = -1;
+  bool store_cropped = false;  // p-line S clause (envutil_basic.h:684-687)
+  int p_crop_x0 = 0, p_crop_x1 = 0, p_crop_y0 = 0, p_crop_y1 = 0;
   float brighten = 1.0f;
   std::vector<facet_spec> facet_spec_v;
   std::vector<std::string> addenda;

@@ -61,7 +61,8 @@ struct FacetDev {
 };
 
 struct TargetDev {
-  int32_t projection, width, height, normalize;
+  int32_t projection, width, height, normalize;  // width x height: the raster that is rendered (the crop, if any)
+  int32_t full_w, full_h, off_x, off_y;  // the target the steppers are built for, and the crop's origin in it
   float fx0, fx1, fy0, fy1;  // stepper_base scaling factors (stepper.h:299-302)
   float delta;               // 16 * (a1-a0)/W                (stepper.h:305)
   float bias_x, bias_y;      // bias of deriv_stepper's r10 / r01 (stepper.h:303-304,1606-1625)

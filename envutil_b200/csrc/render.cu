@@ -15,8 +15,10 @@ __global__ void k_planar_tables(TargetDev T, float2* __restrict__ col, float2* _
     float bias = i < T.width ? 0.0f : T.bias_x;
     int seg0 = (x / EU_SEGMENT) * EU_SEGMENT;
     int r = x - seg0, lane = r % EU_LANES, v = r / EU_LANES;
-    float ll0 = (float)(2 * lane) + (float)(seg0 * 2 + 1);
-    float p = bias + ll0 * T.fx1 + ((float)(2 * T.width) - ll0) * T.fx0;
+    // a cropped output feeds the steppers offset discrete coordinates (zimt/wielding.h:391-407); the
+    // segments are those of the crop, the scaling is the whole target's
+    float ll0 = (float)(2 * lane) + (float)((seg0 + T.off_x) * 2 + 1);
+    float p = bias + ll0 * T.fx1 + ((float)(2 * T.full_w) - ll0) * T.fx0;
     for (int k = 0; k < v; k++) p += T.delta;
     ColTerm c;
     dev_col_term(T, p, c);
@@ -27,8 +29,8 @@ __global__ void k_planar_tables(TargetDev T, float2* __restrict__ col, float2* _
   if (j >= 0 && j < 2 * T.height) {
     int y = j % T.height;
     float bias = j < T.height ? 0.0f : T.bias_y;
-    int ll1 = y * 2 + 1;
-    float p = bias + ll1 * T.fy1 + (float)(2 * T.height - ll1) * T.fy0;
+    int ll1 = (y + T.off_y) * 2 + 1;
+    float p = bias + ll1 * T.fy1 + (float)(2 * T.full_h - ll1) * T.fy0;
     RowTerm rt;
     dev_row_term(T, p, y, rt);
     row[j] = make_float2(rt.a, rt.b);

@@ -108,7 +108,7 @@ class Engine:
         t, fa, o, taps, ntaps = st
         hs = sources if sources is not None else self.stage(job, st)
         if out is None:
-            out = np.empty((t.height, t.width, t.nchannels), dtype=np.float32)
+            out = np.empty(t.out_shape() + (t.nchannels,), dtype=np.float32)
         tm = capi.Timing()
         try:
             capi.check(self.lib.eu_render(C.byref(t), C.byref(o), len(job.facets), fa, hs, taps, ntaps,
@@ -168,7 +168,7 @@ class Engine:
         st = structs or job.structs(self.lib)
         t, fa, o, taps, ntaps = st
         hs = sources if sources is not None else self.stage(job, st)
-        idx = np.empty((t.height, t.width), dtype=np.int32)
+        idx = np.empty(t.out_shape(), dtype=np.int32)
         try:
             capi.check(self.lib.eu_debug_planes(C.byref(t), C.byref(o), len(job.facets), fa, hs, idx.ctypes.data),
                        self.lib)

@@ -102,6 +102,8 @@ class Job:
     twine_max: int = 8
     synopsis: str = "panorama"
     solo: int = -1
+    crop_out: Optional[tuple] = None  # PTO p-line S clause (x0, x1, y0, y1): only this window of the target is
+                                      # rendered and stored (envutil_main.cc:615-627, envutil_payload.cc:440-474)
     single: int = -1  # --single K: render into facet K's geometry, undo its brighten (envutil_main.cc:1157-1178)
     support_min: int = 8
     tile_size: int = 64
@@ -113,10 +115,12 @@ class Job:
 
     # ---- reference command line (real spellings, envutil_main.cc:190-372) ----
     def uses_pto(self):
-        return any(f.eev or f.a or f.b or f.c or f.d or f.e or f.g or f.t or f.tr_x or f.tr_y or f.tr_z
-                   or f.has_alpha_spec() or f.window is not None for f in self.facets)
+        return self.crop_out is not None or any(
+            f.eev or f.a or f.b or f.c or f.d or f.e or f.g or f.t or f.tr_x or f.tr_y or f.tr_z
+            or f.has_alpha_spec() or f.window is not None for f in self.facets)
 
     _PTO_CODE = {"rectilinear": 0, "cylindrical": 1, "fisheye": 3, "spherical": 4, "stereographic": 10}
+    _PTO_P_CODE = {"rectilinear": 0, "cylindrical": 1, "spherical": 2, "fisheye": 3, "stereographic": 4}  # p-line, :585-602
 
     def pto_lines(self, facet_paths):
         """i-lines for the facets (PTO subset, reference envutil_main.cc:655-822)."""
@@ -142,6 +146,12 @@ class Job:
             for m in f.masks:  # k-lines: exclude masks (envutil_main.cc:829-904)
                 pts = " ".join("%s %s" % (repr(float(x)), repr(float(y))) for x, y in m)
                 lines.append(f'k i{i} t0 p"{pts}"')
+        if self.crop_out is not None:
+            # the p-line is honoured only when --width is absent; then it supplies projection, size and
+            # hfov, and the camera angles are NOT converted from degrees (envutil_main.cc:1180-1194)
+            assert self.yaw == 0 and self.pitch == 0 and self.roll == 0 and self.height and self.single < 0
+            lines.append("p f%d w%d h%d v%r S%d,%d,%d,%d" % ((self._PTO_P_CODE[self.projection], self.width, self.height,
+                                                            float(self.hfov)) + tuple(int(v) for v in self.crop_out)))
         return lines
 
     def cli_args(self, facet_paths, output):
@@ -153,9 +163,10 @@ class Job:
             for f, p in zip(self.facets, facet_paths):
                 args += ["--facet", p, f.projection, repr(float(f.hfov)), repr(float(f.yaw)), repr(float(f.pitch)),
                          repr(float(f.roll))]
-        args += ["--projection", self.projection, "--hfov", repr(float(self.hfov)), "--width", str(self.width)]
-        if self.height:
-            args += ["--height", str(self.height)]
+        if self.crop_out is None:
+            args += ["--projection", self.projection, "--hfov", repr(float(self.hfov)), "--width", str(self.width)]
+            if self.height:
+                args += ["--height", str(self.height)]
         args += ["--yaw", repr(float(self.yaw)), "--pitch", repr(float(self.pitch)), "--roll", repr(float(self.roll))]
         args += ["--degree", str(self.degree), "--prefilter", str(self.prefilter), "--twine", str(self.twine)]
         if self.twine != 0:
@@ -208,6 +219,10 @@ class Job:
         f32 = lambda v: float(np.float32(v)) * (math.pi / 180.0)
         t.hfov = f32(self.hfov)
         t.yaw, t.pitch, t.roll = f32(self.yaw), f32(self.pitch), f32(self.roll)
+        if self.crop_out is not None:  # p-line route: hfov is parsed as a double there (envutil_main.cc:613)
+            t.hfov = float(self.hfov) * (math.pi / 180.0)
+            x0, x1, y0, y1 = (int(v) for v in self.crop_out)
+            t.crop_x0, t.crop_y0, t.crop_width, t.crop_height = x0, y0, x1 - x0, y1 - y0
         if self.single < 0:
             capi.check(lib.eu_target_prepare(C.byref(t)), lib)
         n = len(self.facets)

@@ -90,6 +90,12 @@ typedef struct eu_target {
   /* derived */
   double x0, x1, y0, y1;
   double step;
+  /* cropped output (PTO p-line "S x0,x1,y0,y1", envutil_main.cc:615-627): crop_width > 0 renders the
+   * window [crop_x0, crop_x0+crop_width) x [crop_y0, crop_y0+crop_height) of the width x height target
+   * only - the output raster has the crop's size, rows of eu_render_rows count from the crop's top
+   * (envutil_payload.cc:440-443,470-474: the discrete coordinates fed to the steppers are offset).
+   * Not for cubemap / biatan6 targets. All zero = the whole target. */
+  int32_t crop_x0, crop_y0, crop_width, crop_height;
 } eu_target_t;
 
 typedef struct eu_opts {

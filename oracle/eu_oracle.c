@@ -934,7 +934,8 @@ typedef struct {
 } facet_ctx;
 
 typedef struct {
-  int projection, width, height, normalize;
+  int projection, width, height, normalize; /* width x height: the raster rendered (the crop, if any) */
+  int full_w, full_h, off_x, off_y;         /* the target the steppers are built for; the crop's origin */
   float fx0, fx1, fy0, fy1, delta;
   float bias_x, bias_y; /* of the biased steppers r10 / r01 */
   float section_md, refc_md;
@@ -947,8 +948,14 @@ static void target_setup(const eu_target_t* t, target_ctx* T) {
   orc_get_extent(t->projection, w, h, t->hfov, e);
   float a0 = (float)e[0], a1 = (float)e[1], b0 = (float)e[2], b1 = (float)e[3];
   T->projection = t->projection;
-  T->width = w;
-  T->height = h;
+  /* cropped output, envutil_payload.cc:440-443,470-474: the raster has the crop's size and the
+   * discrete coordinates handed to the steppers are offset by the crop's origin */
+  T->width = t->crop_width > 0 ? t->crop_width : w;
+  T->height = t->crop_width > 0 ? t->crop_height : h;
+  T->full_w = w;
+  T->full_h = h;
+  T->off_x = t->crop_width > 0 ? t->crop_x0 : 0;
+  T->off_y = t->crop_width > 0 ? t->crop_y0 : 0;
   T->fx1 = (float)(a1 / (2.0 * w));
   T->fx0 = (float)(a0 / (2.0 * w));
   T->fy1 = (float)(b1 / (2.0 * h));
@@ -966,14 +973,14 @@ static void target_setup(const eu_target_t* t, target_ctx* T) {
 static float planar_x(const target_ctx* T, int x, float bias) {
   int seg0 = (x / ORC_SEGMENT) * ORC_SEGMENT;
   int r = x - seg0, lane = r % ORC_LANES, v = r / ORC_LANES;
-  float ll0 = (float)(2 * lane) + (float)(seg0 * 2 + 1);
-  float p = bias + ll0 * T->fx1 + ((float)(2 * T->width) - ll0) * T->fx0;
+  float ll0 = (float)(2 * lane) + (float)((seg0 + T->off_x) * 2 + 1);
+  float p = bias + ll0 * T->fx1 + ((float)(2 * T->full_w) - ll0) * T->fx0;
   for (int i = 0; i < v; i++) p += T->delta;
   return p;
 }
 static float planar_y(const target_ctx* T, int y, float bias) {
-  int ll1 = y * 2 + 1;
-  return bias + ll1 * T->fy1 + (float)(2 * T->height - ll1) * T->fy0;
+  int ll1 = (y + T->off_y) * 2 + 1;
+  return bias + ll1 * T->fy1 + (float)(2 * T->full_h - ll1) * T->fy0;
 }
 
 static float norm3(const float v[3]) {

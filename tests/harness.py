@@ -85,9 +85,10 @@ def oracle_render(job, want_index=False, threads=0, rows=None, sources=None):
     st = job.structs()
     t, fa, o, taps, ntaps = st
     hs = sources if sources is not None else oracle_sources(job, st)
-    row0, row1 = rows or (0, t.height)
-    out = np.empty((row1 - row0, t.width, t.nchannels), dtype=np.float32)
-    idx = np.empty((row1 - row0, t.width), dtype=np.int32) if want_index else None
+    oh, ow = t.out_shape()
+    row0, row1 = rows or (0, oh)
+    out = np.empty((row1 - row0, ow, t.nchannels), dtype=np.float32)
+    idx = np.empty((row1 - row0, ow), dtype=np.int32) if want_index else None
     rc = lib.orc_render(C.byref(t), C.byref(o), len(job.facets), fa, hs, taps, ntaps, row0, row1,
                         out.ctypes.data, idx.ctypes.data if want_index else None, threads)
     assert rc == 0, rc

@@ -242,6 +242,12 @@ def _build():
     add("single2_voronoi4_d3_tw2", Job(_voronoi_facets(), "spherical", 360.0, 64, 32, single=2, degree=3, twine=2))
     add("single0_cm_ll", Job([FacetSpec(_cm(32), "cubemap", 90.0), _ll_facet(128)], "spherical", 360.0, 64, 32, single=0))
     tr = _translated_facets()
+    # cropped output: PTO p-line with an S clause (the steppers see offset discrete coordinates)
+    add("cropout_ll_sph_d1", Job([_ll_facet(256)], "spherical", 360.0, 1200, 600, crop_out=(500, 1120, 100, 420)))  # > 1 segment
+    add("cropout_ll_rect_d3_tw2", Job([_ll_facet(128)], "rectilinear", 90.0, 160, 120, degree=3, twine=2,
+                                      crop_out=(37, 150, 11, 97)))
+    add("cropout_ll_cyl_d1_tw2", Job([_ll_facet(256)], "cylindrical", 360.0, 640, 90, twine=2, crop_out=(30, 610, 5, 70)))
+    add("cropout_voronoi4_fish_d1", Job(_voronoi_facets(), "fisheye", 200.0, 200, 200, crop_out=(20, 180, 40, 200)))
     add("tr1_sph_d1", Job(tr[:1], "spherical", 360.0, 192, 96))
     add("tr1_rect_d1_tw2", Job(tr[1:2], "rectilinear", 100.0, 96, 64, yaw=30.0, twine=2))
     add("tr3_voronoi_sph_d1", Job(tr, "spherical", 360.0, 256, 128, yaw=11.0, pitch=3.0))

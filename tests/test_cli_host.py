@@ -40,7 +40,7 @@ def _floats(line, key):
 
 @pytest.mark.parametrize("name", ["ll_rect_d1_oddangles", "ll_fish_d1_tw4", "ll_rect_d1_tw3_sigma", "hdr3_sph_d3_tw2",
                                   "lens3_voronoi_sph_d1", "eev_voronoi_sph_d1", "ll_cube_d3_rot", "voronoi4_solo2",
-                                  "cm_sph_d1_support4_tile16"])
+                                  "cm_sph_d1_support4_tile16", "cropout_ll_rect_d3_tw2", "cropout_voronoi4_fish_d1"])
 def test_dry_run_equals_marshalling(cli, tmp_path, name):
     job = jobs.JOBS[name]
     paths = _write_facets(job, str(tmp_path))
@@ -51,6 +51,8 @@ def test_dry_run_equals_marshalling(cli, tmp_path, name):
     t, fa, o, taps, ntaps = job.structs()
     tl = [l for l in lines if l.startswith("target ")][0]
     assert "%dx%d" % (t.width, t.height) in tl
+    if t.crop_width > 0:  # p-line S clause
+        assert "crop %dx%d+%d+%d" % (t.crop_width, t.crop_height, t.crop_x0, t.crop_y0) in lines
     assert _floats(tl, "hfov")[0] == t.hfov and _floats(tl, "yaw")[0] == t.yaw
     assert _floats(tl, "pitch")[0] == t.pitch and _floats(tl, "roll")[0] == t.roll
     el = [l for l in lines if l.startswith("extent ")][0]
@@ -136,7 +138,8 @@ def test_pto_back_references(cli, tmp_path):
                                   "auto_tw_voronoi_d3", "auto_tw_up_ll_rect_d1", "auto_tw_density_ll_ba6",
                                   "mask_crop4_voronoi_sph_d1", "crop_fish_sph_d1", "mask_grey_sph_d1_tw2",
                                   "win_voronoi_sph_d1", "win_rect_rect_d3_tw2", "single1_hdr3_d1",
-                                  "single2_voronoi4_d3_tw2", "single0_cm_ll"])
+                                  "single2_voronoi4_d3_tw2", "single0_cm_ll", "cropout_ll_sph_d1",
+                                  "cropout_ll_rect_d3_tw2", "cropout_ll_cyl_d1_tw2", "cropout_voronoi4_fish_d1"])
 def test_cli_output_equals_reference_output(cli, tmp_path, name):
     """The drop-in claim end to end: the SAME command line given to the reference binary and to
     envutil_b200_cli produces the same file, bit for bit (golden sha256 of the reference run)."""
