@@ -45,6 +45,7 @@ class Target(C.Structure):
         ("x0", C.c_double), ("x1", C.c_double), ("y0", C.c_double), ("y1", C.c_double),
         ("step", C.c_double),
         ("crop_x0", C.c_int32), ("crop_y0", C.c_int32), ("crop_width", C.c_int32), ("crop_height", C.c_int32),
+        ("single", C.c_int32), ("reserved", C.c_int32),
     ]
 
     def out_shape(self):

@@ -69,6 +69,7 @@ struct Context {
   FacetDev* d_facets = nullptr;
   int facets_cap = 0;
   float* d_taps = nullptr;
+  float* d_invcoef = nullptr;  // inverse_lcp spline of a 'single' job's target facet (inverse_planar)
   int taps_cap = 0;
   float* d_out = nullptr;
   size_t out_cap = 0;
@@ -194,7 +195,7 @@ bool known_source(eu_source_h s) {
 
 // facet -> FacetDev: what source_t / mount_t / cubemap_view_t / environment hold
 // (environment.h:594-645,970-1006,1428-1461,1786-1860), narrowed as the functors narrow it
-int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, FacetDev& F) {
+int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, FacetDev& F, const eu_facet_t* ft = nullptr) {
   memset(&F, 0, sizeof(F));
   if (s->projection != f->projection || s->nch != f->nchannels ||
       (s->kind == EU_SRC_MOUNT && (s->w != f->window_width || s->h != f->window_height)))
@@ -251,10 +252,12 @@ int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, Fac
   F.brighten = (float)(f->brighten == 0.0 ? 1.0 : f->brighten);
   F.hdr_optimum = 0.0f;
   F.hdr_kind = EU_HDR_MIDDLE;
-  F.generic = f->has_translation ? 1 : 0;
+  // generic_r3, envutil_payload.cc:1636-1809: a facet with translation - or every facet, when the job is a
+  // 'single' on a facet with lens correction / translation (`ft`) - gets its rays from the generic stepper
+  F.generic = (f->has_translation || ft) ? 1 : 0;
+  F.g_nstage = 0;
   if (F.generic) {
-    // generic_r3(ft, fs) for an untranslated target (envutil_payload.cc:1640-1716): the matrices
-    // are r3_t<float>, built from make_r3_t's double rows narrowed element by element
+    // the matrices are r3_t<float>, built from make_r3_t's double rows narrowed element by element
     auto rot = [](double r, double p, double y, int inv, float out[9]) {
       double d[9];
       eu_rotation_matrix(r, p, y, inv, d);
@@ -264,21 +267,62 @@ int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, Fac
       for (int i = 0; i < 3; i++)
         for (int c = 0; c < 3; c++) o[3 * i + c] = (a[3 * i] * b[c] + a[3 * i + 1] * b[3 + c]) + a[3 * i + 2] * b[6 + c];
     };
-    float r_camera[9], rs_tp[9], rs_tpi[9], r_facet[9];
-    rot(t->roll, t->pitch, t->yaw, 0, r_camera);
+    auto plane_shift = [](const eu_facet_t* q, const float tp[9], float sh[3]) {  // :1683-1695,1709-1716
+      sh[0] = (float)q->tr_x; sh[1] = (float)q->tr_y; sh[2] = (float)q->tr_z;
+      if (q->tp_y != 0 || q->tp_p != 0 || q->tp_r != 0) {  // rotate(xel_t<double,3>(shift), r): in double
+        double sd[3] = {sh[0], sh[1], sh[2]}, od[3];
+        for (int c = 0; c < 3; c++) od[c] = (sd[0] * tp[c] + sd[1] * tp[3 + c]) + sd[2] * tp[6 + c];
+        for (int c = 0; c < 3; c++) sh[c] = (float)od[c];
+      }
+    };
+    auto stage = [&](int k, const float a[9], const float b[9], const float shift[3], float dcp) {  // tf3d_t ctor
+      FacetDev::TfStage& S = F.g_st[k];
+      memcpy(S.a, a, sizeof(S.a));
+      memcpy(S.b, b, sizeof(S.b));
+      mul(a, b, S.ab);
+      for (int c = 0; c < 3; c++) S.shift[c] = shift[c];
+      S.has_shift = (shift[0] != 0 || shift[1] != 0 || shift[2] != 0) ? 1 : 0;
+      S.dcp = dcp;
+    };
+    float r_camera[9], rt_tp[9], rt_tpi[9], rs_tp[9], rs_tpi[9], r_facet[9], m1[9], m2[9];
+    if (ft) rot(ft->roll, ft->pitch, ft->yaw, 0, r_camera);
+    else rot(t->roll, t->pitch, t->yaw, 0, r_camera);
     rot(f->tp_r, f->tp_p, f->tp_y, 1, rs_tp);
     rot(f->tp_r, f->tp_p, f->tp_y, 0, rs_tpi);
     rot(f->roll, f->pitch, f->yaw, 1, r_facet);
-    float sh[3] = {(float)f->tr_x, (float)f->tr_y, (float)f->tr_z};
-    if (f->tp_y != 0 || f->tp_p != 0 || f->tp_r != 0) {  // rotate(xel_t<double,3>(shift_s), rs_tp): in double
-      double sd[3] = {sh[0], sh[1], sh[2]}, od[3];
-      for (int c = 0; c < 3; c++) od[c] = (sd[0] * rs_tp[c] + sd[1] * rs_tp[3 + c]) + sd[2] * rs_tp[6 + c];
-      for (int c = 0; c < 3; c++) sh[c] = (float)od[c];
+    const bool have_ttp = ft && (ft->tr_x != 0 || ft->tr_y != 0 || ft->tr_z != 0);
+    const bool have_stp = (f->tr_x != 0 || f->tr_y != 0 || f->tr_z != 0);
+    float shift_t[3] = {0.f, 0.f, 0.f}, shift_s[3], dcp = 1.0f;
+    if (ft) {
+      rot(ft->tp_r, ft->tp_p, ft->tp_y, 1, rt_tp);
+      rot(ft->tp_r, ft->tp_p, ft->tp_y, 0, rt_tpi);
+      plane_shift(ft, rt_tp, shift_t);
+      dcp = (float)(1.0 - shift_t[2]);
+      for (int c = 0; c < 3; c++) shift_t[c] = -shift_t[c];
     }
-    mul(r_camera, rs_tp, F.g_t2m);
-    mul(rs_tpi, r_facet, F.g_m2s);
-    for (int c = 0; c < 3; c++) F.g_shift[c] = sh[c];
-    F.g_dcp = 1.0f;
+    plane_shift(f, rs_tp, shift_s);
+    if (have_ttp) {
+      mul(r_camera, rt_tp, m1);
+      if (have_stp) {
+        stage(0, m1, rt_tpi, shift_t, dcp);
+        mul(rs_tpi, r_facet, m2);
+        stage(1, rs_tp, m2, shift_s, 1.0f);
+        F.g_nstage = 2;
+      } else {
+        mul(rt_tpi, r_facet, m2);
+        stage(0, m1, m2, shift_t, dcp);
+        F.g_nstage = 1;
+      }
+    } else if (have_stp) {
+      mul(r_camera, rs_tp, m1);
+      mul(rs_tpi, r_facet, m2);
+      stage(0, m1, m2, shift_s, 1.0f);
+      F.g_nstage = 1;
+    } else {  // rotate_t(rotate(r_camera, r_facet))
+      const float zero[3] = {0.f, 0.f, 0.f};
+      stage(0, r_camera, r_facet, zero, 1.0f);
+      F.g_nstage = 1;
+    }
   }
   return EU_OK;
 }
@@ -319,6 +363,71 @@ struct Plan {
   RenderParams P;
   int launches;
 };
+
+// pto_planar<float, L, true>: the inverse planar transformation of a 'single' job's target facet. The knots
+// of inverse_lcp's spline (lens_correction.h:341-386) are found on the host - Newton's method in double,
+// eu_polynomial<double, 4>::inverse (:133-170) - and become b-spline coefficients on the device with the
+// very kernels that prefilter rasters (one line of EU_INV_NK floats, NATURAL), then the NATURAL brace.
+int inverse_planar(const eu_facet_t* ft, cudaStream_t cs, InvPlanarDev& IP) {
+  memset(&IP, 0, sizeof(IP));
+  IP.on = 1;
+  IP.has_shear = ft->has_shear;
+  IP.has_shift = ft->has_shift;
+  IP.has_lcp = ft->has_lcp;
+  IP.shear_g = ft->shear_g;
+  IP.shear_t = ft->shear_t;
+  IP.s = ft->s;
+  IP.h = (float)ft->shift_h;
+  IP.v = (float)ft->shift_v;
+  for (int i = 0; i < 16; i++) IP.wm[i] = (float)eu_bspline_weights[3][i / 4][i % 4];
+  const int sz = EU_INV_SZ, nk = EU_INV_NK;
+  const double cf[5] = {ft->a, ft->b, ft->c, 1.0 - (ft->a + ft->b + ft->c), 0.0};
+  double dcf[5];
+  {
+    size_t power = 4;
+    for (int i = 0; i <= 4; i++) { dcf[i] = cf[i] * power; --power; }
+  }
+  auto fn = [&](double x) {
+    double sum = 0.0, power = 1.0;
+    for (int i = 0; i <= 4; i++) { sum += cf[4 - i] * power; power *= x; }
+    return sum;
+  };
+  auto der = [&](double x) {
+    double sum = 0.0, power = 1.0;
+    for (int i = 0; i < 4; i++) { sum += dcf[4 - i - 1] * power; power *= x; }
+    return sum;
+  };
+  const double r_max = ft->r_max * ((sz + 3.0) / sz);
+  IP.rr_max = fn(r_max);
+  float knots[EU_INV_NK];
+  for (int i = 0; i < nk; i++) {
+    double notch = (double)i / (nk - 1);
+    notch *= notch;
+    notch *= IP.rr_max;
+    double current = i * r_max / sz, result, difference = 0.0, last_difference = DBL_MAX;
+    const double tolerance = 100 * DBL_EPSILON;
+    for (int count = 0; count < 16; count++) {
+      result = fn(current);
+      difference = notch - result;
+      if (last_difference == difference) break;
+      if (fabs(difference) <= tolerance) break;
+      last_difference = difference;
+      current = current + difference / der(current);
+    }
+    if (!(fabs(difference) < tolerance))  // the reference asserts here (lens_correction.h:186-190)
+      return fail(EU_ERR_ARGUMENT, "the lens polynomial a=%g b=%g c=%g cannot be inverted", ft->a, ft->b, ft->c);
+    knots[i] = (float)(notch == 0.0 ? 1.0 / der(0.0) : (current / notch) - 1);
+  }
+  if (!g.d_invcoef) CK(cudaMalloc(&g.d_invcoef, sizeof(float) * (EU_INV_NK + 8)));
+  float* core = g.d_invcoef + 4;  // 16-byte aligned start of the line; the brace uses core[-2..-1] and core[nk..nk+1]
+  CK(cudaMemcpyAsync(core, knots, sizeof(knots), cudaMemcpyHostToDevice, cs));  // pageable: staged before return
+  IirDev f;
+  iir_setup(f, EU_BC_NATURAL, 3, (long double)FLT_EPSILON, nk);
+  CK(eu_launch_iir_x(core, EU_INV_NK + 4, 1, nk, 1, f, cs));
+  CK(eu_launch_brace_natural_1d(core, nk, 2, cs));
+  IP.coef = core;
+  return EU_OK;
+}
 
 // builds the plan and uploads the per-job tables; everything is enqueued on g.stream
 // `cs`: the stream the render will be launched on. The per-job facet array and tap list live in
@@ -370,10 +479,22 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   P.n_taps = n_taps;
   P.nch = nch;
   P.tstride = sources[first_of(nf, o)]->tstride;
+  // a 'single' job on a facet with lens correction / shift / shear / translation (fuse(), :2058-2068)
+  const eu_facet_t* ft = nullptr;
+  if (t->single > 0) {
+    if (t->single > nf) return fail(EU_ERR_ARGUMENT, "target.single %d is beyond the facet count %d", t->single, nf);
+    const eu_facet_t* cand = &facets[t->single - 1];
+    if (cand->has_2d_tf || cand->has_translation) ft = cand;
+  }
   std::vector<FacetDev> F(nf);
   for (int i = 0; i < nf; i++) {
-    int rc = facet_dev(t, &facets[i], sources[i], F[i]);
+    int rc = facet_dev(t, &facets[i], sources[i], F[i], ft);
     if (rc) return rc;
+  }
+  if (ft && ft->has_2d_tf) {  // tf22 = pto_planar<float, L, true>(ft), envutil_payload.cc:1864
+    int rc = inverse_planar(ft, cs, P.inv);
+    if (rc) return rc;
+    plan.launches += 2;
   }
   if (mode == EU_MODE_HDR) {  // _hdr_merge_syn ctor, envutil_payload.cc:1354-1375
     float lowest = 100000.0f, highest = -1.0f;
@@ -661,6 +782,7 @@ void eu_shutdown(void) {
   cudaFree(g.d_planar);
   cudaFree(g.d_facets);
   cudaFree(g.d_taps);
+  cudaFree(g.d_invcoef);
   cudaFree(g.d_out);
   cudaFree(g.d_index);
   cudaDeviceSynchronize();

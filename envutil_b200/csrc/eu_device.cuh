@@ -193,8 +193,54 @@ __device__ __forceinline__ void dev_rot3(const float v[3], const float* __restri
 // generic_stepper (stepper.h:353-470) over tf_ex_facet::eval (envutil_payload.cc:1841-1883): the
 // bare planar coordinate -> X_to_ray of the target projection (geometry.h:151-567) -> tf3d_t::eval
 // (geometry.h:1886-1925). Used for facets with PanoTools translation (TrX/TrY/TrZ).
-__device__ __forceinline__ void dev_generic_ray(const TargetDev& T, const FacetDev& F, float h, float v, float ray[3]) {
+template <int ORDER>
+__device__ __forceinline__ void dev_weights(const float* __restrict__ wmat, float delta, float w[ORDER]);
+
+// inverse_lcp::eval (lens_correction.h:396-405). Its argument is norm(out) / s with a double s: a DOUBLE
+// vector, so the reduction to spline coordinates runs in double and is narrowed where the float
+// evaluator takes it; clamp gate (NATURAL, zimt/eval.h:2101-2110), cubic 1-D window (eval.h:937-960)
+__device__ __forceinline__ float dev_inv_lcp_factor(const InvPlanarDev& P, float radius) {
+  double in = (double)radius / P.s;
+  in = in / P.rr_max;
+  in = sqrt(in);
+  in *= (double)(EU_INV_NK - 1);
+  float cx = (float)in;
+  const float lower = 0.0f, upper = (float)(EU_INV_NK - 1);
+  if (cx < lower) cx = lower;
+  else if (cx > upper) cx = upper;
+  float fl = floorf(cx), t = cx - fl;
+  int ix = (int)fl;
+  float w[4];
+  dev_weights<4>(P.wm, t, w);
+  const float* __restrict__ c = P.coef + (ix - 1);
+  float sum = __ldg(c);
+  sum *= w[0];
+#pragma unroll
+  for (int i = 1; i < 4; i++) sum += w[i] * __ldg(c + i);
+  sum += 1.0f;
+  return sum;
+}
+
+__device__ __forceinline__ void dev_generic_ray(const TargetDev& T, const InvPlanarDev& IP, const FacetDev& F, float h,
+                                                float v, float ray[3]) {
   float in[3];  // RIGHT, DOWN, FORWARD
+  if (IP.on) {  // tf22: pto_planar<T, L, true>::eval, environment.h:285-307
+    if (IP.has_shear) {  // float vector op double scalar is evaluated in double (gen_simd_type.h:274-316)
+      v = (float)(((double)v - IP.shear_t * (double)h) / (1 - IP.shear_t * IP.shear_g));
+      h = (float)((double)h - IP.shear_g * (double)v);
+    }
+    if (IP.has_shift) {  // operator-= narrows its scalar operand first (vector_common.h:302-316)
+      h -= IP.h;
+      v -= IP.v;
+    }
+    if (IP.has_lcp) {
+      float sqn = h * h;
+      sqn += v * v;
+      float factor = dev_inv_lcp_factor(IP, sqrtf(sqn));
+      h *= factor;
+      v *= factor;
+    }
+  }
   switch (T.projection) {
     case EU_SPHERICAL: {
       float sinlat, coslat, sinlon, coslon;
@@ -222,19 +268,26 @@ __device__ __forceinline__ void dev_generic_ray(const TargetDev& T, const FacetD
       in[0] = eu_sinf(r) * eu_sinf(phi);
     }
   }
-  float out[3];
-  dev_rot3(in, F.g_t2m, out);
-  if (out[2] <= 0.0f) {
-    out[0] = 0.0f; out[1] = 0.0f; out[2] = -INFINITY;
-  } else {
-    out[0] /= out[2];
-    out[1] /= out[2];
-    out[2] = 1.0f;
+  float out[3] = {in[0], in[1], in[2]};
+  for (int k = 0; k < F.g_nstage; k++) {  // generic_r3: tf3d_t::eval per stage, geometry.h:1886-1925
+    const FacetDev::TfStage& S = F.g_st[k];
+    if (!S.has_shift) {
+      dev_rot3(out, S.ab, out);
+      continue;
+    }
+    dev_rot3(out, S.a, out);
+    if (out[2] <= 0.0f) {
+      out[0] = 0.0f; out[1] = 0.0f; out[2] = -INFINITY;
+    } else {
+      out[0] /= out[2];
+      out[1] /= out[2];
+      out[2] = 1.0f;
 #pragma unroll
-    for (int c = 0; c < 3; c++) out[c] *= F.g_dcp;
+      for (int c = 0; c < 3; c++) out[c] *= S.dcp;
 #pragma unroll
-    for (int c = 0; c < 3; c++) out[c] -= F.g_shift[c];
-    dev_rot3(out, F.g_m2s, out);
+      for (int c = 0; c < 3; c++) out[c] -= S.shift[c];
+      dev_rot3(out, S.b, out);
+    }
   }
   if (T.normalize) {
     float n = dev_norm3(out);

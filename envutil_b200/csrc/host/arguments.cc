@@ -426,13 +426,9 @@ int arguments::init(int argc, const char** argv) {
 
   // ---- target (envutil_main.cc:1180-1232) -----------------------------------------------
   if (single >= 0) {
-    // 'single': the target takes over the facet's geometry (envutil_main.cc:1157-1178); the facet's
-    // own lens correction / translation on the TARGET side needs the inverse lens path
+    // 'single': the target takes over the facet's geometry (envutil_main.cc:1157-1178)
     const facet_spec& fs = facet_spec_v[single];
-    if (fs.f.has_2d_tf || fs.f.has_translation) {
-      error = "--single on a facet with lens correction or translation needs the inverse lens path, which is not built";
-      return EU_ERR_UNSUPPORTED;
-    }
+    t.single = single + 1;  // the kernels invert the facet's lens correction / translation (tf_ex_facet)
     t.projection = fs.f.projection;
     projection_str = projection_name[t.projection];
     t.width = fs.f.width;

@@ -32,6 +32,9 @@ cudaError_t eu_launch_iir_y(float* core, int stride, int nch, int w, int h, int 
                             cudaStream_t st);
 cudaError_t eu_launch_iir_y_spherical(float* core, int stride, int nch, int w, int h, const IirDev& f,
                                       cudaStream_t st);
+// NATURAL brace of one line of n floats: k values before and after, twice the end value minus the
+// mirrored one (zimt/brace.h:254-266,299-311)
+cudaError_t eu_launch_brace_natural_1d(float* core, int n, int k, cudaStream_t st);
 cudaError_t eu_launch_brace(float* core, int stride, int nch, int w, int h, int lx, int rx, int ly, int ry, int bc0,
                             int bc1, int spherical, cudaStream_t st);
 cudaError_t eu_launch_cubemap_support(float* ir, int pitch, int nch, int face_px, int section_px, int left, int right,

@@ -56,8 +56,27 @@ struct FacetDev {
   int32_t hdr_kind;
   // generic_stepper + tf_ex_facet + generic_r3 + tf3d_t: facets with PanoTools translation
   // (envutil_payload.cc:1628-1883, geometry.h:1850-1942). Float matrices, rows as r3_t holds them.
-  int32_t generic;
-  float g_t2m[9], g_m2s[9], g_shift[3], g_dcp;
+  // 'single' jobs on a facet with lens correction / translation put every facet on the generic stepper
+  // and generic_r3(ft, fs) becomes up to two tf3d_t in sequence (envutil_payload.cc:1716-1760); a stage
+  // without shift is the single rotation ab = rotate(a, b).
+  int32_t generic, g_nstage;
+  struct TfStage {
+    int32_t has_shift;
+    float a[9], b[9], ab[9], shift[3], dcp;
+  } g_st[2];
+};
+
+// pto_planar<float, L, true> of a 'single' job's target facet (environment.h:240-309): the inverse of
+// shear, shift and lens polynomial applied to the planar target coordinate before it becomes a ray;
+// inverse_lcp's spline (lens_correction.h:273-406): EU_INV_NK knots, NATURAL cubic, braced by 2
+#define EU_INV_SZ 100
+#define EU_INV_NK (EU_INV_SZ + 4)
+struct InvPlanarDev {
+  int32_t on, has_shear, has_shift, has_lcp;
+  double shear_g, shear_t, s, rr_max;
+  float h, v;
+  const float* coef;  // device memory: coefficient of knot 0 (two brace values before, two after the last)
+  float wm[16];       // cubic weight matrix (the job's own degree may differ)
 };
 
 struct TargetDev {
@@ -96,6 +115,7 @@ constexpr RenderSpec eu_render_specs[EU_N_SPECS] = {
 struct RenderParams {
   TargetDev trg;
   FacetDev f0;              // the facet of single-facet jobs (constant bank)
+  InvPlanarDev inv;         // 'single' jobs: inverse planar transformation of the target facet
   float wmat[64];           // (degree+1)^2 weight matrix (zimt/basis.h:419-543), float, packed
   const FacetDev* facets;   // all facets (global memory), used by the synopsis modes
   const float* taps;        // n_taps x (x*4, y*4, w)  (twining.h:106-121)

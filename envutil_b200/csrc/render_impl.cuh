@@ -89,11 +89,11 @@ struct PixelTerms {
   float px, pxb, py, pyb;  // bare planar coordinates (generic steppers only)
 };
 template <bool GEN, int WHICH>
-__device__ __forceinline__ void dev_facet_ray(const TargetDev& T, const FacetDev& F, const PixelTerms& t, int y,
-                                              float r[3]) {
+__device__ __forceinline__ void dev_facet_ray(const TargetDev& T, const InvPlanarDev& IP, const FacetDev& F,
+                                              const PixelTerms& t, int y, float r[3]) {
   if constexpr (GEN) {
     if (F.generic) {
-      dev_generic_ray(T, F, WHICH == 1 ? t.pxb : t.px, WHICH == 2 ? t.pyb : t.py, r);
+      dev_generic_ray(T, IP, F, WHICH == 1 ? t.pxb : t.px, WHICH == 2 ? t.pyb : t.py, r);
       return;
     }
   }
@@ -320,8 +320,8 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
   int idx;
   if constexpr (!TWINE) {
     auto ray_of = [&](int i, float r[3]) {
-      if constexpr (MODE == EU_MODE_SINGLE) dev_facet_ray<GEN, 0>(T, f0, t, y, r);
-      else dev_facet_ray<GEN, 0>(T, dev_facet_at<SP>(fa, i), t, y, r);
+      if constexpr (MODE == EU_MODE_SINGLE) dev_facet_ray<GEN, 0>(T, P.inv, f0, t, y, r);
+      else dev_facet_ray<GEN, 0>(T, P.inv, dev_facet_at<SP>(fa, i), t, y, r);
     };
     idx = dev_synopsis<NCH, TS, MODE, DEG, GEN, SP>(P, f0, fa, ray_of, active, px);
   } else {
@@ -333,9 +333,9 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
     idx = -1;
     if constexpr (MODE == EU_MODE_SINGLE) {
       float r00[3], du[3], dv[3];
-      dev_facet_ray<GEN, 0>(T, f0, t, y, r00);
-      dev_facet_ray<GEN, 1>(T, f0, t, y, du);
-      dev_facet_ray<GEN, 2>(T, f0, t, y, dv);
+      dev_facet_ray<GEN, 0>(T, P.inv, f0, t, y, r00);
+      dev_facet_ray<GEN, 1>(T, P.inv, f0, t, y, du);
+      dev_facet_ray<GEN, 2>(T, P.inv, f0, t, y, dv);
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         du[c] = du[c] - r00[c];
@@ -357,9 +357,9 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
       for (int i = 0; i < P.n_facets; i++) {
         const FacetDev& F = dev_facet_at<SP>(fa, i);
         float r00[3], r10[3], r01[3];
-        dev_facet_ray<GEN, 0>(T, F, t, y, r00);
-        dev_facet_ray<GEN, 1>(T, F, t, y, r10);
-        dev_facet_ray<GEN, 2>(T, F, t, y, r01);
+        dev_facet_ray<GEN, 0>(T, P.inv, F, t, y, r00);
+        dev_facet_ray<GEN, 1>(T, P.inv, F, t, y, r10);
+        dev_facet_ray<GEN, 2>(T, P.inv, F, t, y, r01);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
           np[i][c] = r00[c];

@@ -633,6 +633,18 @@ cudaError_t eu_launch_iir_y_spherical(float* core, int stride, int nch, int w, i
   k_iir_y_spherical<<<(n + IIRY_THREADS - 1) / IIRY_THREADS, IIRY_THREADS, 0, st>>>(core, stride, nch, w, h, f);
   return cudaGetLastError();
 }
+__global__ void k_brace_natural_1d(float* core, int n, int k) {
+  int i = threadIdx.x;
+  if (i < k) {
+    core[-1 - i] = core[0] + core[0] - core[1 + i];
+    core[n + i] = core[n - 1] + core[n - 1] - core[n - 2 - i];
+  }
+}
+cudaError_t eu_launch_brace_natural_1d(float* core, int n, int k, cudaStream_t st) {
+  k_brace_natural_1d<<<1, 32, 0, st>>>(core, n, k);
+  return cudaGetLastError();
+}
+
 cudaError_t eu_launch_brace(float* core, int stride, int nch, int w, int h, int lx, int rx, int ly, int ry, int bc0,
                             int bc1, int spherical, cudaStream_t st) {
   int cw = w + lx + rx, chh = h + ly + ry;

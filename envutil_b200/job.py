@@ -251,6 +251,7 @@ class Job:
             capi.check(lib.eu_facet_prepare(C.byref(s)), lib)
         if self.single >= 0:  # (facet_base&) args = facet_spec_v[single]: geometry in radians as the facet has it
             sf = fa[self.single]
+            t.single = self.single + 1
             t.projection, t.width, t.height = sf.projection, sf.width, sf.height
             t.hfov, t.yaw, t.pitch, t.roll = sf.hfov, sf.yaw, sf.pitch, sf.roll
             b = np.float32(gains[self.single])

@@ -96,6 +96,11 @@ typedef struct eu_target {
    * (envutil_payload.cc:440-443,470-474: the discrete coordinates fed to the steppers are offset).
    * Not for cubemap / biatan6 targets. All zero = the whole target. */
   int32_t crop_x0, crop_y0, crop_width, crop_height;
+  /* --single K (envutil_main.cc:1157-1178): the target has taken over the geometry of facets[K]; set
+   * single = K + 1 (0 = not a 'single' job). The library needs the facet itself when it carries lens
+   * correction, shift, shear or translation: the rays are then produced by the generic stepper through
+   * the INVERSE of those transformations (tf_ex_facet, envutil_payload.cc:1841-1883). */
+  int32_t single, reserved;
 } eu_target_t;
 
 typedef struct eu_opts {

@@ -931,9 +931,25 @@ typedef struct {
    * (envutil_payload.cc:1628-1883, geometry.h:1850-1942); float matrices, rows as r3_t holds them */
   int generic;
   float g_t2m[9], g_m2s[9], g_shift[3], g_dcp;
+  /* 'single' jobs whose target facet has lens correction / shift / shear / translation: generic_r3(ft, fs)
+   * is up to two tf3d_t in sequence (envutil_payload.cc:1716-1760); a tf3d_t without shift is one rotation */
+  int g_nstage;
+  struct { int has_shift; float a[9], b[9], ab[9], shift[3], dcp; } g_st[2];
 } facet_ctx;
 
+#define INV_SZ 100            /* knot count passed by pto_planar's ctor, environment.h:250 */
+#define INV_NK (INV_SZ + 4)
+/* pto_planar<float, L, true> of the target facet (environment.h:240-309): the inverse of shear, shift
+ * and lens polynomial; inverse_lcp's spline (lens_correction.h:273-406) */
 typedef struct {
+  int on, has_shear, has_shift, has_lcp;
+  double shear_g, shear_t, s, rr_max;
+  float h, v;
+  float coef[2 + INV_NK + 2]; /* braced NATURAL cubic spline, core at [2] */
+} inv_planar_t;
+
+typedef struct {
+  inv_planar_t inv;
   int projection, width, height, normalize; /* width x height: the raster rendered (the crop, if any) */
   int full_w, full_h, off_x, off_y;         /* the target the steppers are built for; the crop's origin */
   float fx0, fx1, fy0, fy1, delta;
@@ -947,6 +963,7 @@ static void target_setup(const eu_target_t* t, target_ctx* T) {
   int w = t->width, h = t->height;
   orc_get_extent(t->projection, w, h, t->hfov, e);
   float a0 = (float)e[0], a1 = (float)e[1], b0 = (float)e[2], b1 = (float)e[3];
+  memset(&T->inv, 0, sizeof(T->inv));
   T->projection = t->projection;
   /* cropped output, envutil_payload.cc:440-443,470-474: the raster has the crop's size and the
    * discrete coordinates handed to the steppers are offset by the crop's origin */
@@ -1004,8 +1021,110 @@ static void matmulf(const float a[9], const float b[9], float m[9]) {
 /* generic_stepper::init/increase (stepper.h:353-470) over tf_ex_facet::eval
  * (envutil_payload.cc:1841-1883): planar -> X_to_ray of the target projection (geometry.h:151-567)
  * -> tf3d_t::eval (geometry.h:1886-1925). */
+/* eu_polynomial<double, 4>, lens_correction.h:86-175 */
+static double poly4(const double cf[5], double x) {
+  double sum = 0.0, power = 1.0;
+  for (int i = 0; i <= 4; i++) { sum += cf[4 - i] * power; power *= x; }
+  return sum;
+}
+static double poly4_deriv(const double dcf[5], double x) {
+  double sum = 0.0, power = 1.0;
+  for (int i = 0; i < 4; i++) { sum += dcf[4 - i - 1] * power; power *= x; }
+  return sum;
+}
+static int poly4_inverse(const double cf[5], const double dcf[5], double desired, double* x) { /* Newton, :133-170 */
+  const double tolerance = 100 * DBL_EPSILON;
+  double current = *x, result, difference = 0.0, last_difference = DBL_MAX;
+  for (int count = 0; count < 16; count++) {
+    result = poly4(cf, current);
+    difference = desired - result;
+    if (last_difference == difference) break;
+    if (fabs(difference) <= tolerance) break;
+    last_difference = difference;
+    current = current + difference / poly4_deriv(dcf, current);
+  }
+  if (fabs(difference) < tolerance) { *x = current; return 1; }
+  return 0;
+}
+/* inverse_lcp ctor, lens_correction.h:341-386: knots of the factor-minus-one spline, NATURAL cubic,
+ * prefiltered and braced like any zimt::bspline<float, 1> */
+static int inv_lcp_setup(inv_planar_t* P, double a, double b, double c, double r_max_in) {
+  const int sz = INV_SZ, nk = INV_NK;
+  double cf[5] = {a, b, c, 1.0 - (a + b + c), 0.0}, dcf[5];
+  {
+    size_t power = 4;
+    for (int i = 0; i <= 4; i++) { dcf[i] = cf[i] * power; --power; }
+  }
+  double r_max = r_max_in * ((sz + 3.0) / sz);
+  P->rr_max = poly4(cf, r_max);
+  float* core = P->coef + 2;
+  for (int i = 0; i < nk; i++) {
+    double notch = (double)i / (nk - 1);
+    notch *= notch;
+    notch *= P->rr_max;
+    double out = i * r_max / sz;
+    if (!poly4_inverse(cf, dcf, notch, &out)) return -1;
+    core[i] = (float)(notch == 0.0 ? 1.0 / poly4_deriv(dcf, 0.0) : (out / notch) - 1);
+  }
+  iir_t f;
+  iir_setup(&f, BC_NATURAL, 3, (long double)FLT_EPSILON);
+  iir_line(&f, core, 1, nk);
+  for (int k = 0; k < 2; k++) { /* bracer, NATURAL: twice the pivot minus the mirrored source, brace.h:254-266,299-311 */
+    core[-1 - k] = core[0] + core[0] - core[1 + k];
+    core[nk + k] = core[nk - 1] + core[nk - 1] - core[nk - 2 - k];
+  }
+  return 0;
+}
+/* inverse_lcp::eval, lens_correction.h:396-405, called with norm(out) / s - a DOUBLE vector (float vector
+ * over double scalar) - so the reduction to spline coordinates runs in double and is narrowed when the
+ * float evaluator takes it; clamp gate (NATURAL, eval.h:2101-2110), cubic 1-D evaluation (eval.h:937-960) */
+static float inv_lcp_factor(const inv_planar_t* P, float radius) {
+  double in = (double)radius / P->s;
+  in = in / P->rr_max;
+  in = sqrt(in);
+  in *= (INV_NK - 1);
+  float cx = (float)in;
+  const float lower = 0.0f, upper = (float)(INV_NK - 1);
+  if (cx < lower) cx = lower;
+  else if (cx > upper) cx = upper;
+  float fl = floorf(cx), t = cx - fl;
+  int ix = (int)fl;
+  float wm[16], w[4];
+  orc_weight_matrix(3, wm);
+  float power = t;
+  for (int k = 0; k < 4; k++) w[k] = wm[k];
+  for (int row = 1; row < 4; row++) {
+    for (int k = 0; k < 4; k++) w[k] += power * wm[row * 4 + k];
+    if (row < 3) power *= t;
+  }
+  const float* c = P->coef + 2 + ix - 1;
+  float sum = c[0];
+  sum *= w[0];
+  for (int i = 1; i < 4; i++) sum += w[i] * c[i];
+  sum += 1;
+  return sum;
+}
+
 static void generic_ray(const target_ctx* T, const facet_ctx* F, float h, float v, float ray[3]) {
   float in[3]; /* RIGHT, DOWN, FORWARD */
+  if (T->inv.on) { /* tf22: pto_planar<T, L, true>::eval, environment.h:285-307 */
+    const inv_planar_t* P = &T->inv;
+    if (P->has_shear) { /* float vector op double scalar is evaluated in double (gen_simd_type.h:274-316) */
+      v = (float)(((double)v - P->shear_t * (double)h) / (1 - P->shear_t * P->shear_g));
+      h = (float)((double)h - P->shear_g * (double)v);
+    }
+    if (P->has_shift) { /* operator-= narrows its scalar operand first (vector_common.h:302-316) */
+      h -= P->h;
+      v -= P->v;
+    }
+    if (P->has_lcp) {
+      float sqn = h * h;
+      sqn += v * v;
+      float factor = inv_lcp_factor(P, sqrtf(sqn));
+      h *= factor;
+      v *= factor;
+    }
+  }
   switch (T->projection) {
     case EU_SPHERICAL: {
       float sinlat, coslat, sinlon, coslon;
@@ -1034,6 +1153,26 @@ static void generic_ray(const target_ctx* T, const facet_ctx* F, float h, float 
     }
   }
   float out[3];
+  if (F->g_nstage > 0) { /* generic_r3(ft, fs): tf3d_t::eval per stage, geometry.h:1886-1925 */
+    out[0] = in[0]; out[1] = in[1]; out[2] = in[2];
+    for (int k = 0; k < F->g_nstage; k++) {
+      if (!F->g_st[k].has_shift) {
+        rot3f(out, F->g_st[k].ab, out);
+        continue;
+      }
+      rot3f(out, F->g_st[k].a, out);
+      if (out[2] <= 0.0f) {
+        out[0] = 0.0f; out[1] = 0.0f; out[2] = -INFINITY;
+      } else {
+        out[0] /= out[2];
+        out[1] /= out[2];
+        out[2] = 1.0f;
+        for (int c = 0; c < 3; c++) out[c] *= F->g_st[k].dcp;
+        for (int c = 0; c < 3; c++) out[c] -= F->g_st[k].shift[c];
+        rot3f(out, F->g_st[k].b, out);
+      }
+    }
+  } else {
   rot3f(in, F->g_t2m, out);
   if (out[2] <= 0.0f) {
     out[0] = 0.0f; out[1] = 0.0f; out[2] = -INFINITY;
@@ -1044,6 +1183,7 @@ static void generic_ray(const target_ctx* T, const facet_ctx* F, float h, float 
     for (int c = 0; c < 3; c++) out[c] *= F->g_dcp;
     for (int c = 0; c < 3; c++) out[c] -= F->g_shift[c];
     rot3f(out, F->g_m2s, out);
+  }
   }
   if (T->normalize) {
     float n = norm3(out);
@@ -1438,8 +1578,73 @@ static void voronoi_plus_group(int nf, const facet_ctx* F, int nl, float (*rays)
   }
 }
 
+static void r3f(double roll, double pitch, double yaw, int inverse, float m[9]) { /* make_r3_t -> r3_t<float> */
+  double d[9];
+  orc_rotation(roll, pitch, yaw, inverse, d);
+  for (int i = 0; i < 9; i++) m[i] = (float)d[i];
+}
+/* tf3d_t ctor, geometry.h:1865-1880 */
+static void tf3d_stage(facet_ctx* F, int k, const float a[9], const float b[9], const float shift[3], float dcp) {
+  memcpy(F->g_st[k].a, a, sizeof(float) * 9);
+  memcpy(F->g_st[k].b, b, sizeof(float) * 9);
+  matmulf(a, b, F->g_st[k].ab);
+  for (int c = 0; c < 3; c++) F->g_st[k].shift[c] = shift[c];
+  F->g_st[k].has_shift = (shift[0] != 0 || shift[1] != 0 || shift[2] != 0);
+  F->g_st[k].dcp = dcp;
+}
+/* a translation given in model space, taken to the CS of its translation plane (envutil_payload.cc:1683-1695) */
+static void plane_shift(const eu_facet_t* f, const float tp[9], float sh[3]) {
+  sh[0] = (float)f->tr_x; sh[1] = (float)f->tr_y; sh[2] = (float)f->tr_z;
+  if (f->tp_y != 0 || f->tp_p != 0 || f->tp_r != 0) { /* rotate(xel_t<double,3>(shift), r): in double */
+    double sd[3] = {sh[0], sh[1], sh[2]}, o[3];
+    for (int c = 0; c < 3; c++) o[c] = (sd[0] * tp[c] + sd[1] * tp[3 + c]) + sd[2] * tp[6 + c];
+    for (int c = 0; c < 3; c++) sh[c] = (float)o[c];
+  }
+}
+/* generic_r3(ft, fs), envutil_payload.cc:1636-1760: target facet ft in the camera position */
+static void generic_r3_setup(const eu_facet_t* ft, const eu_facet_t* fs, facet_ctx* F) {
+  float r_camera[9], rt_tp[9], rt_tpi[9], rs_tp[9], rs_tpi[9], r_facet[9], m1[9], m2[9];
+  r3f(ft->roll, ft->pitch, ft->yaw, 0, r_camera);
+  r3f(ft->tp_r, ft->tp_p, ft->tp_y, 1, rt_tp);
+  r3f(ft->tp_r, ft->tp_p, ft->tp_y, 0, rt_tpi);
+  r3f(fs->tp_r, fs->tp_p, fs->tp_y, 1, rs_tp);
+  r3f(fs->tp_r, fs->tp_p, fs->tp_y, 0, rs_tpi);
+  r3f(fs->roll, fs->pitch, fs->yaw, 1, r_facet);
+  int have_ttp = (ft->tr_x != 0 || ft->tr_y != 0 || ft->tr_z != 0);
+  int have_stp = (fs->tr_x != 0 || fs->tr_y != 0 || fs->tr_z != 0);
+  float shift_t[3], shift_s[3];
+  plane_shift(ft, rt_tp, shift_t);
+  float dcp = (float)(1.0 - shift_t[2]);
+  for (int c = 0; c < 3; c++) shift_t[c] = -shift_t[c];
+  plane_shift(fs, rs_tp, shift_s);
+  if (have_ttp) {
+    matmulf(r_camera, rt_tp, m1);
+    if (have_stp) {
+      tf3d_stage(F, 0, m1, rt_tpi, shift_t, dcp);
+      matmulf(rs_tpi, r_facet, m2);
+      tf3d_stage(F, 1, rs_tp, m2, shift_s, 1.0f);
+      F->g_nstage = 2;
+    } else {
+      matmulf(rt_tpi, r_facet, m2);
+      tf3d_stage(F, 0, m1, m2, shift_t, dcp);
+      F->g_nstage = 1;
+    }
+  } else if (have_stp) {
+    matmulf(r_camera, rs_tp, m1);
+    matmulf(rs_tpi, r_facet, m2);
+    tf3d_stage(F, 0, m1, m2, shift_s, 1.0f);
+    F->g_nstage = 1;
+  } else { /* rotate_t(rotate(r_camera, r_facet)) */
+    const float zero[3] = {0.f, 0.f, 0.f};
+    float id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    tf3d_stage(F, 0, r_camera, r_facet, zero, 1.0f);
+    (void)id;
+    F->g_nstage = 1;
+  }
+}
+
 static int facet_setup(const eu_target_t* t, const eu_opts_t* o, const eu_facet_t* f, const orc_source_t* src,
-                       facet_ctx* F) {
+                       facet_ctx* F, const eu_facet_t* ft) {
   memset(F, 0, sizeof(*F));
   F->src = src;
   F->projection = f->projection;
@@ -1521,6 +1726,10 @@ static int facet_setup(const eu_target_t* t, const eu_opts_t* o, const eu_facet_
     for (int c = 0; c < 3; c++) F->g_shift[c] = sh[c];
     F->g_dcp = 1.0f;
   }
+  if (ft) { /* 'single' target with lens correction / translation: every facet steps generically (:2063-2068) */
+    F->generic = 1;
+    generic_r3_setup(ft, f, F);
+  }
   double step = orc_get_step(f->projection, f->width, f->height, f->hfov);
   F->recip_step = (float)(1.0 / step);
   F->brighten = (float)(f->brighten == 0.0 ? 1.0 : f->brighten);
@@ -1534,8 +1743,25 @@ int orc_render(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   if (nf < 1 || nf > 64) return EU_ERR_ARGUMENT;
   target_ctx T;
   target_setup(t, &T);
+  const eu_facet_t* ft = NULL;
+  if (t->single > 0 && t->single <= nf) {
+    const eu_facet_t* cand = &facets[t->single - 1];
+    if (cand->has_2d_tf || cand->has_translation) ft = cand;
+  }
+  if (ft && ft->has_2d_tf) { /* tf22 = pto_planar<float, L, true>(ft) */
+    T.inv.on = 1;
+    T.inv.has_shear = ft->has_shear;
+    T.inv.has_shift = ft->has_shift;
+    T.inv.has_lcp = ft->has_lcp;
+    T.inv.shear_g = ft->shear_g;
+    T.inv.shear_t = ft->shear_t;
+    T.inv.s = ft->s;
+    T.inv.h = (float)ft->shift_h;
+    T.inv.v = (float)ft->shift_v;
+    if (ft->has_lcp && inv_lcp_setup(&T.inv, ft->a, ft->b, ft->c, ft->r_max) != 0) return -1;
+  }
   facet_ctx* F = (facet_ctx*)calloc((size_t)nf, sizeof(facet_ctx));
-  for (int i = 0; i < nf; i++) facet_setup(t, o, &facets[i], sources[i], &F[i]);
+  for (int i = 0; i < nf; i++) facet_setup(t, o, &facets[i], sources[i], &F[i], ft);
   int nch = t->nchannels;
   int mode = 0;
   int first = 0;

@@ -242,6 +242,16 @@ def _build():
     add("single2_voronoi4_d3_tw2", Job(_voronoi_facets(), "spherical", 360.0, 64, 32, single=2, degree=3, twine=2))
     add("single0_cm_ll", Job([FacetSpec(_cm(32), "cubemap", 90.0), _ll_facet(128)], "spherical", 360.0, 64, 32, single=0))
     tr = _translated_facets()
+    # --single on facets WITH lens correction / shift / shear / translation: the generic stepper runs the
+    # inverse planar transformation (inverse_lcp's spline) and the inverse translation (tf_ex_facet)
+    lf, tf = _lens_facets(), _translated_facets()
+    add("single0_lens3_d1", Job(lf, "spherical", 360.0, 64, 32, single=0))                  # a, b, c, d, e, g, t
+    add("single1_lens3_d3_tw2", Job(lf, "spherical", 360.0, 64, 32, single=1, degree=3, twine=2))
+    add("single2_lens3_d1", Job(lf, "spherical", 360.0, 64, 32, single=2))                  # fisheye target facet
+    add("single0_tr3_d1", Job(tf, "spherical", 360.0, 64, 32, single=0))                    # target translation only
+    add("single1_tr3_d1_tw2", Job(tf, "spherical", 360.0, 64, 32, single=1, twine=2))       # tilted translation plane
+    add("single0_lens_tr_hdr_d1", Job([lf[0], tf[0], tf[1]], "spherical", 360.0, 64, 32, single=0, synopsis="hdr_merge"))
+    add("single1_tr_lens_d1", Job([lf[1], tf[1], lf[2]], "spherical", 360.0, 64, 32, single=1))   # both sides translated
     # cropped output: PTO p-line with an S clause (the steppers see offset discrete coordinates)
     add("cropout_ll_sph_d1", Job([_ll_facet(256)], "spherical", 360.0, 1200, 600, crop_out=(500, 1120, 100, 420)))  # > 1 segment
     add("cropout_ll_rect_d3_tw2", Job([_ll_facet(128)], "rectilinear", 90.0, 160, 120, degree=3, twine=2,

@@ -138,7 +138,8 @@ def test_pto_back_references(cli, tmp_path):
                                   "auto_tw_voronoi_d3", "auto_tw_up_ll_rect_d1", "auto_tw_density_ll_ba6",
                                   "mask_crop4_voronoi_sph_d1", "crop_fish_sph_d1", "mask_grey_sph_d1_tw2",
                                   "win_voronoi_sph_d1", "win_rect_rect_d3_tw2", "single1_hdr3_d1",
-                                  "single2_voronoi4_d3_tw2", "single0_cm_ll", "cropout_ll_sph_d1",
+                                  "single2_voronoi4_d3_tw2", "single0_cm_ll", "single0_lens3_d1",
+                                  "single1_lens3_d3_tw2", "single1_tr3_d1_tw2", "single1_tr_lens_d1", "cropout_ll_sph_d1",
                                   "cropout_ll_rect_d3_tw2", "cropout_ll_cyl_d1_tw2", "cropout_voronoi4_fish_d1"])
 def test_cli_output_equals_reference_output(cli, tmp_path, name):
     """The drop-in claim end to end: the SAME command line given to the reference binary and to
