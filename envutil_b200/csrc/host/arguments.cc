@@ -139,8 +139,8 @@ int arguments::init(int argc, const char** argv) {
   }
   // --twine_precise is accepted and ignored, as in the reference: only environment9 reads it
   // (environment.h:1997), which dispatch::payload never instantiates
-  if (has("--photo") || !split.empty() || has("--mask_for")) {
-    error = "--photo / --split / --mask_for are outside the built path";
+  if (has("--photo") || has("--mask_for")) {
+    error = "--photo / --mask_for are outside the built path";
     return EU_ERR_UNSUPPORTED;
   }
 
@@ -427,20 +427,9 @@ int arguments::init(int argc, const char** argv) {
   // ---- target (envutil_main.cc:1180-1232) -----------------------------------------------
   if (single >= 0) {
     // 'single': the target takes over the facet's geometry (envutil_main.cc:1157-1178)
-    const facet_spec& fs = facet_spec_v[single];
-    t.single = single + 1;  // the kernels invert the facet's lens correction / translation (tf_ex_facet)
-    t.projection = fs.f.projection;
-    projection_str = projection_name[t.projection];
-    t.width = fs.f.width;
-    t.height = fs.f.height;
-    t.hfov = fs.f.hfov;
-    t.yaw = fs.f.yaw;
-    t.pitch = fs.f.pitch;
-    t.roll = fs.f.roll;
-    if (fs.brighten != 1.0) {  // work(): float unbrighten = 1.0 / fct.brighten
-      float unbrighten = 1.0 / fs.brighten;
-      t.gain = unbrighten;
-    }
+    // (extent and step follow below, from the same get_extent call)
+    int rc2 = take_single(single);
+    if (rc2) return rc2;
   } else if (p_line_present) {
     t.hfov = p_line_hfov;
     t.projection = p_line_projection;
@@ -533,6 +522,39 @@ int arguments::twine_setup() {
     int ord = 0;
     for (const auto& c : twine_spread) printf("%d\tx:\t%g\ty:\t%g\tw:\t%g\n", ord++, c.x, c.y, c.w);
   }
+  return EU_OK;
+}
+
+int arguments::take_single(int i) {
+  if (i < 0 || i >= (int)facet_spec_v.size()) {
+    error = "single facet index out of range";
+    return EU_ERR_ARGUMENT;
+  }
+  const facet_spec& fs = facet_spec_v[i];
+  single = i;
+  t.single = i + 1;  // the kernels invert the facet's lens correction / translation (tf_ex_facet)
+  t.projection = fs.f.projection;
+  projection_str = projection_name[t.projection];
+  t.width = fs.f.width;
+  t.height = fs.f.height;
+  t.hfov = fs.f.hfov;
+  t.yaw = fs.f.yaw;
+  t.pitch = fs.f.pitch;
+  t.roll = fs.f.roll;
+  t.gain = 0.0;
+  if (fs.brighten != 1.0) {  // work(): float unbrighten = 1.0 / fct.brighten
+    float unbrighten = 1.0 / fs.brighten;
+    t.gain = unbrighten;
+  }
+  // a 'single' job stores the whole facet (args.store_cropped = false, envutil_main.cc:1714,1726)
+  t.crop_x0 = t.crop_y0 = t.crop_width = t.crop_height = 0;
+  double e[4];
+  eu_get_extent(t.projection, t.width, t.height, t.hfov, e);
+  t.x0 = e[0];
+  t.x1 = e[1];
+  t.y0 = e[2];
+  t.y1 = e[3];
+  t.step = (t.x1 - t.x0) / t.width;
   return EU_OK;
 }
 

@@ -5,6 +5,9 @@
 #include <chrono>
 #include <cstdio>
 
+#include <algorithm>
+#include <vector>
+
 #include "envutil_host.h"
 
 namespace eu_host {
@@ -141,6 +144,28 @@ int core(int argc, const char** argv) {
              f.f.hfov, f.f.yaw, f.f.pitch, f.f.roll, f.f.step, f.brighten, f.f.has_lcp, f.f.shift_h, f.f.shift_v,
              f.f.shear_g, f.f.shear_t);
     for (const auto& c : args.twine_spread) printf("tap %.9g %.9g %.9g\n", c.x, c.y, c.w);
+    return 0;
+  }
+  if (!args.split.empty()) {  // one 'single' job per facet, envutil_main.cc:1679-1721
+    // image_series (envutil_basic.h:212-263): one '%' makes the name a printf format for the facet number
+    const bool is_format = std::count(args.split.begin(), args.split.end(), '%') == 1;
+    for (int i = 0; i < args.nfacets; i++) {
+      if (i == args.solo) continue;  // the solo facet is what the others are re-created from
+      rc = args.take_single(i);
+      if (rc) {
+        fprintf(stderr, "envutil_b200: %s\n", args.error.c_str());
+        return rc;
+      }
+      if (is_format) {
+        std::vector<char> buffer(args.split.size() + 16);
+        snprintf(buffer.data(), buffer.size(), args.split.c_str(), i);
+        args.output = buffer.data();
+      } else {
+        args.output = args.split;
+      }
+      rc = dp->payload(nch, ninp, args.t.projection);
+      if (rc) return rc;
+    }
     return 0;
   }
   return dp->payload(nch, ninp, args.t.projection);

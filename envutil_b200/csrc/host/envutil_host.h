@@ -57,6 +57,9 @@ struct arguments {
   // reason in `error` (the reference asserts / exit(-1)s instead)
   int init(int argc, const char** argv);
   int twine_setup();
+  // (facet_base&) args = facet_spec_v[i]; args.single = i - the target takes over facet i's geometry
+  // (envutil_main.cc:1157-1178 and the --split loop, :1679-1721)
+  int take_single(int i);
   std::string error;
 };
 

@@ -278,3 +278,11 @@ CLI_EXTRAS = {
     "twf_ll_rect_d1": ("ll_rect_d1_rot", "-0.3 -0.2 1\n0.3 -0.2 2\n0.0 0.35 3\n0.1 0.0 1.5\n", ["--twine_normalize"]),
     "twf_raw_voronoi_d1": ("voronoi4_sph_d1", "-0.25 0 0.5\n0.25 0 0.5\n", ["--twine_width", "1.5"]),
 }
+
+
+# --split FORMAT runs of the reference CLI (one output per facet, the solo facet excepted): name ->
+# (base job, extra command-line arguments). Golden: manifest[name]["outputs"][facet] = shape + sha256.
+SPLITS = {
+    "split_lens3_d1": ("lens3_voronoi_sph_d1", []),
+    "split_tr3_solo2_d1_tw2": ("tr3_voronoi_sph_d1", ["--solo", "2", "--twine", "2"]),
+}

@@ -177,6 +177,31 @@ def test_cli_twf_filter_equals_reference(cli, tmp_path, name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(jobs.SPLITS))
+def test_cli_split_equals_reference(cli, tmp_path, name):
+    """--split FORMAT: one 'single' job per facet (the solo facet excepted), each through the inverse
+    lens / translation path where the facet has one; every file equals the reference's."""
+    import hashlib
+    import json
+    man = json.load(open(os.path.join(harness.GOLDEN, "manifest.json")))[name]
+    base, extra = jobs.SPLITS[name]
+    job = jobs.JOBS[base]
+    paths = _write_facets(job, str(tmp_path))
+    args = job.cli_args(paths, "unused.euf")
+    k = args.index("--output")
+    del args[k:k + 2]
+    r = subprocess.run([cli] + args + extra + ["--split", str(tmp_path / "re%02d.euf")], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    made = sorted(p.name for p in tmp_path.glob("re*.euf"))
+    assert made == sorted("re%02d.euf" % int(i) for i in man["outputs"])
+    for i, want in man["outputs"].items():
+        img = euf.read_euf(str(tmp_path / ("re%02d.euf" % int(i))))
+        assert list(img.shape) == want["shape"]
+        assert hashlib.sha256(np.ascontiguousarray(img, dtype="<f4").tobytes()).hexdigest() == want["sha256"], i
+
+
+@pytest.mark.gpu
 def test_cli_pipe_mode_keeps_sources_staged(cli, tmp_path):
     job = jobs.JOBS["cm_sph_d3"]
     p = _write_facets(job, str(tmp_path))[0]

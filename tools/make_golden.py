@@ -69,6 +69,34 @@ def main():
                           "sha256": hashlib.sha256(np.ascontiguousarray(pm, dtype="<f4").tobytes()).hexdigest(),
                           "cli_extra": True}
         print(name, manifest[name]["sha256"][:12])
+    import subprocess
+    from envutil_b200 import euf
+    for name, (base, extra) in sorted(jobs.SPLITS.items()):  # --split: one output per facet
+        job = jobs.JOBS[base]
+        for attempt in range(6):
+            with tempfile.TemporaryDirectory(prefix="euref_") as d:
+                paths = []
+                for i, f in enumerate(job.facets):
+                    paths.append(os.path.join(d, "facet%d.euf" % i))
+                    euf.write_euf(paths[-1], f.image)
+                args = job.cli_args(paths, "unused.euf")
+                k = args.index("--output")
+                del args[k:k + 2]
+                r = subprocess.run([harness.ref_binary("pm")] + args + extra + ["--split", os.path.join(d, "re%02d.euf")],
+                                   capture_output=True, text=True)
+                if r.returncode == -11 and attempt < 5:  # see _retry
+                    continue
+                assert r.returncode == 0, r.stderr[-2000:]
+                outs = {}
+                for i in range(len(job.facets)):
+                    q = os.path.join(d, "re%02d.euf" % i)
+                    if os.path.exists(q):
+                        img = euf.read_euf(q)
+                        outs[str(i)] = {"shape": list(img.shape),
+                                        "sha256": hashlib.sha256(np.ascontiguousarray(img, dtype="<f4").tobytes()).hexdigest()}
+                manifest[name] = {"split": True, "base": base, "extra": extra, "outputs": outs}
+                print(name, sorted(outs))
+                break
     with open(os.path.join(harness.GOLDEN, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 
