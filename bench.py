@@ -427,7 +427,7 @@ def ours(args):
     # upload of step n+1 overlaps the download of step n
     DEPTH = 3
     ring = [h_out] + [torch.empty((H, W, C), dtype=torch.float32).pin_memory() for _ in range(DEPTH - 1)]
-    pipe_steps = max(e2e_steps, 4 * DEPTH)
+    pipe_steps = max(e2e_steps, 8 * DEPTH)
 
     finish_stamps = []
 

@@ -176,6 +176,53 @@ def test_cli_twf_filter_equals_reference(cli, tmp_path, name):
     assert hashlib.sha256(np.ascontiguousarray(img, dtype="<f4").tobytes()).hexdigest() == man["sha256"]
 
 
+FACES = ["left", "right", "top", "bottom", "front", "back"]
+
+
+def test_cubeface_series_input_is_one_cubemap(cli, tmp_path):
+    """A facet name with one '%' is a cubeface series (envutil_basic.h:267-356): six square images named
+    by direction stand for the 1:6 stripe. Dry run: the job is the same as for the stripe in one file."""
+    job = jobs.JOBS["cm_sph_d3"]
+    img = job.facets[0].image
+    F = img.shape[1]
+    for i, n in enumerate(FACES):
+        euf.write_euf(str(tmp_path / ("face_%s.euf" % n)), np.ascontiguousarray(img[i * F:(i + 1) * F]))
+    one = _write_facets(job, str(tmp_path))
+    a = subprocess.run([cli] + job.cli_args([str(tmp_path / "face_%s.euf")], "o.euf") + ["--dry_run"], capture_output=True,
+                       text=True)
+    b = subprocess.run([cli] + job.cli_args(one, "o.euf") + ["--dry_run"], capture_output=True, text=True)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    strip = lambda out: [re.sub(r"^(facet \d+) \S+", r"\1", l) for l in out.splitlines()]  # the file name differs
+    assert strip(a.stdout) == strip(b.stdout)
+
+
+@pytest.mark.gpu
+def test_cli_cubeface_series_in_and_out(cli, tmp_path):
+    """Six-file cubemaps on both sides: reading a series gives the reference's output for the stripe
+    (golden), writing a cubemap to a '%' name gives six files that are the faces of the stripe."""
+    import hashlib
+    import json
+    man = json.load(open(os.path.join(harness.GOLDEN, "manifest.json")))
+    job = jobs.JOBS["cm_sph_d3"]
+    img = job.facets[0].image
+    F = img.shape[1]
+    for i, n in enumerate(FACES):
+        euf.write_euf(str(tmp_path / ("face_%s.euf" % n)), np.ascontiguousarray(img[i * F:(i + 1) * F]))
+    outp = str(tmp_path / "o.euf")
+    r = subprocess.run([cli] + job.cli_args([str(tmp_path / "face_%s.euf")], outp), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = euf.read_euf(outp)
+    assert hashlib.sha256(np.ascontiguousarray(got, dtype="<f4").tobytes()).hexdigest() == man["cm_sph_d3"]["sha256"]
+    job = jobs.JOBS["ll_cube_d1"]
+    p = _write_facets(job, str(tmp_path))
+    r = subprocess.run([cli] + job.cli_args(p, str(tmp_path / "out_%s.euf")), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    faces = [euf.read_euf(str(tmp_path / ("out_%s.euf" % n))) for n in FACES]
+    whole = np.concatenate(faces, axis=0)
+    assert list(whole.shape) == man["ll_cube_d1"]["shape"]
+    assert hashlib.sha256(np.ascontiguousarray(whole, dtype="<f4").tobytes()).hexdigest() == man["ll_cube_d1"]["sha256"]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(jobs.SPLITS))
 def test_cli_split_equals_reference(cli, tmp_path, name):
