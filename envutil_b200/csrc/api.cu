@@ -843,7 +843,11 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
   int launches = 0;
   float copy_ms = 0;
   CK(cudaEventRecord(g.ev[0], st));
-  rc = stage_on_device(f, o, pixels, kind, st, async ? g.up_stream : st, s, &launches, &copy_ms);
+  // Host rasters ALWAYS travel on the upload stream, also for the blocking entry point: the staging /
+  // render stream then never issues a PCIe copy itself. (Measured: once it had - blocking calls before
+  // pipelined ones - the pipelined uploads and downloads stopped overlapping, 9 -> 20-50 ms per frame.)
+  rc = stage_on_device(f, o, pixels, kind, st, (async || kind == cudaMemcpyHostToDevice) ? g.up_stream : st, s, &launches,
+                       &copy_ms);
   if (rc == EU_OK) rc = maybe_pad(o, s, st, &launches);
   if (rc != EU_OK) return rc;
   CK(cudaEventRecord(g.ev[1], st));
@@ -1075,10 +1079,13 @@ int eu_render(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_f
   eu_timing_t tm;
   rc = eu_render_rows(t, o, n_facets, facets, sources, taps, n_taps, 0, out_height(t), g.d_out, g.stream, &tm);
   if (rc) return rc;
-  CK(cudaEventRecord(g.ev[2], g.stream));
-  CK(cudaMemcpyAsync(out, g.d_out, n * sizeof(float), cudaMemcpyDeviceToHost, g.stream));
-  CK(cudaEventRecord(g.ev[3], g.stream));
-  CK(cudaStreamSynchronize(g.stream));
+  // the download runs on the download stream, for the same reason as the upload above
+  CK(cudaEventRecord(g.ev[1], g.stream));
+  CK(cudaStreamWaitEvent(g.down_stream, g.ev[1], 0));
+  CK(cudaEventRecord(g.ev[2], g.down_stream));
+  CK(cudaMemcpyAsync(out, g.d_out, n * sizeof(float), cudaMemcpyDeviceToHost, g.down_stream));
+  CK(cudaEventRecord(g.ev[3], g.down_stream));
+  CK(cudaStreamSynchronize(g.down_stream));
   if (timing) {
     *timing = tm;
     CK(cudaEventElapsedTime(&timing->d2h_ms, g.ev[2], g.ev[3]));
