@@ -1214,7 +1214,13 @@ int eu_source_reserve(const char* asset_key, const eu_facet_t* f, const eu_opts_
   g.sources.push_back(s);
   if (asset_key && *asset_key) {
     s->key = asset_key;
-    g.by_key[s->key] = s;
+    auto it = g.by_key.find(s->key);
+    if (it != g.by_key.end()) {  // replaced: the old object stays alive until released / aged out
+      it->second->key.clear();
+      it->second = s;
+    } else {
+      g.by_key[s->key] = s;
+    }
   }
   *out = s;
   *d_core = s->container + (size_t)s->ly * s->pitch + (size_t)s->lx * s->nch;

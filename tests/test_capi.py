@@ -31,15 +31,16 @@ def test_struct_layout_matches_header(lib, tmp_path):
     """sizeof/offsetof as the C compiler sees the header == the ctypes mirror."""
     prog = tmp_path / "layout.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "envutil_b200.h"\n'
-                    'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(eu_facet_t), sizeof(eu_target_t),'
+                    'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(eu_facet_t), sizeof(eu_target_t),'
                     'sizeof(eu_opts_t), sizeof(eu_tap_t), sizeof(eu_timing_t), offsetof(eu_facet_t, brighten),'
-                    'offsetof(eu_facet_t, shift_h), offsetof(eu_facet_t, window_width));return 0;}\n')
+                    'offsetof(eu_facet_t, shift_h), offsetof(eu_facet_t, window_width), offsetof(eu_target_t, crop_x0),'
+                    'offsetof(eu_target_t, single));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(capi.Facet), C.sizeof(capi.Target), C.sizeof(capi.Opts), C.sizeof(capi.Tap),
             C.sizeof(capi.Timing), capi.Facet.brighten.offset, capi.Facet.shift_h.offset,
-            capi.Facet.window_width.offset]
+            capi.Facet.window_width.offset, capi.Target.crop_x0.offset, capi.Target.single.offset]
     assert got == want
 
 
@@ -61,6 +62,11 @@ def test_no_cpu_fallback(lib):
     assert lib.eu_render(C.byref(t), C.byref(o), 0, None, None, None, 0, None, None) == -5  # EU_ERR_STATE
     assert lib.eu_cycle() == -5
     assert lib.eu_source_find(b"x") is None
+    f, h, ptr, pitch = capi.Facet(), capi.SourceH(), C.c_void_p(), C.c_int()
+    assert lib.eu_source_reserve(None, C.byref(f), C.byref(o), C.byref(h), C.byref(ptr), C.byref(pitch)) == -5
+    assert lib.eu_render_rows_pitched(C.byref(t), C.byref(o), 0, None, None, None, 0, 0, 1, None, 0, None, None) == -5
+    assert lib.eu_frame_alloc(16, C.byref(ptr)) == -5
+    assert lib.eu_frame_open(b"\0" * 64, C.byref(ptr)) == -5
 
 
 def test_product_does_not_reference_the_oracle():
