@@ -857,7 +857,11 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
     CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
     CK(cudaEventElapsedTime(&copy_ms, g.ev[2], g.ev[3]));
     bool host = kind == cudaMemcpyHostToDevice;
-    t->render_ms = host ? ms - copy_ms : ms;  // staging kernels (device-side placement copy included)
+    // staging kernels (a device-side placement copy included). Host rasters arrive on the upload stream
+    // and the staging stream waits for ev[3], the end of the copies: the kernels are what lies between
+    // that event and ev[1] (the allocation and the clear happen on the upload stream, before ev[2]).
+    if (host) CK(cudaEventElapsedTime(&ms, g.ev[3], g.ev[1]));
+    t->render_ms = ms;
     t->h2d_ms = host ? copy_ms : 0.0f;
     t->d2h_ms = 0;
     t->launches = launches;

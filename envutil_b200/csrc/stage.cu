@@ -439,13 +439,26 @@ __device__ __forceinline__ int brace_map(int i, int n, int bc) {
   if (i >= n) return bc == EU_BC_PERIODIC ? i - n : 2 * n - 1 - i;
   return i;
 }
+// The launch covers the frame only: (ly + ry) full container rows, then (lx + rx) columns beside the
+// core rows - a few thousand texels, not the whole container.
 __global__ void k_brace(float* core, int stride, int nch, int w, int h, int lx, int rx, int ly, int ry, int bc0,
                         int bc1, int spherical) {
-  int cw = w + lx + rx, chh = h + ly + ry;
-  int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y;
-  if (X >= cw || Y >= chh) return;
+  const int cw = w + lx + rx;
+  const long long n_rows = (long long)cw * (ly + ry), n_cols = (long long)(lx + rx) * h;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows + n_cols) return;
+  int X, Y;  // container coordinates
+  if (i < n_rows) {
+    int r = (int)(i / cw);
+    X = (int)(i - (long long)r * cw);
+    Y = r < ly ? r : h + r;  // rows 0..ly-1 above the core, rows ly+h.. below it
+  } else {
+    long long j = i - n_rows;
+    int r = (int)(j / (lx + rx)), c = (int)(j - (long long)r * (lx + rx));
+    Y = ly + r;
+    X = c < lx ? c : w + c;  // columns 0..lx-1 left of the core, columns lx+w.. right of it
+  }
   int x = X - lx, y = Y - ly;
-  if (x >= 0 && x < w && y >= 0 && y < h) return;
   int sx = brace_map(x, w, bc0), sy;
   if (spherical && (y < 0 || y >= h)) {
     sy = y < 0 ? -1 - y : 2 * h - 1 - y;
@@ -647,9 +660,9 @@ cudaError_t eu_launch_brace_natural_1d(float* core, int n, int k, cudaStream_t s
 
 cudaError_t eu_launch_brace(float* core, int stride, int nch, int w, int h, int lx, int rx, int ly, int ry, int bc0,
                             int bc1, int spherical, cudaStream_t st) {
-  int cw = w + lx + rx, chh = h + ly + ry;
-  dim3 grid((cw + 127) / 128, chh);
-  k_brace<<<grid, 128, 0, st>>>(core, stride, nch, w, h, lx, rx, ly, ry, bc0, bc1, spherical);
+  const long long n = (long long)(w + lx + rx) * (ly + ry) + (long long)(lx + rx) * h;
+  if (n <= 0) return cudaSuccess;
+  k_brace<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(core, stride, nch, w, h, lx, rx, ly, ry, bc0, bc1, spherical);
   return cudaGetLastError();
 }
 
