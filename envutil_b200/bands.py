@@ -15,6 +15,22 @@ def bands(height, world):
     return [band(height, world, r) for r in range(world)]
 
 
+def weighted_bands(row_cost, world):
+    """Contiguous bands with (nearly) equal summed cost - SURVEY 8e: 'optionally balance by cost' where
+    the per-row work varies (rows of a panorama that no facet covers, fisheye corners ...). row_cost:
+    one non-negative number per row. Every band has at least one row; returns [(row0, row1)] * world."""
+    import numpy as np
+    cost = np.asarray(row_cost, dtype=np.float64)
+    height = int(cost.size)
+    if world < 1 or height < world:
+        raise ValueError("need at least one row per rank")
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    edges = [0] + [int(np.searchsorted(cum, cum[-1] * k / world)) for k in range(1, world)] + [height]
+    for k in range(1, world):            # strictly increasing, leaving a row for every later band
+        edges[k] = min(max(edges[k], edges[k - 1] + 1), height - (world - k))
+    return [(edges[k], edges[k + 1]) for k in range(world)]
+
+
 def gather_bands(local, height, world, rank, dist, dst=0):
     """Assemble the full frame on `dst` from per-rank band tensors (torch.distributed; works with
     gloo on CPU tensors and nccl on CUDA tensors). Bands may be ragged (height % world != 0):

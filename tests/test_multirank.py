@@ -26,6 +26,34 @@ def test_band_partition_properties():
         bands.band(10, 2, 2)
 
 
+def test_weighted_bands():
+    import json
+    import math
+    for world in (1, 2, 3, 8):  # uniform cost = the plain partition (up to where the odd row goes)
+        wb = bands.weighted_bands(np.ones(4096), world)
+        assert wb[0][0] == 0 and wb[-1][1] == 4096 and all(a[1] == b[0] for a, b in zip(wb, wb[1:]))
+        assert max(b - a for a, b in wb) - min(b - a for a, b in wb) <= 1
+    wb = bands.weighted_bands([0, 0, 0, 10, 0, 0, 0, 0], 4)  # all the work in one row: still one row each
+    assert all(b > a for a, b in wb) and wb[-1][1] == 8
+    with pytest.raises(ValueError):
+        bands.weighted_bands([1.0, 1.0], 3)
+    # the cost model of tools/bench_c5_multi.py (stage B per covered row + stage A rows it owns)
+    # reproduces the bands recorded with the measured runs
+    H, W, h, w, P = 8192, 16384, 4000, 6000, 6
+    vext = math.tan(math.radians(50.0)) * h / w
+    to_row = lambda v: (v / (2.0 * vext) + 0.5) * h - 0.5
+    lat = (np.arange(H + 1) / H - 0.5) * math.pi
+    lim = math.radians(89.9)
+    fr = np.clip(to_row(np.tan(np.clip(lat, -lim, lim))), 0.0, float(h))
+    corner = math.atan(math.tan(math.radians(50.0)) * h / w / math.cos(math.radians(50.0)))
+    mid = 0.5 * (lat[:-1] + lat[1:])
+    cost = W * np.where(np.abs(mid) <= corner, 26.0, 6.0) + P * w * np.diff(fr) * 35.0
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for world in (2, 4, 8):
+        rec = json.load(open(os.path.join(root, "profiles", "r01g_c5_pipeline_n%d.json" % world)))["bands"]
+        assert [list(b) for b in bands.weighted_bands(cost, world)] == rec
+
+
 def _worker(rank, world, port, name, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

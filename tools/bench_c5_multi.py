@@ -118,13 +118,7 @@ def main():
         corner = math.atan(math.tan(math.radians(50.0)) * h / w / math.cos(math.radians(50.0)))  # highest latitude in sight
         mid = 0.5 * (lat[:-1] + lat[1:])
         cost = W_pano * np.where(np.abs(mid) <= corner, 26.0, 6.0) + P * w * np.diff(fr) * 35.0
-        cum = np.concatenate([[0.0], np.cumsum(cost)])
-        cuts = [int(np.searchsorted(cum, cum[-1] * k / world)) for k in range(1, world)]
-        edges = [0] + cuts + [H_pano]
-        for k in range(1, len(edges)):  # strictly increasing
-            edges[k] = max(edges[k], edges[k - 1] + 1)
-        edges[-1] = H_pano
-        return [(edges[k], edges[k + 1]) for k in range(world)]
+        return eu_bands.weighted_bands(cost, world)
     all_bands = eu_bands.bands(H_pano, world)
     if a.plan == "stripes" and a.bands == "cost" and world > 1 and a.gather == "peer":  # gather_bands wants equal bands
         all_bands = cost_bands()
