@@ -599,13 +599,11 @@ static bool launch_iir_x_rows(float* core, int stride, int w, int h, const IirDe
   rpb = std::min(rpb, std::max(1, (h + 295) / 296));  // small rasters: spread the rows over the SMs
   const int threads = ((rpb * NCH + 31) / 32) * 32;
   const size_t smem = (size_t)rpb * row_bytes;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(k_iir_x_rows<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
-      cudaGetLastError();  // not sticky: the tiled kernel takes over
-      return false;
-    }
-    configured = true;
+  // per launch, not once: the attribute belongs to the device the library is initialised on, and that
+  // may change between eu_shutdown and the next eu_init
+  if (cudaFuncSetAttribute(k_iir_x_rows<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
+    cudaGetLastError();  // not sticky: the tiled kernel takes over
+    return false;
   }
   k_iir_x_rows<NCH><<<(h + rpb - 1) / rpb, threads, smem, st>>>(core, stride, w, h, f, rpb, lead, span);
   return true;
