@@ -56,7 +56,7 @@ int arguments::init(int argc, const char** argv) {
   *this = arguments();
   std::map<std::string, std::string> one;        // last value of single-valued options
   std::vector<std::vector<std::string>> facets;  // --facet IMAGE PROJECTION HFOV YAW PITCH ROLL
-  std::vector<std::string> inputs;
+  std::vector<std::string> inputs, photos;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     const option* o = nullptr;
@@ -78,6 +78,8 @@ int arguments::init(int argc, const char** argv) {
       addenda.push_back(argv[i + 1]);
     } else if (a == "--input") {
       inputs.push_back(argv[i + 1]);
+    } else if (a == "--photo") {
+      photos.push_back(argv[i + 1]);
     } else {
       one[a] = argv[i + 1];
     }
@@ -129,7 +131,7 @@ int arguments::init(int argc, const char** argv) {
     error = "unknown projection '" + projection_str + "'";
     return EU_ERR_ARGUMENT;
   }
-  if (pto_file.empty() && addenda.empty() && facets.empty() && inputs.empty() && !has("--photo")) {
+  if (pto_file.empty() && addenda.empty() && facets.empty() && inputs.empty() && photos.empty()) {
     error = "no facets: give --facet, --input, --pto or --pto_line";
     return EU_ERR_ARGUMENT;
   }
@@ -139,8 +141,8 @@ int arguments::init(int argc, const char** argv) {
   }
   // --twine_precise is accepted and ignored, as in the reference: only environment9 reads it
   // (environment.h:1997), which dispatch::payload never instantiates
-  if (has("--photo") || has("--mask_for")) {
-    error = "--photo / --mask_for are outside the built path";
+  if (has("--mask_for")) {
+    error = "--mask_for is outside the built path";
     return EU_ERR_UNSUPPORTED;
   }
 
@@ -347,6 +349,9 @@ int arguments::init(int argc, const char** argv) {
       return EU_ERR_ARGUMENT;
     }
   }
+  // --photo IMAGE (envutil_main.cc:916-927): projection and hfov from the image's metadata, and where
+  // there is none - .euf rasters carry none - "rectilinear" and 65 degrees (envutil_basic.h:596-627)
+  for (const auto& ph : photos) facets.push_back({ph, "rectilinear", "65", "0", "0", "0"});
   for (const auto& fv : facets) {
     facet_spec fs;
     fs.filename = fv[0];

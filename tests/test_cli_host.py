@@ -87,6 +87,24 @@ def test_input_alias_and_spline_degree(cli, tmp_path):
     assert a.stdout == b.stdout and "degree 3" in a.stdout
 
 
+def test_photo_is_a_rectilinear_65_degree_facet(cli, tmp_path):
+    """--photo IMAGE (envutil_main.cc:916-927): projection and hfov come from image metadata; without any
+    (.euf has none) the reference assumes rectilinear, 65 degrees. Photos are numbered after the facets."""
+    job = jobs.JOBS["rect_src_sph_d1"]
+    p = _write_facets(job, str(tmp_path))[0]
+    base = ["--projection", "spherical", "--hfov", "360", "--width", "128", "--height", "64", "--twine", "0",
+            "--output", str(tmp_path / "o.euf"), "--dry_run"]
+    a = subprocess.run([cli, "--photo", p] + base, capture_output=True, text=True)
+    b = subprocess.run([cli, "--facet", p, "rectilinear", "65", "0", "0", "0"] + base, capture_output=True, text=True)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    assert a.stdout == b.stdout and "rectilinear" in a.stdout
+    c = subprocess.run([cli, "--photo", p, "--facet", p, "rectilinear", "80", "30", "0", "0"] + base, capture_output=True,
+                       text=True)
+    fl = [l for l in c.stdout.splitlines() if l.startswith("facet ")]
+    assert c.returncode == 0 and len(fl) == 2
+    assert _floats(fl[0], "hfov")[0] == 80 * (np.pi / 180.0) and _floats(fl[1], "hfov")[0] == 65 * (np.pi / 180.0)
+
+
 def test_pipe_mode_and_errors(cli, tmp_path):
     job = jobs.JOBS["ll_rect_d1"]
     p = _write_facets(job, str(tmp_path))[0]
