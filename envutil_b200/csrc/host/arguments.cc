@@ -202,52 +202,88 @@ int arguments::init(int argc, const char** argv) {
       facet_spec fs;
       fs.facet_no = nfacets++;
       if (!ln.get("Pano").empty()) {
-        error = "i-line Pano clause (unstitching) is outside the built path";
-        return EU_ERR_UNSUPPORTED;
-      }
-      fs.filename = ln.get("n");
-      if (!fs.filename.empty() && fs.filename[0] == '"') fs.filename = fs.filename.substr(1, fs.filename.size() - 2);
-      fs.asset_key = fs.filename;
-      int prj = iglean(ln.get("f"));
-      if (prj == 0) fs.f.projection = EU_RECTILINEAR;
-      else if (prj == 1) fs.f.projection = EU_CYLINDRICAL;
-      else if (prj == 2 || prj == 3) fs.f.projection = EU_FISHEYE;
-      else if (prj == 4) fs.f.projection = EU_SPHERICAL;
-      else if (prj == 10) fs.f.projection = EU_STEREOGRAPHIC;
-      else {
-        error = "can't handle PTO projection code " + std::to_string(prj) + " in i-line";
-        return EU_ERR_ARGUMENT;
-      }
-      int w, h, c;
-      if (!read_raster_header(fs.filename, w, h, c)) {
-        error = "failed to open facet image '" + fs.filename + "'";
-        return EU_ERR_ARGUMENT;
-      }
-      fs.f.width = w;
-      fs.f.height = h;
-      fs.f.nchannels = c;
-      fs.f.hfov = (M_PI / 180.0) * std::stod(ln.get("v"));
-      {  // 'W x0,x1,y0,y1': the file holds a window of an image of w x h pixels (envutil_main.cc:754-786)
-        const std::string& win = ln.get("W");
-        if (!win.empty()) {
-          int v[4];
-          if (sscanf(win.c_str(), "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) != 4) {
-            error = "bad W clause '" + win + "'";
+        // 'Pano' clause, envutil_main.cc:673-712: this facet IS the stitched panorama - it takes the p-line's
+        // projection, field of view and crop, and becomes the solo facet the others are re-created from
+        // (--split, "unstitching")
+        if (!p_line_present) {
+          error = "an i-line with a Pano clause needs a p-line";
+          return EU_ERR_ARGUMENT;
+        }
+        fs.filename = ln.get("Pano");
+        if (!fs.filename.empty() && fs.filename[0] == '"') fs.filename = fs.filename.substr(1, fs.filename.size() - 2);
+        fs.asset_key = fs.filename;
+        fs.f.projection = p_line_projection;
+        fs.f.hfov = p_line_hfov;
+        int w, h, c;
+        if (!read_raster_header(fs.filename, w, h, c)) {
+          error = "failed to open facet image '" + fs.filename + "'";
+          return EU_ERR_ARGUMENT;
+        }
+        fs.f.width = w;
+        fs.f.height = h;
+        fs.f.nchannels = c;
+        if (store_cropped) {  // the file holds the crop window of the p-line's panorama
+          if (p_crop_x1 - p_crop_x0 != w || p_crop_y1 - p_crop_y0 != h) {
+            error = "the Pano image must have the size of the p-line's crop window";
             return EU_ERR_ARGUMENT;
           }
-          fs.f.window_x_offset = v[0];
-          fs.f.window_y_offset = v[2];
-          fs.f.window_width = v[1] - v[0];
-          fs.f.window_height = v[3] - v[2];
-          if (fs.f.window_width != w || fs.f.window_height != h) {
-            error = "the W window must have the size of the image file";
+          fs.f.width = p_line_width;
+          fs.f.height = p_line_height;
+          fs.f.window_x_offset = p_crop_x0;
+          fs.f.window_y_offset = p_crop_y0;
+          fs.f.window_width = w;
+          fs.f.window_height = h;
+          if (fs.f.width < p_crop_x1 || fs.f.height < p_crop_y1) {
+            error = "the p-line's crop window does not lie inside its panorama";
             return EU_ERR_ARGUMENT;
           }
-          fs.f.width = iglean(ln.get("w"));
-          fs.f.height = iglean(ln.get("h"));
-          if (fs.f.width == 0 || fs.f.height == 0) {
-            error = "a W window needs the total size (w, h)";
-            return EU_ERR_ARGUMENT;
+        }
+        solo = fs.facet_no;
+      } else {
+        fs.filename = ln.get("n");
+        if (!fs.filename.empty() && fs.filename[0] == '"') fs.filename = fs.filename.substr(1, fs.filename.size() - 2);
+        fs.asset_key = fs.filename;
+        int prj = iglean(ln.get("f"));
+        if (prj == 0) fs.f.projection = EU_RECTILINEAR;
+        else if (prj == 1) fs.f.projection = EU_CYLINDRICAL;
+        else if (prj == 2 || prj == 3) fs.f.projection = EU_FISHEYE;
+        else if (prj == 4) fs.f.projection = EU_SPHERICAL;
+        else if (prj == 10) fs.f.projection = EU_STEREOGRAPHIC;
+        else {
+          error = "can't handle PTO projection code " + std::to_string(prj) + " in i-line";
+          return EU_ERR_ARGUMENT;
+        }
+        int w, h, c;
+        if (!read_raster_header(fs.filename, w, h, c)) {
+          error = "failed to open facet image '" + fs.filename + "'";
+          return EU_ERR_ARGUMENT;
+        }
+        fs.f.width = w;
+        fs.f.height = h;
+        fs.f.nchannels = c;
+        fs.f.hfov = (M_PI / 180.0) * std::stod(ln.get("v"));
+        {  // 'W x0,x1,y0,y1': the file holds a window of an image of w x h pixels (envutil_main.cc:754-786)
+          const std::string& win = ln.get("W");
+          if (!win.empty()) {
+            int v[4];
+            if (sscanf(win.c_str(), "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) != 4) {
+              error = "bad W clause '" + win + "'";
+              return EU_ERR_ARGUMENT;
+            }
+            fs.f.window_x_offset = v[0];
+            fs.f.window_y_offset = v[2];
+            fs.f.window_width = v[1] - v[0];
+            fs.f.window_height = v[3] - v[2];
+            if (fs.f.window_width != w || fs.f.window_height != h) {
+              error = "the W window must have the size of the image file";
+              return EU_ERR_ARGUMENT;
+            }
+            fs.f.width = iglean(ln.get("w"));
+            fs.f.height = iglean(ln.get("h"));
+            if (fs.f.width == 0 || fs.f.height == 0) {
+              error = "a W window needs the total size (w, h)";
+              return EU_ERR_ARGUMENT;
+            }
           }
         }
       }
@@ -278,7 +314,7 @@ int arguments::init(int argc, const char** argv) {
         eev_sum += fs.brighten;
         eev_count++;
       }
-      fs.native_nchannels = c;
+      fs.native_nchannels = fs.f.nchannels;
       {  // lens crop "S x0,x1,y0,y1" (envutil_main.cc:811-822)
         const std::string& crop = ln.get("S");
         if (!crop.empty()) {

@@ -105,6 +105,37 @@ def test_photo_is_a_rectilinear_65_degree_facet(cli, tmp_path):
     assert _floats(fl[0], "hfov")[0] == 80 * (np.pi / 180.0) and _floats(fl[1], "hfov")[0] == 65 * (np.pi / 180.0)
 
 
+def test_pano_clause_is_a_solo_panorama_facet(cli, tmp_path):
+    """i-line 'Pano' clause (envutil_main.cc:673-712, 'unstitching'): the facet takes the p-line's projection,
+    hfov (and crop) and becomes the solo facet that --split re-creates the others from. The job equals the
+    one spelled out with an ordinary i-line, --solo and an explicit target (the reference binary gives
+    bit-identical files for the two forms; checked when this test was written)."""
+    pano = np.zeros((64, 128, 3), np.float32)
+    euf.write_euf(str(tmp_path / "pano.euf"), pano)
+    for n in ("a", "b"):
+        euf.write_euf(str(tmp_path / (n + ".euf")), np.zeros((64, 96, 3), np.float32))
+    rest = ('i w96 h64 f0 v80 y30 p10 r5 a0.01 b-0.02 n"%s"\ni w96 h64 f0 v70 y-40 p-5 r0 TrX0.02 n"%s"\n'
+            % (tmp_path / "a.euf", tmp_path / "b.euf"))
+    (tmp_path / "A.pto").write_text('p f2 w128 h64 v360\ni w128 h64 f4 v360 y0 p0 r0 Pano"%s"\n' % (tmp_path / "pano.euf") + rest)
+    (tmp_path / "B.pto").write_text('i w128 h64 f4 v360 y0 p0 r0 n"%s"\n' % (tmp_path / "pano.euf") + rest)
+    common = ["--twine", "0", "--split", str(tmp_path / "re%02d.euf"), "--dry_run"]
+    a = subprocess.run([cli, "--pto", str(tmp_path / "A.pto")] + common, capture_output=True, text=True)
+    b = subprocess.run([cli, "--pto", str(tmp_path / "B.pto"), "--solo", "0", "--projection", "spherical", "--hfov", "360",
+                        "--width", "128", "--height", "64"] + common, capture_output=True, text=True)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    assert a.stdout == b.stdout and "solo 0" in a.stdout
+    # cropped panorama: the file holds the p-line's S window
+    euf.write_euf(str(tmp_path / "crop.euf"), np.zeros((40, 100, 3), np.float32))
+    (tmp_path / "C.pto").write_text('p f2 w128 h64 v360 S10,110,12,52\ni w128 h64 f4 v360 y0 p0 r0 Pano"%s"\n'
+                                    % (tmp_path / "crop.euf") + rest)
+    c = subprocess.run([cli, "--pto", str(tmp_path / "C.pto")] + common, capture_output=True, text=True)
+    assert c.returncode == 0, c.stderr
+    assert re.search(r"facet 0 \S+ spherical 128x64x3", c.stdout)
+    bad = subprocess.run([cli, "--pto_line", 'i w128 h64 f4 v360 Pano"%s"' % (tmp_path / "pano.euf"), "--output", "x.euf",
+                          "--dry_run"], capture_output=True, text=True)
+    assert bad.returncode != 0 and "needs a p-line" in bad.stderr
+
+
 def test_pipe_mode_and_errors(cli, tmp_path):
     job = jobs.JOBS["ll_rect_d1"]
     p = _write_facets(job, str(tmp_path))[0]
