@@ -280,6 +280,30 @@ CLI_EXTRAS = {
 }
 
 
+def _edge_jobs():
+    """Degenerate sizes: one-pixel and ragged targets, sources smaller than a spline window, tiny cube
+    faces. CPU: oracle == reference (golden). GPU: tests/test_gpu_parity.py::test_edge_jobs (added without a
+    GPU run at hand, therefore not yet part of the must-pass set)."""
+    rng = np.random.default_rng(5)
+    ll = lambda w, h: rng.random((h, w, 3), dtype=np.float32)
+    cm = lambda f: rng.random((6 * f, f, 3), dtype=np.float32)
+    E = {
+        "edge_1x1_rect_from_ll8": Job([FacetSpec(ll(8, 4), "spherical", 360.0)], "rectilinear", 60.0, 1, 1),
+        "edge_17x3_sph_from_cm4_d3": Job([FacetSpec(cm(4), "cubemap", 90.0)], "spherical", 360.0, 17, 3, degree=3),
+        "edge_ll4x2_d3_rect": Job([FacetSpec(ll(4, 2), "spherical", 360.0)], "rectilinear", 90.0, 33, 9, degree=3),
+        "edge_ll2x2_d3_sph": Job([FacetSpec(ll(2, 2), "spherical", 360.0)], "spherical", 360.0, 16, 8, degree=3),
+        "edge_rect3x2_src_d2_tw2": Job([FacetSpec(rng.random((2, 3, 3), dtype=np.float32), "rectilinear", 50.0)],
+                                       "rectilinear", 70.0, 31, 7, degree=2, twine=2),
+        "edge_cube_target_w1": Job([FacetSpec(ll(16, 8), "spherical", 360.0)], "cubemap", 90.0, 1),
+        "edge_513_wide_cyl_tw3": Job([FacetSpec(ll(32, 16), "spherical", 360.0)], "cylindrical", 360.0, 513, 2, twine=3),
+    }
+    for k, v in E.items():
+        v.name = k
+    return E
+
+
+EDGE_JOBS = _edge_jobs()
+
 # --split FORMAT runs of the reference CLI (one output per facet, the solo facet excepted): name ->
 # (base job, extra command-line arguments). Golden: manifest[name]["outputs"][facet] = shape + sha256.
 SPLITS = {

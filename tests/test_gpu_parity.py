@@ -4,6 +4,7 @@ indices bit-exact. Because the kernels use the same binary32 elementary function
 same operation order as the oracle (include/eu_math.h, -fmad=false), the tests demand more:
 every float of every small job is BIT-IDENTICAL (0 differing values)."""
 import copy
+import os
 import ctypes as C
 
 import numpy as np
@@ -287,3 +288,25 @@ def test_stage_one_renders_into_stage_two_source(engine, degree):
         engine.release([h])
         engine.release(via_upload)
         engine.release(hsa)
+
+
+@pytest.mark.xfail(strict=False, reason="added without a GPU run at hand; promote to must-pass once seen green")
+@pytest.mark.parametrize("name", sorted(jobs.EDGE_JOBS))
+def test_edge_jobs(name):
+    """Degenerate sizes (one-pixel and ragged targets, sources smaller than a spline window, 4-px cube
+    faces): the oracle equals the reference on them (golden); the kernels should equal the oracle. Each job
+    runs in a process of its own, so that a device fault on an untried size cannot reach the other tests."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "import harness, jobs\n"
+            "from envutil_b200.engine import Engine\n"
+            "job = jobs.EDGE_JOBS[%r]\n"
+            "eng = Engine(0)\n"
+            "out = eng.render(job)\n"
+            "c = harness.compare(out, harness.oracle_render(job))\n"
+            "print(c)\n"
+            "sys.exit(0 if c['n_diff'] == 0 else 3)\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), name))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-1500:]

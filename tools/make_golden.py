@@ -46,8 +46,9 @@ def _retry(job, kind, n=5):
 def main():
     os.makedirs(harness.GOLDEN, exist_ok=True)
     manifest = {}
-    for name in sorted(jobs.JOBS):
-        job = jobs.JOBS[name]
+    all_jobs = dict(jobs.JOBS, **jobs.EDGE_JOBS)
+    for name in sorted(all_jobs):
+        job = all_jobs[name]
         pm = _retry(job, "pm")
         lm = _retry(job, "libm")
         c = harness.compare(lm, pm)
