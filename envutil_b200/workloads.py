@@ -11,6 +11,13 @@ from .job import FacetSpec, Job
 
 RGB = 12  # bytes per float RGB texel
 
+# Distinct texels of the staged container(s) that the full-size job reads, counted from the tap addresses
+# of the oracle (tools/count_touched.py; SURVEY.md 8d asks for the exact count). Other scales fall back to
+# the fractions estimated in the survey.
+EXACT_TOUCHED = {"C1": 627648, "C2": 25241100, "C3a": 120655786, "C3b": 100734138, "C4": 19806305,
+                 "C5A": 72047136,   # one position: three brackets, every texel once
+                 "C5B": 69790864}   # 48 % of the six merged images: only the winning facet is evaluated
+
 
 def c1(scale=1, **kw):
     """configs[0]: lat/lon 4096x2048 -> rectilinear 1920x1080 hfov 90, bilinear, no twining."""
@@ -19,6 +26,8 @@ def c1(scale=1, **kw):
     out_px = job.width * job.height
     # 7.48 % of the source is inside the 90-degree view (counted numerically)
     alg = out_px * RGB + int(0.0748 * src.shape[0] * src.shape[1]) * RGB
+    if scale == 1:
+        alg = out_px * RGB + EXACT_TOUCHED["C1"] * RGB
     return job, alg
 
 
@@ -30,6 +39,8 @@ def c2(scale=1, **kw):
     job = Job([FacetSpec(src, "cubemap", 90.0)], "spherical", 360.0, 8192 // scale, 4096 // scale, degree=3,
               name="C2", **kw)
     alg = job.width * job.height * RGB + 6 * face * face * RGB
+    if scale == 1:  # the cubic windows along the face edges reach into the support frame: +0.13 %
+        alg = job.width * job.height * RGB + EXACT_TOUCHED["C2"] * RGB
     return job, alg
 
 
@@ -38,6 +49,8 @@ def c3a(scale=1, **kw):
     src = synth.latlon(16384 // scale)
     job = Job([FacetSpec(src, "spherical", 360.0)], "biatan6", 90.0, 4096 // scale, degree=1, name="C3a", **kw)
     alg = job.width * 6 * job.width * RGB + src.shape[0] * src.shape[1] * RGB
+    if scale == 1:  # 90 % of the source: where the cube faces sample coarser than the lat/lon grid, texels are skipped
+        alg = job.width * 6 * job.width * RGB + EXACT_TOUCHED["C3a"] * RGB
     return job, alg
 
 
@@ -46,6 +59,8 @@ def c3b(cube, **kw):
     face = cube.shape[1]
     job = Job([FacetSpec(cube, "biatan6", 90.0)], "spherical", 360.0, 4 * face, 2 * face, degree=1, name="C3b", **kw)
     alg = job.width * job.height * RGB + 6 * face * face * RGB
+    if face == 4096:
+        alg = job.width * job.height * RGB + EXACT_TOUCHED["C3b"] * RGB
     return job, alg
 
 
@@ -57,6 +72,8 @@ def c4(scale=1, **kw):
     job = Job([FacetSpec(src, "spherical", 360.0)], "fisheye", 180.0, 4096 // scale, 4096 // scale, twine=4,
               name="C4", **kw)
     alg = job.width * job.height * RGB + int(0.557 * src.shape[0] * src.shape[1]) * RGB
+    if scale == 1:
+        alg = job.width * job.height * RGB + EXACT_TOUCHED["C4"] * RGB
     return job, alg
 
 
@@ -86,6 +103,8 @@ def c5_stage_a(facets3, **kw):
     # bracket, whose brighten is 1, so the un-brighten step of work() is a no-op
     job = Job(list(facets3), "rectilinear", f.hfov, w, h, yaw=f.yaw, synopsis="hdr_merge", single=0, name="C5A", **kw)
     alg = w * h * RGB * (1 + len(facets3))
+    if (w, h, len(facets3)) == (6000, 4000, 3):
+        alg = w * h * RGB + EXACT_TOUCHED["C5A"] * RGB
     return job, alg
 
 
@@ -103,4 +122,7 @@ def c5_stage_b(merged, yaws, hfov=100.0, scale=1, **kw):
 def c5_stage_b_geometry(fs, scale=1, **kw):
     job = Job(fs, "spherical", 360.0, 16384 // scale, 8192 // scale, name="C5B", **kw)
     alg = job.width * job.height * RGB + sum(f.shape()[0] * f.shape()[1] for f in fs) * RGB
+    if scale == 1 and len(fs) == 6 and all(f.shape()[:2] == (6000, 4000) for f in fs):
+        # only the winning facet of a pixel is evaluated: 48 % of the six merged images are ever read
+        alg = job.width * job.height * RGB + EXACT_TOUCHED["C5B"] * RGB
     return job, alg

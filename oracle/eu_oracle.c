@@ -546,6 +546,31 @@ static float gate_periodic(float c, float lower, float upper) {
   return cc + lower;
 }
 
+/* Optional instrumentation ("recompute the distinct source texels touched exactly from the
+ * oracle's tap addresses"): one byte per CONTAINER texel of a registered source, set for every texel a
+ * spline window reads. Racing threads all store the same value. */
+#define ORC_TOUCH_MAX 64
+static struct { const orc_source_t* src; unsigned char* map; } g_touch[ORC_TOUCH_MAX];
+static int g_touch_n = 0;
+void orc_touch_map(const orc_source_t* src, unsigned char* map) { /* src NULL: forget every map */
+  if (!src) { g_touch_n = 0; return; }
+  for (int i = 0; i < g_touch_n; i++)
+    if (g_touch[i].src == src) { g_touch[i].map = map; return; }
+  if (g_touch_n < ORC_TOUCH_MAX) { g_touch[g_touch_n].src = src; g_touch[g_touch_n].map = map; g_touch_n++; }
+}
+size_t orc_touch_map_size(const orc_source_t* src) { return (size_t)src->cw * src->chh; }
+static void touch_window(const orc_source_t* s, int ix, int iy, int degree) {
+  if (g_touch_n == 0) return;
+  unsigned char* map = NULL;
+  for (int i = 0; i < g_touch_n; i++)
+    if (g_touch[i].src == s) map = g_touch[i].map;
+  if (!map) return;
+  int h2 = degree / 2;
+  for (int j = 0; j <= degree; j++)
+    for (int i = 0; i <= degree; i++)
+      map[(size_t)(iy - h2 + j + s->ly) * s->cw + (size_t)(ix - h2 + i + s->lx)] = 1;
+}
+
 /* safe evaluator = mapper + evaluator (zimt/eval.h:2039-2164, :1237-1300, :903-1059).
  * degree: the evaluator's degree (spline_degree + shift). crd in spline coordinates. */
 static void spline_eval(const orc_source_t* s, int degree, const float* wmat, float cx, float cy, float* out) {
@@ -564,6 +589,7 @@ static void spline_eval(const orc_source_t* s, int degree, const float* wmat, fl
     float f = roundf(cx); fx = cx - f; ix = (int)f;
     f = roundf(cy); fy = cy - f; iy = (int)f;
   }
+  touch_window(s, ix, iy, degree);
   if (degree == 0) {
     const float* p = texel(s, ix, iy);
     for (int c = 0; c < nch; c++) out[c] = p[c];
