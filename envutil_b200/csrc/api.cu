@@ -821,8 +821,9 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
       (f->window_width != f->width || f->window_height != f->height))
     return fail(EU_ERR_ARGUMENT, "cubemaps cannot be windowed");
   // zimt degrades an axis of extent 1 to the CONSTANT boundary condition with a clamp-to-zero gate
-  // (zimt/eval.h:2060-2064); that special case is not restated (found by comparing the oracle with the
-  // reference on 2x1 and 4x1 rasters), so such rasters are refused rather than rendered differently
+  // (zimt/eval.h:2060-2064); the kernels do not restate that special case yet (it was found by comparing
+  // the oracle with the reference on 2x1 and 4x1 rasters), so such rasters are refused rather than
+  // rendered differently
   if (f->window_width == 1 || f->window_height == 1)
     return fail(EU_ERR_UNSUPPORTED, "rasters with a single row or column are not supported");
   cudaStream_t st = g.stream;

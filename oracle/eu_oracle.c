@@ -579,6 +579,10 @@ static void spline_eval(const orc_source_t* s, int degree, const float* wmat, fl
   float ux = (float)((long double)(s->w - 1) + 0.5L), uy = (float)((long double)(s->h - 1) + 0.5L);
   cx = (s->bc0 == BC_PERIODIC) ? gate_periodic(cx, -0.5f, ux) : gate_mirror(cx, -0.5f, ux);
   cy = (s->bc1 == BC_PERIODIC) ? gate_periodic(cy, -0.5f, uy) : gate_mirror(cy, -0.5f, uy);
+  /* an axis of extent 1 is gated as CONSTANT with both limits 0: a clamp that always yields 0
+   * (build_safe_ev, zimt/eval.h:2060-2064) */
+  if (s->w == 1) cx = 0.0f;
+  if (s->h == 1) cy = 0.0f;
   /* split, zimt/basis.h:102-146 */
   float fx, fy;
   int ix, iy;

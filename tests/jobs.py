@@ -295,6 +295,11 @@ def _edge_jobs():
         "edge_rect3x2_src_d2_tw2": Job([FacetSpec(rng.random((2, 3, 3), dtype=np.float32), "rectilinear", 50.0)],
                                        "rectilinear", 70.0, 31, 7, degree=2, twine=2),
         "edge_cube_target_w1": Job([FacetSpec(ll(16, 8), "spherical", 360.0)], "cubemap", 90.0, 1),
+        # single-row / single-column rasters: zimt gates that axis as CONSTANT (always coordinate 0). The oracle
+        # restates it; the library still refuses such rasters (EU_ERR_UNSUPPORTED), so the GPU leg xfails
+        "edge_ll2x1_src_d1": Job([FacetSpec(ll(2, 1), "spherical", 360.0)], "spherical", 360.0, 16, 8),
+        "edge_rect1x5_src_d3": Job([FacetSpec(rng.random((5, 1, 3), dtype=np.float32), "rectilinear", 30.0)], "spherical",
+                                   360.0, 16, 8, degree=3),
         "edge_513_wide_cyl_tw3": Job([FacetSpec(ll(32, 16), "spherical", 360.0)], "cylindrical", 360.0, 513, 2, twine=3),
     }
     for k, v in E.items():
