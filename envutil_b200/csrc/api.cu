@@ -695,6 +695,10 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
     return EU_OK;
   }
   mount_layout(f, degree, s);
+  // zimt's bracer folds repeatedly when a brace is wider than the raster (a 2-px image under a quintic
+  // spline); that is not restated (found by the randomised sweep against the reference)
+  if (s->lx > s->w || s->rx > s->w || s->ly > s->h || s->ry > s->h)
+    return fail(EU_ERR_UNSUPPORTED, "a %dx%d raster is smaller than the brace of a degree-%d spline", s->w, s->h, degree);
   size_t n = (size_t)s->pitch * s->chh;
   CK(pool_alloc(&s->container, n, cpst));
   int stride = s->pitch;
@@ -1216,6 +1220,10 @@ int eu_source_reserve(const char* asset_key, const eu_facet_t* f, const eu_opts_
   s->degree = o->spline_degree;
   s->tstride = f->nchannels;
   mount_layout(f, o->spline_degree, s);
+  if (s->lx > s->w || s->rx > s->w || s->ly > s->h || s->ry > s->h) {
+    delete s;
+    return fail(EU_ERR_UNSUPPORTED, "the raster is smaller than the brace of its spline");
+  }
   cudaError_t e = pool_alloc(&s->container, (size_t)s->pitch * s->chh);
   if (e != cudaSuccess) {
     delete s;

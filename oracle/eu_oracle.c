@@ -700,33 +700,44 @@ static void cubemap_fill_support(orc_source_t* s) {
     for (int st = 0; st < 4; st++) {
       if (!on[st]) continue;
       int x0 = win[st][0], y0 = win[st][1], x1 = win[st][2], y1 = win[st][3];
-      /* a stripe never reads its own section, rows can be written as they are computed */
+      /* zimt::process works through a line in vectors of 16 pixels: a vector is evaluated from the IR as
+       * it is, then stored (zimt/wielding.h:317-455). That matters for odd face widths only: the face is
+       * then not centred in its section (left frame = right frame - 1) while the pixel-to-ray step
+       * assumes it is (ishift = S - 1), so the first frame row below the TOP/BOTTOM faces (first column
+       * right of the LEFT/RIGHT faces) maps onto its OWN section's edge and averages in the frame texel
+       * before it - already rewritten if that lies in an earlier vector of the line, not yet if in the same.
+       * (The LEFT/RIGHT column reads the line ABOVE, which another thread of the reference is working on at
+       * the same time: a race in the reference; this restatement takes the lines in order. Odd face widths
+       * are therefore not pinned for the texels that depend on that column - see DESIGN.md.) */
       for (int y = y0; y < y1; y++) {
-        for (int x = x0; x < x1; x++) {
-          int c0 = 2 * x - ishift, c1 = 2 * y - ishift;
-          float ray[3];
-          switch (face) { /* fill_frame_t::eval, :733-780 */
-            case CM_FRONT: ray[0] = (float)c0; ray[1] = (float)c1; ray[2] = (float)ithird; break;
-            case CM_BACK: ray[0] = (float)(-c0); ray[1] = (float)c1; ray[2] = (float)(-ithird); break;
-            case CM_RIGHT: ray[0] = (float)ithird; ray[1] = (float)c1; ray[2] = (float)(-c0); break;
-            case CM_LEFT: ray[0] = (float)(-ithird); ray[1] = (float)c1; ray[2] = (float)c0; break;
-            case CM_BOTTOM: ray[0] = (float)(-c0); ray[1] = (float)ithird; ray[2] = (float)c1; break;
-            default: ray[0] = (float)(-c0); ray[1] = (float)(-ithird); ray[2] = (float)(-c1); break;
+        for (int v0 = x0; v0 < x1; v0 += ORC_LANES) {
+          int v1 = v0 + ORC_LANES < x1 ? v0 + ORC_LANES : x1;
+          for (int x = v0; x < v1; x++) {
+            int c0 = 2 * x - ishift, c1 = 2 * y - ishift;
+            float ray[3];
+            switch (face) { /* fill_frame_t::eval, :733-780 */
+              case CM_FRONT: ray[0] = (float)c0; ray[1] = (float)c1; ray[2] = (float)ithird; break;
+              case CM_BACK: ray[0] = (float)(-c0); ray[1] = (float)c1; ray[2] = (float)(-ithird); break;
+              case CM_RIGHT: ray[0] = (float)ithird; ray[1] = (float)c1; ray[2] = (float)(-c0); break;
+              case CM_LEFT: ray[0] = (float)(-ithird); ray[1] = (float)c1; ray[2] = (float)c0; break;
+              case CM_BOTTOM: ray[0] = (float)(-c0); ray[1] = (float)ithird; ray[2] = (float)c1; break;
+              default: ray[0] = (float)(-c0); ray[1] = (float)(-ithird); ray[2] = (float)(-c1); break;
+            }
+            int fv;
+            float in_face[2], pk[2];
+            ray_to_cubeface(ray, &fv, in_face);
+            /* metrics_t::get_pickup_coordinate_px, cubemap.h:401-411: refc_md is a double here */
+            pk[0] = (float)((double)in_face[0] + m->refc_md);
+            pk[1] = (float)((double)in_face[1] + m->refc_md);
+            pk[0] *= (float)m->model_to_px;
+            pk[1] *= (float)m->model_to_px;
+            pk[1] += (float)(fv * S);
+            pk[0] -= .5f;
+            pk[1] -= .5f;
+            spline_eval(s, 1, NULL, pk[0], pk[1], rowbuf + (size_t)(x - v0) * nch);
           }
-          int fv;
-          float in_face[2], pk[2];
-          ray_to_cubeface(ray, &fv, in_face);
-          /* metrics_t::get_pickup_coordinate_px, cubemap.h:401-411: refc_md is a double here */
-          pk[0] = (float)((double)in_face[0] + m->refc_md);
-          pk[1] = (float)((double)in_face[1] + m->refc_md);
-          pk[0] *= (float)m->model_to_px;
-          pk[1] *= (float)m->model_to_px;
-          pk[1] += (float)(fv * S);
-          pk[0] -= .5f;
-          pk[1] -= .5f;
-          spline_eval(s, 1, NULL, pk[0], pk[1], rowbuf + (size_t)(x - x0) * nch);
+          memcpy(texel(s, v0, face * S + y), rowbuf, tb * (v1 - v0));
         }
-        memcpy(texel(s, x0, face * S + y), rowbuf, tb * (x1 - x0));
       }
     }
   }
