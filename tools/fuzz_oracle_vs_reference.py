@@ -54,6 +54,17 @@ def random_facet(rng, nch):
                 kw.update(tp_y=float(rng.uniform(-15, 15)), tp_p=float(rng.uniform(-10, 10)))
         if rng.random() < .25:
             kw.update(eev=float(rng.choice([10.0, 11.5, 12.0, 13.0, 14.0])))
+        r = rng.random()
+        if r < .12 and w > 8 and h > 8:      # lens crop (S clause) -> feathered alpha
+            kw.update(crop=(int(rng.integers(0, w // 3)), int(rng.integers(2 * w // 3, w)),
+                            int(rng.integers(0, h // 3)), int(rng.integers(2 * h // 3, h))))
+        elif r < .24 and w > 8 and h > 8:    # exclude mask (k-line) -> feathered alpha
+            n = int(rng.integers(3, 7))
+            kw.update(masks=(tuple((float(rng.uniform(0, w)), float(rng.uniform(0, h))) for _ in range(n)),))
+        elif r < .34:                        # the file is a window of a larger image (W clause)
+            tw, th = w + int(rng.integers(0, 40)), h + int(rng.integers(0, 30))
+            x0, y0 = int(rng.integers(0, tw - w + 1)), int(rng.integers(0, th - h + 1))
+            kw.update(window=(x0, x0 + w, y0, y0 + h), total_width=tw, total_height=th)
         return FacetSpec(img(w, h), kind, float(rng.uniform(30, 130)), yaw=float(rng.uniform(-180, 180)),
                          pitch=float(rng.uniform(-60, 60)), roll=float(rng.uniform(-20, 20)), **kw)
     if kind == "stereographic":
@@ -91,6 +102,11 @@ def random_job(rng):
     if trg == "spherical" and rng.random() < .5:
         height = 0
         width += width & 1
+    if (trg not in ("cubemap", "biatan6") and height and width > 4 and height > 4 and "single" not in kw
+            and rng.random() < .12):  # cropped output: p-line with an S clause (no camera rotation on that route)
+        x0, y0 = int(rng.integers(0, width // 2)), int(rng.integers(0, height // 2))
+        kw.update(crop_out=(x0, int(rng.integers(x0 + 1, width + 1)), y0, int(rng.integers(y0 + 1, height + 1))),
+                  yaw=0.0, pitch=0.0, roll=0.0)
     return Job(facets, trg, hfov, width, height, **kw)
 
 
