@@ -9,6 +9,7 @@
 // the GPU is not usable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -666,6 +667,18 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
     if (rc) return fail(rc, "bad cubemap metrics (face %d px, hfov %g, support %d, tile %d)", f->width, f->hfov,
                         o->support_min, o->tile_size);
     int S = s->cm.section_px, Fpx = f->width, L = s->cm.left_frame_px, R = s->cm.right_frame_px;
+    // The spline windows of rays that hit a face edge reach degree/2 + 1 texels into the support frame. With
+    // --support_min / --tile_size chosen so that there is less (e.g. 0 and 1: no frame at all) the reference
+    // reads the unset brace of its b-spline object - undefined there (found by the randomised sweep: values
+    // of 1e25) - and the kernels would read outside the container: refused.
+    {
+      const int need = degree / 2 + 1;
+      // faces wider than 90 degrees carry support inside the image (inherent_support_px, cubemap.h:300-301)
+      const int inherent = f->hfov > M_PI_2 ? (int)std::trunc(s->cm.model_to_px * (tan(f->hfov / 2.0) - 1.0)) : 0;
+      if (L + inherent < need || R + inherent < need)
+        return fail(EU_ERR_UNSUPPORTED, "cubemap support frame of %d/%d px is narrower than the %d px a degree-%d "
+                    "spline needs (raise --support_min)", L, R, need, degree);
+    }
     s->w = s->cw = S;
     s->h = s->chh = 6 * S;
     s->lx = s->ly = s->rx = s->ry = 0;

@@ -91,6 +91,16 @@ def random_job(rng):
             "cubemap": float(rng.choice([90.0, 100.0])), "biatan6": 90.0}[trg]
     kw = dict(degree=int(rng.choice([0, 1, 1, 1, 2, 3, 3, 4, 5, 7])), twine=int(rng.choice([0, 0, 0, 2, 3, -1])),
               yaw=float(rng.uniform(-180, 180)), pitch=float(rng.uniform(-80, 80)), roll=float(rng.uniform(-40, 40)))
+    if rng.random() < .2:    # prefilter degree of its own (--prefilter)
+        kw["prefilter"] = int(rng.choice([0, 1, 2, 3, 5]))
+    if kw["twine"] > 0 and rng.random() < .5:
+        kw.update(twine_width=float(rng.uniform(.5, 2.5)))
+        if rng.random() < .5:
+            kw.update(twine_sigma=float(rng.uniform(.3, 2.0)), twine_threshold=float(rng.choice([0.0, 0.01, 0.05])))
+    if kw["twine"] < 0 and rng.random() < .5:
+        kw.update(twine_density=float(rng.uniform(.5, 2.0)), twine_max=int(rng.integers(2, 9)))
+    if any(f.projection in ("cubemap", "biatan6") for f in facets) and rng.random() < .4:
+        kw.update(support_min=int(rng.choice([0, 2, 4, 8, 12])), tile_size=int(rng.choice([1, 2, 8, 16, 64])))
     if nf > 1:
         r = rng.random()
         if r < .25 and nch in (1, 3):
@@ -151,7 +161,20 @@ def main():
             odd_cube = any(f.projection in ("cubemap", "biatan6") and f.native_shape()[0] % 2 for f in job.facets)
             tiny = any(f.projection not in ("cubemap", "biatan6") and min(f.native_shape()[:2]) < job.degree // 2 + 1
                        for f in job.facets)
-            if odd_cube or tiny:
+            thin = False  # cubemap support frame narrower than the spline window: undefined in the reference
+            for f in job.facets:
+                if f.projection in ("cubemap", "biatan6"):
+                    import ctypes as C
+                    from envutil_b200 import capi
+                    oi, od = (C.c_int32 * 4)(), (C.c_double * 4)()
+                    capi.load().eu_cubemap_metrics(f.native_shape()[0], f.hfov * 3.141592653589793 / 180.0, job.support_min,
+                                                   job.tile_size, oi, od)
+                    frame_l = oi[1]
+                    frame_r = oi[2]
+                    import math
+                    inherent = int(math.trunc(od[1] * (math.tan(math.radians(f.hfov) / 2.0) - 1.0))) if f.hfov > 90.0 else 0
+                    thin = thin or min(frame_l, frame_r) + inherent < job.degree // 2 + 1
+            if odd_cube or tiny or thin:
                 known += 1
                 continue
             bad += 1
@@ -161,7 +184,7 @@ def main():
         else:
             ok += 1
     print("jobs %d: identical %d, different %d (+ %d in the known categories: odd cube face width, raster smaller "
-          "than its brace), oracle errors %d, reference refused/crashed %d" % (a.n, ok, bad, known, crashed, skipped))
+          "than its brace, cubemap support frame narrower than the spline window), oracle errors %d, reference refused/crashed %d" % (a.n, ok, bad, known, crashed, skipped))
 
 
 if __name__ == "__main__":
