@@ -86,7 +86,9 @@ def random_job(rng):
         trg = "spherical"
     width = int(rng.integers(1, 90))
     height = 0 if trg in ("cubemap", "biatan6") else int(rng.integers(1, 60))
-    hfov = {"spherical": 360.0, "cylindrical": float(rng.uniform(60, 360)), "rectilinear": float(rng.uniform(20, 140)),
+    if trg not in ("cubemap", "biatan6") and rng.random() < .1:  # several 512-px segments per line
+        width, height = int(rng.integers(513, 1200)), int(rng.integers(1, 5))
+    hfov = {"spherical": float(rng.choice([360.0, 360.0, rng.uniform(40, 360)])), "cylindrical": float(rng.uniform(60, 360)), "rectilinear": float(rng.uniform(20, 140)),
             "stereographic": float(rng.uniform(60, 250)), "fisheye": float(rng.uniform(90, 300)),
             "cubemap": float(rng.choice([90.0, 100.0])), "biatan6": 90.0}[trg]
     kw = dict(degree=int(rng.choice([0, 1, 1, 1, 2, 3, 3, 4, 5, 7])), twine=int(rng.choice([0, 0, 0, 2, 3, -1])),
