@@ -421,32 +421,32 @@ static float* texel(const orc_source_t* s, int x, int y) { /* core coordinates *
   return s->core + (ptrdiff_t)y * (ptrdiff_t)s->stride + (ptrdiff_t)x * s->nch;
 }
 
-/* bracer::apply for one axis, zimt/brace.h:151-338, copying boundary conditions */
+/* bracer::apply for one axis, zimt/brace.h:151-338, copying boundary conditions. The reference fills the two
+ * braces in lock-step from the core outwards, each slice from the slice its mirror image (or period)
+ * points at - which, when a brace is wider than the core, is a brace slice filled a few steps earlier.
+ * The closed form of that is folding the index with period 2m (REFLECT) or m (PERIODIC). */
+static int brace_src(int i, int m, int bc) { /* core index that container slice i (core coordinates) copies */
+  if (bc == BC_PERIODIC) {
+    i %= m;
+    return i < 0 ? i + m : i;
+  }
+  i %= 2 * m;
+  if (i < 0) i += 2 * m;
+  return i < m ? i : 2 * m - 1 - i;
+}
 static void brace_axis(orc_source_t* s, int axis, int bc, int lsz, int rsz) {
   int nch = s->nch;
   if (axis == 0) {
     int m = s->w;
     for (int Y = -s->ly; Y < s->chh - s->ly; Y++) {
-      for (int k = 0; k < lsz; k++) {
-        int src = (bc == BC_PERIODIC) ? m - 1 - k : k;
-        memcpy(texel(s, -1 - k, Y), texel(s, src, Y), sizeof(float) * nch);
-      }
-      for (int k = 0; k < rsz; k++) {
-        int src = (bc == BC_PERIODIC) ? k : m - 1 - k;
-        memcpy(texel(s, m + k, Y), texel(s, src, Y), sizeof(float) * nch);
-      }
+      for (int k = 0; k < lsz; k++) memcpy(texel(s, -1 - k, Y), texel(s, brace_src(-1 - k, m, bc), Y), sizeof(float) * nch);
+      for (int k = 0; k < rsz; k++) memcpy(texel(s, m + k, Y), texel(s, brace_src(m + k, m, bc), Y), sizeof(float) * nch);
     }
   } else {
     int m = s->h;
     size_t rowb = sizeof(float) * s->stride;
-    for (int k = 0; k < lsz; k++) {
-      int src = (bc == BC_PERIODIC) ? m - 1 - k : k;
-      memcpy(texel(s, -s->lx, -1 - k), texel(s, -s->lx, src), rowb);
-    }
-    for (int k = 0; k < rsz; k++) {
-      int src = (bc == BC_PERIODIC) ? k : m - 1 - k;
-      memcpy(texel(s, -s->lx, m + k), texel(s, -s->lx, src), rowb);
-    }
+    for (int k = 0; k < lsz; k++) memcpy(texel(s, -s->lx, -1 - k), texel(s, -s->lx, brace_src(-1 - k, m, bc)), rowb);
+    for (int k = 0; k < rsz; k++) memcpy(texel(s, -s->lx, m + k), texel(s, -s->lx, brace_src(m + k, m, bc)), rowb);
   }
 }
 
