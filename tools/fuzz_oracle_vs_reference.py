@@ -18,6 +18,8 @@ import numpy as np  # noqa: E402
 import harness  # noqa: E402
 from envutil_b200.job import FacetSpec, Job  # noqa: E402
 
+SCALE = int(os.environ.get("FUZZ_SCALE", "1"))  # multiplies the upper bounds of the random raster sizes
+
 TARGETS = ["spherical", "cylindrical", "rectilinear", "stereographic", "fisheye", "cubemap", "biatan6"]
 
 
@@ -28,13 +30,13 @@ def random_facet(rng, nch):
         a = rng.random((h, w, nch), dtype=np.float32)
         return a[:, :, 0] if nch == 1 and rng.random() < .5 else a
     if kind in ("cubemap", "biatan6"):
-        f = int(rng.integers(3, 40))
+        f = int(rng.integers(3, 40 * SCALE))
         return FacetSpec(img(f, 6 * f), kind, float(rng.choice([90.0, 90.0, 100.0, 120.0])))
-    w, h = int(rng.integers(2, 70)), int(rng.integers(2, 50))
+    w, h = int(rng.integers(2, 70 * SCALE)), int(rng.integers(2, 50 * SCALE))
     if kind == "spherical":
         full = rng.random() < .6
         if full:
-            h = int(rng.integers(2, 30)); w = 2 * h
+            h = int(rng.integers(2, 30 * SCALE)); w = 2 * h
             return FacetSpec(img(w, h), kind, 360.0, yaw=float(rng.uniform(-180, 180)), pitch=float(rng.uniform(-90, 90)),
                              roll=float(rng.uniform(-30, 30)))
         return FacetSpec(img(w, h), kind, float(rng.uniform(40, 300)), yaw=float(rng.uniform(-180, 180)))
@@ -84,8 +86,8 @@ def random_job(rng):
     translated = any(f.tr_x or f.tr_y or f.tr_z for f in facets)
     if translated and trg in ("cubemap", "biatan6"):
         trg = "spherical"
-    width = int(rng.integers(1, 90))
-    height = 0 if trg in ("cubemap", "biatan6") else int(rng.integers(1, 60))
+    width = int(rng.integers(1, 90 * SCALE))
+    height = 0 if trg in ("cubemap", "biatan6") else int(rng.integers(1, 60 * SCALE))
     if trg not in ("cubemap", "biatan6") and rng.random() < .1:  # several 512-px segments per line
         width, height = int(rng.integers(513, 1200)), int(rng.integers(1, 5))
     hfov = {"spherical": float(rng.choice([360.0, 360.0, rng.uniform(40, 360)])), "cylindrical": float(rng.uniform(60, 360)), "rectilinear": float(rng.uniform(20, 140)),
