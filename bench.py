@@ -167,6 +167,14 @@ def run_reference_cpu(job, steps, warmup, workdir):
     """Times the unmodified reference on this box's host cores. Returns a dict."""
     from envutil_b200 import euf
     exe = os.path.join(ROOT, "oracle", "_ref", "envutil_ref_fast")
+    isa = "-march=x86-64-v3"
+    try:  # the AVX-512 build of the same sources where the host has it (a zimt vector = one zmm register)
+        flags = open("/proc/cpuinfo").read()
+        exe512 = exe + "512"
+        if all((" " + f) in flags for f in ("avx512f", "avx512vl", "avx512bw", "avx512dq", "avx512cd")) and os.path.exists(exe512):
+            exe, isa = exe512, "-march=x86-64-v4"
+    except OSError:
+        pass
     mpix = job.width * (job.height or job.width) / 1e6
     ncores = os.cpu_count() or 1
     if os.path.exists(exe):
@@ -198,8 +206,8 @@ def run_reference_cpu(job, steps, warmup, workdir):
                           "prefilter + render, wall clock minus raster file I/O" % (steps, mpix),
                 "ms_per_step": t * 1e3,
                 "render_only_mpix_s": (mpix / float(np.mean(render_s))) if render_s else None,
-                "build": "oracle/_ref/envutil_ref_fast: unmodified reference sources, g++ -O3 -march=x86-64-v3, "
-                         "zimt goading back-end"}
+                "build": "oracle/_ref/%s: unmodified reference sources, g++ -O3 %s, zimt goading back-end"
+                         % (os.path.basename(exe), isa)}
     # fallback: the C oracle port, a band of rows sized for a few seconds
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import harness
