@@ -518,7 +518,11 @@ def ours(args):
                        "l2": "inputs_larger_than_l2 (321 MB source IR + 403 MB output per frame vs 126 MB L2)",
                        "texel_layout": "float4-padded" if args.padded else "interleaved-rgb",
                        "gather": "direct (L1)" if args.no_tiles else "footprint staged in shared memory by cp.async.bulk",
-                       "parity": "bit-exact vs pinned-math reference build (tests/)"},
+                       "arithmetic": capi.ARITHMETIC,  # "contracted" only with EU_ARITHMETIC=contracted (opt-in build)
+                       "parity": "bit-exact vs pinned-math reference build (tests/)" if capi.ARITHMETIC == "exact" else
+                                 "window evaluation with fused multiply-adds: indices identical, values within 2.6e-6 "
+                                 "relative (hdr_merge 1.6e-5) of the pinned-math reference build, RMS <= 2.7e-7 "
+                                 "(tests/test_contracted.py)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": tr["traffic_bytes"] if tr else None,
                          "traffic_source": tr["source"] if tr else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_launch,

@@ -8,7 +8,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libenvutil_b200.so")
+# EU_ARITHMETIC=contracted selects the opt-in build whose window evaluation uses fused multiply-adds
+# (include/envutil_b200.h: eu_render_arithmetic); anything else is the bit-exact default
+ARITHMETIC = "contracted" if os.environ.get("EU_ARITHMETIC", "") == "contracted" else "exact"
+LIB_PATH = os.path.join(_HERE, "libenvutil_b200_fma.so" if ARITHMETIC == "contracted" else "libenvutil_b200.so")
 
 # eu_projection_t (reference envutil_basic.h:99-109)
 SPHERICAL, CYLINDRICAL, RECTILINEAR, STEREOGRAPHIC, FISHEYE, CUBEMAP, BIATAN6, PRJ_NONE = range(8)
@@ -98,6 +101,7 @@ SYMBOLS = {
     "eu_shutdown": (None, []),
     "eu_last_error": (C.c_char_p, []),
     "eu_device_count": (C.c_int, []),
+    "eu_render_arithmetic": (C.c_int, []),
     "eu_source_upload": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p,
                                    C.POINTER(SourceH), C.POINTER(Timing)]),
     "eu_source_upload_device": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p, C.c_void_p,
@@ -149,6 +153,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    if lib.eu_render_arithmetic() != (1 if ARITHMETIC == "contracted" else 0):
+        raise RuntimeError(f"{LIB_PATH} was not built with the {ARITHMETIC} arithmetic it is named for")
     _lib = lib
     return lib
 

@@ -444,6 +444,36 @@ __device__ __forceinline__ void dev_weights(const float* __restrict__ wmat, floa
   }
 }
 
+// ---- opt-in arithmetic variant (libenvutil_b200_fma.so, built with -DEU_CONTRACT_WINDOW) ----------------
+// The default library rounds every product and every sum of the window evaluation separately, as the
+// reference's parity build does (-ffp-contract=off): that is what makes the output bit-identical, and it
+// is 198 of the C2 kernel's 469 instructions per warp. A reference built the usual way (g++ -O3 with FMA
+// hardware: -ffp-contract=fast) fuses those pairs itself. With EU_CONTRACT_WINDOW the weights of the
+// WINDOW, the window sum and the twining accumulation use fused multiply-adds; rays, source coordinates,
+// gates, window positions, face and facet indices stay exactly as they are (same bits), so the variant
+// differs from the default by a few ulp of each pixel value and in nothing else.
+#ifdef EU_CONTRACT_WINDOW
+#define EU_WIN_MULADD(a, b, c) __fmaf_rn((a), (b), (c))
+template <int ORDER>
+__device__ __forceinline__ void dev_window_weights(const float* __restrict__ wmat, float delta, float w[ORDER]) {
+  float power = delta;
+#pragma unroll
+  for (int k = 0; k < ORDER; k++) w[k] = wmat[k];
+#pragma unroll
+  for (int row = 1; row < ORDER; row++) {
+#pragma unroll
+    for (int k = 0; k < ORDER; k++) w[k] = __fmaf_rn(power, wmat[row * ORDER + k], w[k]);
+    if (row < ORDER - 1) power *= delta;
+  }
+}
+#else
+#define EU_WIN_MULADD(a, b, c) ((c) + (a) * (b))
+template <int ORDER>
+__device__ __forceinline__ void dev_window_weights(const float* __restrict__ wmat, float delta, float w[ORDER]) {
+  dev_weights<ORDER>(wmat, delta, w);
+}
+#endif
+
 // Where a spline coordinate lands: gates (zimt/eval.h:2039-2164) + split (zimt/basis.h:102-146).
 struct Located {
   int ix, iy;    // integral part: the window covers [ix - deg/2, ix - deg/2 + deg] (zimt/eval.h:732)
@@ -477,8 +507,8 @@ __device__ __forceinline__ void dev_window_sum(const float* __restrict__ p0, int
     for (int i = 0; i < ORDER; i++) dev_load_texel<NCH, TS, SMEM>(row + i * TS, t[j][i]);
   }
   float wx[ORDER], wy[ORDER];
-  dev_weights<ORDER>(wmat, fx, wx);
-  dev_weights<ORDER>(wmat, fy, wy);
+  dev_window_weights<ORDER>(wmat, fx, wx);
+  dev_window_weights<ORDER>(wmat, fy, wy);
 #pragma unroll
   for (int j = 0; j < ORDER; j++) {
     float sub[NCH];
@@ -487,7 +517,7 @@ __device__ __forceinline__ void dev_window_sum(const float* __restrict__ p0, int
 #pragma unroll
     for (int i = 1; i < ORDER; i++) {
 #pragma unroll
-      for (int c = 0; c < NCH; c++) sub[c] += wx[i] * t[j][i][c];
+      for (int c = 0; c < NCH; c++) sub[c] = EU_WIN_MULADD(wx[i], t[j][i][c], sub[c]);
     }
     if (j == 0) {
 #pragma unroll
@@ -497,7 +527,7 @@ __device__ __forceinline__ void dev_window_sum(const float* __restrict__ p0, int
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < NCH; c++) out[c] += sub[c] * wy[j];
+      for (int c = 0; c < NCH; c++) out[c] = EU_WIN_MULADD(sub[c], wy[j], out[c]);
     }
   }
 }
@@ -515,12 +545,12 @@ __device__ __forceinline__ void dev_eval_linear(const float* __restrict__ p, int
   for (int c = 0; c < NCH; c++) {
     float sum = p00[c];
     sum *= wl0;
-    sum += p10[c] * wr0;
+    sum = EU_WIN_MULADD(p10[c], wr0, sum);
     sum *= wl1;
     float sub = p01[c];
     sub *= wl0;
-    sub += p11[c] * wr0;
-    sum += sub * wr1;
+    sub = EU_WIN_MULADD(p11[c], wr0, sub);
+    sum = EU_WIN_MULADD(sub, wr1, sum);
     out[c] = sum;
   }
 }
@@ -666,12 +696,12 @@ __device__ __noinline__ void dev_spline_eval_rt(const SourceDev& S, int degree, 
     for (int c = 0; c < SNCH; c++) {
       float sum = __ldg(p0 + c);
       sum *= wl0;
-      sum += __ldg(p0 + ts + c) * wr0;
+      sum = EU_WIN_MULADD(__ldg(p0 + ts + c), wr0, sum);
       sum *= wl1;
       float sub = __ldg(p0 + S.stride + c);
       sub *= wl0;
-      sub += __ldg(p0 + S.stride + ts + c) * wr0;
-      sum += sub * wr1;
+      sub = EU_WIN_MULADD(__ldg(p0 + S.stride + ts + c), wr0, sub);
+      sum = EU_WIN_MULADD(sub, wr1, sum);
       out[c] = sum;
     }
     return;
@@ -683,7 +713,7 @@ __device__ __noinline__ void dev_spline_eval_rt(const SourceDev& S, int degree, 
     float power = delta;
     for (int k = 0; k < order; k++) w[k] = wmat[k];
     for (int row = 1; row < order; row++) {
-      for (int k = 0; k < order; k++) w[k] += power * wmat[row * order + k];
+      for (int k = 0; k < order; k++) w[k] = EU_WIN_MULADD(power, wmat[row * order + k], w[k]);
       if (row < order - 1) power *= delta;
     }
   }
@@ -694,12 +724,12 @@ __device__ __noinline__ void dev_spline_eval_rt(const SourceDev& S, int degree, 
       const float* __restrict__ row = p0 + (ptrdiff_t)j * S.stride + c;
       float sub = __ldg(row);
       sub *= wx[0];
-      for (int i = 1; i < order; i++) sub += wx[i] * __ldg(row + i * ts);
+      for (int i = 1; i < order; i++) sub = EU_WIN_MULADD(wx[i], __ldg(row + i * ts), sub);
       if (j == 0) {
         sum = sub;
         sum *= wy[0];
       } else {
-        sum += sub * wy[j];
+        sum = EU_WIN_MULADD(sub, wy[j], sum);
       }
     }
     out[c] = sum;

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
         int id = dev_eval_facet<NCH, TS, DEG, GEN>(P, f0, r, help);
         if (k == 0) idx = id;
 #pragma unroll
-        for (int c = 0; c < NCH; c++) acc[c] += cw * help[c];
+        for (int c = 0; c < NCH; c++) acc[c] = EU_WIN_MULADD(cw, help[c], acc[c]);
       }
     } else {
       // per-facet ninepacks live in local memory; the taps loop re-reads them
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
         int id = dev_synopsis<NCH, TS, MODE, DEG, GEN, SP>(P, f0, fa, ray_of, active, help);
         if (k == 0) idx = id;
 #pragma unroll
-        for (int c = 0; c < NCH; c++) acc[c] += cw * help[c];
+        for (int c = 0; c < NCH; c++) acc[c] = EU_WIN_MULADD(cw, help[c], acc[c]);
       }
     }
 #pragma unroll
@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
         dev_brighten<NCH>(F, help);
       }
 #pragma unroll
-      for (int c = 0; c < NCH; c++) px[c] += tw * help[c];
+      for (int c = 0; c < NCH; c++) px[c] = EU_WIN_MULADD(tw, help[c], px[c]);
     }
   }
   if (T.unbrighten != 1.0f) {

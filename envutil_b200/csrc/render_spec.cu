@@ -55,3 +55,14 @@ bool eu_launch_render_spec(const RenderParams& P, cudaStream_t st) {
   }
   return false;
 }
+
+// Which arithmetic the render kernels of this library were compiled with (include/envutil_b200.h):
+// 0 = every product and sum rounded separately (bit-identical to the reference's parity build),
+// 1 = fused multiply-adds in the window evaluation and the twining accumulation (eu_device.cuh)
+extern "C" int eu_render_arithmetic(void) {
+#ifdef EU_CONTRACT_WINDOW
+  return 1;
+#else
+  return 0;
+#endif
+}

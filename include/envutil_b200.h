@@ -188,6 +188,12 @@ int eu_init(int device_id);
 void eu_shutdown(void);
 const char* eu_last_error(void);
 int eu_device_count(void);
+/* Arithmetic of the render kernels in this build of the library. 0 (libenvutil_b200.so, the default):
+ * no contraction anywhere, output bit-identical to the reference built with -ffp-contract=off. 1
+ * (libenvutil_b200_fma.so, opt-in): the b-spline window evaluation (zimt/eval.h:903-1059) and the
+ * twining accumulation (twining.h:106-263) use fused multiply-adds, as a reference built with
+ * g++'s default -ffp-contract=fast on FMA hardware does; coordinates and indices are unchanged. */
+int eu_render_arithmetic(void);
 
 /* Stage one source raster: upload, place into the braced container (lat/lon & mounted
  * images, reference environment.h:594-950) or the cubemap internal representation

@@ -571,6 +571,15 @@ static void touch_window(const orc_source_t* s, int ix, int iy, int degree) {
       map[(size_t)(iy - h2 + j + s->ly) * s->cw + (size_t)(ix - h2 + i + s->lx)] = 1;
 }
 
+/* Opt-in arithmetic of the library's libenvutil_b200_fma.so build (include/envutil_b200.h, eu_render_arithmetic):
+ * fused multiply-adds in the window evaluation and the twining accumulation of a RENDER (never while a
+ * source is staged). Not the reference's arithmetic - the reference parity build rounds every product -
+ * but what the contracted kernels are checked against bit for bit; the CPU tests state how far it is from
+ * the pinned arithmetic. orc_set_arithmetic(1) asks for it, orc_render applies it for its own duration. */
+static int g_contract_req = 0, g_contract = 0;
+void orc_set_arithmetic(int contracted) { g_contract_req = contracted != 0; }
+static inline float win_muladd(float a, float b, float c) { return g_contract ? fmaf(a, b, c) : c + a * b; }
+
 /* safe evaluator = mapper + evaluator (zimt/eval.h:2039-2164, :1237-1300, :903-1059).
  * degree: the evaluator's degree (spline_degree + shift). crd in spline coordinates. */
 static void spline_eval(const orc_source_t* s, int degree, const float* wmat, float cx, float cy, float* out) {
@@ -608,12 +617,12 @@ static void spline_eval(const orc_source_t* s, int degree, const float* wmat, fl
     for (int c = 0; c < nch; c++) {
       float sum = p00[c];
       sum *= wl0;
-      sum += p10[c] * wr0;
+      sum = win_muladd(p10[c], wr0, sum);
       sum *= wl1;
       float sub = p01[c];
       sub *= wl0;
-      sub += p11[c] * wr0;
-      sum += sub * wr1;
+      sub = win_muladd(p11[c], wr0, sub);
+      sum = win_muladd(sub, wr1, sum);
       out[c] = sum;
     }
     return;
@@ -627,7 +636,7 @@ static void spline_eval(const orc_source_t* s, int degree, const float* wmat, fl
     float power = delta;
     for (int k = 0; k < order; k++) w[k] = wmat[k];
     for (int row = 1; row < order; row++) {
-      for (int k = 0; k < order; k++) w[k] += power * wmat[row * order + k];
+      for (int k = 0; k < order; k++) w[k] = win_muladd(power, wmat[row * order + k], w[k]);
       if (row < order - 1) power *= delta;
     }
   }
@@ -639,12 +648,12 @@ static void spline_eval(const orc_source_t* s, int degree, const float* wmat, fl
       const float* row = texel(s, ix - h2, iy - h2 + j) + c;
       float sub = row[0];
       sub *= wx[0];
-      for (int i = 1; i < order; i++) sub += wx[i] * row[(size_t)i * nch];
+      for (int i = 1; i < order; i++) sub = win_muladd(wx[i], row[(size_t)i * nch], sub);
       if (j == 0) {
         sum = sub;
         sum *= wy[0];
       } else {
-        sum += sub * wy[j];
+        sum = win_muladd(sub, wy[j], sum);
       }
     }
     out[c] = sum;
@@ -1778,9 +1787,20 @@ static int facet_setup(const eu_target_t* t, const eu_opts_t* o, const eu_facet_
   return 0;
 }
 
+static int orc_render_impl(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_t* facets,
+                           orc_source_t* const* sources, const eu_tap_t* taps, int n_taps, int row0, int row1,
+                           float* out, int32_t* index_out, int n_threads);
 int orc_render(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_t* facets,
                orc_source_t* const* sources, const eu_tap_t* taps, int n_taps, int row0, int row1, float* out,
                int32_t* index_out, int n_threads) {
+  g_contract = g_contract_req; /* the opt-in arithmetic holds for the render only, see orc_set_arithmetic */
+  int rc = orc_render_impl(t, o, nf, facets, sources, taps, n_taps, row0, row1, out, index_out, n_threads);
+  g_contract = 0;
+  return rc;
+}
+static int orc_render_impl(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_t* facets,
+                           orc_source_t* const* sources, const eu_tap_t* taps, int n_taps, int row0, int row1,
+                           float* out, int32_t* index_out, int n_threads) {
   if (nf < 1 || nf > 64) return EU_ERR_ARGUMENT;
   target_ctx T;
   target_setup(t, &T);
@@ -1878,7 +1898,7 @@ int orc_render(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
             for (int l = 0; l < nl; l++) hid[l] = synopsis(mode, nfe, FE, sub[l], nch, help[l]);
           for (int l = 0; l < nl; l++) {
             if (k == 0) ids[l] = hid[l];
-            for (int c = 0; c < nch; c++) res[l][c] += cw * help[l][c];
+            for (int c = 0; c < nch; c++) res[l][c] = win_muladd(cw, help[l][c], res[l][c]);
           }
         }
       }

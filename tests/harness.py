@@ -46,6 +46,7 @@ def oracle():
         lib.orc_render.argtypes = [C.POINTER(capi.Target), C.POINTER(capi.Opts), C.c_int, C.POINTER(capi.Facet),
                                    C.POINTER(C.c_void_p), C.POINTER(capi.Tap), C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_int]
+        lib.orc_set_arithmetic.argtypes = [C.c_int]
         lib.orc_get_extent.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double)]
         lib.orc_get_step.restype = C.c_double
         lib.orc_get_step.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double]
@@ -79,8 +80,10 @@ def oracle_container(handle):
     return p, tuple(shp)
 
 
-def oracle_render(job, want_index=False, threads=0, rows=None, sources=None):
-    """Render the job with the C oracle. Returns H x W x C float32 (and the index plane)."""
+def oracle_render(job, want_index=False, threads=0, rows=None, sources=None, contracted=False):
+    """Render the job with the C oracle. Returns H x W x C float32 (and the index plane).
+    contracted: the arithmetic of the opt-in libenvutil_b200_fma.so build (orc_set_arithmetic) instead of
+    the reference's."""
     lib = oracle()
     st = job.structs()
     t, fa, o, taps, ntaps = st
@@ -89,8 +92,12 @@ def oracle_render(job, want_index=False, threads=0, rows=None, sources=None):
     row0, row1 = rows or (0, oh)
     out = np.empty((row1 - row0, ow, t.nchannels), dtype=np.float32)
     idx = np.empty((row1 - row0, ow), dtype=np.int32) if want_index else None
-    rc = lib.orc_render(C.byref(t), C.byref(o), len(job.facets), fa, hs, taps, ntaps, row0, row1,
-                        out.ctypes.data, idx.ctypes.data if want_index else None, threads)
+    lib.orc_set_arithmetic(1 if contracted else 0)
+    try:
+        rc = lib.orc_render(C.byref(t), C.byref(o), len(job.facets), fa, hs, taps, ntaps, row0, row1,
+                            out.ctypes.data, idx.ctypes.data if want_index else None, threads)
+    finally:
+        lib.orc_set_arithmetic(0)
     assert rc == 0, rc
     if sources is None:
         for h in hs:

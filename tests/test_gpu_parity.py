@@ -290,6 +290,8 @@ def test_stage_one_renders_into_stage_two_source(engine, degree):
         engine.release(hsa)
 
 
+@pytest.mark.skipif(os.environ.get("EU_GPU_UNTRIED") != "1",
+                    reason="sizes no GPU run has seen yet: opt in with EU_GPU_UNTRIED=1 (tools/gpu_first_call.sh does)")
 @pytest.mark.xfail(strict=False, reason="added without a GPU run at hand; promote to must-pass once seen green")
 def test_edge_jobs():
     """Degenerate sizes (one-pixel and ragged targets, sources smaller than a spline window, 4-px cube
