@@ -190,6 +190,13 @@ def run_reference_cpu(job, steps, warmup, workdir):
             t0 = time.perf_counter()
             r = subprocess.run(cmd, capture_output=True, text=True, env=env)
             wall = time.perf_counter() - t0
+            if r.returncode != 0 and i == 0 and exe.endswith("512"):
+                # the AVX-512 build does not run on this host after all: the AVX2 build of the same sources
+                exe, isa = exe[:-3], "-march=x86-64-v3"
+                cmd[0] = exe
+                t0 = time.perf_counter()
+                r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+                wall = time.perf_counter() - t0
             if r.returncode != 0:
                 raise RuntimeError("reference failed: " + r.stderr[-2000:])
             rd = re.findall(r"eushim: read time ([0-9.eE+-]+) ms", r.stdout)
