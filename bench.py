@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--scale", type=int, default=1, help="shrink the workload (tests only; invalid as a bench)")
     ap.add_argument("--padded", type=int, default=0, help="1: 16-byte RGB texels in HBM")
     ap.add_argument("--no-tiles", type=int, default=0, help="1: direct-gather kernel (no shared-memory staging)")
+    ap.add_argument("--warp-tiles", type=int, default=0,
+                    help="1: experimental kernel that stages the gather footprint per warp (k_render_warp)")
     ap.add_argument("--partition", default="frames", choices=["frames", "bands"],
                     help="N > 1: frames = one full frame per rank per step (weak scaling, default); bands = the ranks "
                          "split ONE frame into row bands, gathered on rank 0 over NCCL (strong scaling)")
@@ -319,6 +321,7 @@ def ours(args):
     if not bands_mode:
         job.yaw = 360.0 * rank / world  # every rank renders its own view of the same environment
     job.padded, job.no_tiles = bool(args.padded), bool(args.no_tiles)
+    job.warp_tiles = bool(args.warp_tiles)
     job.narrow_stores = bool(args.narrow_stores)
     eng = Engine(local)
     st = job.structs(eng.lib)
@@ -500,7 +503,8 @@ def ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        tr = measured_traffic() if (args.scale == 1 and not args.padded and not args.no_tiles and not bands_mode) else None
+        tr = measured_traffic() if (args.scale == 1 and not args.padded and not args.no_tiles and not args.warp_tiles
+                                    and not bands_mode) else None
         alg_launch = alg // world if bands_mode else alg  # a band touches its share of output and source
         achieved = alg_launch / (ms_per_step * 1e-3) / 1e9  # per launch = per GPU
         cpu = None
@@ -524,7 +528,9 @@ def ours(args):
                        "partition": "row bands of one frame, gathered on rank 0" if bands_mode else "one frame per rank", "out_mpix_per_frame": mpix,
                        "l2": "inputs_larger_than_l2 (321 MB source IR + 403 MB output per frame vs 126 MB L2)",
                        "texel_layout": "float4-padded" if args.padded else "interleaved-rgb",
-                       "gather": "direct (L1)" if args.no_tiles else "footprint staged in shared memory by cp.async.bulk",
+                       "gather": "direct (L1)" if args.no_tiles else
+                                 "footprint staged in shared memory per warp by cp.async.bulk (experimental)" if args.warp_tiles else
+                                 "footprint staged in shared memory by cp.async.bulk",
                        "arithmetic": capi.ARITHMETIC,  # "contracted" only with EU_ARITHMETIC=contracted (opt-in build)
                        "parity": "bit-exact vs pinned-math reference build (tests/)" if capi.ARITHMETIC == "exact" else
                                  "window evaluation with fused multiply-adds: indices identical, values within 2.6e-6 "
@@ -533,7 +539,7 @@ def ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": tr["traffic_bytes"] if tr else None,
                          "traffic_source": tr["source"] if tr else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_launch,
-                         "kernel": "k_render<3,...>" if args.no_tiles else "k_render_tiled<3,...>", "frac_of_8TBs_spec": achieved / 8000.0},
+                         "kernel": "k_render<3,...>" if args.no_tiles else "k_render_warp<3,...>" if args.warp_tiles else "k_render_tiled<3,...>", "frac_of_8TBs_spec": achieved / 8000.0},
             "e2e": {"value": world * mpix / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h_src.numel() * 4), "d2h_bytes_per_step": int(h_out.numel() * 4),
                     "ms_per_step": e2e_ms, "steps": e2e_steps,

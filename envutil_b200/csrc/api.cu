@@ -509,7 +509,7 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     for (int i = 0; i < nf; i++) F[i].hdr_kind = (i == lo) ? EU_HDR_LOW : (i == hi) ? EU_HDR_HIGH : EU_HDR_MIDDLE;
   }
   P.f0 = F[first];
-  P.use_tiles = (o->reserved[1] & 1) ? 0 : 1;
+  P.use_tiles = (o->reserved[1] & 1) ? 0 : ((o->reserved[1] & 8) ? 2 : 1);  // 2: per-warp staging (opt-in)
   P.src_cw = sources[first]->cw;
   P.src_ch = sources[first]->chh;
   P.src_lx = sources[first]->lx;

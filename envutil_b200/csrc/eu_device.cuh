@@ -454,6 +454,7 @@ __device__ __forceinline__ void dev_weights(const float* __restrict__ wmat, floa
 // differs from the default by a few ulp of each pixel value and in nothing else.
 #ifdef EU_CONTRACT_WINDOW
 #define EU_WIN_MULADD(a, b, c) __fmaf_rn((a), (b), (c))
+#define EU_WIN_ACC(c, a, b) c = __fmaf_rn((a), (b), c)
 template <int ORDER>
 __device__ __forceinline__ void dev_window_weights(const float* __restrict__ wmat, float delta, float w[ORDER]) {
   float power = delta;
@@ -468,6 +469,7 @@ __device__ __forceinline__ void dev_window_weights(const float* __restrict__ wma
 }
 #else
 #define EU_WIN_MULADD(a, b, c) ((c) + (a) * (b))
+#define EU_WIN_ACC(c, a, b) c += (a) * (b)  // the statement as the run-time evaluator has always had it
 template <int ORDER>
 __device__ __forceinline__ void dev_window_weights(const float* __restrict__ wmat, float delta, float w[ORDER]) {
   dev_weights<ORDER>(wmat, delta, w);
@@ -696,12 +698,12 @@ __device__ __noinline__ void dev_spline_eval_rt(const SourceDev& S, int degree, 
     for (int c = 0; c < SNCH; c++) {
       float sum = __ldg(p0 + c);
       sum *= wl0;
-      sum = EU_WIN_MULADD(__ldg(p0 + ts + c), wr0, sum);
+      EU_WIN_ACC(sum, __ldg(p0 + ts + c), wr0);
       sum *= wl1;
       float sub = __ldg(p0 + S.stride + c);
       sub *= wl0;
-      sub = EU_WIN_MULADD(__ldg(p0 + S.stride + ts + c), wr0, sub);
-      sum = EU_WIN_MULADD(sub, wr1, sum);
+      EU_WIN_ACC(sub, __ldg(p0 + S.stride + ts + c), wr0);
+      EU_WIN_ACC(sum, sub, wr1);
       out[c] = sum;
     }
     return;
@@ -713,7 +715,7 @@ __device__ __noinline__ void dev_spline_eval_rt(const SourceDev& S, int degree, 
     float power = delta;
     for (int k = 0; k < order; k++) w[k] = wmat[k];
     for (int row = 1; row < order; row++) {
-      for (int k = 0; k < order; k++) w[k] = EU_WIN_MULADD(power, wmat[row * order + k], w[k]);
+      for (int k = 0; k < order; k++) EU_WIN_ACC(w[k], power, wmat[row * order + k]);
       if (row < order - 1) power *= delta;
     }
   }
@@ -724,12 +726,12 @@ __device__ __noinline__ void dev_spline_eval_rt(const SourceDev& S, int degree, 
       const float* __restrict__ row = p0 + (ptrdiff_t)j * S.stride + c;
       float sub = __ldg(row);
       sub *= wx[0];
-      for (int i = 1; i < order; i++) sub = EU_WIN_MULADD(wx[i], __ldg(row + i * ts), sub);
+      for (int i = 1; i < order; i++) EU_WIN_ACC(sub, wx[i], __ldg(row + i * ts));
       if (j == 0) {
         sum = sub;
         sum *= wy[0];
       } else {
-        sum = EU_WIN_MULADD(sub, wy[j], sum);
+        EU_WIN_ACC(sum, sub, wy[j]);
       }
     }
     out[c] = sum;

@@ -131,7 +131,7 @@ struct RenderParams {
   int32_t any_generic;  // the general build is needed: some facet uses the generic stepper (translation) or
                         // differs from the job in channel count / texel stride
   int32_t spec;       // index into eu_render_specs the job matches (0: none)
-  int32_t use_tiles;  // 1: stage the gather footprint in shared memory where the kernel supports it
+  int32_t use_tiles;  // 1: stage the gather footprint in shared memory where the kernel supports it; 2: per warp
   int32_t src_cw, src_ch;  // container shape of f0's source in texels (tile path)
   int32_t src_lx, src_ly;  // its left / top brace: core texel (0,0) is container texel (lx, ly)
   const float* src_base;   // first float of f0's container (256-byte aligned, rows 16-byte aligned)

@@ -594,6 +594,106 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
   dev_store_pixel<NCH>(P, T, x, y, px, wslot[threadIdx.y]);
 }
 
+// ------------------------------------------------------------------------------------------
+// Opt-in variant of the kernel above (eu_opts_t.reserved[1] bit 3; written at the end of round 1 from what
+// ncu showed on the C2 kernel - 29 % of the warp samples sit at the two block barriers, the shared-memory
+// reduction and the mbarrier wait - and NOT yet run on a GPU): every WARP stages the footprint of its own
+// 32 pixels (one row of the tile) into its own slice of shared memory, counted on its own mbarrier. No block-wide
+// synchronisation is left: the bounding box is a warp reduction whose result every lane holds, lane 0 arms
+// the barrier and issues the row copies, and a warp whose footprint does not fit gathers from HBM without
+// holding the others up. It costs about three times the L2 -> shared traffic (the rows that the eight warps
+// of a tile share are fetched by each of them). Values and their order of combination are those of the
+// other kernels: bit-identical output.
+// ------------------------------------------------------------------------------------------
+#define EU_WARP_TILE_FLOATS 1024  // 4 KB staged footprint per warp, 32 KB per block
+#define EU_WARP_TILE_ROWS 16
+
+template <int NCH, int TS, int DEG, int SP = 0>
+__global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_warp(const __grid_constant__ RenderParams P) {
+  static_assert(DEG == 3, "built for the cubic evaluator");
+  constexpr int ORDER = DEG + 1, H2 = DEG / 2;
+  constexpr int NWARP = TILE_X * TILE_Y / 32;
+  __shared__ __align__(128) float tiles[NWARP][EU_WARP_TILE_FLOATS];
+  __shared__ __align__(16) float wslot[TILE_Y][NCH == 3 ? TILE_X * 3 : 4];  // dev_store_pixel
+  __shared__ __align__(8) uint64_t mbars[NWARP];
+
+  SpecView<SP> V(P);
+  const TargetDev& T = V.trg();
+  const FacetDev& F = V.f0();
+  const SourceDev& S = F.src;
+  const int lane = threadIdx.x, wid = threadIdx.y;  // TILE_X == 32: a warp is one row of the tile
+  const int x = blockIdx.x * TILE_X + lane;
+  const int y = P.row0 + blockIdx.y * TILE_Y + wid;
+  if (y >= P.row1) return;  // the whole warp: nobody else waits for it
+  const bool inside = x < T.width;
+  float* tile = tiles[wid];
+  uint64_t* mbar = &mbars[wid];
+  if (lane == 0) mbar_init(mbar, 1);
+  __syncwarp();
+
+  // ---- phase 1: rays and window origins ------------------------------------------------
+  const int xc = inside ? x : 0;
+  const int xf = first_lane_column(xc);
+  float2 c0 = __ldg(P.col_tab + xc), r0 = __ldg(P.row_tab + y);
+  ColTerm col{c0.x, c0.y};
+  RowTerm row{r0.x, r0.y};
+  ColTerm first = col;
+  if (T.projection == EU_CYLINDRICAL && T.normalize) {
+    float2 f0 = __ldg(P.col_tab + xf);
+    first = ColTerm{f0.x, f0.y};
+  }
+  float r00[3];
+  dev_stepper(T, F.xx, F.yy, F.zz, col, row, first, y, r00);
+  int face;
+  float cx, cy;
+  bool hit = dev_facet_coordinate(F, r00, face, cx, cy) && inside;
+  Located L = dev_locate(S, DEG, hit ? cx : 0.0f, hit ? cy : 0.0f);
+  // window origin in CONTAINER texel coordinates (container rows start 16-byte aligned)
+  const int lox = L.ix - H2 + P.src_lx, loy = L.iy - H2 + P.src_ly;
+  const int mnx = __reduce_min_sync(0xffffffffu, hit ? lox : INT_MAX);
+  const int mxx = __reduce_max_sync(0xffffffffu, hit ? lox : INT_MIN);
+  const int mny = __reduce_min_sync(0xffffffffu, hit ? loy : INT_MAX);
+  const int mxy = __reduce_max_sync(0xffffffffu, hit ? loy : INT_MIN);
+  int a0 = 0, wf = 0, rows = 0;  // warp-uniform
+  if (mnx <= mxx) {              // at least one pixel of the warp hits the source
+    a0 = (mnx * TS) & ~3;        // 16-byte granule within the container row
+    wf = (((mxx + ORDER) * TS - a0) + 3) & ~3;
+    rows = mxy - mny + ORDER;
+    if (rows > EU_WARP_TILE_ROWS || rows * wf > EU_WARP_TILE_FLOATS || wf <= 0 || rows <= 0) rows = 0;
+  }
+  const bool staged = rows > 0;
+  if (staged) {
+    if (lane == 0) {  // arm, then one bulk copy per row: all from the thread that initialised the barrier
+      mbar_expect_tx(mbar, (uint32_t)(rows * wf) * 4u);
+      for (int rid = 0; rid < rows; rid++)
+        bulk_row_g2s(tile + rid * wf, P.src_base + (ptrdiff_t)(mny + rid) * S.stride + a0, (uint32_t)wf * 4u, mbar);
+    }
+    __syncwarp();
+    mbar_wait(mbar, 0);
+  }
+
+  // ---- phase 2: windows ------------------------------------------------------------------
+  if (!inside) return;
+  float px[NCH];
+  if (!hit) {
+#pragma unroll
+    for (int c = 0; c < NCH; c++) px[c] = 0.0f;
+  } else {
+    if (staged)
+      dev_window_eval<NCH, TS, DEG, true>(tile + (loy - mny) * wf + (lox * TS - a0), wf, DEG, P.wmat, L.fx, L.fy, px);
+    else
+      dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)loy * S.stride + (ptrdiff_t)lox * TS, S.stride, DEG,
+                                           P.wmat, L.fx, L.fy, px);
+    dev_brighten<NCH>(F, px);
+  }
+  if (T.unbrighten != 1.0f) {
+    constexpr int NCOL = (NCH == 2 || NCH == 4) ? NCH - 1 : NCH;
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) px[c] *= T.unbrighten;
+  }
+  dev_store_pixel<NCH>(P, T, x, y, px, wslot[wid]);
+}
+
 template <int NCH, int TS, int MODE, bool TWINE>
 static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st) {
   if constexpr (MODE == EU_MODE_SINGLE) {
@@ -602,6 +702,12 @@ static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_
     // and loses for the bilinear one (4 taps/px: C3b 1.56 vs 1.32 ms), where the two block-wide
     // synchronisations cost more than the gathers they replace - so it is used for degree 3 only.
     if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.any_generic && P.degree == 3) {
+      if constexpr (!TWINE && NCH == 3) {
+        if (P.use_tiles == 2) {  // opt-in: per-warp staging (RGB rasters, no twining)
+          k_render_warp<NCH, TS, 3><<<grid, block, 0, st>>>(P);
+          return;
+        }
+      }
       k_render_tiled<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P);
       return;
     }

@@ -111,6 +111,7 @@ class Job:
     no_tiles: bool = False  # back-end option: never stage gather footprints in shared memory (reserved[1] bit 0)
     narrow_stores: bool = False  # back-end option: 4-byte pixel stores even into peer frames (reserved[1] bit 2)
     no_spec: bool = False   # back-end option: never use the kernels compiled for one job shape (reserved[1] bit 1)
+    warp_tiles: bool = False  # back-end option (experimental): footprint staging per warp, not per block (bit 3)
     name: str = ""
 
     # ---- reference command line (real spellings, envutil_main.cc:190-372) ----
@@ -264,7 +265,8 @@ class Job:
         o.solo = 0 if n == 1 else self.solo  # forced for a single facet (envutil_main.cc:996-997)
         o.support_min, o.tile_size = self.support_min, self.tile_size
         o.reserved[0] = 1 if self.padded else 0
-        o.reserved[1] = (1 if self.no_tiles else 0) | (2 if self.no_spec else 0) | (4 if self.narrow_stores else 0)
+        o.reserved[1] = (1 if self.no_tiles else 0) | (2 if self.no_spec else 0) | (4 if self.narrow_stores else 0) | \
+            (8 if self.warp_tiles else 0)
         taps = (capi.Tap * 1024)()
         tw = C.c_int(0)
         ntaps = lib.eu_make_spread(C.byref(t), C.byref(o), n, fa, self.twine, self.twine_width, self.twine_density,

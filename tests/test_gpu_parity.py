@@ -320,3 +320,42 @@ def test_edge_jobs():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1500:]
+
+
+@pytest.mark.skipif(os.environ.get("EU_GPU_UNTRIED") != "1",
+                    reason="a kernel no GPU run has seen yet: opt in with EU_GPU_UNTRIED=1 (tools/gpu_first_call.sh does)")
+def test_warp_staged_kernel_is_bit_exact():
+    """k_render_warp (eu_opts_t.reserved[1] bit 3: the gather footprint staged per warp instead of per block):
+    every cubic RGB single-facet job without twining, general and shape-compiled builds, 12- and 16-byte texels,
+    plus a C2-shaped job large enough for full tiles. One separate process with a two-minute limit - the kernel
+    waits on an mbarrier, and a mistake there would hang rather than fail."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "import copy\n"
+            "import harness, jobs\n"
+            "from envutil_b200 import synth\n"
+            "from envutil_b200.engine import Engine\n"
+            "from envutil_b200.job import FacetSpec, Job\n"
+            "eng = Engine(0)\n"
+            "todo = {n: j for n, j in jobs.JOBS.items() if j.degree == 3 and len(j.facets) == 1 and not j.twine\n"
+            "        and j.facets[0].image.shape[-1] == 3}\n"
+            "todo['c2_small'] = Job([FacetSpec(synth.cubemap(256), 'cubemap', 90.0)], 'spherical', 360.0, 1024, 512, degree=3)\n"
+            "todo['ll_rect_big'] = Job([FacetSpec(synth.latlon(1024), 'spherical', 360.0)], 'rectilinear', 80.0, 640, 360,\n"
+            "                          degree=3, yaw=40.0, pitch=-70.0, roll=25.0)\n"
+            "bad = 0\n"
+            "for name in sorted(todo):\n"
+            "    ref = harness.oracle_render(todo[name])\n"
+            "    for no_spec in (False, True):\n"
+            "        for padded in (False, True):\n"
+            "            job = copy.copy(todo[name])\n"
+            "            job.warp_tiles, job.no_spec, job.padded = True, no_spec, padded\n"
+            "            c = harness.compare(eng.render(job), ref)\n"
+            "            print(name, no_spec, padded, c['n_diff'], flush=True)\n"
+            "            bad += c['n_diff'] != 0\n"
+            "print('jobs', len(todo))\n"
+            "sys.exit(3 if bad else 0)\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1500:]

@@ -26,4 +26,13 @@ if grep -q '"value"' "$OUT/bench_contracted.json"; then
   EU_ARITHMETIC=contracted step ncu_launches_contracted 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file "$OUT/launches_contracted.csv" python bench.py --steps 20 --warmup 3 --no-cpu-baseline
 fi
+# 6. LAST, because a mistake in it would hang rather than fail: the per-warp staging kernel (k_render_warp).
+#    Parity first (own process, two-minute limit inside the test), the bench only if that passed.
+EU_GPU_UNTRIED=1 step pytest_warp 200 python -m pytest tests/test_gpu_parity.py::test_warp_staged_kernel_is_bit_exact -q -rxXs
+if grep -q "1 passed" "$OUT/pytest_warp.log"; then
+  step bench_warp 300 python bench.py --warp-tiles 1 --no-cpu-baseline
+  tail -n 1 "$OUT/bench_warp.log" > "$OUT/bench_warp.json"
+  EU_ARITHMETIC=contracted step bench_warp_contracted 300 python bench.py --warp-tiles 1 --no-cpu-baseline
+  tail -n 1 "$OUT/bench_warp_contracted.log" > "$OUT/bench_warp_contracted.json"
+fi
 cat "$OUT/summary.txt"
