@@ -603,14 +603,15 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
 // the barrier and issues the row copies, and a warp whose footprint does not fit gathers from HBM without
 // holding the others up. It costs about three times the L2 -> shared traffic (the rows that the eight warps
 // of a tile share are fetched by each of them). Values and their order of combination are those of the
-// other kernels: bit-identical output.
+// other kernels: bit-identical output. Unlike the block-staged kernel it is also instantiated for the
+// bilinear evaluator - that one lost to direct gathers because of the two block barriers, which are gone here.
 // ------------------------------------------------------------------------------------------
 #define EU_WARP_TILE_FLOATS 1024  // 4 KB staged footprint per warp, 32 KB per block
 #define EU_WARP_TILE_ROWS 16
 
 template <int NCH, int TS, int DEG, int SP = 0>
 __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_warp(const __grid_constant__ RenderParams P) {
-  static_assert(DEG == 3, "built for the cubic evaluator");
+  static_assert(DEG == 1 || DEG == 3, "built for the bilinear and cubic evaluators");
   constexpr int ORDER = DEG + 1, H2 = DEG / 2;
   constexpr int NWARP = TILE_X * TILE_Y / 32;
   __shared__ __align__(128) float tiles[NWARP][EU_WARP_TILE_FLOATS];
@@ -701,9 +702,15 @@ static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_
     // Measured on B200 (profiles/): it wins for the cubic window (16 taps/px: C2 0.60 vs 0.75 ms)
     // and loses for the bilinear one (4 taps/px: C3b 1.56 vs 1.32 ms), where the two block-wide
     // synchronisations cost more than the gathers they replace - so it is used for degree 3 only.
+    if constexpr (!TWINE && NCH == 3) {  // opt-in: per-warp staging (RGB rasters, no twining), also bilinear
+      if (P.use_tiles == 2 && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.any_generic && P.degree == 1) {
+        k_render_warp<NCH, TS, 1><<<grid, block, 0, st>>>(P);
+        return;
+      }
+    }
     if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.any_generic && P.degree == 3) {
       if constexpr (!TWINE && NCH == 3) {
-        if (P.use_tiles == 2) {  // opt-in: per-warp staging (RGB rasters, no twining)
+        if (P.use_tiles == 2) {
           k_render_warp<NCH, TS, 3><<<grid, block, 0, st>>>(P);
           return;
         }

@@ -11,6 +11,12 @@ inline bool tiles_ok(const RenderParams& P) {
 template <int SP, bool TWINE>
 bool single(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st, bool with_cubic) {
   if (P.degree == 1) {
+    if constexpr (!TWINE) {
+      if (P.use_tiles == 2 && P.out && !P.index_out && (P.f0.src.stride & 3) == 0) {  // opt-in variant
+        k_render_warp<3, 3, 1, SP><<<grid, block, 0, st>>>(P);
+        return true;
+      }
+    }
     k_render<3, 3, EU_MODE_SINGLE, TWINE, 1, false, false, SP><<<grid, block, 0, st>>>(P);
     return true;
   }

@@ -27,12 +27,14 @@ if grep -q '"value"' "$OUT/bench_contracted.json"; then
     --log-file "$OUT/launches_contracted.csv" python bench.py --steps 20 --warmup 3 --no-cpu-baseline
 fi
 # 6. LAST, because a mistake in it would hang rather than fail: the per-warp staging kernel (k_render_warp).
-#    Parity first (own process, two-minute limit inside the test), the bench only if that passed.
-EU_GPU_UNTRIED=1 step pytest_warp 200 python -m pytest tests/test_gpu_parity.py::test_warp_staged_kernel_is_bit_exact -q -rxXs
+#    Parity first (own process, four-minute limit inside the test), the bench only if that passed.
+EU_GPU_UNTRIED=1 step pytest_warp 330 python -m pytest tests/test_gpu_parity.py::test_warp_staged_kernel_is_bit_exact -q -rxXs
 if grep -q "1 passed" "$OUT/pytest_warp.log"; then
   step bench_warp 300 python bench.py --warp-tiles 1 --no-cpu-baseline
   tail -n 1 "$OUT/bench_warp.log" > "$OUT/bench_warp.json"
   EU_ARITHMETIC=contracted step bench_warp_contracted 300 python bench.py --warp-tiles 1 --no-cpu-baseline
   tail -n 1 "$OUT/bench_warp_contracted.log" > "$OUT/bench_warp_contracted.json"
+  # every single-facet config, block-staged / direct (0) against per-warp staging (4), same inputs
+  step configs_warp 420 python tools/bench_configs.py --configs C1,C2,C3a,C3b --padded 0,4 --steps 10
 fi
 cat "$OUT/summary.txt"
