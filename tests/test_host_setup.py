@@ -175,3 +175,19 @@ def test_bspline_constants_match_oracle(lib):
     orc.orc_weight_matrix(3, m)
     want = np.array([[1, 4, 1, 0], [-3, 0, 3, 0], [3, -6, 3, 0], [-1, 3, -3, 1]], dtype=np.float64) / 6.0
     assert np.allclose(np.array(list(m)).reshape(4, 4), want.astype(np.float32), atol=0)
+
+
+def test_backend_option_bits(lib):
+    """Job's back-end switches land in eu_opts_t.reserved as include/envutil_b200.h documents them; none is set
+    by default (the measured, GPU-tested kernels are what a plain job runs)."""
+    import copy
+    import jobs
+    job = copy.copy(jobs.JOBS["ll_rect_d3_rot"])
+    o = job.structs(lib)[2]
+    assert (o.reserved[0], o.reserved[1]) == (0, 0)
+    for field, word, bit in (("padded", 0, 1), ("no_tiles", 1, 1), ("no_spec", 1, 2), ("narrow_stores", 1, 4),
+                             ("warp_tiles", 1, 8)):
+        j = copy.copy(job)
+        setattr(j, field, True)
+        o = j.structs(lib)[2]
+        assert o.reserved[word] == bit and o.reserved[1 - word] == 0, field
