@@ -598,7 +598,8 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
 // Opt-in variant of the kernel above (eu_opts_t.reserved[1] bit 3; written at the end of round 1 from what
 // ncu showed on the C2 kernel - 29 % of the warp samples sit at the two block barriers, the shared-memory
 // reduction and the mbarrier wait - and NOT yet run on a GPU): every WARP stages the footprint of its own
-// 32 pixels (one row of the tile) into its own slice of shared memory, counted on its own mbarrier. No block-wide
+// 32 pixels (one row of the tile; with twining: plus a margin, as above) into its own slice of shared memory,
+// counted on its own mbarrier. No block-wide
 // synchronisation is left: the bounding box is a warp reduction whose result every lane holds, lane 0 arms
 // the barrier and issues the row copies, and a warp whose footprint does not fit gathers from HBM without
 // holding the others up. It costs about three times the L2 -> shared traffic (the rows that the eight warps
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
 #define EU_WARP_TILE_FLOATS 1024  // 4 KB staged footprint per warp, 32 KB per block
 #define EU_WARP_TILE_ROWS 16
 
-template <int NCH, int TS, int DEG, int SP = 0>
+template <int NCH, int TS, bool TWINE, int DEG, int SP = 0>
 __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_warp(const __grid_constant__ RenderParams P) {
   static_assert(DEG == 1 || DEG == 3, "built for the bilinear and cubic evaluators");
   constexpr int ORDER = DEG + 1, H2 = DEG / 2;
@@ -655,11 +656,20 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_warp(const __grid_con
   const int mxx = __reduce_max_sync(0xffffffffu, hit ? lox : INT_MIN);
   const int mny = __reduce_min_sync(0xffffffffu, hit ? loy : INT_MAX);
   const int mxy = __reduce_max_sync(0xffffffffu, hit ? loy : INT_MIN);
-  int a0 = 0, wf = 0, rows = 0;  // warp-uniform
-  if (mnx <= mxx) {              // at least one pixel of the warp hits the source
-    a0 = (mnx * TS) & ~3;        // 16-byte granule within the container row
-    wf = (((mxx + ORDER) * TS - a0) + 3) & ~3;
-    rows = mxy - mny + ORDER;
+  int a0 = 0, wf = 0, rows = 0, by0 = 0;  // warp-uniform
+  if (mnx <= mxx) {                       // at least one pixel of the warp hits the source
+    int bx0 = mnx, bx1 = mxx, by1 = mxy;
+    by0 = mny;
+    if constexpr (TWINE) {  // sub-rays stray up to half a pixel from the centre ray (a tap outside the box
+                            // gathers from HBM, so the margin decides speed, never the result)
+      const int bw = mxx - mnx + 1, mx = (bw * 5) / 64 + 2, my = 2;
+      bx0 -= mx; bx1 += mx; by0 -= my; by1 += my;
+      bx0 = max(bx0, 0); by0 = max(by0, 0);  // keep the box inside the container
+      bx1 = min(bx1, P.src_cw - ORDER); by1 = min(by1, P.src_ch - ORDER);
+    }
+    a0 = (bx0 * TS) & ~3;  // 16-byte granule within the container row
+    wf = (((bx1 + ORDER) * TS - a0) + 3) & ~3;
+    rows = by1 - by0 + ORDER;
     if (rows > EU_WARP_TILE_ROWS || rows * wf > EU_WARP_TILE_FLOATS || wf <= 0 || rows <= 0) rows = 0;
   }
   const bool staged = rows > 0;
@@ -667,7 +677,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_warp(const __grid_con
     if (lane == 0) {  // arm, then one bulk copy per row: all from the thread that initialised the barrier
       mbar_expect_tx(mbar, (uint32_t)(rows * wf) * 4u);
       for (int rid = 0; rid < rows; rid++)
-        bulk_row_g2s(tile + rid * wf, P.src_base + (ptrdiff_t)(mny + rid) * S.stride + a0, (uint32_t)wf * 4u, mbar);
+        bulk_row_g2s(tile + rid * wf, P.src_base + (ptrdiff_t)(by0 + rid) * S.stride + a0, (uint32_t)wf * 4u, mbar);
     }
     __syncwarp();
     mbar_wait(mbar, 0);
@@ -676,16 +686,63 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_warp(const __grid_con
   // ---- phase 2: windows ------------------------------------------------------------------
   if (!inside) return;
   float px[NCH];
-  if (!hit) {
+  if constexpr (!TWINE) {
+    if (!hit) {
+#pragma unroll
+      for (int c = 0; c < NCH; c++) px[c] = 0.0f;
+    } else {
+      if (staged)
+        dev_window_eval<NCH, TS, DEG, true>(tile + (loy - by0) * wf + (lox * TS - a0), wf, DEG, P.wmat, L.fx, L.fy, px);
+      else
+        dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)loy * S.stride + (ptrdiff_t)lox * TS, S.stride, DEG,
+                                             P.wmat, L.fx, L.fy, px);
+      dev_brighten<NCH>(F, px);
+    }
+  } else {
+    // deriv_stepper (stepper.h:1606-1694) + twine_t (twining.h:106-263), as in k_render_tiled
+    float2 c1 = __ldg(P.col_tab + T.width + x), r1 = __ldg(P.row_tab + T.height + y);
+    ColTerm colb{c1.x, c1.y};
+    RowTerm rowb{r1.x, r1.y};
+    ColTerm firstb = colb;
+    if (T.projection == EU_CYLINDRICAL && T.normalize) {
+      float2 f1 = __ldg(P.col_tab + T.width + xf);
+      firstb = ColTerm{f1.x, f1.y};
+    }
+    float du[3], dv[3], help[NCH];
+    dev_stepper(T, F.xx, F.yy, F.zz, colb, row, firstb, y, du);
+    dev_stepper(T, F.xx, F.yy, F.zz, col, rowb, first, y, dv);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      du[c] = du[c] - r00[c];
+      dv[c] = dv[c] - r00[c];
+    }
 #pragma unroll
     for (int c = 0; c < NCH; c++) px[c] = 0.0f;
-  } else {
-    if (staged)
-      dev_window_eval<NCH, TS, DEG, true>(tile + (loy - mny) * wf + (lox * TS - a0), wf, DEG, P.wmat, L.fx, L.fy, px);
-    else
-      dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)loy * S.stride + (ptrdiff_t)lox * TS, S.stride, DEG,
-                                           P.wmat, L.fx, L.fy, px);
-    dev_brighten<NCH>(F, px);
+    const int bx1 = a0 + wf, by1 = by0 + rows;
+    for (int k = 0; k < P.n_taps; k++) {
+      float tx = __ldg(P.taps + 3 * k), ty = __ldg(P.taps + 3 * k + 1), tw = __ldg(P.taps + 3 * k + 2);
+      float r[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) r[c] = r00[c] + tx * du[c] + ty * dv[c];
+      int fc;
+      float sx, sy;
+      if (!dev_facet_coordinate(F, r, fc, sx, sy)) {
+#pragma unroll
+        for (int c = 0; c < NCH; c++) help[c] = 0.0f;
+      } else {
+        Located K = dev_locate(S, DEG, sx, sy);
+        const int kx = K.ix - H2 + P.src_lx, ky = K.iy - H2 + P.src_ly;
+        const bool in_box = staged && kx * TS >= a0 && (kx + ORDER) * TS <= bx1 && ky >= by0 && ky + ORDER <= by1;
+        if (in_box)
+          dev_window_eval<NCH, TS, DEG, true>(tile + (ky - by0) * wf + (kx * TS - a0), wf, DEG, P.wmat, K.fx, K.fy, help);
+        else
+          dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)ky * S.stride + (ptrdiff_t)kx * TS, S.stride, DEG,
+                                               P.wmat, K.fx, K.fy, help);
+        dev_brighten<NCH>(F, help);
+      }
+#pragma unroll
+      for (int c = 0; c < NCH; c++) px[c] = EU_WIN_MULADD(tw, help[c], px[c]);
+    }
   }
   if (T.unbrighten != 1.0f) {
     constexpr int NCOL = (NCH == 2 || NCH == 4) ? NCH - 1 : NCH;
@@ -702,16 +759,16 @@ static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_
     // Measured on B200 (profiles/): it wins for the cubic window (16 taps/px: C2 0.60 vs 0.75 ms)
     // and loses for the bilinear one (4 taps/px: C3b 1.56 vs 1.32 ms), where the two block-wide
     // synchronisations cost more than the gathers they replace - so it is used for degree 3 only.
-    if constexpr (!TWINE && NCH == 3) {  // opt-in: per-warp staging (RGB rasters, no twining), also bilinear
+    if constexpr (NCH == 3) {  // opt-in: per-warp staging (RGB rasters), also for the bilinear evaluator
       if (P.use_tiles == 2 && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.any_generic && P.degree == 1) {
-        k_render_warp<NCH, TS, 1><<<grid, block, 0, st>>>(P);
+        k_render_warp<NCH, TS, TWINE, 1><<<grid, block, 0, st>>>(P);
         return;
       }
     }
     if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.any_generic && P.degree == 3) {
-      if constexpr (!TWINE && NCH == 3) {
+      if constexpr (NCH == 3) {
         if (P.use_tiles == 2) {
-          k_render_warp<NCH, TS, 3><<<grid, block, 0, st>>>(P);
+          k_render_warp<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P);
           return;
         }
       }

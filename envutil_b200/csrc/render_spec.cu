@@ -11,11 +11,9 @@ inline bool tiles_ok(const RenderParams& P) {
 template <int SP, bool TWINE>
 bool single(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st, bool with_cubic) {
   if (P.degree == 1) {
-    if constexpr (!TWINE) {
-      if (P.use_tiles == 2 && P.out && !P.index_out && (P.f0.src.stride & 3) == 0) {  // opt-in variant
-        k_render_warp<3, 3, 1, SP><<<grid, block, 0, st>>>(P);
-        return true;
-      }
+    if (P.use_tiles == 2 && P.out && !P.index_out && (P.f0.src.stride & 3) == 0) {  // opt-in variant
+      k_render_warp<3, 3, TWINE, 1, SP><<<grid, block, 0, st>>>(P);
+      return true;
     }
     k_render<3, 3, EU_MODE_SINGLE, TWINE, 1, false, false, SP><<<grid, block, 0, st>>>(P);
     return true;
@@ -23,7 +21,7 @@ bool single(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st, bool 
   if (P.degree == 3 && with_cubic) {
     if constexpr (!TWINE) {
       if (tiles_ok(P)) {
-        if (P.use_tiles == 2) k_render_warp<3, 3, 3, SP><<<grid, block, 0, st>>>(P);  // opt-in variant
+        if (P.use_tiles == 2) k_render_warp<3, 3, false, 3, SP><<<grid, block, 0, st>>>(P);  // opt-in variant
         else k_render_tiled<3, 3, false, 3, SP><<<grid, block, 0, st>>>(P);
         return true;
       }

@@ -113,7 +113,7 @@ typedef struct eu_opts {
   int32_t reserved[2];      /* back-end options, 0 = defaults. [0] 1: 16-byte RGB texels in HBM; [1] bit 0: no
                                shared-memory footprint staging, bit 1: no kernels compiled for one job shape, bit 2: no 128-bit
                                pixel stores into peer frames, bit 3: footprint staging per warp instead of per block
-                               (bilinear and cubic RGB jobs without twining; experimental) */
+                               (bilinear and cubic single-facet RGB jobs; experimental) */
 } eu_opts_t;
 
 /* One twining tap: sub-pixel offset in units of the target's pixel step and weight

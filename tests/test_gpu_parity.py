@@ -326,7 +326,7 @@ def test_edge_jobs():
                     reason="a kernel no GPU run has seen yet: opt in with EU_GPU_UNTRIED=1 (tools/gpu_first_call.sh does)")
 def test_warp_staged_kernel_is_bit_exact():
     """k_render_warp (eu_opts_t.reserved[1] bit 3: the gather footprint staged per warp instead of per block):
-    every bilinear or cubic RGB single-facet job without twining, general and shape-compiled builds, 12- and 16-byte texels,
+    every bilinear or cubic RGB single-facet job, with and without twining, general and shape-compiled builds, 12- and 16-byte texels,
     plus a C2-shaped job large enough for full tiles. One separate process with a four-minute limit - the kernel
     waits on an mbarrier, and a mistake there would hang rather than fail."""
     import subprocess
@@ -338,7 +338,7 @@ def test_warp_staged_kernel_is_bit_exact():
             "from envutil_b200.engine import Engine\n"
             "from envutil_b200.job import FacetSpec, Job\n"
             "eng = Engine(0)\n"
-            "todo = {n: j for n, j in jobs.JOBS.items() if j.degree in (1, 3) and len(j.facets) == 1 and not j.twine\n"
+            "todo = {n: j for n, j in jobs.JOBS.items() if j.degree in (1, 3) and len(j.facets) == 1\n"
             "        and j.facets[0].image.shape[-1] == 3}\n"
             "todo['c2_small'] = Job([FacetSpec(synth.cubemap(256), 'cubemap', 90.0)], 'spherical', 360.0, 1024, 512, degree=3)\n"
             "todo['ll_rect_big'] = Job([FacetSpec(synth.latlon(1024), 'spherical', 360.0)], 'rectilinear', 80.0, 640, 360,\n"

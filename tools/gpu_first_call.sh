@@ -35,6 +35,6 @@ if grep -q "1 passed" "$OUT/pytest_warp.log"; then
   EU_ARITHMETIC=contracted step bench_warp_contracted 300 python bench.py --warp-tiles 1 --no-cpu-baseline
   tail -n 1 "$OUT/bench_warp_contracted.log" > "$OUT/bench_warp_contracted.json"
   # every single-facet config, block-staged / direct (0) against per-warp staging (4), same inputs
-  step configs_warp 420 python tools/bench_configs.py --configs C1,C2,C3a,C3b --padded 0,4 --steps 10
+  step configs_warp 420 python tools/bench_configs.py --configs C1,C2,C3a,C3b,C4 --padded 0,4 --steps 10
 fi
 cat "$OUT/summary.txt"
