@@ -34,6 +34,8 @@ if grep -q "1 passed" "$OUT/pytest_warp.log"; then
   tail -n 1 "$OUT/bench_warp.log" > "$OUT/bench_warp.json"
   EU_ARITHMETIC=contracted step bench_warp_contracted 300 python bench.py --warp-tiles 1 --no-cpu-baseline
   tail -n 1 "$OUT/bench_warp_contracted.log" > "$OUT/bench_warp_contracted.json"
+  # launch list + one full capture of the per-warp kernel (tools/gpu_profile.sh writes gpurun_out/*_r02warp*)
+  BENCH_FLAGS="--warp-tiles 1" step profile_warp 420 bash tools/gpu_profile.sh r02warp
   # every single-facet config, block-staged / direct (0) against per-warp staging (4), same inputs
   step configs_warp 420 python tools/bench_configs.py --configs C1,C2,C3a,C3b,C4 --padded 0,4 --steps 10
 fi
