@@ -1,7 +1,7 @@
 #!/bin/bash
 # Everything that was written after the GPU time of round 1 had run out, in the order of what it can break:
 # run as ONE gpurun call at the start of the next round,
-#   gpurun --timeout 1500 -- 'bash tools/gpu_first_call.sh'
+#   gpurun --timeout 2700 -- 'bash tools/gpu_first_call.sh'
 # and read gpurun_out/first_call/. Each step has its own time limit and its own process, so that a fault on
 # an untried size cannot take the later steps with it.
 set -u
