@@ -598,17 +598,23 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
 // Opt-in variant of the kernel above (eu_opts_t.reserved[1] bit 3; written at the end of round 1 from what
 // ncu showed on the C2 kernel - 29 % of the warp samples sit at the two block barriers, the shared-memory
 // reduction and the mbarrier wait - and NOT yet run on a GPU): every WARP stages the footprint of its own
-// 32 pixels (one row of the tile; with twining: plus a margin, as above) into its own slice of shared memory,
-// counted on its own mbarrier. No block-wide
+// 32 pixels (with twining: plus a margin, as above) into its own slice of shared memory, counted on its own
+// mbarrier. The 32 pixels are an 8 x 4 patch of the tile, not a row of it: modelled on the BASELINE configs
+// (window origins from the projection formulas), a 32 x 1 strip fits a 4 KB budget for only 72 % (C2), 59 %
+// (C3a) and 22 % (C4) of the warps - near the poles and cube-face diagonals a strip's bounding box is as tall
+// as it is wide - where an 8 x 4 patch fits 3 KB for 99.8 %, 98 % and 91 %, at 8 instead of 13 staged floats
+// per pixel (the 32 x 8 block tile: 5). No block-wide
 // synchronisation is left: the bounding box is a warp reduction whose result every lane holds, lane 0 arms
 // the barrier and issues the row copies, and a warp whose footprint does not fit gathers from HBM without
-// holding the others up. It costs about three times the L2 -> shared traffic (the rows that the eight warps
-// of a tile share are fetched by each of them). Values and their order of combination are those of the
+// holding the others up. It costs about 1.6 times the L2 -> shared traffic (the texels that neighbouring
+// patches share are fetched by each of them). Values and their order of combination are those of the
 // other kernels: bit-identical output. Unlike the block-staged kernel it is also instantiated for the
 // bilinear evaluator - that one lost to direct gathers because of the two block barriers, which are gone here.
 // ------------------------------------------------------------------------------------------
-#define EU_WARP_TILE_FLOATS 1024  // 4 KB staged footprint per warp, 32 KB per block
+#define EU_WARP_TILE_FLOATS 768   // 3 KB staged footprint per warp, 24 KB per block: 8 blocks per SM
 #define EU_WARP_TILE_ROWS 16
+#define EU_WARP_PATCH_X 8  // the 32 pixels of a warp: an 8 x 4 patch (see below)
+#define EU_WARP_PATCH_Y 4
 
 template <int NCH, int TS, bool TWINE, int DEG, int SP = 0>
 __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_warp(const __grid_constant__ RenderParams P) {
@@ -616,27 +622,32 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_warp(const __grid_con
   constexpr int ORDER = DEG + 1, H2 = DEG / 2;
   constexpr int NWARP = TILE_X * TILE_Y / 32;
   __shared__ __align__(128) float tiles[NWARP][EU_WARP_TILE_FLOATS];
-  __shared__ __align__(16) float wslot[TILE_Y][NCH == 3 ? TILE_X * 3 : 4];  // dev_store_pixel
   __shared__ __align__(8) uint64_t mbars[NWARP];
+  static_assert(TILE_X == 4 * EU_WARP_PATCH_X && TILE_Y == 2 * EU_WARP_PATCH_Y && EU_WARP_PATCH_X * EU_WARP_PATCH_Y == 32,
+                "a 32x8 tile is 4x2 patches of one warp each");
 
   SpecView<SP> V(P);
   const TargetDev& T = V.trg();
   const FacetDev& F = V.f0();
   const SourceDev& S = F.src;
-  const int lane = threadIdx.x, wid = threadIdx.y;  // TILE_X == 32: a warp is one row of the tile
-  const int x = blockIdx.x * TILE_X + lane;
-  const int y = P.row0 + blockIdx.y * TILE_Y + wid;
-  if (y >= P.row1) return;  // the whole warp: nobody else waits for it
-  const bool inside = x < T.width;
+  // the warp's pixels: a PATCH_X x PATCH_Y patch of the tile, lanes row-major inside it. (Nothing on the
+  // single-facet path depends on which pixels share a warp: the zimt-vector semantics of the steppers are
+  // functions of the pixel's own column, first_lane_column.)
+  const int lane = threadIdx.x, wid = threadIdx.y;
+  const int x = blockIdx.x * TILE_X + (wid & 3) * EU_WARP_PATCH_X + (lane % EU_WARP_PATCH_X);
+  const int ytop = P.row0 + blockIdx.y * TILE_Y + (wid >> 2) * EU_WARP_PATCH_Y;
+  const int y = ytop + lane / EU_WARP_PATCH_X;
+  if (ytop >= P.row1 || blockIdx.x * TILE_X + (wid & 3) * EU_WARP_PATCH_X >= T.width) return;  // the whole warp
+  const bool inside = x < T.width && y < P.row1;
   float* tile = tiles[wid];
   uint64_t* mbar = &mbars[wid];
   if (lane == 0) mbar_init(mbar, 1);
   __syncwarp();
 
   // ---- phase 1: rays and window origins ------------------------------------------------
-  const int xc = inside ? x : 0;
+  const int xc = inside ? x : 0, yc = inside ? y : ytop;
   const int xf = first_lane_column(xc);
-  float2 c0 = __ldg(P.col_tab + xc), r0 = __ldg(P.row_tab + y);
+  float2 c0 = __ldg(P.col_tab + xc), r0 = __ldg(P.row_tab + yc);
   ColTerm col{c0.x, c0.y};
   RowTerm row{r0.x, r0.y};
   ColTerm first = col;
@@ -645,7 +656,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_warp(const __grid_con
     first = ColTerm{f0.x, f0.y};
   }
   float r00[3];
-  dev_stepper(T, F.xx, F.yy, F.zz, col, row, first, y, r00);
+  dev_stepper(T, F.xx, F.yy, F.zz, col, row, first, yc, r00);
   int face;
   float cx, cy;
   bool hit = dev_facet_coordinate(F, r00, face, cx, cy) && inside;
@@ -749,7 +760,11 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_warp(const __grid_con
 #pragma unroll
     for (int c = 0; c < NCOL; c++) px[c] *= T.unbrighten;
   }
-  dev_store_pixel<NCH>(P, T, x, y, px, wslot[wid]);
+  // the patch's rows are runs of PATCH_X pixels: plain per-channel stores (L2 merges the sectors), also into
+  // a peer frame - the 128-bit path of dev_store_pixel needs a warp that is one row
+  float* dst = P.out + (size_t)(y - P.row0) * P.out_pitch + (size_t)x * NCH;
+#pragma unroll
+  for (int c = 0; c < NCH; c++) dst[c] = px[c];
 }
 
 template <int NCH, int TS, int MODE, bool TWINE>
