@@ -26,12 +26,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=500)
     ap.add_argument("--seed", type=int, default=11)
+    ap.add_argument("--warp-tiles", type=int, default=0,
+                    help="1: ask for the per-warp staging kernel (k_render_warp) wherever a job is eligible for it")
     a = ap.parse_args()
     rng = np.random.default_rng(a.seed)
     eng = Engine(0)
     same = diff = refused = known = 0
     for k in range(a.n):
         job = random_job(rng)
+        job.warp_tiles = bool(a.warp_tiles)
         desc = "%s<-%s d%d tw%d %dx%d" % (job.projection, "+".join("%s%dx%d" % ((f.projection,) + f.native_shape()[:2])
                                                                     for f in job.facets), job.degree, job.twine,
                                           job.width, job.height)

@@ -30,6 +30,7 @@ fi
 #    Parity first (own process, four-minute limit inside the test), the bench only if that passed.
 EU_GPU_UNTRIED=1 step pytest_warp 330 python -m pytest tests/test_gpu_parity.py::test_warp_staged_kernel_is_bit_exact -q -rxXs
 if grep -q "1 passed" "$OUT/pytest_warp.log"; then
+  step fuzz_gpu_warp 400 python tools/fuzz_gpu_vs_oracle.py --n 300 --seed 12 --warp-tiles 1
   step bench_warp 300 python bench.py --warp-tiles 1 --no-cpu-baseline
   tail -n 1 "$OUT/bench_warp.log" > "$OUT/bench_warp.json"
   EU_ARITHMETIC=contracted step bench_warp_contracted 300 python bench.py --warp-tiles 1 --no-cpu-baseline
