@@ -101,3 +101,17 @@ def test_contracted_kernels_equal_contracted_oracle():
     r = _run(code, {"EU_ARITHMETIC": "contracted"})
     print(r.stdout)
     assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-1500:]
+
+
+def test_contracted_oracle_is_pinned_to_itself():
+    """The variant's restatement has no reference build to be pinned to (a compiler chooses its own
+    contractions), so its outputs are pinned to themselves: tests/golden/contracted.json holds the hashes of
+    the twelve jobs above as first written, against accidental changes of the restatement."""
+    import hashlib
+    import json
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "contracted.json")))
+    assert sorted(want) == sorted(SUBSET)
+    for name in SUBSET:
+        out = harness.oracle_render(jobs.JOBS[name], contracted=True)
+        assert list(out.shape) == want[name]["shape"]
+        assert hashlib.sha256(out.tobytes()).hexdigest() == want[name]["sha256"], name
