@@ -354,6 +354,21 @@ def test_warp_staged_kernel_is_bit_exact():
             "            print(name, no_spec, padded, c['n_diff'], flush=True)\n"
             "            bad += c['n_diff'] != 0\n"
             "print('jobs', len(todo))\n"
+            "# row bands with edges that are no multiples of the 4-row patch (eu_render_rows, the multi-GPU unit)\n"
+            "import numpy as np, torch\n"
+            "job = copy.copy(todo['c2_small']); job.warp_tiles = True\n"
+            "st = job.structs(); t = st[0]\n"
+            "hs = eng.stage(job, st)\n"
+            "buf = torch.zeros((t.height, t.width, t.nchannels), dtype=torch.float32, device='cuda:0')\n"
+            "edges = [0, 7, 40, 41, 203, t.height]\n"
+            "stream = torch.cuda.current_stream().cuda_stream\n"
+            "for r0, r1 in zip(edges[:-1], edges[1:]):\n"
+            "    eng.render_rows(job, hs, st, r0, r1, buf[r0].data_ptr(), stream)\n"
+            "torch.cuda.synchronize()\n"
+            "same = np.array_equal(buf.cpu().numpy(), harness.oracle_render(todo['c2_small']))\n"
+            "print('bands', same, flush=True)\n"
+            "eng.release(hs)\n"
+            "bad += not same\n"
             "sys.exit(3 if bad else 0)\n"
             % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
