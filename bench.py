@@ -533,9 +533,9 @@ def ours(args):
                                  "footprint staged in shared memory by cp.async.bulk",
                        "arithmetic": capi.ARITHMETIC,  # "contracted" only with EU_ARITHMETIC=contracted (opt-in build)
                        "parity": "bit-exact vs pinned-math reference build (tests/)" if capi.ARITHMETIC == "exact" else
-                                 "window evaluation with fused multiply-adds: indices identical, values within 2.6e-6 "
-                                 "relative (hdr_merge 1.6e-5) of the pinned-math reference build, RMS <= 2.7e-7 "
-                                 "(tests/test_contracted.py)"},
+                                 "window evaluation with fused multiply-adds: indices identical, values within 3.5e-7 "
+                                 "relative (RMS 5.8e-8) of the pinned-math reference build on this workload, 2.6e-6 "
+                                 "(hdr_merge 1.6e-5) over the 98 small jobs (tests/test_contracted.py, DESIGN.md 2)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": tr["traffic_bytes"] if tr else None,
                          "traffic_source": tr["source"] if tr else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_launch,
