@@ -8,10 +8,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# EU_ARITHMETIC=contracted selects the opt-in build whose window evaluation uses fused multiply-adds
-# (include/envutil_b200.h: eu_render_arithmetic); anything else is the bit-exact default
+# EU_ARITHMETIC=contracted makes Job.structs() ask for the contracted arithmetic (EU_OPT_CONTRACTED: fused
+# multiply-adds in the window evaluation) unless a Job says otherwise; anything else is the bit-exact default.
+# Both arithmetics live in the one library.
 ARITHMETIC = "contracted" if os.environ.get("EU_ARITHMETIC", "") == "contracted" else "exact"
-LIB_PATH = os.path.join(_HERE, "libenvutil_b200_fma.so" if ARITHMETIC == "contracted" else "libenvutil_b200.so")
+LIB_PATH = os.path.join(_HERE, "libenvutil_b200.so")
+OPT_NO_TILES, OPT_NO_SHAPES, OPT_NARROW_STORES, OPT_CONTRACTED = 1, 2, 4, 16  # eu_opts_t.reserved[1]
 
 # eu_projection_t (reference envutil_basic.h:99-109)
 SPHERICAL, CYLINDRICAL, RECTILINEAR, STEREOGRAPHIC, FISHEYE, CUBEMAP, BIATAN6, PRJ_NONE = range(8)
@@ -121,6 +123,9 @@ SYMBOLS = {
     "eu_render_rows_pitched": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
                                          C.POINTER(SourceH), C.POINTER(Tap), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_int, C.c_void_p, C.POINTER(Timing)]),
+    "eu_render_rect_pitched": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
+                                         C.POINTER(SourceH), C.POINTER(Tap), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Timing)]),
     "eu_source_reserve": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.POINTER(SourceH),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
     "eu_source_commit": (C.c_int, [SourceH, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p, C.POINTER(Timing)]),
@@ -136,6 +141,8 @@ SYMBOLS = {
     "eu_frame_close": (C.c_int, [C.c_void_p]),
     "eu_debug_planes": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
                                   C.POINTER(SourceH), C.c_void_p]),
+    "eu_debug_tie_plane": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
+                                     C.POINTER(SourceH), C.c_int, C.c_void_p]),
 }
 
 _lib = None
@@ -153,8 +160,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.eu_render_arithmetic() != (1 if ARITHMETIC == "contracted" else 0):
-        raise RuntimeError(f"{LIB_PATH} was not built with the {ARITHMETIC} arithmetic it is named for")
+    if lib.eu_render_arithmetic() != 2:
+        raise RuntimeError(f"{LIB_PATH} does not carry both arithmetics: rebuild (__graft_entry__.build())")
     _lib = lib
     return lib
 

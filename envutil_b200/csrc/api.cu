@@ -44,6 +44,12 @@ struct eu_source {
 
 namespace {
 
+#define EU_TABLE_SLOTS 8
+#define EU_PLANAR_ENTRIES 6
+#define EU_SLOT_FACETS_BYTES (sizeof(FacetDev) * EU_MAX_FACETS)
+#define EU_SLOT_TAPS_BYTES (sizeof(float) * 3 * EU_MAX_TAPS)
+#define EU_SLOT_BYTES (EU_SLOT_FACETS_BYTES + EU_SLOT_TAPS_BYTES + sizeof(float) * (EU_INV_NK + 8))
+
 struct Context {
   bool up = false;
   int device = -1;
@@ -62,16 +68,28 @@ struct Context {
   std::vector<eu_source*> sources;
   std::map<std::string, eu_source*> by_key;
   long cycle = 0;
-  // per-job scratch, grown on demand
-  float2* d_planar = nullptr;  // column terms [2][W] then row terms [2][H]
-  size_t planar_cap = 0;
-  TargetDev planar_for;
-  bool planar_valid = false;
-  FacetDev* d_facets = nullptr;
-  int facets_cap = 0;
-  float* d_taps = nullptr;
-  float* d_invcoef = nullptr;  // inverse_lcp spline of a 'single' job's target facet (inverse_planar)
-  int taps_cap = 0;
+  // Per-job tables. A plan's facet array, tap list and inverse-lens spline live in ONE slot of a small ring;
+  // the slot is rewritten on the stream the next plan renders on only after that stream has waited for the
+  // event recorded behind the slot's last consumer, so jobs on different streams (eu_render_rows on a
+  // caller's stream, eu_render_async on the library's) never see each other's tables.
+  struct TableSlot {
+    unsigned char* mem = nullptr;  // FacetDev[EU_MAX_FACETS] | taps[3 * EU_MAX_TAPS] | invcoef[EU_INV_NK + 8]
+    cudaEvent_t used = nullptr;
+    bool in_use = false;
+  } slots[EU_TABLE_SLOTS];
+  int next_slot = 0;
+  // stepper tables (k_planar_tables) of the most recent targets: pipelines that alternate between targets
+  // (the two stages of BASELINE configs[4]) find theirs again instead of draining the device
+  struct PlanarEntry {
+    float2* buf = nullptr;  // column terms [2][W], row terms [2][H], then the bare planar coordinates
+    size_t cap = 0;
+    TargetDev key;
+    bool valid = false;
+    long stamp = 0;
+    cudaEvent_t used = nullptr;
+    bool in_use = false;
+  } planar[EU_PLANAR_ENTRIES];
+  long planar_clock = 0;
   float* d_out = nullptr;
   size_t out_cap = 0;
   int32_t* d_index = nullptr;
@@ -363,13 +381,47 @@ int first_of(int nf, const eu_opts_t* o) { return (nf > 1 && o->solo >= 0 && o->
 struct Plan {
   RenderParams P;
   int launches;
+  int slot = -1;    // Context::slots entry holding this plan's tables (-1: none needed)
+  int planar = -1;  // Context::planar entry holding its stepper tables
 };
+
+// after the plan's last kernel has been enqueued on `st`: later plans may reuse its tables once this point
+// of `st` has been reached
+cudaError_t plan_done(const Plan& plan, cudaStream_t st) {
+  if (plan.slot >= 0) {
+    cudaError_t e = cudaEventRecord(g.slots[plan.slot].used, st);
+    if (e != cudaSuccess) return e;
+    g.slots[plan.slot].in_use = true;
+  }
+  if (plan.planar >= 0) {
+    cudaError_t e = cudaEventRecord(g.planar[plan.planar].used, st);
+    if (e != cudaSuccess) return e;
+    g.planar[plan.planar].in_use = true;
+  }
+  return cudaSuccess;
+}
+
+// the plan's table slot, ready to be written on `cs`
+int take_slot(Plan& plan, cudaStream_t cs, unsigned char** mem) {
+  if (plan.slot < 0) {
+    plan.slot = g.next_slot;
+    g.next_slot = (g.next_slot + 1) % EU_TABLE_SLOTS;
+    Context::TableSlot& S = g.slots[plan.slot];
+    if (!S.mem) {
+      CK(cudaMalloc(&S.mem, EU_SLOT_BYTES));
+      CK(cudaEventCreateWithFlags(&S.used, cudaEventDisableTiming));
+    }
+    if (S.in_use) CK(cudaStreamWaitEvent(cs, S.used, 0));
+  }
+  *mem = g.slots[plan.slot].mem;
+  return EU_OK;
+}
 
 // pto_planar<float, L, true>: the inverse planar transformation of a 'single' job's target facet. The knots
 // of inverse_lcp's spline (lens_correction.h:341-386) are found on the host - Newton's method in double,
 // eu_polynomial<double, 4>::inverse (:133-170) - and become b-spline coefficients on the device with the
 // very kernels that prefilter rasters (one line of EU_INV_NK floats, NATURAL), then the NATURAL brace.
-int inverse_planar(const eu_facet_t* ft, cudaStream_t cs, InvPlanarDev& IP) {
+int inverse_planar(const eu_facet_t* ft, cudaStream_t cs, float* d_invcoef, InvPlanarDev& IP) {
   memset(&IP, 0, sizeof(IP));
   IP.on = 1;
   IP.has_shear = ft->has_shear;
@@ -419,8 +471,7 @@ int inverse_planar(const eu_facet_t* ft, cudaStream_t cs, InvPlanarDev& IP) {
       return fail(EU_ERR_ARGUMENT, "the lens polynomial a=%g b=%g c=%g cannot be inverted", ft->a, ft->b, ft->c);
     knots[i] = (float)(notch == 0.0 ? 1.0 / der(0.0) : (current / notch) - 1);
   }
-  if (!g.d_invcoef) CK(cudaMalloc(&g.d_invcoef, sizeof(float) * (EU_INV_NK + 8)));
-  float* core = g.d_invcoef + 4;  // 16-byte aligned start of the line; the brace uses core[-2..-1] and core[nk..nk+1]
+  float* core = d_invcoef + 4;  // 16-byte aligned start of the line; the brace uses core[-2..-1] and core[nk..nk+1]
   CK(cudaMemcpyAsync(core, knots, sizeof(knots), cudaMemcpyHostToDevice, cs));  // pageable: staged before return
   IirDev f;
   iir_setup(f, EU_BC_NATURAL, 3, (long double)FLT_EPSILON, nk);
@@ -493,7 +544,10 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     if (rc) return rc;
   }
   if (ft && ft->has_2d_tf) {  // tf22 = pto_planar<float, L, true>(ft), envutil_payload.cc:1864
-    int rc = inverse_planar(ft, cs, P.inv);
+    unsigned char* mem = nullptr;
+    int rc = take_slot(plan, cs, &mem);
+    if (rc) return rc;
+    rc = inverse_planar(ft, cs, reinterpret_cast<float*>(mem + EU_SLOT_FACETS_BYTES + EU_SLOT_TAPS_BYTES), P.inv);
     if (rc) return rc;
     plan.launches += 2;
   }
@@ -509,7 +563,7 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     for (int i = 0; i < nf; i++) F[i].hdr_kind = (i == lo) ? EU_HDR_LOW : (i == hi) ? EU_HDR_HIGH : EU_HDR_MIDDLE;
   }
   P.f0 = F[first];
-  P.use_tiles = (o->reserved[1] & 1) ? 0 : ((o->reserved[1] & 8) ? 2 : 1);  // 2: per-warp staging (opt-in)
+  P.use_tiles = (o->reserved[1] & EU_OPT_NO_TILES) ? 0 : 1;
   P.src_cw = sources[first]->cw;
   P.src_ch = sources[first]->chh;
   P.src_lx = sources[first]->lx;
@@ -517,52 +571,68 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   P.src_base = sources[first]->container;
   P.n_facets = mode == EU_MODE_SINGLE ? 1 : nf;
   if (mode != EU_MODE_SINGLE) {
-    if (nf > g.facets_cap) {
-      if (g.d_facets) CK(cudaFree(g.d_facets));
-      g.d_facets = nullptr;
-      g.facets_cap = 0;
-      CK(cudaMalloc(&g.d_facets, sizeof(FacetDev) * EU_MAX_FACETS));
-      g.facets_cap = EU_MAX_FACETS;
-    }
-    CK(cudaMemcpyAsync(g.d_facets, F.data(), sizeof(FacetDev) * nf, cudaMemcpyHostToDevice, cs));
-    P.facets = g.d_facets;
+    unsigned char* mem = nullptr;
+    int rc = take_slot(plan, cs, &mem);
+    if (rc) return rc;
+    // pageable source: the call returns once the data sit in the driver's staging buffer
+    CK(cudaMemcpyAsync(mem, F.data(), sizeof(FacetDev) * nf, cudaMemcpyHostToDevice, cs));
+    P.facets = reinterpret_cast<const FacetDev*>(mem);
   }
   if (n_taps > 0) {
-    if (n_taps > g.taps_cap) {
-      if (g.d_taps) CK(cudaFree(g.d_taps));
-      g.d_taps = nullptr;
-      g.taps_cap = 0;
-      CK(cudaMalloc(&g.d_taps, sizeof(float) * 3 * EU_MAX_TAPS));
-      g.taps_cap = EU_MAX_TAPS;
-    }
+    unsigned char* mem = nullptr;
+    int rc = take_slot(plan, cs, &mem);
+    if (rc) return rc;
     std::vector<float> tp(3 * (size_t)n_taps);
     for (int k = 0; k < n_taps; k++) {  // bias 4 = 1/0.25, twining.h:106-121
       tp[3 * k] = taps[k].x * 4.0f;
       tp[3 * k + 1] = taps[k].y * 4.0f;
       tp[3 * k + 2] = taps[k].w;
     }
-    // pageable source: the call returns once the data sit in the driver's staging buffer
-    CK(cudaMemcpyAsync(g.d_taps, tp.data(), sizeof(float) * tp.size(), cudaMemcpyHostToDevice, cs));
-    P.taps = g.d_taps;
+    CK(cudaMemcpyAsync(mem + EU_SLOT_FACETS_BYTES, tp.data(), sizeof(float) * tp.size(), cudaMemcpyHostToDevice, cs));
+    P.taps = reinterpret_cast<const float*>(mem + EU_SLOT_FACETS_BYTES);
   }
-  // planar tables: recomputed only when the target changes
+  // stepper tables: recomputed only for a target that is not among the recent ones
   const int ow = out_width(t), oh = out_height(t);
-  size_t need = 3 * (size_t)(ow + oh);  // float2 terms + the bare planar coordinate per entry, in float2 units
-  if (!g.planar_valid || memcmp(&g.planar_for, &P.trg, sizeof(TargetDev)) != 0 || need > g.planar_cap) {
+  {
+    const size_t need = 3 * (size_t)(ow + oh);  // float2 terms + the bare planar coordinate per entry, in float2 units
     TargetDev key = P.trg;
-    CK(cudaDeviceSynchronize());  // nothing in flight may still read the old tables
-    int rc = grow(g.d_planar, g.planar_cap, need);
-    if (rc) return rc;
-    CK(eu_launch_planar_tables(P.trg, g.d_planar, g.d_planar + 2 * (size_t)ow,
-                               reinterpret_cast<float*>(g.d_planar + 2 * (size_t)(ow + oh)), g.stream));
-    plan.launches++;
-    g.planar_for = key;
-    g.planar_valid = true;
+    key.normalize = 0;  // does not enter the tables
+    int hit = -1, victim = 0;
+    for (int i = 0; i < EU_PLANAR_ENTRIES; i++) {
+      Context::PlanarEntry& E = g.planar[i];
+      if (E.valid && memcmp(&E.key, &key, sizeof(TargetDev)) == 0) hit = i;
+      if (!E.valid) { if (g.planar[victim].valid) victim = i; }
+      else if (g.planar[victim].valid && E.stamp < g.planar[victim].stamp) victim = i;
+    }
+    if (hit < 0) {
+      Context::PlanarEntry& E = g.planar[victim];
+      if (!E.used) CK(cudaEventCreateWithFlags(&E.used, cudaEventDisableTiming));
+      if (E.in_use) CK(cudaStreamWaitEvent(g.stream, E.used, 0));  // its last reader, on whatever stream that was
+      E.valid = false;
+      if (need > E.cap) {
+        if (E.buf) CK(cudaFreeAsync(E.buf, g.stream));
+        E.buf = nullptr;
+        E.cap = 0;
+        CK(cudaMallocAsync((void**)&E.buf, need * sizeof(float2), g.stream));
+        E.cap = need;
+      }
+      CK(eu_launch_planar_tables(P.trg, E.buf, E.buf + 2 * (size_t)ow, reinterpret_cast<float*>(E.buf + 2 * (size_t)(ow + oh)),
+                                 g.stream));
+      plan.launches++;
+      E.key = key;
+      E.valid = true;
+      hit = victim;
+    }
+    Context::PlanarEntry& E = g.planar[hit];
+    E.stamp = ++g.planar_clock;
+    plan.planar = hit;
+    P.col_tab = E.buf;
+    P.row_tab = E.buf + 2 * (size_t)ow;
+    P.planar_raw = reinterpret_cast<const float*>(E.buf + 2 * (size_t)(ow + oh));
   }
-  // normalize is part of TargetDev but does not change the tables; keep the key exact anyway
-  P.col_tab = g.d_planar;
-  P.row_tab = g.d_planar + 2 * (size_t)ow;
-  P.planar_raw = reinterpret_cast<const float*>(g.d_planar + 2 * (size_t)(ow + oh));
+  P.col0 = 0;
+  P.col1 = ow;
+  P.arith = (o->reserved[1] & EU_OPT_CONTRACTED) ? 1 : 0;
   // the specialised kernels assume every facet they touch has the job's channel count and one
   // texel stride; anything else (and translation) runs the general build
   P.any_generic = 0;
@@ -585,7 +655,7 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     }
     if (fits) P.spec = sp;
   }
-  if (o->reserved[1] & 2) P.spec = 0;  // back-end option: general kernels only
+  if (o->reserved[1] & EU_OPT_NO_SHAPES) P.spec = 0;  // back-end option: general kernels only
   {
     int d = o->spline_degree;
     for (int row = 0; row <= d; row++)
@@ -748,6 +818,9 @@ extern "C" {
 
 const char* eu_last_error(void) { return g_err; }
 
+// both arithmetics are built in; eu_opts_t.reserved[1] bit 4 (EU_OPT_CONTRACTED) selects per job
+int eu_render_arithmetic(void) { return 2; }
+
 int eu_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -768,7 +841,8 @@ int eu_init(int device_id) {
   CK(cudaSetDevice(device_id));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device_id));
-  if (prop.major < 10)
+  // arch-specific ('a') code is not forward compatible: sm_100a SASS runs on compute capability 10.0 only
+  if (prop.major != 10 || prop.minor != 0)
     return fail(EU_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device_id, prop.major,
                 prop.minor);
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
@@ -788,7 +862,6 @@ int eu_init(int device_id) {
   for (auto& e : g.ev) CK(cudaEventCreate(&e));
   g.device = device_id;
   g.up = true;
-  g.planar_valid = false;
   return EU_OK;
 }
 
@@ -796,10 +869,14 @@ void eu_shutdown(void) {
   if (!g.up) return;
   cudaStreamSynchronize(g.stream);
   while (!g.sources.empty()) free_source(g.sources.back());
-  cudaFree(g.d_planar);
-  cudaFree(g.d_facets);
-  cudaFree(g.d_taps);
-  cudaFree(g.d_invcoef);
+  for (auto& S : g.slots) {
+    cudaFree(S.mem);
+    if (S.used) cudaEventDestroy(S.used);
+  }
+  for (auto& E : g.planar) {
+    if (E.buf) cudaFreeAsync(E.buf, g.stream);
+    if (E.used) cudaEventDestroy(E.used);
+  }
   cudaFree(g.d_out);
   cudaFree(g.d_index);
   cudaDeviceSynchronize();
@@ -1042,12 +1119,24 @@ int eu_render_rows(const eu_target_t* t, const eu_opts_t* o, int n_facets, const
 int eu_render_rows_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
                            const eu_source_h* sources, const eu_tap_t* taps, int n_taps, int row0, int row1,
                            float* d_out, int out_pitch_floats, void* cuda_stream, eu_timing_t* timing) {
+  if (!t) return fail(EU_ERR_ARGUMENT, "null argument");
+  return eu_render_rect_pitched(t, o, n_facets, facets, sources, taps, n_taps, row0, row1, 0, out_width(t), d_out,
+                                out_pitch_floats, cuda_stream, timing);
+}
+
+int eu_render_rect_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+                           const eu_source_h* sources, const eu_tap_t* taps, int n_taps, int row0, int row1, int col0,
+                           int col1, float* d_out, int out_pitch_floats, void* cuda_stream, eu_timing_t* timing) {
   int rc = need_up();
   if (rc) return rc;
   Plan plan;
   rc = build_plan(t, o, n_facets, facets, sources, taps, n_taps, (cudaStream_t)cuda_stream, plan);
   if (rc) return rc;
   if (row0 < 0 || row1 > out_height(t) || row0 >= row1) return fail(EU_ERR_ARGUMENT, "bad row band [%d,%d)", row0, row1);
+  if (col0 < 0 || col1 > out_width(t) || col0 >= col1 || (col0 & 31))
+    return fail(EU_ERR_ARGUMENT, "bad column range [%d,%d): it must lie inside the raster and start at a multiple of 32", col0, col1);
+  plan.P.col0 = col0;
+  plan.P.col1 = col1;
   if (!d_out) return fail(EU_ERR_ARGUMENT, "null output");
   if (out_pitch_floats < out_width(t) * t->nchannels) return fail(EU_ERR_ARGUMENT, "output pitch %d is shorter than a row", out_pitch_floats);
   cudaStream_t caller = (cudaStream_t)cuda_stream;
@@ -1075,11 +1164,12 @@ int eu_render_rows_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facet
       g_peer_asked = d_out;
     }
     plan.P.wide_stores = g_peer_answer;
-    if (o->reserved[1] & 4) plan.P.wide_stores = 0;  // back-end option: 4-byte stores everywhere
+    if (o->reserved[1] & EU_OPT_NARROW_STORES) plan.P.wide_stores = 0;  // back-end option: 4-byte stores everywhere
   }
   if (timing) CK(cudaEventRecord(g.ev[0], caller));
   int shape = 0;
   CK(eu_launch_render(plan.P, caller, &shape));
+  CK(plan_done(plan, caller));
   plan.launches++;
   if (timing) {
     CK(cudaEventRecord(g.ev[1], caller));
@@ -1158,6 +1248,7 @@ int eu_render_async(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
   plan.P.index_out = nullptr;
   CK(cudaEventRecord(J.start, g.stream));
   CK(eu_launch_render(plan.P, g.stream));
+  CK(plan_done(plan, g.stream));
   CK(cudaEventRecord(J.rendered, g.stream));
   CK(cudaStreamWaitEvent(g.down_stream, J.rendered, 0));
   CK(cudaMemcpyAsync(out, J.d_out, n * sizeof(float), cudaMemcpyDeviceToHost, g.down_stream));
@@ -1207,7 +1298,30 @@ int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
   plan.P.out_pitch = out_width(t) * t->nchannels;
   plan.P.index_out = g.d_index;
   CK(eu_launch_render(plan.P, g.stream));
+  CK(plan_done(plan, g.stream));
   CK(cudaMemcpyAsync(index_out, g.d_index, n * sizeof(int32_t), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return EU_OK;
+}
+
+int eu_debug_tie_plane(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+                       const eu_source_h* sources, int ulps, unsigned char* tie_out) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!t || !tie_out || ulps < 0) return fail(EU_ERR_ARGUMENT, "bad argument");
+  Plan plan;
+  rc = build_plan(t, o, n_facets, facets, sources, nullptr, 0, g.stream, plan);
+  if (rc) return rc;
+  size_t n = (size_t)out_width(t) * out_height(t);
+  unsigned char* d_tie = nullptr;
+  CK(cudaMallocAsync((void**)&d_tie, n, g.stream));
+  plan.P.row0 = 0;
+  plan.P.row1 = out_height(t);
+  cudaError_t e = eu_launch_tie_plane(plan.P, d_tie, ulps, g.stream);
+  if (e == cudaSuccess) e = plan_done(plan, g.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tie_out, d_tie, n, cudaMemcpyDeviceToHost, g.stream);
+  cudaFreeAsync(d_tie, g.stream);
+  if (e != cudaSuccess) return fail(EU_ERR_CUDA, "tie plane: %s", cudaGetErrorString(e));
   CK(cudaStreamSynchronize(g.stream));
   return EU_OK;
 }

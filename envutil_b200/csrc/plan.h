@@ -131,11 +131,13 @@ struct RenderParams {
   int32_t any_generic;  // the general build is needed: some facet uses the generic stepper (translation) or
                         // differs from the job in channel count / texel stride
   int32_t spec;       // index into eu_render_specs the job matches (0: none)
-  int32_t use_tiles;  // 1: stage the gather footprint in shared memory where the kernel supports it; 2: per warp
+  int32_t use_tiles;  // 1: stage the gather footprint in shared memory where the kernel supports it
   int32_t src_cw, src_ch;  // container shape of f0's source in texels (tile path)
   int32_t src_lx, src_ly;  // its left / top brace: core texel (0,0) is container texel (lx, ly)
   const float* src_base;   // first float of f0's container (256-byte aligned, rows 16-byte aligned)
   int32_t row0, row1;  // rows rendered by this launch
+  int32_t col0, col1;  // columns rendered by this launch (col0 a multiple of 32; the whole width unless a caller narrows it)
+  int32_t arith;       // 0: every product and sum rounded separately; 1: fused multiply-adds in the window evaluation
   float* out;          // first float of row `row0`
   int32_t out_pitch;   // floats from one output row to the next (width * nch for a dense band)
   int32_t wide_stores; // 1: `out` is another GPU's memory - RGB pixels leave as 128-bit stores (dev_store_pixel)

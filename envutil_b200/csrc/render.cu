@@ -46,16 +46,17 @@ cudaError_t eu_launch_planar_tables(const TargetDev& T, float2* d_col, float2* d
 
 cudaError_t eu_launch_render(const RenderParams& P, cudaStream_t st, int* spec_used) {
   if (spec_used) *spec_used = 0;
+  const bool fma = P.arith == 1;
   // the general build (any_generic) ignores the compile-time texel stride, any TU of the right
   // channel count serves it
-  if (eu_launch_render_spec(P, st)) {
+  if (fma ? eu_launch_render_spec_fma(P, st) : eu_launch_render_spec(P, st)) {
     if (spec_used) *spec_used = P.spec;
     return cudaGetLastError();
   }
-  if (P.nch == 1) return eu_launch_render_c1(P, st);
-  if (P.nch == 2) return eu_launch_render_c2(P, st);
-  if (P.nch == 3 && (P.tstride == 3 || P.any_generic)) return eu_launch_render_c3(P, st);
-  if (P.nch == 3 && P.tstride == 4) return eu_launch_render_c3p(P, st);
-  if (P.nch == 4) return eu_launch_render_c4(P, st);
+  if (P.nch == 1) return fma ? eu_launch_render_c1_fma(P, st) : eu_launch_render_c1(P, st);
+  if (P.nch == 2) return fma ? eu_launch_render_c2_fma(P, st) : eu_launch_render_c2(P, st);
+  if (P.nch == 3 && (P.tstride == 3 || P.any_generic)) return fma ? eu_launch_render_c3_fma(P, st) : eu_launch_render_c3(P, st);
+  if (P.nch == 3 && P.tstride == 4) return fma ? eu_launch_render_c3p_fma(P, st) : eu_launch_render_c3p(P, st);
+  if (P.nch == 4) return fma ? eu_launch_render_c4_fma(P, st) : eu_launch_render_c4(P, st);
   return cudaErrorInvalidValue;
 }

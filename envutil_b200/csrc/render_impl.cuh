@@ -19,6 +19,21 @@
 #define TILE_X 32
 #define TILE_Y 8
 
+// Both arithmetics live in one library (eu_opts_t.reserved[1] bit 4 selects per job): the render translation
+// units are compiled twice, the second time with -DEU_CONTRACT_WINDOW (eu_device.cuh: fused multiply-adds in
+// the window evaluation and the twining accumulation). Kernels and launchers of the two builds must not share
+// symbols, so everything below sits in a namespace named after the arithmetic and the exported launchers
+// carry a suffix (render.cu picks by RenderParams::arith).
+#ifdef EU_CONTRACT_WINDOW
+#define EU_ARITH_NS eu_contracted
+#define EU_ARITH_FN(name) name##_fma
+#else
+#define EU_ARITH_NS eu_exact
+#define EU_ARITH_FN(name) name
+#endif
+
+namespace EU_ARITH_NS {
+
 __device__ __forceinline__ int first_lane_column(int x) {
   int seg0 = (x / EU_SEGMENT) * EU_SEGMENT;
   return seg0 + (x - seg0) % EU_LANES;
@@ -43,7 +58,7 @@ __device__ __forceinline__ void dev_store_pixel(const RenderParams& P, const Tar
   } else if constexpr (NCH == 3) {
     const int lane = threadIdx.x;  // TILE_X == 32: a warp is one row of the tile
     const bool vec = P.wide_stores && ((P.out_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) &&
-                     (blockIdx.x * TILE_X + TILE_X <= T.width);  // warp-uniform
+                     (x - lane + TILE_X <= P.col1);  // warp-uniform: the whole warp renders
     if (vec) {
       wslot[lane * 3] = px[0];
       wslot[lane * 3 + 1] = px[1];
@@ -275,14 +290,14 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
     __syncthreads();
     fa = reinterpret_cast<const FacetDev*>(sfa);
   }
-  int x = blockIdx.x * TILE_X + threadIdx.x;
+  int x = P.col0 + blockIdx.x * TILE_X + threadIdx.x;
   int y = P.row0 + blockIdx.y * TILE_Y + threadIdx.y;
-  const bool active = x < T.width && y < P.row1;
+  const bool active = x < P.col1 && y < P.row1;
   if constexpr (MODE != EU_MODE_VORONOI_PLUS) {
     if (!active) return;
   } else {  // all lanes stay for the half-warp votes; idle ones compute on a pixel that exists
     if (y >= P.row1) return;  // whole warp (a warp is one row of the tile)
-    x = min(x, T.width - 1);
+    x = min(x, P.col1 - 1);
   }
   int xf = first_lane_column(x);
   PixelTerms t;
@@ -452,9 +467,9 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
   const FacetDev& F = V.f0();
   const SourceDev& S = F.src;
   const int tid = threadIdx.y * TILE_X + threadIdx.x;
-  const int x = blockIdx.x * TILE_X + threadIdx.x;
+  const int x = P.col0 + blockIdx.x * TILE_X + threadIdx.x;
   const int y = P.row0 + blockIdx.y * TILE_Y + threadIdx.y;
-  const bool inside = x < T.width && y < P.row1;
+  const bool inside = x < P.col1 && y < P.row1;
   if (tid == 0) mbar_init(&mbar, 1);
 
   // ---- phase 1: rays and window origins ------------------------------------------------
@@ -594,179 +609,6 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
   dev_store_pixel<NCH>(P, T, x, y, px, wslot[threadIdx.y]);
 }
 
-// ------------------------------------------------------------------------------------------
-// Opt-in variant of the kernel above (eu_opts_t.reserved[1] bit 3; written at the end of round 1 from what
-// ncu showed on the C2 kernel - 29 % of the warp samples sit at the two block barriers, the shared-memory
-// reduction and the mbarrier wait - and NOT yet run on a GPU): every WARP stages the footprint of its own
-// 32 pixels (with twining: plus a margin, as above) into its own slice of shared memory, counted on its own
-// mbarrier. The 32 pixels are an 8 x 4 patch of the tile, not a row of it: modelled on the BASELINE configs
-// (window origins from the projection formulas), a 32 x 1 strip fits a 4 KB budget for only 72 % (C2), 59 %
-// (C3a) and 22 % (C4) of the warps - near the poles and cube-face diagonals a strip's bounding box is as tall
-// as it is wide - where an 8 x 4 patch fits 3 KB for 99.8 %, 98 % and 91 %, at 8 instead of 13 staged floats
-// per pixel (the 32 x 8 block tile: 5). No block-wide
-// synchronisation is left: the bounding box is a warp reduction whose result every lane holds, lane 0 arms
-// the barrier and issues the row copies, and a warp whose footprint does not fit gathers from HBM without
-// holding the others up. It costs about 1.6 times the L2 -> shared traffic (the texels that neighbouring
-// patches share are fetched by each of them). Values and their order of combination are those of the
-// other kernels: bit-identical output. Unlike the block-staged kernel it is also instantiated for the
-// bilinear evaluator - that one lost to direct gathers because of the two block barriers, which are gone here.
-// ------------------------------------------------------------------------------------------
-#define EU_WARP_TILE_FLOATS 768   // 3 KB staged footprint per warp, 24 KB per block: 8 blocks per SM
-#define EU_WARP_TILE_ROWS 16
-#define EU_WARP_PATCH_X 8  // the 32 pixels of a warp: an 8 x 4 patch (see below)
-#define EU_WARP_PATCH_Y 4
-
-template <int NCH, int TS, bool TWINE, int DEG, int SP = 0>
-__global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_warp(const __grid_constant__ RenderParams P) {
-  static_assert(DEG == 1 || DEG == 3, "built for the bilinear and cubic evaluators");
-  constexpr int ORDER = DEG + 1, H2 = DEG / 2;
-  constexpr int NWARP = TILE_X * TILE_Y / 32;
-  __shared__ __align__(128) float tiles[NWARP][EU_WARP_TILE_FLOATS];
-  __shared__ __align__(8) uint64_t mbars[NWARP];
-  static_assert(TILE_X == 4 * EU_WARP_PATCH_X && TILE_Y == 2 * EU_WARP_PATCH_Y && EU_WARP_PATCH_X * EU_WARP_PATCH_Y == 32,
-                "a 32x8 tile is 4x2 patches of one warp each");
-
-  SpecView<SP> V(P);
-  const TargetDev& T = V.trg();
-  const FacetDev& F = V.f0();
-  const SourceDev& S = F.src;
-  // the warp's pixels: a PATCH_X x PATCH_Y patch of the tile, lanes row-major inside it. (Nothing on the
-  // single-facet path depends on which pixels share a warp: the zimt-vector semantics of the steppers are
-  // functions of the pixel's own column, first_lane_column.)
-  const int lane = threadIdx.x, wid = threadIdx.y;
-  const int x = blockIdx.x * TILE_X + (wid & 3) * EU_WARP_PATCH_X + (lane % EU_WARP_PATCH_X);
-  const int ytop = P.row0 + blockIdx.y * TILE_Y + (wid >> 2) * EU_WARP_PATCH_Y;
-  const int y = ytop + lane / EU_WARP_PATCH_X;
-  if (ytop >= P.row1 || blockIdx.x * TILE_X + (wid & 3) * EU_WARP_PATCH_X >= T.width) return;  // the whole warp
-  const bool inside = x < T.width && y < P.row1;
-  float* tile = tiles[wid];
-  uint64_t* mbar = &mbars[wid];
-  if (lane == 0) mbar_init(mbar, 1);
-  __syncwarp();
-
-  // ---- phase 1: rays and window origins ------------------------------------------------
-  const int xc = inside ? x : 0, yc = inside ? y : ytop;
-  const int xf = first_lane_column(xc);
-  float2 c0 = __ldg(P.col_tab + xc), r0 = __ldg(P.row_tab + yc);
-  ColTerm col{c0.x, c0.y};
-  RowTerm row{r0.x, r0.y};
-  ColTerm first = col;
-  if (T.projection == EU_CYLINDRICAL && T.normalize) {
-    float2 f0 = __ldg(P.col_tab + xf);
-    first = ColTerm{f0.x, f0.y};
-  }
-  float r00[3];
-  dev_stepper(T, F.xx, F.yy, F.zz, col, row, first, yc, r00);
-  int face;
-  float cx, cy;
-  bool hit = dev_facet_coordinate(F, r00, face, cx, cy) && inside;
-  Located L = dev_locate(S, DEG, hit ? cx : 0.0f, hit ? cy : 0.0f);
-  // window origin in CONTAINER texel coordinates (container rows start 16-byte aligned)
-  const int lox = L.ix - H2 + P.src_lx, loy = L.iy - H2 + P.src_ly;
-  const int mnx = __reduce_min_sync(0xffffffffu, hit ? lox : INT_MAX);
-  const int mxx = __reduce_max_sync(0xffffffffu, hit ? lox : INT_MIN);
-  const int mny = __reduce_min_sync(0xffffffffu, hit ? loy : INT_MAX);
-  const int mxy = __reduce_max_sync(0xffffffffu, hit ? loy : INT_MIN);
-  int a0 = 0, wf = 0, rows = 0, by0 = 0;  // warp-uniform
-  if (mnx <= mxx) {                       // at least one pixel of the warp hits the source
-    int bx0 = mnx, bx1 = mxx, by1 = mxy;
-    by0 = mny;
-    if constexpr (TWINE) {  // sub-rays stray up to half a pixel from the centre ray (a tap outside the box
-                            // gathers from HBM, so the margin decides speed, never the result)
-      const int bw = mxx - mnx + 1, mx = (bw * 5) / 64 + 2, my = 2;
-      bx0 -= mx; bx1 += mx; by0 -= my; by1 += my;
-      bx0 = max(bx0, 0); by0 = max(by0, 0);  // keep the box inside the container
-      bx1 = min(bx1, P.src_cw - ORDER); by1 = min(by1, P.src_ch - ORDER);
-    }
-    a0 = (bx0 * TS) & ~3;  // 16-byte granule within the container row
-    wf = (((bx1 + ORDER) * TS - a0) + 3) & ~3;
-    rows = by1 - by0 + ORDER;
-    if (rows > EU_WARP_TILE_ROWS || rows * wf > EU_WARP_TILE_FLOATS || wf <= 0 || rows <= 0) rows = 0;
-  }
-  const bool staged = rows > 0;
-  if (staged) {
-    if (lane == 0) {  // arm, then one bulk copy per row: all from the thread that initialised the barrier
-      mbar_expect_tx(mbar, (uint32_t)(rows * wf) * 4u);
-      for (int rid = 0; rid < rows; rid++)
-        bulk_row_g2s(tile + rid * wf, P.src_base + (ptrdiff_t)(by0 + rid) * S.stride + a0, (uint32_t)wf * 4u, mbar);
-    }
-    __syncwarp();
-    mbar_wait(mbar, 0);
-  }
-
-  // ---- phase 2: windows ------------------------------------------------------------------
-  if (!inside) return;
-  float px[NCH];
-  if constexpr (!TWINE) {
-    if (!hit) {
-#pragma unroll
-      for (int c = 0; c < NCH; c++) px[c] = 0.0f;
-    } else {
-      if (staged)
-        dev_window_eval<NCH, TS, DEG, true>(tile + (loy - by0) * wf + (lox * TS - a0), wf, DEG, P.wmat, L.fx, L.fy, px);
-      else
-        dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)loy * S.stride + (ptrdiff_t)lox * TS, S.stride, DEG,
-                                             P.wmat, L.fx, L.fy, px);
-      dev_brighten<NCH>(F, px);
-    }
-  } else {
-    // deriv_stepper (stepper.h:1606-1694) + twine_t (twining.h:106-263), as in k_render_tiled
-    float2 c1 = __ldg(P.col_tab + T.width + x), r1 = __ldg(P.row_tab + T.height + y);
-    ColTerm colb{c1.x, c1.y};
-    RowTerm rowb{r1.x, r1.y};
-    ColTerm firstb = colb;
-    if (T.projection == EU_CYLINDRICAL && T.normalize) {
-      float2 f1 = __ldg(P.col_tab + T.width + xf);
-      firstb = ColTerm{f1.x, f1.y};
-    }
-    float du[3], dv[3], help[NCH];
-    dev_stepper(T, F.xx, F.yy, F.zz, colb, row, firstb, y, du);
-    dev_stepper(T, F.xx, F.yy, F.zz, col, rowb, first, y, dv);
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      du[c] = du[c] - r00[c];
-      dv[c] = dv[c] - r00[c];
-    }
-#pragma unroll
-    for (int c = 0; c < NCH; c++) px[c] = 0.0f;
-    const int bx1 = a0 + wf, by1 = by0 + rows;
-    for (int k = 0; k < P.n_taps; k++) {
-      float tx = __ldg(P.taps + 3 * k), ty = __ldg(P.taps + 3 * k + 1), tw = __ldg(P.taps + 3 * k + 2);
-      float r[3];
-#pragma unroll
-      for (int c = 0; c < 3; c++) r[c] = r00[c] + tx * du[c] + ty * dv[c];
-      int fc;
-      float sx, sy;
-      if (!dev_facet_coordinate(F, r, fc, sx, sy)) {
-#pragma unroll
-        for (int c = 0; c < NCH; c++) help[c] = 0.0f;
-      } else {
-        Located K = dev_locate(S, DEG, sx, sy);
-        const int kx = K.ix - H2 + P.src_lx, ky = K.iy - H2 + P.src_ly;
-        const bool in_box = staged && kx * TS >= a0 && (kx + ORDER) * TS <= bx1 && ky >= by0 && ky + ORDER <= by1;
-        if (in_box)
-          dev_window_eval<NCH, TS, DEG, true>(tile + (ky - by0) * wf + (kx * TS - a0), wf, DEG, P.wmat, K.fx, K.fy, help);
-        else
-          dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)ky * S.stride + (ptrdiff_t)kx * TS, S.stride, DEG,
-                                               P.wmat, K.fx, K.fy, help);
-        dev_brighten<NCH>(F, help);
-      }
-#pragma unroll
-      for (int c = 0; c < NCH; c++) px[c] = EU_WIN_MULADD(tw, help[c], px[c]);
-    }
-  }
-  if (T.unbrighten != 1.0f) {
-    constexpr int NCOL = (NCH == 2 || NCH == 4) ? NCH - 1 : NCH;
-#pragma unroll
-    for (int c = 0; c < NCOL; c++) px[c] *= T.unbrighten;
-  }
-  // the patch's rows are runs of PATCH_X pixels: plain per-channel stores (L2 merges the sectors), also into
-  // a peer frame - the 128-bit path of dev_store_pixel needs a warp that is one row
-  float* dst = P.out + (size_t)(y - P.row0) * P.out_pitch + (size_t)x * NCH;
-#pragma unroll
-  for (int c = 0; c < NCH; c++) dst[c] = px[c];
-}
-
 template <int NCH, int TS, int MODE, bool TWINE>
 static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st) {
   if constexpr (MODE == EU_MODE_SINGLE) {
@@ -774,19 +616,7 @@ static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_
     // Measured on B200 (profiles/): it wins for the cubic window (16 taps/px: C2 0.60 vs 0.75 ms)
     // and loses for the bilinear one (4 taps/px: C3b 1.56 vs 1.32 ms), where the two block-wide
     // synchronisations cost more than the gathers they replace - so it is used for degree 3 only.
-    if constexpr (NCH == 3) {  // opt-in: per-warp staging (RGB rasters), also for the bilinear evaluator
-      if (P.use_tiles == 2 && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.any_generic && P.degree == 1) {
-        k_render_warp<NCH, TS, TWINE, 1><<<grid, block, 0, st>>>(P);
-        return;
-      }
-    }
     if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.any_generic && P.degree == 3) {
-      if constexpr (NCH == 3) {
-        if (P.use_tiles == 2) {
-          k_render_warp<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P);
-          return;
-        }
-      }
       k_render_tiled<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P);
       return;
     }
@@ -815,7 +645,7 @@ static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_
 template <int NCH, int TS>
 static cudaError_t launch_render(const RenderParams& P, cudaStream_t st) {
   dim3 block(TILE_X, TILE_Y);
-  dim3 grid((P.trg.width + TILE_X - 1) / TILE_X, (P.row1 - P.row0 + TILE_Y - 1) / TILE_Y);
+  dim3 grid((P.col1 - P.col0 + TILE_X - 1) / TILE_X, (P.row1 - P.row0 + TILE_Y - 1) / TILE_Y);
   bool tw = P.n_taps > 0;
   constexpr bool ALPHA = (NCH == 2 || NCH == 4);
   switch (P.mode) {
@@ -845,3 +675,6 @@ static cudaError_t launch_render(const RenderParams& P, cudaStream_t st) {
   }
   return cudaGetLastError();
 }
+
+}  // namespace EU_ARITH_NS
+using namespace EU_ARITH_NS;

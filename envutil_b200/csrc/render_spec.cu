@@ -11,18 +11,13 @@ inline bool tiles_ok(const RenderParams& P) {
 template <int SP, bool TWINE>
 bool single(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st, bool with_cubic) {
   if (P.degree == 1) {
-    if (P.use_tiles == 2 && P.out && !P.index_out && (P.f0.src.stride & 3) == 0) {  // opt-in variant
-      k_render_warp<3, 3, TWINE, 1, SP><<<grid, block, 0, st>>>(P);
-      return true;
-    }
     k_render<3, 3, EU_MODE_SINGLE, TWINE, 1, false, false, SP><<<grid, block, 0, st>>>(P);
     return true;
   }
   if (P.degree == 3 && with_cubic) {
     if constexpr (!TWINE) {
       if (tiles_ok(P)) {
-        if (P.use_tiles == 2) k_render_warp<3, 3, false, 3, SP><<<grid, block, 0, st>>>(P);  // opt-in variant
-        else k_render_tiled<3, 3, false, 3, SP><<<grid, block, 0, st>>>(P);
+        k_render_tiled<3, 3, false, 3, SP><<<grid, block, 0, st>>>(P);
         return true;
       }
     }
@@ -34,10 +29,10 @@ bool single(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st, bool 
 }  // namespace
 
 // true: a kernel was launched (check cudaGetLastError); false: no compiled-in shape fits the job
-bool eu_launch_render_spec(const RenderParams& P, cudaStream_t st) {
+bool EU_ARITH_FN(eu_launch_render_spec)(const RenderParams& P, cudaStream_t st) {
   if (P.spec <= 0 || P.spec >= EU_N_SPECS || P.nch != 3 || P.tstride != 3 || P.any_generic) return false;
   dim3 block(TILE_X, TILE_Y);
-  dim3 grid((P.trg.width + TILE_X - 1) / TILE_X, (P.row1 - P.row0 + TILE_Y - 1) / TILE_Y);
+  dim3 grid((P.col1 - P.col0 + TILE_X - 1) / TILE_X, (P.row1 - P.row0 + TILE_Y - 1) / TILE_Y);
   const bool tw = P.n_taps > 0;
   if (P.mode == EU_MODE_SINGLE) {
     switch (P.spec) {
@@ -59,15 +54,4 @@ bool eu_launch_render_spec(const RenderParams& P, cudaStream_t st) {
     return true;
   }
   return false;
-}
-
-// Which arithmetic the render kernels of this library were compiled with (include/envutil_b200.h):
-// 0 = every product and sum rounded separately (bit-identical to the reference's parity build),
-// 1 = fused multiply-adds in the window evaluation and the twining accumulation (eu_device.cuh)
-extern "C" int eu_render_arithmetic(void) {
-#ifdef EU_CONTRACT_WINDOW
-  return 1;
-#else
-  return 0;
-#endif
 }

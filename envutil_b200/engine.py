@@ -82,6 +82,14 @@ class Engine:
             self.last_timing = tm
         return tm
 
+    def render_rect_pitched(self, job, sources, structs, row0, row1, col0, col1, d_out, pitch_floats, stream=0):
+        """Columns [col0, col1) of rows [row0, row1) (col0 a multiple of 32); d_out = address of row0, column 0."""
+        t, fa, o, taps, ntaps = structs
+        capi.check(self.lib.eu_render_rect_pitched(C.byref(t), C.byref(o), len(job.facets), fa, sources, taps, ntaps,
+                                                   row0, row1, col0, col1, C.c_void_p(d_out), pitch_floats,
+                                                   C.c_void_p(stream), None), self.lib)
+        self.launches += 1
+
     def commit(self, handle, facet_struct, opts, stream=0):
         tm = capi.Timing()
         capi.check(self.lib.eu_source_commit(handle, C.byref(facet_struct), C.byref(opts), C.c_void_p(stream), C.byref(tm)),
@@ -142,11 +150,15 @@ class Engine:
         t, fa, o, taps, ntaps = structs
         n = len(job.facets)
         hs = (capi.SourceH * n)()
-        for i in range(n):
-            h = capi.SourceH()
-            capi.check(self.lib.eu_source_upload_async(None, C.byref(fa[i]), C.byref(o), C.c_void_p(pinned_pixels[i]),
-                                                       C.byref(h)), self.lib)
-            hs[i] = h
+        try:
+            for i in range(n):
+                h = capi.SourceH()
+                capi.check(self.lib.eu_source_upload_async(None, C.byref(fa[i]), C.byref(o), C.c_void_p(pinned_pixels[i]),
+                                                           C.byref(h)), self.lib)
+                hs[i] = h
+        except RuntimeError:  # the handles staged so far go back
+            self.release(hs)
+            raise
         jh = C.c_void_p()
         try:
             capi.check(self.lib.eu_render_async(C.byref(t), C.byref(o), n, fa, hs, taps, ntaps, C.c_void_p(pinned_out),
@@ -163,6 +175,21 @@ class Engine:
         self.release(hs)
         self.launches += tm.launches
         return tm
+
+    def tie_plane(self, job, sources, structs, ulps=8):
+        """H x W uint8: 1 where the cube-face / winning-facet choice is within `ulps` of flipping
+        (eu_debug_tie_plane); None for jobs without such a choice."""
+        t, fa, o, taps, ntaps = structs
+        single = len(job.facets) == 1 or o.solo >= 0
+        if single and job.facets[max(o.solo, 0)].projection not in ("cubemap", "biatan6"):
+            return None
+        if not single and o.synopsis != capi.SYN_PANORAMA:
+            return None
+        tie = np.empty(t.out_shape(), dtype=np.uint8)
+        capi.check(self.lib.eu_debug_tie_plane(C.byref(t), C.byref(o), len(job.facets), fa, sources, ulps,
+                                               tie.ctypes.data), self.lib)
+        self.launches += 1
+        return tie
 
     def index_plane(self, job, sources=None, structs=None):
         st = structs or job.structs(self.lib)

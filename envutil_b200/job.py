@@ -111,7 +111,8 @@ class Job:
     no_tiles: bool = False  # back-end option: never stage gather footprints in shared memory (reserved[1] bit 0)
     narrow_stores: bool = False  # back-end option: 4-byte pixel stores even into peer frames (reserved[1] bit 2)
     no_spec: bool = False   # back-end option: never use the kernels compiled for one job shape (reserved[1] bit 1)
-    warp_tiles: bool = False  # back-end option (experimental): footprint staging per warp, not per block (bit 3)
+    contracted: Optional[bool] = None  # arithmetic of the render kernels: fused multiply-adds in the window evaluation
+                                       # (EU_OPT_CONTRACTED); None = what EU_ARITHMETIC says (default: exact)
     name: str = ""
 
     # ---- reference command line (real spellings, envutil_main.cc:190-372) ----
@@ -265,8 +266,9 @@ class Job:
         o.solo = 0 if n == 1 else self.solo  # forced for a single facet (envutil_main.cc:996-997)
         o.support_min, o.tile_size = self.support_min, self.tile_size
         o.reserved[0] = 1 if self.padded else 0
-        o.reserved[1] = (1 if self.no_tiles else 0) | (2 if self.no_spec else 0) | (4 if self.narrow_stores else 0) | \
-            (8 if self.warp_tiles else 0)
+        contracted = capi.ARITHMETIC == "contracted" if self.contracted is None else self.contracted
+        o.reserved[1] = (capi.OPT_NO_TILES if self.no_tiles else 0) | (capi.OPT_NO_SHAPES if self.no_spec else 0) | \
+            (capi.OPT_NARROW_STORES if self.narrow_stores else 0) | (capi.OPT_CONTRACTED if contracted else 0)
         taps = (capi.Tap * 1024)()
         tw = C.c_int(0)
         ntaps = lib.eu_make_spread(C.byref(t), C.byref(o), n, fa, self.twine, self.twine_width, self.twine_density,

@@ -110,11 +110,19 @@ typedef struct eu_opts {
   int32_t solo;             /* -1, or the single facet to show; forced to 0 for one facet */
   int32_t support_min;      /* cubemap IR support, default 8  (envutil_main.cc:458) */
   int32_t tile_size;        /* cubemap IR tile size, default 64 (envutil_main.cc:457) */
-  int32_t reserved[2];      /* back-end options, 0 = defaults. [0] 1: 16-byte RGB texels in HBM; [1] bit 0: no
-                               shared-memory footprint staging, bit 1: no kernels compiled for one job shape, bit 2: no 128-bit
-                               pixel stores into peer frames, bit 3: footprint staging per warp instead of per block
-                               (bilinear and cubic single-facet RGB jobs; experimental) */
+  int32_t reserved[2];      /* back-end options, 0 = defaults. [0] 1: 16-byte RGB texels in HBM; [1]: EU_OPT_* bits */
 } eu_opts_t;
+/* eu_opts_t.reserved[1] */
+#define EU_OPT_NO_TILES 1      /* never stage the gather footprint in shared memory */
+#define EU_OPT_NO_SHAPES 2     /* never use the kernels compiled for one job shape */
+#define EU_OPT_NARROW_STORES 4 /* no 128-bit pixel stores into peer frames */
+/* Arithmetic of the render kernels. Default (bit clear): no contraction anywhere - every product and sum is rounded
+ * separately, the output is bit-identical to the reference built with -ffp-contract=off. With EU_OPT_CONTRACTED the
+ * b-spline weights, the window sum (zimt/eval.h:903-1059) and the twining accumulation (twining.h:106-263) use fused
+ * multiply-adds, as a reference built with g++'s default -ffp-contract=fast on FMA hardware does. Rays, source
+ * coordinates, gates, window positions, face and facet indices are the same bits either way; pixel values move by a few
+ * ulp (measured against the pinned reference build at BASELINE's full sizes: profiles/). */
+#define EU_OPT_CONTRACTED 16
 
 /* One twining tap: sub-pixel offset in units of the target's pixel step and weight
  * (args.twine_spread, reference envutil_main.cc:1253-1355; consumed at twining.h:106-121). */
@@ -189,11 +197,8 @@ int eu_init(int device_id);
 void eu_shutdown(void);
 const char* eu_last_error(void);
 int eu_device_count(void);
-/* Arithmetic of the render kernels in this build of the library. 0 (libenvutil_b200.so, the default):
- * no contraction anywhere, output bit-identical to the reference built with -ffp-contract=off. 1
- * (libenvutil_b200_fma.so, opt-in): the b-spline window evaluation (zimt/eval.h:903-1059) and the
- * twining accumulation (twining.h:106-263) use fused multiply-adds, as a reference built with
- * g++'s default -ffp-contract=fast on FMA hardware does; coordinates and indices are unchanged. */
+/* Number of arithmetics the render kernels are built in: 2 (exact and contracted, selected per job by
+ * EU_OPT_CONTRACTED in eu_opts_t.reserved[1]). */
 int eu_render_arithmetic(void);
 
 /* Stage one source raster: upload, place into the braced container (lat/lon & mounted
@@ -238,6 +243,13 @@ int eu_render_rows_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facet
                            const eu_facet_t* facets, const eu_source_h* sources, const eu_tap_t* taps,
                            int n_taps, int row0, int row1, float* d_out, int out_pitch_floats,
                            void* cuda_stream, eu_timing_t* timing);
+/* same, restricted to the columns [col0, col1) of those rows (col0 a multiple of 32): d_out still points at the
+ * first float of row `row0`, column 0. Pipelines that need only part of an intermediate raster (BASELINE
+ * configs[4]: stage B samples a curved region of every merged image) render just the rectangles that cover it. */
+int eu_render_rect_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facets,
+                           const eu_facet_t* facets, const eu_source_h* sources, const eu_tap_t* taps,
+                           int n_taps, int row0, int row1, int col0, int col1, float* d_out,
+                           int out_pitch_floats, void* cuda_stream, eu_timing_t* timing);
 /* A source whose raster is produced on the device: two-stage jobs (BASELINE configs[4]: hdr_merge
  * of a position's brackets, then the panorama over the merged images) hand the first stage's result
  * to the second without an intermediate raster and without the placement copy of
@@ -284,6 +296,14 @@ int eu_frame_close(float* d_frame);
  * facet) or the winning facet of the panorama synopsis (-1: no facet hit). Host buffer w*h. */
 int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets,
                     const eu_facet_t* facets, const eu_source_h* sources, int32_t* index_out);
+
+/* The tie band of the same job ("indices bit-exact except within a tie band ... mask those pixels,
+ * report their count"): per target pixel 1 where the cube-face choice (ray_to_cubeface, geometry.h:1178-1289:
+ * the two largest |components| of the ray) or the winning facet (_voronoi_syn, envutil_payload.cc:818-956: the
+ * two best z * recip_step scores) is within `ulps` units in the last place of flipping, else 0. A build of the
+ * reference with another math library may choose the other face / facet exactly there. Host buffer w*h bytes. */
+int eu_debug_tie_plane(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+                       const eu_source_h* sources, int ulps, unsigned char* tie_out);
 
 #ifdef __cplusplus
 }

@@ -1,13 +1,12 @@
-"""The opt-in arithmetic variant (libenvutil_b200_fma.so, EU_ARITHMETIC=contracted; include/envutil_b200.h
-eu_render_arithmetic): fused multiply-adds in the b-spline window evaluation and the twining accumulation,
-nothing else. The default library stays bit-identical to the reference's parity build; this variant is what
-a reference compiled with g++'s default -ffp-contract=fast on FMA hardware resembles, and it has to stay
-within BASELINE.json's tolerance (1e-5 relative) of the pinned reference.
+"""The contracted arithmetic (EU_OPT_CONTRACTED in eu_opts_t.reserved[1], include/envutil_b200.h): fused
+multiply-adds in the b-spline window evaluation and the twining accumulation, nothing else. The default arithmetic
+stays bit-identical to the reference's parity build; this one is what a reference compiled with g++'s default
+-ffp-contract=fast on FMA hardware resembles, and it has to stay within BASELINE.json's tolerance (1e-5 relative)
+of the pinned reference. Both sets of kernels live in the one library.
 
-CPU: the library variant loads and names its arithmetic; the oracle's restatement of the variant
-(orc_set_arithmetic) keeps every index plane and differs from the pinned arithmetic by at most 2.6e-6
-relative (hdr_merge's near-zero denominators: 1.6e-5), RMS <= 2.7e-7, over all 98 small jobs.
-GPU (opt-in, no GPU run has seen it yet): the contracted kernels equal the contracted oracle bit for bit.
+CPU: the oracle's restatement of the variant (orc_set_arithmetic) keeps every index plane and differs from the
+pinned arithmetic by at most 2.6e-6 relative (hdr_merge's near-zero denominators: 1.6e-5), RMS <= 2.7e-7, over all
+98 small jobs. GPU: the contracted kernels equal the contracted oracle bit for bit on every small job.
 """
 import os
 import subprocess
@@ -33,22 +32,26 @@ def _run(code, env_extra):
     return subprocess.run([sys.executable, "-c", pre + code], capture_output=True, text=True, env=env, timeout=600)
 
 
-def test_library_variants_name_their_arithmetic(lib):
-    """Both builds export the whole C ABI (capi.load checks every symbol) and say which arithmetic their
-    render kernels use; the loader refuses a library that is not what its name says."""
-    assert lib.eu_render_arithmetic() == 0
-    r = _run("import os\nfrom envutil_b200 import capi\nlib = capi.load()\n"
-             "print(capi.ARITHMETIC, os.path.basename(capi.LIB_PATH), lib.eu_render_arithmetic())\n",
+def test_library_carries_both_arithmetics(lib):
+    """One library, two sets of render kernels; Job.contracted / EU_ARITHMETIC=contracted set the option bit."""
+    assert lib.eu_render_arithmetic() == 2
+    import copy
+    job = copy.copy(jobs.JOBS["ll_rect_d3_rot"])
+    assert job.structs(lib)[2].reserved[1] == 0
+    job.contracted = True
+    assert job.structs(lib)[2].reserved[1] == 16
+    r = _run("import jobs\nfrom envutil_b200 import capi\n"
+             "print(capi.ARITHMETIC, jobs.JOBS['ll_rect_d3_rot'].structs()[2].reserved[1])\n",
              {"EU_ARITHMETIC": "contracted"})
     assert r.returncode == 0, r.stderr[-1500:]
-    assert r.stdout.split() == ["contracted", "libenvutil_b200_fma.so", "1"]
+    assert r.stdout.split() == ["contracted", "16"]
 
 
 def test_variants_share_everything_but_the_render_kernels():
-    """Staging, API and host set-up are the same objects in both libraries (so a staged source has the same
-    bits in both); only the render translation units are compiled twice."""
+    """Staging, API and host set-up are compiled once (so a staged source has the same bits for both arithmetics);
+    only the render translation units are compiled twice."""
     import __graft_entry__ as g
-    assert set(g.FMA_SOURCES) == {s for s in g.CUDA_SOURCES if s.startswith("render_")}
+    assert set(g.FMA_SOURCES) == {s for s in g.CUDA_SOURCES if s.startswith("render_") and s != "render_tie.cu"}
     assert "stage.cu" not in g.FMA_SOURCES and "api.cu" not in g.FMA_SOURCES and "render.cu" not in g.FMA_SOURCES
 
 
@@ -76,31 +79,23 @@ def test_contracted_arithmetic_differs_where_it_should():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("EU_GPU_UNTRIED") != "1",
-                    reason="no GPU run has seen this build yet: opt in with EU_GPU_UNTRIED=1 (tools/gpu_first_call.sh does)")
-def test_contracted_kernels_equal_contracted_oracle():
-    """All small jobs through libenvutil_b200_fma.so in ONE separate process (the library is a process-wide
-    singleton): bit-identical to the oracle's restatement of the variant, within tolerance of the pinned one."""
-    code = ("import numpy as np, harness, jobs\n"
-            "from envutil_b200 import capi\n"
-            "from envutil_b200.engine import Engine\n"
-            "assert capi.load().eu_render_arithmetic() == 1\n"
-            "eng = Engine(0)\n"
-            "bad = 0; worst = 0.0\n"
-            "for name in sorted(jobs.JOBS):\n"
-            "    job = jobs.JOBS[name]\n"
-            "    out = eng.render(job)\n"
-            "    c = harness.compare(out, harness.oracle_render(job, contracted=True))\n"
-            "    e = harness.compare(out, harness.oracle_render(job))\n"
-            "    worst = max(worst, e['max_rel'])\n"
-            "    if c['n_diff'] or e['max_rel'] > (5e-5 if 'hdr' in name else 1e-5):\n"
-            "        bad += 1; print(name, c, e, flush=True)\n"
-            "print('worst max_rel vs the pinned arithmetic', worst)\n"
-            "eng.close()\n"
-            "sys.exit(3 if bad else 0)\n")
-    r = _run(code, {"EU_ARITHMETIC": "contracted"})
-    print(r.stdout)
-    assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-1500:]
+def test_contracted_kernels_equal_contracted_oracle(engine):
+    """Every small job with EU_OPT_CONTRACTED: bit-identical to the oracle's restatement of the variant, within
+    tolerance of the pinned arithmetic, and the option does not leak into the next (exact) job."""
+    import copy
+    worst = 0.0
+    for name in sorted(jobs.JOBS):
+        job = copy.copy(jobs.JOBS[name])
+        job.contracted = True
+        out = engine.render(job)
+        c = harness.compare(out, harness.oracle_render(job, contracted=True))
+        e = harness.compare(out, harness.oracle_render(job))
+        worst = max(worst, e["max_rel"])
+        assert c["n_diff"] == 0, (name, c)
+        assert e["max_rel"] <= (5e-5 if "hdr" in name else 1e-5), (name, e)
+    print("worst max_rel vs the pinned arithmetic", worst)
+    job = jobs.JOBS["ll_rect_d3_rot"]
+    assert harness.compare(engine.render(job), harness.oracle_render(job))["n_diff"] == 0
 
 
 def test_contracted_oracle_is_pinned_to_itself():

@@ -290,14 +290,11 @@ def test_stage_one_renders_into_stage_two_source(engine, degree):
         engine.release(hsa)
 
 
-@pytest.mark.skipif(os.environ.get("EU_GPU_UNTRIED") != "1",
-                    reason="sizes no GPU run has seen yet: opt in with EU_GPU_UNTRIED=1 (tools/gpu_first_call.sh does)")
-@pytest.mark.xfail(strict=False, reason="added without a GPU run at hand; promote to must-pass once seen green")
 def test_edge_jobs():
-    """Degenerate sizes (one-pixel and ragged targets, sources smaller than a spline window, 4-px cube
-    faces): the oracle equals the reference on them (golden); the kernels should equal the oracle, or the
-    library should refuse the job. All of them run in ONE separate process with a two-minute limit, so
-    that a device fault or a hang on an untried size cannot reach the other tests."""
+    """Degenerate sizes (one-pixel and ragged targets, sources smaller than a spline window, single rows and
+    columns, 4-px cube faces): the oracle equals the reference on them (golden); the kernels equal the oracle,
+    or the library refuses the job. All of them run in ONE separate process with a two-minute limit, so
+    that a device fault on such a size cannot reach the other tests."""
     import subprocess
     import sys
     code = ("import sys; sys.path[:0] = [%r, %r]\n"
@@ -322,55 +319,49 @@ def test_edge_jobs():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1500:]
 
 
-@pytest.mark.skipif(os.environ.get("EU_GPU_UNTRIED") != "1",
-                    reason="a kernel no GPU run has seen yet: opt in with EU_GPU_UNTRIED=1 (tools/gpu_first_call.sh does)")
-def test_warp_staged_kernel_is_bit_exact():
-    """k_render_warp (eu_opts_t.reserved[1] bit 3: the gather footprint staged per warp instead of per block):
-    every bilinear or cubic RGB single-facet job, with and without twining, general and shape-compiled builds, 12- and 16-byte texels,
-    plus a C2-shaped job large enough for full tiles. One separate process with a four-minute limit - the kernel
-    waits on an mbarrier, and a mistake there would hang rather than fail."""
-    import subprocess
-    import sys
-    code = ("import sys; sys.path[:0] = [%r, %r]\n"
-            "import copy\n"
-            "import harness, jobs\n"
-            "from envutil_b200 import synth\n"
-            "from envutil_b200.engine import Engine\n"
-            "from envutil_b200.job import FacetSpec, Job\n"
-            "eng = Engine(0)\n"
-            "todo = {n: j for n, j in jobs.JOBS.items() if j.degree in (1, 3) and len(j.facets) == 1\n"
-            "        and j.facets[0].image.shape[-1] == 3}\n"
-            "todo['c2_small'] = Job([FacetSpec(synth.cubemap(256), 'cubemap', 90.0)], 'spherical', 360.0, 1024, 512, degree=3)\n"
-            "todo['ll_rect_big'] = Job([FacetSpec(synth.latlon(1024), 'spherical', 360.0)], 'rectilinear', 80.0, 640, 360,\n"
-            "                          degree=3, yaw=40.0, pitch=-70.0, roll=25.0)\n"
-            "bad = 0\n"
-            "for name in sorted(todo):\n"
-            "    ref = harness.oracle_render(todo[name])\n"
-            "    for no_spec in (False, True):\n"
-            "        for padded in (False, True):\n"
-            "            job = copy.copy(todo[name])\n"
-            "            job.warp_tiles, job.no_spec, job.padded = True, no_spec, padded\n"
-            "            c = harness.compare(eng.render(job), ref)\n"
-            "            print(name, no_spec, padded, c['n_diff'], flush=True)\n"
-            "            bad += c['n_diff'] != 0\n"
-            "print('jobs', len(todo))\n"
-            "# row bands with edges that are no multiples of the 4-row patch (eu_render_rows, the multi-GPU unit)\n"
-            "import numpy as np, torch\n"
-            "job = copy.copy(todo['c2_small']); job.warp_tiles = True\n"
-            "st = job.structs(); t = st[0]\n"
-            "hs = eng.stage(job, st)\n"
-            "buf = torch.zeros((t.height, t.width, t.nchannels), dtype=torch.float32, device='cuda:0')\n"
-            "edges = [0, 7, 40, 41, 203, t.height]\n"
-            "stream = torch.cuda.current_stream().cuda_stream\n"
-            "for r0, r1 in zip(edges[:-1], edges[1:]):\n"
-            "    eng.render_rows(job, hs, st, r0, r1, buf[r0].data_ptr(), stream)\n"
-            "torch.cuda.synchronize()\n"
-            "same = np.array_equal(buf.cpu().numpy(), harness.oracle_render(todo['c2_small']))\n"
-            "print('bands', same, flush=True)\n"
-            "eng.release(hs)\n"
-            "bad += not same\n"
-            "sys.exit(3 if bad else 0)\n"
-            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))))
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
-    print(r.stdout)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1500:]
+def _rects(h, w):
+    """A partition of an h x w raster into rectangles whose column edges are multiples of 32 and whose row edges
+    are not multiples of the 8-row tile."""
+    cols = sorted({0, w} | {c for c in (32, 96, 32 * ((w // 2) // 32 + 1)) if 0 < c < w})
+    rows = sorted({0, h} | {r for r in (5, 13, h // 2 + 3) if 0 < r < h})
+    return [(r0, r1, c0, c1) for r0, r1 in zip(rows[:-1], rows[1:]) for c0, c1 in zip(cols[:-1], cols[1:])]
+
+
+@pytest.mark.parametrize("name", ["cm_sph_d3", "ll_rect_d1", "ll_fish_d1_tw4", "voronoi4_sph_d3_rot", "hdr3_rect_d1",
+                                  "rgba4_voronoi_sph_d3", "tr1_sph_d1"])
+def test_rectangles_assemble_the_frame(engine, name):
+    """eu_render_rect_pitched (rows x columns, the unit of pipelines that need only part of an intermediate
+    raster): a frame rendered rectangle by rectangle equals the oracle's frame bit for bit - footprint-staged
+    cubic kernel, direct kernels, twining, the synopses (voronoi_plus votes per 16-lane vector), the generic stepper."""
+    import torch
+    job = jobs.JOBS[name]
+    st = job.structs()
+    t = st[0]
+    h, w = t.out_shape()
+    hs = engine.stage(job, st)
+    try:
+        buf = torch.full((h, w, t.nchannels), -7.0, dtype=torch.float32, device="cuda:0")
+        stream = torch.cuda.current_stream().cuda_stream
+        for r0, r1, c0, c1 in _rects(h, w):
+            engine.render_rect_pitched(job, hs, st, r0, r1, c0, c1, buf[r0].data_ptr(), w * t.nchannels, stream)
+        torch.cuda.synchronize()
+        got = buf.cpu().numpy()
+    finally:
+        engine.release(hs)
+    assert harness.compare(got, harness.oracle_render(job))["n_diff"] == 0
+
+
+def test_rectangle_arguments_are_checked(engine):
+    job = jobs.JOBS["ll_rect_d1"]
+    st = job.structs()
+    hs = engine.stage(job, st)
+    try:
+        import torch
+        t = st[0]
+        buf = torch.zeros((t.height, t.width, t.nchannels), dtype=torch.float32, device="cuda:0")
+        for bad in ((0, 4, 16, 64), (0, 4, 0, t.width + 1), (0, 4, 64, 64), (4, 4, 0, 32)):
+            with pytest.raises(RuntimeError):
+                engine.render_rect_pitched(job, hs, st, bad[0], bad[1], bad[2], bad[3], buf.data_ptr(),
+                                           t.width * t.nchannels, 0)
+    finally:
+        engine.release(hs)

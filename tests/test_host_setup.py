@@ -186,7 +186,7 @@ def test_backend_option_bits(lib):
     o = job.structs(lib)[2]
     assert (o.reserved[0], o.reserved[1]) == (0, 0)
     for field, word, bit in (("padded", 0, 1), ("no_tiles", 1, 1), ("no_spec", 1, 2), ("narrow_stores", 1, 4),
-                             ("warp_tiles", 1, 8)):
+                             ("contracted", 1, 16)):
         j = copy.copy(job)
         setattr(j, field, True)
         o = j.structs(lib)[2]

@@ -36,7 +36,7 @@ def run(eng, job, alg, steps, padded, keep_output=False, flush=None):
         padded = padded[-1]
     job.padded = bool(padded & 1)
     job.no_tiles = bool(padded & 2)
-    job.warp_tiles = bool(padded & 4)
+    job.contracted = bool(padded & 8)
     st = job.structs(eng.lib)
     t = st[0]
     hs = eng.stage(job, st)
@@ -78,7 +78,7 @@ def run(eng, job, alg, steps, padded, keep_output=False, flush=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="C1,C2,C3a,C3b,C4")
-    ap.add_argument("--padded", default="0", help="comma list of variants: bit 0 = 16-byte texels, bit 1 = direct-gather kernel (no staging), bit 2 = per-warp staging (k_render_warp, experimental)")
+    ap.add_argument("--padded", default="0", help="comma list of variants: bit 0 = 16-byte texels, bit 1 = direct-gather kernel (no staging), bit 3 = contracted arithmetic (EU_OPT_CONTRACTED)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--scale", type=int, default=1)
     a = ap.parse_args()

@@ -1,8 +1,7 @@
 #!/usr/bin/env python3
 """The same random jobs as tools/fuzz_oracle_vs_reference.py, through the CUDA path and the oracle, compared
 bit for bit (runs on a B200 box; the oracle is the checker). Jobs the library refuses (EU_ERR_UNSUPPORTED /
-EU_ERR_ARGUMENT) are counted, not compared. Written at the end of round 1, when no GPU time was left: the
-first thing to run in the next round.
+EU_ERR_ARGUMENT) are counted, not compared. First run on a B200 at the start of round 2 (profiles/r02a_parity_summary.txt).
 
   python tools/fuzz_gpu_vs_oracle.py [--n 500] [--seed 11]
 """
@@ -26,15 +25,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=500)
     ap.add_argument("--seed", type=int, default=11)
-    ap.add_argument("--warp-tiles", type=int, default=0,
-                    help="1: ask for the per-warp staging kernel (k_render_warp) wherever a job is eligible for it")
+    ap.add_argument("--contracted", type=int, default=0,
+                    help="1: the contracted arithmetic (EU_OPT_CONTRACTED) against the oracle's restatement of it")
     a = ap.parse_args()
     rng = np.random.default_rng(a.seed)
     eng = Engine(0)
     same = diff = refused = known = 0
     for k in range(a.n):
         job = random_job(rng)
-        job.warp_tiles = bool(a.warp_tiles)
+        job.contracted = bool(a.contracted)
         desc = "%s<-%s d%d tw%d %dx%d" % (job.projection, "+".join("%s%dx%d" % ((f.projection,) + f.native_shape()[:2])
                                                                     for f in job.facets), job.degree, job.twine,
                                           job.width, job.height)
@@ -46,7 +45,7 @@ def main():
                 print("#%d LIBRARY ERROR %s: %s" % (k, desc, str(e)[:160]), flush=True)
             continue
         try:
-            ref = harness.oracle_render(job)
+            ref = harness.oracle_render(job, contracted=bool(a.contracted))
         except Exception as e:
             print("#%d ORACLE ERROR %s: %s" % (k, desc, str(e)[:120]), flush=True)
             continue
