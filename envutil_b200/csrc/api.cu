@@ -40,6 +40,7 @@ struct eu_source {
   long last_used_cycle;
   int refs;
   bool foreign_use;  // rendered from on a caller's stream: release has to synchronise the device
+  bool reserved = false;  // container handed out by eu_source_reserve (eu_source_write_rect / eu_source_commit)
 };
 
 namespace {
@@ -184,8 +185,8 @@ void source_dev(const eu_source* s, SourceDev& d) {
   d.nch = s->nch;
   d.w = s->w;
   d.h = s->h;
-  d.bc0 = s->bc0;
-  d.bc1 = s->bc1;
+  d.bc0 = s->w == 1 ? EU_BC_CONST0 : s->bc0;  // zimt gates an axis of extent 1 as CONSTANT (zimt/eval.h:2060-2068)
+  d.bc1 = s->h == 1 ? EU_BC_CONST0 : s->bc1;
   // limits of the safe evaluator's gates: -0.5 .. N-0.5 (zimt/bspline.h:233-286)
   d.upper_x = (float)((long double)(s->w - 1) + 0.5L);
   d.upper_y = (float)((long double)(s->h - 1) + 0.5L);
@@ -493,6 +494,8 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   if (n_taps > 0 && !taps) return fail(EU_ERR_ARGUMENT, "taps missing");
   if (t->width <= 0 || t->height <= 0) return fail(EU_ERR_ARGUMENT, "target not prepared");
   if (t->crop_width > 0) {
+    // unreachable through the reference's surface: a crop comes from a PTO p-line, whose projection codes
+    // (envutil_main.cc:590-611) do not include cubemaps
     if (t->projection == EU_CUBEMAP || t->projection == EU_BIATAN6)
       return fail(EU_ERR_UNSUPPORTED, "cropped output of a cubemap target");
     if (t->crop_height <= 0 || t->crop_x0 < 0 || t->crop_y0 < 0 || t->crop_x0 + t->crop_width > t->width ||
@@ -509,8 +512,6 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     if (sources[i]->degree != o->spline_degree)
       return fail(EU_ERR_ARGUMENT, "source %d was staged for degree %d, job asks for %d", i, sources[i]->degree,
                   o->spline_degree);
-    if (facets[i].has_translation && (t->projection == EU_CUBEMAP || t->projection == EU_BIATAN6))
-      return fail(EU_ERR_UNSUPPORTED, "facet %d: PanoTools translation with a cubemap target is not built", i);
     sources[i]->last_used_cycle = g.cycle;
   }
   RenderParams& P = plan.P;
@@ -759,7 +760,10 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
     // allocate, clear and fill on the copy stream: an asynchronous upload does not wait for the
     // staging stream (which may still be busy with the previous job), only the other way round
     CK(pool_alloc(&s->container, n, cpst));
-    CK(cudaMemsetAsync(s->container, 0, n * sizeof(float), cpst));
+    // even face widths: the placement copies write every face texel and the support fill every frame texel
+    // before anything reads it, so the container need not be cleared (321 MB at C2's size). Odd widths: the
+    // fill reads frame texels it has not written yet (stage.cu, k_cm_fill_ordered) - zero, as in the reference.
+    if ((Fpx & 1) || L == 0 || R == 0) CK(cudaMemsetAsync(s->container, 0, n * sizeof(float), cpst));
     CK(cudaEventRecord(g.ev[2], cpst));  // start of the placement copies (timing of the blocking upload)
     for (int face = 0; face < 6; face++)
       CK(cudaMemcpy2DAsync(s->container + (size_t)(face * S + L) * pitch + (size_t)L * nch, (size_t)pitch * sizeof(float),
@@ -778,10 +782,6 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
     return EU_OK;
   }
   mount_layout(f, degree, s);
-  // zimt's bracer folds repeatedly when a brace is wider than the raster (a 2-px image under a quintic
-  // spline); that is not restated (found by the randomised sweep against the reference)
-  if (s->lx > s->w || s->rx > s->w || s->ly > s->h || s->ry > s->h)
-    return fail(EU_ERR_UNSUPPORTED, "a %dx%d raster is smaller than the brace of a degree-%d spline", s->w, s->h, degree);
   size_t n = (size_t)s->pitch * s->chh;
   CK(pool_alloc(&s->container, n, cpst));
   int stride = s->pitch;
@@ -897,12 +897,8 @@ void eu_shutdown(void) {
   g = Context();
 }
 
-static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
-                         cudaMemcpyKind kind, cudaStream_t caller, eu_source_h* out, eu_timing_t* t,
-                         bool async = false) {
-  int rc = need_up();
-  if (rc) return rc;
-  if (!f || !o || !pixels || !out) return fail(EU_ERR_ARGUMENT, "null argument");
+// what every entry point that stages a raster demands of its description (eu_source_upload*, eu_source_reserve)
+static int check_raster(const eu_facet_t* f, const eu_opts_t* o) {
   if (f->width <= 0 || f->height <= 0 || f->nchannels < 1 || f->nchannels > 4)
     return fail(EU_ERR_ARGUMENT, "bad raster description %dx%dx%d", f->width, f->height, f->nchannels);
   if (o->spline_degree < 0 || o->spline_degree > EU_MAX_DEGREE)
@@ -914,12 +910,17 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
   if ((f->projection == EU_CUBEMAP || f->projection == EU_BIATAN6) &&
       (f->window_width != f->width || f->window_height != f->height))
     return fail(EU_ERR_ARGUMENT, "cubemaps cannot be windowed");
-  // zimt degrades an axis of extent 1 to the CONSTANT boundary condition with a clamp-to-zero gate
-  // (zimt/eval.h:2060-2064); the kernels do not restate that special case yet (it was found by comparing
-  // the oracle with the reference on 2x1 and 4x1 rasters), so such rasters are refused rather than
-  // rendered differently
-  if (f->window_width == 1 || f->window_height == 1)
-    return fail(EU_ERR_UNSUPPORTED, "rasters with a single row or column are not supported");
+  return EU_OK;
+}
+
+static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, const float* pixels,
+                         cudaMemcpyKind kind, cudaStream_t caller, eu_source_h* out, eu_timing_t* t,
+                         bool async = false) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!f || !o || !pixels || !out) return fail(EU_ERR_ARGUMENT, "null argument");
+  rc = check_raster(f, o);
+  if (rc) return rc;
   cudaStream_t st = g.stream;
   if (kind == cudaMemcpyDeviceToDevice) {  // order our stream after the caller's work on the raster
     CK(cudaEventRecord(g.ev[2], caller));
@@ -930,6 +931,7 @@ static int upload_common(const char* asset_key, const eu_facet_t* f, const eu_op
     eu_source* s;
     ~Guard() {
       if (s) {
+        cudaStreamSynchronize(g.up_stream);  // placement copies of a failed upload may still be in flight
         pool_free(s->container);
         delete s;
       }
@@ -1334,9 +1336,8 @@ int eu_source_reserve(const char* asset_key, const eu_facet_t* f, const eu_opts_
   if (!f || !o || !out || !d_core || !pitch_floats) return fail(EU_ERR_ARGUMENT, "null argument");
   if (f->projection == EU_CUBEMAP || f->projection == EU_BIATAN6)
     return fail(EU_ERR_UNSUPPORTED, "eu_source_reserve is for single images (a cubemap's faces are re-arranged on upload)");
-  if (f->width <= 0 || f->height <= 0 || f->nchannels < 1 || f->nchannels > 4 || f->window_width <= 0 || f->window_height <= 0)
-    return fail(EU_ERR_ARGUMENT, "bad raster description (run eu_facet_prepare)");
-  if (o->spline_degree < 0 || o->spline_degree > EU_MAX_DEGREE) return fail(EU_ERR_ARGUMENT, "spline degree out of range");
+  rc = check_raster(f, o);
+  if (rc) return rc;
   eu_source* s = new eu_source();
   s->container = nullptr;
   s->last_used_cycle = g.cycle;
@@ -1347,15 +1348,15 @@ int eu_source_reserve(const char* asset_key, const eu_facet_t* f, const eu_opts_
   s->degree = o->spline_degree;
   s->tstride = f->nchannels;
   mount_layout(f, o->spline_degree, s);
-  if (s->lx > s->w || s->rx > s->w || s->ly > s->h || s->ry > s->h) {
-    delete s;
-    return fail(EU_ERR_UNSUPPORTED, "the raster is smaller than the brace of its spline");
-  }
   cudaError_t e = pool_alloc(&s->container, (size_t)s->pitch * s->chh);
+  // rows the caller never writes are zero, not whatever the pool held (a prefilter would spread NaNs)
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->container, 0, (size_t)s->pitch * s->chh * sizeof(float), g.stream);
   if (e != cudaSuccess) {
+    pool_free(s->container);
     delete s;
     return fail(EU_ERR_CUDA, "container: %s", cudaGetErrorString(e));
   }
+  s->reserved = true;
   g.sources.push_back(s);
   if (asset_key && *asset_key) {
     s->key = asset_key;
@@ -1378,24 +1379,58 @@ int eu_source_commit(eu_source_h s, const eu_facet_t* f, const eu_opts_t* o, voi
   if (rc) return rc;
   if (!s || !f || !o) return fail(EU_ERR_ARGUMENT, "null argument");
   if (!known_source(s)) return fail(EU_ERR_ARGUMENT, "not a live source handle");
-  if (s->kind != EU_SRC_MOUNT) return fail(EU_ERR_ARGUMENT, "not a reserved single-image source");
+  if (s->kind != EU_SRC_MOUNT || !s->reserved) return fail(EU_ERR_ARGUMENT, "not a reserved single-image source");
+  // the description must be the one the container was laid out for (texel stride, shape, boundary conditions)
+  eu_source probe;
+  mount_layout(f, o->spline_degree, &probe);
+  if (f->nchannels != s->nch || f->projection != s->projection || o->spline_degree != s->degree || probe.w != s->w ||
+      probe.h != s->h || probe.bc0 != s->bc0 || probe.bc1 != s->bc1 || probe.pitch != s->pitch)
+    return fail(EU_ERR_ARGUMENT, "eu_source_commit: the facet / options differ from those given to eu_source_reserve");
   int pdeg = o->prefilter_degree < 0 ? o->spline_degree : o->prefilter_degree;
   if (pdeg > EU_MAX_DEGREE) return fail(EU_ERR_ARGUMENT, "prefilter degree %d out of range", pdeg);
   cudaStream_t caller = (cudaStream_t)cuda_stream, st = g.stream;
   CK(cudaEventRecord(g.ev[2], caller));  // the rows were written on the caller's stream
   CK(cudaStreamWaitEvent(st, g.ev[2], 0));
   int launches = 0;
-  CK(cudaEventRecord(g.ev[0], st));
+  if (t) CK(cudaEventRecord(g.ev[0], st));
   rc = mount_finish(f, pdeg, s, st, &launches);
   if (rc) return rc;
+  // later work of the caller's stream (renders from this source) comes after the brace
   CK(cudaEventRecord(g.ev[1], st));
-  CK(cudaStreamSynchronize(st));
-  if (t) {
+  CK(cudaStreamWaitEvent(caller, g.ev[1], 0));
+  if (t) {  // blocking and timed; with t == NULL the call only enqueues
+    CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&t->render_ms, g.ev[0], g.ev[1]));
     t->h2d_ms = t->d2h_ms = 0;
     t->launches = launches;
     t->shape = 0;
   }
+  return EU_OK;
+}
+
+int eu_source_write_rect(eu_source_h s, const float* pixels, size_t src_pitch_floats, int row0, int row1, int col0,
+                         int col1, void* cuda_stream) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!s || !pixels) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (!known_source(s) || !s->reserved) return fail(EU_ERR_ARGUMENT, "not a source from eu_source_reserve");
+  if (row0 < 0 || row1 > s->h || row0 >= row1 || col0 < 0 || col1 > s->w || col0 >= col1)
+    return fail(EU_ERR_ARGUMENT, "rectangle [%d,%d) x [%d,%d) does not lie inside the %dx%d raster", row0, row1, col0, col1,
+                s->w, s->h);
+  const size_t wb = (size_t)(col1 - col0) * s->nch * sizeof(float);
+  if (src_pitch_floats * sizeof(float) < wb) return fail(EU_ERR_ARGUMENT, "source pitch shorter than the rectangle's rows");
+  float* dst = s->container + (size_t)(s->ly + row0) * s->pitch + (size_t)(s->lx + col0) * s->nch;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g.up_stream;
+  cudaPointerAttributes pa;
+  cudaMemcpyKind kind = cudaMemcpyHostToDevice;
+  if (cudaPointerGetAttributes(&pa, pixels) == cudaSuccess) {
+    if (pa.type == cudaMemoryTypeDevice) kind = cudaMemcpyDeviceToDevice;
+  } else {
+    cudaGetLastError();
+  }
+  CK(cudaMemcpy2DAsync(dst, (size_t)s->pitch * sizeof(float), pixels, src_pitch_floats * sizeof(float), wb, row1 - row0, kind,
+                       st));
+  if (!cuda_stream) CK(cudaStreamSynchronize(st));
   return EU_OK;
 }
 

@@ -260,12 +260,35 @@ __device__ __forceinline__ void dev_generic_ray(const TargetDev& T, const InvPla
       in[0] = eu_sinf(theta) * eu_sinf(phi);
       break;
     }
-    default: {  // EU_FISHEYE
+    case EU_FISHEYE: {
       float r = sqrtf(h * h + v * v);
       float phi = eu_atan2f(h, -v);
       in[2] = eu_cosf(r);
       in[1] = -eu_sinf(r) * eu_cosf(phi);
       in[0] = eu_sinf(r) * eu_sinf(phi);
+      break;
+    }
+    default: {  // EU_CUBEMAP, EU_BIATAN6: ir_to_ray_t / ba6_to_ray_t with their default metrics (section 2.0,
+                // reference centre 1.0: roll_out_23, geometry.h:1800-1834,660-775,857-990). The double members
+                // only ever meet floats in exact operations (a halving, small even integers, 1.0), so float is it
+      h += 1.0f;
+      v += 6.0f;
+      const int section = (int)(v / 2.0f);
+      v -= (float)section * 2.0f;
+      h -= 1.0f;
+      v -= 1.0f;
+      if (T.projection == EU_BIATAN6) {
+        h = eu_tanf(h * (float)(EU_PI / 4.0));
+        v = eu_tanf(v * (float)(EU_PI / 4.0));
+      }
+      switch (section) {
+        case CM_LEFT: in[0] = -1.0f; in[1] = v; in[2] = h; break;
+        case CM_RIGHT: in[0] = 1.0f; in[1] = v; in[2] = -h; break;
+        case CM_TOP: in[0] = -h; in[1] = -1.0f; in[2] = -v; break;
+        case CM_BOTTOM: in[0] = -h; in[1] = 1.0f; in[2] = v; break;
+        case CM_FRONT: in[0] = h; in[1] = v; in[2] = 1.0f; break;
+        default: in[0] = -h; in[1] = v; in[2] = -1.0f; break;
+      }
     }
   }
   float out[3] = {in[0], in[1], in[2]};
@@ -389,6 +412,9 @@ __device__ __forceinline__ float dev_vfmod(float lhs, float rhs) {
   return lhs;
 }
 __device__ __forceinline__ float dev_gate(float c, int bc, float upper) {
+  // an axis of extent 1 is gated as CONSTANT with both limits 0: a clamp that always yields 0
+  // (build_safe_ev, zimt/eval.h:2060-2068)
+  if (bc == EU_BC_CONST0) return 0.0f;
   const float lower = -0.5f;
   float cc = c - lower;
   float w = upper - lower;
@@ -414,18 +440,20 @@ __device__ __forceinline__ float dev_gate(float c, int bc, float upper) {
 }
 
 // one texel at p. TS: floats from one texel to the next (NCH, or 4 = 16-byte texels: one 128-bit
-// load). SMEM: p points into the block's shared-memory tile, else into HBM (read-only path).
-template <int NCH, int TS, bool SMEM>
+// load). SMEM: 1 = p points into the block's shared-memory tile, 0 = into HBM (read-only path), 2 = into HBM
+// that this very kernel is writing (loads that bypass the non-coherent caches: the ordered cubemap fill).
+template <int NCH, int TS, int SMEM>
 __device__ __forceinline__ void dev_load_texel(const float* __restrict__ p, float v[NCH]) {
   if constexpr (TS == 4) {
-    float4 t = SMEM ? *reinterpret_cast<const float4*>(p) : __ldg(reinterpret_cast<const float4*>(p));
+    float4 t = SMEM == 1 ? *reinterpret_cast<const float4*>(p)
+                         : (SMEM == 2 ? __ldcg(reinterpret_cast<const float4*>(p)) : __ldg(reinterpret_cast<const float4*>(p)));
     v[0] = t.x;
     if constexpr (NCH > 1) v[1] = t.y;
     if constexpr (NCH > 2) v[2] = t.z;
     if constexpr (NCH > 3) v[3] = t.w;
   } else {
 #pragma unroll
-    for (int c = 0; c < NCH; c++) v[c] = SMEM ? p[c] : __ldg(p + c);
+    for (int c = 0; c < NCH; c++) v[c] = SMEM == 1 ? p[c] : (SMEM == 2 ? __ldcg(p + c) : __ldg(p + c));
   }
 }
 
@@ -497,7 +525,7 @@ __device__ __forceinline__ Located dev_locate(const SourceDev& S, int degree, fl
 
 // evaluator::eval for a fixed degree > 1: window sum in the reference's order
 // (zimt/eval.h:903-996). p0 -> texel (ix - deg/2, iy - deg/2); pitch: floats per row.
-template <int NCH, int TS, int DEG, bool SMEM>
+template <int NCH, int TS, int DEG, int SMEM>
 __device__ __forceinline__ void dev_window_sum(const float* __restrict__ p0, int pitch, const float* __restrict__ wmat,
                                                float fx, float fy, float out[NCH]) {
   constexpr int ORDER = DEG + 1;
@@ -534,7 +562,7 @@ __device__ __forceinline__ void dev_window_sum(const float* __restrict__ p0, int
   }
 }
 
-template <int NCH, int TS, bool SMEM>
+template <int NCH, int TS, int SMEM>
 __device__ __forceinline__ void dev_eval_linear(const float* __restrict__ p, int pitch, float fx, float fy,
                                                 float out[NCH]) {  // _eval_linear, zimt/eval.h:1004-1059
   float p00[NCH], p10[NCH], p01[NCH], p11[NCH];
@@ -559,7 +587,7 @@ __device__ __forceinline__ void dev_eval_linear(const float* __restrict__ p, int
 
 // the window evaluation for a located coordinate; p0 -> texel (ix - degree/2, iy - degree/2).
 // DEG >= 0: degree fixed at compile time; DEG < 0: read at run time (all degrees 0..7).
-template <int NCH, int TS, int DEG, bool SMEM>
+template <int NCH, int TS, int DEG, int SMEM>
 __device__ __forceinline__ void dev_window_eval(const float* __restrict__ p0, int pitch, int degree,
                                                 const float* __restrict__ wmat, float fx, float fy, float out[NCH]) {
   if constexpr (DEG == 1) {
@@ -581,14 +609,14 @@ __device__ __forceinline__ void dev_window_eval(const float* __restrict__ p0, in
 }
 
 // safe evaluator = mapper + evaluator (zimt/eval.h:2039-2164, :1237-1300), gathering from HBM
-template <int NCH, int TS, int DEG>
+template <int NCH, int TS, int DEG, int SPACE = 0>
 __device__ __forceinline__ void dev_spline_eval(const SourceDev& S, int degree, const float* __restrict__ wmat,
                                                 float cx, float cy, float out[NCH]) {
   if constexpr (DEG >= 0) degree = DEG;
   Located L = dev_locate(S, degree, cx, cy);
   const int h2 = degree / 2;
   const float* p0 = S.core + (ptrdiff_t)(L.iy - h2) * S.stride + (ptrdiff_t)(L.ix - h2) * TS;
-  dev_window_eval<NCH, TS, DEG, false>(p0, S.stride, degree, wmat, L.fx, L.fy, out);
+  dev_window_eval<NCH, TS, DEG, SPACE>(p0, S.stride, degree, wmat, L.fx, L.fy, out);
 }
 
 // ray_to_cubeface, geometry.h:1178-1357 (>= ties favour x over y over z)

@@ -14,7 +14,8 @@
 #define EU_LANES 16     // zimt vector width of the reference build we track (zimt/simd.h:106-123)
 
 enum { EU_SRC_MOUNT = 0, EU_SRC_CUBEMAP = 1, EU_SRC_BIATAN6 = 2 };
-enum { EU_BC_PERIODIC = 0, EU_BC_REFLECT = 1, EU_BC_NATURAL = 2, EU_BC_MIRROR = 3 };
+// CONST0: the gate of an axis of extent 1 (zimt/eval.h:2060-2068), never a boundary condition of the prefilter
+enum { EU_BC_PERIODIC = 0, EU_BC_REFLECT = 1, EU_BC_NATURAL = 2, EU_BC_MIRROR = 3, EU_BC_CONST0 = 4 };
 // VORONOI_PLUS: alpha compositing of the z-sorted facets (_voronoi_syn_plus), 2/4-channel jobs
 enum { EU_MODE_SINGLE = 0, EU_MODE_VORONOI = 1, EU_MODE_HDR = 2, EU_MODE_VORONOI_PLUS = 3 };
 enum { EU_HDR_LOW = 0, EU_HDR_MIDDLE = 1, EU_HDR_HIGH = 2 };

@@ -434,10 +434,19 @@ __global__ void __launch_bounds__(IIRY_THREADS) k_iir_y_spherical(float* core, i
 // brace: every container texel outside the core is a copy of a core texel (PERIODIC / REFLECT
 // index maps of zimt/brace.h:189-215; spherical: rows beyond the poles continue on the
 // opposite meridian, environment.h:473-516, then the periodic x brace over all rows)
+// zimt's bracer fills the two braces in lock-step from the core outwards, each slice from the slice its mirror
+// image (or period) points at - a brace slice filled a few steps earlier when the brace is wider than the core
+// (a 2-px raster under a quintic spline). The closed form of that is folding the index with period 2n
+// (REFLECT) or n (PERIODIC).
 __device__ __forceinline__ int brace_map(int i, int n, int bc) {
-  if (i < 0) return bc == EU_BC_PERIODIC ? n + i : -1 - i;
-  if (i >= n) return bc == EU_BC_PERIODIC ? i - n : 2 * n - 1 - i;
-  return i;
+  if (i >= 0 && i < n) return i;
+  if (bc == EU_BC_PERIODIC) {
+    i %= n;
+    return i < 0 ? i + n : i;
+  }
+  i %= 2 * n;
+  if (i < 0) i += 2 * n;
+  return i < n ? i : 2 * n - 1 - i;
 }
 // The launch covers the frame only: (ly + ry) full container rows, then (lx + rx) columns beside the
 // core rows - a few thousand texels, not the whole container.
@@ -499,12 +508,10 @@ __global__ void k_cm_ring(float* ir, int stride, int nch, int F, int S, int L, i
 // one frame stripe of one section, by bilinear reprojection from the other sections
 // (fill_frame_t::eval, cubemap.h:733-810). Coordinates are doubled integers relative to the
 // section centre (:867-868).
-template <int NCH>
-__global__ void k_cm_fill(float* ir, SourceDev S, int face, int x0, int y0, int x1, int y1, int section_px,
-                          int ithird, double refc_md, float model_to_px) {
-  int x = x0 + blockIdx.x * blockDim.x + threadIdx.x;
-  int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= x1 || y >= y1) return;
+// fill_frame_t::eval for frame pixel (x, y) of section `face` (cubemap.h:733-810)
+template <int NCH, int SPACE>
+__device__ __forceinline__ void dev_cm_fill_pixel(const SourceDev& S, int face, int x, int y, int section_px, int ithird,
+                                                  double refc_md, float model_to_px, float px[NCH]) {
   int ishift = section_px - 1;
   int c0 = 2 * x - ishift, c1 = 2 * y - ishift;
   float ray[3];
@@ -517,7 +524,7 @@ __global__ void k_cm_fill(float* ir, SourceDev S, int face, int x0, int y0, int 
     default: ray[0] = (float)(-c0); ray[1] = (float)(-ithird); ray[2] = (float)(-c1); break;
   }
   int fv;
-  float in_face[2], pk[2], px[NCH];
+  float in_face[2], pk[2];
   dev_cubeface(ray, fv, in_face);
   // metrics_t::get_pickup_coordinate_px, cubemap.h:401-411 (refc_md is a double member there)
   pk[0] = (float)((double)in_face[0] + refc_md);
@@ -527,19 +534,79 @@ __global__ void k_cm_fill(float* ir, SourceDev S, int face, int x0, int y0, int 
   pk[1] += (float)(fv * section_px);
   pk[0] -= .5f;
   pk[1] -= .5f;
-  dev_spline_eval<NCH, NCH, 1>(S, 1, nullptr, pk[0], pk[1], px);
+  dev_spline_eval<NCH, NCH, 1, SPACE>(S, 1, nullptr, pk[0], pk[1], px);
+}
+
+template <int NCH>
+__global__ void k_cm_fill(float* ir, SourceDev S, int face, int L, int R, int section_px, int ithird, double refc_md,
+                          float model_to_px) {
+  // the four stripes of the section's frame as one index space: top (S x L), bottom (S x R), left (L x mid),
+  // right (R x mid), mid = S - L - R rows. With an EVEN face width a frame pixel's ray hits ANOTHER face, so the
+  // stripes of one section do not read each other and one launch per face keeps the reference's result.
+  const int Sx = section_px, mid = Sx - L - R;
+  const long long n_top = (long long)Sx * L, n_bot = (long long)Sx * R, n_left = (long long)L * mid, n_right = (long long)R * mid;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int x, y;
+  if (i < n_top) { y = (int)(i / Sx); x = (int)(i % Sx); }
+  else if ((i -= n_top) < n_bot) { y = Sx - R + (int)(i / Sx); x = (int)(i % Sx); }
+  else if ((i -= n_bot) < n_left) { y = L + (int)(i / L); x = (int)(i % L); }
+  else if ((i -= n_left) < n_right) { y = L + (int)(i / R); x = Sx - R + (int)(i % R); }
+  else return;
+  float px[NCH];
+  dev_cm_fill_pixel<NCH, 0>(S, face, x, y, section_px, ithird, refc_md, model_to_px, px);
   float* d = ir + (ptrdiff_t)(face * section_px + y) * S.stride + (ptrdiff_t)x * NCH;
 #pragma unroll
   for (int c = 0; c < NCH; c++) d[c] = px[c];
 }
 
+// ODD face widths. The face is then not centred in its section (left frame = right frame - 1) while the
+// pixel-to-ray step assumes it is (ishift = section_px - 1, cubemap.h:861-868), so some frame pixels map onto
+// their OWN section and read frame texels the same fill is rewriting: the result depends on the order in which
+// zimt::process works - faces, stripes and lines in sequence, a line in vectors of 16 pixels, each vector
+// evaluated from the raster as it is and then stored (zimt/wielding.h:317-455). One block walks exactly that
+// order (lanes 0..15 = the pixels of a vector; loads bypass the non-coherent caches). Where the reference is
+// deterministic this reproduces it; the LEFT/RIGHT column that reads the line above races in the reference
+// itself (another thread works on that line) - there the lines are taken in order, as the oracle does.
+// Slow by construction (a few microseconds per vector), used for odd widths only.
+template <int NCH>
+__global__ void k_cm_fill_ordered(float* ir, SourceDev S, int L, int R, int F, int section_px, int ithird, double refc_md,
+                                  float model_to_px) {
+  const int Sx = section_px, lane = threadIdx.x;
+  for (int face = 0; face < 6; face++) {
+    const int win[4][4] = {{0, 0, Sx, L}, {0, Sx - R, Sx, Sx}, {0, L, L, Sx - R}, {L + F, L, Sx, Sx - R}};
+    const int on[4] = {L > 0, R > 0, L > 0, R > 0};
+    for (int st = 0; st < 4; st++) {
+      if (!on[st]) continue;
+      const int x0 = win[st][0], y0 = win[st][1], x1 = win[st][2], y1 = win[st][3];
+      for (int y = y0; y < y1; y++) {
+        for (int v0 = x0; v0 < x1; v0 += EU_LANES) {
+          const int x = v0 + lane;
+          float px[NCH];
+          const bool mine = lane < EU_LANES && x < x1;
+          if (mine) dev_cm_fill_pixel<NCH, 2>(S, face, x, y, section_px, ithird, refc_md, model_to_px, px);
+          __syncthreads();  // every pixel of the vector is evaluated before any is stored
+          if (mine) {
+            float* d = ir + (ptrdiff_t)(face * section_px + y) * S.stride + (ptrdiff_t)x * NCH;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) __stcg(d + c, px[c]);
+          }
+          __threadfence_block();
+          __syncthreads();  // ... and stored before the next vector is evaluated
+        }
+      }
+    }
+  }
+}
+
 // interleaved nch-float texels (rows of src_pitch floats) -> dense 16-byte texels
 __global__ void k_pad_texels(const float* __restrict__ src, int src_pitch, float4* __restrict__ dst, int cw, int chh,
                              int nch) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= cw || y >= chh) return;
-  const float* s = src + (size_t)y * src_pitch + (size_t)x * nch;
-  dst[(size_t)y * cw + x] = make_float4(s[0], nch > 1 ? s[1] : 0.f, nch > 2 ? s[2] : 0.f, 0.f);
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= cw) return;
+  for (int y = blockIdx.y; y < chh; y += gridDim.y) {  // gridDim.y is limited to 65535 rows
+    const float* s = src + (size_t)y * src_pitch + (size_t)x * nch;
+    dst[(size_t)y * cw + x] = make_float4(s[0], nch > 1 ? s[1] : 0.f, nch > 2 ? s[2] : 0.f, 0.f);
+  }
 }
 
 // ---- alpha of masked / cropped facets (environment.h:703-890) -----------------------------
@@ -555,22 +622,26 @@ __device__ __forceinline__ int dev_reflect(int i, int w) {
   return i;
 }
 __global__ void k_alpha_feather_x(const unsigned char* __restrict__ in, float* __restrict__ out, int w, int h) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= w) return;
   const float k5[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
-  float s = 0.0f;
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    float s = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 5; j++) s += k5[j] * (float)in[(size_t)y * w + dev_reflect(x - 2 + j, w)];
-  out[(size_t)y * w + x] = s;
+    for (int j = 0; j < 5; j++) s += k5[j] * (float)in[(size_t)y * w + dev_reflect(x - 2 + j, w)];
+    out[(size_t)y * w + x] = s;
+  }
 }
 __global__ void k_alpha_feather_y(const float* __restrict__ in, float* __restrict__ out, int w, int h) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= w) return;
   const float k5[5] = {1.0f / 16.0f, 4.0f / 16.0f, 6.0f / 16.0f, 4.0f / 16.0f, 1.0f / 16.0f};
-  float s = 0.0f;
+  for (int y = blockIdx.y; y < h; y += gridDim.y) {
+    float s = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 5; j++) s += k5[j] * in[(size_t)dev_reflect(y - 2 + j, h) * w + x];
-  out[(size_t)y * w + x] = s;
+    for (int j = 0; j < 5; j++) s += k5[j] * in[(size_t)dev_reflect(y - 2 + j, h) * w + x];
+    out[(size_t)y * w + x] = s;
+  }
 }
 // raster of native_nch channels -> nch channels (an added alpha channel is 1), times alpha
 __global__ void k_alpha_apply(const float* __restrict__ raw, int native_nch, const float* __restrict__ alpha,
@@ -682,38 +753,44 @@ cudaError_t eu_launch_cubemap_support(float* ir, int pitch, int nch, int F, int 
   src.upper_x = (float)((long double)(S - 1) + 0.5L);
   src.upper_y = (float)((long double)(6 * S - 1) + 0.5L);
   int ithird = (int)(model_to_px * 2);
-  // the reference fills face after face, stripe after stripe, and later stripes read ring
-  // pixels that earlier ones have overwritten (cubemap.h:819-911): keep that order.
-  for (int face = 0; face < 6; face++) {
-    int win[4][4] = {{0, 0, S, L}, {0, S - R, S, S}, {0, L, L, S - R}, {L + F, L, S, S - R}};
-    int on[4] = {L > 0, R > 0, L > 0, R > 0};
-    for (int s = 0; s < 4; s++) {
-      if (!on[s]) continue;
-      int x0 = win[s][0], y0 = win[s][1], x1 = win[s][2], y1 = win[s][3];
-      if (x1 <= x0 || y1 <= y0) continue;
-      dim3 block(32, 8), grid((x1 - x0 + 31) / 32, (y1 - y0 + 7) / 8);
-      switch (nch) {
-        case 1: k_cm_fill<1><<<grid, block, 0, st>>>(ir, src, face, x0, y0, x1, y1, S, ithird, refc_md, (float)model_to_px); break;
-        case 2: k_cm_fill<2><<<grid, block, 0, st>>>(ir, src, face, x0, y0, x1, y1, S, ithird, refc_md, (float)model_to_px); break;
-        case 3: k_cm_fill<3><<<grid, block, 0, st>>>(ir, src, face, x0, y0, x1, y1, S, ithird, refc_md, (float)model_to_px); break;
-        case 4: k_cm_fill<4><<<grid, block, 0, st>>>(ir, src, face, x0, y0, x1, y1, S, ithird, refc_md, (float)model_to_px); break;
-        default: return cudaErrorInvalidValue;
-      }
-      ++*n_launches;
+  if (F & 1) {  // odd face width: the fill reads what it writes - one block in the reference's order
+    switch (nch) {
+      case 1: k_cm_fill_ordered<1><<<1, 32, 0, st>>>(ir, src, L, R, F, S, ithird, refc_md, (float)model_to_px); break;
+      case 2: k_cm_fill_ordered<2><<<1, 32, 0, st>>>(ir, src, L, R, F, S, ithird, refc_md, (float)model_to_px); break;
+      case 3: k_cm_fill_ordered<3><<<1, 32, 0, st>>>(ir, src, L, R, F, S, ithird, refc_md, (float)model_to_px); break;
+      case 4: k_cm_fill_ordered<4><<<1, 32, 0, st>>>(ir, src, L, R, F, S, ithird, refc_md, (float)model_to_px); break;
+      default: return cudaErrorInvalidValue;
     }
+    ++*n_launches;
+    return cudaGetLastError();
+  }
+  // the reference fills face after face, and later faces read ring pixels that earlier ones have overwritten
+  // (cubemap.h:819-911): keep that order. Within a face the four stripes are independent (see k_cm_fill).
+  const int mid = S - L - R;
+  const long long n = (long long)S * (L + R) + (long long)(L + R) * (mid > 0 ? mid : 0);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  for (int face = 0; face < 6; face++) {
+    switch (nch) {
+      case 1: k_cm_fill<1><<<blocks, 256, 0, st>>>(ir, src, face, L, R, S, ithird, refc_md, (float)model_to_px); break;
+      case 2: k_cm_fill<2><<<blocks, 256, 0, st>>>(ir, src, face, L, R, S, ithird, refc_md, (float)model_to_px); break;
+      case 3: k_cm_fill<3><<<blocks, 256, 0, st>>>(ir, src, face, L, R, S, ithird, refc_md, (float)model_to_px); break;
+      case 4: k_cm_fill<4><<<blocks, 256, 0, st>>>(ir, src, face, L, R, S, ithird, refc_md, (float)model_to_px); break;
+      default: return cudaErrorInvalidValue;
+    }
+    ++*n_launches;
   }
   return cudaGetLastError();
 }
 
 cudaError_t eu_launch_pad_texels(const float* src, int src_pitch, float* dst, int cw, int chh, int nch, cudaStream_t st) {
-  dim3 grid((cw + 255) / 256, chh);
+  dim3 grid((cw + 255) / 256, chh < 65535 ? chh : 65535);
   k_pad_texels<<<grid, 256, 0, st>>>(src, src_pitch, reinterpret_cast<float4*>(dst), cw, chh, nch);
   return cudaGetLastError();
 }
 
 cudaError_t eu_launch_alpha_apply(const unsigned char* mask, float* tmp_a, float* tmp_b, const float* raw, int native_nch,
                                   float* out, int nch, int w, int h, cudaStream_t st) {
-  dim3 grid((w + 255) / 256, h);
+  dim3 grid((w + 255) / 256, h < 65535 ? h : 65535);
   k_alpha_feather_x<<<grid, 256, 0, st>>>(mask, tmp_a, w, h);
   k_alpha_feather_y<<<grid, 256, 0, st>>>(tmp_a, tmp_b, w, h);
   size_t n = (size_t)w * h;

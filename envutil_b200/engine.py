@@ -90,12 +90,17 @@ class Engine:
                                                    C.c_void_p(stream), None), self.lib)
         self.launches += 1
 
-    def commit(self, handle, facet_struct, opts, stream=0):
+    def commit(self, handle, facet_struct, opts, stream=0, timed=True):
         tm = capi.Timing()
-        capi.check(self.lib.eu_source_commit(handle, C.byref(facet_struct), C.byref(opts), C.c_void_p(stream), C.byref(tm)),
-                   self.lib)
-        self.launches += tm.launches
+        capi.check(self.lib.eu_source_commit(handle, C.byref(facet_struct), C.byref(opts), C.c_void_p(stream),
+                                             C.byref(tm) if timed else None), self.lib)
+        self.launches += tm.launches if timed else 1  # bilinear sources: the brace kernel
         return tm
+
+    def write_rect(self, handle, pixels_ptr, src_pitch_floats, row0, row1, col0, col1, stream=0):
+        """Rows [row0,row1) x columns [col0,col1) of a reserved source from host / device memory at pixels_ptr."""
+        capi.check(self.lib.eu_source_write_rect(handle, C.c_void_p(pixels_ptr), src_pitch_floats, row0, row1, col0, col1,
+                                                 C.c_void_p(stream)), self.lib)
 
     def release(self, handles):
         for h in handles:

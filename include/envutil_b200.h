@@ -192,7 +192,10 @@ int eu_cubemap_metrics(int face_px, double hfov, int support_min, int tile_size,
 
 /* ---------------------------------------------------------------------------------------
  * Device side. One process drives one GPU (multi-GPU = one process per GPU, each rendering
- * a row band; see eu_render_rows). Single caller, blocking, like payload(). */
+ * a row band; see eu_render_rows). Single caller, blocking, like payload(): the library keeps one
+ * context per process and is NOT thread-safe - all calls must come from one host thread at a time
+ * (eu_last_error alone is per thread). Jobs on different CUDA streams are safe: every plan's tables
+ * live in their own slot, reused only behind an event recorded after the kernels that read them. */
 int eu_init(int device_id);
 void eu_shutdown(void);
 const char* eu_last_error(void);
@@ -262,6 +265,14 @@ int eu_source_reserve(const char* asset_key, const eu_facet_t* f, const eu_opts_
                       float** d_core, int* pitch_floats);
 int eu_source_commit(eu_source_h s, const eu_facet_t* f, const eu_opts_t* o, void* cuda_stream,
                      eu_timing_t* t);
+/* Fill part of a reserved source from a raster in host (page-locked, for a truly asynchronous copy) or device
+ * memory: the rectangle rows [row0,row1) x columns [col0,col1) of the image; `pixels` points at its first texel,
+ * rows src_pitch_floats apart. Enqueued on cuda_stream (NULL: the library's upload stream, and the call blocks).
+ * Ranks of a multi-GPU job upload just the part of every source their band of the output can see. Rows and
+ * columns never written read as zero. f and o given to eu_source_commit must be those given to
+ * eu_source_reserve; with t == NULL eu_source_commit only enqueues (later work on cuda_stream is ordered after it). */
+int eu_source_write_rect(eu_source_h s, const float* pixels, size_t src_pitch_floats, int row0, int row1, int col0,
+                         int col1, void* cuda_stream);
 /* Pipelined jobs. payload() is blocking, but a host that streams jobs (pipe mode, sequences) can
  * keep the PCIe links busy in both directions: eu_source_upload_async enqueues the H2D copy on an
  * upload stream and the staging kernels behind it, eu_render_async enqueues the render and - on a

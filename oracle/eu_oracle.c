@@ -1194,12 +1194,33 @@ static void generic_ray(const target_ctx* T, const facet_ctx* F, float h, float 
       in[0] = eu_sinf(theta) * eu_sinf(phi);
       break;
     }
-    default: { /* EU_FISHEYE */
+    case EU_FISHEYE: {
       float r = sqrtf(h * h + v * v);
       float phi = eu_atan2f(h, -v);
       in[2] = eu_cosf(r);
       in[1] = -eu_sinf(r) * eu_cosf(phi);
       in[0] = eu_sinf(r) * eu_sinf(phi);
+      break;
+    }
+    default: { /* EU_CUBEMAP, EU_BIATAN6: ir_to_ray_t / ba6_to_ray_t as roll_out_23 default-constructs them
+                * (geometry.h:1800-1834,660-775,857-990): section_md 2.0, refc_md 1.0, ul2c = {1, 6} */
+      float c0 = h + 1.0f, c1 = v + 6.0f;
+      int section = (int)((double)c1 / 2.0);
+      c1 = (float)((double)c1 - (double)section * 2.0);
+      c0 -= 1.0f;
+      c1 -= 1.0f;
+      if (T->projection == EU_BIATAN6) {
+        c0 = eu_tanf(c0 * (float)(M_PI / 4));
+        c1 = eu_tanf(c1 * (float)(M_PI / 4));
+      }
+      switch (section) {
+        case CM_LEFT: in[0] = -1.0f; in[1] = c1; in[2] = c0; break;
+        case CM_RIGHT: in[0] = 1.0f; in[1] = c1; in[2] = -c0; break;
+        case CM_TOP: in[0] = -c0; in[1] = -1.0f; in[2] = -c1; break;
+        case CM_BOTTOM: in[0] = -c0; in[1] = 1.0f; in[2] = c1; break;
+        case CM_FRONT: in[0] = c0; in[1] = c1; in[2] = 1.0f; break;
+        default: in[0] = -c0; in[1] = c1; in[2] = -1.0f; break;
+      }
     }
   }
   float out[3];

@@ -264,6 +264,11 @@ def _build():
     add("tr3_voronoi_fish_d3_tw2", Job(tr, "fisheye", 200.0, 96, 96, degree=3, twine=2))
     add("tr2_cyl_d1", Job(tr[:2], "cylindrical", 300.0, 200, 60))
     add("tr2_ster_d1", Job(tr[1::-1], "stereographic", 220.0, 100, 100, yaw=-10.0))
+    # translated facets with cubemap / biatan6 targets: the generic stepper over ir_to_ray_t / ba6_to_ray_t
+    # (geometry.h:660-990; envutil_payload.cc:2097-2111 with STP = cubemap)
+    add("tr1_cube_d1", Job(tr[:1], "cubemap", 90.0, 48, yaw=-20.0))
+    add("tr3_voronoi_ba6_d1_tw2", Job(tr, "biatan6", 90.0, 40, twine=2, yaw=15.0, pitch=-8.0))
+    add("tr2_cube100_d3", Job(tr[:2], "cubemap", 100.0, 36, degree=3))
     return J
 
 
