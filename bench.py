@@ -4,28 +4,27 @@
     python bench.py --gpus N --steps K --warmup W            (ours: sm_100a kernels via the C ABI)
     python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU path)
 
-Workload (config.workload): BASELINE.json configs[1] - a synthetic 1:6 cubemap with 2048-px
-faces reprojected to a full spherical 8192x4096 image with a cubic b-spline (prefiltered),
-float RGB. A step is one rendered frame per GPU.
+N = 1  workload (config.workload): BASELINE.json configs[1] - a synthetic 1:6 cubemap with 2048-px faces
+       reprojected to a full spherical 8192x4096 image with a cubic b-spline (prefiltered), float RGB; a step is
+       one rendered frame. The line also carries `configs`: every other BASELINE config measured the same way in
+       the same run (device-timed render, roofline, staging), and the configs[4] pipeline on this one GPU.
+N > 1  workload: BASELINE.json configs[4] ("... at 1/2/4/8 GPUs") - the PTO stitch of 6 positions x 3 exposure
+       brackets into a 16384x8192 panorama, ONE frame split into row bands over the ranks (strong scaling;
+       envutil_b200/c5.py). A step is the whole two-stage pipeline. `--workload c2 --partition frames|bands`
+       keeps round 1's replica frames / C2 bands.
 
-  value     whole-job Mpix/s of the render kernel with the staged source resident in HBM,
-            CUDA events around exactly K back-to-back launches, max over ranks
-  roofline  algorithmic bytes per launch (output store + the six cube faces) /
-            average launch duration of k_render inside that same timed region, against the
-            measured copy bandwidth in MEASURED_PEAKS.json
-  e2e       the same frames through the host-buffer C ABI a cuda_dispatch::payload() would
-            call: eu_source_upload (pinned host raster -> H2D -> IR build -> prefilter) +
-            eu_render (kernel -> D2H into a pinned host buffer), wall clock, every step
+  value     whole-job Mpix/s, CUDA events around exactly K steps with all inputs resident in HBM, max over ranks
+  roofline  algorithmic bytes per launch of the dominant kernel / its average duration inside that timed region,
+            against the measured copy bandwidth in MEASURED_PEAKS.json; `secondary` = the instruction-issue bound
+            of the same kernel from its ncu instruction count (profiles/)
+  e2e       the same work through the host-buffer C ABI: page-locked host rasters -> H2D -> staging -> render ->
+            D2H into a page-locked host frame, wall clock, every step (N > 1: every rank moves only its own part
+            of the sources and its own band, over its own PCIe link, into one frame in shared host memory)
   cpu_baseline / --impl reference
-            the UNMODIFIED reference (oracle/_ref/envutil_ref_fast, built from
-            /root/reference by oracle/Makefile: -O3 -march=x86-64-v3, zimt goading back-end,
-            zimt thread pool = 2 x hardware threads) running the same job on this box's host
-            cores; a step is one process run = its payload() (source build + prefilter +
-            render), wall clock minus the time the file shim spent reading/writing rasters.
-            Falls back to the C oracle port (OpenMP, all cores) if the binary is absent.
-Multi-GPU (weak scaling): rank 0 synthesises the source, broadcasts the raster over NCCL,
-every rank stages it and renders its own full frame per step (camera yaw = 360 * rank / N);
-no data-path collective inside the timed region.
+            the UNMODIFIED reference (oracle/_ref/envutil_ref_fast[512], built from /root/reference by
+            oracle/Makefile: -O3, zimt goading back-end - highway is not in this image -, zimt thread pool =
+            2 x hardware threads) running the same job on this box's host cores; a step is one process run = its
+            payload() (source build + prefilter + render), wall clock minus the time the file shim spent on rasters.
 """
 import argparse
 import json
@@ -43,6 +42,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "output Mpix/s (device-timed)"
+DEFAULT_ARITHMETIC = "exact"
 UNIT = "Mpix/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
 
@@ -56,11 +56,20 @@ def parse_args():
     ap.add_argument("--scale", type=int, default=1, help="shrink the workload (tests only; invalid as a bench)")
     ap.add_argument("--padded", type=int, default=0, help="1: 16-byte RGB texels in HBM")
     ap.add_argument("--no-tiles", type=int, default=0, help="1: direct-gather kernel (no shared-memory staging)")
-    ap.add_argument("--warp-tiles", type=int, default=0,
-                    help="1: experimental kernel that stages the gather footprint per warp (k_render_warp)")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c5"],
+                    help="auto: C2 on one GPU (the headline config), the C5 row-band pipeline on N > 1")
+    ap.add_argument("--arithmetic", default=DEFAULT_ARITHMETIC, choices=["exact", "contracted"],
+                    help="render kernels: exact = no contraction (bit-identical to the reference's parity build); contracted = "
+                         "fused multiply-adds in the window evaluation (EU_OPT_CONTRACTED; parity in profiles/)")
+    ap.add_argument("--configs", default="C1,C3a,C3b,C4,C5",
+                    help="N = 1: the other BASELINE configs measured beside the headline ('' = none)")
+    ap.add_argument("--budget-s", type=float, default=240.0,
+                    help="N = 1: configs that would start after this many seconds of run time are skipped (and listed)")
+    ap.add_argument("--c5-plan", default="needed", choices=["needed", "full"],
+                    help="C5 stage A: merge only the texels stage B samples (default) or every texel of every position")
     ap.add_argument("--partition", default="frames", choices=["frames", "bands"],
-                    help="N > 1: frames = one full frame per rank per step (weak scaling, default); bands = the ranks "
-                         "split ONE frame into row bands, gathered on rank 0 over NCCL (strong scaling)")
+                    help="--workload c2, N > 1: frames = one full frame per rank per step (replicas, weak scaling); bands "
+                         "= the ranks split ONE C2 frame into row bands (strong scaling)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="bands: peer = every rank's render kernel stores its band straight into rank 0's frame over "
                          "NVLink (eu_frame_*; render and gather are one kernel, default); nccl = band buffers + gather")
@@ -262,6 +271,214 @@ def reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# evidence files under profiles/ (committed; produced on a B200 by tools/full_parity.py and tools/gpu_profile.sh)
+def _profile_json(name):
+    p = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except ValueError:
+            pass
+    return None
+
+
+def parity_record(config, arithmetic):
+    """max / RMS of the CUDA path against both builds of the reference for one config at FULL size, whole frame
+    (tools/full_parity.py on the B200 box; bench.py itself never runs the checker outside its cpu_baseline leg)."""
+    d = _profile_json("r02_parity_full_%s.json" % arithmetic)
+    if not d:
+        return {"source": None, "note": "profiles/r02_parity_full_%s.json not present" % arithmetic}
+    for rec in d.get("configs", []):
+        if rec.get("config") == config:
+            out = {"source": "profiles/r02_parity_full_%s.json (tools/full_parity.py, whole frame at full size)" % arithmetic,
+                   "eps": d.get("eps"), "tolerance": d.get("tolerance")}
+            vp = rec.get("vs_pinned", {})
+            out["vs_pinned"] = {"max": vp.get("max_rel"), "rms": vp.get("rms_rel"), "n_diff": vp.get("n_diff"), "n": vp.get("n")}
+            vl = rec.get("vs_libm")
+            if vl:
+                m = vl.get("masked", {})
+                out["vs_libm"] = {"max": vl.get("max_rel"), "rms": vl.get("rms_rel"), "n_beyond_1e-5": vl.get("n_beyond_1e-5"),
+                                  "masked": m.get("pixels"), "max_outside_tie_band": m.get("max_rel")}
+            rs = rec.get("ref_self")
+            if rs:
+                out["reference_builds_apart"] = {"max": rs.get("max_rel"), "rms": rs.get("rms_rel")}
+            if "round_trip" in rec:
+                out["round_trip"] = rec["round_trip"]
+            return out
+    return {"source": None, "note": "no record for %s" % config}
+
+
+def kernel_record(config, arithmetic):
+    """ncu figures of the config's render kernel (one launch, --set full): DRAM bytes, instructions, L2 hit rate."""
+    d = _profile_json("r02_kernels.json") or {}
+    return d.get("%s/%s" % (config, arithmetic)) or d.get(config)
+
+
+def roofline_of(alg_bytes, ms, peak, peak_src, config, arithmetic, sm_mhz=1965.0):
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    k = kernel_record(config, arithmetic)
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+         "traffic": k.get("dram_bytes") if k else None, "traffic_source": k.get("source") if k else None,
+         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes), "frac_of_8TBs_spec": achieved / 8000.0}
+    if k and k.get("inst_executed"):
+        # the kernel's instruction stream at one warp instruction per scheduler per cycle: 148 SMs x 4 schedulers
+        floor_ms = k["inst_executed"] / (148 * 4 * sm_mhz * 1e6) * 1e3
+        r["secondary"] = {"bound": "issue", "frac": floor_ms / ms, "floor_ms": floor_ms, "inst_executed": k["inst_executed"],
+                          "l2_hit_pct": k.get("l2_hit_pct"), "issue_active_pct": k.get("issue_active_pct"),
+                          "kernel": k.get("kernel"), "source": k.get("source")}
+    return r
+
+
+def numa_setup(local):
+    """Pin this rank to the CPUs next to its GPU (NVML affinity) before any page-locked buffer is allocated, so that
+    first-touch places the buffers on the GPU's NUMA node. Returns what was done, for the bench line."""
+    info = {"cpus_before": len(os.sched_getaffinity(0))}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        info.update({"gpu_cpus": len(cpus), "cpus_after": len(os.sched_getaffinity(0))})
+        try:
+            info["numa_node"] = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:
+            pass
+    except Exception as e:  # affinity is an optimisation, never a requirement
+        info["error"] = str(e)[:120]
+    return info
+
+
+def time_launches(torch, fn, steps, warmup=3, flush=None):
+    """Average device time of fn() in ms: CUDA events on the launching stream around `steps` back-to-back calls
+    (flush: an L2-sized buffer cleared before every call, each call timed on its own)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if flush is None:
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+    tot = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / steps
+
+
+def bench_other_configs(args, eng, torch, peak, peak_src, t_run0):
+    """Every BASELINE config besides the headline, in this run: device-timed render (inputs resident in HBM, larger
+    than L2 or L2 flushed), roofline against exact algorithmic bytes, staging time, parity record of the config."""
+    from envutil_b200 import c5, synth, workloads
+    from envutil_b200.job import FacetSpec, Job
+    want = [c for c in args.configs.split(",") if c]
+    out, skipped = [], []
+    contracted = args.arithmetic == "contracted"
+    stream = torch.cuda.current_stream().cuda_stream
+    steps = max(3, min(args.steps, 10))
+
+    def over_budget(name):
+        if time.perf_counter() - t_run0 > args.budget_s:
+            skipped.append(name)
+            return True
+        return False
+
+    def single(job, alg, name, flush=None, keep=None, dev_src=None):
+        job.contracted = contracted
+        st = job.structs(eng.lib)
+        t = st[0]
+        if dev_src is not None:
+            hs = eng.stage_device(job, [dev_src.data_ptr()], st, stream=stream)
+        else:
+            hs = eng.stage(job, st)
+        stage_ms = sum(tm.render_ms for tm in eng.last_stage_timing)
+        d_out = torch.empty((t.height, t.width, t.nchannels), dtype=torch.float32, device="cuda")
+        ms = time_launches(torch, lambda: eng.render_rows(job, hs, st, 0, t.height, d_out.data_ptr(), stream, timed=False),
+                           steps, 3, flush)
+        eng.release(hs)
+        mpix = t.width * t.height / 1e6
+        rec = {"config": name, "workload": job.name, "out": "%dx%d" % (t.width, t.height), "value": mpix / (ms * 1e-3),
+               "unit": UNIT, "ms": ms, "steps": steps,
+               "l2": "flushed between launches" if flush is not None else "inputs larger than L2",
+               "roofline": roofline_of(alg, ms, peak, peak_src, name, args.arithmetic),
+               "staging": {"ms": stage_ms}, "parity": parity_record(name, args.arithmetic)}
+        out.append(rec)
+        return d_out if keep else None
+
+    if "C1" in want and not over_budget("C1"):
+        job, alg = workloads.c1(args.scale)
+        job.name = "C1: lat/lon 4096x2048 -> rectilinear 1920x1080 hfov 90, bilinear"
+        single(job, alg, "C1", flush=torch.empty(256 << 20, dtype=torch.uint8, device="cuda"))
+    if ("C3a" in want or "C3b" in want) and not over_budget("C3"):
+        job, alg = workloads.c3a(args.scale)
+        job.name = "C3a: lat/lon 16384x8192 -> biatan6 cubemap 4096px faces, bilinear"
+        cube = single(job, alg, "C3a", keep=True)
+        del job
+        if "C3b" in want:
+            face = cube.shape[1]
+            job2 = Job([FacetSpec(None, "biatan6", 90.0, width=face, height=6 * face, nchannels=3)], "spherical", 360.0,
+                       4 * face, 2 * face, degree=1, name="C3b: that biatan6 cubemap -> lat/lon 16384x8192, bilinear")
+            alg2 = job2.width * job2.height * workloads.RGB + 6 * face * face * workloads.RGB
+            if face == 4096:
+                alg2 = job2.width * job2.height * workloads.RGB + workloads.EXACT_TOUCHED["C3b"] * workloads.RGB
+            single(job2, alg2, "C3b", dev_src=cube)
+        del cube
+    if "C4" in want and not over_budget("C4"):
+        job, alg = workloads.c4(args.scale)
+        job.name = "C4: lat/lon 8192x4096 -> fisheye 4096x4096 hfov 180, twine 4 (16 sub-rays per pixel), bilinear"
+        single(job, alg, "C4")
+    if "C5" in want and not over_budget("C5"):
+        (w, h), (W, H) = c5.sizes(args.scale)
+        checks = {}
+        for plan in ("full", "needed"):
+            pl = c5.Pipeline(eng, torch, 0, 1, args.scale, plan=plan, contracted=contracted)
+            pl.upload()
+            a_ms = time_launches(torch, pl.stage_a, 3, 2)
+            pl.stage_b_staging()
+            sb_ms = time_launches(torch, pl.stage_b_staging, 3, 1)
+            b_ms = time_launches(torch, pl.stage_b, 3, 2)
+            pipe_ms = time_launches(torch, pl.step_device, 3, 1)
+            torch.cuda.synchronize()
+            checks[plan] = float(pl.d_band[0][::61, ::67].double().sum().item())
+            mp_a = c5.stage_a_pixels(pl.rects) * c5.POSITIONS / 1e6
+            if plan == "full":
+                out.append({"config": "C5A", "workload": "C5 stage A: 6 x hdr_merge (--single 0) of 3 brackets %dx%d, every texel "
+                            "merged (as the reference runs it)" % (w, h), "out": "6 x %dx%d" % (w, h),
+                            "value": mp_a / (a_ms * 1e-3), "unit": UNIT, "ms": a_ms, "steps": 3, "l2": "inputs larger than L2",
+                            "roofline": roofline_of(pl.stage_a_alg_bytes(), a_ms, peak, peak_src, "C5A", args.arithmetic),
+                            "staging": {"ms": None, "note": "bilinear sources: brace only, inside the upload"},
+                            "parity": parity_record("C5A", args.arithmetic)})
+                out.append({"config": "C5B", "workload": "C5 stage B: voronoi panorama of the 6 merged rasters -> spherical %dx%d"
+                            % (W, H), "out": "%dx%d" % (W, H), "value": W * H / 1e6 / (b_ms * 1e-3), "unit": UNIT, "ms": b_ms,
+                            "steps": 3, "l2": "inputs larger than L2",
+                            "roofline": roofline_of(pl.alg_b_full, b_ms, peak, peak_src, "C5B", args.arithmetic),
+                            "staging": {"ms": sb_ms, "what": "brace of the six merged rasters"},
+                            "parity": parity_record("C5B", args.arithmetic)})
+            rec = {"config": "C5 pipeline (%s)" % plan, "out": "%dx%d" % (W, H), "value": W * H / 1e6 / (pipe_ms * 1e-3),
+                   "unit": UNIT, "ms": pipe_ms, "stage_a_ms": a_ms, "stage_b_staging_ms": sb_ms, "stage_b_ms": b_ms,
+                   "stage_a_mpix": mp_a, "h2d_bytes": pl.h2d_bytes, "checksum": checks[plan],
+                   "workload": "configs[4] on ONE GPU: stage A + brace + stage B, brackets resident in HBM; plan '%s' = %s" % (
+                       plan, "stage A merges every texel of every position" if plan == "full" else
+                       "stage A merges only the rectangles of each position that stage B samples (49 % of the columns)")}
+            out.append(rec)
+            pl.close()
+            del pl
+        out[-1]["checksum_equals_full_merge"] = checks["needed"] == checks["full"]
+    return out, skipped
+
+
+# ---------------------------------------------------------------------------------------------
 def ours(args):
     import torch
     import torch.distributed as dist
@@ -274,6 +491,10 @@ def ours(args):
         raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = numa_setup(local)
+    from envutil_b200 import synth
+    synth.WORKERS = max(1, min(16, len(os.sched_getaffinity(0)) // max(1, world)))
+    t_run0 = time.perf_counter()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -321,7 +542,7 @@ def ours(args):
     if not bands_mode:
         job.yaw = 360.0 * rank / world  # every rank renders its own view of the same environment
     job.padded, job.no_tiles = bool(args.padded), bool(args.no_tiles)
-    job.warp_tiles = bool(args.warp_tiles)
+    job.contracted = args.arithmetic == "contracted"
     job.narrow_stores = bool(args.narrow_stores)
     eng = Engine(local)
     st = job.structs(eng.lib)
@@ -479,31 +700,45 @@ def ours(args):
     # staging stream (the first passes still grow it: 321 MB from the driver per job, tens of ms each)
     pipelined(4 * DEPTH)
     e2e_s, best_stamps, best_t0 = None, None, None
+    rep_times = []
     for _ in range(REPS):
         barrier()
         t0 = time.perf_counter()
         pipelined(pipe_steps)
         barrier()
         dt = time.perf_counter() - t0
+        rep_times.append(dt)
         if e2e_s is None or dt < e2e_s:
             e2e_s, best_stamps, best_t0 = dt, list(finish_stamps), t0
     finish_stamps[:] = best_stamps
     t0 = best_t0
     gc.enable()
-    te = torch.tensor([e2e_s / pipe_steps, e2e_blocking_s / e2e_steps], dtype=torch.float64, device=dev)
+    rep_times.sort()
+    e2e_median_s = rep_times[len(rep_times) // 2]
+    te = torch.tensor([e2e_s / pipe_steps, e2e_blocking_s / e2e_steps, e2e_median_s / pipe_steps], dtype=torch.float64,
+                      device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te[0].item()) * 1e3
     e2e_blocking_ms = float(te[1].item()) * 1e3
+    e2e_median_ms = float(te[2].item()) * 1e3
     e2e_steps = pipe_steps
     h_out = ring[(pipe_steps - 1) % DEPTH]
     e2e_ok = bool(np.array_equal(h_out[::97, ::89].numpy(), d_out[::97, ::89].cpu().numpy()))
     if sampler:
         sampler.stop()
 
+    other, skipped = [], []
+    if rank == 0 and world == 1 and args.configs:
+        eng.release(hs)
+        hs = None
+        del d_out
+        torch.cuda.empty_cache()
+        pk, pk_src = measured_peak()
+        other, skipped = bench_other_configs(args, eng, torch, pk, pk_src, t_run0)
     if rank == 0:
         peak, peak_src = measured_peak()
-        tr = measured_traffic() if (args.scale == 1 and not args.padded and not args.no_tiles and not args.warp_tiles
+        tr = measured_traffic() if (args.scale == 1 and not args.padded and not args.no_tiles
                                     and not bands_mode) else None
         alg_launch = alg // world if bands_mode else alg  # a band touches its share of output and source
         achieved = alg_launch / (ms_per_step * 1e-3) / 1e9  # per launch = per GPU
@@ -518,6 +753,14 @@ def ours(args):
                 except Exception as e:  # the baseline is context; never let it sink the bench line
                     cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
                            "sample": "failed: %s" % str(e)[:200]}
+        roof = roofline_of(alg_launch, ms_per_step, peak, peak_src, "C2", args.arithmetic,
+                           clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965.0)
+        if roof["traffic"] is None and tr:
+            roof["traffic"], roof["traffic_source"] = tr["traffic_bytes"], tr["source"]
+        roof["kernel"] = "k_render<3,...>" if args.no_tiles else "k_render_tiled<3,...>"
+        if cpu and cpu.get("build"):
+            cpu["build"] += ("; highway / Vc are not in this image, so this is zimt's plain-loop ('goading') back-end - the "
+                             "reference's default highway build may be faster")
         line = {
             "metric": METRIC, "value": (1 if bands_mode else world) * mpix / (ms_per_step * 1e-3), "unit": UNIT,
             "n_gpus": world,
@@ -529,20 +772,20 @@ def ours(args):
                        "l2": "inputs_larger_than_l2 (321 MB source IR + 403 MB output per frame vs 126 MB L2)",
                        "texel_layout": "float4-padded" if args.padded else "interleaved-rgb",
                        "gather": "direct (L1)" if args.no_tiles else
-                                 "footprint staged in shared memory per warp by cp.async.bulk (experimental)" if args.warp_tiles else
                                  "footprint staged in shared memory by cp.async.bulk",
-                       "arithmetic": capi.ARITHMETIC,  # "contracted" only with EU_ARITHMETIC=contracted (opt-in build)
-                       "parity": "bit-exact vs pinned-math reference build (tests/)" if capi.ARITHMETIC == "exact" else
-                                 "window evaluation with fused multiply-adds: indices identical, values within 3.5e-7 "
-                                 "relative (RMS 5.8e-8) of the pinned-math reference build on this workload, 2.6e-6 "
-                                 "(hdr_merge 1.6e-5) over the 98 small jobs (tests/test_contracted.py, DESIGN.md 2)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": tr["traffic_bytes"] if tr else None,
-                         "traffic_source": tr["source"] if tr else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_launch,
-                         "kernel": "k_render<3,...>" if args.no_tiles else "k_render_warp<3,...>" if args.warp_tiles else "k_render_tiled<3,...>", "frac_of_8TBs_spec": achieved / 8000.0},
+                       "arithmetic": args.arithmetic,  # eu_opts_t.reserved[1] & EU_OPT_CONTRACTED
+                       "parity": parity_record("C2", args.arithmetic), "numa": numa,
+                       "value_scope": "the render kernel alone (source staged and resident); cpu_baseline.value is the "
+                                      "reference's whole payload() - compare `staging_plus_render` with it, or "
+                                      "`value` with cpu_baseline.render_only_mpix_s"},
+            "staging_plus_render": {"value": mpix / ((stage_ms + ms_per_step) * 1e-3), "unit": UNIT,
+                                    "ms": stage_ms + ms_per_step, "scope": "device-timed staging + render = payload()'s scope"},
+            "roofline": roof,
             "e2e": {"value": world * mpix / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(h_src.numel() * 4), "d2h_bytes_per_step": int(h_out.numel() * 4),
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "median_of_repetitions": {"value": world * mpix / (e2e_median_ms * 1e-3), "ms_per_step": e2e_median_ms,
+                                              "repetitions_ms_per_step": [round(t / pipe_steps * 1e3, 3) for t in rep_times]},
                     "scope": "every step: H2D of the 302 MB raster + cubemap IR + prefilter + render + D2H of the 403 MB "
                              "frame, pinned host buffers, wall clock; eu_source_upload_async / eu_render_async / "
                              "eu_job_wait with 3 jobs in flight (upload of step n+1 overlaps download of step n); "
@@ -571,20 +814,335 @@ def ours(args):
                                      ("NCCL gather of band buffers, timed separately" if bands_mode else None)),
                           "peer_frame_equals_single_gpu_render": peer_ok},
             "cpu_baseline": cpu, "checksum": checksum, "setup_s": setup_s,
+            "configs": other, "configs_skipped": skipped, "run_s": time.perf_counter() - t_run0,
         }
         print(json.dumps(line))
-    eng.release(hs)
+    if hs is not None:
+        eng.release(hs)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+# ---------------------------------------------------------------------------------------------
+# N > 1 (and --workload c5): BASELINE configs[4] split into row bands over the ranks
+def c5_workload_name(scale, world):
+    from envutil_b200 import c5
+    (w, h), (W, H) = c5.sizes(scale)
+    return ("C5: PTO stitch of 6 synthetic rectilinear %dx%d positions x 3 exposure brackets (hdr_merge per position, "
+            "voronoi panorama) -> spherical %dx%d, float RGB, bilinear" % (w, h, W, H))
+
+
+def ours_c5(args):
+    import torch
+    import torch.distributed as dist
+    from envutil_b200 import bands as eu_bands, c5, synth
+    from envutil_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa = numa_setup(local)  # before any page-locked allocation: first touch places it next to this GPU
+    synth.WORKERS = max(1, min(16, len(os.sched_getaffinity(0)) // max(1, min(world, 4))))
+    t_run0 = time.perf_counter()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def over_ranks(v, op="max"):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def every_rank(obj):
+        if world == 1:
+            return [obj]
+        got = [None] * world
+        dist.all_gather_object(got, obj)
+        return got
+
+    (w, h), (W, H) = c5.sizes(args.scale)
+    eng = Engine(local)
+    # ---- ONE frame in shared host memory; every rank page-locks and fills its own band ----------------
+    tag = os.environ.get("MASTER_PORT", "0") + "_" + str(os.getppid() if world > 1 else os.getpid())
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    frame_path = os.path.join(shm, "eu_c5_frame_%s.f32" % tag)
+    if rank == 0:
+        np.memmap(frame_path, dtype=np.float32, mode="w+", shape=(H, W, 3)).flush()
+    barrier()
+    frame_np = np.memmap(frame_path, dtype=np.float32, mode="r+", shape=(H, W, 3))
+    frame_t = torch.from_numpy(frame_np)
+    t_setup = time.perf_counter()
+    pl = c5.Pipeline(eng, torch, rank, world, args.scale, plan=args.c5_plan, contracted=args.arithmetic == "contracted",
+                     host_frame=frame_t)
+    band_t = frame_t[pl.row0:pl.row1]
+    band_t.zero_()  # first touch by the rank that owns the band
+    rt = torch.cuda.cudart()
+    reg = rt.cudaHostRegister(band_t.data_ptr(), band_t.numel() * 4, 0)
+    registered = int(reg) == 0 if not isinstance(reg, tuple) else int(reg[0]) == 0
+    setup_s = time.perf_counter() - t_setup
+
+    # ---- device-timed: stage A + brace + stage B on resident brackets, exactly K steps -------------------
+    pl.upload()
+    torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        pl.step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 5.0:
+            time.sleep(0.02)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_before = eng.launches
+    tw0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        pl.step_device()
+    ev1.record()
+    barrier()
+    tw1 = time.perf_counter()
+    my_ms = ev0.elapsed_time(ev1) / args.steps
+    ms_per_step = over_ranks(my_ms)
+    launches = over_ranks(eng.launches - launches_before, "sum")
+    clocks = None
+    if sampler:
+        time.sleep(0.15)
+        clocks = ClockSampler.summarise(sampler.window(tw0, tw1))
+        sampler.stop()
+    # the stages on their own (same launches, timed separately; not part of `value`)
+    a_ms = time_launches(torch, pl.stage_a, max(3, min(args.steps, 10)), 1)
+    sb_ms = time_launches(torch, pl.stage_b_staging, max(3, min(args.steps, 10)), 1)
+    b_ms = time_launches(torch, pl.stage_b, max(3, min(args.steps, 10)), 1)
+
+    # ---- e2e: host rasters in, host frame out, every step ---------------------------------------------------
+    e2e_steps = args.e2e_steps or max(2, min(args.steps, 6))
+    import gc
+    gc.collect()
+    gc.disable()
+    for _ in range(2):
+        pl.step_e2e()
+    pl.finish()
+    reps = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pl.step_e2e()
+        pl.finish()
+        barrier()
+        reps.append(over_ranks(time.perf_counter() - t0))
+    gc.enable()
+    # the copies on their own: this rank's upload (H2D + brace) and its band's download
+    up_ms = time_launches(torch, pl.upload, 2, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    band_t.copy_(pl.d_band[0], non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    down_ms = e0.elapsed_time(e1)
+    barrier()
+    # ---- beside the timed regions: the bands gathered into rank 0's HBM over NCCL -----------------
+    gather_ms = 0.0
+    if world > 1:
+        full = eu_bands.gather_ragged(pl.d_band[0], pl.bands, rank, dist)  # first use sets up the channels
+        del full
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = eu_bands.gather_ragged(pl.d_band[0], pl.bands, rank, dist)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+        dev_checksum = float(full[::61, ::67].double().sum().item()) if rank == 0 else None
+        del full
+    else:
+        dev_checksum = float(pl.d_band[0][::61, ::67].double().sum().item())
+    barrier()
+    per_rank = every_rank({"rank": rank, "rows": [pl.row0, pl.row1], "ms": my_ms, "stage_a_ms": a_ms, "stage_b_staging_ms": sb_ms,
+                           "stage_b_ms": b_ms, "stage_a_mpix": c5.stage_a_pixels(pl.rects) * c5.POSITIONS / 1e6,
+                           "stage_a_alg_bytes": pl.stage_a_alg_bytes(), "h2d_bytes": pl.h2d_bytes, "d2h_bytes": pl.d2h_bytes,
+                           "upload_ms": up_ms, "download_ms": down_ms, "host_band_page_locked": registered, "numa": numa})
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        host_checksum = float(frame_np[::61, ::67].astype(np.float64).sum())
+        slow = max(per_rank, key=lambda r: r["stage_a_ms"])
+        roof = roofline_of(slow["stage_a_alg_bytes"], slow["stage_a_ms"], peak, peak_src, "C5A", args.arithmetic,
+                           clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else 1965.0)
+        roof["kernel"] = "k_render<3,3,hdr_merge,...> (stage A, the slowest rank's launches)"
+        mpix = W * H / 1e6
+        reps_sorted = sorted(reps)
+        e2e_best, e2e_med = reps_sorted[0] / e2e_steps, reps_sorted[len(reps) // 2] / e2e_steps
+        h2d_total = sum(r["h2d_bytes"] for r in per_rank)
+        line = {
+            "metric": METRIC, "value": mpix / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": c5_workload_name(args.scale, world), "frames_per_step": 1, "out_mpix_per_frame": mpix,
+                       "partition": "row bands of ONE panorama, one band per rank, sized by estimated cost (c5.plan_bands); "
+                                    "reference work splitting: lines x segments of one frame (zimt/wielding.h:251-265)",
+                       "c5": {"plan": args.c5_plan,
+                              "what": ("stage A merges only the rectangles of every position that this rank's band of stage B "
+                                       "samples (the voronoi winner is the position nearest in longitude: 49 % of each raster's "
+                                       "columns; rows by the band's latitudes) - the panorama is bit-identical to the one from "
+                                       "fully merged rasters (configs[] of the N=1 line: checksum_equals_full_merge)")
+                              if args.c5_plan == "needed" else "stage A merges every texel of every position",
+                              "bands": [list(b) for b in pl.bands]},
+                       "l2": "inputs_larger_than_l2 (per rank: bracket rectangles + merged rasters + band >> 126 MB)",
+                       "arithmetic": args.arithmetic,
+                       "parity": {"C5A": parity_record("C5A", args.arithmetic), "C5B": parity_record("C5B", args.arithmetic)},
+                       "value_scope": "stage A + brace + stage B, device-timed, brackets resident in HBM; max over ranks"},
+            "roofline": roof,
+            "e2e": {"value": mpix / e2e_best, "unit": UNIT, "h2d_bytes_per_step": int(h2d_total),
+                    "d2h_bytes_per_step": int(W * H * 12), "ms_per_step": e2e_best * 1e3, "steps": e2e_steps,
+                    "median_of_repetitions": {"value": mpix / e2e_med, "ms_per_step": e2e_med * 1e3,
+                                              "repetitions_ms_per_step": [round(t / e2e_steps * 1e3, 3) for t in reps]},
+                    "scope": "every step, every rank: H2D of its rectangles of the 18 bracket rasters from page-locked host "
+                             "memory (eu_source_write_rect) + brace + stage A + stage B + D2H of its band into ONE frame in "
+                             "shared page-locked host memory over its own PCIe link; the download of step n overlaps the "
+                             "upload of step n+1; wall clock, max over ranks, fastest of 3 repetitions",
+                    "breakdown_ms": {"upload_max": max(r["upload_ms"] for r in per_rank),
+                                     "download_max": max(r["download_ms"] for r in per_rank), "device_step": ms_per_step},
+                    "host_frame_checksum": host_checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "multi_gpu": {"broadcast_ms": 0.0,
+                          "source_distribution": "none: every rank uploads its own part of the sources (e2e.h2d_bytes_per_step is "
+                                                 "the sum over ranks; per_rank[].upload_ms)",
+                          "gather_ms": gather_ms,
+                          "gather": "beside the timed regions: NCCL gather of the bands into rank 0's HBM; the e2e path needs none "
+                                    "(every rank stores its band into the shared host frame, per_rank[].download_ms)",
+                          "collectives_in_timed_region": 0, "nccl_ranks": world, "per_rank": per_rank,
+                          "checksum_device_gather": dev_checksum, "checksum_host_frame": host_checksum,
+                          "frame_complete": dev_checksum == host_checksum},
+            "cpu_baseline": None, "checksum": host_checksum, "setup_s": setup_s, "run_s": time.perf_counter() - t_run0,
+        }
+        print(json.dumps(line))
+    barrier()
+    if registered:
+        rt.cudaHostUnregister(band_t.data_ptr())
+    pl.close()
+    eng.close()
+    del frame_t, frame_np, band_t
+    barrier()
+    if rank == 0:
+        try:
+            os.unlink(frame_path)
+        except OSError:
+            pass
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_c5(args):
+    """The unmodified reference on configs[4], on rank 0's host cores: a step = six `--synopsis hdr_merge --single 0` runs
+    (one per position) + the panorama run over their outputs, wall clock minus the file shim's raster I/O."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from envutil_b200 import c5, euf, synth, workloads
+    synth.WORKERS = max(1, min(16, os.cpu_count() or 1))
+    exe = os.path.join(ROOT, "oracle", "_ref", "envutil_ref_fast")
+    isa = "-march=x86-64-v3"
+    try:
+        flags = open("/proc/cpuinfo").read()
+        if all((" " + f) in flags for f in ("avx512f", "avx512vl", "avx512bw", "avx512dq", "avx512cd")) and os.path.exists(exe + "512"):
+            exe, isa = exe + "512", "-march=x86-64-v4"
+    except OSError:
+        pass
+    (w, h), (W, H) = c5.sizes(args.scale)
+    steps = max(1, min(args.steps, 2))
+    warm = 1 if args.warmup > 0 else 0
+    mpix = W * H / 1e6
+    ncores = os.cpu_count() or 1
+    need = 18 * w * h * 12 + 6 * w * h * 12 + (64 << 20)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil_free("/dev/shm") > need else None
+    with tempfile.TemporaryDirectory(prefix="eubench_c5_", dir=base) as d:
+        fs = workloads.c5_facets(args.scale)
+        paths = []
+        for i, f in enumerate(fs):
+            p = os.path.join(d, "bracket%02d.euf" % i)
+            euf.write_euf(p, f.image)
+            paths.append(p)
+            f.image = None
+        env_w = dict(os.environ)
+        env_nw = dict(os.environ, EUSHIM_NOWRITE="1")
+
+        def run(cmd, env):
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+            wall = time.perf_counter() - t0
+            if r.returncode != 0:
+                raise RuntimeError("reference failed: " + r.stderr[-1500:])
+            rd = re.findall(r"eushim: read time ([0-9.eE+-]+) ms", r.stdout)
+            wr = re.findall(r"eushim: write time ([0-9.eE+-]+) ms", r.stdout)
+            return wall - ((float(rd[-1]) if rd else 0.0) + (float(wr[-1]) if wr else 0.0)) / 1e3
+
+        from envutil_b200.job import FacetSpec
+        ts = []
+        for it in range(warm + steps):
+            tot = 0.0
+            merged = []
+            for pz in range(c5.POSITIONS):
+                sub = [FacetSpec(None, "rectilinear", c5.HFOV_DEG, yaw=c5.YAW_STEP_DEG * pz, eev=ev, width=w, height=h, nchannels=3)
+                       for ev in c5.EVS]
+                job, _ = workloads.c5_stage_a_geometry(sub, w, h)
+                outp = os.path.join(d, "merged%d.euf" % pz)
+                tot += run([exe, "-v"] + job.cli_args(paths[3 * pz:3 * pz + 3], outp), env_w)
+                merged.append(outp)
+            fsb = [FacetSpec(None, "rectilinear", c5.HFOV_DEG, yaw=c5.YAW_STEP_DEG * pz, width=w, height=h, nchannels=3)
+                   for pz in range(c5.POSITIONS)]
+            jobb, _ = workloads.c5_stage_b_geometry(fsb, args.scale)
+            tot += run([exe, "-v"] + jobb.cli_args(merged, os.path.join(d, "pano.euf")), env_nw)
+            if it >= warm:
+                ts.append(tot)
+    t = float(np.mean(ts))
+    build = ("oracle/_ref/%s: unmodified reference sources, g++ -O3 %s, zimt goading back-end (highway / Vc are not in this "
+             "image; the reference's default highway build may be faster)" % (os.path.basename(exe), isa))
+    cb = {"value": mpix / t, "unit": UNIT, "cores": ncores, "threads": 2 * ncores, "kind": "reference", "build": build,
+          "sample": "%d whole pipelines: 6 stage-A process runs + 1 stage-B run each = their payload()s, wall clock minus "
+                    "raster file I/O" % steps}
+    line = {"impl": "reference", "metric": METRIC, "value": mpix / t, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": c5_workload_name(args.scale, args.gpus), "frames_per_step": 1,
+                       "note": "CPU reference runs once on rank 0's host cores; steps/warmup bounded to %d/%d pipelines"
+                               % (steps, warm)},
+            "cpu_baseline": cb, "e2e": {"value": mpix / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def shutil_free(path):
+    import shutil
+    try:
+        return shutil.disk_usage(path).free
+    except OSError:
+        return 0
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
-        return reference_arm(args)
-    return ours(args)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        wl = args.workload if args.workload != "auto" else ("c2" if max(world, args.gpus) == 1 else "c5")
+        return reference_c5(args) if wl == "c5" else reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = args.workload if args.workload != "auto" else ("c2" if world == 1 else "c5")
+    return ours_c5(args) if wl == "c5" else ours(args)
 
 
 if __name__ == "__main__":

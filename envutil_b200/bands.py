@@ -47,6 +47,19 @@ def gather_bands(local, height, world, rank, dist, dst=0):
     return torch.cat(parts, dim=0)
 
 
+def gather_ragged(local, all_bands, rank, dist, dst=0):
+    """gather_bands for bands of ANY heights (cost-balanced partitions): all_bands = [(row0, row1)] per rank."""
+    import torch
+    tallest = max(r1 - r0 for r0, r1 in all_bands)
+    pad = torch.zeros((tallest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in all_bands] if rank == dst else None
+    dist.gather(pad, out, dst=dst)
+    if rank != dst:
+        return None
+    return torch.cat([out[r][: b[1] - b[0]] for r, b in enumerate(all_bands)], dim=0)
+
+
 class PeerFrame:
     """One frame in the HBM of rank `dst` that every rank renders its row band into (fused render +
     gather: the kernel's stores travel over NVLink, include/envutil_b200.h eu_frame_*). The owner

@@ -1420,7 +1420,7 @@ int eu_source_write_rect(eu_source_h s, const float* pixels, size_t src_pitch_fl
   const size_t wb = (size_t)(col1 - col0) * s->nch * sizeof(float);
   if (src_pitch_floats * sizeof(float) < wb) return fail(EU_ERR_ARGUMENT, "source pitch shorter than the rectangle's rows");
   float* dst = s->container + (size_t)(s->ly + row0) * s->pitch + (size_t)(s->lx + col0) * s->nch;
-  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : g.up_stream;
+  cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL is the legacy default stream, as for eu_render_rows
   cudaPointerAttributes pa;
   cudaMemcpyKind kind = cudaMemcpyHostToDevice;
   if (cudaPointerGetAttributes(&pa, pixels) == cudaSuccess) {
@@ -1430,7 +1430,6 @@ int eu_source_write_rect(eu_source_h s, const float* pixels, size_t src_pitch_fl
   }
   CK(cudaMemcpy2DAsync(dst, (size_t)s->pitch * sizeof(float), pixels, src_pitch_floats * sizeof(float), wb, row1 - row0, kind,
                        st));
-  if (!cuda_stream) CK(cudaStreamSynchronize(st));
   return EU_OK;
 }
 

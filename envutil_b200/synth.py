@@ -52,16 +52,31 @@ def _rows(h, rows_per_chunk=512):
         yield y0, min(h, y0 + rows_per_chunk)
 
 
+WORKERS = 1  # row chunks are independent: > 1 evaluates them on that many threads (numpy's ufuncs release the GIL)
+
+
+def _each(chunks, fn):
+    chunks = list(chunks)
+    if WORKERS <= 1 or len(chunks) < 2:
+        for c in chunks:
+            fn(*c)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=WORKERS) as ex:
+        list(ex.map(lambda c: fn(*c), chunks))
+
+
 def latlon(width, height=None, noise=0.05):
     """Full spherical (360x180) lat/lon image, width x width/2."""
     height = height or width // 2
     out = np.empty((height, width, 3), dtype=np.float32)
     lon = _centres(width, -np.pi, np.pi)
     lat = _centres(height, -np.pi / 2, np.pi / 2)
-    for y0, y1 in _rows(height):
+    def chunk(y0, y1):
         LON, LAT = np.meshgrid(lon, lat[y0:y1])
         idx = (np.arange(y0, y1, dtype=np.int64)[:, None] * width + np.arange(width, dtype=np.int64)[None, :])
         out[y0:y1] = scene(LON, LAT, idx, noise)
+    _each(_rows(height, 128 if WORKERS > 1 else 512), chunk)
     return out
 
 
@@ -83,8 +98,7 @@ def cubemap(face_px, biatan6=False, hfov_deg=90.0, noise=0.05):
     if biatan6:
         p = np.tan(p * (np.pi / 4.0))
     one = np.ones((1, 1))
-    for face in range(6):
-        for y0, y1 in _rows(w):
+    def chunk(face, y0, y1):
             P0, P1 = np.meshgrid(p, p[y0:y1])
             if face == 0:    # left
                 x, y, z = -one, P1, P0
@@ -103,6 +117,7 @@ def cubemap(face_px, biatan6=False, hfov_deg=90.0, noise=0.05):
             idx = ((face * w + np.arange(y0, y1, dtype=np.int64))[:, None] * w
                    + np.arange(w, dtype=np.int64)[None, :])
             out[face * w + y0: face * w + y1] = scene(lon, lat, idx, noise)
+    _each(((face, y0, y1) for face in range(6) for y0, y1 in _rows(w, 128 if WORKERS > 1 else 512)), chunk)
     return out
 
 
@@ -132,16 +147,20 @@ def rotation(yaw_deg=0.0, pitch_deg=0.0, roll_deg=0.0):
 
 
 def rectilinear_facet(width, height, hfov_deg, yaw_deg=0.0, pitch_deg=0.0, roll_deg=0.0,
-                      gain=1.0, noise=0.05, seed_offset=0):
+                      gain=1.0, noise=0.05, seed_offset=0, rows=None, cols=None):
     """Rectilinear photo of the scene taken by a camera with the given orientation;
-    gain scales the linear values before clamping to [0,1] (exposure bracket)."""
-    out = np.empty((height, width, 3), dtype=np.float32)
+    gain scales the linear values before clamping to [0,1] (exposure bracket).
+    rows=(r0, r1) / cols=(c0, c1): only that window of the width x height image - the very texels the whole image
+    has there (directions and noise are functions of the texel's position in the whole image)."""
+    r0, r1 = rows if rows is not None else (0, height)
+    c0, c1 = cols if cols is not None else (0, width)
+    out = np.empty((r1 - r0, c1 - c0, 3), dtype=np.float32)
     ex = np.tan(np.radians(hfov_deg) / 2.0)
     ey = ex * height / width
-    px = _centres(width, -ex, ex)
+    px = _centres(width, -ex, ex)[c0:c1]
     py = _centres(height, -ey, ey)
     R = rotation(yaw_deg, pitch_deg, roll_deg)
-    for y0, y1 in _rows(height):
+    def chunk(y0, y1):
         X, Y = np.meshgrid(px, py[y0:y1])
         Z = np.ones_like(X)
         wx = X * R[0, 0] + Y * R[1, 0] + Z * R[2, 0]
@@ -149,7 +168,9 @@ def rectilinear_facet(width, height, hfov_deg, yaw_deg=0.0, pitch_deg=0.0, roll_
         wz = X * R[0, 2] + Y * R[1, 2] + Z * R[2, 2]
         lon, lat = _dir_to_lonlat(wx, wy, wz)
         idx = (np.arange(y0, y1, dtype=np.int64)[:, None] * width
-               + np.arange(width, dtype=np.int64)[None, :] + seed_offset)
+               + np.arange(c0, c1, dtype=np.int64)[None, :] + seed_offset)
         v = scene(lon, lat, idx, noise).astype(np.float64) * gain
-        out[y0:y1] = np.clip(v, 0.0, 1.0)
+        out[y0 - r0:y1 - r0] = np.clip(v, 0.0, 1.0)
+    step = 128 if WORKERS > 1 else 512
+    _each(((y0, min(r1, y0 + step)) for y0 in range(r0, r1, step)), chunk)
     return out

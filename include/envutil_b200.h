@@ -267,7 +267,8 @@ int eu_source_commit(eu_source_h s, const eu_facet_t* f, const eu_opts_t* o, voi
                      eu_timing_t* t);
 /* Fill part of a reserved source from a raster in host (page-locked, for a truly asynchronous copy) or device
  * memory: the rectangle rows [row0,row1) x columns [col0,col1) of the image; `pixels` points at its first texel,
- * rows src_pitch_floats apart. Enqueued on cuda_stream (NULL: the library's upload stream, and the call blocks).
+ * rows src_pitch_floats apart. Enqueued on cuda_stream (asynchronous for page-locked host memory; pageable memory is
+ * staged before the call returns).
  * Ranks of a multi-GPU job upload just the part of every source their band of the output can see. Rows and
  * columns never written read as zero. f and o given to eu_source_commit must be those given to
  * eu_source_reserve; with t == NULL eu_source_commit only enqueues (later work on cuda_stream is ordered after it). */

@@ -287,8 +287,7 @@ CLI_EXTRAS = {
 
 def _edge_jobs():
     """Degenerate sizes: one-pixel and ragged targets, sources smaller than a spline window, tiny cube
-    faces. CPU: oracle == reference (golden). GPU: tests/test_gpu_parity.py::test_edge_jobs (added without a
-    GPU run at hand, therefore not yet part of the must-pass set)."""
+    faces. CPU: oracle == reference (golden). GPU: tests/test_gpu_parity.py::test_edge_jobs."""
     rng = np.random.default_rng(5)
     ll = lambda w, h: rng.random((h, w, 3), dtype=np.float32)
     cm = lambda f: rng.random((6 * f, f, 3), dtype=np.float32)
@@ -300,8 +299,7 @@ def _edge_jobs():
         "edge_rect3x2_src_d2_tw2": Job([FacetSpec(rng.random((2, 3, 3), dtype=np.float32), "rectilinear", 50.0)],
                                        "rectilinear", 70.0, 31, 7, degree=2, twine=2),
         "edge_cube_target_w1": Job([FacetSpec(ll(16, 8), "spherical", 360.0)], "cubemap", 90.0, 1),
-        # single-row / single-column rasters: zimt gates that axis as CONSTANT (always coordinate 0). The oracle
-        # restates it; the library still refuses such rasters (EU_ERR_UNSUPPORTED), so the GPU leg xfails
+        # single-row / single-column rasters: zimt gates that axis as CONSTANT (always coordinate 0)
         "edge_ll2x1_src_d1": Job([FacetSpec(ll(2, 1), "spherical", 360.0)], "spherical", 360.0, 16, 8),
         "edge_rect1x5_src_d3": Job([FacetSpec(rng.random((5, 1, 3), dtype=np.float32), "rectilinear", 30.0)], "spherical",
                                    360.0, 16, 8, degree=3),
@@ -313,6 +311,29 @@ def _edge_jobs():
 
 
 EDGE_JOBS = _edge_jobs()
+
+
+def _odd_cube_jobs():
+    """Cubemaps with an ODD face width: the support fill then reads frame texels it is rewriting, so its result
+    depends on the order zimt::process works in (16-pixel vectors, line after line; DESIGN.md section 2). The
+    oracle restates that order and equals the reference wherever the reference is deterministic; the kernels
+    (stage.cu, k_cm_fill_ordered) are held to the oracle."""
+    rng = np.random.default_rng(9)
+    cm = lambda f: rng.random((6 * f, f, 3), dtype=np.float32)
+    O = {
+        "odd_cm5_sph_d1": Job([FacetSpec(cm(5), "cubemap", 90.0)], "spherical", 360.0, 64, 32),
+        "odd_cm35_sph_d1": Job([FacetSpec(cm(35), "cubemap", 90.0)], "spherical", 360.0, 160, 80),
+        "odd_cm47_rect_d3": Job([FacetSpec(cm(47), "cubemap", 90.0)], "rectilinear", 100.0, 96, 64, degree=3, yaw=40.0,
+                                pitch=50.0),
+        "odd_ba9_sph_d1_tw2": Job([FacetSpec(cm(9), "biatan6", 90.0)], "spherical", 360.0, 48, 24, twine=2),
+        "odd_cm101_hfov96_sph_d1": Job([FacetSpec(cm(101), "cubemap", 96.0)], "spherical", 360.0, 200, 100),
+    }
+    for k, v in O.items():
+        v.name = k
+    return O
+
+
+ODD_CUBE_JOBS = _odd_cube_jobs()
 
 # --split FORMAT runs of the reference CLI (one output per facet, the solo facet excepted): name ->
 # (base job, extra command-line arguments). Golden: manifest[name]["outputs"][facet] = shape + sha256.

@@ -84,6 +84,8 @@ def main():
     a = ap.parse_args()
     a.padded = [int(v) for v in a.padded.split(",")]
     want = a.configs.split(",")
+    from envutil_b200 import synth
+    synth.WORKERS = max(1, min(16, os.cpu_count() or 1))
     eng = Engine(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     s = a.scale

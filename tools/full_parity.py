@@ -3,6 +3,8 @@
 binaries under oracle/_ref/ (run here, on the box's host cores) - every config, every pixel.
 
   python tools/full_parity.py [--configs C1,C2,C3a,C3b,C4,C5A,C5B] [--out gpurun_out/parity_full.json]
+writes <out>_exact.json and <out>_contracted.json: the same frames rendered with both arithmetics of the library
+(EU_OPT_CONTRACTED), each compared with the same reference frames.
 
 Per config one record:
   vs_pinned   GPU frame against oracle/_ref/envutil_ref_pm (the reference sources with the elementary
@@ -36,12 +38,12 @@ EPS = 1e-3
 TOL = 1e-5
 
 
-def rel_stats(a, b, mask=None, chunk_rows=512):
-    """max / RMS of |a-b| / max(|b|, EPS) over all floats (row chunks: the frames are GB-sized), count of
-    floats that differ, count beyond TOL. mask: H x W bool, pixels to leave out."""
-    h = a.shape[0]
-    mx, ss, n, ndiff, nbeyond, mabs = 0.0, 0.0, 0, 0, 0, 0.0
-    for y0 in range(0, h, chunk_rows):
+def rel_stats(a, b, mask=None, chunk_rows=256):
+    """max / RMS of |a-b| / max(|b|, EPS) over all floats (row chunks on a few threads: the frames are GB-sized),
+    count of floats that differ, count beyond TOL. mask: H x W bool, pixels to leave out."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def part(y0):
         x = a[y0:y0 + chunk_rows].astype(np.float64)
         y = b[y0:y0 + chunk_rows].astype(np.float64)
         d = np.abs(x - y)
@@ -51,15 +53,15 @@ def rel_stats(a, b, mask=None, chunk_rows=512):
             rel = rel[keep]
             d = d[keep]
         if rel.size == 0:
-            continue
-        mx = max(mx, float(rel.max()))
-        mabs = max(mabs, float(d.max()))
-        ss += float((rel * rel).sum())
-        n += rel.size
-        ndiff += int((d != 0).sum())
-        nbeyond += int((rel > TOL).sum())
-    return {"max_rel": mx, "rms_rel": (ss / max(n, 1)) ** 0.5, "max_abs": mabs, "n_diff": ndiff, "n_beyond_1e-5": nbeyond,
-            "n": n}
+            return 0.0, 0.0, 0.0, 0, 0, 0
+        return (float(rel.max()), float(d.max()), float((rel * rel).sum()), int(rel.size), int((d != 0).sum()),
+                int((rel > TOL).sum()))
+    with ThreadPoolExecutor(max_workers=max(1, min(16, os.cpu_count() or 1))) as ex:
+        parts = list(ex.map(part, range(0, a.shape[0], chunk_rows)))
+    n = sum(p[3] for p in parts)
+    return {"max_rel": max(p[0] for p in parts), "rms_rel": (sum(p[2] for p in parts) / max(n, 1)) ** 0.5,
+            "max_abs": max(p[1] for p in parts), "n_diff": sum(p[4] for p in parts),
+            "n_beyond_1e-5": sum(p[5] for p in parts), "n": n}
 
 
 def run_reference(job, kind, workdir, paths=None, tag="out"):
@@ -84,48 +86,62 @@ def run_reference(job, kind, workdir, paths=None, tag="out"):
     return img, dt, paths
 
 
-def parity_of(engine, job, workdir, want_libm=True, keep_gpu=False, log=None):
-    """GPU frame of the job against both reference builds. Returns the record (and the GPU frame)."""
+ARITHMETICS = ("exact", "contracted")
+
+
+def parity_of(engine, job, workdir, want_libm=True, keep=False, log=None):
+    """GPU frames of the job - both arithmetics of the library - against both reference builds.
+    Returns ({arithmetic: record}, pinned reference frame or None)."""
     st = job.structs(engine.lib)
-    t0 = time.perf_counter()
     hs = engine.stage(job, st)
+    gpu = {}
     try:
-        gpu = engine.render(job, sources=hs, structs=st)
+        for ar in ARITHMETICS:
+            job.contracted = ar == "contracted"
+            t0 = time.perf_counter()
+            gpu[ar] = (engine.render(job, sources=hs, structs=job.structs(engine.lib)), time.perf_counter() - t0)
+        job.contracted = None
         tie = engine.tie_plane(job, hs, st, 8)
     finally:
+        job.contracted = None
         engine.release(hs)
-    gpu_s = time.perf_counter() - t0
     pm, pm_s, paths = run_reference(job, "pm", workdir)
-    rec = {"config": job.name, "out": "%dx%d" % (gpu.shape[1], gpu.shape[0]), "floats": int(gpu.size),
-           "vs_pinned": rel_stats(gpu, pm), "ref_pm_s": pm_s, "gpu_path_s": gpu_s,
-           "tie_pixels": int(tie.sum()) if tie is not None else 0}
-    if log:
-        log("%s vs_pinned %s" % (job.name, rec["vs_pinned"]))
+    lm, lm_s = (None, None)
     if want_libm:
         lm, lm_s, _ = run_reference(job, "libm", workdir, paths)
-        rec["vs_libm"] = rel_stats(gpu, lm)
-        if tie is not None and tie.any():
-            m = rel_stats(gpu, lm, mask=tie.astype(bool))
-            rec["vs_libm"]["masked"] = {"pixels": int(tie.sum()), "max_rel": m["max_rel"], "rms_rel": m["rms_rel"],
-                                        "n_beyond_1e-5": m["n_beyond_1e-5"]}
-        else:
-            rec["vs_libm"]["masked"] = {"pixels": 0, "max_rel": rec["vs_libm"]["max_rel"],
-                                        "rms_rel": rec["vs_libm"]["rms_rel"],
-                                        "n_beyond_1e-5": rec["vs_libm"]["n_beyond_1e-5"]}
-        rec["ref_self"] = rel_stats(pm, lm)
-        rec["ref_libm_s"] = lm_s
-        if log:
-            log("%s vs_libm %s" % (job.name, rec["vs_libm"]))
-        del lm
     for p in paths:
         os.unlink(p)
-    return (rec, gpu, pm) if keep_gpu else (rec, None, None)
+    ref_self = rel_stats(pm, lm) if want_libm else None
+    recs = {}
+    for ar in ARITHMETICS:
+        frame, gpu_s = gpu[ar]
+        rec = {"config": job.name, "out": "%dx%d" % (frame.shape[1], frame.shape[0]), "floats": int(frame.size),
+               "vs_pinned": rel_stats(frame, pm), "ref_pm_s": pm_s, "gpu_render_and_download_s": gpu_s,
+               "tie_pixels": int(tie.sum()) if tie is not None else 0}
+        if want_libm:
+            rec["vs_libm"] = rel_stats(frame, lm)
+            if tie is not None and tie.any():
+                m = rel_stats(frame, lm, mask=tie.astype(bool))
+                rec["vs_libm"]["masked"] = {"pixels": int(tie.sum()), "max_rel": m["max_rel"], "rms_rel": m["rms_rel"],
+                                            "n_beyond_1e-5": m["n_beyond_1e-5"]}
+            else:
+                rec["vs_libm"]["masked"] = {"pixels": 0, "max_rel": rec["vs_libm"]["max_rel"],
+                                            "rms_rel": rec["vs_libm"]["rms_rel"],
+                                            "n_beyond_1e-5": rec["vs_libm"]["n_beyond_1e-5"]}
+            rec["ref_self"] = ref_self
+            rec["ref_libm_s"] = lm_s
+        recs[ar] = rec
+        if log:
+            log("%s %s vs_pinned %s" % (job.name, ar, rec["vs_pinned"]))
+            if want_libm:
+                log("%s %s vs_libm %s" % (job.name, ar, rec["vs_libm"]))
+    back = {ar: gpu[ar][0] for ar in ARITHMETICS} if keep else None
+    return recs, (pm if keep else None), back
 
 
 def configs_iter(engine, want, workdir, scale=1, want_libm=True, log=None):
-    """Yields one record per config, in BASELINE order. C3b takes the reference's own C3a output as its
-    input (both legs of the round trip are then compared on identical inputs), C5B the reference's
-    stage-A results."""
+    """Yields {arithmetic: record} per config, in BASELINE order. C3b takes the reference's own C3a output as its
+    input (both legs of the round trip are then compared on identical inputs), C5B the reference's stage-A results."""
     if "C1" in want:
         job, _ = workloads.c1(scale)
         yield parity_of(engine, job, workdir, want_libm, log=log)[0]
@@ -134,45 +150,48 @@ def configs_iter(engine, want, workdir, scale=1, want_libm=True, log=None):
         yield parity_of(engine, job, workdir, want_libm, log=log)[0]
     if "C3a" in want or "C3b" in want:
         job, _ = workloads.c3a(scale)
-        rec, gpu, pm = parity_of(engine, job, workdir, want_libm, keep_gpu=True, log=log)
+        recs, pm, _ = parity_of(engine, job, workdir, want_libm, keep=True, log=log)
         ll = job.facets[0].image
         if "C3a" in want:
-            yield rec
+            yield recs
         if "C3b" in want:
-            del gpu
             job2, _ = workloads.c3b(pm)
-            rec2, back, back_ref = parity_of(engine, job2, workdir, want_libm, keep_gpu=True, log=log)
-            e = rel_round_trip(back, ll)
+            recs2, back_ref, back = parity_of(engine, job2, workdir, want_libm, keep=True, log=log)
             e_ref = rel_round_trip(back_ref, ll)
-            rec2["round_trip"] = {"gpu": e, "reference": e_ref}
-            yield rec2
+            for ar in ARITHMETICS:
+                recs2[ar]["round_trip"] = {"gpu": rel_round_trip(back[ar], ll), "reference": e_ref}
+            yield recs2
     if "C4" in want:
         job, _ = workloads.c4(scale)
         yield parity_of(engine, job, workdir, want_libm, log=log)[0]
     if "C5A" in want or "C5B" in want:
         fs = workloads.c5_facets(scale)
-        merged, yaws, recs = [], [], []
+        merged, yaws, per = [], [], []
         for k in range(0, len(fs), 3):
             job, _ = workloads.c5_stage_a(fs[k:k + 3])
             job.name = "C5A[%d]" % (k // 3)
             # every position for the reference's merged image (stage B's input); libm only on the first
-            rec, gpu, pm = parity_of(engine, job, workdir, want_libm and k == 0, keep_gpu=True, log=log)
-            recs.append(rec)
+            recs, pm, _ = parity_of(engine, job, workdir, want_libm and k == 0, keep=True, log=log)
+            per.append(recs)
             merged.append(pm)
             yaws.append(fs[k].yaw)
-            del gpu
         if "C5A" in want:
-            agg = {"config": "C5A", "out": "6 x %s" % recs[0]["out"], "floats": sum(r["floats"] for r in recs),
-                   "vs_pinned": {"max_rel": max(r["vs_pinned"]["max_rel"] for r in recs),
-                                 "rms_rel": float(np.sqrt(np.mean([r["vs_pinned"]["rms_rel"] ** 2 for r in recs]))),
-                                 "n_diff": sum(r["vs_pinned"]["n_diff"] for r in recs),
-                                 "n_beyond_1e-5": sum(r["vs_pinned"]["n_beyond_1e-5"] for r in recs),
-                                 "n": sum(r["vs_pinned"]["n"] for r in recs)},
-                   "tie_pixels": 0, "positions": recs}
-            if "vs_libm" in recs[0]:
-                agg["vs_libm"] = dict(recs[0]["vs_libm"], note="position 0 only")
-                agg["ref_self"] = recs[0]["ref_self"]
-            yield agg
+            out = {}
+            for ar in ARITHMETICS:
+                rs = [r[ar] for r in per]
+                agg = {"config": "C5A", "out": "6 x %s" % rs[0]["out"], "floats": sum(r["floats"] for r in rs),
+                       "vs_pinned": {"max_rel": max(r["vs_pinned"]["max_rel"] for r in rs),
+                                     "rms_rel": float(np.sqrt(np.mean([r["vs_pinned"]["rms_rel"] ** 2 for r in rs]))),
+                                     "max_abs": max(r["vs_pinned"]["max_abs"] for r in rs),
+                                     "n_diff": sum(r["vs_pinned"]["n_diff"] for r in rs),
+                                     "n_beyond_1e-5": sum(r["vs_pinned"]["n_beyond_1e-5"] for r in rs),
+                                     "n": sum(r["vs_pinned"]["n"] for r in rs)},
+                       "tie_pixels": 0, "positions": rs}
+                if "vs_libm" in rs[0]:
+                    agg["vs_libm"] = dict(rs[0]["vs_libm"], note="position 0 only")
+                    agg["ref_self"] = rs[0]["ref_self"]
+                out[ar] = agg
+            yield out
         if "C5B" in want:
             del fs
             job, _ = workloads.c5_stage_b(merged, yaws, scale=scale)
@@ -196,29 +215,31 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "parity_full.json"))
     ap.add_argument("--no-libm", action="store_true")
     a = ap.parse_args()
-    from envutil_b200 import capi
     from envutil_b200.engine import Engine
     eng = Engine(0)
     base = "/dev/shm" if os.path.isdir("/dev/shm") else None
     workdir = tempfile.mkdtemp(prefix="euparity_", dir=base)
-    recs = []
+    recs = {ar: [] for ar in ARITHMETICS}
     t0 = time.time()
 
     def log(s):
         print("[%6.1f s] %s" % (time.time() - t0, s), file=sys.stderr, flush=True)
     try:
-        for rec in configs_iter(eng, a.configs.split(","), workdir, a.scale, not a.no_libm, log):
-            recs.append(rec)
-            print(json.dumps(rec), flush=True)
+        for both in configs_iter(eng, a.configs.split(","), workdir, a.scale, not a.no_libm, log):
+            for ar in ARITHMETICS:
+                recs[ar].append(both[ar])
+            print(json.dumps(both), flush=True)
     finally:
         shutil.rmtree(workdir, ignore_errors=True)
         eng.close()
-    os.makedirs(os.path.dirname(a.out), exist_ok=True)
-    with open(a.out, "w") as f:
-        json.dump({"arithmetic": capi.ARITHMETIC if hasattr(capi, "ARITHMETIC") else "exact", "scale": a.scale,
-                   "eps": EPS, "tolerance": TOL, "cores": os.cpu_count(), "configs": recs,
-                   "reference_builds": {"pinned": "oracle/_ref/envutil_ref_pm (-O2 -ffp-contract=off, eu_math.h interposed)",
-                                        "libm": "oracle/_ref/envutil_ref (-O2 -ffp-contract=off, stock libm)"}}, f, indent=1)
+    os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+    stem = a.out[:-5] if a.out.endswith(".json") else a.out
+    for ar in ARITHMETICS:
+        with open("%s_%s.json" % (stem, ar), "w") as f:
+            json.dump({"arithmetic": ar, "scale": a.scale, "eps": EPS, "tolerance": TOL, "cores": os.cpu_count(),
+                       "configs": recs[ar], "seconds": time.time() - t0,
+                       "reference_builds": {"pinned": "oracle/_ref/envutil_ref_pm (-O2 -ffp-contract=off, eu_math.h interposed)",
+                                            "libm": "oracle/_ref/envutil_ref (-O2 -ffp-contract=off, stock libm)"}}, f, indent=1)
     return 0
 
 
