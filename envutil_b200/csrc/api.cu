@@ -213,6 +213,32 @@ bool known_source(eu_source_h s) {
   return false;
 }
 
+// dev_div_const (eu_device.cuh): is  q = x * rcp;  r = fma(-q, y, x);  fma(r, rcp, q)  with rcp = RN(1 / y) the correctly
+// rounded x / y for EVERY x? Checked by exhaustion over the 2^23 significands of one binade of x (the three
+// operations and the division all scale exactly with the exponent of x, away from the subnormal and overflow
+// ranges; the sign is symmetric). About 10 ms per distinct divisor, remembered.
+bool exact_by_reciprocal(float y) {
+  static std::map<uint32_t, bool> known;
+  uint32_t key;
+  memcpy(&key, &y, 4);
+  auto it = known.find(key);
+  if (it != known.end()) return it->second;
+  bool ok = std::isfinite(y) && y != 0.0f && fabsf(y) > 1e-18f && fabsf(y) < 1e18f;
+  if (ok) {
+    const float rcp = 1.0f / y;
+    for (uint32_t m = 0; m < (1u << 23) && ok; m++) {
+      const uint32_t bits = 0x3f800000u | m;  // 1.0 <= x < 2.0
+      float x;
+      memcpy(&x, &bits, 4);
+      const float q = x * rcp;
+      const float r = fmaf(-q, y, x);
+      ok = fmaf(r, rcp, q) == x / y;
+    }
+  }
+  known[key] = ok;
+  return ok;
+}
+
 // facet -> FacetDev: what source_t / mount_t / cubemap_view_t / environment hold
 // (environment.h:594-645,970-1006,1428-1461,1786-1860), narrowed as the functors narrow it
 int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, FacetDev& F, const eu_facet_t* ft = nullptr) {
@@ -236,6 +262,10 @@ int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, Fac
   F.ext_h = (float)(f->y1 - f->y0);
   F.total_w = (float)f->width;
   F.total_h = (float)f->height;
+  F.rcp_w = 1.0f / F.ext_w;
+  F.rcp_h = 1.0f / F.ext_h;
+  F.fast_div = 0;
+  if (s->kind == EU_SRC_MOUNT) F.fast_div = (exact_by_reciprocal(F.ext_w) ? 1 : 0) | (exact_by_reciprocal(F.ext_h) ? 2 : 0);
   {  // window extent, environment.h:607-618: x0 + (offset / total_width) * (x1 - x0) etc., in double,
      // narrowed for the float compares of test_crd (:970-978). BOTH axes use widths (sic).
     double wx = f->x1 - f->x0, wy = f->y1 - f->y0;
@@ -552,6 +582,15 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     if (rc) return rc;
     plan.launches += 2;
   }
+  for (int i = 1; i < nf; i++) {  // same_geometry: FacetDev::same_geom
+    FacetDev a = F[i - 1], b = F[i];
+    a.src.core = b.src.core = nullptr;
+    a.brighten = b.brighten = 0.0f;
+    a.hdr_optimum = b.hdr_optimum = 0.0f;
+    a.hdr_kind = b.hdr_kind = 0;
+    a.same_geom = b.same_geom = 0;
+    F[i].same_geom = memcmp(&a, &b, sizeof(FacetDev)) == 0 ? 1 : 0;
+  }
   if (mode == EU_MODE_HDR) {  // _hdr_merge_syn ctor, envutil_payload.cc:1354-1375
     float lowest = 100000.0f, highest = -1.0f;
     int lo = -1, hi = -1;
@@ -591,6 +630,10 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     }
     CK(cudaMemcpyAsync(mem + EU_SLOT_FACETS_BYTES, tp.data(), sizeof(float) * tp.size(), cudaMemcpyHostToDevice, cs));
     P.taps = reinterpret_cast<const float*>(mem + EU_SLOT_FACETS_BYTES);
+    if (n_taps <= EU_INLINE_TAPS) {
+      memcpy(P.ptaps, tp.data(), sizeof(float) * tp.size());
+      P.taps_inline = 1;
+    }
   }
   // stepper tables: recomputed only for a target that is not among the recent ones
   const int ow = out_width(t), oh = out_height(t);
@@ -646,11 +689,15 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   P.spec = 0;
   for (int sp = 1; sp < EU_N_SPECS && !P.spec; sp++) {
     const RenderSpec& rs = eu_render_specs[sp];
-    bool fits = (rs.tproj < 0 || rs.tproj == P.trg.projection) && (rs.tnorm < 0 || rs.tnorm == P.trg.normalize);
+    bool fits = (rs.tproj < 0 || rs.tproj == P.trg.projection) && (rs.tnorm < 0 || rs.tnorm == P.trg.normalize) &&
+                n_taps <= EU_INLINE_TAPS;  // their twining filter travels in the parameter block
     for (int i = 0; i < nf && fits; i++) {
       if (mode == EU_MODE_SINGLE && i != first) continue;
       const FacetDev& f = F[i];
-      fits = !f.has_lcp && !f.generic && (rs.skind < 0 || rs.skind == f.kind) &&
+      // the kernels compiled for a shape also assume 32-bit window offsets and proven reciprocal divisions
+      const bool small = (long long)sources[i]->pitch * sources[i]->chh < (1ll << 31);
+      fits = small && (f.kind != EU_SRC_MOUNT || f.fast_div == 3) && !f.has_lcp && !f.generic &&
+             (rs.skind < 0 || rs.skind == f.kind) &&
              (rs.sproj < 0 || rs.sproj == f.projection) && (rs.bc0 < 0 || rs.bc0 == f.src.bc0) &&
              (rs.bc1 < 0 || rs.bc1 == f.src.bc1) && (rs.mask_always < 0 || rs.mask_always == f.mask_always);
     }

@@ -37,6 +37,7 @@ __device__ __forceinline__ void dev_spec_facet(FacetDev& F) {
   if constexpr (s.bc1 >= 0) F.src.bc1 = s.bc1;
   if constexpr (s.mask_always >= 0) F.mask_always = s.mask_always;
   if constexpr (SP != 0) F.has_lcp = 0;
+  if constexpr (SP != 0) F.fast_div = 3;  // proven for every facet of a job that matches a shape (api.cu)
 }
 template <int SP>
 __device__ __forceinline__ decltype(auto) dev_facet_at(const FacetDev* __restrict__ fa, int i) {
@@ -388,9 +389,16 @@ __device__ __forceinline__ void dev_mount_coordinate(const FacetDev& F, const fl
 }
 
 // source_t::test_crd (environment.h:970-978) + the z > 0 test of rectilinear mounts (:1123-1127)
+// A ray the generic stepper has invalidated - (0, 0, -inf), normalised to (0, 0, NaN) - misses every mounted image in
+// the reference: its NaN is the x86 default NaN, whose SIGN BIT IS SET, so atan2(0, NaN) takes the "x negative"
+// branch and yields pi - a latitude no image covers (the other projections produce NaN coordinates, which fail
+// every comparison). NVIDIA GPUs produce the positive canonical NaN, atan2(0, NaN) would be 0 and the ray would
+// hit the image centre: hence the explicit test. (Found by the random sweep: a `--single` job on a translated
+// facet, seed 12 job 136.)
 __device__ __forceinline__ bool dev_mount_mask(const FacetDev& F, const float r[3], const float c[2]) {
   bool m = (c[0] >= F.win_x0) && (c[0] <= F.win_x1) && (c[1] >= F.win_y0) && (c[1] <= F.win_y1);
   if (F.projection == EU_RECTILINEAR) m = m && (r[2] > 0.0f);
+  else m = m && (r[2] == r[2]);
   return m;
 }
 
@@ -609,13 +617,17 @@ __device__ __forceinline__ void dev_window_eval(const float* __restrict__ p0, in
 }
 
 // safe evaluator = mapper + evaluator (zimt/eval.h:2039-2164, :1237-1300), gathering from HBM
-template <int NCH, int TS, int DEG, int SPACE = 0>
+// I32: the container holds fewer than 2^31 floats, so the window's offset from the core fits 32 bits (the plan
+// builder checks that before it picks a kernel compiled this way): one 64-bit multiply-add instead of three
+template <int NCH, int TS, int DEG, int SPACE = 0, bool I32 = false>
 __device__ __forceinline__ void dev_spline_eval(const SourceDev& S, int degree, const float* __restrict__ wmat,
                                                 float cx, float cy, float out[NCH]) {
   if constexpr (DEG >= 0) degree = DEG;
   Located L = dev_locate(S, degree, cx, cy);
   const int h2 = degree / 2;
-  const float* p0 = S.core + (ptrdiff_t)(L.iy - h2) * S.stride + (ptrdiff_t)(L.ix - h2) * TS;
+  const float* p0;
+  if constexpr (I32) p0 = S.core + ((L.iy - h2) * S.stride + (L.ix - h2) * TS);
+  else p0 = S.core + (ptrdiff_t)(L.iy - h2) * S.stride + (ptrdiff_t)(L.ix - h2) * TS;
   dev_window_eval<NCH, TS, DEG, SPACE>(p0, S.stride, degree, wmat, L.fx, L.fy, out);
 }
 
@@ -639,6 +651,21 @@ __device__ __forceinline__ void dev_cubeface(const float c[3], int& face, float 
   }
 }
 
+// x / y for a divisor that is a constant of the facet: q = x * RN(1/y), one exact residual (fma), one correction
+// (fma) - Markstein's sequence, three instructions where IEEE division costs ten. It yields the correctly rounded
+// quotient RN(x / y), i.e. the very bits of `x / y`, whenever the host has PROVEN that for this y: the set-up code
+// runs the sequence over all 2^23 significands of x against the division (api.cu, exact_by_reciprocal; the
+// result scales exactly with the exponent of x, and the operands here are far from the subnormal and overflow
+// ranges) and sets `ok` only then. Otherwise the division itself is used.
+__device__ __forceinline__ float dev_div_const(float x, float y, float rcp, int ok) {
+  if (ok) {
+    float q = x * rcp;
+    float r = __fmaf_rn(-q, y, x);
+    return __fmaf_rn(r, rcp, q);
+  }
+  return x / y;
+}
+
 // First half of environment::eval (environment.h:1821-1842): ray -> spline coordinate of the
 // facet's source, via mount_t (:1172-1196, md_to_spline :988-1006) or cubemap_view_t
 // (:1452-1486). Returns false when the ray misses a mounted image; `face` = cube face or -1.
@@ -650,12 +677,12 @@ __device__ __forceinline__ bool dev_facet_coordinate(const FacetDev& F, const fl
     dev_mount_coordinate(F, r, c);
     if (!dev_mount_mask(F, r, c)) return false;
     float ix = (float)((double)c[0] - F.ext_x0);
-    ix /= F.ext_w;
+    ix = dev_div_const(ix, F.ext_w, F.rcp_w, F.fast_div & 1);
     ix *= F.total_w;
     ix -= .5f;
     ix = ix - F.win_xoff;
     float iy = (float)((double)c[1] - F.ext_y0);
-    iy /= F.ext_h;
+    iy = dev_div_const(iy, F.ext_h, F.rcp_h, F.fast_div & 2);
     iy *= F.total_h;
     iy -= .5f;
     iy = iy - F.win_yoff;
@@ -691,7 +718,7 @@ __device__ __forceinline__ void dev_brighten(const FacetDev& F, float px[NCH]) {
 }
 
 // environment::eval, gathering from HBM. Returns the cube face hit, or -1.
-template <int NCH, int TS, int DEG>
+template <int NCH, int TS, int DEG, bool I32 = false>
 __device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, const float* __restrict__ wmat,
                                               const float r[3], float px[NCH]) {
   int face;
@@ -701,9 +728,33 @@ __device__ __forceinline__ int dev_facet_eval(const FacetDev& F, int degree, con
     for (int i = 0; i < NCH; i++) px[i] = 0.0f;
     return -1;
   }
-  dev_spline_eval<NCH, TS, DEG>(F.src, degree, wmat, cx, cy, px);
+  dev_spline_eval<NCH, TS, DEG, 0, I32>(F.src, degree, wmat, cx, cy, px);
   dev_brighten<NCH>(F, px);
   return face;
+}
+
+// environment::eval in two halves, for callers that evaluate several facets of IDENTICAL geometry (the exposure
+// brackets of one camera position under hdr_merge): where the ray lands is computed once, the window is read
+// from each facet's own container. Same operations in the same order as dev_facet_eval, hence the same bits.
+template <int DEG>
+__device__ __forceinline__ bool dev_facet_locate(const FacetDev& F, int degree, const float r[3], Located& L) {
+  int face;
+  float cx, cy;
+  if (!dev_facet_coordinate(F, r, face, cx, cy)) return false;
+  if constexpr (DEG >= 0) degree = DEG;
+  L = dev_locate(F.src, degree, cx, cy);
+  return true;
+}
+template <int NCH, int TS, int DEG, bool I32>
+__device__ __forceinline__ void dev_facet_window(const FacetDev& F, int degree, const float* __restrict__ wmat,
+                                                 const Located& L, float px[NCH]) {
+  if constexpr (DEG >= 0) degree = DEG;
+  const int h2 = degree / 2;
+  const float* p0;
+  if constexpr (I32) p0 = F.src.core + ((L.iy - h2) * F.src.stride + (L.ix - h2) * TS);
+  else p0 = F.src.core + (ptrdiff_t)(L.iy - h2) * F.src.stride + (ptrdiff_t)(L.ix - h2) * TS;
+  dev_window_eval<NCH, TS, DEG, 0>(p0, F.src.stride, degree, wmat, L.fx, L.fy, px);
+  dev_brighten<NCH>(F, px);
 }
 
 // ---- the general build: any mix of channel counts and texel strides, degree at run time ------

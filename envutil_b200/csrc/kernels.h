@@ -23,6 +23,7 @@ cudaError_t eu_launch_render_c3p(const RenderParams& P, cudaStream_t st);
 cudaError_t eu_launch_render_c4(const RenderParams& P, cudaStream_t st);
 // kernels compiled for one job shape (render_spec.cu); false: none fits, use the general ones
 bool eu_launch_render_spec(const RenderParams& P, cudaStream_t st);
+bool eu_launch_render_spec4(const RenderParams& P, cudaStream_t st);  // 16-byte RGB texels
 // the same translation units compiled with -DEU_CONTRACT_WINDOW (RenderParams::arith == 1)
 cudaError_t eu_launch_render_c1_fma(const RenderParams& P, cudaStream_t st);
 cudaError_t eu_launch_render_c2_fma(const RenderParams& P, cudaStream_t st);
@@ -30,6 +31,7 @@ cudaError_t eu_launch_render_c3_fma(const RenderParams& P, cudaStream_t st);
 cudaError_t eu_launch_render_c3p_fma(const RenderParams& P, cudaStream_t st);
 cudaError_t eu_launch_render_c4_fma(const RenderParams& P, cudaStream_t st);
 bool eu_launch_render_spec_fma(const RenderParams& P, cudaStream_t st);
+bool eu_launch_render_spec4_fma(const RenderParams& P, cudaStream_t st);
 // spec_used (optional): index of the compiled-in job shape whose kernel ran, 0 = a general kernel
 cudaError_t eu_launch_render(const RenderParams& P, cudaStream_t st, int* spec_used = nullptr);
 

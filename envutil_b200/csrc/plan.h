@@ -9,6 +9,7 @@
 #define EU_MAX_FACETS 64
 #define EU_SMEM_FACETS 24  // synopsis jobs with up to this many facets keep them in shared memory
 #define EU_MAX_TAPS 1024
+#define EU_INLINE_TAPS 64  // twining filters up to 8 x 8 travel in the kernel parameter block
 #define EU_MAX_DEGREE 7
 #define EU_SEGMENT 512  // WIELDING_SEGMENT_SIZE (zimt/bill.h:69)
 #define EU_LANES 16     // zimt vector width of the reference build we track (zimt/simd.h:106-123)
@@ -43,6 +44,8 @@ struct FacetDev {
   float total_w, total_h;  // float(total_width/height)               (:994,:999)
   float win_x0, win_x1, win_y0, win_y1;  // window_extent narrowed for the float compares (:970-978)
   float win_xoff, win_yoff;  // window offset in pixels, subtracted after md_to_spline (:1003-1005)
+  float rcp_w, rcp_h;        // RN(1 / ext_w), RN(1 / ext_h) for dev_div_const
+  int32_t fast_div;          // bit 0 / 1: the reciprocal sequence is proven exact for ext_w / ext_h (api.cu)
   int32_t mask_always;     // get_mask yields all-true (cubemaps, fisheye >= 360: :1567,:1741)
   int32_t has_lcp, has_shift, has_shear;  // pto_planar (environment.h:240-284)
   float lcp[4], lcp_s, shift_h, shift_v;
@@ -55,6 +58,9 @@ struct FacetDev {
   // _hdr_merge_syn (envutil_payload.cc:1354-1375)
   float hdr_optimum;
   int32_t hdr_kind;
+  // 1: everything that decides where a ray lands in this facet equals the PREVIOUS facet of the job (exposure
+  // brackets of one camera position): the kernels reuse that facet's window position (api.cu: same_geometry)
+  int32_t same_geom;
   // generic_stepper + tf_ex_facet + generic_r3 + tf3d_t: facets with PanoTools translation
   // (envutil_payload.cc:1628-1883, geometry.h:1850-1942). Float matrices, rows as r3_t holds them.
   // 'single' jobs on a facet with lens correction / translation put every facet on the generic stepper
@@ -120,6 +126,7 @@ struct RenderParams {
   float wmat[64];           // (degree+1)^2 weight matrix (zimt/basis.h:419-543), float, packed
   const FacetDev* facets;   // all facets (global memory), used by the synopsis modes
   const float* taps;        // n_taps x (x*4, y*4, w)  (twining.h:106-121)
+  float ptaps[3 * EU_INLINE_TAPS];  // the same, inside the parameter block, for filters of up to EU_INLINE_TAPS taps
   const float2* col_tab;    // [2][width]: per-column stepper terms, plain and x-biased (eu_device.cuh)
   const float2* row_tab;    // [2][height]: per-row stepper terms, plain and y-biased
   const float* planar_raw;  // [2][width] then [2][height]: the bare planar coordinates (generic steppers)
@@ -127,6 +134,7 @@ struct RenderParams {
   int32_t mode;       // EU_MODE_*
   int32_t degree;     // spline degree of the evaluator
   int32_t n_taps;     // 0: plain rays (ninputs 3), else twining (ninputs 9)
+  int32_t taps_inline;  // the first n_taps entries of `taps` are also in `ptaps` (constant bank: uniform loads)
   int32_t nch;
   int32_t tstride;    // floats per texel in HBM: nch, or 4 (padded RGB); same for all facets
   int32_t any_generic;  // the general build is needed: some facet uses the generic stepper (translation) or

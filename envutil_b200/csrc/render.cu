@@ -49,7 +49,9 @@ cudaError_t eu_launch_render(const RenderParams& P, cudaStream_t st, int* spec_u
   const bool fma = P.arith == 1;
   // the general build (any_generic) ignores the compile-time texel stride, any TU of the right
   // channel count serves it
-  if (fma ? eu_launch_render_spec_fma(P, st) : eu_launch_render_spec(P, st)) {
+  const bool spec_ran = P.tstride == 4 ? (fma ? eu_launch_render_spec4_fma(P, st) : eu_launch_render_spec4(P, st))
+                                       : (fma ? eu_launch_render_spec_fma(P, st) : eu_launch_render_spec(P, st));
+  if (spec_ran) {
     if (spec_used) *spec_used = P.spec;
     return cudaGetLastError();
   }

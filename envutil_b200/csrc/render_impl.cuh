@@ -118,11 +118,22 @@ __device__ __forceinline__ void dev_facet_ray(const TargetDev& T, const InvPlana
 
 // environment::eval of one facet: the specialised evaluator, or - in the general build - the one
 // that copes with any channel count / texel stride / degree
-template <int NCH, int TS, int DEG, bool GEN>
+template <int NCH, int TS, int DEG, bool GEN, bool I32 = false>
 __device__ __forceinline__ int dev_eval_facet(const RenderParams& P, const FacetDev& F, const float r[3],
                                               float px[NCH]) {
   if constexpr (GEN) return dev_facet_eval_general<NCH>(F, P.degree, P.wmat, r, px);
-  else return dev_facet_eval<NCH, TS, DEG>(F, P.degree, P.wmat, r, px);
+  else return dev_facet_eval<NCH, TS, DEG, I32>(F, P.degree, P.wmat, r, px);
+}
+
+// tap k of the twining filter: from the parameter block (constant bank; kernels compiled for a job shape - the plan
+// builder only picks them for filters of up to EU_INLINE_TAPS taps), else from global memory
+template <bool INLINE>
+__device__ __forceinline__ void dev_tap(const RenderParams& P, int k, float& cx, float& cy, float& cw) {
+  if constexpr (INLINE) {
+    cx = P.ptaps[3 * k]; cy = P.ptaps[3 * k + 1]; cw = P.ptaps[3 * k + 2];
+  } else {
+    cx = __ldg(P.taps + 3 * k); cy = __ldg(P.taps + 3 * k + 1); cw = __ldg(P.taps + 3 * k + 2);
+  }
 }
 
 // One synopsis evaluation for rays produced by `ray_of(i, ray)`; returns the index-plane value.
@@ -139,7 +150,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
   if constexpr (MODE == EU_MODE_SINGLE) {
     float r[3];
     ray_of(0, r);
-    return dev_eval_facet<NCH, TS, DEG, GEN>(P, f0, r, px);
+    return dev_eval_facet<NCH, TS, DEG, GEN, SP != 0>(P, f0, r, px);
   } else if constexpr (MODE == EU_MODE_VORONOI) {
     int champion = -1;
     float max_z = -FLT_MAX, best[3] = {0.f, 0.f, 0.f};
@@ -159,7 +170,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
 #pragma unroll
       for (int c = 0; c < NCH; c++) px[c] = 0.0f;
     } else {
-      dev_eval_facet<NCH, TS, DEG, GEN>(P, dev_facet_at<SP>(fa, champion), best, px);
+      dev_eval_facet<NCH, TS, DEG, GEN, SP != 0>(P, dev_facet_at<SP>(fa, champion), best, px);
     }
     return champion;
   } else if constexpr (MODE == EU_MODE_HDR) {
@@ -170,11 +181,29 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
     float qsum = 0.0f, p[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; c++) px[c] = 0.0f;
+    Located L;
+    bool hit = false;
     for (int i = 0; i < P.n_facets; i++) {
       const FacetDev& F = dev_facet_at<SP>(fa, i);
-      float r[3];
-      ray_of(i, r);
-      dev_eval_facet<NCH, TS, DEG, GEN>(P, F, r, p);
+      if constexpr (GEN) {
+        float r[3];
+        ray_of(i, r);
+        dev_eval_facet<NCH, TS, DEG, GEN, SP != 0>(P, F, r, p);
+      } else {
+        // brackets of one camera position share their geometry: the ray and its window position are the
+        // previous facet's (FacetDev::same_geom), only the container differs
+        if (i == 0 || !F.same_geom) {
+          float r[3];
+          ray_of(i, r);
+          hit = dev_facet_locate<DEG>(F, P.degree, r, L);
+        }
+        if (hit) {
+          dev_facet_window<NCH, TS, DEG, SP != 0>(F, P.degree, P.wmat, L, p);
+        } else {
+#pragma unroll
+          for (int c = 0; c < NCH; c++) p[c] = 0.0f;
+        }
+      }
       float grey = p[0];
       if constexpr (NCH >= 3) grey = fmaxf(p[0], fmaxf(p[1], p[2]));
       float q = dev_hdr_quality(grey, F.hdr_optimum, F.hdr_kind);
@@ -238,7 +267,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
     if (try_shortcut && active) {
       float r[3];
       ray_of(top, r);
-      dev_eval_facet<NCH, TS, DEG, GEN>(P, dev_facet_at<SP>(fa, top), r, help);
+      dev_eval_facet<NCH, TS, DEG, GEN, SP != 0>(P, dev_facet_at<SP>(fa, top), r, help);
       have_top = true;
       opaque = help[NCH - 1] >= 1.0f;
     }
@@ -255,7 +284,7 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
         if (!(k == 0 && have_top)) {
           float r[3];
           ray_of(ids[k], r);
-          dev_eval_facet<NCH, TS, DEG, GEN>(P, dev_facet_at<SP>(fa, ids[k]), r, help);
+          dev_eval_facet<NCH, TS, DEG, GEN, SP != 0>(P, dev_facet_at<SP>(fa, ids[k]), r, help);
         }
         if (k == 0) {
 #pragma unroll
@@ -357,11 +386,12 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
         dv[c] = dv[c] - r00[c];
       }
       for (int k = 0; k < P.n_taps; k++) {
-        float cx = __ldg(P.taps + 3 * k), cy = __ldg(P.taps + 3 * k + 1), cw = __ldg(P.taps + 3 * k + 2);
+        float cx, cy, cw;
+        dev_tap<SP != 0>(P, k, cx, cy, cw);
         float r[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) r[c] = r00[c] + cx * du[c] + cy * dv[c];
-        int id = dev_eval_facet<NCH, TS, DEG, GEN>(P, f0, r, help);
+        int id = dev_eval_facet<NCH, TS, DEG, GEN, SP != 0>(P, f0, r, help);
         if (k == 0) idx = id;
 #pragma unroll
         for (int c = 0; c < NCH; c++) acc[c] = EU_WIN_MULADD(cw, help[c], acc[c]);
@@ -383,7 +413,8 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
         }
       }
       for (int k = 0; k < P.n_taps; k++) {
-        float cx = __ldg(P.taps + 3 * k), cy = __ldg(P.taps + 3 * k + 1), cw = __ldg(P.taps + 3 * k + 2);
+        float cx, cy, cw;
+        dev_tap<SP != 0>(P, k, cx, cy, cw);
         auto ray_of = [&](int i, float r[3]) {
 #pragma unroll
           for (int c = 0; c < 3; c++) r[c] = np[i][c] + cx * np[i][3 + c] + cy * np[i][6 + c];
@@ -577,7 +608,8 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
     for (int c = 0; c < NCH; c++) px[c] = 0.0f;
     const int bx1 = a0 + wf, by1 = by0 + rows;
     for (int k = 0; k < P.n_taps; k++) {
-      float tx = __ldg(P.taps + 3 * k), ty = __ldg(P.taps + 3 * k + 1), tw = __ldg(P.taps + 3 * k + 2);
+      float tx, ty, tw;
+      dev_tap<SP != 0>(P, k, tx, ty, tw);
       float r[3];
 #pragma unroll
       for (int c = 0; c < 3; c++) r[c] = r00[c] + tx * du[c] + ty * dv[c];

@@ -269,6 +269,21 @@ def _build():
     add("tr1_cube_d1", Job(tr[:1], "cubemap", 90.0, 48, yaw=-20.0))
     add("tr3_voronoi_ba6_d1_tw2", Job(tr, "biatan6", 90.0, 40, twine=2, yaw=15.0, pitch=-8.0))
     add("tr2_cube100_d3", Job(tr[:2], "cubemap", 100.0, 36, degree=3))
+    # `--single` on a wide translated facet: the target-side translation sends part of the rays behind the
+    # translation plane, the generic stepper marks them (0, 0, -inf) and normalising makes that (0, 0, NaN). On x86 that
+    # NaN carries a set sign bit, atan2 (0, NaN) is pi and every mounted image is missed (found by the random
+    # sweep, seed 12 job 136: the kernels must not see the GPU's positive NaN as a hit at the image centre)
+    rng = np.random.default_rng(136)
+    nf = [FacetSpec(rng.random((20, 62, 3), dtype=np.float32), "spherical", 126.32447081741843, yaw=113.91373814521751),
+          FacetSpec(rng.random((28, 56, 3), dtype=np.float32), "spherical", 360.0, yaw=-111.00090771641756,
+                    pitch=70.69440350613604, roll=-10.717262957604202),
+          FacetSpec(rng.random((21, 66, 3), dtype=np.float32), "spherical", 193.96977974745334, yaw=163.2839892925718),
+          FacetSpec(rng.random((39, 58, 3), dtype=np.float32), "rectilinear", 113.6686449099416, yaw=-98.0931541828372,
+                    pitch=-37.33135403223616, roll=-4.234541700616683, a=-0.0041605062769297756, b=0.014552337415172575,
+                    c=-0.01240534595827941, tr_x=0.07629050379701123, tr_y=-0.03416623475390121, tr_z=0.036574020288230494)]
+    add("single3_nan_rays_d0_tw2", Job(nf, "spherical", 360.0, 63, 17, degree=0, twine=2, twine_width=1.369265271160024,
+                                       single=3))
+    add("single3_nan_rays_d1", Job(nf, "spherical", 360.0, 63, 17, single=3))
     return J
 
 

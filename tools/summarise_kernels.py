@@ -76,7 +76,8 @@ def main():
         rel = os.path.join("profiles", "%s_%s_metrics.txt" % (tag, config.replace("/", "_")))
         allk[config] = {"kernel": v[ik].split("(")[0].replace("void ", ""), "dram_bytes": (rd or 0) + (wr or 0),
                         "dram_read_bytes": rd, "dram_write_bytes": wr, "inst_executed": get("smsp__inst_executed.sum"),
-                        "time_us_under_ncu": get("gpu__time_duration.sum"), "l2_hit_pct": get("lts__t_sector_hit_rate.pct"),
+                        "time_us_under_ncu": (get("gpu__time_duration.sum") or 0.0) *
+                        {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[hdr.index("gpu__time_duration.sum")], 1.0), "l2_hit_pct": get("lts__t_sector_hit_rate.pct"),
                         "l1_hit_pct": get("l1tex__t_sector_hit_rate.pct"),
                         "global_ld_sectors_per_request": (sec / req) if req and sec else None,
                         "issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
