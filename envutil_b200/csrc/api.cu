@@ -278,6 +278,8 @@ int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, Fac
     F.win_y1 = (float)(f->y0 + py1 * wy);
     F.win_xoff = (float)f->window_x_offset;
     F.win_yoff = (float)f->window_y_offset;
+    F.win_margin[0] = 1e-5f * fmaxf(fabsf(F.win_x0), fabsf(F.win_x1)) + 1e-30f;
+    F.win_margin[1] = 1e-5f * fmaxf(fabsf(F.win_y0), fabsf(F.win_y1)) + 1e-30f;
   }
   F.mask_always = (s->kind != EU_SRC_MOUNT) || (f->projection == EU_FISHEYE && f->hfov >= M_PI * 2.0);
   F.has_lcp = f->has_lcp;

@@ -402,8 +402,21 @@ __device__ __forceinline__ bool dev_mount_mask(const FacetDev& F, const float r[
   return m;
 }
 
+// mount_t::get_mask for the synopses that only need to know WHETHER a ray hits (_voronoi_syn tests every facet and
+// evaluates one). Rectilinear mounts - photographs, the common case - decide most rays without the two IEEE
+// divisions of ray_to_rect_t: a ray with z <= 0 (or NaN) misses, and an approximate quotient (2 ulp) that clears
+// the window's edges by a margin of 1e-5 of the edge coordinate (host: FacetDev::win_margin) gives the same
+// answer as the correctly rounded one, because rounding is monotonic; only rays inside that margin take the
+// exact path. The decision is the reference's for every ray.
 __device__ __forceinline__ bool dev_facet_mask(const FacetDev& F, const float r[3]) {
   if (F.mask_always) return true;
+  if (F.projection == EU_RECTILINEAR && !F.has_lcp) {
+    if (!(r[2] > 0.0f)) return false;
+    const float tx = __fdividef(r[0], r[2]), ty = __fdividef(r[1], r[2]);
+    const float mx = F.win_margin[0], my = F.win_margin[1];
+    if (tx < F.win_x0 - mx || tx > F.win_x1 + mx || ty < F.win_y0 - my || ty > F.win_y1 + my) return false;
+    if (tx > F.win_x0 + mx && tx < F.win_x1 - mx && ty > F.win_y0 + my && ty < F.win_y1 - my) return true;
+  }
   float c[2];
   dev_mount_coordinate(F, r, c);
   return dev_mount_mask(F, r, c);

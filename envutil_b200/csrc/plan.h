@@ -44,6 +44,7 @@ struct FacetDev {
   float total_w, total_h;  // float(total_width/height)               (:994,:999)
   float win_x0, win_x1, win_y0, win_y1;  // window_extent narrowed for the float compares (:970-978)
   float win_xoff, win_yoff;  // window offset in pixels, subtracted after md_to_spline (:1003-1005)
+  float win_margin[2];       // dev_facet_mask: how far an approximate coordinate must clear the window's edges (x, y)
   float rcp_w, rcp_h;        // RN(1 / ext_w), RN(1 / ext_h) for dev_div_const
   int32_t fast_div;          // bit 0 / 1: the reciprocal sequence is proven exact for ext_w / ext_h (api.cu)
   int32_t mask_always;     // get_mask yields all-true (cubemaps, fisheye >= 360: :1567,:1741)

@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant
 // order of combination are untouched: the result is bit-identical to the direct kernel.
 // ------------------------------------------------------------------------------------------
 #define EU_TILE_FLOATS 6144  // 24 KB staged footprint per block
+#define EU_TILE_PITCH(w) (((w) + 31) & ~31)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -553,21 +554,27 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
         a0 = (mnx * TS) & ~3;  // 16-byte granule within the container row
         wf = (((mxx + ORDER) * TS - a0) + 3) & ~3;
         rows = mxy - mny + ORDER;
-        if (rows > TILE_X * TILE_Y || rows * wf > EU_TILE_FLOATS || wf <= 0 || rows <= 0) rows = 0;
+        // rows sit EU_TILE_PITCH(wf) floats apart in shared memory (a multiple of the 32 banks, see below)
+        if (rows > TILE_X * TILE_Y || rows * EU_TILE_PITCH(wf) > EU_TILE_FLOATS || wf <= 0 || rows <= 0) rows = 0;
       }
       box[0] = a0; box[1] = mny; box[2] = wf; box[3] = rows;
       if (rows > 0) mbar_expect_tx(&mbar, (uint32_t)(rows * wf) * 4u);
     }
   }
   __syncthreads();
-  const int a0 = box[0], by0 = box[1], wf = box[2], rows = box[3];
+  const int a0 = box[0], by0 = box[1], wcopy = box[2], rows = box[3];
+  // Row pitch in shared memory: the copied width rounded up to a multiple of 32 floats. A warp's pixels usually
+  // spread over two or three source rows; with an arbitrary pitch w, lanes in adjacent rows whose columns differ by
+  // -w/3 (mod 32) hit the same bank - some pair nearly always does. With w = 0 (mod 32) only lanes in the SAME
+  // column (or 32 apart) collide, which a smooth mapping rarely produces. (ncu: 2.15 wavefronts per LDS before.)
+  const int wf = EU_TILE_PITCH(wcopy);
   const bool staged = rows > 0;
   if (staged) {
     // rows are dealt round-robin to the warps (the copy is issued from the uniform datapath, so
     // the lanes of one warp take turns)
     const int rid = (tid & 31) * NWARP + (tid >> 5);
     if (rid < rows)
-      bulk_row_g2s(tile + rid * wf, P.src_base + (ptrdiff_t)(by0 + rid) * S.stride + a0, (uint32_t)wf * 4u, &mbar);
+      bulk_row_g2s(tile + rid * wf, P.src_base + (ptrdiff_t)(by0 + rid) * S.stride + a0, (uint32_t)wcopy * 4u, &mbar);
     mbar_wait(&mbar, 0);
   }
 
@@ -606,7 +613,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
     }
 #pragma unroll
     for (int c = 0; c < NCH; c++) px[c] = 0.0f;
-    const int bx1 = a0 + wf, by1 = by0 + rows;
+    const int bx1 = a0 + wcopy, by1 = by0 + rows;
     for (int k = 0; k < P.n_taps; k++) {
       float tx, ty, tw;
       dev_tap<SP != 0>(P, k, tx, ty, tw);
