@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=int, default=1, help="shrink the workload (tests only; invalid as a bench)")
-    ap.add_argument("--padded", type=int, default=0, help="1: 16-byte RGB texels in HBM")
+    ap.add_argument("--padded", type=int, default=-1, help="RGB texels in HBM: -1 = the library's rule (16-byte for bilinear jobs, 12-byte for the cubic headline), 1 = 16-byte, 0 = 12-byte")
     ap.add_argument("--no-tiles", type=int, default=0, help="1: direct-gather kernel (no shared-memory staging)")
     ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c5"],
                     help="auto: C2 on one GPU (the headline config), the C5 row-band pipeline on N > 1")
@@ -541,7 +541,7 @@ def ours(args):
     bands_mode = args.partition == "bands" and world > 1
     if not bands_mode:
         job.yaw = 360.0 * rank / world  # every rank renders its own view of the same environment
-    job.padded, job.no_tiles = bool(args.padded), bool(args.no_tiles)
+    job.padded, job.no_tiles = (None if args.padded < 0 else bool(args.padded)), bool(args.no_tiles)
     job.contracted = args.arithmetic == "contracted"
     job.narrow_stores = bool(args.narrow_stores)
     eng = Engine(local)
@@ -550,9 +550,9 @@ def ours(args):
     H, W, C = t.height, t.width, t.nchannels
     mpix = W * H / 1e6
     stream = torch.cuda.current_stream().cuda_stream
-    hs = eng.stage_device(job, [d_src.data_ptr()], st, stream=stream, padded=bool(args.padded))
+    hs = eng.stage_device(job, [d_src.data_ptr()], st, stream=stream)
     eng.release(hs)  # the first staging grows the device pool; report the steady state
-    hs = eng.stage_device(job, [d_src.data_ptr()], st, stream=stream, padded=bool(args.padded))
+    hs = eng.stage_device(job, [d_src.data_ptr()], st, stream=stream)
     stage_ms = eng.last_stage_timing[0].render_ms
     import ctypes as _C
     ir_bytes = 4 * int(eng.lib.eu_source_container_floats(hs[0], (_C.c_int32 * 4)()))  # the staged cubemap IR
@@ -738,7 +738,7 @@ def ours(args):
         other, skipped = bench_other_configs(args, eng, torch, pk, pk_src, t_run0)
     if rank == 0:
         peak, peak_src = measured_peak()
-        tr = measured_traffic() if (args.scale == 1 and not args.padded and not args.no_tiles
+        tr = measured_traffic() if (args.scale == 1 and args.padded != 1 and not args.no_tiles
                                     and not bands_mode) else None
         alg_launch = alg // world if bands_mode else alg  # a band touches its share of output and source
         achieved = alg_launch / (ms_per_step * 1e-3) / 1e9  # per launch = per GPU
@@ -770,7 +770,7 @@ def ours(args):
             "config": {"workload": name, "frames_per_step": 1 if bands_mode else world,
                        "partition": "row bands of one frame, gathered on rank 0" if bands_mode else "one frame per rank", "out_mpix_per_frame": mpix,
                        "l2": "inputs_larger_than_l2 (321 MB source IR + 403 MB output per frame vs 126 MB L2)",
-                       "texel_layout": "float4-padded" if args.padded else "interleaved-rgb",
+                       "texel_layout": "float4-padded" if args.padded == 1 else "interleaved-rgb (the library's rule for cubic jobs; bilinear configs below use 16-byte texels)",
                        "gather": "direct (L1)" if args.no_tiles else
                                  "footprint staged in shared memory by cp.async.bulk",
                        "arithmetic": args.arithmetic,  # eu_opts_t.reserved[1] & EU_OPT_CONTRACTED

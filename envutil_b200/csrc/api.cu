@@ -605,7 +605,7 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     for (int i = 0; i < nf; i++) F[i].hdr_kind = (i == lo) ? EU_HDR_LOW : (i == hi) ? EU_HDR_HIGH : EU_HDR_MIDDLE;
   }
   P.f0 = F[first];
-  P.use_tiles = (o->reserved[1] & EU_OPT_NO_TILES) ? 0 : 1;
+  P.use_tiles = (o->reserved[1] & EU_OPT_NO_TILES) ? 0 : ((o->reserved[1] & 32) ? 3 : 1);  // 3: previous tiled kernel (A/B)
   P.src_cw = sources[first]->cw;
   P.src_ch = sources[first]->chh;
   P.src_lx = sources[first]->lx;
@@ -842,9 +842,14 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
   return mount_finish(f, pdeg, s, st, launches);
 }
 
-// optional 16-byte texel layout for RGB sources (o->reserved[0] == 1): one LDG.128 per tap
+// 16-byte texel layout for RGB sources: one LDG.128 per tap instead of three LDG.32. Measured on B200 with the
+// kernels compiled for a job shape (profiles/r02c_configs_variants.jsonl): bilinear jobs gain 12-17 % (C3a 1.18 ->
+// 1.02 ms, C3b 1.25 -> 1.03, C4 2.09 -> 1.84), the footprint-staged cubic kernel nothing - so it is the default for
+// degree <= 1 and off for higher degrees. o->reserved[0]: 0 = that rule, 1 = always, 2 = never.
 int maybe_pad(const eu_opts_t* o, eu_source* s, cudaStream_t st, int* launches) {
-  if (o->reserved[0] != 1 || s->nch != 3) return EU_OK;
+  if (s->nch != 3) return EU_OK;
+  const bool want = o->reserved[0] == 1 || (o->reserved[0] == 0 && s->degree <= 1);
+  if (!want) return EU_OK;
   size_t ntex = (size_t)s->cw * s->chh;
   float* padded = nullptr;
   CK(pool_alloc(&padded, ntex * 4));

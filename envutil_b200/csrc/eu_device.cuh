@@ -544,11 +544,10 @@ __device__ __forceinline__ Located dev_locate(const SourceDev& S, int degree, fl
   return L;
 }
 
-// evaluator::eval for a fixed degree > 1: window sum in the reference's order
-// (zimt/eval.h:903-996). p0 -> texel (ix - deg/2, iy - deg/2); pitch: floats per row.
+// the window sum proper, weights given (zimt/eval.h:903-996: rows left to right, then down the column of row sums)
 template <int NCH, int TS, int DEG, int SMEM>
-__device__ __forceinline__ void dev_window_sum(const float* __restrict__ p0, int pitch, const float* __restrict__ wmat,
-                                               float fx, float fy, float out[NCH]) {
+__device__ __forceinline__ void dev_window_sum_w(const float* __restrict__ p0, int pitch, const float wx[DEG + 1],
+                                                 const float wy[DEG + 1], float out[NCH]) {
   constexpr int ORDER = DEG + 1;
   float t[ORDER][ORDER][NCH];
 #pragma unroll
@@ -557,9 +556,6 @@ __device__ __forceinline__ void dev_window_sum(const float* __restrict__ p0, int
 #pragma unroll
     for (int i = 0; i < ORDER; i++) dev_load_texel<NCH, TS, SMEM>(row + i * TS, t[j][i]);
   }
-  float wx[ORDER], wy[ORDER];
-  dev_window_weights<ORDER>(wmat, fx, wx);
-  dev_window_weights<ORDER>(wmat, fy, wy);
 #pragma unroll
   for (int j = 0; j < ORDER; j++) {
     float sub[NCH];
@@ -581,6 +577,18 @@ __device__ __forceinline__ void dev_window_sum(const float* __restrict__ p0, int
       for (int c = 0; c < NCH; c++) out[c] = EU_WIN_MULADD(sub[c], wy[j], out[c]);
     }
   }
+}
+
+// evaluator::eval for a fixed degree > 1: window sum in the reference's order
+// (zimt/eval.h:903-996). p0 -> texel (ix - deg/2, iy - deg/2); pitch: floats per row.
+template <int NCH, int TS, int DEG, int SMEM>
+__device__ __forceinline__ void dev_window_sum(const float* __restrict__ p0, int pitch, const float* __restrict__ wmat,
+                                               float fx, float fy, float out[NCH]) {
+  constexpr int ORDER = DEG + 1;
+  float wx[ORDER], wy[ORDER];
+  dev_window_weights<ORDER>(wmat, fx, wx);
+  dev_window_weights<ORDER>(wmat, fy, wy);
+  dev_window_sum_w<NCH, TS, DEG, SMEM>(p0, pitch, wx, wy, out);
 }
 
 template <int NCH, int TS, int SMEM>

@@ -107,7 +107,8 @@ class Job:
     single: int = -1  # --single K: render into facet K's geometry, undo its brighten (envutil_main.cc:1157-1178)
     support_min: int = 8
     tile_size: int = 64
-    padded: bool = False    # back-end option: 16-byte RGB texels in HBM (eu_opts.reserved[0])
+    padded: Optional[bool] = None  # back-end option, eu_opts.reserved[0]: 16-byte RGB texels in HBM - None = the library's
+                                   # rule (bilinear and nearest-neighbour jobs), True = always, False = never
     no_tiles: bool = False  # back-end option: never stage gather footprints in shared memory (reserved[1] bit 0)
     narrow_stores: bool = False  # back-end option: 4-byte pixel stores even into peer frames (reserved[1] bit 2)
     no_spec: bool = False   # back-end option: never use the kernels compiled for one job shape (reserved[1] bit 1)
@@ -265,10 +266,11 @@ class Job:
         o.synopsis = capi.SYN_HDR_MERGE if self.synopsis == "hdr_merge" else capi.SYN_PANORAMA
         o.solo = 0 if n == 1 else self.solo  # forced for a single facet (envutil_main.cc:996-997)
         o.support_min, o.tile_size = self.support_min, self.tile_size
-        o.reserved[0] = 1 if self.padded else 0
+        o.reserved[0] = 0 if self.padded is None else (1 if self.padded else 2)
         contracted = capi.ARITHMETIC == "contracted" if self.contracted is None else self.contracted
         o.reserved[1] = (capi.OPT_NO_TILES if self.no_tiles else 0) | (capi.OPT_NO_SHAPES if self.no_spec else 0) | \
-            (capi.OPT_NARROW_STORES if self.narrow_stores else 0) | (capi.OPT_CONTRACTED if contracted else 0)
+            (capi.OPT_NARROW_STORES if self.narrow_stores else 0) | (capi.OPT_CONTRACTED if contracted else 0) | \
+            (32 if getattr(self, "tiled_v1", False) else 0)
         taps = (capi.Tap * 1024)()
         tw = C.c_int(0)
         ntaps = lib.eu_make_spread(C.byref(t), C.byref(o), n, fa, self.twine, self.twine_width, self.twine_density,

@@ -110,7 +110,9 @@ typedef struct eu_opts {
   int32_t solo;             /* -1, or the single facet to show; forced to 0 for one facet */
   int32_t support_min;      /* cubemap IR support, default 8  (envutil_main.cc:458) */
   int32_t tile_size;        /* cubemap IR tile size, default 64 (envutil_main.cc:457) */
-  int32_t reserved[2];      /* back-end options, 0 = defaults. [0] 1: 16-byte RGB texels in HBM; [1]: EU_OPT_* bits */
+  int32_t reserved[2];      /* back-end options, 0 = defaults. [0]: texel layout of RGB sources in HBM - 0 = 16-byte texels
+                               for degree <= 1 (one 128-bit load per tap), 12-byte texels otherwise; 1 = always 16-byte;
+                               2 = always 12-byte. [1]: EU_OPT_* bits */
 } eu_opts_t;
 /* eu_opts_t.reserved[1] */
 #define EU_OPT_NO_TILES 1      /* never stage the gather footprint in shared memory */

@@ -56,16 +56,13 @@ def test_staged_container_bit_exact(engine, name):
 
 
 @pytest.mark.parametrize("name", ["ll_rect_d1_rot", "cm_sph_d3", "voronoi4_sph_d1", "ll_fish_d1_tw4"])
-def test_padded_texel_layout_is_bit_exact(engine, name):
-    """The 16-byte texel layout (one 128-bit load per tap) changes addresses, not values."""
-    job = jobs.JOBS[name]
-    st = job.structs()
-    hs = engine.stage(job, st, padded=True)
-    try:
-        out = engine.render(job, sources=hs, structs=st)
-    finally:
-        engine.release(hs)
-    assert harness.compare(out, harness.oracle_render(job))["n_diff"] == 0
+@pytest.mark.parametrize("padded", [True, False])
+def test_texel_layouts_are_bit_exact(engine, name, padded):
+    """The 16-byte texel layout (one 128-bit load per tap; the library's default for bilinear RGB jobs) and the
+    12-byte one (its default for higher degrees) change addresses, not values: both forced, for every listed job."""
+    job = copy.copy(jobs.JOBS[name])
+    job.padded = padded
+    assert harness.compare(engine.render(job), harness.oracle_render(job))["n_diff"] == 0
 
 
 # job -> the compiled-in job shape (plan.h: eu_render_specs) whose kernel must have rendered it

@@ -185,6 +185,9 @@ def test_backend_option_bits(lib):
     job = copy.copy(jobs.JOBS["ll_rect_d3_rot"])
     o = job.structs(lib)[2]
     assert (o.reserved[0], o.reserved[1]) == (0, 0)
+    job.padded = False  # 12-byte texels whatever the degree
+    assert job.structs(lib)[2].reserved[0] == 2
+    job.padded = None
     for field, word, bit in (("padded", 0, 1), ("no_tiles", 1, 1), ("no_spec", 1, 2), ("narrow_stores", 1, 4),
                              ("contracted", 1, 16)):
         j = copy.copy(job)
