@@ -244,7 +244,7 @@ class Pipeline:
             hnd, core, pitch = self.src_b[p]
             for (r0, r1, c0, c1) in self.rects:
                 eng.render_rect_pitched(self.jobs_a[p], self.hs_a[p], self.st_a[p], r0, r1, c0, c1, core + r0 * pitch * 4,
-                                        pitch, self.stream)
+                                        pitch, self.stream, texel_floats=eng.texel_floats[hnd.value])
 
     def stage_b_staging(self):
         for p in range(POSITIONS):

@@ -125,9 +125,9 @@ SYMBOLS = {
                                          C.c_int, C.c_void_p, C.POINTER(Timing)]),
     "eu_render_rect_pitched": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
                                          C.POINTER(SourceH), C.POINTER(Tap), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                         C.c_void_p, C.c_int, C.c_void_p, C.POINTER(Timing)]),
+                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(Timing)]),
     "eu_source_reserve": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.POINTER(SourceH),
-                                    C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "eu_source_commit": (C.c_int, [SourceH, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p, C.POINTER(Timing)]),
     "eu_source_write_rect": (C.c_int, [SourceH, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "eu_source_upload_async": (C.c_int, [C.c_char_p, C.POINTER(Facet), C.POINTER(Opts), C.c_void_p,

@@ -734,7 +734,10 @@ void mount_layout(const eu_facet_t* f, int degree, eu_source* s) {
 
 // the core of a mounted image is in place: prefilter (degree > 1) and brace
 int mount_finish(const eu_facet_t* f, int pdeg, eu_source* s, cudaStream_t st, int* launches) {
-  const int nch = f->nchannels, stride = s->pitch;
+  // a reserved RGB source in the 16-byte layout is braced as 4-float texels (it is never prefiltered: that layout is
+  // chosen for degree <= 1 only)
+  const int nch = (s->tstride == 4 && f->nchannels == 3) ? 4 : f->nchannels, stride = s->pitch;
+  if (nch != f->nchannels && pdeg > 1) return fail(EU_ERR_UNSUPPORTED, "16-byte RGB texels cannot be prefiltered in place");
   float* core = s->container + (size_t)s->ly * stride + (size_t)s->lx * nch;
   bool sphere = is_full_sphere(f);
   if (sphere && (s->ly > s->h || s->ry > s->h)) return fail(EU_ERR_ARGUMENT, "image too small for its brace");
@@ -853,7 +856,7 @@ int maybe_pad(const eu_opts_t* o, eu_source* s, cudaStream_t st, int* launches) 
   size_t ntex = (size_t)s->cw * s->chh;
   float* padded = nullptr;
   CK(pool_alloc(&padded, ntex * 4));
-  cudaError_t e = eu_launch_pad_texels(s->container, s->pitch, padded, s->cw, s->chh, s->nch, st);
+  cudaError_t e = eu_launch_pad_texels(s->container, s->pitch, padded, s->cw, s->cw, s->chh, s->nch, st);
   if (e != cudaSuccess) {
     pool_free(padded);
     return fail(EU_ERR_CUDA, "pad kernel: %s", cudaGetErrorString(e));
@@ -1177,12 +1180,13 @@ int eu_render_rows_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facet
                            float* d_out, int out_pitch_floats, void* cuda_stream, eu_timing_t* timing) {
   if (!t) return fail(EU_ERR_ARGUMENT, "null argument");
   return eu_render_rect_pitched(t, o, n_facets, facets, sources, taps, n_taps, row0, row1, 0, out_width(t), d_out,
-                                out_pitch_floats, cuda_stream, timing);
+                                out_pitch_floats, 0, cuda_stream, timing);
 }
 
 int eu_render_rect_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
                            const eu_source_h* sources, const eu_tap_t* taps, int n_taps, int row0, int row1, int col0,
-                           int col1, float* d_out, int out_pitch_floats, void* cuda_stream, eu_timing_t* timing) {
+                           int col1, float* d_out, int out_pitch_floats, int out_texel_floats, void* cuda_stream,
+                           eu_timing_t* timing) {
   int rc = need_up();
   if (rc) return rc;
   Plan plan;
@@ -1193,8 +1197,15 @@ int eu_render_rect_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facet
     return fail(EU_ERR_ARGUMENT, "bad column range [%d,%d): it must lie inside the raster and start at a multiple of 32", col0, col1);
   plan.P.col0 = col0;
   plan.P.col1 = col1;
+  if (out_texel_floats == 0) out_texel_floats = t->nchannels;
+  if (out_texel_floats != t->nchannels && !(t->nchannels == 3 && out_texel_floats == 4))
+    return fail(EU_ERR_ARGUMENT, "output texels of %d floats for a %d-channel job", out_texel_floats, t->nchannels);
+  if (out_texel_floats == 4 && t->nchannels == 3 && ((out_pitch_floats & 3) || (reinterpret_cast<uintptr_t>(d_out) & 15)))
+    return fail(EU_ERR_ARGUMENT, "16-byte output texels need a 16-byte aligned raster");
+  plan.P.out_tstride = out_texel_floats;
   if (!d_out) return fail(EU_ERR_ARGUMENT, "null output");
-  if (out_pitch_floats < out_width(t) * t->nchannels) return fail(EU_ERR_ARGUMENT, "output pitch %d is shorter than a row", out_pitch_floats);
+  if (out_pitch_floats < out_width(t) * (out_texel_floats ? out_texel_floats : t->nchannels))
+    return fail(EU_ERR_ARGUMENT, "output pitch %d is shorter than a row", out_pitch_floats);
   cudaStream_t caller = (cudaStream_t)cuda_stream;
   if (caller != g.stream)
     for (int i = 0; i < n_facets; i++) sources[i]->foreign_use = true;
@@ -1301,6 +1312,7 @@ int eu_render_async(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
   plan.P.row1 = out_height(t);
   plan.P.out = J.d_out;
   plan.P.out_pitch = out_width(t) * t->nchannels;
+  plan.P.out_tstride = t->nchannels;
   plan.P.index_out = nullptr;
   CK(cudaEventRecord(J.start, g.stream));
   CK(eu_launch_render(plan.P, g.stream));
@@ -1352,6 +1364,7 @@ int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets, cons
   plan.P.row1 = out_height(t);
   plan.P.out = nullptr;
   plan.P.out_pitch = out_width(t) * t->nchannels;
+  plan.P.out_tstride = t->nchannels;
   plan.P.index_out = g.d_index;
   CK(eu_launch_render(plan.P, g.stream));
   CK(plan_done(plan, g.stream));
@@ -1384,10 +1397,10 @@ int eu_debug_tie_plane(const eu_target_t* t, const eu_opts_t* o, int n_facets, c
 
 // ---- a source whose raster is produced on the device, in place -----------------------------
 int eu_source_reserve(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, eu_source_h* out, float** d_core,
-                      int* pitch_floats) {
+                      int* pitch_floats, int* texel_floats) {
   int rc = need_up();
   if (rc) return rc;
-  if (!f || !o || !out || !d_core || !pitch_floats) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (!f || !o || !out || !d_core || !pitch_floats || !texel_floats) return fail(EU_ERR_ARGUMENT, "null argument");
   if (f->projection == EU_CUBEMAP || f->projection == EU_BIATAN6)
     return fail(EU_ERR_UNSUPPORTED, "eu_source_reserve is for single images (a cubemap's faces are re-arranged on upload)");
   rc = check_raster(f, o);
@@ -1402,6 +1415,11 @@ int eu_source_reserve(const char* asset_key, const eu_facet_t* f, const eu_opts_
   s->degree = o->spline_degree;
   s->tstride = f->nchannels;
   mount_layout(f, o->spline_degree, s);
+  // the texel layout follows the same rule as an uploaded source's (maybe_pad): RGB for degree <= 1 in 16-byte texels
+  if (s->nch == 3 && (o->reserved[0] == 1 || (o->reserved[0] == 0 && o->spline_degree <= 1))) {
+    s->tstride = 4;
+    s->pitch = s->cw * 4;
+  }
   cudaError_t e = pool_alloc(&s->container, (size_t)s->pitch * s->chh);
   // rows the caller never writes are zero, not whatever the pool held (a prefilter would spread NaNs)
   if (e == cudaSuccess) e = cudaMemsetAsync(s->container, 0, (size_t)s->pitch * s->chh * sizeof(float), g.stream);
@@ -1423,8 +1441,9 @@ int eu_source_reserve(const char* asset_key, const eu_facet_t* f, const eu_opts_
     }
   }
   *out = s;
-  *d_core = s->container + (size_t)s->ly * s->pitch + (size_t)s->lx * s->nch;
+  *d_core = s->container + (size_t)s->ly * s->pitch + (size_t)s->lx * s->tstride;
   *pitch_floats = s->pitch;
+  *texel_floats = s->tstride;
   return EU_OK;
 }
 
@@ -1438,7 +1457,7 @@ int eu_source_commit(eu_source_h s, const eu_facet_t* f, const eu_opts_t* o, voi
   eu_source probe;
   mount_layout(f, o->spline_degree, &probe);
   if (f->nchannels != s->nch || f->projection != s->projection || o->spline_degree != s->degree || probe.w != s->w ||
-      probe.h != s->h || probe.bc0 != s->bc0 || probe.bc1 != s->bc1 || probe.pitch != s->pitch)
+      probe.h != s->h || probe.bc0 != s->bc0 || probe.bc1 != s->bc1 || probe.cw != s->cw || probe.chh != s->chh)
     return fail(EU_ERR_ARGUMENT, "eu_source_commit: the facet / options differ from those given to eu_source_reserve");
   int pdeg = o->prefilter_degree < 0 ? o->spline_degree : o->prefilter_degree;
   if (pdeg > EU_MAX_DEGREE) return fail(EU_ERR_ARGUMENT, "prefilter degree %d out of range", pdeg);
@@ -1473,7 +1492,7 @@ int eu_source_write_rect(eu_source_h s, const float* pixels, size_t src_pitch_fl
                 s->w, s->h);
   const size_t wb = (size_t)(col1 - col0) * s->nch * sizeof(float);
   if (src_pitch_floats * sizeof(float) < wb) return fail(EU_ERR_ARGUMENT, "source pitch shorter than the rectangle's rows");
-  float* dst = s->container + (size_t)(s->ly + row0) * s->pitch + (size_t)(s->lx + col0) * s->nch;
+  float* dst = s->container + (size_t)(s->ly + row0) * s->pitch + (size_t)(s->lx + col0) * s->tstride;
   cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL is the legacy default stream, as for eu_render_rows
   cudaPointerAttributes pa;
   cudaMemcpyKind kind = cudaMemcpyHostToDevice;
@@ -1481,6 +1500,16 @@ int eu_source_write_rect(eu_source_h s, const float* pixels, size_t src_pitch_fl
     if (pa.type == cudaMemoryTypeDevice) kind = cudaMemcpyDeviceToDevice;
   } else {
     cudaGetLastError();
+  }
+  if (s->tstride != s->nch) {  // 16-byte texels: the rectangle lands in a scratch buffer and is widened on the device
+    float* tmp = nullptr;
+    const size_t rowf = (size_t)(col1 - col0) * s->nch;
+    CK(cudaMallocAsync((void**)&tmp, rowf * (row1 - row0) * sizeof(float), st));
+    cudaError_t e = cudaMemcpy2DAsync(tmp, rowf * sizeof(float), pixels, src_pitch_floats * sizeof(float), wb, row1 - row0, kind, st);
+    if (e == cudaSuccess) e = eu_launch_pad_texels(tmp, (int)rowf, dst, s->pitch / 4, col1 - col0, row1 - row0, s->nch, st);
+    cudaFreeAsync(tmp, st);
+    if (e != cudaSuccess) return fail(EU_ERR_CUDA, "write_rect: %s", cudaGetErrorString(e));
+    return EU_OK;
   }
   CK(cudaMemcpy2DAsync(dst, (size_t)s->pitch * sizeof(float), pixels, src_pitch_floats * sizeof(float), wb, row1 - row0, kind,
                        st));

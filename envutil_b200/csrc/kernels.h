@@ -55,4 +55,6 @@ cudaError_t eu_launch_cubemap_support(float* ir, int pitch, int nch, int face_px
 // then y (REFLECT), then expand the raster to `nch` channels and multiply every channel by it
 cudaError_t eu_launch_alpha_apply(const unsigned char* mask, float* tmp_a, float* tmp_b, const float* raw, int native_nch,
                                   float* out, int nch, int w, int h, cudaStream_t st);
-cudaError_t eu_launch_pad_texels(const float* src, int src_pitch, float* dst, int cw, int chh, int nch, cudaStream_t st);
+// rows of nch-float texels -> 16-byte texels, cw x chh of them, destination rows dst_pitch_texels apart
+cudaError_t eu_launch_pad_texels(const float* src, int src_pitch, float* dst, int dst_pitch_texels, int cw, int chh, int nch,
+                                 cudaStream_t st);

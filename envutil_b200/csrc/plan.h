@@ -150,6 +150,7 @@ struct RenderParams {
   int32_t arith;       // 0: every product and sum rounded separately; 1: fused multiply-adds in the window evaluation
   float* out;          // first float of row `row0`
   int32_t out_pitch;   // floats from one output row to the next (width * nch for a dense band)
+  int32_t out_tstride; // floats from one output pixel to the next: nch, or 4 for RGB rendered into a 16-byte-texel container
   int32_t wide_stores; // 1: `out` is another GPU's memory - RGB pixels leave as 128-bit stores (dev_store_pixel)
   int32_t* index_out;  // optional index plane (face / winning facet)
 };

@@ -48,6 +48,13 @@ __device__ __forceinline__ int first_lane_column(int x) {
 template <int NCH>
 __device__ __forceinline__ void dev_store_pixel(const RenderParams& P, const TargetDev& T, int x, int y,
                                                 const float px[NCH], float* wslot) {
+  if constexpr (NCH == 3) {
+    if (P.out_tstride == 4) {  // RGB into a container of 16-byte texels (stage one of a two-stage job): one 128-bit store
+      float* d4 = P.out + (size_t)(y - P.row0) * P.out_pitch + (size_t)x * 4;
+      *reinterpret_cast<float4*>(d4) = make_float4(px[0], px[1], px[2], 0.0f);
+      return;
+    }
+  }
   float* dst = P.out + (size_t)(y - P.row0) * P.out_pitch + (size_t)x * NCH;
   if constexpr (NCH == 4) {
     if (((P.out_pitch & 3) | (int)(reinterpret_cast<uintptr_t>(P.out) & 15)) == 0) {

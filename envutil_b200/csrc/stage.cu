@@ -599,13 +599,13 @@ __global__ void k_cm_fill_ordered(float* ir, SourceDev S, int L, int R, int F, i
 }
 
 // interleaved nch-float texels (rows of src_pitch floats) -> dense 16-byte texels
-__global__ void k_pad_texels(const float* __restrict__ src, int src_pitch, float4* __restrict__ dst, int cw, int chh,
-                             int nch) {
+__global__ void k_pad_texels(const float* __restrict__ src, int src_pitch, float4* __restrict__ dst, int dst_pitch_texels,
+                             int cw, int chh, int nch) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= cw) return;
   for (int y = blockIdx.y; y < chh; y += gridDim.y) {  // gridDim.y is limited to 65535 rows
     const float* s = src + (size_t)y * src_pitch + (size_t)x * nch;
-    dst[(size_t)y * cw + x] = make_float4(s[0], nch > 1 ? s[1] : 0.f, nch > 2 ? s[2] : 0.f, 0.f);
+    dst[(size_t)y * dst_pitch_texels + x] = make_float4(s[0], nch > 1 ? s[1] : 0.f, nch > 2 ? s[2] : 0.f, 0.f);
   }
 }
 
@@ -782,9 +782,10 @@ cudaError_t eu_launch_cubemap_support(float* ir, int pitch, int nch, int F, int 
   return cudaGetLastError();
 }
 
-cudaError_t eu_launch_pad_texels(const float* src, int src_pitch, float* dst, int cw, int chh, int nch, cudaStream_t st) {
+cudaError_t eu_launch_pad_texels(const float* src, int src_pitch, float* dst, int dst_pitch_texels, int cw, int chh, int nch,
+                                 cudaStream_t st) {
   dim3 grid((cw + 255) / 256, chh < 65535 ? chh : 65535);
-  k_pad_texels<<<grid, 256, 0, st>>>(src, src_pitch, reinterpret_cast<float4*>(dst), cw, chh, nch);
+  k_pad_texels<<<grid, 256, 0, st>>>(src, src_pitch, reinterpret_cast<float4*>(dst), dst_pitch_texels, cw, chh, nch);
   return cudaGetLastError();
 }
 

@@ -65,28 +65,36 @@ class Engine:
     # ---- sources produced on the device, in place (eu_source_reserve / eu_source_commit) -----
     def reserve(self, facet_struct, opts):
         """Container of a single-image source whose raster a render will write; returns
-        (handle, device address of core texel (0,0), row pitch in floats)."""
-        h, core, pitch = capi.SourceH(), C.c_void_p(), C.c_int()
+        (handle, device address of core texel (0,0), row pitch in floats). The texel stride in floats (the channel
+        count, or 4 for RGB in the 16-byte layout) is remembered in self.texel_floats[handle]."""
+        h, core, pitch, tex = capi.SourceH(), C.c_void_p(), C.c_int(), C.c_int()
         capi.check(self.lib.eu_source_reserve(None, C.byref(facet_struct), C.byref(opts), C.byref(h), C.byref(core),
-                                              C.byref(pitch)), self.lib)
+                                              C.byref(pitch), C.byref(tex)), self.lib)
+        if not hasattr(self, "texel_floats"):
+            self.texel_floats = {}
+        self.texel_floats[h.value] = tex.value
         return h, core.value, pitch.value
 
-    def render_rows_pitched(self, job, sources, structs, row0, row1, d_out, pitch_floats, stream=0, timed=True):
+    def render_rows_pitched(self, job, sources, structs, row0, row1, d_out, pitch_floats, stream=0, timed=True,
+                            texel_floats=0):
         t, fa, o, taps, ntaps = structs
         tm = capi.Timing()
-        capi.check(self.lib.eu_render_rows_pitched(C.byref(t), C.byref(o), len(job.facets), fa, sources, taps, ntaps,
-                                                   row0, row1, C.c_void_p(d_out), pitch_floats, C.c_void_p(stream),
-                                                   C.byref(tm) if timed else None), self.lib)
+        capi.check(self.lib.eu_render_rect_pitched(C.byref(t), C.byref(o), len(job.facets), fa, sources, taps, ntaps,
+                                                   row0, row1, 0, t.out_shape()[1], C.c_void_p(d_out), pitch_floats,
+                                                   texel_floats, C.c_void_p(stream), C.byref(tm) if timed else None),
+                   self.lib)
         self.launches += tm.launches if timed else 1
         if timed:
             self.last_timing = tm
         return tm
 
-    def render_rect_pitched(self, job, sources, structs, row0, row1, col0, col1, d_out, pitch_floats, stream=0):
-        """Columns [col0, col1) of rows [row0, row1) (col0 a multiple of 32); d_out = address of row0, column 0."""
+    def render_rect_pitched(self, job, sources, structs, row0, row1, col0, col1, d_out, pitch_floats, stream=0,
+                            texel_floats=0):
+        """Columns [col0, col1) of rows [row0, row1) (col0 a multiple of 32); d_out = address of row0, column 0;
+        texel_floats: floats per output pixel (0 = the channel count; 4 = RGB into a 16-byte-texel container)."""
         t, fa, o, taps, ntaps = structs
         capi.check(self.lib.eu_render_rect_pitched(C.byref(t), C.byref(o), len(job.facets), fa, sources, taps, ntaps,
-                                                   row0, row1, col0, col1, C.c_void_p(d_out), pitch_floats,
+                                                   row0, row1, col0, col1, C.c_void_p(d_out), pitch_floats, texel_floats,
                                                    C.c_void_p(stream), None), self.lib)
         self.launches += 1
 

@@ -250,21 +250,24 @@ int eu_render_rows_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facet
                            void* cuda_stream, eu_timing_t* timing);
 /* same, restricted to the columns [col0, col1) of those rows (col0 a multiple of 32): d_out still points at the
  * first float of row `row0`, column 0. Pipelines that need only part of an intermediate raster (BASELINE
- * configs[4]: stage B samples a curved region of every merged image) render just the rectangles that cover it. */
+ * configs[4]: stage B samples a curved region of every merged image) render just the rectangles that cover it.
+ * out_texel_floats: floats from one output pixel to the next - 0 or nchannels for a dense raster, 4 for an RGB job
+ * that renders into a reserved source whose texels are 16 bytes (eu_source_reserve reports it). */
 int eu_render_rect_pitched(const eu_target_t* t, const eu_opts_t* o, int n_facets,
                            const eu_facet_t* facets, const eu_source_h* sources, const eu_tap_t* taps,
                            int n_taps, int row0, int row1, int col0, int col1, float* d_out,
-                           int out_pitch_floats, void* cuda_stream, eu_timing_t* timing);
+                           int out_pitch_floats, int out_texel_floats, void* cuda_stream, eu_timing_t* timing);
 /* A source whose raster is produced on the device: two-stage jobs (BASELINE configs[4]: hdr_merge
  * of a position's brackets, then the panorama over the merged images) hand the first stage's result
  * to the second without an intermediate raster and without the placement copy of
  * eu_source_upload_device. eu_source_reserve allocates the braced container of a single image
- * (not a cubemap) and returns the device address of core texel (0,0) and the row pitch in floats;
- * the caller fills the rows (eu_render_rows_pitched with that address and pitch), then
+ * (not a cubemap) and returns the device address of core texel (0,0), the row pitch and the texel stride in floats
+ * (the container follows the library's layout rule: RGB texels of bilinear jobs are 16 bytes, eu_opts_t.reserved[0]);
+ * the caller fills the rows (eu_render_rect_pitched with that address, pitch and texel stride), then
  * eu_source_commit - ordered after cuda_stream's work - prefilters and braces. The handle is
  * used and released like any other source. */
 int eu_source_reserve(const char* asset_key, const eu_facet_t* f, const eu_opts_t* o, eu_source_h* out,
-                      float** d_core, int* pitch_floats);
+                      float** d_core, int* pitch_floats, int* texel_floats);
 int eu_source_commit(eu_source_h s, const eu_facet_t* f, const eu_opts_t* o, void* cuda_stream,
                      eu_timing_t* t);
 /* Fill part of a reserved source from a raster in host (page-locked, for a truly asynchronous copy) or device

@@ -63,7 +63,7 @@ def test_no_cpu_fallback(lib):
     assert lib.eu_cycle() == -5
     assert lib.eu_source_find(b"x") is None
     f, h, ptr, pitch = capi.Facet(), capi.SourceH(), C.c_void_p(), C.c_int()
-    assert lib.eu_source_reserve(None, C.byref(f), C.byref(o), C.byref(h), C.byref(ptr), C.byref(pitch)) == -5
+    assert lib.eu_source_reserve(None, C.byref(f), C.byref(o), C.byref(h), C.byref(ptr), C.byref(pitch), C.byref(pitch)) == -5
     assert lib.eu_render_rows_pitched(C.byref(t), C.byref(o), 0, None, None, None, 0, 0, 1, None, 0, None, None) == -5
     assert lib.eu_frame_alloc(16, C.byref(ptr)) == -5
     assert lib.eu_frame_open(b"\0" * 64, C.byref(ptr)) == -5

@@ -265,8 +265,10 @@ def test_stage_one_renders_into_stage_two_source(engine, degree):
     try:
         # two bands, to exercise the row offset inside the container
         mid = ta.height // 3
-        engine.render_rows_pitched(ja, hsa, sta, 0, mid, core, pitch, 0, timed=True)
-        engine.render_rows_pitched(ja, hsa, sta, mid, ta.height, core + mid * pitch * 4, pitch, 0, timed=True)
+        tex = engine.texel_floats[h.value]  # 4 for the bilinear panorama (16-byte RGB texels), 3 for the cubic one
+        assert tex == (4 if degree == 1 else 3)
+        engine.render_rows_pitched(ja, hsa, sta, 0, mid, core, pitch, 0, timed=True, texel_floats=tex)
+        engine.render_rows_pitched(ja, hsa, sta, mid, ta.height, core + mid * pitch * 4, pitch, 0, timed=True, texel_floats=tex)
         engine.commit(h, fb[0], ob)
         got, shp = engine.container(h)
         want, wshp = engine.container(via_upload[0])
