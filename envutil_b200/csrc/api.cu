@@ -605,7 +605,7 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     for (int i = 0; i < nf; i++) F[i].hdr_kind = (i == lo) ? EU_HDR_LOW : (i == hi) ? EU_HDR_HIGH : EU_HDR_MIDDLE;
   }
   P.f0 = F[first];
-  P.use_tiles = (o->reserved[1] & EU_OPT_NO_TILES) ? 0 : ((o->reserved[1] & 32) ? 3 : 1);  // 3: previous tiled kernel (A/B)
+  P.use_tiles = (o->reserved[1] & EU_OPT_NO_TILES) ? 0 : 1;
   P.src_cw = sources[first]->cw;
   P.src_ch = sources[first]->chh;
   P.src_lx = sources[first]->lx;

@@ -309,8 +309,10 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
 // GEN: some facet of the job uses the generic stepper (PanoTools translation); kept out of the
 // common instantiations because the extra per-facet branch costs ~20 % on multi-facet jobs
 // SP: the job shape the kernel is compiled for (plan.h: eu_render_specs; 0 = any)
+// Kernels compiled for a job shape are asked to fit six blocks per SM (<= 40 registers): the hdr_merge and voronoi
+// shapes are latency-bound at the four to five blocks their 54 / 42 registers allowed (ncu: issue-active 62 %).
 template <int NCH, int TS, int MODE, bool TWINE, int DEG, bool PF, bool GEN, int SP = 0>
-__global__ void __launch_bounds__(TILE_X* TILE_Y) k_render(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(TILE_X* TILE_Y, (SP != 0 && MODE != EU_MODE_SINGLE) ? 6 : 1) k_render(const __grid_constant__ RenderParams P) {
   SpecView<SP> V(P);
   const TargetDev& T = V.trg();
   const FacetDev& f0 = V.f0();
@@ -493,178 +495,7 @@ __device__ __forceinline__ void bulk_row_g2s(float* dst, const float* src, uint3
 }
 
 template <int NCH, int TS, bool TWINE, int DEG, int SP = 0>
-__global__ void __launch_bounds__(TILE_X* TILE_Y, 8) k_render_tiled(const __grid_constant__ RenderParams P) {
-  static_assert(DEG == 1 || DEG == 3, "tile path is built for the bilinear and cubic evaluators");
-  constexpr int ORDER = DEG + 1, H2 = DEG / 2;
-  constexpr int NWARP = TILE_X * TILE_Y / 32;
-  __shared__ __align__(128) float tile[EU_TILE_FLOATS];
-  __shared__ int red[NWARP][4];
-  __shared__ __align__(16) float wslot[TILE_Y][NCH == 3 ? TILE_X * 3 : 4];  // dev_store_pixel
-  __shared__ __align__(8) uint64_t mbar;
-
-  SpecView<SP> V(P);
-  const TargetDev& T = V.trg();
-  const FacetDev& F = V.f0();
-  const SourceDev& S = F.src;
-  const int tid = threadIdx.y * TILE_X + threadIdx.x;
-  const int x = P.col0 + blockIdx.x * TILE_X + threadIdx.x;
-  const int y = P.row0 + blockIdx.y * TILE_Y + threadIdx.y;
-  const bool inside = x < P.col1 && y < P.row1;
-  if (tid == 0) mbar_init(&mbar, 1);
-
-  // ---- phase 1: rays and window origins ------------------------------------------------
-  const int xc = inside ? x : 0, yc = inside ? y : P.row0;
-  const int xf = first_lane_column(xc);
-  float2 c0 = __ldg(P.col_tab + xc), r0 = __ldg(P.row_tab + yc);
-  ColTerm col{c0.x, c0.y};
-  RowTerm row{r0.x, r0.y};
-  ColTerm first = col;
-  if (T.projection == EU_CYLINDRICAL && T.normalize) {
-    float2 f0 = __ldg(P.col_tab + xf);
-    first = ColTerm{f0.x, f0.y};
-  }
-  float r00[3];
-  dev_stepper(T, F.xx, F.yy, F.zz, col, row, first, yc, r00);
-  int face;
-  float cx, cy;
-  bool hit = dev_facet_coordinate(F, r00, face, cx, cy) && inside;
-  Located L = dev_locate(S, DEG, hit ? cx : 0.0f, hit ? cy : 0.0f);
-  // window origin in CONTAINER texel coordinates (container rows start 16-byte aligned)
-  const int lox = L.ix - H2 + P.src_lx, loy = L.iy - H2 + P.src_ly;
-  {
-    int mnx = hit ? lox : INT_MAX, mxx = hit ? lox : INT_MIN, mny = hit ? loy : INT_MAX, mxy = hit ? loy : INT_MIN;
-    mnx = __reduce_min_sync(0xffffffffu, mnx);
-    mxx = __reduce_max_sync(0xffffffffu, mxx);
-    mny = __reduce_min_sync(0xffffffffu, mny);
-    mxy = __reduce_max_sync(0xffffffffu, mxy);
-    if ((tid & 31) == 0) {
-      red[tid >> 5][0] = mnx; red[tid >> 5][1] = mxx; red[tid >> 5][2] = mny; red[tid >> 5][3] = mxy;
-    }
-  }
-  __syncthreads();  // the ONE block-wide barrier: the warps' boxes are in `red`, the mbarrier is initialised
-  // Every warp reduces the eight boxes itself (four loads, four warp reductions) and derives the block's box -
-  // cheaper than a second barrier to hand round what one warp computed.
-  int a0 = 0, wcopy = 0, rows = 0, by0 = 0;
-  {
-    const int l = (tid & 31) < NWARP ? (tid & 31) : 0;
-    int mnx = __reduce_min_sync(0xffffffffu, red[l][0]);
-    int mxx = __reduce_max_sync(0xffffffffu, red[l][1]);
-    int mny = __reduce_min_sync(0xffffffffu, red[l][2]);
-    int mxy = __reduce_max_sync(0xffffffffu, red[l][3]);
-    if (mnx <= mxx) {  // at least one pixel of the block hits the source
-      if constexpr (TWINE) {  // sub-rays stray up to half a pixel from the centre ray
-        int bw = mxx - mnx + 1, bh = mxy - mny + 1;
-        int mx = (bw * 5) / 64 + 2, my = (bh * 5) / 64 + 2;
-        mnx -= mx; mxx += mx; mny -= my; mxy += my;
-        // keep the box inside the container
-        mnx = max(mnx, 0); mny = max(mny, 0);
-        mxx = min(mxx, P.src_cw - ORDER); mxy = min(mxy, P.src_ch - ORDER);
-      }
-      a0 = (mnx * TS) & ~3;  // 16-byte granule within the container row
-      wcopy = (((mxx + ORDER) * TS - a0) + 3) & ~3;
-      rows = mxy - mny + ORDER;
-      by0 = mny;
-      if (rows * EU_TILE_PITCH(wcopy) > EU_TILE_FLOATS || wcopy <= 0 || rows <= 0) rows = 0;
-    }
-  }
-  const int wf = EU_TILE_PITCH(wcopy);
-  const bool staged = rows > 0;
-  if (staged && tid < 32) {
-    // warp 0 arms the barrier and issues one bulk copy per row (the copy is issued from the uniform datapath,
-    // so the lanes take turns); the other warps go straight on to their weights
-    if (tid == 0) mbar_expect_tx(&mbar, (uint32_t)(rows * wcopy) * 4u);
-    __syncwarp();
-    for (int rid = tid; rid < rows; rid += 32)
-      bulk_row_g2s(tile + rid * wf, P.src_base + (ptrdiff_t)(by0 + rid) * S.stride + a0, (uint32_t)wcopy * 4u, &mbar);
-  }
-  // the b-spline weights do not need the texels: computed while the copies fly
-  float wx[ORDER], wy[ORDER];
-  if constexpr (!TWINE && DEG > 1) {
-    dev_window_weights<ORDER>(P.wmat, L.fx, wx);
-    dev_window_weights<ORDER>(P.wmat, L.fy, wy);
-  }
-  if (staged) mbar_wait(&mbar, 0);
-
-  // ---- phase 2: windows ------------------------------------------------------------------
-  if (!inside) return;
-  float px[NCH];
-  if constexpr (!TWINE) {
-    if (!hit) {
-#pragma unroll
-      for (int c = 0; c < NCH; c++) px[c] = 0.0f;
-    } else {
-      if constexpr (DEG > 1) {
-        if (staged)
-          dev_window_sum_w<NCH, TS, DEG, 1>(tile + (loy - by0) * wf + (lox * TS - a0), wf, wx, wy, px);
-        else
-          dev_window_sum_w<NCH, TS, DEG, 0>(P.src_base + (ptrdiff_t)loy * S.stride + (ptrdiff_t)lox * TS, S.stride, wx, wy, px);
-      } else {
-        if (staged)
-          dev_window_eval<NCH, TS, DEG, true>(tile + (loy - by0) * wf + (lox * TS - a0), wf, DEG, P.wmat, L.fx, L.fy, px);
-        else
-          dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)loy * S.stride + (ptrdiff_t)lox * TS, S.stride, DEG,
-                                               P.wmat, L.fx, L.fy, px);
-      }
-      dev_brighten<NCH>(F, px);
-    }
-  } else {
-    // deriv_stepper (stepper.h:1606-1694) + twine_t (twining.h:106-263)
-    float2 c1 = __ldg(P.col_tab + T.width + x), r1 = __ldg(P.row_tab + T.height + y);
-    ColTerm colb{c1.x, c1.y};
-    RowTerm rowb{r1.x, r1.y};
-    ColTerm firstb = colb;
-    if (T.projection == EU_CYLINDRICAL && T.normalize) {
-      float2 f1 = __ldg(P.col_tab + T.width + xf);
-      firstb = ColTerm{f1.x, f1.y};
-    }
-    float du[3], dv[3], help[NCH];
-    dev_stepper(T, F.xx, F.yy, F.zz, colb, row, firstb, y, du);
-    dev_stepper(T, F.xx, F.yy, F.zz, col, rowb, first, y, dv);
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      du[c] = du[c] - r00[c];
-      dv[c] = dv[c] - r00[c];
-    }
-#pragma unroll
-    for (int c = 0; c < NCH; c++) px[c] = 0.0f;
-    const int bx1 = a0 + wcopy, by1 = by0 + rows;
-    for (int k = 0; k < P.n_taps; k++) {
-      float tx, ty, tw;
-      dev_tap<SP != 0>(P, k, tx, ty, tw);
-      float r[3];
-#pragma unroll
-      for (int c = 0; c < 3; c++) r[c] = r00[c] + tx * du[c] + ty * dv[c];
-      int fc;
-      float sx, sy;
-      if (!dev_facet_coordinate(F, r, fc, sx, sy)) {
-#pragma unroll
-        for (int c = 0; c < NCH; c++) help[c] = 0.0f;
-      } else {
-        Located K = dev_locate(S, DEG, sx, sy);
-        const int kx = K.ix - H2 + P.src_lx, ky = K.iy - H2 + P.src_ly;
-        const bool in_box = staged && kx * TS >= a0 && (kx + ORDER) * TS <= bx1 && ky >= by0 && ky + ORDER <= by1;
-        if (in_box)
-          dev_window_eval<NCH, TS, DEG, true>(tile + (ky - by0) * wf + (kx * TS - a0), wf, DEG, P.wmat, K.fx, K.fy, help);
-        else
-          dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)ky * S.stride + (ptrdiff_t)kx * TS, S.stride, DEG,
-                                               P.wmat, K.fx, K.fy, help);
-        dev_brighten<NCH>(F, help);
-      }
-#pragma unroll
-      for (int c = 0; c < NCH; c++) px[c] = EU_WIN_MULADD(tw, help[c], px[c]);
-    }
-  }
-  if (T.unbrighten != 1.0f) {
-    constexpr int NCOL = (NCH == 2 || NCH == 4) ? NCH - 1 : NCH;
-#pragma unroll
-    for (int c = 0; c < NCOL; c++) px[c] *= T.unbrighten;
-  }
-  dev_store_pixel<NCH>(P, T, x, y, px, wslot[threadIdx.y]);
-}
-
-// the kernel above as it was before the single-barrier restructuring (A/B on the GPU: eu_opts_t.reserved[1] bit 5)
-template <int NCH, int TS, bool TWINE, int DEG, int SP = 0>
-__global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled_v1(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_constant__ RenderParams P) {
   static_assert(DEG == 1 || DEG == 3, "tile path is built for the bilinear and cubic evaluators");
   constexpr int ORDER = DEG + 1, H2 = DEG / 2;
   constexpr int NWARP = TILE_X * TILE_Y / 32;
@@ -734,21 +565,22 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled_v1(const __grid
         a0 = (mnx * TS) & ~3;  // 16-byte granule within the container row
         wf = (((mxx + ORDER) * TS - a0) + 3) & ~3;
         rows = mxy - mny + ORDER;
-        if (rows > TILE_X * TILE_Y || rows * wf > EU_TILE_FLOATS || wf <= 0 || rows <= 0) rows = 0;
+        if (rows > TILE_X * TILE_Y || rows * EU_TILE_PITCH(wf) > EU_TILE_FLOATS || wf <= 0 || rows <= 0) rows = 0;
       }
       box[0] = a0; box[1] = mny; box[2] = wf; box[3] = rows;
       if (rows > 0) mbar_expect_tx(&mbar, (uint32_t)(rows * wf) * 4u);
     }
   }
   __syncthreads();
-  const int a0 = box[0], by0 = box[1], wf = box[2], rows = box[3];
+  const int a0 = box[0], by0 = box[1], wcopy = box[2], rows = box[3];
+  const int wf = EU_TILE_PITCH(wcopy);  // row pitch in shared memory
   const bool staged = rows > 0;
   if (staged) {
     // rows are dealt round-robin to the warps (the copy is issued from the uniform datapath, so
     // the lanes of one warp take turns)
     const int rid = (tid & 31) * NWARP + (tid >> 5);
     if (rid < rows)
-      bulk_row_g2s(tile + rid * wf, P.src_base + (ptrdiff_t)(by0 + rid) * S.stride + a0, (uint32_t)wf * 4u, &mbar);
+      bulk_row_g2s(tile + rid * wf, P.src_base + (ptrdiff_t)(by0 + rid) * S.stride + a0, (uint32_t)wcopy * 4u, &mbar);
     mbar_wait(&mbar, 0);
   }
 
@@ -787,7 +619,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled_v1(const __grid
     }
 #pragma unroll
     for (int c = 0; c < NCH; c++) px[c] = 0.0f;
-    const int bx1 = a0 + wf, by1 = by0 + rows;
+    const int bx1 = a0 + wcopy, by1 = by0 + rows;
     for (int k = 0; k < P.n_taps; k++) {
       float tx, ty, tw;
       dev_tap<SP != 0>(P, k, tx, ty, tw);
@@ -830,8 +662,7 @@ static void launch_deg(const RenderParams& P, dim3 grid, dim3 block, cudaStream_
     // and loses for the bilinear one (4 taps/px: C3b 1.56 vs 1.32 ms), where the two block-wide
     // synchronisations cost more than the gathers they replace - so it is used for degree 3 only.
     if (P.use_tiles && P.out && !P.index_out && (P.f0.src.stride & 3) == 0 && !P.any_generic && P.degree == 3) {
-      if (P.use_tiles == 3) k_render_tiled_v1<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P);
-      else k_render_tiled<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P);
+      k_render_tiled<NCH, TS, TWINE, 3><<<grid, block, 0, st>>>(P);
       return;
     }
   }

@@ -16,8 +16,7 @@ bool single(const RenderParams& P, dim3 grid, dim3 block, cudaStream_t st, bool 
   if (P.degree == 3 && with_cubic) {
     if constexpr (!TWINE) {
       if (tiles_ok(P)) {
-        if (P.use_tiles == 3) k_render_tiled_v1<3, TS, false, 3, SP><<<grid, block, 0, st>>>(P);
-        else k_render_tiled<3, TS, false, 3, SP><<<grid, block, 0, st>>>(P);
+        k_render_tiled<3, TS, false, 3, SP><<<grid, block, 0, st>>>(P);
         return true;
       }
     }

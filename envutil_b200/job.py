@@ -269,8 +269,7 @@ class Job:
         o.reserved[0] = 0 if self.padded is None else (1 if self.padded else 2)
         contracted = capi.ARITHMETIC == "contracted" if self.contracted is None else self.contracted
         o.reserved[1] = (capi.OPT_NO_TILES if self.no_tiles else 0) | (capi.OPT_NO_SHAPES if self.no_spec else 0) | \
-            (capi.OPT_NARROW_STORES if self.narrow_stores else 0) | (capi.OPT_CONTRACTED if contracted else 0) | \
-            (32 if getattr(self, "tiled_v1", False) else 0)
+            (capi.OPT_NARROW_STORES if self.narrow_stores else 0) | (capi.OPT_CONTRACTED if contracted else 0)
         taps = (capi.Tap * 1024)()
         tw = C.c_int(0)
         ntaps = lib.eu_make_spread(C.byref(t), C.byref(o), n, fa, self.twine, self.twine_width, self.twine_density,
