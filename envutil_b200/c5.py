@@ -111,9 +111,11 @@ def full_rects(w, h):
     return [(0, h, 0, w)]
 
 
-def row_costs(w, h, W, H, n_strips=N_STRIPS, c_a=31.0, c_b=26.0, c_b0=6.0):
-    """Estimated cost of every panorama row (arbitrary unit ~ picoseconds): stage B's pixels (c_b where a position is
-    in sight, c_b0 elsewhere) + the rows of the six positions that this row adds to stage A (c_a per merged texel)."""
+def row_costs(w, h, W, H, n_strips=N_STRIPS, c_a=28.4, c_b=18.8, c_b0=13.2):
+    """Estimated cost of every panorama row in picoseconds: stage B's pixels (c_b where a position is in sight, c_b0
+    elsewhere: six rays and six mask tests are computed either way) + the rows of the six positions that this row adds
+    to stage A (c_a per merged texel). The constants are measured on a B200 (tools/calibrate_c5_cost.py,
+    profiles/r02f_c5_cost_calibration.json)."""
     ex, ey = _extent(w, h)
     edges = strip_edges(w, h, n_strips)
     lat = np.array([lat_of_row(r, H) for r in range(H)])

@@ -69,8 +69,8 @@ __device__ __forceinline__ float dev_norm3(const float v[3]) {  // zimt/xel.h:75
 //   cylindrical     sin(px)      cos(px)      py           -
 //   rectilinear     px           -            py           -
 //   fisheye/stereo  px           -            py           -          (not separable)
-//   cubemap         px           -            p1           -          p1 = py + (3-face) section_md - refc_md
-//   biatan6         tan(px pi/4) -            tan(p1 pi/4) -
+//   cubemap         px           -            p1           face       p1 = py + (3-face) section_md - refc_md
+//   biatan6         tan(px pi/4) -            tan(p1 pi/4) face       (face = y / width, as integer bits)
 // `first` is the column term of the same lane in the first vector of the pixel's 512-px segment
 // (the cylindrical stepper keeps rcp_length from there, stepper.h:766-769).
 // ------------------------------------------------------------------------------------------
@@ -93,6 +93,7 @@ __device__ __forceinline__ void dev_row_term(const TargetDev& T, float py, int y
     float p1 = py + (3 - face) * T.section_md - T.refc_md;
     if (T.projection == EU_BIATAN6) p1 = eu_tanf(p1 * (float)(EU_PI / 4.0));
     r.a = p1;
+    r.b = __int_as_float(face);  // the face of the row, for dev_stepper (an integer division per pixel otherwise)
   }
 }
 
@@ -157,19 +158,22 @@ __device__ __forceinline__ void dev_stepper(const TargetDev& T, const float* xx,
       break;
     }
     default: {  // EU_CUBEMAP, EU_BIATAN6 (stepper.h:1289-1345,1478-1560)
-      int face = y / T.width;
+      const int face = __float_as_int(row.b);  // y / width, from the row table
       float p1 = row.a, p0 = col.a;
       float ccc[3], vvv[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        // the +-1.0 literals promote the sums to double in the reference
+        // The +-1.0 literals promote these sums to double in the reference: float(double(a) + double(b)) for two
+        // floats a, b. That is the float sum a + b, bit for bit - the double sum is exact unless the exponents are
+        // more than 29 binades apart, and then both roundings return the larger operand (checked on 4e8 random
+        // pairs including subnormals and infinities) - so the conversions and the double adds are left out.
         switch (face) {
-          case CM_LEFT: ccc[i] = (float)(-1.0 * xx[i] + (double)(p1 * yy[i])); vvv[i] = zz[i]; break;
-          case CM_RIGHT: ccc[i] = (float)(1.0 * xx[i] + (double)(p1 * yy[i])); vvv[i] = -zz[i]; break;
-          case CM_TOP: ccc[i] = (float)(-1.0 * yy[i] - (double)(p1 * zz[i])); vvv[i] = -xx[i]; break;
-          case CM_BOTTOM: ccc[i] = (float)(1.0 * yy[i] + (double)(p1 * zz[i])); vvv[i] = -xx[i]; break;
-          case CM_FRONT: ccc[i] = (float)((double)(p1 * yy[i]) + 1.0 * zz[i]); vvv[i] = xx[i]; break;
-          default: ccc[i] = (float)((double)(p1 * yy[i]) - 1.0 * zz[i]); vvv[i] = -xx[i]; break;
+          case CM_LEFT: ccc[i] = -xx[i] + p1 * yy[i]; vvv[i] = zz[i]; break;
+          case CM_RIGHT: ccc[i] = xx[i] + p1 * yy[i]; vvv[i] = -zz[i]; break;
+          case CM_TOP: ccc[i] = -yy[i] - p1 * zz[i]; vvv[i] = -xx[i]; break;
+          case CM_BOTTOM: ccc[i] = yy[i] + p1 * zz[i]; vvv[i] = -xx[i]; break;
+          case CM_FRONT: ccc[i] = p1 * yy[i] + zz[i]; vvv[i] = xx[i]; break;
+          default: ccc[i] = p1 * yy[i] - zz[i]; vvv[i] = -xx[i]; break;
         }
       }
 #pragma unroll

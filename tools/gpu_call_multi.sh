@@ -1,5 +1,5 @@
 #!/bin/bash
-# One box, N GPUs (gpurun --gpus N): the 2-GPU tests and the configs[4] row-band bench on 2..N ranks, plus the replica line.
+# One box, N GPUs (gpurun --gpus N): the configs[4] row-band bench on 1, 2 .. N ranks, the reference arm, the replica line.
 set -u
 cd "$(dirname "$0")/.."
 N=${1:-2}
@@ -8,9 +8,8 @@ mkdir -p "$OUT"
 step() { name=$1; shift; echo "== $name" | tee -a "$OUT/summary.txt"; s=$(date +%s); timeout "$1" "${@:2}" > "$OUT/$name.log" 2>&1; echo "   rc=$? $(( $(date +%s) - s )) s" | tee -a "$OUT/summary.txt"; }
 RUN="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 nvidia-smi topo -m > "$OUT/topo.txt" 2>&1
-numactl -H > "$OUT/numa.txt" 2>&1 || lscpu | grep -i numa > "$OUT/numa.txt"
-step pytest_2gpu 600 python -m pytest tests/test_gpu_peer_frame.py -q -m gpu -s
-for n in 2 4 8; do
+lscpu | grep -i -E "numa|model name|^cpu\(s\)" > "$OUT/numa.txt" 2>&1
+for n in $N 4 2; do
   if [ $n -le $N ]; then
     step bench_n$n 900 $RUN --nproc-per-node $n --master-port $((29600 + n)) bench.py --gpus $n --steps 20 --warmup 5
     grep '^{"metric"' "$OUT/bench_n$n.log" | tail -n 1 > "$OUT/bench_n$n.json"
@@ -18,8 +17,7 @@ for n in 2 4 8; do
 done
 step bench_n1_c5 600 python bench.py --workload c5 --steps 20 --warmup 5
 grep '^{"metric"' "$OUT/bench_n1_c5.log" | tail -n 1 > "$OUT/bench_n1_c5.json"
-step bench_n${N}_equal 900 $RUN --nproc-per-node $N --master-port 29650 bench.py --gpus $N --steps 20 --warmup 5 --c5-plan full
-grep '^{"metric"' "$OUT/bench_n${N}_equal.log" | tail -n 1 > "$OUT/bench_n${N}_fullmerge.json"
 step bench_n${N}_replicas 900 $RUN --nproc-per-node $N --master-port 29660 bench.py --gpus $N --steps 20 --warmup 5 --workload c2 --partition frames
 grep '^{"metric"' "$OUT/bench_n${N}_replicas.log" | tail -n 1 > "$OUT/bench_n${N}_replicas.json"
+if [ $N -le 2 ]; then step pytest_2gpu 600 python -m pytest tests/test_gpu_peer_frame.py -q -m gpu -s; fi
 cat "$OUT/summary.txt"
