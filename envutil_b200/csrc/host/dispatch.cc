@@ -32,8 +32,8 @@ struct cuda_dispatch : public dispatch_base {
     o.solo = a.solo;
     o.support_min = a.support_min;
     o.tile_size = a.tile_size;
-    o.reserved[0] = a.padded ? 1 : 0;
-    o.reserved[1] = a.no_tiles ? 1 : 0;
+    o.reserved[0] = a.padded ? 1 : (a.plain_texels ? 2 : 0);
+    o.reserved[1] = (a.no_tiles ? EU_OPT_NO_TILES : 0) | (a.contracted ? EU_OPT_CONTRACTED : 0);
     std::vector<eu_facet_t> fv;
     std::vector<eu_source_h> sv;
     float stage_ms = 0, h2d_ms = 0;

@@ -50,7 +50,9 @@ struct arguments {
   std::vector<facet_spec> facet_spec_v;
   std::vector<std::string> addenda;
   // back-end options (not in the reference)
-  bool padded = false, no_tiles = false, dry_run = false;
+  // back-end options (not part of envutil's surface): --padded / --plain_texels force the 16- / 12-byte RGB texel layout
+  // (default: the library's rule), --no_tiles the direct-gather kernels, --contracted the fused multiply-add arithmetic
+  bool padded = false, plain_texels = false, no_tiles = false, contracted = false, dry_run = false;
   int device = 0;
 
   // parse the command line the reference's way; returns 0 or a negative eu_status_t, with the
