@@ -140,6 +140,10 @@ SYMBOLS = {
     "eu_frame_export": (C.c_int, [C.c_void_p, C.c_char_p]),
     "eu_frame_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "eu_frame_close": (C.c_int, [C.c_void_p]),
+    "eu_screen_lut": (None, [C.POINTER(C.c_float)]),
+    "eu_render_screen": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet), C.POINTER(SourceH),
+                                   C.POINTER(Tap), C.c_int, C.c_void_p, C.POINTER(Timing)]),
+    "eu_to_screen_device": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]),
     "eu_debug_planes": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),
                                   C.POINTER(SourceH), C.c_void_p]),
     "eu_debug_tie_plane": (C.c_int, [C.POINTER(Target), C.POINTER(Opts), C.c_int, C.POINTER(Facet),

@@ -95,6 +95,7 @@ struct Context {
   size_t out_cap = 0;
   int32_t* d_index = nullptr;
   size_t index_cap = 0;
+  float* d_screen_lut = nullptr;  // eu_screen_lut's table, uploaded on first use
 };
 Context g;
 thread_local char g_err[512] = "";
@@ -936,6 +937,8 @@ void eu_shutdown(void) {
   }
   cudaFree(g.d_out);
   cudaFree(g.d_index);
+  cudaFree(g.d_screen_lut);
+  g.d_screen_lut = nullptr;
   cudaDeviceSynchronize();
   for (auto& e : g.ev) cudaEventDestroy(e);
   for (auto& j : g.jobs) {
@@ -1349,6 +1352,67 @@ int eu_job_wait(eu_job_h job, eu_timing_t* timing) {
   return EU_OK;
 }
 
+// ---- tethered output (to_screen_t, envutil_payload.cc:298-413) --------------------------------------
+static int screen_lut_ready(cudaStream_t st) {
+  if (g.d_screen_lut) return EU_OK;
+  float lut[257];
+  eu_screen_lut(lut);
+  CK(cudaMalloc(&g.d_screen_lut, sizeof(lut)));
+  // first use only: a blocking copy from the stack, then a device-wide synchronise, so that the table is in place
+  // for whichever stream reads it first (a pageable copy this small may return before its DMA has finished)
+  CK(cudaMemcpy(g.d_screen_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());
+  (void)st;
+  return EU_OK;
+}
+
+int eu_to_screen_device(const float* d_pixels, int nchannels, size_t n_pixels, uint32_t* d_out, void* cuda_stream) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!d_pixels || !d_out) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (nchannels < 1 || nchannels > 4) return fail(EU_ERR_ARGUMENT, "%d channels", nchannels);
+  if ((nchannels == 4 && (reinterpret_cast<uintptr_t>(d_pixels) & 15)) || (nchannels == 2 && (reinterpret_cast<uintptr_t>(d_pixels) & 7)))
+    return fail(EU_ERR_ARGUMENT, "pixels of %d channels must be %d-byte aligned", nchannels, nchannels * 4);
+  rc = screen_lut_ready((cudaStream_t)cuda_stream);
+  if (rc) return rc;
+  CK(eu_launch_to_screen(d_pixels, nchannels, n_pixels, g.d_screen_lut, d_out, (cudaStream_t)cuda_stream));
+  return EU_OK;
+}
+
+int eu_render_screen(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+                     const eu_source_h* sources, const eu_tap_t* taps, int n_taps, uint32_t* out, eu_timing_t* timing) {
+  int rc = need_up();
+  if (rc) return rc;
+  if (!t || !out) return fail(EU_ERR_ARGUMENT, "null argument");
+  if (t->width <= 0 || t->height <= 0 || t->nchannels < 1) return fail(EU_ERR_ARGUMENT, "target not prepared");
+  const size_t npx = (size_t)out_width(t) * out_height(t);
+  rc = grow(g.d_out, g.out_cap, npx * t->nchannels);
+  if (rc) return rc;
+  rc = grow(g.d_index, g.index_cap, npx);
+  if (rc) return rc;
+  rc = screen_lut_ready(g.stream);
+  if (rc) return rc;
+  eu_target_t tt = *t;
+  tt.gain = 0.0;  // work() skips the un-brighten stage when it runs tethered (envutil_payload.cc:491)
+  eu_timing_t tm;
+  rc = eu_render_rows(&tt, o, n_facets, facets, sources, taps, n_taps, 0, out_height(t), g.d_out, g.stream, &tm);
+  if (rc) return rc;
+  uint32_t* d_scr = reinterpret_cast<uint32_t*>(g.d_index);
+  CK(eu_launch_to_screen(g.d_out, t->nchannels, npx, g.d_screen_lut, d_scr, g.stream));
+  tm.launches += 1;
+  CK(cudaEventRecord(g.ev[1], g.stream));
+  CK(cudaStreamWaitEvent(g.down_stream, g.ev[1], 0));
+  CK(cudaEventRecord(g.ev[2], g.down_stream));
+  CK(cudaMemcpyAsync(out, d_scr, npx * sizeof(uint32_t), cudaMemcpyDeviceToHost, g.down_stream));
+  CK(cudaEventRecord(g.ev[3], g.down_stream));
+  CK(cudaStreamSynchronize(g.down_stream));
+  if (timing) {
+    *timing = tm;
+    CK(cudaEventElapsedTime(&timing->d2h_ms, g.ev[2], g.ev[3]));
+  }
+  return EU_OK;
+}
+
 int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
                     const eu_source_h* sources, int32_t* index_out) {
   int rc = need_up();
@@ -1505,7 +1569,12 @@ int eu_source_write_rect(eu_source_h s, const float* pixels, size_t src_pitch_fl
     float* tmp = nullptr;
     const size_t rowf = (size_t)(col1 - col0) * s->nch;
     CK(cudaMallocAsync((void**)&tmp, rowf * (row1 - row0) * sizeof(float), st));
-    cudaError_t e = cudaMemcpy2DAsync(tmp, rowf * sizeof(float), pixels, src_pitch_floats * sizeof(float), wb, row1 - row0, kind, st);
+    // a rectangle whose rows follow each other in the caller's buffer travels as ONE contiguous copy: measured on a B200
+    // box, the pitched form of the same bytes is 10 % slower alone and overlaps a concurrent download far worse
+    // (configs[4], one GPU: upload || download 58.7 ms against 48.9 ms, profiles/r02h_probe_overlap.txt)
+    cudaError_t e = src_pitch_floats == rowf
+                        ? cudaMemcpyAsync(tmp, pixels, wb * (size_t)(row1 - row0), kind, st)
+                        : cudaMemcpy2DAsync(tmp, rowf * sizeof(float), pixels, src_pitch_floats * sizeof(float), wb, row1 - row0, kind, st);
     if (e == cudaSuccess) e = eu_launch_pad_texels(tmp, (int)rowf, dst, s->pitch / 4, col1 - col0, row1 - row0, s->nch, st);
     cudaFreeAsync(tmp, st);
     if (e != cudaSuccess) return fail(EU_ERR_CUDA, "write_rect: %s", cudaGetErrorString(e));

@@ -38,7 +38,7 @@ const option option_table[] = {
     {"--input_colour_space", 1}, {"--pto", 1}, {"--pto_line", 1}, {"--solo", 1}, {"--mask_for", 1},
     {"--nchannels", 1},
     // back-end
-    {"--device", 1}, {"--padded", 0}, {"--plain_texels", 0}, {"--no_tiles", 0}, {"--contracted", 0}, {"--dry_run", 0}};
+    {"--device", 1}, {"--padded", 0}, {"--plain_texels", 0}, {"--no_tiles", 0}, {"--contracted", 0}, {"--screen_out", 1}, {"--dry_run", 0}};
 
 double glean(const std::string& s) { return s.empty() ? 0.0 : std::stod(s); }
 int iglean(const std::string& s) { return s.empty() ? 0 : std::stoi(s); }
@@ -126,6 +126,7 @@ int arguments::init(int argc, const char** argv) {
   no_tiles = has("--no_tiles");
   plain_texels = has("--plain_texels");
   contracted = has("--contracted");
+  screen_out = str("--screen_out", "");
   dry_run = has("--dry_run");
   if (prefilter_degree < 0) prefilter_degree = spline_degree;
   t.projection = projection_from_name(projection_str);

@@ -3,6 +3,7 @@
 // 2336,1885,425): per facet find-or-stage the source (the asset cache lives in the library),
 // render, write the raster, conclude the cycle.
 #include <chrono>
+#include <cstdint>
 #include <cstdio>
 
 #include <algorithm>
@@ -85,8 +86,36 @@ struct cuda_dispatch : public dispatch_base {
     int n_taps = ninputs == 9 ? (int)taps.size() : 0;  // ninputs == 9 <=> twining (envutil_main.cc:1673)
     // a cropped output (p-line S) has the crop's size (envutil_payload.cc:440-443)
     const int ow = t.crop_width > 0 ? t.crop_width : t.width, oh = t.crop_width > 0 ? t.crop_height : t.height;
-    std::vector<float> out((size_t)ow * oh * nchannels);
     eu_timing_t tm{};
+    if (a.tethered || !a.screen_out.empty()) {
+      // work()'s tethered branch (envutil_payload.cc:524-531): act + to_screen_t into the viewer's frame buffer
+      std::vector<std::uint32_t> own;
+      std::uint32_t* frame = a.p_screen_data;
+      if (!frame) {
+        own.resize((size_t)ow * oh);
+        frame = own.data();
+      }
+      rc = eu_render_screen(&t, &o, (int)fv.size(), fv.data(), sv.data(), taps.data(), n_taps, frame, &tm);
+      if (rc) {
+        fprintf(stderr, "envutil_b200: %s\n", eu_last_error());
+        return rc;
+      }
+      if (a.verbose)
+        printf("frame rendering time: %.3f ms (device), staging %.3f ms, h2d %.3f ms, d2h %.3f ms, %d launches\n", tm.render_ms,
+               stage_ms, h2d_ms, tm.d2h_ms, tm.launches);
+      if (!a.screen_out.empty()) {
+        FILE* fp = fopen(a.screen_out.c_str(), "wb");
+        if (!fp || fwrite(frame, sizeof(std::uint32_t), (size_t)ow * oh, fp) != (size_t)ow * oh) {
+          fprintf(stderr, "envutil_b200: cannot write '%s'\n", a.screen_out.c_str());
+          if (fp) fclose(fp);
+          return EU_ERR_ARGUMENT;
+        }
+        fclose(fp);
+      }
+      eu_cycle();
+      return 0;
+    }
+    std::vector<float> out((size_t)ow * oh * nchannels);
     rc = eu_render(&t, &o, (int)fv.size(), fv.data(), sv.data(), taps.data(), n_taps, out.data(), &tm);
     if (rc) {
       fprintf(stderr, "envutil_b200: %s\n", eu_last_error());

@@ -9,6 +9,7 @@
 // The per-pixel work behind payload() is not here: cuda_dispatch::payload marshals `args` into
 // the POD structs of include/envutil_b200.h and calls libenvutil_b200.so.
 #pragma once
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -54,6 +55,12 @@ struct arguments {
   // (default: the library's rule), --no_tiles the direct-gather kernels, --contracted the fused multiply-add arithmetic
   bool padded = false, plain_texels = false, no_tiles = false, contracted = false, dry_run = false;
   int device = 0;
+  // tethered output (reference envutil_basic.h:637-638, envutil_main.cc:1650,1791): payload() stores one uint32 sRGBA
+  // value per pixel into p_screen_data (the viewer's frame buffer) instead of writing an image file. --screen_out FILE
+  // (back-end option) runs a job that way without a viewer and writes the buffer to FILE as raw little-endian uint32.
+  bool tethered = false;
+  std::uint32_t* p_screen_data = nullptr;
+  std::string screen_out;
 
   // parse the command line the reference's way; returns 0 or a negative eu_status_t, with the
   // reason in `error` (the reference asserts / exit(-1)s instead)

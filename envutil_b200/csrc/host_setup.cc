@@ -281,6 +281,23 @@ int eu_cubemap_metrics(int face_px, double hfov, int support_min, int tile_size,
   return EU_OK;
 }
 
+// The knots of to_screen_t's transfer function (lut_based_tf's constructor, envutil_payload.cc:243-267, with
+// fn = RGB2sRGB<double, double> :221-231 and amplify = 255). fn is held as std::function<float(float)>, so the knot
+// position i / 255.0 is narrowed to float on the way in and the curve's value on the way out, before the
+// multiplication by 255 (in double) and the store into the float core. lut[256] is the NATURAL brace value
+// (2 c[255] - c[254], zimt/brace.h:254-266): the evaluator only ever multiplies it by 0.
+void eu_screen_lut(float lut[257]) {
+  for (int i = 0; i < 256; i++) {
+    const double x = i / 255.0;
+    const double v = (double)(float)x;
+    double r = 1.055 * std::pow(v, 0.41666666666666667) - 0.055;
+    if (v <= 0.0031308) r = 12.92 * v;
+    const float fr = (float)r;
+    lut[i] = (float)((double)fr * 255.0);
+  }
+  lut[256] = 2.0f * lut[255] - lut[254];
+}
+
 }  // extern "C"
 
 // arguments::twine_setup (envutil_main.cc:1405-1616) incl. its quirks: `solo > 0` (not >= 0),

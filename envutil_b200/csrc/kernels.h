@@ -58,3 +58,6 @@ cudaError_t eu_launch_alpha_apply(const unsigned char* mask, float* tmp_a, float
 // rows of nch-float texels -> 16-byte texels, cw x chh of them, destination rows dst_pitch_texels apart
 cudaError_t eu_launch_pad_texels(const float* src, int src_pitch, float* dst, int dst_pitch_texels, int cw, int chh, int nch,
                                  cudaStream_t st);
+// tethered output (screen.cu): n pixels of nch interleaved floats -> uint32 sRGBA through the 257-entry table of
+// eu_screen_lut (to_screen_t, envutil_payload.cc:298-413)
+cudaError_t eu_launch_to_screen(const float* px, int nch, size_t n, const float* lut, uint32_t* out, cudaStream_t st);

@@ -142,6 +142,23 @@ class Engine:
         self.launches += tm.launches
         return out
 
+    def render_screen(self, job, sources=None, structs=None):
+        """The job as a tethered frame: H x W uint32 sRGBA (eu_render_screen; to_screen_t of the reference)."""
+        st = structs or job.structs(self.lib)
+        t, fa, o, taps, ntaps = st
+        hs = sources if sources is not None else self.stage(job, st)
+        out = np.empty(t.out_shape(), dtype=np.uint32)
+        tm = capi.Timing()
+        try:
+            capi.check(self.lib.eu_render_screen(C.byref(t), C.byref(o), len(job.facets), fa, hs, taps, ntaps,
+                                                 out.ctypes.data, C.byref(tm)), self.lib)
+        finally:
+            if sources is None:
+                self.release(hs)
+        self.last_timing = tm
+        self.launches += tm.launches
+        return out
+
     def render_rows(self, job, sources, structs, row0, row1, d_out, stream=0, timed=True):
         """Rows [row0,row1) into device memory at address d_out, on CUDA stream `stream`."""
         t, fa, o, taps, ntaps = structs

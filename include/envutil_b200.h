@@ -309,6 +309,21 @@ int eu_frame_export(const float* d_frame, unsigned char handle[EU_FRAME_HANDLE_B
 int eu_frame_open(const unsigned char handle[EU_FRAME_HANDLE_BYTES], float** d_frame);
 int eu_frame_close(float* d_frame);
 
+/* Tethered output: the frame as the reference hands it to its viewer (visor) instead of writing an image file -
+ * one uint32 sRGBA value per pixel (A<<24 | B<<16 | G<<8 | R). Replaces `act + to_screen_t` in work()
+ * (reference envutil_payload.cc:298-413,524-531; the frame buffer is args.p_screen_data, envutil_main.cc:1791):
+ * every channel goes through a 256-knot table of 255 * sRGB(x) with linear interpolation (lut_based_tf, :243-283)
+ * and is truncated; one channel = grey, opaque; two = grey + alpha; three = opaque RGB; four = RGBA. As in the
+ * reference, a 'single' job's un-brighten gain (eu_target_t.gain) is NOT applied on this path (:491).
+ * eu_render_screen = eu_render with that store: out is a host buffer of width*height uint32 - a third of the float
+ * frame's bytes cross PCIe. eu_to_screen_device converts n_pixels of nchannels interleaved floats already in device
+ * memory (asynchronous on cuda_stream). eu_screen_lut fills the table (256 knots + one brace value; host, no GPU). */
+void eu_screen_lut(float lut[257]);
+int eu_render_screen(const eu_target_t* t, const eu_opts_t* o, int n_facets, const eu_facet_t* facets,
+                     const eu_source_h* sources, const eu_tap_t* taps, int n_taps, uint32_t* out,
+                     eu_timing_t* timing);
+int eu_to_screen_device(const float* d_pixels, int nchannels, size_t n_pixels, uint32_t* d_out, void* cuda_stream);
+
 /* Index plane for bit-exact parity checks: per target pixel the cube face hit (single cubemap
  * facet) or the winning facet of the panorama synopsis (-1: no facet hit). Host buffer w*h. */
 int eu_debug_planes(const eu_target_t* t, const eu_opts_t* o, int n_facets,

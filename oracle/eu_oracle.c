@@ -1938,3 +1938,55 @@ static int orc_render_impl(const eu_target_t* t, const eu_opts_t* o, int nf, con
   free(F);
   return 0;
 }
+
+/* ---- tethered output: lut_based_tf + to_screen_t (envutil_payload.cc:221-413) --------------------------------
+ * The knots: `std::function<float(float)> fn = RGB2sRGB<double, double>` is called with the double x = i / 255.0,
+ * so x is narrowed to float on the way in and the result on the way out; `double y = fn(x) * 255.0` is stored
+ * into the float core (:262-267). Degree 1 needs no prefilter. The evaluator is the safe 1-D one: clamp to
+ * [0, 255] (NATURAL, zimt/eval.h:2101-2110), floor/remainder split, _eval_linear level 0 (zimt/eval.h:1037-1059):
+ * sum = c[i] * (1 - t); sum += c[i + 1] * t. c[256] is the NATURAL brace 2 c[255] - c[254]; it only ever meets t = 0. */
+void orc_screen_lut(float lut[257]) {
+  for (int i = 0; i < 256; i++) {
+    double x = i / 255.0;
+    double v = (double)(float)x;
+    double r = 1.055 * pow(v, 0.41666666666666667) - 0.055;
+    if (v <= 0.0031308) r = 12.92 * v;
+    float fr = (float)r;
+    double y = (double)fr * 255.0;
+    lut[i] = (float)y;
+  }
+  lut[256] = 2.0f * lut[255] - lut[254];
+}
+
+static uint32_t screen_channel(const float* lut, float in) {
+  float c = in * 255.0f;
+  if (c < 0.0f) c = 0.0f;
+  else if (c > 255.0f) c = 255.0f;
+  float fl = floorf(c), t = c - fl;
+  int i = (int)fl;
+  float wl = 1.0f - t, wr = t;
+  float sum = lut[i];
+  sum *= wl;
+  float help = lut[i + 1];
+  help = help * wr;
+  sum += help;
+  return (uint32_t)sum;
+}
+
+void orc_to_screen(const float* px, int nch, size_t n, uint32_t* out) {
+  float lut[257];
+  orc_screen_lut(lut);
+  for (size_t k = 0; k < n; k++) {
+    const float* p = px + k * (size_t)nch;
+    uint32_t c[4];
+    for (int j = 0; j < nch; j++) c[j] = screen_channel(lut, p[j]);
+    uint32_t o;
+    switch (nch) {
+      case 1: o = 0xFF000000u | (c[0] << 16) | (c[0] << 8) | c[0]; break;
+      case 2: o = (c[1] << 24) | (c[0] << 16) | (c[0] << 8) | c[0]; break;
+      case 3: o = 0xFF000000u | (c[2] << 16) | (c[1] << 8) | c[0]; break;
+      default: o = (c[3] << 24) | (c[2] << 16) | (c[1] << 8) | c[0]; break;
+    }
+    out[k] = o;
+  }
+}

@@ -124,6 +124,33 @@ def reference_render(job, kind="pm", extra_args=(), keep_log=False):
         return (img, r.stdout) if keep_log else img
 
 
+def reference_screen(job, kind="pm", refine=False):
+    """The job through the reference's TETHERED pipeline (handle_job -> core(tethered) -> act + to_screen_t,
+    envutil_main.cc:1755-1868, envutil_payload.cc:298-413,524-531): H x W uint32 sRGBA, as visor's frame buffer
+    receives it. The oracle build's visor stub (oracle/shim/visor_stub/visor.h) runs one job described by the
+    environment instead of visor's shared-memory queue."""
+    exe = ref_binary(kind)
+    assert exe, "oracle/_ref is not built (make -C oracle ref)"
+    t = job.structs()[0]
+    oh, ow = t.out_shape()
+    with tempfile.TemporaryDirectory(prefix="euref_") as d:
+        paths = []
+        for i, f in enumerate(job.facets):
+            p = os.path.join(d, f"facet{i}.euf")
+            euf.write_euf(p, f.image)
+            paths.append(p)
+        argf, outp = os.path.join(d, "args.txt"), os.path.join(d, "frame.u32")
+        with open(argf, "w") as fh:
+            fh.write("\n".join(["visor"] + job.cli_args(paths, os.path.join(d, "none.euf"))) + "\n")
+        env = dict(os.environ, EU_TETHER_SPEC="%d %d %r %r %r %r 1.0 %d" % (ow, oh, float(job.yaw), float(job.pitch),
+                                                                          float(job.roll), float(job.hfov), int(refine)),
+                   EU_TETHER_ARGS=argf, EU_TETHER_OUT=outp)
+        r = subprocess.run([exe, "+"], capture_output=True, text=True, env=env)
+        if r.returncode != 0 or not os.path.exists(outp):
+            raise RuntimeError(f"reference (tethered) failed ({r.returncode})\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+        return np.fromfile(outp, dtype="<u4").reshape(oh, ow)
+
+
 def compare(a, b, eps=1e-3):
     """max and RMS of |a-b| / max(|b|, eps), plus the count of differing values."""
     a = np.asarray(a, dtype=np.float64)

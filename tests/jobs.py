@@ -356,3 +356,9 @@ SPLITS = {
     "split_lens3_d1": ("lens3_voronoi_sph_d1", []),
     "split_tr3_solo2_d1_tw2": ("tr3_voronoi_sph_d1", ["--solo", "2", "--twine", "2"]),
 }
+
+# tethered output (to_screen_t, envutil_payload.cc:298-413): jobs whose uint32 sRGBA frame is pinned by the reference's
+# own tethered pipeline (tests/golden/screen.json, tools/make_golden_screen.py). One to four channels, twining, both
+# synopses, and a 'single' job with a gain (which the tethered path does not apply, envutil_payload.cc:491).
+SCREEN_JOBS = ["ll_rect_d1", "cm_sph_d3", "ll_fish_d1_tw4", "voronoi4_sph_d1", "hdr3_rect_d1", "grey_ll_rect_d3",
+               "ga_cm_sph_d3", "ga2_voronoi_sph_d1", "rgba1_rect_d1", "rgba4_voronoi_sph_d1", "single1_hdr3_d1"]

@@ -207,6 +207,26 @@ def test_cli_output_equals_reference_output(cli, tmp_path, name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cm_sph_d3", "ga2_voronoi_sph_d1", "single1_hdr3_d1"])
+def test_cli_tethered_frame_equals_reference_frame(cli, tmp_path, name):
+    """The same command line, rendered tethered (--screen_out: payload() stores uint32 sRGBA as it would into visor's
+    frame buffer), equals the frame the reference's own tethered pipeline produced (tests/golden/screen.json)."""
+    import hashlib
+    import json
+    job = jobs.JOBS[name]
+    paths = _write_facets(job, str(tmp_path))
+    scr = str(tmp_path / "frame.u32")
+    r = subprocess.run([cli] + job.cli_args(paths, str(tmp_path / "none.euf")) + ["--screen_out", scr], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    man = json.load(open(os.path.join(harness.GOLDEN, "screen.json")))[name]
+    frame = np.fromfile(scr, dtype="<u4")
+    assert frame.size == man["shape"][0] * man["shape"][1]
+    assert hashlib.sha256(frame.tobytes()).hexdigest() == man["sha256"]
+    assert not os.path.exists(str(tmp_path / "none.euf"))  # tethered jobs write no image file
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(jobs.CLI_EXTRAS))
 def test_cli_twf_filter_equals_reference(cli, tmp_path, name):
     """--twf_file / --twine_normalize / --twine_width scaling: same command line, same bits."""
