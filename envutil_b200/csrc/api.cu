@@ -96,6 +96,17 @@ struct Context {
   int32_t* d_index = nullptr;
   size_t index_cap = 0;
   float* d_screen_lut = nullptr;  // eu_screen_lut's table, uploaded on first use
+  // eu_source_write_rect into 16-byte-texel containers: the rectangle lands in one of these scratch buffers (H2D on a
+  // copy stream of its own) and a kernel on the caller's stream widens it into the container. With a ring of them
+  // the copies of consecutive rectangles follow each other without waiting for the kernels in between.
+  struct RectSlot {
+    float* buf = nullptr;
+    size_t cap = 0;
+    cudaEvent_t copied = nullptr, freed = nullptr;
+    bool used = false;
+  } rect_ring[3];
+  int next_rect = 0;
+  cudaStream_t rect_stream = nullptr;
 };
 Context g;
 thread_local char g_err[512] = "";
@@ -606,6 +617,18 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     for (int i = 0; i < nf; i++) F[i].hdr_kind = (i == lo) ? EU_HDR_LOW : (i == hi) ? EU_HDR_HIGH : EU_HDR_MIDDLE;
   }
   P.f0 = F[first];
+  {  // RenderParams::cube_tab: the face vectors of the cubemap / biatan6 steppers for f0, signs folded in
+    const float *xx = P.f0.xx, *yy = P.f0.yy, *zz = P.f0.zz;
+    const float* rows[6][3] = {{xx, yy, zz}, {xx, yy, zz}, {yy, zz, xx}, {yy, zz, xx}, {zz, yy, xx}, {zz, yy, xx}};
+    // CM_LEFT -xx + p1 yy, zz | RIGHT xx + p1 yy, -zz | TOP -yy - p1 zz, -xx | BOTTOM yy + p1 zz, -xx |
+    // FRONT p1 yy + zz, xx | BACK p1 yy - zz, -xx      (stepper.h:1304-1331)
+    const float sign[6][3] = {{-1, 1, 1}, {1, 1, -1}, {-1, -1, -1}, {1, 1, -1}, {1, 1, 1}, {-1, 1, -1}};
+    for (int f = 0; f < 6; f++)
+      for (int k = 0; k < 3; k++) {
+        for (int i = 0; i < 3; i++) P.cube_tab[f][4 * k + i] = sign[f][k] < 0 ? -rows[f][k][i] : rows[f][k][i];
+        P.cube_tab[f][4 * k + 3] = 0.0f;
+      }
+  }
   P.use_tiles = (o->reserved[1] & EU_OPT_NO_TILES) ? 0 : 1;
   P.src_cw = sources[first]->cw;
   P.src_ch = sources[first]->chh;
@@ -711,6 +734,15 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
     int d = o->spline_degree;
     for (int row = 0; row <= d; row++)
       for (int k = 0; k <= d; k++) P.wmat[row * (d + 1) + k] = (float)eu_bspline_weights[d][row][k];
+    // the shape kernels skip the cubic matrix's zero terms (dev_window_weights<4, true>): only if they ARE +0
+    if (d == 3) {
+      const int z[4] = {3, 5, 7, 11};
+      for (int i : z) {
+        uint32_t bits;
+        memcpy(&bits, &P.wmat[i], 4);
+        if (bits != 0u) P.spec = 0;
+      }
+    }
   }
   return EU_OK;
 }
@@ -939,6 +971,15 @@ void eu_shutdown(void) {
   cudaFree(g.d_index);
   cudaFree(g.d_screen_lut);
   g.d_screen_lut = nullptr;
+  for (auto& R : g.rect_ring) {
+    cudaFree(R.buf);
+    if (R.copied) cudaEventDestroy(R.copied);
+    if (R.freed) cudaEventDestroy(R.freed);
+    R = Context::RectSlot();
+  }
+  if (g.rect_stream) cudaStreamDestroy(g.rect_stream);
+  g.rect_stream = nullptr;
+  g.next_rect = 0;
   cudaDeviceSynchronize();
   for (auto& e : g.ev) cudaEventDestroy(e);
   for (auto& j : g.jobs) {
@@ -1566,17 +1607,38 @@ int eu_source_write_rect(eu_source_h s, const float* pixels, size_t src_pitch_fl
     cudaGetLastError();
   }
   if (s->tstride != s->nch) {  // 16-byte texels: the rectangle lands in a scratch buffer and is widened on the device
-    float* tmp = nullptr;
     const size_t rowf = (size_t)(col1 - col0) * s->nch;
-    CK(cudaMallocAsync((void**)&tmp, rowf * (row1 - row0) * sizeof(float), st));
+    const size_t need = rowf * (size_t)(row1 - row0);
+    if (!g.rect_stream) CK(cudaStreamCreateWithFlags(&g.rect_stream, cudaStreamNonBlocking));
+    Context::RectSlot& R = g.rect_ring[g.next_rect];
+    g.next_rect = (g.next_rect + 1) % 3;
+    if (!R.copied) {
+      CK(cudaEventCreateWithFlags(&R.copied, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&R.freed, cudaEventDisableTiming));
+    }
+    if (need > R.cap) {  // grows to the largest rectangle seen; the kernel that last read the old buffer has to finish
+      if (R.used) CK(cudaEventSynchronize(R.freed));
+      if (R.buf) CK(cudaFree(R.buf));
+      R.buf = nullptr;
+      R.cap = 0;
+      CK(cudaMalloc((void**)&R.buf, need * sizeof(float)));
+      R.cap = need;
+      R.used = false;
+    }
+    // device rasters may have been produced by earlier work on the caller's stream: their copy stays on it
+    cudaStream_t cs = kind == cudaMemcpyDeviceToDevice ? st : g.rect_stream;
+    if (R.used) CK(cudaStreamWaitEvent(cs, R.freed, 0));  // the widening kernel of three rectangles ago
     // a rectangle whose rows follow each other in the caller's buffer travels as ONE contiguous copy: measured on a B200
     // box, the pitched form of the same bytes is 10 % slower alone and overlaps a concurrent download far worse
     // (configs[4], one GPU: upload || download 58.7 ms against 48.9 ms, profiles/r02h_probe_overlap.txt)
     cudaError_t e = src_pitch_floats == rowf
-                        ? cudaMemcpyAsync(tmp, pixels, wb * (size_t)(row1 - row0), kind, st)
-                        : cudaMemcpy2DAsync(tmp, rowf * sizeof(float), pixels, src_pitch_floats * sizeof(float), wb, row1 - row0, kind, st);
-    if (e == cudaSuccess) e = eu_launch_pad_texels(tmp, (int)rowf, dst, s->pitch / 4, col1 - col0, row1 - row0, s->nch, st);
-    cudaFreeAsync(tmp, st);
+                        ? cudaMemcpyAsync(R.buf, pixels, wb * (size_t)(row1 - row0), kind, cs)
+                        : cudaMemcpy2DAsync(R.buf, rowf * sizeof(float), pixels, src_pitch_floats * sizeof(float), wb, row1 - row0, kind, cs);
+    if (e == cudaSuccess) e = cudaEventRecord(R.copied, cs);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, R.copied, 0);  // the caller's stream: everything after this call sees the texels
+    if (e == cudaSuccess) e = eu_launch_pad_texels(R.buf, (int)rowf, dst, s->pitch / 4, col1 - col0, row1 - row0, s->nch, st);
+    if (e == cudaSuccess) e = cudaEventRecord(R.freed, st);
+    R.used = true;
     if (e != cudaSuccess) return fail(EU_ERR_CUDA, "write_rect: %s", cudaGetErrorString(e));
     return EU_OK;
   }

@@ -187,6 +187,26 @@ __device__ __forceinline__ void dev_stepper(const TargetDev& T, const float* xx,
   }
 }
 
+// The cubemap / biatan6 stepper of a single-facet job with the face's vectors read from RenderParams::cube_tab
+// (plan.h): bit for bit what the switch in dev_stepper computes.
+__device__ __forceinline__ void dev_stepper_cube_tab(const TargetDev& T, const float (*tab)[12], ColTerm col, RowTerm row,
+                                                     float ray[3]) {
+  const int face = __float_as_int(row.b);
+  const float4 a = *reinterpret_cast<const float4*>(tab[face]);
+  const float4 b = *reinterpret_cast<const float4*>(tab[face] + 4);
+  const float4 c = *reinterpret_cast<const float4*>(tab[face] + 8);
+  const float p1 = row.a, p0 = col.a;
+  const float ccc0 = a.x + p1 * b.x, ccc1 = a.y + p1 * b.y, ccc2 = a.z + p1 * b.z;
+  ray[0] = ccc0 + p0 * c.x;
+  ray[1] = ccc1 + p0 * c.y;
+  ray[2] = ccc2 + p0 * c.z;
+  if (T.normalize) {
+    float n = dev_norm3(ray);
+#pragma unroll
+    for (int i = 0; i < 3; i++) ray[i] /= n;
+  }
+}
+
 // rotate(xel_t<float,3>, r3_t<float>), geometry.h:74-82
 __device__ __forceinline__ void dev_rot3(const float v[3], const float* __restrict__ m, float out[3]) {
   float o[3];
@@ -505,11 +525,23 @@ __device__ __forceinline__ void dev_weights(const float* __restrict__ wmat, floa
 // WINDOW, the window sum and the twining accumulation use fused multiply-adds; rays, source coordinates,
 // gates, window positions, face and facet indices stay exactly as they are (same bits), so the variant
 // differs from the default by a few ulp of each pixel value and in nothing else.
+// WSTD (cubic only): the plan builder has checked that the weight matrix has the cubic b-spline's exact zeros at
+// [0][3], [1][1], [1][3] and [2][3] (zimt/basis.h:419-543 yields them as exact zeros). delta is a remainder
+// c - floor(c) >= +0 (or NaN), so each skipped term is w + (+0) = w for a w that is never -0, and w[3] = 0 + t = t:
+// the same bits with 7 instructions fewer per axis. (A NaN delta still reaches every weight through a later row.)
 #ifdef EU_CONTRACT_WINDOW
 #define EU_WIN_MULADD(a, b, c) __fmaf_rn((a), (b), (c))
 #define EU_WIN_ACC(c, a, b) c = __fmaf_rn((a), (b), c)
-template <int ORDER>
+template <int ORDER, bool WSTD = false>
 __device__ __forceinline__ void dev_window_weights(const float* __restrict__ wmat, float delta, float w[ORDER]) {
+  if constexpr (ORDER == 4 && WSTD) {
+    const float p1 = delta, p2 = p1 * delta, p3 = p2 * delta;
+    w[0] = __fmaf_rn(p3, wmat[12], __fmaf_rn(p2, wmat[8], __fmaf_rn(p1, wmat[4], wmat[0])));
+    w[1] = __fmaf_rn(p3, wmat[13], __fmaf_rn(p2, wmat[9], wmat[1]));
+    w[2] = __fmaf_rn(p3, wmat[14], __fmaf_rn(p2, wmat[10], __fmaf_rn(p1, wmat[6], wmat[2])));
+    w[3] = p3 * wmat[15];
+    return;
+  }
   float power = delta;
 #pragma unroll
   for (int k = 0; k < ORDER; k++) w[k] = wmat[k];
@@ -523,8 +555,22 @@ __device__ __forceinline__ void dev_window_weights(const float* __restrict__ wma
 #else
 #define EU_WIN_MULADD(a, b, c) ((c) + (a) * (b))
 #define EU_WIN_ACC(c, a, b) c += (a) * (b)  // the statement as the run-time evaluator has always had it
-template <int ORDER>
+template <int ORDER, bool WSTD = false>
 __device__ __forceinline__ void dev_window_weights(const float* __restrict__ wmat, float delta, float w[ORDER]) {
+  if constexpr (ORDER == 4 && WSTD) {
+    const float p1 = delta, p2 = p1 * delta, p3 = p2 * delta;
+    w[0] = wmat[0] + p1 * wmat[4];
+    w[1] = wmat[1];
+    w[2] = wmat[2] + p1 * wmat[6];
+    w[0] += p2 * wmat[8];
+    w[1] += p2 * wmat[9];
+    w[2] += p2 * wmat[10];
+    w[0] += p3 * wmat[12];
+    w[1] += p3 * wmat[13];
+    w[2] += p3 * wmat[14];
+    w[3] = p3 * wmat[15];
+    return;
+  }
   dev_weights<ORDER>(wmat, delta, w);
 }
 #endif
@@ -585,13 +631,13 @@ __device__ __forceinline__ void dev_window_sum_w(const float* __restrict__ p0, i
 
 // evaluator::eval for a fixed degree > 1: window sum in the reference's order
 // (zimt/eval.h:903-996). p0 -> texel (ix - deg/2, iy - deg/2); pitch: floats per row.
-template <int NCH, int TS, int DEG, int SMEM>
+template <int NCH, int TS, int DEG, int SMEM, bool WSTD = false>
 __device__ __forceinline__ void dev_window_sum(const float* __restrict__ p0, int pitch, const float* __restrict__ wmat,
                                                float fx, float fy, float out[NCH]) {
   constexpr int ORDER = DEG + 1;
   float wx[ORDER], wy[ORDER];
-  dev_window_weights<ORDER>(wmat, fx, wx);
-  dev_window_weights<ORDER>(wmat, fy, wy);
+  dev_window_weights<ORDER, WSTD>(wmat, fx, wx);
+  dev_window_weights<ORDER, WSTD>(wmat, fy, wy);
   dev_window_sum_w<NCH, TS, DEG, SMEM>(p0, pitch, wx, wy, out);
 }
 
@@ -620,13 +666,14 @@ __device__ __forceinline__ void dev_eval_linear(const float* __restrict__ p, int
 
 // the window evaluation for a located coordinate; p0 -> texel (ix - degree/2, iy - degree/2).
 // DEG >= 0: degree fixed at compile time; DEG < 0: read at run time (all degrees 0..7).
-template <int NCH, int TS, int DEG, int SMEM>
+// WSTD: the kernel is compiled for a job shape (the plan builder picks those only for the standard cubic matrix)
+template <int NCH, int TS, int DEG, int SMEM, bool WSTD = false>
 __device__ __forceinline__ void dev_window_eval(const float* __restrict__ p0, int pitch, int degree,
                                                 const float* __restrict__ wmat, float fx, float fy, float out[NCH]) {
   if constexpr (DEG == 1) {
     dev_eval_linear<NCH, TS, SMEM>(p0, pitch, fx, fy, out);
   } else if constexpr (DEG == 3) {
-    dev_window_sum<NCH, TS, 3, SMEM>(p0, pitch, wmat, fx, fy, out);
+    dev_window_sum<NCH, TS, 3, SMEM, WSTD>(p0, pitch, wmat, fx, fy, out);
   } else {
     switch (degree) {
       case 0: dev_load_texel<NCH, TS, SMEM>(p0, out); break;
@@ -653,7 +700,7 @@ __device__ __forceinline__ void dev_spline_eval(const SourceDev& S, int degree, 
   const float* p0;
   if constexpr (I32) p0 = S.core + ((L.iy - h2) * S.stride + (L.ix - h2) * TS);
   else p0 = S.core + (ptrdiff_t)(L.iy - h2) * S.stride + (ptrdiff_t)(L.ix - h2) * TS;
-  dev_window_eval<NCH, TS, DEG, SPACE>(p0, S.stride, degree, wmat, L.fx, L.fy, out);
+  dev_window_eval<NCH, TS, DEG, SPACE, I32>(p0, S.stride, degree, wmat, L.fx, L.fy, out);
 }
 
 // ray_to_cubeface, geometry.h:1178-1357 (>= ties favour x over y over z)
@@ -778,7 +825,7 @@ __device__ __forceinline__ void dev_facet_window(const FacetDev& F, int degree, 
   const float* p0;
   if constexpr (I32) p0 = F.src.core + ((L.iy - h2) * F.src.stride + (L.ix - h2) * TS);
   else p0 = F.src.core + (ptrdiff_t)(L.iy - h2) * F.src.stride + (ptrdiff_t)(L.ix - h2) * TS;
-  dev_window_eval<NCH, TS, DEG, 0>(p0, F.src.stride, degree, wmat, L.fx, L.fy, px);
+  dev_window_eval<NCH, TS, DEG, 0, I32>(p0, F.src.stride, degree, wmat, L.fx, L.fy, px);
   dev_brighten<NCH>(F, px);
 }
 

@@ -123,6 +123,12 @@ constexpr RenderSpec eu_render_specs[EU_N_SPECS] = {
 struct RenderParams {
   TargetDev trg;
   FacetDev f0;              // the facet of single-facet jobs (constant bank)
+  // cubemap / biatan6 TARGETS, single-facet jobs: per cube face the constant part and the direction of the face's
+  // stepper for f0 (stepper.h:1304-1331: ccc = +-row_a + p1 * +-row_b, vvv = +-row_c of the facet's basis) as
+  // A[3], pad, B[3], pad, C[3], pad with the signs folded in: ray = (A + p1 * B) + p0 * C, the same products and
+  // sums with the same operands as the switch (a + (-b) is a - b, -(p1 * b) is p1 * (-b)): one indexed constant load
+  // per vector instead of three switches on the face per pixel
+  alignas(16) float cube_tab[6][12];
   InvPlanarDev inv;         // 'single' jobs: inverse planar transformation of the target facet
   float wmat[64];           // (degree+1)^2 weight matrix (zimt/basis.h:419-543), float, packed
   const FacetDev* facets;   // all facets (global memory), used by the synopsis modes

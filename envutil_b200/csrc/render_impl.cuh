@@ -110,14 +110,19 @@ struct PixelTerms {
   RowTerm row, rowb;
   float px, pxb, py, pyb;  // bare planar coordinates (generic steppers only)
 };
+// ctab: RenderParams::cube_tab when F is the job's only facet (single-facet jobs), else null
 template <bool GEN, int WHICH>
 __device__ __forceinline__ void dev_facet_ray(const TargetDev& T, const InvPlanarDev& IP, const FacetDev& F,
-                                              const PixelTerms& t, int y, float r[3]) {
+                                              const PixelTerms& t, int y, float r[3], const float (*ctab)[12] = nullptr) {
   if constexpr (GEN) {
     if (F.generic) {
       dev_generic_ray(T, IP, F, WHICH == 1 ? t.pxb : t.px, WHICH == 2 ? t.pyb : t.py, r);
       return;
     }
+  }
+  if (ctab != nullptr && T.projection >= EU_CUBEMAP) {
+    dev_stepper_cube_tab(T, ctab, WHICH == 1 ? t.colb : t.col, WHICH == 2 ? t.rowb : t.row, r);
+    return;
   }
   dev_stepper(T, F.xx, F.yy, F.zz, WHICH == 1 ? t.colb : t.col, WHICH == 2 ? t.rowb : t.row,
               WHICH == 1 ? t.firstb : t.first, y, r);
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y, (SP != 0 && MODE != EU_MODE_SI
   int idx;
   if constexpr (!TWINE) {
     auto ray_of = [&](int i, float r[3]) {
-      if constexpr (MODE == EU_MODE_SINGLE) dev_facet_ray<GEN, 0>(T, P.inv, f0, t, y, r);
+      if constexpr (MODE == EU_MODE_SINGLE) dev_facet_ray<GEN, 0>(T, P.inv, f0, t, y, r, P.cube_tab);
       else dev_facet_ray<GEN, 0>(T, P.inv, dev_facet_at<SP>(fa, i), t, y, r);
     };
     idx = dev_synopsis<NCH, TS, MODE, DEG, GEN, SP>(P, f0, fa, ray_of, active, px);
@@ -386,9 +391,9 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y, (SP != 0 && MODE != EU_MODE_SI
     idx = -1;
     if constexpr (MODE == EU_MODE_SINGLE) {
       float r00[3], du[3], dv[3];
-      dev_facet_ray<GEN, 0>(T, P.inv, f0, t, y, r00);
-      dev_facet_ray<GEN, 1>(T, P.inv, f0, t, y, du);
-      dev_facet_ray<GEN, 2>(T, P.inv, f0, t, y, dv);
+      dev_facet_ray<GEN, 0>(T, P.inv, f0, t, y, r00, P.cube_tab);
+      dev_facet_ray<GEN, 1>(T, P.inv, f0, t, y, du, P.cube_tab);
+      dev_facet_ray<GEN, 2>(T, P.inv, f0, t, y, dv, P.cube_tab);
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         du[c] = du[c] - r00[c];
@@ -527,7 +532,8 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
     first = ColTerm{f0.x, f0.y};
   }
   float r00[3];
-  dev_stepper(T, F.xx, F.yy, F.zz, col, row, first, yc, r00);
+  if (T.projection >= EU_CUBEMAP) dev_stepper_cube_tab(T, P.cube_tab, col, row, r00);
+  else dev_stepper(T, F.xx, F.yy, F.zz, col, row, first, yc, r00);
   int face;
   float cx, cy;
   bool hit = dev_facet_coordinate(F, r00, face, cx, cy) && inside;
@@ -593,9 +599,9 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
       for (int c = 0; c < NCH; c++) px[c] = 0.0f;
     } else {
       if (staged)
-        dev_window_eval<NCH, TS, DEG, true>(tile + (loy - by0) * wf + (lox * TS - a0), wf, DEG, P.wmat, L.fx, L.fy, px);
+        dev_window_eval<NCH, TS, DEG, true, SP != 0>(tile + (loy - by0) * wf + (lox * TS - a0), wf, DEG, P.wmat, L.fx, L.fy, px);
       else
-        dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)loy * S.stride + (ptrdiff_t)lox * TS, S.stride, DEG,
+        dev_window_eval<NCH, TS, DEG, false, SP != 0>(P.src_base + (ptrdiff_t)loy * S.stride + (ptrdiff_t)lox * TS, S.stride, DEG,
                                              P.wmat, L.fx, L.fy, px);
       dev_brighten<NCH>(F, px);
     }
@@ -610,8 +616,13 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
       firstb = ColTerm{f1.x, f1.y};
     }
     float du[3], dv[3], help[NCH];
-    dev_stepper(T, F.xx, F.yy, F.zz, colb, row, firstb, y, du);
-    dev_stepper(T, F.xx, F.yy, F.zz, col, rowb, first, y, dv);
+    if (T.projection >= EU_CUBEMAP) {
+      dev_stepper_cube_tab(T, P.cube_tab, colb, row, du);
+      dev_stepper_cube_tab(T, P.cube_tab, col, rowb, dv);
+    } else {
+      dev_stepper(T, F.xx, F.yy, F.zz, colb, row, firstb, y, du);
+      dev_stepper(T, F.xx, F.yy, F.zz, col, rowb, first, y, dv);
+    }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       du[c] = du[c] - r00[c];
@@ -636,9 +647,9 @@ __global__ void __launch_bounds__(TILE_X* TILE_Y) k_render_tiled(const __grid_co
         const int kx = K.ix - H2 + P.src_lx, ky = K.iy - H2 + P.src_ly;
         const bool in_box = staged && kx * TS >= a0 && (kx + ORDER) * TS <= bx1 && ky >= by0 && ky + ORDER <= by1;
         if (in_box)
-          dev_window_eval<NCH, TS, DEG, true>(tile + (ky - by0) * wf + (kx * TS - a0), wf, DEG, P.wmat, K.fx, K.fy, help);
+          dev_window_eval<NCH, TS, DEG, true, SP != 0>(tile + (ky - by0) * wf + (kx * TS - a0), wf, DEG, P.wmat, K.fx, K.fy, help);
         else
-          dev_window_eval<NCH, TS, DEG, false>(P.src_base + (ptrdiff_t)ky * S.stride + (ptrdiff_t)kx * TS, S.stride, DEG,
+          dev_window_eval<NCH, TS, DEG, false, SP != 0>(P.src_base + (ptrdiff_t)ky * S.stride + (ptrdiff_t)kx * TS, S.stride, DEG,
                                                P.wmat, K.fx, K.fy, help);
         dev_brighten<NCH>(F, help);
       }

@@ -273,7 +273,11 @@ int eu_source_commit(eu_source_h s, const eu_facet_t* f, const eu_opts_t* o, voi
 /* Fill part of a reserved source from a raster in host (page-locked, for a truly asynchronous copy) or device
  * memory: the rectangle rows [row0,row1) x columns [col0,col1) of the image; `pixels` points at its first texel,
  * rows src_pitch_floats apart. Enqueued on cuda_stream (asynchronous for page-locked host memory; pageable memory is
- * staged before the call returns).
+ * staged before the call returns): work enqueued on cuda_stream after the call sees the texels, and the host buffer
+ * may be reused once cuda_stream has reached that point. A HOST raster must hold its final contents when the call is
+ * made - the library may start reading it at once, on a copy stream of its own, so that the copies of consecutive
+ * rectangles follow each other while kernels on cuda_stream widen them into 16-byte texels. Device rasters are read in
+ * stream order.
  * Ranks of a multi-GPU job upload just the part of every source their band of the output can see. Rows and
  * columns never written read as zero. f and o given to eu_source_commit must be those given to
  * eu_source_reserve; with t == NULL eu_source_commit only enqueues (later work on cuda_stream is ordered after it). */
