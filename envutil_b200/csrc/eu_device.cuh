@@ -349,6 +349,18 @@ __device__ __forceinline__ void dev_generic_ray(const TargetDev& T, const InvPla
 // source side
 // ------------------------------------------------------------------------------------------
 
+// eu_atan2f(y, x) for an x whose sign bit is clear (a square root of a sum of squares: +0 at least, or NaN - and
+// a NaN result does not depend on the skipped step): eu_atan2f without its "x negative" correction.
+__device__ __forceinline__ float dev_atan2f_xpos(float y, float x) {
+  float ax = eu_fabsf(x), ay = eu_fabsf(y);
+  float mx = ax > ay ? ax : ay;
+  float mn = ax > ay ? ay : ax;
+  float t = (mx == 0.0f) ? 0.0f : mn / mx;
+  float p = eu_katanf(t);
+  if (ay > ax) p = (EU_PIO2_HI - p) + EU_PIO2_LO;
+  return eu_copysignf(p, y);
+}
+
 // mount_t::get_coordinate_nomask (environment.h:1077-1110) over the ray_to_X functors
 // (geometry.h:277-534) and pto_planar's forward path (environment.h:254-283)
 __device__ __forceinline__ void dev_mount_coordinate(const FacetDev& F, const float r[3], float c[2]) {
@@ -359,7 +371,7 @@ __device__ __forceinline__ void dev_mount_coordinate(const FacetDev& F, const fl
       break;
     case EU_SPHERICAL: {
       float s = sqrtf(r[0] * r[0] + r[2] * r[2]);
-      c[1] = eu_atan2f(r[1], s);
+      c[1] = dev_atan2f_xpos(r[1], s);
       c[0] = eu_atan2f(r[0], r[2]);
       break;
     }
@@ -703,6 +715,11 @@ __device__ __forceinline__ void dev_spline_eval(const SourceDev& S, int degree, 
   dev_window_eval<NCH, TS, DEG, SPACE, I32>(p0, S.stride, degree, wmat, L.fx, L.fy, out);
 }
 
+// eu_atanf for an argument in [-1, 1] or NaN - what dev_cubeface yields: each in-face coordinate is a component
+// divided by one of no smaller magnitude, and rounding is monotonic. eu_atanf's |x| > 1 branch (a division and a
+// correction by pi/2, include/eu_math.h) never runs for such arguments; these are its remaining operations.
+__device__ __forceinline__ float dev_atanf_unit(float x) { return eu_copysignf(eu_katanf(eu_fabsf(x)), x); }
+
 // ray_to_cubeface, geometry.h:1178-1357 (>= ties favour x over y over z)
 __device__ __forceinline__ void dev_cubeface(const float c[3], int& face, float in_face[2]) {
   bool m1 = fabsf(c[0]) >= fabsf(c[1]);
@@ -764,8 +781,8 @@ __device__ __forceinline__ bool dev_facet_coordinate(const FacetDev& F, const fl
     float in_face[2], pk[2];
     dev_cubeface(r, face, in_face);
     if (F.kind == EU_SRC_BIATAN6) {
-      in_face[0] = (float)(4.0 / EU_PI) * eu_atanf(in_face[0]);
-      in_face[1] = (float)(4.0 / EU_PI) * eu_atanf(in_face[1]);
+      in_face[0] = (float)(4.0 / EU_PI) * dev_atanf_unit(in_face[0]);
+      in_face[1] = (float)(4.0 / EU_PI) * dev_atanf_unit(in_face[1]);
     }
     pk[0] = in_face[0] + F.refc_md;
     pk[1] = in_face[1] + F.refc_md;

@@ -169,6 +169,16 @@ __device__ __forceinline__ int dev_synopsis(const RenderParams& P, const FacetDe
     for (int i = 0; i < P.n_facets; i++) {
       const FacetDev& F = dev_facet_at<SP>(fa, i);
       float r[3];
+      if constexpr (!GEN) {
+        // A rectilinear mount only sees rays with z > 0 (the first thing dev_facet_mask tests, environment.h:1123-1127):
+        // z alone is computed before the branch - of this first evaluation only r[2] is live - and the facets behind the
+        // camera (half of a full panorama's) cost a third of a ray. The second evaluation reuses z.
+        if (F.projection == EU_RECTILINEAR && !F.mask_always) {
+          float rz[3];
+          ray_of(i, rz);
+          if (!(rz[2] > 0.0f)) continue;
+        }
+      }
       ray_of(i, r);
       if (!dev_facet_mask(F, r)) continue;
       float cz = r[2] * F.recip_step;
