@@ -39,6 +39,7 @@ class Facet(C.Structure):
         ("has_2d_tf", C.c_int32), ("has_translation", C.c_int32),
         ("window_width", C.c_int32), ("window_height", C.c_int32),
         ("window_x_offset", C.c_int32), ("window_y_offset", C.c_int32),
+        ("masked", C.c_int32),
     ]
 
 

@@ -316,6 +316,8 @@ int facet_dev(const eu_target_t* t, const eu_facet_t* f, const eu_source* s, Fac
   F.brighten = (float)(f->brighten == 0.0 ? 1.0 : f->brighten);
   F.hdr_optimum = 0.0f;
   F.hdr_kind = EU_HDR_MIDDLE;
+  F.masked = f->masked != 0 ? 1 : 0;
+  F.paint = f->masked == 2 ? 1.0f : 0.0f;
   // generic_r3, envutil_payload.cc:1636-1809: a facet with translation - or every facet, when the job is a
   // 'single' on a facet with lens correction / translation (`ft`) - gets its rays from the generic stepper
   F.generic = (f->has_translation || ft) ? 1 : 0;
@@ -709,6 +711,12 @@ int build_plan(const eu_target_t* t, const eu_opts_t* o, int nf, const eu_facet_
   for (int i = 0; i < nf; i++) {
     if (mode == EU_MODE_SINGLE && i != first) continue;
     if (F[i].generic || sources[i]->nch != nch || sources[i]->tstride != P.tstride) P.any_generic = 1;
+    if (F[i].masked) {  // --mask_for: the general build paints (dev_facet_eval_general)
+      P.any_generic = 1;
+      if (sources[i]->nch != nch && nch > 2)
+        return fail(EU_ERR_ARGUMENT, "a masked facet of %d channels in a job of %d: mono_t converts to one or two channels only "
+                    "(environment.h:1338-1339)", sources[i]->nch, nch);
+    }
   }
   // a compiled-in job shape (plan.h: eu_render_specs): the target and every facet that is
   // evaluated must agree with all values the entry fixes

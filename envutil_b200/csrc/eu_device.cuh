@@ -947,6 +947,32 @@ __device__ __forceinline__ void dev_repix(int in_n, const float in[4], float out
   for (int i = 0; i < OUT; i++) out[i] = o[i];
 }
 
+// mono_t, environment.h:1325-1384: what replaces repix_t for masked facets (jobs of one or two channels)
+template <int OUT>
+__device__ __forceinline__ void dev_mono(int in_n, const float in[4], float out[OUT]) {
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  if (in_n == OUT) {
+    o[0] = in[0]; o[1] = in[1]; o[2] = in[2]; o[3] = in[3];
+  } else if (in_n == 1) {
+    o[0] = in[0]; o[1] = 1.0f;
+  } else if (in_n == 2) {
+    o[0] = in[0] / in[1];
+    if (in[1] == 0.0f) o[0] = 0.0f;
+  } else if (in_n == 3) {
+    o[0] = in[0]; o[1] = 1.0f;
+  } else {
+    if (OUT == 1) {
+      o[0] = in[0];
+      o[0] /= in[3];
+      if (in[3] == 0.0f) o[0] = 0.0f;
+    } else {
+      o[0] = in[0]; o[1] = in[3];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < OUT; i++) out[i] = o[i];
+}
+
 // environment::eval for any facet: evaluate in the source's channel count, repix, brighten
 template <int NCH>
 __device__ __forceinline__ int dev_facet_eval_general(const FacetDev& F, int degree, const float* __restrict__ wmat,
@@ -962,7 +988,22 @@ __device__ __forceinline__ int dev_facet_eval_general(const FacetDev& F, int deg
       default: dev_spline_eval_rt<4>(F.src, degree, wmat, cx, cy, sp); break;
     }
   }
-  dev_repix<NCH>(F.src.nch, sp, px);  // a miss is a zero pixel of the SOURCE type (environment.h:1190-1193)
+  if (F.masked) {
+    // --mask_for: masking_t paints every channel, alpha_masking_t the colour channels times the interpolated alpha
+    // (masking.h:70-139; a miss stays the zero pixel: mount_t clears it after the evaluation)
+    if (hit) {
+      const int n = F.src.nch;
+      if (n == 1 || n == 3) {
+        sp[0] = sp[1] = sp[2] = F.paint;
+      } else {
+        sp[0] = F.paint * sp[n - 1];
+        if (n == 4) sp[1] = sp[2] = sp[0];
+      }
+    }
+    dev_mono<NCH>(F.src.nch, sp, px);
+  } else {
+    dev_repix<NCH>(F.src.nch, sp, px);  // a miss is a zero pixel of the SOURCE type (environment.h:1190-1193)
+  }
   dev_brighten<NCH>(F, px);
   return hit ? face : -1;
 }

@@ -144,10 +144,7 @@ int arguments::init(int argc, const char** argv) {
   }
   // --twine_precise is accepted and ignored, as in the reference: only environment9 reads it
   // (environment.h:1997), which dispatch::payload never instantiates
-  if (has("--mask_for")) {
-    error = "--mask_for is outside the built path";
-    return EU_ERR_UNSUPPORTED;
-  }
+  mask_for = geti("--mask_for", -1);  // envutil_main.cc:999-1001
 
   bool ignore_p_line = false;
   solo = -1;
@@ -463,6 +460,13 @@ int arguments::init(int argc, const char** argv) {
     }
     if (m.f.nchannels == 2 || m.f.nchannels == 4) alpha_seen = true;
     if (m.f.nchannels > nchannels) nchannels = m.f.nchannels;
+    // --mask_for: facet_spec::masked 1 (white) for that facet, 0 (black) for the others, -1 without the option
+    // (envutil_main.cc:1077-1091); eu_facet_t.masked holds it as 2 / 1 / 0
+    m.f.masked = mask_for == -1 ? 0 : (m.facet_no == mask_for ? 2 : 1);
+  }
+  if (mask_for != -1 && mask_for >= (int)facet_spec_v.size()) {
+    error = "--mask_for: no such facet";  // the reference asserts (envutil_main.cc:1001)
+    return EU_ERR_ARGUMENT;
   }
   if (alpha_seen && nchannels == 3) nchannels = 4;
   int nch = geti("--nchannels", 0);

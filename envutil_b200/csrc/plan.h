@@ -62,6 +62,9 @@ struct FacetDev {
   // 1: everything that decides where a ray lands in this facet equals the PREVIOUS facet of the job (exposure
   // brackets of one camera position): the kernels reuse that facet's window position (api.cu: same_geometry)
   int32_t same_geom;
+  // --mask_for (masking.h:70-139): masked != 0 -> the colour channels are `paint` (times alpha, if the source has one)
+  int32_t masked;
+  float paint;
   // generic_stepper + tf_ex_facet + generic_r3 + tf3d_t: facets with PanoTools translation
   // (envutil_payload.cc:1628-1883, geometry.h:1850-1942). Float matrices, rows as r3_t holds them.
   // 'single' jobs on a facet with lens correction / translation put every facet on the generic stepper

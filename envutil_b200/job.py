@@ -102,6 +102,8 @@ class Job:
     twine_max: int = 8
     synopsis: str = "panorama"
     solo: int = -1
+    mask_for: int = -1      # --mask_for K: facet K is painted white, all others black (envutil_main.cc:999-1001,1077-1091)
+    out_channels: int = 0   # --nchannels: the job's channel count instead of the maximum over the facets (:1131-1133)
     crop_out: Optional[tuple] = None  # PTO p-line S clause (x0, x1, y0, y1): only this window of the target is
                                       # rendered and stored (envutil_main.cc:615-627, envutil_payload.cc:440-474)
     single: int = -1  # --single K: render into facet K's geometry, undo its brighten (envutil_main.cc:1157-1178)
@@ -183,6 +185,10 @@ class Job:
             args += ["--synopsis", self.synopsis]
         if self.solo >= 0:
             args += ["--solo", str(self.solo)]
+        if self.mask_for >= 0:
+            args += ["--mask_for", str(self.mask_for)]
+        if self.out_channels:
+            args += ["--nchannels", str(self.out_channels)]
         if self.single >= 0:
             args += ["--single", str(self.single)]
         if self.support_min != 8:
@@ -214,6 +220,8 @@ class Job:
         nch = max(counts)
         if nch == 3 and any(c in (2, 4) for c in counts):
             nch = 4
+        if self.out_channels:
+            nch = self.out_channels
         t = capi.Target()
         t.projection = capi.PROJECTION_NAMES.index(self.projection)
         t.width, t.height, t.nchannels = self.width, self.height, nch
@@ -251,6 +259,8 @@ class Job:
             s.shear_g, s.shear_t = f.g / h, f.t / w  # envutil_main.cc:795-796
             s.a, s.b, s.c, s.h, s.v = f.a, f.b, f.c, f.d, f.e
             s.brighten = gains[i]
+            if self.mask_for >= 0:  # facet_spec::masked 1 / 0 -> eu_facet_t.masked 2 (white) / 1 (black)
+                s.masked = 2 if i == self.mask_for else 1
             capi.check(lib.eu_facet_prepare(C.byref(s)), lib)
         if self.single >= 0:  # (facet_base&) args = facet_spec_v[single]: geometry in radians as the facet has it
             sf = fa[self.single]

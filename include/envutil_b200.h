@@ -74,6 +74,13 @@ typedef struct eu_facet {
    * eu_source_upload is window_width x window_height, width/height/hfov describe the whole image).
    * Leave zero for uncropped facets; eu_facet_prepare then sets the window to the whole image. */
   int32_t window_width, window_height, window_x_offset, window_y_offset;
+  /* input, optional: --mask_for (envutil_main.cc:999-1001,1077-1091; facet_spec::masked, masking.h:70-139). 0 = normal
+   * operation; 1 = this facet is painted BLACK, 2 = WHITE (the reference's masked == 0 / 1): its colour channels are
+   * replaced by the paint value - times the interpolated alpha for facets with an alpha channel - before brighten and
+   * the synopsis. A masked facet whose channel count differs from the job's is converted by mono_t instead of repix_t
+   * (environment.h:1325-1384), which exists for one- and two-channel jobs only. (Occupies what used to be padding:
+   * the struct's size is unchanged.) */
+  int32_t masked;
 } eu_facet_t;
 
 /* Mirror of the members of `arguments` that define the target and the job (reference

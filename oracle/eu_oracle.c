@@ -985,6 +985,8 @@ typedef struct {
    * is up to two tf3d_t in sequence (envutil_payload.cc:1716-1760); a tf3d_t without shift is one rotation */
   int g_nstage;
   struct { int has_shift; float a[9], b[9], ab[9], shift[3], dcp; } g_st[2];
+  int masked;   /* --mask_for: 0 normal, else the colour channels are `paint` (facet_spec::masked, masking.h) */
+  float paint;
 } facet_ctx;
 
 #define INV_SZ 100            /* knot count passed by pto_planar's ctor, environment.h:250 */
@@ -1464,6 +1466,27 @@ static void repix(int in_n, int out_n, const float* in, float* out) {
   }
 }
 
+/* mono_t, environment.h:1325-1384: replaces repix_t for masked facets; one- and two-channel jobs only */
+static void mono(int in_n, int out_n, const float* in, float* out) {
+  if (in_n == out_n) {
+    for (int i = 0; i < in_n; i++) out[i] = in[i];
+  } else if (in_n == 1) {
+    out[0] = in[0]; out[1] = 1.0f;
+  } else if (in_n == 2) {
+    out[0] = in[0] / in[1];
+    if (in[1] == 0.0f) out[0] = 0.0f;
+  } else if (in_n == 3) {
+    out[0] = in[0];
+    if (out_n == 2) out[1] = 1.0f;
+  } else if (out_n == 1) {
+    out[0] = in[0];
+    out[0] /= in[3];
+    if (in[3] == 0.0f) out[0] = 0.0f;
+  } else {
+    out[0] = in[0]; out[1] = in[3];
+  }
+}
+
 /* environment::eval, environment.h:1821-1842 over mount_t::eval :1172-1196 or
  * cubemap_view_t::eval :1473-1486, then repix_t to the job's channel count (:1862-1960), then
  * brighten on the colour channels. Returns the cube face (or -1). */
@@ -1508,8 +1531,21 @@ static int facet_eval(const facet_ctx* F, int nch, const float r[3], float* px) 
     pk[1] -= .5f;
     spline_eval(s, s->degree, s->wmat, pk[0], pk[1], sp);
   }
-  (void)hit;
-  repix(snch, nch, sp, px);
+  if (F->masked) {
+    /* masking_t / alpha_masking_t instead of the evaluator (environment.h:947-961,1585-1587, masking.h:70-139): every
+     * channel is `paint`, or - with an alpha channel - the colour channels are paint * alpha; a miss stays zero */
+    if (hit) {
+      if (snch == 1 || snch == 3) {
+        for (int i = 0; i < snch; i++) sp[i] = F->paint;
+      } else {
+        sp[0] = F->paint * sp[snch - 1];
+        if (snch == 4) sp[1] = sp[2] = sp[0];
+      }
+    }
+    mono(snch, nch, sp, px);
+  } else {
+    repix(snch, nch, sp, px);
+  }
   if (F->brighten != 1.0f) {
     int ncol = (nch == 2 || nch == 4) ? nch - 1 : nch;
     for (int i = 0; i < ncol; i++) px[i] *= F->brighten;
@@ -1804,6 +1840,8 @@ static int facet_setup(const eu_target_t* t, const eu_opts_t* o, const eu_facet_
   double step = orc_get_step(f->projection, f->width, f->height, f->hfov);
   F->recip_step = (float)(1.0 / step);
   F->brighten = (float)(f->brighten == 0.0 ? 1.0 : f->brighten);
+  F->masked = f->masked != 0;
+  F->paint = f->masked == 2 ? 1.0f : 0.0f;
   (void)o;
   return 0;
 }

@@ -197,6 +197,17 @@ def _build():
     hb = _bracket_facets()
     add("hdr3_rgba_rect_d1", Job([FacetSpec(_rgba(f.image, 1), f.projection, f.hfov, yaw=f.yaw, eev=f.eev) for f in hb],
                                  "rectilinear", 70.0, 96, 64, yaw=20.0, synopsis="hdr_merge"))
+    # --- --mask_for: one facet painted white, the others black (masking.h); --nchannels reduces through mono_t ---
+    add("maskfor1_voronoi4_sph_d1", Job(_voronoi_facets(), "spherical", 360.0, 256, 128, mask_for=1))
+    add("maskfor2_voronoi4_grey_d3_tw2", Job(_voronoi_facets(), "spherical", 360.0, 128, 64, degree=3, twine=2, mask_for=2,
+                                             out_channels=1))
+    add("maskfor0_rgba4_voronoi_sph_d1", Job(rgba, "spherical", 360.0, 256, 128, mask_for=0))
+    add("maskfor3_rgba4_ga_rect_d1", Job(rgba, "rectilinear", 120.0, 96, 64, yaw=-20.0, mask_for=3, out_channels=2))
+    add("maskfor1_mixed_rgb_rgba_d1", Job([vf[0], rgba[1], vf[2], rgba[3]], "spherical", 360.0, 192, 96, mask_for=1,
+                                          out_channels=2))
+    add("maskfor0_cm_sph_d1", Job([FacetSpec(_cm(32), "cubemap", 90.0)], "spherical", 360.0, 96, 48, mask_for=0))
+    add("maskfor1_hdr3_rect_d1", Job(_bracket_facets(), "rectilinear", 70.0, 96, 64, yaw=20.0, synopsis="hdr_merge",
+                                     mask_for=1))
     # --- automatic twining (--twine omitted = -1): arguments::twine_setup picks the filter from the
     # magnification (envutil_main.cc:1450-1547) -------------------------------------------------
     add("auto_tw_down_ll_rect_d1", Job([_ll_facet(256)], "rectilinear", 100.0, 48, 32, twine=-1))          # mag < 1

@@ -121,6 +121,10 @@ def random_job(rng):
         x0, y0 = int(rng.integers(0, width // 2)), int(rng.integers(0, height // 2))
         kw.update(crop_out=(x0, int(rng.integers(x0 + 1, width + 1)), y0, int(rng.integers(y0 + 1, height + 1))),
                   yaw=0.0, pitch=0.0, roll=0.0)
+    if "solo" not in kw and "single" not in kw and rng.random() < .12:  # --mask_for, half of them reduced by --nchannels
+        kw["mask_for"] = int(rng.integers(0, nf))
+        if rng.random() < .5:
+            kw["out_channels"] = int(rng.choice([1, 2]))
     return Job(facets, trg, hfov, width, height, **kw)
 
 
