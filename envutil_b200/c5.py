@@ -169,7 +169,7 @@ class Pipeline:
     position as the reference's stage A does. Rasters live in page-locked host memory; step_e2e() moves them."""
 
     def __init__(self, engine, torch, rank=0, world=1, scale=1, plan="needed", balance="cost", contracted=None,
-                 host_frame=None, synth_inputs=True):
+                 host_frame=None, synth_inputs=True, a_streams=None):
         from . import workloads
         from .job import FacetSpec
         self.eng, self.torch, self.rank, self.world, self.scale, self.plan = engine, torch, rank, world, scale, plan
@@ -223,6 +223,9 @@ class Pipeline:
         nb = self.row1 - self.row0
         self.d_band = [torch.empty((nb, self.W, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
         self.copy_stream = torch.cuda.Stream()
+        # stage A on several streams when the rectangles are small (see stage_a)
+        n_side = a_streams if a_streams is not None else (4 if world > 1 else 0)
+        self.side_streams = [torch.cuda.Stream() for _ in range(n_side)]
         self.band_done = [None, None]  # events: the D2H of band buffer k has finished
         self.host_frame = host_frame   # H x W x 3 float32 tensor in page-locked (shared) host memory, or None
         self.d2h_bytes = nb * self.W * 3 * 4
@@ -241,12 +244,30 @@ class Pipeline:
                 eng.commit(hnd, self.st_a[p][1][b], self.st_a[p][2], self.stream, timed=False)
 
     def stage_a(self):
-        eng = self.eng
+        """The merges of the rectangles: independent launches (disjoint parts of six containers). A rank of a multi-GPU job
+        has small rectangles - a launch of one to two waves of blocks, whose tail leaves most SMs idle - so the launches
+        are dealt to a few streams and overlap (fork and join on the pipeline's stream; one GPU: big rectangles, one stream)."""
+        eng, torch = self.eng, self.torch
+        side = self.side_streams
+        if side:
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for s in side:
+                s.wait_event(fork)
+        k = 0
         for p in range(POSITIONS):
             hnd, core, pitch = self.src_b[p]
             for (r0, r1, c0, c1) in self.rects:
+                st = side[k % len(side)].cuda_stream if side else self.stream
+                k += 1
                 eng.render_rect_pitched(self.jobs_a[p], self.hs_a[p], self.st_a[p], r0, r1, c0, c1, core + r0 * pitch * 4,
-                                        pitch, self.stream, texel_floats=eng.texel_floats[hnd.value])
+                                        pitch, st, texel_floats=eng.texel_floats[hnd.value])
+        if side:
+            for s in side:
+                join = torch.cuda.Event()
+                join.record(s)
+                main.wait_event(join)
 
     def stage_b_staging(self):
         for p in range(POSITIONS):
