@@ -223,8 +223,8 @@ class Pipeline:
         nb = self.row1 - self.row0
         self.d_band = [torch.empty((nb, self.W, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
         self.copy_stream = torch.cuda.Stream()
-        # stage A on several streams when the rectangles are small (see stage_a)
-        n_side = a_streams if a_streams is not None else (4 if world > 1 else 0)
+        # stage A on several streams (see stage_a)
+        n_side = a_streams if a_streams is not None else 4
         self.side_streams = [torch.cuda.Stream() for _ in range(n_side)]
         self.band_done = [None, None]  # events: the D2H of band buffer k has finished
         self.host_frame = host_frame   # H x W x 3 float32 tensor in page-locked (shared) host memory, or None
@@ -243,18 +243,28 @@ class Pipeline:
                     eng.write_rect(hnd, t.data_ptr(), (c1 - c0) * 3, r0, r1, c0, c1, self.stream)
                 eng.commit(hnd, self.st_a[p][1][b], self.st_a[p][2], self.stream, timed=False)
 
+    def _fork(self):
+        main = self.torch.cuda.current_stream()
+        fork = self.torch.cuda.Event()
+        fork.record(main)
+        for s in self.side_streams:
+            s.wait_event(fork)
+        return main
+
+    def _join(self, main):
+        for s in self.side_streams:
+            join = self.torch.cuda.Event()
+            join.record(s)
+            main.wait_event(join)
+
     def stage_a(self):
-        """The merges of the rectangles: independent launches (disjoint parts of six containers). A rank of a multi-GPU job
-        has small rectangles - a launch of one to two waves of blocks, whose tail leaves most SMs idle - so the launches
-        are dealt to a few streams and overlap (fork and join on the pipeline's stream; one GPU: big rectangles, one stream)."""
-        eng, torch = self.eng, self.torch
+        """The merges of the rectangles: independent launches (disjoint parts of six containers). Back to back on one
+        stream every launch pays the drain of the one before it - 8 us each, 0.19 ms per step whatever the band
+        (tools/probe_c5_rank.py, profiles/r02l_rank_probe.txt: a rank of 8 spends 0.54 ms here on one stream, 0.34 ms
+        on two or more) - so the launches are dealt to a few streams (fork and join on the pipeline's stream)."""
+        eng = self.eng
         side = self.side_streams
-        if side:
-            main = torch.cuda.current_stream()
-            fork = torch.cuda.Event()
-            fork.record(main)
-            for s in side:
-                s.wait_event(fork)
+        main = self._fork() if side else None
         k = 0
         for p in range(POSITIONS):
             hnd, core, pitch = self.src_b[p]
@@ -264,14 +274,17 @@ class Pipeline:
                 eng.render_rect_pitched(self.jobs_a[p], self.hs_a[p], self.st_a[p], r0, r1, c0, c1, core + r0 * pitch * 4,
                                         pitch, st, texel_floats=eng.texel_floats[hnd.value])
         if side:
-            for s in side:
-                join = torch.cuda.Event()
-                join.record(s)
-                main.wait_event(join)
+            self._join(main)
 
     def stage_b_staging(self):
+        """Brace of the six merged rasters: a few tiny launches each, one position per stream."""
+        side = self.side_streams
+        main = self._fork() if side else None
         for p in range(POSITIONS):
-            self.eng.commit(self.src_b[p][0], self.st_b[1][p], self.st_b[2], self.stream, timed=False)
+            st = side[p % len(side)].cuda_stream if side else self.stream
+            self.eng.commit(self.src_b[p][0], self.st_b[1][p], self.st_b[2], st, timed=False)
+        if side:
+            self._join(main)
 
     def stage_b(self, k=0):
         self.eng.render_rows(self.job_b, self.hs_b, self.st_b, self.row0, self.row1, self.d_band[k].data_ptr(), self.stream,

@@ -1574,16 +1574,15 @@ int eu_source_commit(eu_source_h s, const eu_facet_t* f, const eu_opts_t* o, voi
     return fail(EU_ERR_ARGUMENT, "eu_source_commit: the facet / options differ from those given to eu_source_reserve");
   int pdeg = o->prefilter_degree < 0 ? o->spline_degree : o->prefilter_degree;
   if (pdeg > EU_MAX_DEGREE) return fail(EU_ERR_ARGUMENT, "prefilter degree %d out of range", pdeg);
-  cudaStream_t caller = (cudaStream_t)cuda_stream, st = g.stream;
-  CK(cudaEventRecord(g.ev[2], caller));  // the rows were written on the caller's stream
-  CK(cudaStreamWaitEvent(st, g.ev[2], 0));
+  // prefilter and brace run on the caller's stream, behind the work that wrote the rows and before whatever renders
+  // from the source: commits of different sources on different streams do not meet (they used to hop through the
+  // library's own stream, which chained them)
+  cudaStream_t st = (cudaStream_t)cuda_stream;
   int launches = 0;
   if (t) CK(cudaEventRecord(g.ev[0], st));
   rc = mount_finish(f, pdeg, s, st, &launches);
   if (rc) return rc;
-  // later work of the caller's stream (renders from this source) comes after the brace
-  CK(cudaEventRecord(g.ev[1], st));
-  CK(cudaStreamWaitEvent(caller, g.ev[1], 0));
+  if (t) CK(cudaEventRecord(g.ev[1], st));
   if (t) {  // blocking and timed; with t == NULL the call only enqueues
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&t->render_ms, g.ev[0], g.ev[1]));

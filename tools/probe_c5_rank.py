@@ -27,10 +27,10 @@ def timed(fn, n=30):
     return e0.elapsed_time(e1) / n
 
 
-for world, ranks in ((8, (0, 1, 3)), (4, (0, 1)), (2, (0,))):
+for world, ranks in ((8, (0, 1, 3)), (4, (0, 1)), (2, (0,)), (1, (0,))):
     for rank in ranks:
         row = {"world": world, "rank": rank}
-        for ns in (0, 2, 4, 8):
+        for ns in (0, 2, 4):
             pl = c5.Pipeline(eng, torch, rank, world, 1, synth_inputs=False, a_streams=ns)
             row["rects"] = [list(r) for r in pl.rects]
             row["A_ms_streams%d" % ns] = round(timed(pl.stage_a), 4)
