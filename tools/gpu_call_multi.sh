@@ -17,7 +17,10 @@ for n in $N 4 2; do
 done
 step bench_n1_c5 600 python bench.py --workload c5 --steps 20 --warmup 5
 grep '^{"metric"' "$OUT/bench_n1_c5.log" | tail -n 1 > "$OUT/bench_n1_c5.json"
-step bench_n${N}_replicas 900 $RUN --nproc-per-node $N --master-port 29660 bench.py --gpus $N --steps 20 --warmup 5 --workload c2 --partition frames
-grep '^{"metric"' "$OUT/bench_n${N}_replicas.log" | tail -n 1 > "$OUT/bench_n${N}_replicas.json"
-if [ $N -le 2 ]; then step pytest_2gpu 600 python -m pytest tests/test_gpu_peer_frame.py -q -m gpu -s; fi
+if [ "${REPLICAS:-0}" = 1 ]; then
+  step bench_n${N}_replicas 900 $RUN --nproc-per-node $N --master-port 29660 bench.py --gpus $N --steps 20 --warmup 5 --workload c2 --partition frames
+  grep '^{"metric"' "$OUT/bench_n${N}_replicas.log" | tail -n 1 > "$OUT/bench_n${N}_replicas.json"
+fi
+step pytest_2gpu 600 python -m pytest tests/test_gpu_peer_frame.py -q -m gpu -s
+tail -n 3 "$OUT/pytest_2gpu.log"
 cat "$OUT/summary.txt"
