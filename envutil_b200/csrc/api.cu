@@ -858,9 +858,14 @@ int stage_on_device(const eu_facet_t* f, const eu_opts_t* o, const float* d_pixe
     // fill reads frame texels it has not written yet (stage.cu, k_cm_fill_ordered) - zero, as in the reference.
     if ((Fpx & 1) || L == 0 || R == 0) CK(cudaMemsetAsync(s->container, 0, n * sizeof(float), cpst));
     CK(cudaEventRecord(g.ev[2], cpst));  // start of the placement copies (timing of the blocking upload)
-    for (int face = 0; face < 6; face++)
-      CK(cudaMemcpy2DAsync(s->container + (size_t)(face * S + L) * pitch + (size_t)L * nch, (size_t)pitch * sizeof(float),
-                           d_pixels + (size_t)face * Fpx * Fpx * nch, (size_t)Fpx * tb, (size_t)Fpx * tb, Fpx, kind, cpst));
+    if (kind == cudaMemcpyDeviceToDevice) {  // one kernel for the six faces
+      CK(eu_launch_cubemap_place(d_pixels, s->container, pitch, nch, Fpx, S, L, cpst));
+      ++*launches;
+    } else {
+      for (int face = 0; face < 6; face++)
+        CK(cudaMemcpy2DAsync(s->container + (size_t)(face * S + L) * pitch + (size_t)L * nch, (size_t)pitch * sizeof(float),
+                             d_pixels + (size_t)face * Fpx * Fpx * nch, (size_t)Fpx * tb, (size_t)Fpx * tb, Fpx, kind, cpst));
+    }
     CK(copies_end());
     int nl = 0;
     CK(eu_launch_cubemap_support(s->container, pitch, nch, Fpx, S, L, R, s->cm.refc_md, s->cm.model_to_px, &nl, st));

@@ -51,6 +51,9 @@ cudaError_t eu_launch_brace(float* core, int stride, int nch, int w, int h, int 
                             int bc1, int spherical, cudaStream_t st);
 cudaError_t eu_launch_cubemap_support(float* ir, int pitch, int nch, int face_px, int section_px, int left, int right,
                                       double refc_md, double model_to_px, int* n_launches, cudaStream_t st);
+// the six faces of a cubemap raster in device memory -> the centres of their sections of the IR (one launch)
+cudaError_t eu_launch_cubemap_place(const float* src, float* ir, int pitch, int nch, int face_px, int section_px, int left,
+                                    cudaStream_t st);
 // alpha of masked / cropped facets (stage.cu): feather the 0/1 plane with the 5-tap binomial along x
 // then y (REFLECT), then expand the raster to `nch` channels and multiply every channel by it
 cudaError_t eu_launch_alpha_apply(const unsigned char* mask, float* tmp_a, float* tmp_b, const float* raw, int native_nch,

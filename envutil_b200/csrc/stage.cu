@@ -598,6 +598,21 @@ __global__ void k_cm_fill_ordered(float* ir, SourceDev S, int L, int R, int F, i
   }
 }
 
+// cubemap_t::load for a raster that is already in device memory (cubemap.h:607-640: the six faces go to the centres
+// of their sections): ONE launch for all six faces instead of six pitched device-to-device copies with a stream
+// drain between them. V = float4 when rows and offsets are 16-byte multiples, else float.
+template <typename V>
+__global__ void __launch_bounds__(256) k_cm_place(const V* __restrict__ src, V* __restrict__ dst, int row_v, int face_px,
+                                                  int section_px, int left_px, int dst_pitch_v, int left_v) {
+  const size_t n = (size_t)6 * face_px * row_v;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / row_v;
+    const int k = (int)(i - r * row_v);
+    const int face = (int)(r / face_px), y = (int)(r - (size_t)face * face_px);
+    dst[((size_t)face * section_px + left_px + y) * dst_pitch_v + left_v + k] = __ldg(src + i);
+  }
+}
+
 // interleaved nch-float texels (rows of src_pitch floats) -> dense 16-byte texels
 __global__ void k_pad_texels(const float* __restrict__ src, int src_pitch, float4* __restrict__ dst, int dst_pitch_texels,
                              int cw, int chh, int nch) {
@@ -786,6 +801,20 @@ cudaError_t eu_launch_pad_texels(const float* src, int src_pitch, float* dst, in
                                  cudaStream_t st) {
   dim3 grid((cw + 255) / 256, chh < 65535 ? chh : 65535);
   k_pad_texels<<<grid, 256, 0, st>>>(src, src_pitch, reinterpret_cast<float4*>(dst), dst_pitch_texels, cw, chh, nch);
+  return cudaGetLastError();
+}
+
+cudaError_t eu_launch_cubemap_place(const float* src, float* ir, int pitch, int nch, int F, int S, int L, cudaStream_t st) {
+  const int rowf = F * nch, leftf = L * nch;
+  const bool vec = !(rowf & 3) && !(leftf & 3) && !(pitch & 3) && !((uintptr_t)src & 15) && !((uintptr_t)ir & 15);
+  const size_t n = (size_t)6 * F * (vec ? rowf / 4 : rowf);
+  const size_t want = (n + 255) / 256;
+  const int blocks = (int)(want < (size_t)148 * 32 ? want : (size_t)148 * 32);
+  if (vec)
+    k_cm_place<float4><<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(ir), rowf / 4, F, S, L,
+                                               pitch / 4, leftf / 4);
+  else
+    k_cm_place<float><<<blocks, 256, 0, st>>>(src, ir, rowf, F, S, L, pitch, leftf);
   return cudaGetLastError();
 }
 
