@@ -976,6 +976,19 @@ def ours_c5(args):
     else:
         dev_checksum = float(pl.d_band[0][::61, ::67].double().sum().item())
     barrier()
+    # ---- beside the timed regions: the SAME pipeline on one GPU of this box (rank 0 renders the whole panorama; the
+    # brackets' containers are not filled - the kernels' work does not depend on the values), so that a line of an N-GPU
+    # run carries its own single-GPU figure for this workload (bench.py --gpus 1 measures configs[1], not configs[4])
+    one_gpu = None
+    if world > 1:
+        if rank == 0:
+            p1 = c5.Pipeline(eng, torch, 0, 1, args.scale, plan=args.c5_plan, contracted=args.arithmetic == "contracted",
+                             synth_inputs=False)
+            ms1 = time_launches(torch, p1.step_device, max(3, min(args.steps, 10)), 3)
+            p1.close()
+            one_gpu = {"ms_per_step": ms1, "value": W * H / 1e6 / (ms1 * 1e-3), "unit": UNIT,
+                       "what": "the whole panorama on rank 0's GPU alone, same code, same plan (device-timed, untimed inputs)"}
+        barrier()
     per_rank = every_rank({"rank": rank, "rows": [pl.row0, pl.row1], "ms": my_ms, "stage_a_ms": a_ms, "stage_b_staging_ms": sb_ms,
                            "stage_b_ms": b_ms, "stage_a_mpix": c5.stage_a_pixels(pl.rects) * c5.POSITIONS / 1e6,
                            "stage_a_alg_bytes": pl.stage_a_alg_bytes(), "h2d_bytes": pl.h2d_bytes, "d2h_bytes": pl.d2h_bytes,
@@ -1030,7 +1043,8 @@ def ours_c5(args):
                           "gather_ms": gather_ms,
                           "gather": "beside the timed regions: NCCL gather of the bands into rank 0's HBM; the e2e path needs none "
                                     "(every rank stores its band into the shared host frame, per_rank[].download_ms)",
-                          "collectives_in_timed_region": 0, "nccl_ranks": world, "per_rank": per_rank,
+                          "collectives_in_timed_region": 0, "nccl_ranks": world, "one_gpu_same_workload": one_gpu,
+                          "per_rank": per_rank,
                           "checksum_device_gather": dev_checksum, "checksum_host_frame": host_checksum,
                           "frame_complete": dev_checksum == host_checksum},
             "cpu_baseline": None, "checksum": host_checksum, "setup_s": setup_s, "run_s": time.perf_counter() - t_run0,

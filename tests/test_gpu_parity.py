@@ -284,6 +284,57 @@ def test_stage_one_renders_into_stage_two_source(engine, degree):
         engine.release(hsa)
 
 
+@pytest.mark.parametrize("degree,source", [(1, "host"), (1, "device"), (3, "host"), (3, "device")])
+def test_write_rect_fills_a_reserved_source(engine, degree, source):
+    """eu_source_write_rect: a reserved source filled piecewise - pitched and contiguous host rectangles, device
+    rectangles, more rectangles than the library's scratch ring has slots, growing sizes - equals the source staged
+    from the whole raster (degree 1: 16-byte texels, the rectangles pass through the scratch ring and the widening
+    kernel; degree 3: 12-byte texels, pitched copies straight into the container)."""
+    import torch
+    from envutil_b200.job import FacetSpec, Job
+    rng = np.random.default_rng(5 + degree)
+    w, h = 203, 97
+    img = rng.uniform(0.0, 1.0, size=(h, w, 3)).astype(np.float32)
+    job = Job([FacetSpec(img, "rectilinear", 70.0, yaw=10.0)], "spherical", 360.0, 128, 64, degree=degree)
+    st = job.structs(engine.lib)
+    fa, o = st[1], st[2]
+    whole = engine.stage(job, st)
+    hnd, core, pitch = engine.reserve(fa[0], o)
+    stream = torch.cuda.current_stream().cuda_stream
+    keep = []
+    try:
+        assert engine.texel_floats[hnd.value] == (4 if degree == 1 else 3)
+        # a ragged tiling: column strips of different widths, each cut into bands of growing height
+        cols = [0, 1, 40, 41, 130, w]
+        for c0, c1 in zip(cols[:-1], cols[1:]):
+            r0, step = 0, 3
+            while r0 < h:
+                r1 = min(h, r0 + step)
+                step += 7
+                if (r0 // 3 + c0) % 2:  # pitched: a view into the whole raster
+                    sub = torch.from_numpy(img).pin_memory()
+                    if source == "device":
+                        sub = sub.cuda()
+                    ptr = sub.data_ptr() + (r0 * w + c0) * 3 * 4
+                    keep.append(sub)
+                    engine.write_rect(hnd, ptr, w * 3, r0, r1, c0, c1, stream)
+                else:  # contiguous: its own buffer
+                    sub = torch.from_numpy(np.ascontiguousarray(img[r0:r1, c0:c1])).pin_memory()
+                    if source == "device":
+                        sub = sub.cuda()
+                    keep.append(sub)
+                    engine.write_rect(hnd, sub.data_ptr(), (c1 - c0) * 3, r0, r1, c0, c1, stream)
+                r0 = r1
+        engine.commit(hnd, fa[0], o, stream)
+        got, shp = engine.container(hnd)
+        want, wshp = engine.container(whole[0])
+        assert shp == wshp
+        assert np.array_equal(got, want)
+    finally:
+        engine.release([hnd])
+        engine.release(whole)
+
+
 def test_edge_jobs():
     """Degenerate sizes (one-pixel and ragged targets, sources smaller than a spline window, single rows and
     columns, 4-px cube faces): the oracle equals the reference on them (golden); the kernels equal the oracle,
