@@ -976,18 +976,18 @@ def ours_c5(args):
     else:
         dev_checksum = float(pl.d_band[0][::61, ::67].double().sum().item())
     barrier()
-    # ---- beside the timed regions: the SAME pipeline on one GPU of this box (rank 0 renders the whole panorama; the
-    # brackets' containers are not filled - the kernels' work does not depend on the values), so that a line of an N-GPU
-    # run carries its own single-GPU figure for this workload (bench.py --gpus 1 measures configs[1], not configs[4])
+    # ---- beside the timed regions: the SAME pipeline on one GPU of this box (rank 0 renders the whole panorama from the
+    # whole brackets), so that a line of an N-GPU run carries its own single-GPU figure for this workload
+    # (bench.py --gpus 1 measures configs[1], not configs[4])
     one_gpu = None
     if world > 1:
         if rank == 0:
-            p1 = c5.Pipeline(eng, torch, 0, 1, args.scale, plan=args.c5_plan, contracted=args.arithmetic == "contracted",
-                             synth_inputs=False)
+            p1 = c5.Pipeline(eng, torch, 0, 1, args.scale, plan=args.c5_plan, contracted=args.arithmetic == "contracted")
+            p1.upload()
             ms1 = time_launches(torch, p1.step_device, max(3, min(args.steps, 10)), 3)
             p1.close()
             one_gpu = {"ms_per_step": ms1, "value": W * H / 1e6 / (ms1 * 1e-3), "unit": UNIT,
-                       "what": "the whole panorama on rank 0's GPU alone, same code, same plan (device-timed, untimed inputs)"}
+                       "what": "the whole panorama on rank 0's GPU alone, same code, same plan, brackets resident (device-timed)"}
         barrier()
     per_rank = every_rank({"rank": rank, "rows": [pl.row0, pl.row1], "ms": my_ms, "stage_a_ms": a_ms, "stage_b_staging_ms": sb_ms,
                            "stage_b_ms": b_ms, "stage_a_mpix": c5.stage_a_pixels(pl.rects) * c5.POSITIONS / 1e6,
