@@ -208,6 +208,12 @@ def _build():
     add("maskfor0_cm_sph_d1", Job([FacetSpec(_cm(32), "cubemap", 90.0)], "spherical", 360.0, 96, 48, mask_for=0))
     add("maskfor1_hdr3_rect_d1", Job(_bracket_facets(), "rectilinear", 70.0, 96, 64, yaw=20.0, synopsis="hdr_merge",
                                      mask_for=1))
+    # --- --nchannels on ordinary jobs: repix_t in both directions (environment.h:1205-1309) ---
+    add("nch1_voronoi4_sph_d1", Job(_voronoi_facets(), "spherical", 360.0, 192, 96, out_channels=1))
+    add("nch4_grey_ll_rect_d3", Job([FacetSpec(_grey(_ll(128)), "spherical", 360.0)], "rectilinear", 90.0, 64, 36, degree=3,
+                                    out_channels=4, **ROT))
+    add("nch3_rgba1_rect_d1_tw2", Job(rgba[:1], "rectilinear", 90.0, 96, 64, yaw=-100.0, twine=2, out_channels=3))
+    add("nch2_hdr3_rect_d1", Job(_bracket_facets(), "rectilinear", 70.0, 96, 64, yaw=20.0, synopsis="hdr_merge", out_channels=2))
     # --- automatic twining (--twine omitted = -1): arguments::twine_setup picks the filter from the
     # magnification (envutil_main.cc:1450-1547) -------------------------------------------------
     add("auto_tw_down_ll_rect_d1", Job([_ll_facet(256)], "rectilinear", 100.0, 48, 32, twine=-1))          # mag < 1

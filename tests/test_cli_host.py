@@ -190,7 +190,8 @@ def test_pto_back_references(cli, tmp_path):
                                   "single2_voronoi4_d3_tw2", "single0_cm_ll", "single0_lens3_d1",
                                   "single1_lens3_d3_tw2", "single1_tr3_d1_tw2", "single1_tr_lens_d1", "cropout_ll_sph_d1",
                                   "cropout_ll_rect_d3_tw2", "cropout_ll_cyl_d1_tw2", "cropout_voronoi4_fish_d1",
-                                  "maskfor2_voronoi4_grey_d3_tw2", "maskfor3_rgba4_ga_rect_d1", "maskfor1_mixed_rgb_rgba_d1"])
+                                  "maskfor2_voronoi4_grey_d3_tw2", "maskfor3_rgba4_ga_rect_d1", "maskfor1_mixed_rgb_rgba_d1",
+                                  "nch1_voronoi4_sph_d1", "nch4_grey_ll_rect_d3", "nch3_rgba1_rect_d1_tw2"])
 def test_cli_output_equals_reference_output(cli, tmp_path, name):
     """The drop-in claim end to end: the SAME command line given to the reference binary and to
     envutil_b200_cli produces the same file, bit for bit (golden sha256 of the reference run)."""

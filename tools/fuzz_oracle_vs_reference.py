@@ -125,6 +125,8 @@ def random_job(rng):
         kw["mask_for"] = int(rng.integers(0, nf))
         if rng.random() < .5:
             kw["out_channels"] = int(rng.choice([1, 2]))
+    if "mask_for" not in kw and "single" not in kw and rng.random() < .08:  # --nchannels on an ordinary job: repix_t both ways
+        kw["out_channels"] = int(rng.integers(1, 5))
     return Job(facets, trg, hfov, width, height, **kw)
 
 
