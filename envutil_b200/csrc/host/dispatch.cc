@@ -168,10 +168,10 @@ int core(int argc, const char** argv) {
            args.twine, ninp, args.synopsis.c_str(), args.solo);
     for (const auto& f : args.facet_spec_v)
       printf("facet %d %s %s %dx%dx%d hfov %.17g ypr %.17g %.17g %.17g step %.17g brighten %.9g lcp %d shift %.17g %.17g "
-             "shear %.17g %.17g\n",
+             "shear %.17g %.17g masked %d\n",
              f.facet_no, f.filename.c_str(), projection_name[f.f.projection], f.f.width, f.f.height, f.f.nchannels,
              f.f.hfov, f.f.yaw, f.f.pitch, f.f.roll, f.f.step, f.brighten, f.f.has_lcp, f.f.shift_h, f.f.shift_v,
-             f.f.shear_g, f.f.shear_t);
+             f.f.shear_g, f.f.shear_t, f.f.masked);
     for (const auto& c : args.twine_spread) printf("tap %.9g %.9g %.9g\n", c.x, c.y, c.w);
     return 0;
   }

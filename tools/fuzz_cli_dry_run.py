@@ -50,8 +50,8 @@ def check(job, d):
             r.returncode, ok_py, r.stderr.strip()[:120])
     lines = r.stdout.splitlines()
     tl = [l for l in lines if l.startswith("target ")][0]
-    if "%dx%d" % (t.width, t.height) not in tl:
-        return "target size: " + tl
+    if "%dx%d nch %d " % (t.width, t.height, t.nchannels) not in tl:
+        return "target size / channels: " + tl
     if [floats(tl, k)[0] for k in ("hfov", "yaw", "pitch", "roll")] != [t.hfov, t.yaw, t.pitch, t.roll]:
         return "target angles: " + tl
     el = [l for l in lines if l.startswith("extent ")][0]
@@ -63,7 +63,8 @@ def check(job, d):
     for i, l in enumerate(fl):
         if (floats(l, "hfov")[0] != fa[i].hfov or floats(l, "ypr") != [fa[i].yaw, fa[i].pitch, fa[i].roll]
                 or floats(l, " step")[0] != fa[i].step or np.float32(floats(l, "brighten")[0]) != np.float32(fa[i].brighten)
-                or floats(l, "shift") != [fa[i].shift_h, fa[i].shift_v] or floats(l, "shear") != [fa[i].shear_g, fa[i].shear_t]):
+                or floats(l, "shift") != [fa[i].shift_h, fa[i].shift_v] or floats(l, "shear") != [fa[i].shear_g, fa[i].shear_t]
+                or int(l.rsplit("masked ", 1)[1]) != fa[i].masked):
             return "facet %d: %s" % (i, l[:200])
     tp = [l for l in lines if l.startswith("tap ")]
     if len(tp) != ntaps:
