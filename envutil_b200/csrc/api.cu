@@ -1407,7 +1407,7 @@ int eu_job_wait(eu_job_h job, eu_timing_t* timing) {
 }
 
 // ---- tethered output (to_screen_t, envutil_payload.cc:298-413) --------------------------------------
-static int screen_lut_ready(cudaStream_t st) {
+static int screen_lut_ready() {
   if (g.d_screen_lut) return EU_OK;
   float lut[257];
   eu_screen_lut(lut);
@@ -1416,7 +1416,6 @@ static int screen_lut_ready(cudaStream_t st) {
   // for whichever stream reads it first (a pageable copy this small may return before its DMA has finished)
   CK(cudaMemcpy(g.d_screen_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
   CK(cudaDeviceSynchronize());
-  (void)st;
   return EU_OK;
 }
 
@@ -1427,7 +1426,7 @@ int eu_to_screen_device(const float* d_pixels, int nchannels, size_t n_pixels, u
   if (nchannels < 1 || nchannels > 4) return fail(EU_ERR_ARGUMENT, "%d channels", nchannels);
   if ((nchannels == 4 && (reinterpret_cast<uintptr_t>(d_pixels) & 15)) || (nchannels == 2 && (reinterpret_cast<uintptr_t>(d_pixels) & 7)))
     return fail(EU_ERR_ARGUMENT, "pixels of %d channels must be %d-byte aligned", nchannels, nchannels * 4);
-  rc = screen_lut_ready((cudaStream_t)cuda_stream);
+  rc = screen_lut_ready();
   if (rc) return rc;
   CK(eu_launch_to_screen(d_pixels, nchannels, n_pixels, g.d_screen_lut, d_out, (cudaStream_t)cuda_stream));
   return EU_OK;
@@ -1444,7 +1443,7 @@ int eu_render_screen(const eu_target_t* t, const eu_opts_t* o, int n_facets, con
   if (rc) return rc;
   rc = grow(g.d_index, g.index_cap, npx);
   if (rc) return rc;
-  rc = screen_lut_ready(g.stream);
+  rc = screen_lut_ready();
   if (rc) return rc;
   eu_target_t tt = *t;
   tt.gain = 0.0;  // work() skips the un-brighten stage when it runs tethered (envutil_payload.cc:491)
