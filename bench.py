@@ -982,12 +982,15 @@ def ours_c5(args):
     one_gpu = None
     if world > 1:
         if rank == 0:
-            p1 = c5.Pipeline(eng, torch, 0, 1, args.scale, plan=args.c5_plan, contracted=args.arithmetic == "contracted")
-            p1.upload()
-            ms1 = time_launches(torch, p1.step_device, max(3, min(args.steps, 10)), 3)
-            p1.close()
-            one_gpu = {"ms_per_step": ms1, "value": W * H / 1e6 / (ms1 * 1e-3), "unit": UNIT,
-                       "what": "the whole panorama on rank 0's GPU alone, same code, same plan, brackets resident (device-timed)"}
+            try:  # an extra beside the measurement: never at the price of the line (or of the ranks waiting at the barrier)
+                p1 = c5.Pipeline(eng, torch, 0, 1, args.scale, plan=args.c5_plan, contracted=args.arithmetic == "contracted")
+                p1.upload()
+                ms1 = time_launches(torch, p1.step_device, max(3, min(args.steps, 10)), 3)
+                p1.close()
+                one_gpu = {"ms_per_step": ms1, "value": W * H / 1e6 / (ms1 * 1e-3), "unit": UNIT,
+                           "what": "the whole panorama on rank 0's GPU alone, same code, same plan, brackets resident (device-timed)"}
+            except Exception as e:  # noqa: BLE001
+                one_gpu = {"error": "%s: %s" % (type(e).__name__, e)}
         barrier()
     per_rank = every_rank({"rank": rank, "rows": [pl.row0, pl.row1], "ms": my_ms, "stage_a_ms": a_ms, "stage_b_staging_ms": sb_ms,
                            "stage_b_ms": b_ms, "stage_a_mpix": c5.stage_a_pixels(pl.rects) * c5.POSITIONS / 1e6,
