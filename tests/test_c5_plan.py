@@ -88,6 +88,22 @@ def test_cost_bands_are_balanced():
         assert max(per) < 1.1 * (sum(per) / world)
 
 
+def test_transfer_bytes_per_rank_are_even_at_eight_ranks():
+    """bands sized by device cost also spread the PCIe traffic - the polar ranks download most and
+    upload next to nothing - so a rank's H2D + D2H bytes stay within 469 ... 594 MB of the 544 MB mean at N = 8, and the
+    rectangles of all ranks together are 0.529 of the rasters."""
+    (w, h), (W, H) = c5.sizes(1)
+    bands = c5.plan_bands(8, 1)
+    sums, merged = [], 0
+    for r0, r1 in bands:
+        rects = c5.rects_for_band(r0, r1, w, h, H)
+        h2d = c5.stage_a_pixels(rects) * c5.POSITIONS * c5.BRACKETS * 12
+        merged += c5.stage_a_pixels(rects)
+        sums.append(h2d + (r1 - r0) * W * 12)
+    assert 460e6 < min(sums) and max(sums) < 600e6
+    assert abs(merged / (w * h) - 0.529) < 0.01
+
+
 def test_windowed_synthesis_equals_the_whole_raster():
     from envutil_b200 import synth, workloads
     fs = workloads.c5_facets(scale=20, positions=2)
